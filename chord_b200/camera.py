@@ -1,0 +1,171 @@
+"""Host mirror of the reference camera / per-view uniform fill.
+
+Follows source/utils/camera.cpp:17-154 (ICamera::fillViewUniformParameter, computeRelativeWorldFrustum),
+source/utils/utils.cpp:186-198 (infiniteInvertZPerspectiveRH_ZO), application/flower/widget/viewport.cpp:435-445
+(relative lookAt view, projection), source/renderer/renderer.cpp:175-263 (PerframeCameraView /
+InstanceCullingViewInfo fill, last-frame hand-off) and source/scene/scene_node.cpp:42-90 (object data).
+Math-convention 4x4 matrices (M @ v) in numpy float32; the dtype fields store them column-major (``M.T``).
+"""
+import math
+
+import numpy as np
+
+from . import abi
+
+F = np.float32
+
+
+def infinite_invert_z_perspective_rh_zo(aspect, fovy, z_near):
+    """utils.cpp:186-198.  Returns math-convention M (clip = M @ view)."""
+    t = F(math.tan(F(fovy) * F(0.5)))
+    m = np.zeros((4, 4), dtype=F)
+    m[0, 0] = F(1.0) / (F(aspect) * t)
+    m[1, 1] = F(1.0) / t
+    m[3, 2] = F(-1.0)          # glm result[2][3] = -1  -> row 3, col 2
+    m[2, 3] = F(z_near)        # glm result[3][2] = zNear -> row 2, col 3
+    return m
+
+
+def perspective_rh_zo(fovy, aspect, z_near, z_far):
+    """glm::perspectiveRH_ZO (called with near/far swapped by the reference for reversed z)."""
+    t = F(math.tan(F(fovy) / F(2.0)))
+    m = np.zeros((4, 4), dtype=F)
+    m[0, 0] = F(1.0) / (F(aspect) * t)
+    m[1, 1] = F(1.0) / t
+    m[2, 2] = F(z_far) / (F(z_near) - F(z_far))
+    m[3, 2] = F(-1.0)
+    m[2, 3] = -(F(z_far) * F(z_near)) / (F(z_far) - F(z_near))
+    return m
+
+
+def _normalize(v):
+    v = np.asarray(v, dtype=F)
+    return v / F(np.sqrt(np.dot(v, v)))
+
+
+def look_at_rh(eye, center, up):
+    """glm::lookAtRH."""
+    f = _normalize(np.asarray(center, dtype=F) - np.asarray(eye, dtype=F))
+    s = _normalize(np.cross(f, np.asarray(up, dtype=F)))
+    u = np.cross(s, f)
+    m = np.eye(4, dtype=F)
+    m[0, :3], m[1, :3], m[2, :3] = s, u, -f
+    m[0, 3], m[1, 3], m[2, 3] = -np.dot(s, eye), -np.dot(u, eye), np.dot(f, eye)
+    return m.astype(F)
+
+
+class Camera:
+    """ViewportCamera stand-in: double-precision world position, relative (camera at origin) view."""
+
+    def __init__(self, position, front, up=(0.0, 1.0, 0.0), fovy=math.radians(45.0), z_near=0.001, z_far=20000.0,
+                 width=1920, height=1080):
+        self.position = np.asarray(position, dtype=np.float64)
+        self.front = _normalize(front)
+        self.right = _normalize(np.cross(self.front, np.asarray(up, dtype=F)))
+        self.up = _normalize(np.cross(self.right, self.front))
+        self.fovy, self.z_near, self.z_far = float(fovy), float(z_near), float(z_far)
+        self.width, self.height = int(width), int(height)
+
+    @property
+    def aspect(self):
+        return F(self.width) / F(self.height)
+
+    def view_matrix(self):
+        return look_at_rh(np.zeros(3, dtype=F), self.front, self.up)
+
+    def project_matrix(self):
+        return infinite_invert_z_perspective_rh_zo(self.aspect, self.fovy, self.z_near)
+
+    def frustum_planes(self):
+        """camera.cpp:80-154 computeRelativeWorldFrustum, order left, down, right, top, front, back."""
+        fwd, up, right = self.front, self.up, self.right
+        t = F(math.tan(F(self.fovy) * F(0.5)))
+        near_c, far_c = fwd * F(self.z_near), fwd * F(self.z_far)
+        yn, yf = F(self.z_near) * t, F(self.z_far) * t
+        ynv, xnv = yn * up, yn * self.aspect * right
+        yfv, xfv = yf * up, yf * self.aspect * right
+        nrt, nrd, nlt, nld = near_c + xnv + ynv, near_c + xnv - ynv, near_c - xnv + ynv, near_c - xnv - ynv
+        frt, frd, flt, fld = far_c + xfv + yfv, far_c + xfv - yfv, far_c - xfv + yfv, far_c - xfv - yfv
+
+        def plane(pc, p1, p2):
+            n = _normalize(np.cross(p1 - pc, p2 - pc))
+            return np.array([n[0], n[1], n[2], -np.dot(n, pc)], dtype=F)
+
+        return np.stack([plane(fld, flt, nld), plane(frd, fld, nrd), plane(frt, frd, nrt),
+                         plane(flt, frt, nlt), plane(nrt, nrd, nlt), plane(frt, flt, frd)]).astype(F)
+
+
+def fill_view(camera, jitter=(0.0, 0.0), last_view=None, frame_counter=0, sun_direction=(0.3, -0.8, 0.2)):
+    """PerframeCameraView record (camera.cpp:17-78 + renderer.cpp:175-211)."""
+    v = np.zeros((), dtype=abi.PerframeCameraView)
+    W, H = camera.width, camera.height
+    v['renderDimension'] = [W, H, F(1.0) / F(W), F(1.0) / F(H)]
+    v['jitterData'][:2] = jitter
+    rel_view = camera.view_matrix()
+    proj = camera.project_matrix()
+    v['translatedWorldToView'] = rel_view.T
+    v['viewToTranslatedWorld'] = np.linalg.inv(rel_view.astype(np.float64)).astype(F).T
+    v['translatedWorldToClip_NoJitter'] = (proj @ rel_view).astype(F).T
+    proj_zfar = perspective_rh_zo(camera.fovy, camera.aspect, camera.z_far, camera.z_near)
+    v['clipToTranslatedWorldWithZFar_NoJitter'] = np.linalg.inv((proj_zfar @ rel_view).astype(np.float64)).astype(F).T
+    jm = np.eye(4, dtype=F)
+    jm[0, 3] += F(2.0) * F(jitter[0]) / F(W)
+    jm[1, 3] += F(-2.0) * F(jitter[1]) / F(H)
+    pj = (jm @ proj).astype(F)
+    v['viewToClip'] = pj.T
+    v['clipToView'] = np.linalg.inv(pj.astype(np.float64)).astype(F).T
+    w2c = (pj @ rel_view).astype(F)
+    v['translatedWorldToClip'] = w2c.T
+    v['clipToTranslatedWorld'] = np.linalg.inv(w2c.astype(np.float64)).astype(F).T
+    v['frustumPlane'] = camera.frustum_planes()
+    # kilometre-space camera (manager_atmosphere: earth centre below the origin)
+    cam_km = camera.position / 1000.0
+    earth_center_km = np.array([0.0, -6360.0, 0.0])
+    v['cameraPositionWS_km'] = abi.double3_to_storage(cam_km)
+    v['cameraToEarthCenter_km'] = abi.double3_to_storage(cam_km - earth_center_km)
+    v['cameraFovy'], v['zNear'], v['zFar'] = camera.fovy, camera.z_near, camera.z_far
+    v['cameraWorldPos'] = abi.double3_to_storage(camera.position)
+    v['forwardRS'] = (np.linalg.inv(rel_view.astype(np.float64)) @ np.array([0, 0, -1, 0.0]))[:3].astype(F)
+    bd = v['basicData']
+    bd['frameCounter'] = frame_counter
+    bd['frameCounterMod8'] = frame_counter % 8
+    bd['sunInfo']['direction'] = _normalize(sun_direction)
+    bd['atmosphere']['earthCenterKm'] = earth_center_km
+    if last_view is None:
+        last_view = v
+        v['bCameraCut'] = 1
+    v['translatedWorldToClipLastFrame'] = last_view['translatedWorldToClip']
+    v['translatedWorldToClipLastFrame_NoJitter'] = last_view['translatedWorldToClip_NoJitter']
+    v['clipToTranslatedWorld_LastFrame'] = last_view['clipToTranslatedWorld']
+    v['jitterData'][2:] = last_view['jitterData'][:2]
+    v['cameraWorldPosLastFrame'] = last_view['cameraWorldPos']
+    v['frustumPlaneLastFrame'] = last_view['frustumPlane']
+    return v
+
+
+def fill_instance_view(view):
+    """renderer.cpp:252-263 main-view InstanceCullingViewInfo."""
+    iv = np.zeros((), dtype=abi.InstanceCullingViewInfo)
+    iv['frustumPlanesRS'] = view['frustumPlane']
+    iv['translatedWorldToClip'] = view['translatedWorldToClip']
+    iv['clipToTranslatedWorld'] = np.linalg.inv(view['translatedWorldToClip'].T.astype(np.float64)).astype(F).T
+    iv['cameraWorldPos'] = view['cameraWorldPos']
+    iv['renderDimension'] = view['renderDimension']
+    return iv
+
+
+def fill_object(local_to_world, camera, primitive_detail, material, local_to_world_last=None, camera_last=None):
+    """scene_node.cpp:42-90 getObjectBasicData + component_gltf_mesh.cpp:58-122."""
+    o = np.zeros((), dtype=abi.GPUObjectGLTFPrimitive)
+    m = np.array(local_to_world, dtype=np.float64)
+    m[:3, 3] -= camera.position
+    mf = m.astype(F)
+    o['localToTranslatedWorld'] = mf.T
+    o['translatedWorldToLocal'] = np.linalg.inv(mf.astype(np.float64)).astype(F).T
+    s = np.array([np.linalg.norm(mf[:3, 0]), np.linalg.norm(mf[:3, 1]), np.linalg.norm(mf[:3, 2])], dtype=F)
+    o['scaleExtractFromMatrix'] = [s[0], s[1], s[2], np.abs(s).max()]
+    ml = np.array(local_to_world if local_to_world_last is None else local_to_world_last, dtype=np.float64)
+    ml[:3, 3] -= (camera if camera_last is None else camera_last).position
+    o['localToTranslatedWorldLastFrame'] = ml.astype(F).T
+    o['GLTFPrimitiveDetail'], o['GLTFMaterialData'] = primitive_detail, material
+    return o

@@ -1,0 +1,367 @@
+"""Seeded synthetic scenes in chord's GPU asset layout (S1, S5, S2/S3 stand-ins).
+
+The layout follows the reference's asset packing: per meshlet ``[vertex remap u32 x V][tri (i0|i1<<8|i2<<16) u32 x T]``
+appended to ``meshletData`` with ``dataOffset`` in u32 units (source/asset/gltf/asset_gltf_helper.cpp:522-548),
+separate tightly packed position / normal / uv / tangent arrays (:572-584), cluster groups of <= 4 meshlets with
+(error, parentError) spheres (source/asset/nanite_builder.cpp:851-868; LOD-0 error = -1, root parentError = FLT_MAX,
+:420, :891).  Real Sponza/Bistro assets are not available offline, so S2/S3 are procedural "cities".
+"""
+import math
+
+import numpy as np
+
+from . import abi, camera as cam
+
+F = np.float32
+FLT_MAX = np.finfo(np.float32).max
+
+
+def _patch_topology(q=8):
+    """(q+1)^2 vertices, 2*q*q triangles, CCW when seen from +normal (u x v). Returns packed u32 tris."""
+    n = q + 1
+    tris = []
+    for j in range(q):
+        for i in range(q):
+            a, b, c, d = j * n + i, j * n + i + 1, (j + 1) * n + i, (j + 1) * n + i + 1
+            tris.append((a, b, d))
+            tris.append((a, d, c))
+    t = np.array(tris, dtype=np.uint32)
+    return (t[:, 0] | (t[:, 1] << 8) | (t[:, 2] << 16)).astype(np.uint32)
+
+
+def default_material(two_sided=0, alpha_mode=0, material_type=abi.LIGHTING_TYPE_GLTF_PBR, base_color=(0.8, 0.8, 0.8, 1.0),
+                     metallic=0.0, roughness=0.5, alpha_cutoff=0.5):
+    """Untextured material as the reference fills it (source/asset/gltf/asset_gltf.cpp:295-358)."""
+    m = np.zeros((), dtype=abi.GLTFMaterialGPUData)
+    m['alphaMode'], m['alphaCutOff'], m['bTwoSided'] = alpha_mode, alpha_cutoff, two_sided
+    m['baseColorId'] = 0                      # builtin white
+    m['baseColorFactor'] = base_color
+    m['emissiveFactor'] = (0, 0, 0)
+    m['emissiveTexture'] = 0                  # builtin transparent
+    m['metallicFactor'], m['roughnessFactor'] = metallic, roughness
+    m['metallicRoughnessTexture'] = abi.UNVALID_ID
+    m['normalTexture'] = abi.UNVALID_ID
+    m['normalFactorScale'] = 1.0
+    m['occlusionTextureStrength'] = 1.0
+    m['materialType'] = material_type
+    return m
+
+
+def _meshlet_records(pos_by_meshlet, data_offsets, V, T, lod, normal):
+    """Bounds / cone for meshlets given their vertex positions (M, V, 3)."""
+    M = pos_by_meshlet.shape[0]
+    ms = np.zeros(M, dtype=abi.GPUGLTFMeshlet)
+    ms['posMin'] = pos_by_meshlet.min(axis=1)
+    ms['posMax'] = pos_by_meshlet.max(axis=1)
+    ms['dataOffset'] = data_offsets
+    ms['vertexTriangleCount'] = abi.pack_vertex_triangle_count(V, T)
+    ms['coneAxis'] = normal
+    ms['coneCutOff'] = 0.0
+    ms['coneApex'] = pos_by_meshlet.mean(axis=1)
+    ms['lod'] = lod
+    return ms
+
+
+def single_meshlet_scene(width=256, height=256, seed=1):
+    """S1: one 9x9-vertex grid meshlet (128 tri), plane + seeded +-5% z jitter, identity object matrix,
+    camera fovy 45deg looking down -Z so the patch covers ~60% of the viewport."""
+    rng = np.random.default_rng(seed)
+    q = 8
+    dist = 2.0
+    half = dist * math.tan(math.radians(22.5)) * 0.78
+    g = np.linspace(-half, half, q + 1, dtype=F)
+    xx, yy = np.meshgrid(g, g)
+    zz = (-dist + (rng.random((q + 1, q + 1)) - 0.5) * 0.1 * half).astype(F)
+    pos = np.stack([xx, yy, zz], axis=-1).reshape(-1, 3).astype(F)
+    V, T = (q + 1) ** 2, 2 * q * q
+    data = np.concatenate([np.arange(V, dtype=np.uint32), _patch_topology(q)])
+    meshlets = _meshlet_records(pos[None], np.array([0], dtype=np.uint32), V, T, 0, (0, 0, 1))
+    groups = np.zeros(1, dtype=abi.GPUGLTFMeshletGroup)
+    groups['clusterPosCenter'] = pos.mean(axis=0)
+    groups['parentPosCenter'] = pos.mean(axis=0)
+    groups['error'], groups['parentError'] = -1.0, FLT_MAX
+    groups['meshletOffset'], groups['meshletCount'] = 0, 1
+    normals = np.tile(np.array([0, 0, 1], dtype=F), (V, 1))
+    uv = np.stack([(xx / (2 * half) + 0.5), (yy / (2 * half) + 0.5)], axis=-1).reshape(-1, 2).astype(F)
+    tang = np.tile(np.array([1, 0, 0, 1], dtype=F), (V, 1))
+    prim = np.zeros(1, dtype=abi.GLTFPrimitiveBuffer)
+    prim['posMin'], prim['posMax'], prim['posAverage'] = pos.min(axis=0), pos.max(axis=0), pos.mean(axis=0)
+    prim['vertexCount'], prim['meshletGroupCount'] = V, 1
+    scene = abi.HostScene([dict(meshlets=meshlets, positions=pos, normals=normals, uv0=uv, tangents=tang,
+                                meshletData=data, groups=groups, groupIndices=np.zeros(1, dtype=np.uint32))],
+                          prim, np.array([default_material()]))
+    camera = cam.Camera((0, 0, 0), (0, 0, -1), width=width, height=height)
+    objects = np.array([cam.fill_object(np.eye(4), camera, 0, 0)])
+    return scene, camera, objects
+
+
+def patch_stream_scene(n_meshlets, width=3840, height=2160, seed=5, area_range=(0.5, 1.5), depth_range=(1.0, 100.0),
+                       overdraw_scale=1.0):
+    """S5: ``n_meshlets`` camera-facing 8x8-quad patches (V=81, T=128) whose projected triangle area is uniform in
+    ``area_range`` px^2, patch centres uniform over the viewport, depth uniform in ``depth_range`` metres; one
+    opaque one-sided object, identity matrix, camera at the origin looking down -Z."""
+    rng = np.random.default_rng(seed)
+    q, V, T = 8, 81, 128
+    fovy = math.radians(45.0)
+    tan_half = math.tan(fovy * 0.5)
+    M = int(n_meshlets)
+    depth = rng.uniform(depth_range[0], depth_range[1], M)
+    area = rng.uniform(area_range[0], area_range[1], M) * overdraw_scale
+    side_px = np.sqrt(2.0 * area)                       # quad side in pixels
+    px_world = 2.0 * depth * tan_half / height          # world units per pixel at that depth
+    cx = rng.uniform(0, width, M)
+    cy = rng.uniform(0, height, M)
+    ang = rng.uniform(0, 2 * math.pi, M)
+    # patch-local grid, rotated in the view plane
+    g = (np.arange(q + 1) - q / 2.0)
+    gx, gy = np.meshgrid(g, g)                           # (9, 9)
+    gx, gy = gx.reshape(-1), gy.reshape(-1)
+    ca, sa = np.cos(ang)[:, None], np.sin(ang)[:, None]
+    ox = (gx[None] * ca - gy[None] * sa) * side_px[:, None]   # pixels
+    oy = (gx[None] * sa + gy[None] * ca) * side_px[:, None]
+    sx = cx[:, None] + ox
+    sy = cy[:, None] + oy
+    wx = (sx - width / 2.0) * px_world[:, None]
+    wy = -(sy - height / 2.0) * px_world[:, None]
+    wz = -depth[:, None] + (rng.random((M, V)) - 0.5) * 0.05 * (side_px * px_world)[:, None]
+    pos = np.stack([wx, wy, np.broadcast_to(wz, wx.shape)], axis=-1).astype(F)       # (M, V, 3)
+    # the patch was built with screen-y down; flip winding so the camera-facing side is CCW in y-up NDC
+    topo = _patch_topology(q)
+    i0, i1, i2 = topo & 0xFF, (topo >> 8) & 0xFF, (topo >> 16) & 0xFF
+    topo = (i0 | (i2 << 8) | (i1 << 16)).astype(np.uint32)
+    stride = V + T
+    data = np.empty((M, stride), dtype=np.uint32)
+    data[:, :V] = (np.arange(M, dtype=np.uint32)[:, None] * V + np.arange(V, dtype=np.uint32)[None])
+    data[:, V:] = topo[None]
+    offsets = (np.arange(M, dtype=np.uint64) * stride).astype(np.uint32)
+    meshlets = _meshlet_records(pos, offsets, V, T, 0, (0, 0, 1))
+    G = (M + 3) // 4
+    groups = np.zeros(G, dtype=abi.GPUGLTFMeshletGroup)
+    groups['error'], groups['parentError'] = -1.0, FLT_MAX
+    groups['meshletOffset'] = np.arange(G, dtype=np.uint32) * 4
+    groups['meshletCount'] = np.minimum(4, M - np.arange(G) * 4)
+    centers = pos.mean(axis=1)
+    groups['clusterPosCenter'] = centers[::4][:G]
+    groups['parentPosCenter'] = centers[::4][:G]
+    flat = pos.reshape(-1, 3)
+    prim = np.zeros(1, dtype=abi.GLTFPrimitiveBuffer)
+    prim['posMin'], prim['posMax'], prim['posAverage'] = flat.min(axis=0), flat.max(axis=0), flat.mean(axis=0)
+    prim['vertexCount'], prim['meshletGroupCount'] = len(flat), G
+    scene = abi.HostScene([dict(meshlets=meshlets, positions=flat, meshletData=data.reshape(-1), groups=groups,
+                                groupIndices=np.arange(M, dtype=np.uint32))],
+                          prim, np.array([default_material()]))
+    camera = cam.Camera((0, 0, 0), (0, 0, -1), fovy=fovy, width=width, height=height)
+    objects = np.array([cam.fill_object(np.eye(4), camera, 0, 0)])
+    cmds = np.zeros(M, dtype=abi.DrawCmd)
+    cmds['meshletId'] = np.arange(M, dtype=np.uint32)
+    cmds['slot'] = np.arange(M, dtype=np.uint32)
+    return scene, camera, objects, cmds
+
+
+# ----------------------------------------------------------------------------------------------- city (S2/S3)
+def _face_lod_chain(origin, du, dv, patches, normal, vert_base, data_base, meshlet_base, lods):
+    """One planar face of ``patches x patches`` LOD-0 patches (8x8 quads each) with a quadtree LOD chain.
+
+    Returns dict of arrays to append: positions/normals/uv/tangents, meshletData, meshlets, and a list of group
+    tuples (lod, meshlet indices (local to the primitive), centre, radius-ish error, parent info)."""
+    q = 8
+    out_pos, out_nrm, out_uv, out_tan, out_data, out_meshlets = [], [], [], [], [], []
+    groups = []     # (meshlet_ids, own_center, own_error, parent_center, parent_error)
+    topo = _patch_topology(q)
+    origin, du, dv, normal = (np.asarray(a, dtype=np.float64) for a in (origin, du, dv, normal))
+    tangent = du / np.linalg.norm(du)
+    level_ids = []
+    vcount, dcount, mcount = 0, 0, 0
+    p = patches
+    lod = 0
+    face_len = max(np.linalg.norm(du), np.linalg.norm(dv))
+    while True:
+        n = p * q + 1
+        s = np.linspace(0.0, 1.0, n)
+        uu, vv = np.meshgrid(s, s)
+        pos = (origin[None, None] + uu[..., None] * du[None, None] + vv[..., None] * dv[None, None]).reshape(-1, 3)
+        out_pos.append(pos.astype(F))
+        out_nrm.append(np.tile(normal.astype(F), (n * n, 1)))
+        out_uv.append(np.stack([uu, vv], axis=-1).reshape(-1, 2).astype(F))
+        out_tan.append(np.tile(np.append(tangent, 1.0).astype(F), (n * n, 1)))
+        ids = np.zeros((p, p), dtype=np.int64)
+        for pj in range(p):
+            for pi in range(p):
+                jj, ii = np.meshgrid(np.arange(q + 1) + pj * q, np.arange(q + 1) + pi * q, indexing='ij')
+                remap = (vert_base + vcount + jj * n + ii).reshape(-1).astype(np.uint32)
+                mpos = pos[(jj * n + ii).reshape(-1)]
+                rec = _meshlet_records(mpos[None].astype(F), np.array([data_base + dcount], dtype=np.uint32),
+                                       (q + 1) ** 2, 2 * q * q, lod, normal.astype(F))
+                out_data.append(np.concatenate([remap, topo]))
+                out_meshlets.append(rec)
+                ids[pj, pi] = meshlet_base + mcount
+                dcount += len(remap) + len(topo)
+                mcount += 1
+        level_ids.append(ids)
+        vcount += n * n
+        lod += 1
+        if p == 1 or lod >= lods:
+            break
+        p //= 2
+    # DAG (nanite_builder.cpp:851-868 semantics on a quadtree): the level-k meshlet at (j, i) was produced by
+    # simplifying the 2x2 block of level-(k-1) meshlets under it, so its own sphere is Sph(k, j, i) and the parent
+    # sphere of those four children is the same Sph(k, j, i).  A GPU cluster group collects meshlets sharing both
+    # spheres: 2x2 blocks at level 0, single meshlets above.
+    nl = len(level_ids)
+
+    def sph(level, j, i):
+        pl = level_ids[level].shape[0]
+        c = origin + ((i + 0.5) / pl) * du + ((j + 0.5) / pl) * dv
+        err = 0.5 * face_len / (level_ids[level - 1].shape[0] * q)      # detail removed going k-1 -> k
+        return c, err
+
+    for level in range(nl):
+        ids = level_ids[level]
+        pl = ids.shape[0]
+        if level == 0 and nl > 1:
+            for bj in range(pl // 2):
+                for bi in range(pl // 2):
+                    mids = ids[bj * 2:bj * 2 + 2, bi * 2:bi * 2 + 2].reshape(-1)
+                    pc, pe = sph(1, bj, bi)
+                    groups.append((mids.astype(np.uint32), pc, -1.0, pc, pe))
+        elif level == 0:
+            for bj in range(0, pl, 2):
+                for bi in range(0, pl, 2):
+                    mids = ids[bj:bj + 2, bi:bi + 2].reshape(-1)
+                    c = origin + 0.5 * du + 0.5 * dv
+                    groups.append((mids.astype(np.uint32), c, -1.0, c, FLT_MAX))
+        else:
+            for j in range(pl):
+                for i in range(pl):
+                    oc, oe = sph(level, j, i)
+                    if level == nl - 1:
+                        pc, pe = oc, FLT_MAX
+                    else:
+                        pc, pe = sph(level + 1, j // 2, i // 2)
+                    groups.append((np.array([ids[j, i]], dtype=np.uint32), oc, oe, pc, pe))
+    return dict(positions=np.concatenate(out_pos), normals=np.concatenate(out_nrm), uv0=np.concatenate(out_uv),
+                tangents=np.concatenate(out_tan), meshletData=np.concatenate(out_data),
+                meshlets=np.concatenate(out_meshlets), groups=groups, lod0=int(level_ids[0].size))
+
+
+def _box_primitive(size, patches, lods, five_faces=True):
+    """Axis-aligned box [0,sx]x[0,sy]x[0,sz] in local space; faces outward, optional no bottom."""
+    sx, sy, sz = size
+    faces = [
+        ((0, 0, sz), (sx, 0, 0), (0, sy, 0), (0, 0, 1)),     # +z
+        ((sx, 0, 0), (-sx, 0, 0), (0, sy, 0), (0, 0, -1)),   # -z
+        ((sx, 0, sz), (0, 0, -sz), (0, sy, 0), (1, 0, 0)),   # +x
+        ((0, 0, 0), (0, 0, sz), (0, sy, 0), (-1, 0, 0)),     # -x
+        ((0, sy, sz), (sx, 0, 0), (0, 0, -sz), (0, 1, 0)),   # +y (roof)
+    ]
+    if not five_faces:
+        faces.append(((0, 0, 0), (sx, 0, 0), (0, 0, sz), (0, -1, 0)))
+    return faces
+
+
+class _PrimBuilder:
+    def __init__(self):
+        self.pos, self.nrm, self.uv, self.tan, self.data, self.meshlets = [], [], [], [], [], []
+        self.groups, self.group_indices = [], []
+        self.prims = []
+        self.nv = self.nd = self.nm = self.ng = self.ngi = 0
+        self.lod0 = []
+
+    def add_primitive(self, faces, patches, lods):
+        v0, m0, g0, gi0 = self.nv, self.nm, self.ng, self.ngi
+        lod0 = 0
+        allpos = []
+        for (o, du, dv, nrm) in faces:
+            f = _face_lod_chain(o, du, dv, patches, nrm, self.nv - v0, self.nd, self.nm - m0, lods)
+            self.pos.append(f['positions']); self.nrm.append(f['normals']); self.uv.append(f['uv0'])
+            self.tan.append(f['tangents']); self.data.append(f['meshletData']); self.meshlets.append(f['meshlets'])
+            allpos.append(f['positions'])
+            self.nv += len(f['positions']); self.nd += len(f['meshletData']); self.nm += len(f['meshlets'])
+            lod0 += f['lod0']
+            for (mids, oc, oe, pc, pe) in f['groups']:
+                g = np.zeros((), dtype=abi.GPUGLTFMeshletGroup)
+                g['clusterPosCenter'], g['error'] = oc, oe
+                g['parentPosCenter'], g['parentError'] = pc, pe
+                g['meshletOffset'], g['meshletCount'] = self.ngi - gi0, len(mids)
+                self.groups.append(g)
+                self.group_indices.append(mids)
+                self.ng += 1; self.ngi += len(mids)
+        ap = np.concatenate(allpos)
+        p = np.zeros((), dtype=abi.GLTFPrimitiveBuffer)
+        p['posMin'], p['posMax'], p['posAverage'] = ap.min(axis=0), ap.max(axis=0), ap.mean(axis=0)
+        p['vertexOffset'], p['vertexCount'] = v0, self.nv - v0
+        p['meshletOffset'] = m0
+        p['meshletGroupOffset'], p['meshletGroupIndicesOffset'], p['meshletGroupCount'] = g0, gi0, self.ng - g0
+        self.prims.append(p)
+        self.lod0.append(lod0)
+        return len(self.prims) - 1
+
+    def finish(self, materials):
+        datas = dict(meshlets=np.concatenate(self.meshlets), positions=np.concatenate(self.pos),
+                     normals=np.concatenate(self.nrm), uv0=np.concatenate(self.uv), tangents=np.concatenate(self.tan),
+                     meshletData=np.concatenate(self.data), groups=np.array(self.groups),
+                     groupIndices=np.concatenate(self.group_indices))
+        return abi.HostScene([datas], np.array(self.prims), np.array(materials))
+
+
+def city_scene(n_buildings=26, patches=4, lods=3, width=1920, height=1080, seed=2, ground_patches=8):
+    """S2/S3 stand-in: a grid of box buildings (instanced from 3 prototypes with a quadtree LOD DAG per face) on a
+    coarse ground slab, camera at street level so that near-plane clipping, large triangles, LOD cuts and occlusion
+    all occur.  ``n_buildings=26, patches=4`` ~ 266 k LOD-0 triangles (S2); ``n_buildings=371`` ~ 3.8 M (S3)."""
+    rng = np.random.default_rng(seed)
+    b = _PrimBuilder()
+    protos = [b.add_primitive(_box_primitive(sz, patches, lods), patches, lods)
+              for sz in ((10.0, 30.0, 10.0), (14.0, 18.0, 12.0), (8.0, 45.0, 8.0))]
+    side = int(math.ceil(math.sqrt(n_buildings)))
+    pitch = 24.0
+    extent = side * pitch
+    ground = b.add_primitive([((0, 0, extent), (extent, 0, 0), (0, 0, -extent), (0, 1, 0))], ground_patches, 1)
+    mats = [default_material(base_color=(0.7, 0.7, 0.72, 1.0)),
+            default_material(two_sided=1, base_color=(0.5, 0.6, 0.5, 1.0)),
+            default_material(alpha_mode=1, alpha_cutoff=0.5, base_color=(0.6, 0.4, 0.3, 1.0)),
+            default_material(base_color=(0.3, 0.3, 0.3, 1.0), roughness=0.9)]
+    scene = b.finish(mats)
+    camera = cam.Camera((extent * 0.5 + 3.0, 1.7, extent + 6.0), (-0.12, 0.08, -1.0), width=width, height=height)
+    objs = []
+    transforms = []
+    k = 0
+    for j in range(side):
+        for i in range(side):
+            if k >= n_buildings:
+                break
+            proto = protos[int(rng.integers(0, len(protos)))]
+            m = np.eye(4)
+            yaw = rng.uniform(-0.3, 0.3)
+            s = rng.uniform(0.8, 1.25)
+            c, sn = math.cos(yaw), math.sin(yaw)
+            m[:3, :3] = np.array([[c, 0, sn], [0, 1, 0], [-sn, 0, c]]) * s
+            m[:3, 3] = (i * pitch + rng.uniform(2, 8), 0.0, j * pitch + rng.uniform(2, 8))
+            transforms.append((m, proto, int(rng.integers(0, 3))))
+            k += 1
+    transforms.append((np.eye(4), ground, 3))
+    for (m, proto, mat) in transforms:
+        objs.append(cam.fill_object(m, camera, proto, mat))
+    objects = np.array(objs)
+    lod0_total = int(sum(b.lod0[p] for (_, p, _) in transforms))
+    group_total = int(sum(int(scene.primitives[p]['meshletGroupCount']) for (_, p, _) in transforms))
+    return scene, camera, objects, dict(lod0MeshletCount=lod0_total, meshletGroupCount=group_total,
+                                        transforms=transforms)
+
+
+def refill_objects(transforms, camera, camera_last=None):
+    """Per-frame GPUObjectGLTFPrimitive array for a moved camera (static geometry)."""
+    return np.array([cam.fill_object(m, camera, proto, mat, camera_last=camera_last) for (m, proto, mat) in transforms])
+
+
+def synthetic_luts(seed=7):
+    """Seeded stand-ins for the Bruneton transmittance (256x64) / irradiance (64x16) RGBA16F LUTs."""
+    rng = np.random.default_rng(seed)
+    u = np.linspace(0, 1, 256)[None, :, None]
+    v = np.linspace(0, 1, 64)[:, None, None]
+    tr = np.clip(0.2 + 0.8 * u * (0.5 + 0.5 * v) + 0.02 * rng.random((64, 256, 1)), 0, 1) * np.array([1.0, 0.95, 0.85])
+    tr = np.concatenate([tr, np.ones((64, 256, 1))], axis=-1).astype(np.float16)
+    u = np.linspace(0, 1, 64)[None, :, None]
+    v = np.linspace(0, 1, 16)[:, None, None]
+    ir = (0.02 + 0.1 * u * (1.0 - 0.5 * v)) * np.array([0.6, 0.8, 1.0])
+    ir = np.concatenate([ir, np.ones((16, 64, 1))], axis=-1).astype(np.float16)
+    return np.ascontiguousarray(tr), np.ascontiguousarray(ir)

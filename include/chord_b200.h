@@ -1,0 +1,199 @@
+/*
+ * chord_b200.h — C ABI of libchord_b200.so: chord's Nanite-style visibility-buffer
+ * path (cluster cull -> software raster -> HZB -> tile classify -> material resolve)
+ * as hand-written sm_100a CUDA kernels, headless.
+ *
+ * This is the drop-in boundary for the reference's renderer pass graph.  Each entry
+ * point cites the reference function it replaces.  Mapping of the reference's
+ * vocabulary onto the ABI:
+ *     graphics::GraphicsQueue&       -> the context's CUDA stream (calls are stream-ordered, asynchronous)
+ *     bindless buffer / texture ids  -> device pointers resolved at chord_scene_upload
+ *     PoolBufferGPUOnlyRef pairs     -> chord_cmdlist  (CountAndCmdBuffer, postprocessing.h:48)
+ *     HZBContext                     -> chord_hzb      (render_helper.h:411-451)
+ *     GBufferTextures                -> owned by chord_frame (render_textures.h:10-61)
+ *     check(...) crash               -> non-zero return + chord_last_error()
+ * Every function returns 0 on success, never throws, never falls back to a CPU path.
+ * One host thread per context.
+ */
+#ifndef CHORD_B200_H
+#define CHORD_B200_H
+
+#include "chord_abi_types.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CHORD_B200_ABI_VERSION 1
+
+typedef struct chord_ctx     chord_ctx;
+typedef struct chord_frame   chord_frame;
+typedef struct chord_cmdlist chord_cmdlist;
+typedef struct chord_hzb     chord_hzb;
+
+enum {
+    CHORD_OK = 0,
+    CHORD_ERR_INVALID = 1,      /* bad argument (reference: check() failure) */
+    CHORD_ERR_CUDA = 2,         /* CUDA runtime error, text in chord_last_error() */
+    CHORD_ERR_CAPACITY = 3,     /* a list/queue capacity would be exceeded */
+    CHORD_ERR_NO_DEVICE = 4
+};
+
+/* Thread-local text of the last failure on this thread. */
+const char* chord_last_error(void);
+int         chord_abi_version(void);
+
+/* ---- context: replaces graphics::Context + one GraphicsQueue (source/graphics/graphics.h) */
+int  chord_ctx_create(int device, chord_ctx** out);
+void chord_ctx_destroy(chord_ctx* ctx);
+/* cudaStream_t of the context, for callers that interleave their own work / events. */
+void* chord_ctx_stream(chord_ctx* ctx);
+int  chord_ctx_sync(chord_ctx* ctx);
+/* r.instanceculling.{frustumCulling,hzbCulling,meshletConeCulling} cvars folded into
+ * switchFlags bits 0/1/2 (instance_culling.cpp:22-68, gltf.h:10-12). Default 0b111. */
+int  chord_ctx_set_switch_flags(chord_ctx* ctx, uint32_t switchFlags);
+uint32_t chord_ctx_get_switch_flags(const chord_ctx* ctx);
+/* Number of kernels this context has launched since creation (for gpu_launches accounting). */
+uint64_t chord_ctx_kernel_launches(const chord_ctx* ctx);
+
+/* ---- scene: replaces gpu_scene.{h,cpp} pools + the asset GPU buffers
+ * (gltf.h:65-153; packing asset_gltf_helper.cpp:522-548, :572-584).  Arrays are the
+ * reference structs byte-for-byte.  One chord_primitive_datas_desc corresponds to one
+ * GLTFPrimitiveDatasBuffer record (one imported asset). */
+typedef struct {
+    const chord_GPUGLTFMeshlet*      meshlets;       uint32_t meshletCount;
+    const float*                     positions;      uint32_t vertexCount;      /* float3, tightly packed */
+    const float*                     normals;        /* float3 x vertexCount, may be NULL if lighting is not run */
+    const float*                     uv0;            /* float2 x vertexCount, may be NULL */
+    const float*                     tangents;       /* float4 x vertexCount, may be NULL */
+    const uint32_t*                  meshletData;    uint32_t meshletDataCount; /* [remap u32 x V][tri u32 x T] per meshlet */
+    const chord_GPUBVHNode*          bvhNodes;       uint32_t bvhNodeCount;     /* may be NULL */
+    const chord_GPUGLTFMeshletGroup* groups;         uint32_t groupCount;
+    const uint32_t*                  groupIndices;   uint32_t groupIndicesCount;
+} chord_primitive_datas_desc;
+
+typedef struct {
+    const chord_primitive_datas_desc* datas;      uint32_t datasCount;
+    const chord_GLTFPrimitiveBuffer*  primitives; uint32_t primitiveCount;
+    const chord_GLTFMaterialGPUData*  materials;  uint32_t materialCount;
+} chord_scene_desc;
+
+/* Copies everything to HBM (host pointers in, synchronous on return). Replaces any previous scene. */
+int chord_scene_upload(chord_ctx* ctx, const chord_scene_desc* desc);
+
+/* ---- pooled work lists: CountAndCmdBuffer = {uint count, uint3 cmd[capacity]}
+ * (instance_culling.cpp:140-141 sizes them by lod0MeshletCount). */
+int  chord_cmdlist_create(chord_ctx* ctx, uint32_t capacity, chord_cmdlist** out);
+void chord_cmdlist_destroy(chord_cmdlist* list);
+int  chord_cmdlist_upload(chord_cmdlist* list, const chord_draw_cmd* hostCmds, uint32_t count);
+int  chord_cmdlist_readback(chord_cmdlist* list, chord_draw_cmd* hostCmds, uint32_t hostCapacity, uint32_t* outCount);
+uint32_t chord_cmdlist_capacity(const chord_cmdlist* list);
+/* device pointers (count is a single u32, cmds is uint3[capacity]) */
+void* chord_cmdlist_count_ptr(chord_cmdlist* list);
+void* chord_cmdlist_cmds_ptr(chord_cmdlist* list);
+
+/* ---- HZB: HZBContext (render_helper.h:411-451; hzb.cpp:49-74 sizing: nextPOT(dim)/2,
+ * halved again if equal to dim; R16F; floor(log2(max(w,h)))+1 mips, >= 6). */
+int  chord_hzb_create(chord_ctx* ctx, uint32_t depthWidth, uint32_t depthHeight, chord_hzb** out);
+void chord_hzb_destroy(chord_hzb* hzb);
+int  chord_hzb_info(const chord_hzb* hzb, uint32_t* mip0Width, uint32_t* mip0Height, uint32_t* mipCount,
+                    uint32_t* validWidth, uint32_t* validHeight);
+/* which: 0 = min chain, 1 = max chain.  Host buffer receives (w>>mip)*(h>>mip) fp16 bit patterns. */
+int  chord_hzb_readback(chord_hzb* hzb, int which, uint32_t mip, uint16_t* host);
+/* valid depth range {minBits, maxBits} as written by hzb.hlsl:165-172 (DIM_COMPUTE_VALID_RANGE). */
+int  chord_hzb_readback_valid_range(chord_hzb* hzb, uint32_t outMinMaxBits[2]);
+/* Whole min chain as one contiguous device allocation (for NCCL / peer copies), bytes. */
+void*    chord_hzb_chain_ptr(chord_hzb* hzb, int which);
+uint64_t chord_hzb_chain_bytes(const chord_hzb* hzb);
+/* Byte offset of a mip inside the chain allocation. */
+uint64_t chord_hzb_mip_offset(const chord_hzb* hzb, uint32_t mip);
+/* Mark a chain filled from outside (after an all-gather) as valid history. */
+int  chord_hzb_set_valid(chord_hzb* hzb, int valid);
+int  chord_hzb_is_valid(const chord_hzb* hzb);
+
+/* ---- frame: GBufferTextures + per-view uniforms (renderer.cpp:175-263, render_textures.cpp:20-102) */
+typedef struct { uint32_t x0, y0, x1, y1; } chord_rect;   /* pixel rect [x0,x1) x [y0,y1) */
+
+int  chord_frame_create(chord_ctx* ctx, uint32_t width, uint32_t height, chord_frame** out);
+void chord_frame_destroy(chord_frame* frame);
+
+/* Uploads the per-frame uniforms (host pointers, pinned or pageable) and clears the
+ * visibility/depth surface (addClearGbufferPass: vis = 0, depth = 0.0).
+ * lod0MeshletCount / meshletGroupCount = PerframeCollected totals (component_gltf_mesh.cpp:58-122).
+ * tile = NULL renders the full frame; otherwise raster, HZB and resolve are restricted to the
+ * rect (screen-tile partition across GPUs). */
+int chord_frame_begin(chord_frame* frame,
+                      const chord_PerframeCameraView* view,
+                      const chord_InstanceCullingViewInfo* instanceView,
+                      const chord_GPUObjectGLTFPrimitive* objects, uint32_t objectCount,
+                      uint32_t lod0MeshletCount, uint32_t meshletGroupCount,
+                      const chord_rect* tile);
+
+/* instanceCulling (gltf_rendering.h:37; instance_culling.cpp:83-161): per-object frustum
+ * cull, LOD-DAG cut, per-meshlet cone + frustum cull.  out receives (objectId, meshletId, slot)
+ * in canonical order (object, group, meshlet-in-group); slot == index. */
+int chord_instance_culling(chord_frame* frame, chord_cmdlist* out);
+
+/* detail::hzbCulling (instance_culling.cpp:286-351; hzb_mainview_culling.hlsl:35-213).
+ * phase 0: last frame's matrices + HZB, also writes the rejected list. phase 1: this frame's. */
+int chord_hzb_culling(chord_frame* frame, const chord_hzb* hzb, int firstStage,
+                      chord_cmdlist* in, chord_cmdlist* outVisible, chord_cmdlist* outRejected /* NULL in phase 1 */);
+
+/* renderMesh (mesh_raster.cpp:208-253): filter by (alphaMode, twoSided) and rasterise the
+ * list into the frame's visibility/depth surface (K4+K6+K6'+K7 fused). */
+int chord_render_mesh(chord_frame* frame, chord_cmdlist* list);
+
+/* gltfVisibilityRenderingStage0 (mesh_raster.cpp:269-312).  needStage1 mirrors the bool result.
+ * scratchVisible is the pooled list that receives the phase-0 survivors. */
+int chord_visibility_stage0(chord_frame* frame, const chord_hzb* lastFrameHzb /* may be NULL / invalid */,
+                            chord_cmdlist* in, chord_cmdlist* scratchVisible, chord_cmdlist* outRejected,
+                            int* needStage1);
+/* gltfVisibilityRenderingStage1 (mesh_raster.cpp:314-329). */
+int chord_visibility_stage1(chord_frame* frame, const chord_hzb* thisFrameHzb,
+                            chord_cmdlist* rejected, chord_cmdlist* scratchVisible);
+
+/* buildHZB (postprocessing.h:41-54; hzb.cpp:38-227) from the frame's depth. */
+int chord_build_hzb(chord_frame* frame, int bMin, int bMax, int bValidRange, chord_hzb* dst);
+
+/* visibilityMark + prepareShadingTileParam (visibility_tile.cpp:20-111). */
+int chord_visibility_mark(chord_frame* frame, chord_cmdlist* postInstanceCull);
+
+/* lighting (lighting.h:37; lighting.cpp:193-246), PBR branch.  LUT layouts: Appendix B of SURVEY.md. */
+typedef struct {
+    const uint16_t* transmittance;   /* RGBA16F, 256 x 64, host pointer */
+    const uint16_t* irradiance;      /* RGBA16F, 64 x 16, host pointer */
+} chord_atmosphere_luts;
+int chord_atmosphere_luts_upload(chord_ctx* ctx, const chord_atmosphere_luts* luts);
+int chord_lighting(chord_frame* frame, chord_cmdlist* postInstanceCull);
+
+/* ---- read-backs (synchronise the stream) */
+int chord_readback_vis64(chord_frame* frame, uint64_t* host);          /* W*H packed texels */
+int chord_readback_visibility32(chord_frame* frame, uint32_t* host);   /* the reference's R32_UINT image */
+int chord_readback_depth32(chord_frame* frame, float* host);           /* the reference's D32 image */
+/* decoded (objectId, meshletId, triangleId) per pixel through a post-instance-cull list
+ * (visibility_tile.hlsl:47-60); 0xFFFFFFFF triple where no geometry. */
+int chord_readback_decoded(chord_frame* frame, chord_cmdlist* postInstanceCull, uint32_t* hostTriples);
+int chord_readback_tile_marker(chord_frame* frame, uint32_t* hostUint4PerTile);
+enum { CHORD_GBUF_COLOR = 0, CHORD_GBUF_BASECOLOR, CHORD_GBUF_VERTEX_NORMAL, CHORD_GBUF_PIXEL_NORMAL,
+       CHORD_GBUF_MOTION, CHORD_GBUF_AO_ROUGH_METAL, CHORD_GBUF_COUNT };
+/* pre-quantisation fp32 planes, 4 floats per pixel */
+int chord_readback_gbuffer_f32(chord_frame* frame, int which, float* host);
+void* chord_frame_vis64_ptr(chord_frame* frame);
+int   chord_frame_dims(const chord_frame* frame, uint32_t* w, uint32_t* h);
+
+/* ---- statistics written by the raster kernels (device counters, read back on demand) */
+typedef struct {
+    uint64_t trianglesSubmitted;   /* triangles in rasterised meshlets */
+    uint64_t trianglesCulled;      /* removed by the four mesh-shader culls */
+    uint64_t trianglesClipped;     /* took the clip (near / guard band) path */
+    uint64_t trianglesLarge;       /* routed through the tile queue */
+    uint64_t largeQueueOverflow;   /* handled inline because the queue was full */
+    uint64_t meshletsRastered;
+} chord_raster_stats;
+int chord_frame_raster_stats(chord_frame* frame, chord_raster_stats* out);
+int chord_frame_reset_stats(chord_frame* frame);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CHORD_B200_H */

@@ -1,0 +1,165 @@
+"""CPU oracle for chord's visibility-buffer path — TEST INFRASTRUCTURE ONLY (parity unpinned, see chord_oracle.h).
+
+ctypes wrapper over oracle/_build/libchord_oracle.so.  Only tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / ``--impl reference`` legs may import this package; chord_b200 (the product) never does.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from chord_b200 import abi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, '_build', 'libchord_oracle.so')
+
+
+def build(force=False):
+    src = [os.path.join(_HERE, f) for f in ('chord_oracle.c', 'chord_oracle.h')]
+    if force or not os.path.exists(_SO) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in src):
+        subprocess.check_call(['make', '-C', _HERE, '-s'])
+    return _SO
+
+
+class _Frame(C.Structure):
+    _fields_ = [('scene', C.c_void_p), ('view', C.c_void_p), ('iview', C.c_void_p), ('objects', C.c_void_p),
+                ('objectCount', C.c_uint32), ('width', C.c_uint32), ('height', C.c_uint32),
+                ('tile', abi.Rect), ('switchFlags', C.c_uint32), ('threads', C.c_int)]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(_SO)
+        _lib.oracle_instance_culling.restype = C.c_uint32
+        _lib.oracle_f32_to_f16_rtz.restype = C.c_uint16
+        _lib.oracle_f32_to_f16_rtz.argtypes = [C.c_float]
+        _lib.oracle_f16_to_f32.restype = C.c_float
+        _lib.oracle_f16_to_f32.argtypes = [C.c_uint16]
+    return _lib
+
+
+def hzb_dims(w, h):
+    a, b, c = C.c_uint32(), C.c_uint32(), C.c_uint32()
+    lib().oracle_hzb_dims(C.c_uint32(w), C.c_uint32(h), C.byref(a), C.byref(b), C.byref(c))
+    return a.value, b.value, c.value
+
+
+def hzb_mip_offsets(mip0w, mip0h, mips):
+    """Texel offset of every mip inside one contiguous chain; returns (offsets u64[mips], total texels)."""
+    offs, o = [], 0
+    for m in range(mips):
+        offs.append(o)
+        o += max(mip0w >> m, 1) * max(mip0h >> m, 1)
+    return np.array(offs, dtype=np.uint64), o
+
+
+class Frame:
+    """One view of one scene (mirrors the arguments chord_frame_begin takes)."""
+
+    def __init__(self, scene, view, iview, objects, width, height, switch_flags=0b111, tile=None, threads=0):
+        self.scene, self.width, self.height = scene, int(width), int(height)
+        self.view = np.ascontiguousarray(view, dtype=abi.PerframeCameraView).reshape(())
+        self.iview = np.ascontiguousarray(iview, dtype=abi.InstanceCullingViewInfo).reshape(())
+        self.objects = np.ascontiguousarray(objects, dtype=abi.GPUObjectGLTFPrimitive)
+        f = _Frame()
+        f.scene = C.addressof(scene.desc)
+        f.view, f.iview, f.objects = self.view.ctypes.data, self.iview.ctypes.data, self.objects.ctypes.data
+        f.objectCount, f.width, f.height = len(self.objects), self.width, self.height
+        t = tile if tile is not None else (0, 0, self.width, self.height)
+        f.tile = abi.Rect(*t)
+        f.switchFlags, f.threads = switch_flags, threads
+        self.c = f
+
+    def instance_culling(self, capacity):
+        out = np.zeros(max(capacity, 1), dtype=abi.DrawCmd)
+        n = lib().oracle_instance_culling(C.byref(self.c), C.c_void_p(out.ctypes.data), C.c_uint32(capacity))
+        assert n <= capacity, f'oracle_instance_culling overflow {n} > {capacity}'
+        return out[:n].copy()
+
+    def render_mesh(self, cmds, vis64=None):
+        cmds = np.ascontiguousarray(cmds, dtype=abi.DrawCmd)
+        if vis64 is None:
+            vis64 = np.zeros((self.height, self.width), dtype=np.uint64)
+        stats = abi.RasterStats()
+        lib().oracle_render_mesh(C.byref(self.c), C.c_void_p(cmds.ctypes.data), C.c_uint32(len(cmds)),
+                                 C.c_void_p(vis64.ctypes.data), C.byref(stats))
+        return vis64, stats.as_dict()
+
+    def build_hzb(self, vis64, b_min=True, b_max=False, b_range=False):
+        w0, h0, mips = hzb_dims(self.width, self.height)
+        offs, total = hzb_mip_offsets(w0, h0, mips)
+        mn = np.zeros(total, dtype=np.uint16)
+        mx = np.zeros(total, dtype=np.uint16)
+        rng = np.zeros(2, dtype=np.uint32)
+        lib().oracle_build_hzb(C.c_void_p(vis64.ctypes.data), C.c_uint32(self.width), C.c_uint32(self.height),
+                               C.c_int(b_min), C.c_int(b_max), C.c_int(b_range),
+                               C.c_void_p(mn.ctypes.data), C.c_void_p(mx.ctypes.data), C.c_void_p(offs.ctypes.data),
+                               C.c_uint32(w0), C.c_uint32(h0), C.c_uint32(mips), C.c_void_p(rng.ctypes.data))
+        return dict(min=mn, max=mx, offsets=offs, mip0=(w0, h0), mips=mips, range=rng)
+
+    def hzb_culling(self, hzb, first_stage, cmds):
+        cmds = np.ascontiguousarray(cmds, dtype=abi.DrawCmd)
+        vis = np.zeros(max(len(cmds), 1), dtype=abi.DrawCmd)
+        rej = np.zeros(max(len(cmds), 1), dtype=abi.DrawCmd)
+        nv, nr = C.c_uint32(), C.c_uint32()
+        lib().oracle_hzb_culling(C.byref(self.c), C.c_int(first_stage),
+                                 C.c_void_p(hzb['min'].ctypes.data), C.c_void_p(hzb['offsets'].ctypes.data),
+                                 C.c_uint32(hzb['mip0'][0]), C.c_uint32(hzb['mip0'][1]), C.c_uint32(hzb['mips']),
+                                 C.c_void_p(cmds.ctypes.data), C.c_uint32(len(cmds)),
+                                 C.c_void_p(vis.ctypes.data), C.byref(nv), C.c_void_p(rej.ctypes.data), C.byref(nr))
+        return vis[:nv.value].copy(), rej[:nr.value].copy()
+
+    def visibility_mark(self, vis64, post_cull):
+        post_cull = np.ascontiguousarray(post_cull, dtype=abi.DrawCmd)
+        mw, mh = (self.width + 7) // 8, (self.height + 7) // 8
+        out = np.zeros((mh, mw, 4), dtype=np.uint32)
+        lib().oracle_visibility_mark(C.byref(self.c), C.c_void_p(vis64.ctypes.data), C.c_void_p(post_cull.ctypes.data),
+                                     C.c_uint32(len(post_cull)), C.c_void_p(out.ctypes.data))
+        return out
+
+
+def decode(vis64, post_cull):
+    post_cull = np.ascontiguousarray(post_cull, dtype=abi.DrawCmd)
+    out = np.zeros(vis64.shape + (3,), dtype=np.uint32)
+    lib().oracle_decode(C.c_void_p(vis64.ctypes.data), C.c_uint32(vis64.size), C.c_void_p(post_cull.ctypes.data),
+                        C.c_uint32(len(post_cull)), C.c_void_p(out.ctypes.data))
+    return out
+
+
+def raster_clip_triangle(width, height, clip, vis_id, two_sided, vis64=None, tile=None):
+    """Rasterise one clip-space triangle ((3,4) float32) into a packed surface."""
+    clip = np.ascontiguousarray(clip, dtype=np.float32).reshape(12)
+    if vis64 is None:
+        vis64 = np.zeros((height, width), dtype=np.uint64)
+    t = C.byref(abi.Rect(*tile)) if tile is not None else None
+    lib().oracle_raster_clip_triangle(C.c_uint32(width), C.c_uint32(height), t, C.c_void_p(clip.ctypes.data),
+                                      C.c_uint32(vis_id), C.c_int(two_sided), C.c_void_p(vis64.ctypes.data))
+    return vis64
+
+
+def run_frame(scene, view, iview, objects, width, height, lod0_capacity, prev_hzb=None, switch_flags=0b111, threads=0,
+              tile=None):
+    """The reference frame sequence (renderer.cpp:311-363) on the CPU: instance cull -> stage 0 -> HZB -> stage 1 -> HZB."""
+    fr = Frame(scene, view, iview, objects, width, height, switch_flags, tile, threads)
+    post = fr.instance_culling(lod0_capacity)
+    out = dict(post_cull=post)
+    vis64 = np.zeros((height, width), dtype=np.uint64)
+    if prev_hzb is not None and (switch_flags & abi.FLAG_HZB):
+        vis0, rej0 = fr.hzb_culling(prev_hzb, True, post)
+        fr.render_mesh(vis0, vis64)
+        mid = fr.build_hzb(vis64, True, False, False)
+        vis1, _ = fr.hzb_culling(mid, False, rej0)
+        fr.render_mesh(vis1, vis64)
+        out.update(stage0_visible=vis0, stage0_rejected=rej0, stage1_visible=vis1, mid_hzb=mid)
+    else:
+        fr.render_mesh(post, vis64)
+    out['hzb'] = fr.build_hzb(vis64, True, True, True)
+    out['vis64'] = vis64
+    out['frame'] = fr
+    return out

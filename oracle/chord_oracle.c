@@ -1,0 +1,686 @@
+/*
+ * chord_oracle.c — CPU restatement (plain C + OpenMP) of chord's visibility-buffer path.
+ * TEST INFRASTRUCTURE ONLY, see chord_oracle.h.  PARITY UNPINNED (no reference goldens exist).
+ *
+ * Floating-point rules (compile with -ffp-contract=off so that nothing but the
+ * explicit fmaf() calls fuses):
+ *   dot products / matrix rows accumulate left to right:  r = a0*b0; r = fma(a1,b1,r); ...
+ *   every `a*b + c` of the HLSL is one fma; divisions and sqrt are IEEE round-to-nearest;
+ *   min/max are IEEE minNum/maxNum (fminf/fmaxf); float->int is truncation unless stated.
+ */
+#include "chord_oracle.h"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+/* ------------------------------------------------------------------ small math */
+typedef struct { float x, y, z, w; } f4;
+typedef struct { float x, y, z; } f3;
+
+static inline float dot3f(float ax, float ay, float az, float bx, float by, float bz)
+{ float r = ax * bx; r = fmaf(ay, by, r); r = fmaf(az, bz, r); return r; }
+static inline float dot4f(float ax, float ay, float az, float aw, float bx, float by, float bz, float bw)
+{ float r = ax * bx; r = fmaf(ay, by, r); r = fmaf(az, bz, r); r = fmaf(aw, bw, r); return r; }
+
+/* C = A * B, column-major (C[c][r] = row r of A . column c of B) */
+static void mat_mul(const chord_float4x4* A, const chord_float4x4* B, chord_float4x4* C)
+{
+    for (int c = 0; c < 4; c++)
+        for (int r = 0; r < 4; r++)
+            C->m[c * 4 + r] = dot4f(A->m[0 + r], A->m[4 + r], A->m[8 + r], A->m[12 + r],
+                                    B->m[c * 4 + 0], B->m[c * 4 + 1], B->m[c * 4 + 2], B->m[c * 4 + 3]);
+}
+/* M * (x,y,z,w) */
+static inline f4 mat_mul_vec(const chord_float4x4* M, float x, float y, float z, float w)
+{
+    f4 o;
+    o.x = dot4f(M->m[0], M->m[4], M->m[8],  M->m[12], x, y, z, w);
+    o.y = dot4f(M->m[1], M->m[5], M->m[9],  M->m[13], x, y, z, w);
+    o.z = dot4f(M->m[2], M->m[6], M->m[10], M->m[14], x, y, z, w);
+    o.w = dot4f(M->m[3], M->m[7], M->m[11], M->m[15], x, y, z, w);
+    return o;
+}
+
+static inline uint32_t f2u(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
+static inline float u2f(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
+
+/* base.hlsli:175-185 kExtentApplyFactor */
+static const float kExtentApplyFactor[8][3] = {
+    { 1,  1,  1}, {-1, -1, -1}, { 1,  1, -1}, { 1, -1,  1},
+    {-1,  1,  1}, { 1, -1, -1}, {-1, -1,  1}, {-1,  1, -1},
+};
+
+/* ------------------------------------------------------------------ fp16 */
+uint16_t oracle_f32_to_f16_rtz(float v)
+{
+    /* round toward zero, subnormals kept, inf/nan passed through */
+    uint32_t u = f2u(v);
+    uint32_t sign = (u >> 16) & 0x8000u;
+    uint32_t e = (u >> 23) & 0xFFu;
+    uint32_t m = u & 0x7FFFFFu;
+    if (e == 0xFF) return (uint16_t)(sign | 0x7C00u | (m ? 0x200u : 0));
+    int32_t he = (int32_t)e - 127 + 15;
+    if (he >= 31) return (uint16_t)(sign | 0x7BFFu);        /* RTZ: overflow clamps to max finite */
+    if (he <= 0) {
+        if (he < -10) return (uint16_t)sign;
+        m |= 0x800000u;
+        uint32_t shift = (uint32_t)(14 - he);               /* 14..24 */
+        return (uint16_t)(sign | (m >> shift));
+    }
+    return (uint16_t)(sign | ((uint32_t)he << 10) | (m >> 13));
+}
+float oracle_f16_to_f32(uint16_t h)
+{
+    uint32_t sign = ((uint32_t)h & 0x8000u) << 16;
+    uint32_t e = (h >> 10) & 0x1Fu;
+    uint32_t m = h & 0x3FFu;
+    if (e == 0) {
+        if (m == 0) return u2f(sign);
+        /* subnormal: m * 2^-24 */
+        float f = (float)m * 5.9604644775390625e-08f;
+        return sign ? -f : f;
+    }
+    if (e == 31) return u2f(sign | 0x7F800000u | (m << 13));
+    return u2f(sign | ((e - 15 + 127) << 23) | (m << 13));
+}
+
+/* ------------------------------------------------------------------ scene access */
+typedef struct {
+    const chord_GPUObjectGLTFPrimitive* object;
+    const chord_GLTFPrimitiveBuffer* prim;
+    const chord_primitive_datas_desc* datas;
+    const chord_GLTFMaterialGPUData* material;
+} object_refs;
+
+static object_refs get_object(const oracle_frame* f, uint32_t objectId)
+{
+    object_refs r;
+    r.object = &f->objects[objectId];
+    r.prim = &f->scene->primitives[r.object->GLTFPrimitiveDetail];
+    r.datas = &f->scene->datas[r.prim->primitiveDatasBufferId];
+    r.material = &f->scene->materials[r.object->GLTFMaterialData];
+    return r;
+}
+
+static inline int has_flag(uint32_t flags, uint32_t bit) { return (flags & (1u << bit)) != 0u; }
+
+/* base.hlsli:161-171 projectPosToUVz */
+static inline f3 project_pos_to_uvz(float px, float py, float pz, const chord_float4x4* M)
+{
+    f4 h = mat_mul_vec(M, px, py, pz, 1.0f);
+    f3 o;
+    float nx = h.x / h.w, ny = h.y / h.w, nz = h.z / h.w;
+    o.x = fmaf(nx, 0.5f, 0.5f);
+    o.y = fmaf(ny, -0.5f, 0.5f);
+    o.z = nz;
+    return o;
+}
+
+/* base.hlsli:275-305 frustumCulling(planes, centerLS, extentLS, localToTranslatedWorld): true if culled */
+static int frustum_culling(const chord_float4 planes[6], f3 c, f3 e, const chord_float4x4* l2w)
+{
+    f3 p[8];
+    for (int k = 0; k < 8; k++) {
+        float x = fmaf(e.x, kExtentApplyFactor[k][0], c.x);
+        float y = fmaf(e.y, kExtentApplyFactor[k][1], c.y);
+        float z = fmaf(e.z, kExtentApplyFactor[k][2], c.z);
+        f4 w = mat_mul_vec(l2w, x, y, z, 1.0f);
+        p[k].x = w.x; p[k].y = w.y; p[k].z = w.z;
+    }
+    for (int i = 0; i < 6; i++) {
+        int allBack = 1;
+        for (int j = 0; j < 8; j++) {
+            if (dot3f(planes[i].x, planes[i].y, planes[i].z, p[j].x, p[j].y, p[j].z) > -planes[i].w) { allBack = 0; break; }
+        }
+        if (allBack) return 1;
+    }
+    return 0;
+}
+
+/* base.hlsli:248-272 orthoFrustumCulling: true if culled */
+static int ortho_frustum_culling(f3 c, f3 e, const chord_float4x4* localToClip)
+{
+    float mn[3] = {10.0f, 10.0f, 10.0f}, mx[3] = {-10.0f, -10.0f, -10.0f};
+    for (int k = 0; k < 8; k++) {
+        float x = fmaf(e.x, kExtentApplyFactor[k][0], c.x);
+        float y = fmaf(e.y, kExtentApplyFactor[k][1], c.y);
+        float z = fmaf(e.z, kExtentApplyFactor[k][2], c.z);
+        f3 uvz = project_pos_to_uvz(x, y, z, localToClip);
+        mn[0] = fminf(mn[0], uvz.x); mn[1] = fminf(mn[1], uvz.y); mn[2] = fminf(mn[2], uvz.z);
+        mx[0] = fmaxf(mx[0], uvz.x); mx[1] = fmaxf(mx[1], uvz.y); mx[2] = fmaxf(mx[2], uvz.z);
+    }
+    return (mn[0] >= 1.0f) || (mn[1] >= 1.0f) || (mx[0] <= 0.0f) || (mx[1] <= 0.0f);
+}
+
+static inline int is_ortho(const chord_float4x4* M) { return M->m[15] == 1.0f; }   /* base.hlsli:241-244 */
+
+/* base.hlsli:500-518 projectSphereToScreen; tanHalfFovy = tanf(0.5f*fovy) evaluated once per view on the host */
+static float project_sphere_to_screen(f4 sphere, float height, float tanHalfFovy)
+{
+    float d2 = dot3f(sphere.x, sphere.y, sphere.z, sphere.x, sphere.y, sphere.z);
+    float r = sphere.w, r2 = r * r;
+    if (d2 <= r2) return -1.0f;
+    return height * 0.5f / tanHalfFovy * r / sqrtf(d2 - r2);
+}
+
+/* nanite_shared.hlsli:15-49 */
+static int is_meshlet_group_visible(float renderHeight, float tanHalfFovy, const chord_GPUObjectGLTFPrimitive* obj,
+                                    const chord_float4x4* localToView, const chord_GPUGLTFMeshletGroup* g)
+{
+    const int bFinalLod = (g->parentError > CHORD_ERROR_RADIUS_ROOT);
+    const int bFirstLod = (g->error < -0.5f);
+    const float maxScale = obj->basicData.scaleExtractFromMatrix.w;
+    if (!bFinalLod) {
+        f4 v = mat_mul_vec(localToView, g->parentPosCenter.x, g->parentPosCenter.y, g->parentPosCenter.z, 1.0f);
+        f4 s = { v.x, v.y, v.z, maxScale * g->parentError };
+        float parentError = project_sphere_to_screen(s, renderHeight, tanHalfFovy);
+        if (parentError > 0.0f && parentError <= CHORD_ERROR_PIXEL_THRESHOLD) return 0;
+    }
+    if (!bFirstLod) {
+        f4 v = mat_mul_vec(localToView, g->clusterPosCenter.x, g->clusterPosCenter.y, g->clusterPosCenter.z, 1.0f);
+        f4 s = { v.x, v.y, v.z, maxScale * g->error };
+        float error = project_sphere_to_screen(s, renderHeight, tanHalfFovy);
+        if (error < 0.0f || error > CHORD_ERROR_PIXEL_THRESHOLD) return 0;
+    }
+    return 1;
+}
+
+/* nanite_shared.hlsli:51-91 */
+static int is_meshlet_visible(uint32_t switchFlags, const chord_float4 planes[6], const chord_GPUObjectGLTFPrimitive* obj,
+                              const chord_float4x4* l2w, const chord_float4x4* localToClip,
+                              const chord_GPUGLTFMeshlet* m, const chord_GLTFMaterialGPUData* mat)
+{
+    int visible = 1;
+    if (visible && mat->bTwoSided == 0 && has_flag(switchFlags, CHORD_FLAG_CONE_CULL_BIT)) {
+        f4 cam = mat_mul_vec(&obj->basicData.translatedWorldToLocal, 0.0f, 0.0f, 0.0f, 1.0f);
+        float vx = m->coneApex.x - cam.x, vy = m->coneApex.y - cam.y, vz = m->coneApex.z - cam.z;
+        float len = sqrtf(dot3f(vx, vy, vz, vx, vy, vz));
+        vx = vx / len; vy = vy / len; vz = vz / len;
+        if (dot3f(vx, vy, vz, m->coneAxis.x, m->coneAxis.y, m->coneAxis.z) >= m->coneCutOff) visible = 0;
+    }
+    f3 c = { 0.5f * (m->posMin.x + m->posMax.x), 0.5f * (m->posMin.y + m->posMax.y), 0.5f * (m->posMin.z + m->posMax.z) };
+    f3 e = { m->posMax.x - c.x, m->posMax.y - c.y, m->posMax.z - c.z };
+    if (visible && has_flag(switchFlags, CHORD_FLAG_FRUSTUM_CULL_BIT)) {
+        if (is_ortho(localToClip)) visible = !ortho_frustum_culling(c, e, localToClip);
+        else                        visible = !frustum_culling(planes, c, e, l2w);
+    }
+    return visible;
+}
+
+/* ------------------------------------------------------------------ K1 + K2 */
+uint32_t oracle_instance_culling(const oracle_frame* f, chord_draw_cmd* out, uint32_t capacity)
+{
+    const float tanHalfFovy = tanf(0.5f * f->view->cameraFovy);
+    uint32_t count = 0;
+    for (uint32_t objectId = 0; objectId < f->objectCount; objectId++) {
+        object_refs o = get_object(f, objectId);
+        const chord_float4x4* l2w = &o.object->basicData.localToTranslatedWorld;
+        chord_float4x4 localToClip; mat_mul(&f->iview->translatedWorldToClip, l2w, &localToClip);
+
+        /* instance_culling.hlsl:67-99, object level */
+        int visible = 1;
+        f3 c = { (o.prim->posMin.x + o.prim->posMax.x) * 0.5f, (o.prim->posMin.y + o.prim->posMax.y) * 0.5f, (o.prim->posMin.z + o.prim->posMax.z) * 0.5f };
+        f3 e = { o.prim->posMax.x - c.x, o.prim->posMax.y - c.y, o.prim->posMax.z - c.z };
+        if (has_flag(f->switchFlags, CHORD_FLAG_FRUSTUM_CULL_BIT)) {
+            if (is_ortho(&localToClip)) visible = !ortho_frustum_culling(c, e, &localToClip);
+            else                         visible = !frustum_culling(f->iview->frustumPlanesRS, c, e, l2w);
+        }
+        if (!visible) continue;
+
+        /* instance_culling.hlsl:133-208, per cluster group in index order */
+        chord_float4x4 localToView; mat_mul(&f->view->translatedWorldToView, l2w, &localToView);
+        for (uint32_t g = 0; g < o.prim->meshletGroupCount; g++) {
+            const chord_GPUGLTFMeshletGroup* grp = &o.datas->groups[o.prim->meshletGroupOffset + g];
+            if (!is_meshlet_group_visible(f->view->renderDimension.y, tanHalfFovy, o.object, &localToView, grp)) continue;
+            for (uint32_t i = 0; i < grp->meshletCount; i++) {
+                uint32_t idx = o.datas->groupIndices[i + grp->meshletOffset + o.prim->meshletGroupIndicesOffset];
+                uint32_t meshletIndex = o.prim->meshletOffset + idx;
+                const chord_GPUGLTFMeshlet* m = &o.datas->meshlets[meshletIndex];
+                if (is_meshlet_visible(f->switchFlags, f->iview->frustumPlanesRS, o.object, l2w, &localToClip, m, o.material)) {
+                    if (count < capacity) { out[count].objectId = objectId; out[count].meshletId = meshletIndex; out[count].slot = count; }
+                    count++;
+                }
+            }
+        }
+    }
+    return count;
+}
+
+/* ------------------------------------------------------------------ K3 */
+static inline int firstbithigh_i(int32_t v)
+{
+    if (v <= 0) return -1;     /* HLSL firstbithigh(0) == -1; inputs here are never negative */
+    int b = 0; uint32_t u = (uint32_t)v;
+    while (u >>= 1) b++;
+    return b;
+}
+
+void oracle_hzb_culling(const oracle_frame* f, int firstStage,
+                        const uint16_t* hzbMin, const uint64_t* hzbMipOffsets, uint32_t mip0Width, uint32_t mip0Height, uint32_t mipCount,
+                        const chord_draw_cmd* in, uint32_t inCount,
+                        chord_draw_cmd* outVisible, uint32_t* outVisibleCount,
+                        chord_draw_cmd* outRejected, uint32_t* outRejectedCount)
+{
+    (void)mip0Height; (void)mipCount;
+    uint32_t nv = 0, nr = 0;
+    const chord_PerframeCameraView* view = f->view;
+    for (uint32_t t = 0; t < inCount; t++) {
+        const chord_draw_cmd cmd = in[t];
+        object_refs o = get_object(f, cmd.objectId);
+        const chord_GPUGLTFMeshlet* m = &o.datas->meshlets[cmd.meshletId];
+        f3 c = { (m->posMin.x + m->posMax.x) * 0.5f, (m->posMin.y + m->posMax.y) * 0.5f, (m->posMin.z + m->posMax.z) * 0.5f };
+        f3 e = { m->posMax.x - c.x, m->posMax.y - c.y, m->posMax.z - c.z };
+        int visible = 1;
+        if (has_flag(f->switchFlags, CHORD_FLAG_HZB_CULL_BIT)) {
+            float mx[3] = {-10.0f, -10.0f, -10.0f}, mn[3] = {10.0f, 10.0f, 10.0f};
+            chord_float4x4 mvp;
+            if (firstStage) mat_mul(&view->translatedWorldToClipLastFrame, &o.object->basicData.localToTranslatedWorldLastFrame, &mvp);
+            else            mat_mul(&view->translatedWorldToClip, &o.object->basicData.localToTranslatedWorld, &mvp);
+            for (int i = 0; i < 8; i++) {
+                float x = fmaf(e.x, kExtentApplyFactor[i][0], c.x);
+                float y = fmaf(e.y, kExtentApplyFactor[i][1], c.y);
+                float z = fmaf(e.z, kExtentApplyFactor[i][2], c.z);
+                f3 uvz = project_pos_to_uvz(x, y, z, &mvp);
+                mn[0] = fminf(mn[0], uvz.x); mn[1] = fminf(mn[1], uvz.y); mn[2] = fminf(mn[2], uvz.z);
+                mx[0] = fmaxf(mx[0], uvz.x); mx[1] = fmaxf(mx[1], uvz.y); mx[2] = fmaxf(mx[2], uvz.z);
+            }
+            const int zInRange = (mx[2] < 1.0f) && (mn[2] > 0.0f);
+            if (zInRange) {
+                if (mn[0] >= 1.0f || mn[1] >= 1.0f || mx[0] <= 0.0f || mx[1] <= 0.0f) visible = 0;
+            }
+            if (visible && zInRange) {
+                /* saturate */
+                float u0 = fminf(fmaxf(mn[0], 0.0f), 1.0f), v0 = fminf(fmaxf(mn[1], 0.0f), 1.0f);
+                float u1 = fminf(fmaxf(mx[0], 0.0f), 1.0f), v1 = fminf(fmaxf(mx[1], 0.0f), 1.0f);
+                const float W = view->renderDimension.x, H = view->renderDimension.y;
+                int32_t rx0 = (int32_t)fmaf(u0, W, 0.5f), ry0 = (int32_t)fmaf(v0, H, 0.5f);
+                int32_t rx1 = (int32_t)fmaf(u1, W, -0.5f), ry1 = (int32_t)fmaf(v1, H, -0.5f);
+                if (rx0 < 0) rx0 = 0; if (ry0 < 0) ry0 = 0;
+                /* min(renderDimension.xy - 1, pixelRect.zw): float min then int conversion */
+                float fx1 = fminf(W - 1.0f, (float)rx1), fy1 = fminf(H - 1.0f, (float)ry1);
+                rx1 = (int32_t)fx1; ry1 = (int32_t)fy1;
+                if (rx1 < rx0 || ry1 < ry0) {
+                    visible = 0;
+                } else {
+                    int32_t hx0 = rx0 >> 1, hy0 = ry0 >> 1, hx1 = rx1 >> 1, hy1 = ry1 >> 1;
+                    int mlx = firstbithigh_i(hx1 - hx0), mly = firstbithigh_i(hy1 - hy0);
+                    int mipLevel = (mlx > mly ? mlx : mly) - 1;
+                    if (mipLevel < 0) mipLevel = 0;
+                    if (((hx1 >> mipLevel) - (hx0 >> mipLevel) >= 4) || ((hy1 >> mipLevel) - (hy0 >> mipLevel) >= 4)) mipLevel += 1;
+                    int32_t cx0 = hx0 >> mipLevel, cy0 = hy0 >> mipLevel, cx1 = hx1 >> mipLevel, cy1 = hy1 >> mipLevel;
+                    float zMin = 10.0f;
+                    const uint32_t pitch = mip0Width >> mipLevel;
+                    const uint16_t* mip = hzbMin + hzbMipOffsets[mipLevel];
+                    for (int x = 0; x < 4; x++)
+                        for (int y = 0; y < 4; y++) {
+                            int32_t sx = cx0 + x; if (sx > cx1) sx = cx1;
+                            int32_t sy = cy0 + y; if (sy > cy1) sy = cy1;
+                            zMin = fminf(zMin, oracle_f16_to_f32(mip[(uint64_t)sy * pitch + (uint32_t)sx]));
+                        }
+                    if (zMin > mx[2]) visible = 0;
+                }
+            }
+        }
+        if (visible) outVisible[nv++] = cmd;
+        else if (firstStage && outRejected) outRejected[nr++] = cmd;
+    }
+    *outVisibleCount = nv;
+    if (outRejectedCount) *outRejectedCount = nr;
+}
+
+/* ------------------------------------------------------------------ K6' fixed-function rasteriser (specified) */
+typedef struct {
+    uint32_t width, height;
+    chord_rect tile;
+    uint64_t* vis64;
+} raster_target;
+
+static inline void vis_atomic_max(uint64_t* p, uint64_t key)
+{
+    uint64_t old = __atomic_load_n(p, __ATOMIC_RELAXED);
+    while (old < key && !__atomic_compare_exchange_n(p, &old, key, 1, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) { }
+}
+
+static inline int64_t floor_div256(int64_t a) { return a >> 8; }                 /* arithmetic shift == floor */
+static inline int64_t ceil_div256(int64_t a) { return -((-a) >> 8); }
+
+/* screen-space triangle: sx, sy in pixels (y down), sz = z/w */
+static void raster_screen_triangle(const raster_target* rt, const float sx[3], const float sy[3], const float sz[3],
+                                   uint32_t visId, int twoSided)
+{
+    int64_t X[3], Y[3];
+    for (int i = 0; i < 3; i++) {
+        X[i] = (int64_t)lrintf(sx[i] * 256.0f);     /* round-half-even to 1/256 px (subpixelPrecisionBits 8, base.h:443) */
+        Y[i] = (int64_t)lrintf(sy[i] * 256.0f);
+    }
+    int64_t A = (X[1] - X[0]) * (Y[2] - Y[0]) - (X[2] - X[0]) * (Y[1] - Y[0]);
+    if (A == 0) return;
+    if (!twoSided && A > 0) return;                  /* CCW front (helper.h:400) + flipped viewport: front <=> A < 0; cull BACK */
+    const int64_t s = (A > 0) ? 1 : -1;
+    const int64_t absA = (A > 0) ? A : -A;
+
+    int64_t minX = X[0], maxX = X[0], minY = Y[0], maxY = Y[0];
+    for (int i = 1; i < 3; i++) {
+        if (X[i] < minX) minX = X[i]; if (X[i] > maxX) maxX = X[i];
+        if (Y[i] < minY) minY = Y[i]; if (Y[i] > maxY) maxY = Y[i];
+    }
+    int64_t px0 = ceil_div256(minX - 128), px1 = floor_div256(maxX - 128);
+    int64_t py0 = ceil_div256(minY - 128), py1 = floor_div256(maxY - 128);
+    if (px0 < (int64_t)rt->tile.x0) px0 = rt->tile.x0;
+    if (py0 < (int64_t)rt->tile.y0) py0 = rt->tile.y0;
+    if (px1 > (int64_t)rt->tile.x1 - 1) px1 = (int64_t)rt->tile.x1 - 1;
+    if (py1 > (int64_t)rt->tile.y1 - 1) py1 = (int64_t)rt->tile.y1 - 1;
+    if (px0 > px1 || py0 > py1) return;
+
+    /* edge i: v_i -> v_(i+1); weight of the opposite vertex (i+2)%3 */
+    int64_t dx[3], dy[3]; int tl[3];
+    for (int i = 0; i < 3; i++) {
+        int j = (i + 1) % 3;
+        dx[i] = X[j] - X[i]; dy[i] = Y[j] - Y[i];
+        int64_t odx = s * dx[i], ody = s * dy[i];    /* direction after orienting clockwise-in-y-down */
+        tl[i] = (ody == 0 && odx > 0) || (ody < 0); /* top edge | left edge */
+    }
+    const float invA = 1.0f / (float)absA;
+    const float dz1 = sz[1] - sz[0], dz2 = sz[2] - sz[0];
+
+    for (int64_t py = py0; py <= py1; py++) {
+        const int64_t SY = py * 256 + 128;
+        for (int64_t px = px0; px <= px1; px++) {
+            const int64_t SX = px * 256 + 128;
+            int64_t E[3]; int inside = 1;
+            for (int i = 0; i < 3; i++) {
+                E[i] = s * (dx[i] * (SY - Y[i]) - dy[i] * (SX - X[i]));
+                if (!(E[i] > 0 || (E[i] == 0 && tl[i]))) { inside = 0; break; }
+            }
+            if (!inside) continue;
+            /* weights: w1 = E of edge 2 (v2->v0), w2 = E of edge 0 (v0->v1) */
+            float b1 = (float)E[2] * invA;
+            float b2 = (float)E[0] * invA;
+            float z = fmaf(b2, dz2, fmaf(b1, dz1, sz[0]));
+            z = fminf(fmaxf(z, 0.0f), 1.0f);
+            uint64_t key = ((uint64_t)f2u(z) << 32) | (uint64_t)visId;
+            vis_atomic_max(&rt->vis64[(uint64_t)py * rt->width + (uint64_t)px], key);
+        }
+    }
+}
+
+#define GUARD_BAND 8.0f
+#define SCREEN_LIMIT 32768.0f
+
+static inline float clip_plane_dist(const float v[4], int k)
+{
+    switch (k) {
+    case 0: return v[3] - v[2];
+    case 1: return v[2];
+    case 2: return GUARD_BAND * v[3] - v[0];
+    case 3: return GUARD_BAND * v[3] + v[0];
+    case 4: return GUARD_BAND * v[3] - v[1];
+    default: return GUARD_BAND * v[3] + v[1];
+    }
+}
+
+static int to_screen(const raster_target* rt, const float c[4], float* sx, float* sy, float* sz)
+{
+    const float halfW = 0.5f * (float)rt->width, halfH = 0.5f * (float)rt->height;
+    *sx = fmaf(c[0] / c[3], halfW, halfW);
+    *sy = fmaf(c[1] / c[3], -halfH, halfH);       /* flipped viewport, helper.h:304-323 */
+    *sz = c[2] / c[3];
+    return (fabsf(*sx) <= SCREEN_LIMIT) && (fabsf(*sy) <= SCREEN_LIMIT);   /* false for NaN / inf */
+}
+
+/* returns 1 if the clip path was taken */
+static int raster_clip_triangle(const raster_target* rt, const float c[3][4], uint32_t visId, int twoSided)
+{
+    int needClip = 0;
+    float sx[3], sy[3], sz[3];
+    for (int i = 0; i < 3; i++)
+        if (!(c[i][2] >= 0.0f && c[i][2] <= c[i][3])) needClip = 1;
+    if (!needClip)
+        for (int i = 0; i < 3; i++)
+            if (!to_screen(rt, c[i], &sx[i], &sy[i], &sz[i])) needClip = 1;
+    if (!needClip) { raster_screen_triangle(rt, sx, sy, sz, visId, twoSided); return 0; }
+
+    /* Sutherland-Hodgman in clip space; new vertices are always interpolated from the inside
+     * vertex towards the outside one so that a shared edge clips identically in both triangles. */
+    float poly[2][12][4]; int n = 3, cur = 0;
+    memcpy(poly[0], c, sizeof(float) * 12);
+    for (int k = 0; k < 6 && n >= 3; k++) {
+        int m = 0;
+        for (int i = 0; i < n; i++) {
+            const float* a = poly[cur][i];
+            const float* b = poly[cur][(i + 1) % n];
+            float da = clip_plane_dist(a, k), db = clip_plane_dist(b, k);
+            int ina = (da >= 0.0f), inb = (db >= 0.0f);
+            if (ina) { memcpy(poly[cur ^ 1][m++], a, 16); }
+            if (ina != inb) {
+                const float* pin = ina ? a : b; const float* pout = ina ? b : a;
+                float din = ina ? da : db, dout = ina ? db : da;
+                float t = din / (din - dout);
+                for (int j = 0; j < 4; j++) poly[cur ^ 1][m][j] = fmaf(t, pout[j] - pin[j], pin[j]);
+                m++;
+            }
+        }
+        n = m; cur ^= 1;
+    }
+    if (n < 3) return 1;
+    float px[12], py[12], pz[12]; int ok[12];
+    for (int i = 0; i < n; i++) ok[i] = to_screen(rt, poly[cur][i], &px[i], &py[i], &pz[i]);
+    for (int i = 1; i + 1 < n; i++) {
+        if (!(ok[0] && ok[i] && ok[i + 1])) continue;
+        float tx[3] = { px[0], px[i], px[i + 1] }, ty[3] = { py[0], py[i], py[i + 1] }, tz[3] = { pz[0], pz[i], pz[i + 1] };
+        raster_screen_triangle(rt, tx, ty, tz, visId, twoSided);
+    }
+    return 1;
+}
+
+void oracle_raster_clip_triangle(uint32_t width, uint32_t height, const chord_rect* tile,
+                                 const float clip[12], uint32_t visId, int twoSided, uint64_t* vis64)
+{
+    raster_target rt = { width, height, {0, 0, width, height}, vis64 };
+    if (tile) rt.tile = *tile;
+    float c[3][4]; memcpy(c, clip, sizeof(c));
+    raster_clip_triangle(&rt, c, visId, twoSided);
+}
+
+/* 3x3 determinant of rows (x,y,w): mesh_raster.hlsl:147 */
+static inline float minor2(float a, float b, float c, float d) { return fmaf(a, b, -(c * d)); }
+static inline float det3(const float r0[3], const float r1[3], const float r2[3])
+{
+    float m0 = minor2(r1[1], r2[2], r1[2], r2[1]);
+    float m1 = minor2(r1[0], r2[2], r1[2], r2[0]);
+    float m2 = minor2(r1[0], r2[1], r1[1], r2[0]);
+    return fmaf(r0[2], m2, fmaf(-r0[1], m1, r0[0] * m0));
+}
+
+/* ------------------------------------------------------------------ K4 + K6 + K7 */
+void oracle_render_mesh(const oracle_frame* f, const chord_draw_cmd* cmds, uint32_t count, uint64_t* vis64,
+                        chord_raster_stats* stats)
+{
+    raster_target rt = { f->width, f->height, f->tile, vis64 };
+    uint64_t nSub = 0, nCull = 0, nClip = 0, nMesh = 0;
+    const float dimW = f->iview->renderDimension.x, dimH = f->iview->renderDimension.y;
+#ifdef _OPENMP
+    int nthreads = f->threads > 0 ? f->threads : omp_get_max_threads();
+#pragma omp parallel for schedule(dynamic, 16) num_threads(nthreads) reduction(+:nSub,nCull,nClip,nMesh)
+#endif
+    for (uint32_t ci = 0; ci < count; ci++) {
+        const chord_draw_cmd cmd = cmds[ci];
+        object_refs o = get_object(f, cmd.objectId);
+        /* pipeline filter (pipeline_filter.hlsl:41-130; mesh_raster.cpp:224-253): alphaMode 0/1 only */
+        if (o.material->alphaMode > 1u) continue;
+        const int twoSided = o.material->bTwoSided != 0;
+        if (o.material->alphaMode == 1u) {
+            /* masked, untextured: builtin white texel alpha 1.0 (asset_gltf.cpp:295-326); clip(a*factor - cutoff) */
+            float a = fmaf(1.0f, o.material->baseColorFactor.w, -o.material->alphaCutOff);
+            if (a < 0.0f) continue;
+        }
+        const chord_GPUGLTFMeshlet* m = &o.datas->meshlets[cmd.meshletId];
+        const uint32_t V = m->vertexTriangleCount & 0xFFu, T = (m->vertexTriangleCount >> 8) & 0xFFu;
+        chord_float4x4 mvp; mat_mul(&f->iview->translatedWorldToClip, &o.object->basicData.localToTranslatedWorld, &mvp);
+        float hs[CHORD_MESHLET_MAX_VERTICES + 1][4];
+        for (uint32_t i = 0; i < V; i++) {
+            uint32_t vi = o.prim->vertexOffset + o.datas->meshletData[m->dataOffset + i];
+            const float* p = &o.datas->positions[(uint64_t)vi * 3];
+            f4 h = mat_mul_vec(&mvp, p[0], p[1], p[2], 1.0f);
+            hs[i][0] = h.x; hs[i][1] = h.y; hs[i][2] = h.z; hs[i][3] = h.w;
+        }
+        nMesh++; nSub += T;
+        for (uint32_t t = 0; t < T; t++) {
+            uint32_t idx = o.datas->meshletData[m->dataOffset + V + t];
+            uint32_t i0 = idx & 0xFFu, i1 = (idx >> 8) & 0xFFu, i2 = (idx >> 16) & 0xFFu;
+            const float p0[3] = { hs[i0][0], hs[i0][1], hs[i0][3] };
+            const float p1[3] = { hs[i1][0], hs[i1][1], hs[i1][3] };
+            const float p2[3] = { hs[i2][0], hs[i2][1], hs[i2][3] };
+            int culled = 0;
+            if (!twoSided) culled = det3(p0, p1, p2) <= 0.0f;                                    /* #0 */
+            if (!culled) culled = (p0[2] <= 0.0f && p1[2] <= 0.0f && p2[2] <= 0.0f);             /* #1 */
+            float u0 = fmaf(p0[0] / fabsf(p0[2]), 0.5f, 0.5f), v0 = fmaf(p0[1] / fabsf(p0[2]), -0.5f, 0.5f);
+            float u1 = fmaf(p1[0] / fabsf(p1[2]), 0.5f, 0.5f), v1 = fmaf(p1[1] / fabsf(p1[2]), -0.5f, 0.5f);
+            float u2 = fmaf(p2[0] / fabsf(p2[2]), 0.5f, 0.5f), v2 = fmaf(p2[1] / fabsf(p2[2]), -0.5f, 0.5f);
+            float maxU = fmaxf(u0, fmaxf(u1, u2)), maxV = fmaxf(v0, fmaxf(v1, v2));
+            float minU = fminf(u0, fminf(u1, u2)), minV = fminf(v0, fminf(v1, v2));
+            if (!culled) culled = (minU >= 1.0f) || (minV >= 1.0f) || (maxU <= 0.0f) || (maxV <= 0.0f);   /* #2 */
+            if (!culled) {                                                                      /* #3 */
+                float maxSx = maxU * dimW, maxSy = maxV * dimH, minSx = minU * dimW, minSy = minV * dimH;
+                culled = (rintf(minSx) == rintf(maxSx)) || (rintf(minSy) == rintf(maxSy));
+            }
+            if (culled) { nCull++; continue; }
+            const float c[3][4] = {
+                { hs[i0][0], hs[i0][1], hs[i0][2], hs[i0][3] },
+                { hs[i1][0], hs[i1][1], hs[i1][2], hs[i1][3] },
+                { hs[i2][0], hs[i2][1], hs[i2][2], hs[i2][3] } };
+            nClip += (uint64_t)raster_clip_triangle(&rt, c, chord_encode_triangle_instance(t, cmd.slot), twoSided);
+        }
+    }
+    if (stats) {
+        stats->trianglesSubmitted += nSub; stats->trianglesCulled += nCull; stats->trianglesClipped += nClip;
+        stats->meshletsRastered += nMesh;
+    }
+}
+
+/* ------------------------------------------------------------------ K8 */
+static uint32_t next_pot(uint32_t v) { uint32_t p = 1; while (p < v) p <<= 1; return p; }
+
+void oracle_hzb_dims(uint32_t depthW, uint32_t depthH, uint32_t* mip0W, uint32_t* mip0H, uint32_t* mipCount)
+{
+    /* hzb.cpp:49-56 */
+    uint32_t tw = next_pot(depthW) / 2, th = next_pot(depthH) / 2;
+    if (tw == depthW) tw /= 2;
+    if (th == depthH) th /= 2;
+    uint32_t mx = tw > th ? tw : th, mips = 1;
+    while (mx > 1) { mx >>= 1; mips++; }
+    *mip0W = tw; *mip0H = th; *mipCount = mips;
+}
+
+void oracle_build_hzb(const uint64_t* vis64, uint32_t width, uint32_t height,
+                      int bMin, int bMax, int bValidRange,
+                      uint16_t* minChain, uint16_t* maxChain, const uint64_t* mipOffsets,
+                      uint32_t mip0W, uint32_t mip0H, uint32_t mipCount, uint32_t validRangeBits[2])
+{
+    /* mip0 (hzb.hlsl:127-165 / hzb_one.hlsl:131-156): 2x2 footprint with edge clamp, fp32 min/max */
+    float* fmin_ = (float*)malloc(sizeof(float) * (size_t)mip0W * mip0H);
+    float* fmax_ = (float*)malloc(sizeof(float) * (size_t)mip0W * mip0H);
+    uint32_t vmin = ~0u, vmax = 0u;
+    for (uint32_t y = 0; y < mip0H; y++)
+        for (uint32_t x = 0; x < mip0W; x++) {
+            float mn = 0, mx = 0;
+            for (int k = 0; k < 4; k++) {
+                uint32_t sx = 2 * x + (uint32_t)(k >> 1), sy = 2 * y + (uint32_t)(k & 1);
+                if (sx > width - 1) sx = width - 1;
+                if (sy > height - 1) sy = height - 1;
+                float d = u2f((uint32_t)(vis64[(uint64_t)sy * width + sx] >> 32));
+                if (k == 0) { mn = d; mx = d; } else { mn = fminf(mn, d); mx = fmaxf(mx, d); }
+                if (bValidRange && d > 0.0f) {
+                    /* wave min/max then InterlockedMin/Max on asuint; guards zMin<1 / zMax>0 (hzb.hlsl:165-172) */
+                    uint32_t b = f2u(d);
+                    if (d < 1.0f && b < vmin) vmin = b;
+                    if (b > vmax) vmax = b;
+                }
+            }
+            fmin_[(size_t)y * mip0W + x] = mn; fmax_[(size_t)y * mip0W + x] = mx;
+        }
+    if (validRangeBits) { validRangeBits[0] = vmin; validRangeBits[1] = vmax; }
+
+    /* mips 0..5 are reduced in fp32 inside one group and stored as R16F; mip 5 is re-read (fp16) for 6.. .
+     * min: stored RTZ (conservative for reversed-Z; hzb.hlsl:69). max: raw RTZ for mips 0-4, mip 5 stored
+     * as half_bits(RTZ(v))+1 (hzb.hlsl:70) and everything above derives from that. */
+    uint32_t w = mip0W, h = mip0H;
+    for (uint32_t mip = 0; mip < mipCount; mip++) {
+        uint16_t* dmin = bMin ? minChain + mipOffsets[mip] : NULL;
+        uint16_t* dmax = bMax ? maxChain + mipOffsets[mip] : NULL;
+        for (uint32_t y = 0; y < h; y++)
+            for (uint32_t x = 0; x < w; x++) {
+                size_t i = (size_t)y * w + x;
+                if (dmin) dmin[i] = oracle_f32_to_f16_rtz(fmin_[i]);
+                if (dmax) {
+                    uint16_t hb = oracle_f32_to_f16_rtz(fmax_[i]);
+                    if (mip == 5) hb = (uint16_t)(hb + 1);
+                    dmax[i] = hb;
+                }
+            }
+        if (mip == 5) {   /* later mips read back the stored fp16 values */
+            for (size_t i = 0; i < (size_t)w * h; i++) {
+                if (dmin) fmin_[i] = oracle_f16_to_f32(dmin[i]);
+                if (dmax) fmax_[i] = oracle_f16_to_f32(dmax[i]);
+            }
+        }
+        if (mip + 1 == mipCount) break;
+        uint32_t nw = w > 1 ? w / 2 : 1, nh = h > 1 ? h / 2 : 1;
+        for (uint32_t y = 0; y < nh; y++)
+            for (uint32_t x = 0; x < nw; x++) {
+                uint32_t x0 = (w > 1) ? 2 * x : 0, x1 = (w > 1) ? 2 * x + 1 : 0;
+                uint32_t y0 = (h > 1) ? 2 * y : 0, y1 = (h > 1) ? 2 * y + 1 : 0;
+                float a = fmin_[(size_t)y0 * w + x0], b = fmin_[(size_t)y0 * w + x1], c = fmin_[(size_t)y1 * w + x0], d = fmin_[(size_t)y1 * w + x1];
+                float A = fmax_[(size_t)y0 * w + x0], B = fmax_[(size_t)y0 * w + x1], C = fmax_[(size_t)y1 * w + x0], D = fmax_[(size_t)y1 * w + x1];
+                float mn = fminf(fminf(fminf(a, b), c), d), mx = fmaxf(fmaxf(fmaxf(A, B), C), D);
+                /* write in place is safe: index y*nw+x <= y0*w+x0 */
+                fmin_[(size_t)y * nw + x] = mn; fmax_[(size_t)y * nw + x] = mx;
+            }
+        w = nw; h = nh;
+    }
+    free(fmin_); free(fmax_);
+}
+
+/* ------------------------------------------------------------------ K9 + decode */
+void oracle_decode(const uint64_t* vis64, uint32_t pixelCount, const chord_draw_cmd* postCull, uint32_t postCullCount,
+                   uint32_t* triples)
+{
+    for (uint32_t i = 0; i < pixelCount; i++) {
+        uint32_t id = (uint32_t)(vis64[i] & 0xFFFFFFFFu);
+        if (id == 0) { triples[3 * i] = triples[3 * i + 1] = triples[3 * i + 2] = 0xFFFFFFFFu; continue; }
+        uint32_t tri, inst; chord_decode_triangle_instance(id, &tri, &inst);
+        if (inst >= postCullCount) { triples[3 * i] = triples[3 * i + 1] = 0xFFFFFFFEu; triples[3 * i + 2] = tri; continue; }
+        triples[3 * i] = postCull[inst].objectId; triples[3 * i + 1] = postCull[inst].meshletId; triples[3 * i + 2] = tri;
+    }
+}
+
+void oracle_visibility_mark(const oracle_frame* f, const uint64_t* vis64,
+                            const chord_draw_cmd* postCull, uint32_t postCullCount, uint32_t* markerUint4)
+{
+    /* visibility_tile.hlsl:39-131: per 8x8 tile OR of (1 << shadingType); Gather with clamp-to-edge sampler */
+    const uint32_t mw = (f->width + 7) / 8, mh = (f->height + 7) / 8;
+    (void)postCullCount;
+    for (uint32_t ty = 0; ty < mh; ty++)
+        for (uint32_t tx = 0; tx < mw; tx++) {
+            uint32_t mk[4] = {0, 0, 0, 0};
+            for (uint32_t y = 0; y < 8; y++)
+                for (uint32_t x = 0; x < 8; x++) {
+                    uint32_t px = tx * 8 + x, py = ty * 8 + y;
+                    if (px > f->width - 1) px = f->width - 1;
+                    if (py > f->height - 1) py = f->height - 1;
+                    uint32_t id = (uint32_t)(vis64[(uint64_t)py * f->width + px] & 0xFFFFFFFFu);
+                    uint32_t type = CHORD_LIGHTING_TYPE_NONE;
+                    if (id != 0) {
+                        uint32_t tri, inst; chord_decode_triangle_instance(id, &tri, &inst);
+                        object_refs o = get_object(f, postCull[inst].objectId);
+                        type = o.material->materialType;
+                    }
+                    mk[type / 32] |= 1u << (type % 32);
+                }
+            memcpy(&markerUint4[4 * ((size_t)ty * mw + tx)], mk, 16);
+        }
+}

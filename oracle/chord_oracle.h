@@ -1,0 +1,73 @@
+/*
+ * chord_oracle.h — CPU restatement of chord's visibility-buffer path.  TEST INFRASTRUCTURE ONLY:
+ * nothing under chord_b200/ (the product) may include, link or call this.  Only tests/,
+ * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs use it.
+ *
+ * PARITY UNPINNED: the reference ships no golden vectors, tests or fixtures for this path
+ *  and cannot be built or run here (Win32/MSVC/DXC/Vulkan only), so this
+ * oracle is pinned only by (a) being a literal restatement of the cited HLSL, (b) the Vulkan
+ * fixed-function rules written out in DESIGN.md §3, and (c) the independent exact-arithmetic
+ * cross-checks in tests/test_oracle_*.py.
+ */
+#ifndef CHORD_ORACLE_H
+#define CHORD_ORACLE_H
+
+#include "../include/chord_b200.h"   /* public POD types only (scene desc, structs) */
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct {
+    const chord_scene_desc* scene;
+    const chord_PerframeCameraView* view;
+    const chord_InstanceCullingViewInfo* iview;
+    const chord_GPUObjectGLTFPrimitive* objects;
+    uint32_t objectCount;
+    uint32_t width, height;
+    chord_rect tile;            /* scissor; full frame = {0,0,w,h} */
+    uint32_t switchFlags;
+    int threads;                /* OpenMP threads (<=0: default) */
+} oracle_frame;
+
+/* K1+K2: instance_culling.hlsl:47-208 in canonical (object, group, meshlet) order. returns count. */
+uint32_t oracle_instance_culling(const oracle_frame* f, chord_draw_cmd* out, uint32_t capacity);
+
+/* K3: hzb_mainview_culling.hlsl:35-213.  hzbMin = mip chain (fp16 bits), mip m at hzbMipOffsets[m] (in texels),
+ * row pitch = mip0Width >> m. */
+void oracle_hzb_culling(const oracle_frame* f, int firstStage,
+                        const uint16_t* hzbMin, const uint64_t* hzbMipOffsets, uint32_t mip0Width, uint32_t mip0Height, uint32_t mipCount,
+                        const chord_draw_cmd* in, uint32_t inCount,
+                        chord_draw_cmd* outVisible, uint32_t* outVisibleCount,
+                        chord_draw_cmd* outRejected, uint32_t* outRejectedCount);
+
+/* K4+K6+K6'+K7: mesh_raster.hlsl:51-210 + Vulkan fixed-function rules into a packed 64-bit surface (W*H). */
+void oracle_render_mesh(const oracle_frame* f, const chord_draw_cmd* cmds, uint32_t count, uint64_t* vis64,
+                        chord_raster_stats* stats);
+
+/* Rasterise one clip-space triangle (exposed for the exact-arithmetic cross-check tests). */
+void oracle_raster_clip_triangle(uint32_t width, uint32_t height, const chord_rect* tile,
+                                 const float clip[12], uint32_t visId, int twoSided, uint64_t* vis64);
+
+/* K8: hzb.hlsl / hzb_one.hlsl.  Chains receive fp16 bit patterns; offsets as above. */
+void oracle_hzb_dims(uint32_t depthW, uint32_t depthH, uint32_t* mip0W, uint32_t* mip0H, uint32_t* mipCount);
+void oracle_build_hzb(const uint64_t* vis64, uint32_t width, uint32_t height,
+                      int bMin, int bMax, int bValidRange,
+                      uint16_t* minChain, uint16_t* maxChain, const uint64_t* mipOffsets,
+                      uint32_t mip0W, uint32_t mip0H, uint32_t mipCount, uint32_t validRangeBits[2]);
+
+/* K9: visibility_tile.hlsl:63-131 — one uint4 per 8x8 tile. */
+void oracle_visibility_mark(const oracle_frame* f, const uint64_t* vis64,
+                            const chord_draw_cmd* postCull, uint32_t postCullCount, uint32_t* markerUint4);
+
+/* decode through the post-instance-cull list: (object, meshlet, tri) or 0xFFFFFFFF x3 */
+void oracle_decode(const uint64_t* vis64, uint32_t pixelCount, const chord_draw_cmd* postCull, uint32_t postCullCount,
+                   uint32_t* triples);
+
+uint16_t oracle_f32_to_f16_rtz(float v);
+float    oracle_f16_to_f32(uint16_t h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
