@@ -1,0 +1,221 @@
+// common.cuh — shared device/host declarations for libchord_b200 (sm_100a only).
+//
+// Numerics contract: the whole library is compiled with --fmad=false, so the ONLY fused
+// multiply-adds are the explicit __fmaf_rn calls below; divisions and square roots are IEEE round-to-nearest
+// (__fdiv_rn / __fsqrt_rn); min/max are fminf/fmaxf.  Dot products and matrix rows accumulate left to right.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+
+#include "../../include/chord_b200.h"
+
+namespace chordb {
+
+// ------------------------------------------------------------------------------------------------ device scene
+struct DatasDev {
+    const chord_GPUGLTFMeshlet*      meshlets;
+    const float*                     positions;     // float3
+    const float*                     normals;       // float3
+    const float*                     uv0;           // float2
+    const float*                     tangents;      // float4
+    const uint32_t*                  meshletData;
+    const chord_GPUGLTFMeshletGroup* groups;
+    const uint32_t*                  groupIndices;
+    const chord_GPUBVHNode*          bvhNodes;
+};
+
+struct SceneDev {
+    const DatasDev*                  datas;
+    const chord_GLTFPrimitiveBuffer* prims;
+    const chord_GLTFMaterialGPUData* mats;
+    uint32_t nDatas, nPrims, nMats;
+};
+
+// Per-object derived matrices, computed once per frame by k_object_prepare (same arithmetic the per-thread
+// HLSL does: mul(translatedWorldToClip, localToTranslatedWorld) etc.).
+struct ObjectDerived {
+    chord_float4x4 localToClip;        // iview.translatedWorldToClip * localToTranslatedWorld
+    chord_float4x4 localToView;        // view.translatedWorldToView  * localToTranslatedWorld
+    chord_float4x4 localToClipHzb0;    // view.translatedWorldToClipLastFrame * localToTranslatedWorldLastFrame
+    chord_float4x4 localToClipHzb1;    // view.translatedWorldToClip * localToTranslatedWorld
+};
+
+struct FrameDev {
+    SceneDev scene;
+    const chord_PerframeCameraView*       view;
+    const chord_InstanceCullingViewInfo*  iview;
+    const chord_GPUObjectGLTFPrimitive*   objects;
+    const ObjectDerived*                  derived;
+    uint32_t objectCount;
+    uint32_t width, height;
+    chord_rect tile;
+    uint32_t switchFlags;
+    float tanHalfFovy;                  // tanf(0.5f * cameraFovy) evaluated on the host (libm), see DESIGN.md §3
+    unsigned long long* vis64;          // width*height packed texels
+};
+
+// ------------------------------------------------------------------------------------------------ math
+struct f4 { float x, y, z, w; };
+struct f3 { float x, y, z; };
+
+__device__ __forceinline__ float dot3f(float ax, float ay, float az, float bx, float by, float bz)
+{ float r = __fmul_rn(ax, bx); r = __fmaf_rn(ay, by, r); r = __fmaf_rn(az, bz, r); return r; }
+__device__ __forceinline__ float dot4f(float ax, float ay, float az, float aw, float bx, float by, float bz, float bw)
+{ float r = __fmul_rn(ax, bx); r = __fmaf_rn(ay, by, r); r = __fmaf_rn(az, bz, r); r = __fmaf_rn(aw, bw, r); return r; }
+
+__device__ __forceinline__ f4 mat_mul_vec(const float* __restrict__ m, float x, float y, float z, float w)
+{
+    f4 o;
+    o.x = dot4f(m[0], m[4], m[8],  m[12], x, y, z, w);
+    o.y = dot4f(m[1], m[5], m[9],  m[13], x, y, z, w);
+    o.z = dot4f(m[2], m[6], m[10], m[14], x, y, z, w);
+    o.w = dot4f(m[3], m[7], m[11], m[15], x, y, z, w);
+    return o;
+}
+
+__device__ __forceinline__ void mat_mul(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ Cm)
+{
+#pragma unroll
+    for (int c = 0; c < 4; c++)
+#pragma unroll
+        for (int r = 0; r < 4; r++)
+            Cm[c * 4 + r] = dot4f(A[r], A[4 + r], A[8 + r], A[12 + r], B[c * 4], B[c * 4 + 1], B[c * 4 + 2], B[c * 4 + 3]);
+}
+
+// base.hlsli:437-447 (device copies of chord_encode/decode_triangle_instance)
+__device__ __forceinline__ uint32_t enc_vis(uint32_t tri, uint32_t inst) { return (((inst + 1u) & CHORD_MAX_INSTANCE_ID_COUNT) << 8) | (tri & 0xFFu); }
+__device__ __forceinline__ void dec_vis(uint32_t pack, uint32_t& tri, uint32_t& inst) { tri = pack & 0xFFu; inst = ((pack >> 8) & CHORD_MAX_INSTANCE_ID_COUNT) - 1u; }
+
+__device__ __forceinline__ bool has_flag(uint32_t flags, uint32_t bit) { return (flags & (1u << bit)) != 0u; }
+
+__device__ __constant__ const float kExtentApplyFactor[8][3] = {
+    { 1,  1,  1}, {-1, -1, -1}, { 1,  1, -1}, { 1, -1,  1},
+    {-1,  1,  1}, { 1, -1, -1}, {-1, -1,  1}, {-1,  1, -1},
+};
+
+// ------------------------------------------------------------------------------------------------ ordered compaction
+// Single-pass decoupled look-back scan state: one 64-bit word per tile, flag in bits 62..63, value below.
+constexpr unsigned long long kScanFlagAggregate = 1ull << 62;
+constexpr unsigned long long kScanFlagPrefix    = 2ull << 62;
+constexpr unsigned long long kScanValueMask     = (1ull << 62) - 1;
+
+__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long* p)
+{ unsigned long long v; asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p)); return v; }
+__device__ __forceinline__ void st_volatile_u64(unsigned long long* p, unsigned long long v)
+{ asm volatile("st.volatile.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory"); }
+
+// Called by all 32 lanes of ONE warp of the block that owns `tile`; returns the exclusive prefix of the tile
+// (sum of the aggregates of all lower tiles) and publishes this tile's inclusive prefix.
+__device__ __forceinline__ unsigned long long scan_tile_exclusive_prefix(unsigned long long* status, uint32_t tile,
+                                                                         unsigned long long aggregate)
+{
+    const uint32_t lane = threadIdx.x & 31u;
+    if (tile == 0) {
+        if (lane == 0) st_volatile_u64(&status[0], kScanFlagPrefix | aggregate);
+        return 0ull;
+    }
+    if (lane == 0) st_volatile_u64(&status[tile], kScanFlagAggregate | aggregate);
+    unsigned long long exclusive = 0ull;
+    int look = (int)tile - 1;
+    while (true) {
+        const int idx = look - (int)lane;
+        unsigned long long v = (idx >= 0) ? ld_volatile_u64(&status[idx]) : (kScanFlagPrefix | 0ull);
+        const uint32_t flag = (uint32_t)(v >> 62);
+        if (__any_sync(0xffffffffu, flag == 0u)) continue;               // a predecessor has not published yet
+        const uint32_t pmask = __ballot_sync(0xffffffffu, flag == 2u);
+        unsigned long long val = v & kScanValueMask;
+        if (pmask) {
+            const uint32_t first = (uint32_t)__ffs((int)pmask) - 1u;    // nearest tile with an inclusive prefix
+            if (lane > first) val = 0ull;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) val += __shfl_xor_sync(0xffffffffu, val, o);
+        exclusive += val;
+        if (pmask) break;
+        look -= 32;
+    }
+    if (lane == 0) st_volatile_u64(&status[tile], kScanFlagPrefix | (exclusive + aggregate));
+    return exclusive;
+}
+
+// ------------------------------------------------------------------------------------------------ host helpers
+void set_error(const char* fmt, ...);
+#define CHORD_CUDA(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { \
+    chordb::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); return CHORD_ERR_CUDA; } } while (0)
+#define CHORD_REQUIRE(cond, msg) do { if (!(cond)) { chordb::set_error("check(%s) failed: %s", #cond, msg); return CHORD_ERR_INVALID; } } while (0)
+
+}  // namespace chordb
+
+// ------------------------------------------------------------------------------------------------ opaque handles
+struct chord_ctx {
+    int device;
+    cudaStream_t stream;
+    uint32_t switchFlags;
+    uint64_t launches;
+    int smCount;
+    // scene
+    chordb::SceneDev scene;
+    void** sceneAllocs; uint32_t nSceneAllocs;
+    chordb::DatasDev* datasHost;
+    // scratch for ordered compaction
+    unsigned long long* scanStatus; uint32_t scanTiles;
+    uint32_t* scanTicket;
+    // atmosphere LUTs
+    __half* lutTransmittance; __half* lutIrradiance;
+};
+
+struct chord_cmdlist {
+    chord_ctx* ctx;
+    uint32_t capacity;
+    uint32_t* count;            // device
+    chord_draw_cmd* cmds;       // device
+};
+
+struct chord_hzb {
+    chord_ctx* ctx;
+    uint32_t depthW, depthH, mip0W, mip0H, mipCount;
+    uint64_t mipOffset[CHORD_HZB_MAX_MIP_COUNT];   // in texels
+    uint64_t totalTexels;
+    __half* minChain; __half* maxChain;
+    uint32_t* validRange;        // {minBits, maxBits}
+    uint32_t* counter;
+    int valid;
+};
+
+struct chord_frame {
+    chord_ctx* ctx;
+    uint32_t width, height;
+    chord_rect tile;
+    unsigned long long* vis64;
+    chord_PerframeCameraView* dView; chord_InstanceCullingViewInfo* dIView;
+    chord_GPUObjectGLTFPrimitive* dObjects; uint32_t objectCapacity, objectCount;
+    chordb::ObjectDerived* dDerived;
+    uint32_t lod0MeshletCount, meshletGroupCount;
+    float tanHalfFovy;
+    // instance culling scratch
+    uint32_t* objGroupCount; uint32_t* objGroupBase; uint32_t* totalGroups;
+    // raster
+    void* largeTris; uint32_t* largeCounters; uint32_t largeTriCapacity, largeItemCapacity; void* largeItems;
+    unsigned long long* stats;   // device chord_raster_stats
+    // resolve
+    uint32_t* tileMarker; uint32_t* tileList; uint32_t* tileCount; float* gbuffer[CHORD_GBUF_COUNT];
+    chord_PerframeCameraView hView;   // host copy
+    bool begun;
+};
+
+namespace chordb {
+FrameDev make_frame_dev(const chord_frame* f);
+// kernels' host launchers (each returns a CHORD_* status)
+int launch_object_prepare(chord_frame* f);
+int launch_instance_culling(chord_frame* f, chord_cmdlist* out);
+int launch_hzb_culling(chord_frame* f, const chord_hzb* hzb, int firstStage, chord_cmdlist* in, chord_cmdlist* outVis, chord_cmdlist* outRej);
+int launch_render_mesh(chord_frame* f, chord_cmdlist* list);
+int launch_build_hzb(chord_frame* f, int bMin, int bMax, int bRange, chord_hzb* dst);
+int launch_visibility_mark(chord_frame* f, chord_cmdlist* post);
+int launch_lighting(chord_frame* f, chord_cmdlist* post);
+int launch_split_vis(chord_frame* f, uint32_t* vis32, float* depth32);
+int launch_decode(chord_frame* f, chord_cmdlist* post, uint32_t* triples);
+int scan_reset(chord_ctx* ctx, uint32_t tilesNeeded);
+}

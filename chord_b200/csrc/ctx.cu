@@ -1,0 +1,521 @@
+// ctx.cu — context / scene / list / HZB / frame objects and the C-ABI entry points of libchord_b200.
+// Host-side only; every pass body lives in cull.cu / raster.cu / hzb.cu / resolve.cu.
+#include "common.cuh"
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+namespace chordb {
+
+static thread_local char g_error[512] = "";
+
+void set_error(const char* fmt, ...)
+{
+    va_list ap; va_start(ap, fmt);
+    vsnprintf(g_error, sizeof(g_error), fmt, ap);
+    va_end(ap);
+}
+
+FrameDev make_frame_dev(const chord_frame* f)
+{
+    FrameDev d;
+    d.scene = f->ctx->scene;
+    d.view = f->dView; d.iview = f->dIView; d.objects = f->dObjects; d.derived = f->dDerived;
+    d.objectCount = f->objectCount;
+    d.width = f->width; d.height = f->height; d.tile = f->tile;
+    d.switchFlags = f->ctx->switchFlags;
+    d.tanHalfFovy = f->tanHalfFovy;
+    d.vis64 = f->vis64;
+    return d;
+}
+
+int scan_reset(chord_ctx* ctx, uint32_t tilesNeeded)
+{
+    if (tilesNeeded > ctx->scanTiles) {
+        if (ctx->scanStatus) cudaFree(ctx->scanStatus);
+        ctx->scanStatus = nullptr; ctx->scanTiles = 0;
+        uint32_t n = tilesNeeded + 1024;
+        CHORD_CUDA(cudaMalloc(&ctx->scanStatus, sizeof(unsigned long long) * n));
+        ctx->scanTiles = n;
+    }
+    CHORD_CUDA(cudaMemsetAsync(ctx->scanStatus, 0, sizeof(unsigned long long) * (size_t)(tilesNeeded + 1), ctx->stream));
+    CHORD_CUDA(cudaMemsetAsync(ctx->scanTicket, 0, sizeof(uint32_t), ctx->stream));
+    return CHORD_OK;
+}
+
+template <typename T>
+static int upload(chord_ctx* ctx, std::vector<void*>& allocs, const T* host, size_t count, const T** out, size_t padBytes = 64)
+{
+    *out = nullptr;
+    if (!host || count == 0) return CHORD_OK;
+    void* d = nullptr;
+    const size_t bytes = sizeof(T) * count;
+    CHORD_CUDA(cudaMalloc(&d, bytes + padBytes));                 // pad: kernels may read aligned supersets
+    CHORD_CUDA(cudaMemsetAsync((char*)d + bytes, 0, padBytes, ctx->stream));
+    CHORD_CUDA(cudaMemcpyAsync(d, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    allocs.push_back(d);
+    *out = (const T*)d;
+    return CHORD_OK;
+}
+
+static void free_scene(chord_ctx* ctx)
+{
+    for (uint32_t i = 0; i < ctx->nSceneAllocs; i++) cudaFree(ctx->sceneAllocs[i]);
+    free(ctx->sceneAllocs); ctx->sceneAllocs = nullptr; ctx->nSceneAllocs = 0;
+    free(ctx->datasHost); ctx->datasHost = nullptr;
+    memset(&ctx->scene, 0, sizeof(ctx->scene));
+}
+
+}  // namespace chordb
+
+using namespace chordb;
+
+extern "C" {
+
+const char* chord_last_error(void) { return g_error; }
+int chord_abi_version(void) { return CHORD_B200_ABI_VERSION; }
+
+int chord_ctx_create(int device, chord_ctx** out)
+{
+    CHORD_REQUIRE(out != nullptr, "out");
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) { set_error("no CUDA device visible"); return CHORD_ERR_NO_DEVICE; }
+    CHORD_REQUIRE(device >= 0 && device < n, "device index");
+    CHORD_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CHORD_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) { set_error("libchord_b200 is built for sm_100a only; device is sm_%d%d", prop.major, prop.minor); return CHORD_ERR_NO_DEVICE; }
+    chord_ctx* c = (chord_ctx*)calloc(1, sizeof(chord_ctx));
+    c->device = device;
+    c->switchFlags = 0b111;
+    c->smCount = prop.multiProcessorCount;
+    CHORD_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CHORD_CUDA(cudaMalloc(&c->scanTicket, sizeof(uint32_t)));
+    *out = c;
+    return CHORD_OK;
+}
+
+void chord_ctx_destroy(chord_ctx* ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    free_scene(ctx);
+    if (ctx->scanStatus) cudaFree(ctx->scanStatus);
+    if (ctx->scanTicket) cudaFree(ctx->scanTicket);
+    if (ctx->lutTransmittance) cudaFree(ctx->lutTransmittance);
+    if (ctx->lutIrradiance) cudaFree(ctx->lutIrradiance);
+    cudaStreamDestroy(ctx->stream);
+    free(ctx);
+}
+
+void* chord_ctx_stream(chord_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+int chord_ctx_sync(chord_ctx* ctx)
+{
+    CHORD_REQUIRE(ctx, "ctx");
+    CHORD_CUDA(cudaStreamSynchronize(ctx->stream));
+    return CHORD_OK;
+}
+int chord_ctx_set_switch_flags(chord_ctx* ctx, uint32_t f) { CHORD_REQUIRE(ctx, "ctx"); ctx->switchFlags = f & 7u; return CHORD_OK; }
+uint32_t chord_ctx_get_switch_flags(const chord_ctx* ctx) { return ctx ? ctx->switchFlags : 0; }
+uint64_t chord_ctx_kernel_launches(const chord_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int chord_scene_upload(chord_ctx* ctx, const chord_scene_desc* desc)
+{
+    CHORD_REQUIRE(ctx && desc, "null");
+    CHORD_REQUIRE(desc->datasCount > 0 && desc->primitiveCount > 0 && desc->materialCount > 0, "empty scene");
+    CHORD_CUDA(cudaSetDevice(ctx->device));
+    CHORD_CUDA(cudaStreamSynchronize(ctx->stream));
+    free_scene(ctx);
+    std::vector<void*> allocs;
+    ctx->datasHost = (DatasDev*)calloc(desc->datasCount, sizeof(DatasDev));
+    int rc = CHORD_OK;
+    for (uint32_t i = 0; i < desc->datasCount && rc == CHORD_OK; i++) {
+        const chord_primitive_datas_desc& d = desc->datas[i];
+        DatasDev& o = ctx->datasHost[i];
+        if (!d.meshlets || !d.positions || !d.meshletData || !d.groups || !d.groupIndices) { set_error("datas[%u]: missing required array", i); rc = CHORD_ERR_INVALID; break; }
+        if ((rc = upload(ctx, allocs, d.meshlets, d.meshletCount, &o.meshlets))) break;
+        if ((rc = upload(ctx, allocs, d.positions, (size_t)d.vertexCount * 3, &o.positions))) break;
+        if ((rc = upload(ctx, allocs, d.normals, (size_t)d.vertexCount * 3, &o.normals))) break;
+        if ((rc = upload(ctx, allocs, d.uv0, (size_t)d.vertexCount * 2, &o.uv0))) break;
+        if ((rc = upload(ctx, allocs, d.tangents, (size_t)d.vertexCount * 4, &o.tangents))) break;
+        if ((rc = upload(ctx, allocs, d.meshletData, d.meshletDataCount, &o.meshletData))) break;
+        if ((rc = upload(ctx, allocs, d.groups, d.groupCount, &o.groups))) break;
+        if ((rc = upload(ctx, allocs, d.groupIndices, d.groupIndicesCount, &o.groupIndices))) break;
+        if ((rc = upload(ctx, allocs, d.bvhNodes, d.bvhNodeCount, &o.bvhNodes))) break;
+    }
+    if (rc == CHORD_OK) rc = upload(ctx, allocs, ctx->datasHost, desc->datasCount, &ctx->scene.datas);
+    if (rc == CHORD_OK) rc = upload(ctx, allocs, desc->primitives, desc->primitiveCount, &ctx->scene.prims);
+    if (rc == CHORD_OK) rc = upload(ctx, allocs, desc->materials, desc->materialCount, &ctx->scene.mats);
+    ctx->scene.nDatas = desc->datasCount; ctx->scene.nPrims = desc->primitiveCount; ctx->scene.nMats = desc->materialCount;
+    ctx->sceneAllocs = (void**)malloc(sizeof(void*) * (allocs.size() + 1));
+    ctx->nSceneAllocs = (uint32_t)allocs.size();
+    for (size_t i = 0; i < allocs.size(); i++) ctx->sceneAllocs[i] = allocs[i];
+    if (rc != CHORD_OK) { free_scene(ctx); return rc; }
+    CHORD_CUDA(cudaStreamSynchronize(ctx->stream));
+    return CHORD_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- cmd lists
+int chord_cmdlist_create(chord_ctx* ctx, uint32_t capacity, chord_cmdlist** out)
+{
+    CHORD_REQUIRE(ctx && out, "null");
+    CHORD_REQUIRE(capacity > 0, "capacity");
+    CHORD_CUDA(cudaSetDevice(ctx->device));
+    chord_cmdlist* l = (chord_cmdlist*)calloc(1, sizeof(chord_cmdlist));
+    l->ctx = ctx; l->capacity = capacity;
+    CHORD_CUDA(cudaMalloc(&l->count, 16));
+    CHORD_CUDA(cudaMalloc(&l->cmds, sizeof(chord_draw_cmd) * (size_t)capacity + 64));
+    CHORD_CUDA(cudaMemsetAsync(l->count, 0, 16, ctx->stream));
+    *out = l;
+    return CHORD_OK;
+}
+void chord_cmdlist_destroy(chord_cmdlist* l)
+{
+    if (!l) return;
+    cudaStreamSynchronize(l->ctx->stream);
+    cudaFree(l->count); cudaFree(l->cmds); free(l);
+}
+int chord_cmdlist_upload(chord_cmdlist* l, const chord_draw_cmd* host, uint32_t count)
+{
+    CHORD_REQUIRE(l && (host || count == 0), "null");
+    if (count > l->capacity) { set_error("cmdlist upload: %u > capacity %u", count, l->capacity); return CHORD_ERR_CAPACITY; }
+    CHORD_CUDA(cudaMemcpyAsync(l->count, &count, 4, cudaMemcpyHostToDevice, l->ctx->stream));
+    if (count) CHORD_CUDA(cudaMemcpyAsync(l->cmds, host, sizeof(chord_draw_cmd) * (size_t)count, cudaMemcpyHostToDevice, l->ctx->stream));
+    CHORD_CUDA(cudaStreamSynchronize(l->ctx->stream));
+    return CHORD_OK;
+}
+int chord_cmdlist_readback(chord_cmdlist* l, chord_draw_cmd* host, uint32_t hostCapacity, uint32_t* outCount)
+{
+    CHORD_REQUIRE(l && outCount, "null");
+    uint32_t n = 0;
+    CHORD_CUDA(cudaMemcpyAsync(&n, l->count, 4, cudaMemcpyDeviceToHost, l->ctx->stream));
+    CHORD_CUDA(cudaStreamSynchronize(l->ctx->stream));
+    *outCount = n;
+    if (n > l->capacity) { set_error("cmdlist overflowed on device: %u > capacity %u", n, l->capacity); return CHORD_ERR_CAPACITY; }
+    uint32_t m = n < hostCapacity ? n : hostCapacity;
+    if (host && m) {
+        CHORD_CUDA(cudaMemcpyAsync(host, l->cmds, sizeof(chord_draw_cmd) * (size_t)m, cudaMemcpyDeviceToHost, l->ctx->stream));
+        CHORD_CUDA(cudaStreamSynchronize(l->ctx->stream));
+    }
+    return CHORD_OK;
+}
+uint32_t chord_cmdlist_capacity(const chord_cmdlist* l) { return l ? l->capacity : 0; }
+void* chord_cmdlist_count_ptr(chord_cmdlist* l) { return l ? l->count : nullptr; }
+void* chord_cmdlist_cmds_ptr(chord_cmdlist* l) { return l ? l->cmds : nullptr; }
+
+// ---------------------------------------------------------------------------------------------- HZB objects
+static uint32_t next_pot(uint32_t v) { uint32_t p = 1; while (p < v) p <<= 1; return p; }
+
+int chord_hzb_create(chord_ctx* ctx, uint32_t depthW, uint32_t depthH, chord_hzb** out)
+{
+    CHORD_REQUIRE(ctx && out, "null");
+    CHORD_REQUIRE(depthW >= CHORD_MIN_RENDER_DIM && depthH >= CHORD_MIN_RENDER_DIM && depthW <= CHORD_MAX_RENDER_DIM && depthH <= CHORD_MAX_RENDER_DIM, "render dimension outside [64, 4096] (renderer.h:52-53)");
+    CHORD_CUDA(cudaSetDevice(ctx->device));
+    chord_hzb* h = (chord_hzb*)calloc(1, sizeof(chord_hzb));
+    h->ctx = ctx; h->depthW = depthW; h->depthH = depthH;
+    // hzb.cpp:49-56
+    uint32_t tw = next_pot(depthW) / 2, th = next_pot(depthH) / 2;
+    if (tw == depthW) tw /= 2;
+    if (th == depthH) th /= 2;
+    h->mip0W = tw; h->mip0H = th;
+    uint32_t mx = tw > th ? tw : th, mips = 1;
+    while (mx > 1) { mx >>= 1; mips++; }
+    h->mipCount = mips;
+    if (mips < 6 || mips > CHORD_HZB_MAX_MIP_COUNT) { set_error("hzb mip count %u outside [6,12] (hzb.cpp:119)", mips); free(h); return CHORD_ERR_INVALID; }
+    uint64_t o = 0;
+    for (uint32_t m = 0; m < mips; m++) {
+        h->mipOffset[m] = o;
+        uint32_t w = tw >> m, hh = th >> m; if (!w) w = 1; if (!hh) hh = 1;
+        o += (uint64_t)w * hh;
+    }
+    h->totalTexels = o;
+    CHORD_CUDA(cudaMalloc(&h->minChain, sizeof(__half) * o));
+    CHORD_CUDA(cudaMalloc(&h->maxChain, sizeof(__half) * o));
+    CHORD_CUDA(cudaMalloc(&h->validRange, 16));
+    CHORD_CUDA(cudaMalloc(&h->counter, 16));
+    CHORD_CUDA(cudaMemsetAsync(h->minChain, 0, sizeof(__half) * o, ctx->stream));
+    CHORD_CUDA(cudaMemsetAsync(h->maxChain, 0, sizeof(__half) * o, ctx->stream));
+    *out = h;
+    return CHORD_OK;
+}
+void chord_hzb_destroy(chord_hzb* h)
+{
+    if (!h) return;
+    cudaStreamSynchronize(h->ctx->stream);
+    cudaFree(h->minChain); cudaFree(h->maxChain); cudaFree(h->validRange); cudaFree(h->counter); free(h);
+}
+int chord_hzb_info(const chord_hzb* h, uint32_t* w, uint32_t* hh, uint32_t* mips, uint32_t* vw, uint32_t* vh)
+{
+    CHORD_REQUIRE(h, "null");
+    if (w) *w = h->mip0W; if (hh) *hh = h->mip0H; if (mips) *mips = h->mipCount;
+    if (vw) *vw = h->depthW / 2; if (vh) *vh = h->depthH / 2;       // hzb.cpp:151 mip0ValidArea
+    return CHORD_OK;
+}
+int chord_hzb_readback(chord_hzb* h, int which, uint32_t mip, uint16_t* host)
+{
+    CHORD_REQUIRE(h && host, "null");
+    CHORD_REQUIRE(mip < h->mipCount, "mip");
+    uint32_t w = h->mip0W >> mip, hh = h->mip0H >> mip; if (!w) w = 1; if (!hh) hh = 1;
+    const __half* src = (which ? h->maxChain : h->minChain) + h->mipOffset[mip];
+    CHORD_CUDA(cudaMemcpyAsync(host, src, sizeof(__half) * (size_t)w * hh, cudaMemcpyDeviceToHost, h->ctx->stream));
+    CHORD_CUDA(cudaStreamSynchronize(h->ctx->stream));
+    return CHORD_OK;
+}
+int chord_hzb_readback_valid_range(chord_hzb* h, uint32_t out[2])
+{
+    CHORD_REQUIRE(h && out, "null");
+    CHORD_CUDA(cudaMemcpyAsync(out, h->validRange, 8, cudaMemcpyDeviceToHost, h->ctx->stream));
+    CHORD_CUDA(cudaStreamSynchronize(h->ctx->stream));
+    return CHORD_OK;
+}
+void* chord_hzb_chain_ptr(chord_hzb* h, int which) { return h ? (void*)(which ? h->maxChain : h->minChain) : nullptr; }
+uint64_t chord_hzb_chain_bytes(const chord_hzb* h) { return h ? h->totalTexels * sizeof(__half) : 0; }
+uint64_t chord_hzb_mip_offset(const chord_hzb* h, uint32_t mip) { return (h && mip < h->mipCount) ? h->mipOffset[mip] * sizeof(__half) : 0; }
+int chord_hzb_set_valid(chord_hzb* h, int v) { CHORD_REQUIRE(h, "null"); h->valid = v; return CHORD_OK; }
+int chord_hzb_is_valid(const chord_hzb* h) { return h ? h->valid : 0; }
+
+// ---------------------------------------------------------------------------------------------- frames
+static const uint32_t kLargeTriCapacity = 1u << 18;      // 256 k queued large triangles per render_mesh call
+static const uint32_t kLargeItemCapacity = 1u << 22;     // 4 M (triangle, tile-row) work items
+
+int chord_frame_create(chord_ctx* ctx, uint32_t width, uint32_t height, chord_frame** out)
+{
+    CHORD_REQUIRE(ctx && out, "null");
+    CHORD_REQUIRE(width >= CHORD_MIN_RENDER_DIM && height >= CHORD_MIN_RENDER_DIM && width <= CHORD_MAX_RENDER_DIM && height <= CHORD_MAX_RENDER_DIM, "render dimension outside [64, 4096] (renderer.h:52-53)");
+    CHORD_CUDA(cudaSetDevice(ctx->device));
+    chord_frame* f = (chord_frame*)calloc(1, sizeof(chord_frame));
+    f->ctx = ctx; f->width = width; f->height = height;
+    f->tile = chord_rect{0, 0, width, height};
+    CHORD_CUDA(cudaMalloc(&f->vis64, sizeof(unsigned long long) * (size_t)width * height));
+    CHORD_CUDA(cudaMalloc(&f->dView, sizeof(chord_PerframeCameraView)));
+    CHORD_CUDA(cudaMalloc(&f->dIView, sizeof(chord_InstanceCullingViewInfo)));
+    CHORD_CUDA(cudaMalloc(&f->totalGroups, 16));
+    f->largeTriCapacity = kLargeTriCapacity; f->largeItemCapacity = kLargeItemCapacity;
+    CHORD_CUDA(cudaMalloc(&f->largeTris, (size_t)48 * f->largeTriCapacity));
+    CHORD_CUDA(cudaMalloc(&f->largeItems, (size_t)8 * f->largeItemCapacity));
+    CHORD_CUDA(cudaMalloc(&f->largeCounters, 64));
+    CHORD_CUDA(cudaMalloc(&f->stats, sizeof(chord_raster_stats)));
+    CHORD_CUDA(cudaMemsetAsync(f->stats, 0, sizeof(chord_raster_stats), ctx->stream));
+    CHORD_CUDA(cudaMemsetAsync(f->largeCounters, 0, 64, ctx->stream));
+    const uint32_t mw = (width + 7) / 8, mh = (height + 7) / 8;
+    CHORD_CUDA(cudaMalloc(&f->tileMarker, (size_t)16 * mw * mh));
+    CHORD_CUDA(cudaMalloc(&f->tileList, (size_t)8 * mw * mh));
+    CHORD_CUDA(cudaMalloc(&f->tileCount, 16));
+    *out = f;
+    return CHORD_OK;
+}
+
+void chord_frame_destroy(chord_frame* f)
+{
+    if (!f) return;
+    cudaStreamSynchronize(f->ctx->stream);
+    cudaFree(f->vis64); cudaFree(f->dView); cudaFree(f->dIView); cudaFree(f->dObjects); cudaFree(f->dDerived);
+    cudaFree(f->objGroupCount); cudaFree(f->objGroupBase); cudaFree(f->totalGroups);
+    cudaFree(f->largeTris); cudaFree(f->largeItems); cudaFree(f->largeCounters); cudaFree(f->stats);
+    cudaFree(f->tileMarker); cudaFree(f->tileList); cudaFree(f->tileCount);
+    for (int i = 0; i < CHORD_GBUF_COUNT; i++) cudaFree(f->gbuffer[i]);
+    free(f);
+}
+
+int chord_frame_begin(chord_frame* f, const chord_PerframeCameraView* view, const chord_InstanceCullingViewInfo* iview,
+                      const chord_GPUObjectGLTFPrimitive* objects, uint32_t objectCount,
+                      uint32_t lod0MeshletCount, uint32_t meshletGroupCount, const chord_rect* tile)
+{
+    CHORD_REQUIRE(f && view && iview && objects, "null");
+    CHORD_REQUIRE(objectCount > 0, "objectCount (shouldRenderGLTF, mesh_raster.cpp:45-48)");
+    CHORD_REQUIRE(lod0MeshletCount > 0 && meshletGroupCount > 0, "lod0MeshletCount/meshletGroupCount (instance_culling.cpp:108)");
+    CHORD_REQUIRE(f->ctx->scene.datas != nullptr, "no scene uploaded");
+    CHORD_REQUIRE((uint32_t)view->renderDimension.x == f->width && (uint32_t)view->renderDimension.y == f->height, "view.renderDimension != frame size");
+    chord_ctx* ctx = f->ctx;
+    CHORD_CUDA(cudaSetDevice(ctx->device));
+    if (tile) {
+        CHORD_REQUIRE(tile->x0 < tile->x1 && tile->y0 < tile->y1 && tile->x1 <= f->width && tile->y1 <= f->height, "tile rect");
+        f->tile = *tile;
+    } else {
+        f->tile = chord_rect{0, 0, f->width, f->height};
+    }
+    if (objectCount > f->objectCapacity) {
+        cudaFree(f->dObjects); cudaFree(f->dDerived); cudaFree(f->objGroupCount); cudaFree(f->objGroupBase);
+        f->dObjects = nullptr; f->dDerived = nullptr; f->objGroupCount = nullptr; f->objGroupBase = nullptr; f->objectCapacity = 0;
+        uint32_t cap = objectCount + objectCount / 4 + 16;
+        CHORD_CUDA(cudaMalloc(&f->dObjects, sizeof(chord_GPUObjectGLTFPrimitive) * (size_t)cap));
+        CHORD_CUDA(cudaMalloc(&f->dDerived, sizeof(ObjectDerived) * (size_t)cap));
+        CHORD_CUDA(cudaMalloc(&f->objGroupCount, sizeof(uint32_t) * (size_t)(cap + 1)));
+        CHORD_CUDA(cudaMalloc(&f->objGroupBase, sizeof(uint32_t) * (size_t)(cap + 1)));
+        f->objectCapacity = cap;
+    }
+    f->objectCount = objectCount;
+    f->lod0MeshletCount = lod0MeshletCount; f->meshletGroupCount = meshletGroupCount;
+    f->hView = *view;
+    f->tanHalfFovy = tanf(0.5f * view->cameraFovy);
+    CHORD_CUDA(cudaMemcpyAsync(f->dView, view, sizeof(*view), cudaMemcpyHostToDevice, ctx->stream));
+    CHORD_CUDA(cudaMemcpyAsync(f->dIView, iview, sizeof(*iview), cudaMemcpyHostToDevice, ctx->stream));
+    CHORD_CUDA(cudaMemcpyAsync(f->dObjects, objects, sizeof(chord_GPUObjectGLTFPrimitive) * (size_t)objectCount, cudaMemcpyHostToDevice, ctx->stream));
+    // addClearGbufferPass (render_textures.cpp:74-102): visibility = 0, depth = 0.0 -> packed texel 0
+    CHORD_CUDA(cudaMemsetAsync(f->vis64, 0, sizeof(unsigned long long) * (size_t)f->width * f->height, ctx->stream));
+    f->begun = true;
+    return launch_object_prepare(f);
+}
+
+int chord_instance_culling(chord_frame* f, chord_cmdlist* out)
+{
+    CHORD_REQUIRE(f && out && f->begun, "frame not begun");
+    return launch_instance_culling(f, out);
+}
+
+int chord_hzb_culling(chord_frame* f, const chord_hzb* hzb, int firstStage, chord_cmdlist* in, chord_cmdlist* outVisible, chord_cmdlist* outRejected)
+{
+    CHORD_REQUIRE(f && hzb && in && outVisible && f->begun, "null / frame not begun");
+    CHORD_REQUIRE(!firstStage || outRejected, "phase 0 needs a rejected list");
+    CHORD_REQUIRE(hzb->depthW == f->width && hzb->depthH == f->height, "hzb built for another render dimension");
+    CHORD_REQUIRE(outVisible->capacity >= in->capacity && (!outRejected || outRejected->capacity >= in->capacity), "output list capacity");
+    return launch_hzb_culling(f, hzb, firstStage, in, outVisible, firstStage ? outRejected : nullptr);
+}
+
+int chord_render_mesh(chord_frame* f, chord_cmdlist* list)
+{
+    CHORD_REQUIRE(f && list && f->begun, "null / frame not begun");
+    return launch_render_mesh(f, list);
+}
+
+int chord_visibility_stage0(chord_frame* f, const chord_hzb* lastFrameHzb, chord_cmdlist* in, chord_cmdlist* scratchVisible,
+                            chord_cmdlist* outRejected, int* needStage1)
+{
+    CHORD_REQUIRE(f && in && needStage1 && f->begun, "null / frame not begun");
+    *needStage1 = 0;
+    // mesh_raster.cpp:291-309: hzbCtx.isValid() && enableGLTFHZBCulling()
+    if (lastFrameHzb && lastFrameHzb->valid && (f->ctx->switchFlags & (1u << CHORD_FLAG_HZB_CULL_BIT))) {
+        CHORD_REQUIRE(scratchVisible && outRejected, "stage 0 with HZB needs scratch and rejected lists");
+        *needStage1 = 1;
+        int rc = chord_hzb_culling(f, lastFrameHzb, 1, in, scratchVisible, outRejected);
+        if (rc) return rc;
+        return launch_render_mesh(f, scratchVisible);
+    }
+    return launch_render_mesh(f, in);
+}
+
+int chord_visibility_stage1(chord_frame* f, const chord_hzb* thisFrameHzb, chord_cmdlist* rejected, chord_cmdlist* scratchVisible)
+{
+    CHORD_REQUIRE(f && thisFrameHzb && rejected && scratchVisible && f->begun, "null / frame not begun");
+    int rc = chord_hzb_culling(f, thisFrameHzb, 0, rejected, scratchVisible, nullptr);
+    if (rc) return rc;
+    return launch_render_mesh(f, scratchVisible);
+}
+
+int chord_build_hzb(chord_frame* f, int bMin, int bMax, int bValidRange, chord_hzb* dst)
+{
+    CHORD_REQUIRE(f && dst && f->begun, "null / frame not begun");
+    CHORD_REQUIRE(bMin || bMax, "at least one of min/max (hzb.cpp:44)");
+    CHORD_REQUIRE(!bValidRange || (bMin && bMax), "valid range needs min and max (hzb.cpp:47)");
+    CHORD_REQUIRE(dst->depthW == f->width && dst->depthH == f->height, "hzb created for another render dimension");
+    int rc = launch_build_hzb(f, bMin, bMax, bValidRange, dst);
+    if (rc == CHORD_OK) dst->valid = 1;
+    return rc;
+}
+
+int chord_visibility_mark(chord_frame* f, chord_cmdlist* post)
+{
+    CHORD_REQUIRE(f && post && f->begun, "null / frame not begun");
+    return launch_visibility_mark(f, post);
+}
+
+int chord_atmosphere_luts_upload(chord_ctx* ctx, const chord_atmosphere_luts* luts)
+{
+    CHORD_REQUIRE(ctx && luts && luts->transmittance && luts->irradiance, "null");
+    CHORD_CUDA(cudaSetDevice(ctx->device));
+    if (!ctx->lutTransmittance) CHORD_CUDA(cudaMalloc(&ctx->lutTransmittance, 256 * 64 * 4 * sizeof(__half)));
+    if (!ctx->lutIrradiance) CHORD_CUDA(cudaMalloc(&ctx->lutIrradiance, 64 * 16 * 4 * sizeof(__half)));
+    CHORD_CUDA(cudaMemcpyAsync(ctx->lutTransmittance, luts->transmittance, 256 * 64 * 4 * sizeof(__half), cudaMemcpyHostToDevice, ctx->stream));
+    CHORD_CUDA(cudaMemcpyAsync(ctx->lutIrradiance, luts->irradiance, 64 * 16 * 4 * sizeof(__half), cudaMemcpyHostToDevice, ctx->stream));
+    CHORD_CUDA(cudaStreamSynchronize(ctx->stream));
+    return CHORD_OK;
+}
+
+int chord_lighting(chord_frame* f, chord_cmdlist* post)
+{
+    CHORD_REQUIRE(f && post && f->begun, "null / frame not begun");
+    CHORD_REQUIRE(f->ctx->lutTransmittance && f->ctx->lutIrradiance, "atmosphere LUTs not uploaded");
+    return launch_lighting(f, post);
+}
+
+// ---------------------------------------------------------------------------------------------- read-backs
+int chord_readback_vis64(chord_frame* f, uint64_t* host)
+{
+    CHORD_REQUIRE(f && host, "null");
+    CHORD_CUDA(cudaMemcpyAsync(host, f->vis64, sizeof(uint64_t) * (size_t)f->width * f->height, cudaMemcpyDeviceToHost, f->ctx->stream));
+    CHORD_CUDA(cudaStreamSynchronize(f->ctx->stream));
+    return CHORD_OK;
+}
+
+static int readback_split(chord_frame* f, uint32_t* hostVis, float* hostDepth)
+{
+    const size_t n = (size_t)f->width * f->height;
+    uint32_t* dVis = nullptr; float* dDepth = nullptr;
+    CHORD_CUDA(cudaMallocAsync(&dVis, n * 4, f->ctx->stream));
+    CHORD_CUDA(cudaMallocAsync(&dDepth, n * 4, f->ctx->stream));
+    int rc = launch_split_vis(f, dVis, dDepth);
+    if (rc == CHORD_OK && hostVis) CHORD_CUDA(cudaMemcpyAsync(hostVis, dVis, n * 4, cudaMemcpyDeviceToHost, f->ctx->stream));
+    if (rc == CHORD_OK && hostDepth) CHORD_CUDA(cudaMemcpyAsync(hostDepth, dDepth, n * 4, cudaMemcpyDeviceToHost, f->ctx->stream));
+    CHORD_CUDA(cudaFreeAsync(dVis, f->ctx->stream));
+    CHORD_CUDA(cudaFreeAsync(dDepth, f->ctx->stream));
+    CHORD_CUDA(cudaStreamSynchronize(f->ctx->stream));
+    return rc;
+}
+int chord_readback_visibility32(chord_frame* f, uint32_t* host) { CHORD_REQUIRE(f && host, "null"); return readback_split(f, host, nullptr); }
+int chord_readback_depth32(chord_frame* f, float* host) { CHORD_REQUIRE(f && host, "null"); return readback_split(f, nullptr, host); }
+
+int chord_readback_decoded(chord_frame* f, chord_cmdlist* post, uint32_t* hostTriples)
+{
+    CHORD_REQUIRE(f && post && hostTriples, "null");
+    const size_t n = (size_t)f->width * f->height;
+    uint32_t* d = nullptr;
+    CHORD_CUDA(cudaMallocAsync(&d, n * 12, f->ctx->stream));
+    int rc = launch_decode(f, post, d);
+    if (rc == CHORD_OK) CHORD_CUDA(cudaMemcpyAsync(hostTriples, d, n * 12, cudaMemcpyDeviceToHost, f->ctx->stream));
+    CHORD_CUDA(cudaFreeAsync(d, f->ctx->stream));
+    CHORD_CUDA(cudaStreamSynchronize(f->ctx->stream));
+    return rc;
+}
+
+int chord_readback_tile_marker(chord_frame* f, uint32_t* host)
+{
+    CHORD_REQUIRE(f && host, "null");
+    const uint32_t mw = (f->width + 7) / 8, mh = (f->height + 7) / 8;
+    CHORD_CUDA(cudaMemcpyAsync(host, f->tileMarker, (size_t)16 * mw * mh, cudaMemcpyDeviceToHost, f->ctx->stream));
+    CHORD_CUDA(cudaStreamSynchronize(f->ctx->stream));
+    return CHORD_OK;
+}
+
+int chord_readback_gbuffer_f32(chord_frame* f, int which, float* host)
+{
+    CHORD_REQUIRE(f && host && which >= 0 && which < CHORD_GBUF_COUNT, "args");
+    CHORD_REQUIRE(f->gbuffer[which] != nullptr, "lighting has not run on this frame");
+    CHORD_CUDA(cudaMemcpyAsync(host, f->gbuffer[which], sizeof(float) * 4 * (size_t)f->width * f->height, cudaMemcpyDeviceToHost, f->ctx->stream));
+    CHORD_CUDA(cudaStreamSynchronize(f->ctx->stream));
+    return CHORD_OK;
+}
+
+void* chord_frame_vis64_ptr(chord_frame* f) { return f ? f->vis64 : nullptr; }
+int chord_frame_dims(const chord_frame* f, uint32_t* w, uint32_t* h) { CHORD_REQUIRE(f, "null"); if (w) *w = f->width; if (h) *h = f->height; return CHORD_OK; }
+
+int chord_frame_raster_stats(chord_frame* f, chord_raster_stats* out)
+{
+    CHORD_REQUIRE(f && out, "null");
+    CHORD_CUDA(cudaMemcpyAsync(out, f->stats, sizeof(*out), cudaMemcpyDeviceToHost, f->ctx->stream));
+    CHORD_CUDA(cudaStreamSynchronize(f->ctx->stream));
+    return CHORD_OK;
+}
+int chord_frame_reset_stats(chord_frame* f)
+{
+    CHORD_REQUIRE(f, "null");
+    CHORD_CUDA(cudaMemsetAsync(f->stats, 0, sizeof(chord_raster_stats), f->ctx->stream));
+    return CHORD_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,428 @@
+// cull.cu — cluster culling for the visibility-buffer path (sm_100a).
+//
+//   k_object_prepare     per-object derived matrices (what every HLSL thread recomputes with mul())
+//   k_object_cull        K1  instance_culling.hlsl:47-131   object OBB vs frustum -> group count
+//   k_object_scan        exclusive scan of the group counts (canonical object order replaces the InterlockedAdd)
+//   k_group_cull         K2  instance_culling.hlsl:133-208  LOD-DAG cut + cone/frustum per meshlet, ordered compaction
+//   k_hzb_cull<phase>    K3  hzb_mainview_culling.hlsl:35-213 two-phase HZB occlusion, ordered compaction x2
+//
+// All compactions are single-pass decoupled look-back scans (common.cuh) so that the output order is the
+// canonical (object, group, meshlet-in-group) order, fixing the reference's run-to-run nondeterministic slot ids
+//  while staying one pass over the data.
+#include "common.cuh"
+
+namespace chordb {
+
+constexpr int kCullBlock = 256;
+
+// ------------------------------------------------------------------------------------------------ helpers
+struct UVZ { float x, y, z; };
+
+// base.hlsli:161-171 projectPosToUVz
+__device__ __forceinline__ UVZ project_pos_to_uvz(const float* __restrict__ M, float px, float py, float pz)
+{
+    f4 h = mat_mul_vec(M, px, py, pz, 1.0f);
+    UVZ o;
+    o.x = __fmaf_rn(__fdiv_rn(h.x, h.w), 0.5f, 0.5f);
+    o.y = __fmaf_rn(__fdiv_rn(h.y, h.w), -0.5f, 0.5f);
+    o.z = __fdiv_rn(h.z, h.w);
+    return o;
+}
+
+// base.hlsli:275-305: true if culled
+__device__ bool frustum_culling(const chord_float4* __restrict__ planes, f3 c, f3 e, const float* __restrict__ l2w)
+{
+    f3 p[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        float x = __fmaf_rn(e.x, kExtentApplyFactor[k][0], c.x);
+        float y = __fmaf_rn(e.y, kExtentApplyFactor[k][1], c.y);
+        float z = __fmaf_rn(e.z, kExtentApplyFactor[k][2], c.z);
+        f4 w = mat_mul_vec(l2w, x, y, z, 1.0f);
+        p[k].x = w.x; p[k].y = w.y; p[k].z = w.z;
+    }
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+        const chord_float4 pl = planes[i];
+        bool allBack = true;
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+            if (dot3f(pl.x, pl.y, pl.z, p[j].x, p[j].y, p[j].z) > -pl.w) allBack = false;
+        if (allBack) return true;
+    }
+    return false;
+}
+
+// base.hlsli:248-272: true if culled
+__device__ bool ortho_frustum_culling(f3 c, f3 e, const float* __restrict__ localToClip)
+{
+    float mn0 = 10.0f, mn1 = 10.0f, mx0 = -10.0f, mx1 = -10.0f;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        float x = __fmaf_rn(e.x, kExtentApplyFactor[k][0], c.x);
+        float y = __fmaf_rn(e.y, kExtentApplyFactor[k][1], c.y);
+        float z = __fmaf_rn(e.z, kExtentApplyFactor[k][2], c.z);
+        UVZ u = project_pos_to_uvz(localToClip, x, y, z);
+        mn0 = fminf(mn0, u.x); mn1 = fminf(mn1, u.y);
+        mx0 = fmaxf(mx0, u.x); mx1 = fmaxf(mx1, u.y);
+    }
+    return (mn0 >= 1.0f) || (mn1 >= 1.0f) || (mx0 <= 0.0f) || (mx1 <= 0.0f);
+}
+
+// base.hlsli:500-518
+__device__ __forceinline__ float project_sphere_to_screen(float sx, float sy, float sz, float r, float height, float tanHalfFovy)
+{
+    const float d2 = dot3f(sx, sy, sz, sx, sy, sz);
+    const float r2 = __fmul_rn(r, r);
+    if (d2 <= r2) return -1.0f;
+    return __fdiv_rn(__fmul_rn(__fdiv_rn(__fmul_rn(height, 0.5f), tanHalfFovy), r), __fsqrt_rn(__fsub_rn(d2, r2)));
+}
+
+// nanite_shared.hlsli:15-49
+__device__ bool is_meshlet_group_visible(float renderHeight, float tanHalfFovy, float maxScale, const float* __restrict__ localToView,
+                                         const chord_GPUGLTFMeshletGroup& g)
+{
+    const bool bFinalLod = g.parentError > CHORD_ERROR_RADIUS_ROOT;
+    const bool bFirstLod = g.error < -0.5f;
+    if (!bFinalLod) {
+        f4 v = mat_mul_vec(localToView, g.parentPosCenter.x, g.parentPosCenter.y, g.parentPosCenter.z, 1.0f);
+        float pe = project_sphere_to_screen(v.x, v.y, v.z, __fmul_rn(maxScale, g.parentError), renderHeight, tanHalfFovy);
+        if (pe > 0.0f && pe <= CHORD_ERROR_PIXEL_THRESHOLD) return false;
+    }
+    if (!bFirstLod) {
+        f4 v = mat_mul_vec(localToView, g.clusterPosCenter.x, g.clusterPosCenter.y, g.clusterPosCenter.z, 1.0f);
+        float e = project_sphere_to_screen(v.x, v.y, v.z, __fmul_rn(maxScale, g.error), renderHeight, tanHalfFovy);
+        if (e < 0.0f || e > CHORD_ERROR_PIXEL_THRESHOLD) return false;
+    }
+    return true;
+}
+
+__device__ __forceinline__ void meshlet_center_extent(const chord_GPUGLTFMeshlet& m, bool halfFirst, f3& c, f3& e)
+{
+    if (halfFirst) {    // nanite_shared.hlsli:74: 0.5 * (posMin + posMax)
+        c.x = __fmul_rn(0.5f, __fadd_rn(m.posMin.x, m.posMax.x)); c.y = __fmul_rn(0.5f, __fadd_rn(m.posMin.y, m.posMax.y)); c.z = __fmul_rn(0.5f, __fadd_rn(m.posMin.z, m.posMax.z));
+    } else {            // hzb_mainview_culling.hlsl:67: (posMin + posMax) * 0.5  (same value: multiplication commutes)
+        c.x = __fmul_rn(__fadd_rn(m.posMin.x, m.posMax.x), 0.5f); c.y = __fmul_rn(__fadd_rn(m.posMin.y, m.posMax.y), 0.5f); c.z = __fmul_rn(__fadd_rn(m.posMin.z, m.posMax.z), 0.5f);
+    }
+    e.x = __fsub_rn(m.posMax.x, c.x); e.y = __fsub_rn(m.posMax.y, c.y); e.z = __fsub_rn(m.posMax.z, c.z);
+}
+
+// nanite_shared.hlsli:51-91
+__device__ bool is_meshlet_visible(uint32_t switchFlags, const chord_float4* __restrict__ planes, const chord_GPUObjectGLTFPrimitive& obj,
+                                   const float* __restrict__ localToClip, const chord_GPUGLTFMeshlet& m, uint32_t bTwoSided)
+{
+    bool visible = true;
+    if (bTwoSided == 0 && has_flag(switchFlags, CHORD_FLAG_CONE_CULL_BIT)) {
+        f4 cam = mat_mul_vec(obj.basicData.translatedWorldToLocal.m, 0.0f, 0.0f, 0.0f, 1.0f);
+        float vx = __fsub_rn(m.coneApex.x, cam.x), vy = __fsub_rn(m.coneApex.y, cam.y), vz = __fsub_rn(m.coneApex.z, cam.z);
+        float len = __fsqrt_rn(dot3f(vx, vy, vz, vx, vy, vz));
+        vx = __fdiv_rn(vx, len); vy = __fdiv_rn(vy, len); vz = __fdiv_rn(vz, len);
+        if (dot3f(vx, vy, vz, m.coneAxis.x, m.coneAxis.y, m.coneAxis.z) >= m.coneCutOff) visible = false;
+    }
+    if (visible && has_flag(switchFlags, CHORD_FLAG_FRUSTUM_CULL_BIT)) {
+        f3 c, e; meshlet_center_extent(m, true, c, e);
+        if (localToClip[15] == 1.0f) visible = !ortho_frustum_culling(c, e, localToClip);
+        else                         visible = !frustum_culling(planes, c, e, obj.basicData.localToTranslatedWorld.m);
+    }
+    return visible;
+}
+
+// ------------------------------------------------------------------------------------------------ per-object prepare
+__global__ void __launch_bounds__(64) k_object_prepare(FrameDev f, ObjectDerived* __restrict__ out)
+{
+    // one object per block, 64 threads = 4 matrices x 16 elements
+    const uint32_t o = blockIdx.x;
+    const uint32_t which = threadIdx.x >> 4, e = threadIdx.x & 15u, c = e >> 2, r = e & 3u;
+    const chord_GPUObjectGLTFPrimitive& obj = f.objects[o];
+    const float* A; const float* B; float* dst;
+    switch (which) {
+    case 0:  A = f.iview->translatedWorldToClip.m;          B = obj.basicData.localToTranslatedWorld.m;          dst = out[o].localToClip.m; break;
+    case 1:  A = f.view->translatedWorldToView.m;           B = obj.basicData.localToTranslatedWorld.m;          dst = out[o].localToView.m; break;
+    case 2:  A = f.view->translatedWorldToClipLastFrame.m;  B = obj.basicData.localToTranslatedWorldLastFrame.m; dst = out[o].localToClipHzb0.m; break;
+    default: A = f.view->translatedWorldToClip.m;           B = obj.basicData.localToTranslatedWorld.m;          dst = out[o].localToClipHzb1.m; break;
+    }
+    dst[c * 4 + r] = dot4f(A[r], A[4 + r], A[8 + r], A[12 + r], B[c * 4], B[c * 4 + 1], B[c * 4 + 2], B[c * 4 + 3]);
+}
+
+// ------------------------------------------------------------------------------------------------ K1
+__global__ void __launch_bounds__(128) k_object_cull(FrameDev f, uint32_t* __restrict__ groupCount)
+{
+    const uint32_t o = blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= f.objectCount) return;
+    const chord_GPUObjectGLTFPrimitive& obj = f.objects[o];
+    const chord_GLTFPrimitiveBuffer& prim = f.scene.prims[obj.GLTFPrimitiveDetail];
+    bool visible = true;
+    if (has_flag(f.switchFlags, CHORD_FLAG_FRUSTUM_CULL_BIT)) {
+        f3 c, e;
+        c.x = __fmul_rn(__fadd_rn(prim.posMin.x, prim.posMax.x), 0.5f); c.y = __fmul_rn(__fadd_rn(prim.posMin.y, prim.posMax.y), 0.5f); c.z = __fmul_rn(__fadd_rn(prim.posMin.z, prim.posMax.z), 0.5f);
+        e.x = __fsub_rn(prim.posMax.x, c.x); e.y = __fsub_rn(prim.posMax.y, c.y); e.z = __fsub_rn(prim.posMax.z, c.z);
+        const float* l2c = f.derived[o].localToClip.m;
+        if (l2c[15] == 1.0f) visible = !ortho_frustum_culling(c, e, l2c);
+        else                 visible = !frustum_culling(f.iview->frustumPlanesRS, c, e, obj.basicData.localToTranslatedWorld.m);
+    }
+    groupCount[o] = visible ? prim.meshletGroupCount : 0u;
+}
+
+// single block exclusive scan (object counts are small: hundreds to a few hundred thousand)
+__global__ void __launch_bounds__(1024) k_object_scan(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, uint32_t n, uint32_t* __restrict__ total)
+{
+    __shared__ uint32_t warpSums[32];
+    __shared__ uint32_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    for (uint32_t base = 0; base < n; base += 1024) {
+        const uint32_t i = base + threadIdx.x;
+        uint32_t v = (i < n) ? in[i] : 0u;
+        uint32_t s = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, s, o); if (lane >= (uint32_t)o) s += t; }
+        if (lane == 31) warpSums[warp] = s;
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t w = warpSums[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, w, o); if (lane >= (uint32_t)o) w += t; }
+            warpSums[lane] = w;
+        }
+        __syncthreads();
+        const uint32_t warpBase = warp ? warpSums[warp - 1] : 0u;
+        if (i < n) out[i] = carry + warpBase + s - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry += warpBase + s;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { *total = carry; out[n] = carry; }
+}
+
+// ------------------------------------------------------------------------------------------------ K2
+__global__ void __launch_bounds__(kCullBlock) k_group_cull(FrameDev f, const uint32_t* __restrict__ objGroupBase, const uint32_t* __restrict__ totalGroups,
+                                                           unsigned long long* __restrict__ scanStatus, uint32_t* __restrict__ ticket,
+                                                           chord_draw_cmd* __restrict__ outCmds, uint32_t* __restrict__ outCount, uint32_t outCapacity)
+{
+    __shared__ uint32_t sTile;
+    __shared__ uint32_t sWarp[kCullBlock / 32];
+    __shared__ uint32_t sBase;
+    const uint32_t total = *totalGroups;
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    while (true) {
+        __syncthreads();
+        if (threadIdx.x == 0) sTile = atomicAdd(ticket, 1u);
+        __syncthreads();
+        const uint32_t tile = sTile;
+        if ((unsigned long long)tile * kCullBlock >= total) break;
+        const uint32_t t = tile * kCullBlock + threadIdx.x;
+
+        uint32_t visCount = 0, visId[CHORD_CLUSTER_GROUP_MERGE_MAX], objectId = 0;
+        if (t < total) {
+            // canonical order: thread t <-> (object, group) through the scanned bases (binary search: last base <= t)
+            uint32_t lo = 0, hi = f.objectCount;
+            while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (objGroupBase[mid] <= t) lo = mid; else hi = mid; }
+            // skip culled objects that share the same base (count 0): lo is the last one with base <= t, which is the owner
+            objectId = lo;
+            const uint32_t groupId = t - objGroupBase[lo];
+            const chord_GPUObjectGLTFPrimitive& obj = f.objects[objectId];
+            const chord_GLTFPrimitiveBuffer& prim = f.scene.prims[obj.GLTFPrimitiveDetail];
+            const chord_GLTFMaterialGPUData& mat = f.scene.mats[obj.GLTFMaterialData];
+            const DatasDev& datas = f.scene.datas[prim.primitiveDatasBufferId];
+            const chord_GPUGLTFMeshletGroup g = datas.groups[prim.meshletGroupOffset + groupId];
+            const ObjectDerived& der = f.derived[objectId];
+            if (is_meshlet_group_visible(f.view->renderDimension.y, f.tanHalfFovy, obj.basicData.scaleExtractFromMatrix.w, der.localToView.m, g)) {
+                for (uint32_t i = 0; i < g.meshletCount && i < CHORD_CLUSTER_GROUP_MERGE_MAX; i++) {
+                    const uint32_t meshletIndex = prim.meshletOffset + datas.groupIndices[i + g.meshletOffset + prim.meshletGroupIndicesOffset];
+                    const chord_GPUGLTFMeshlet m = datas.meshlets[meshletIndex];
+                    if (is_meshlet_visible(f.switchFlags, f.iview->frustumPlanesRS, obj, der.localToClip.m, m, mat.bTwoSided))
+                        visId[visCount++] = meshletIndex;
+                }
+            }
+        }
+        // block exclusive scan of visCount
+        uint32_t s = visCount;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { uint32_t v = __shfl_up_sync(0xffffffffu, s, o); if (lane >= (uint32_t)o) s += v; }
+        if (lane == 31) sWarp[warp] = s;
+        __syncthreads();
+        uint32_t warpBase = 0, blockTotal = 0;
+#pragma unroll
+        for (int w = 0; w < kCullBlock / 32; w++) { uint32_t v = sWarp[w]; if (w < (int)warp) warpBase += v; blockTotal += v; }
+        if (warp == 0) {
+            unsigned long long ex = scan_tile_exclusive_prefix(scanStatus, tile, blockTotal);
+            if (lane == 0) {
+                sBase = (uint32_t)ex;
+                if ((unsigned long long)(tile + 1) * kCullBlock >= total) *outCount = (uint32_t)ex + blockTotal;   // last tile publishes the count
+            }
+        }
+        __syncthreads();
+        const uint32_t dst = sBase + warpBase + s - visCount;
+        for (uint32_t i = 0; i < visCount; i++) {
+            const uint32_t slot = dst + i;
+            if (slot < outCapacity) outCmds[slot] = chord_draw_cmd{objectId, visId[i], slot};
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ K3
+struct HzbDev {
+    const __half* minChain;
+    uint64_t mipOffset[CHORD_HZB_MAX_MIP_COUNT];
+    uint32_t mip0W, mip0H, mipCount;
+};
+
+template <bool kFirstStage>
+__global__ void __launch_bounds__(kCullBlock) k_hzb_cull(FrameDev f, HzbDev hzb,
+                                                         const chord_draw_cmd* __restrict__ inCmds, const uint32_t* __restrict__ inCount, uint32_t inCapacity,
+                                                         unsigned long long* __restrict__ scanStatus, uint32_t* __restrict__ ticket,
+                                                         chord_draw_cmd* __restrict__ outVis, uint32_t* __restrict__ outVisCount,
+                                                         chord_draw_cmd* __restrict__ outRej, uint32_t* __restrict__ outRejCount)
+{
+    __shared__ uint32_t sTile;
+    __shared__ uint32_t sWarpV[kCullBlock / 32], sWarpR[kCullBlock / 32];
+    __shared__ uint32_t sBaseV, sBaseR;
+    uint32_t total = *inCount; if (total > inCapacity) total = inCapacity;
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const float W = f.view->renderDimension.x, H = f.view->renderDimension.y;
+    while (true) {
+        __syncthreads();
+        if (threadIdx.x == 0) sTile = atomicAdd(ticket, 1u);
+        __syncthreads();
+        const uint32_t tile = sTile;
+        if ((unsigned long long)tile * kCullBlock >= total) break;
+        const uint32_t t = tile * kCullBlock + threadIdx.x;
+        bool active = t < total, visible = true;
+        chord_draw_cmd cmd = chord_draw_cmd{0, 0, 0};
+        if (active) {
+            cmd = inCmds[t];
+            if (has_flag(f.switchFlags, CHORD_FLAG_HZB_CULL_BIT)) {
+                const chord_GPUObjectGLTFPrimitive& obj = f.objects[cmd.objectId];
+                const chord_GLTFPrimitiveBuffer& prim = f.scene.prims[obj.GLTFPrimitiveDetail];
+                const DatasDev& datas = f.scene.datas[prim.primitiveDatasBufferId];
+                const chord_GPUGLTFMeshlet m = datas.meshlets[cmd.meshletId];
+                f3 c, e; meshlet_center_extent(m, false, c, e);
+                const float* mvp = kFirstStage ? f.derived[cmd.objectId].localToClipHzb0.m : f.derived[cmd.objectId].localToClipHzb1.m;
+                float mn0 = 10.0f, mn1 = 10.0f, mn2 = 10.0f, mx0 = -10.0f, mx1 = -10.0f, mx2 = -10.0f;
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    float x = __fmaf_rn(e.x, kExtentApplyFactor[i][0], c.x);
+                    float y = __fmaf_rn(e.y, kExtentApplyFactor[i][1], c.y);
+                    float z = __fmaf_rn(e.z, kExtentApplyFactor[i][2], c.z);
+                    UVZ u = project_pos_to_uvz(mvp, x, y, z);
+                    mn0 = fminf(mn0, u.x); mn1 = fminf(mn1, u.y); mn2 = fminf(mn2, u.z);
+                    mx0 = fmaxf(mx0, u.x); mx1 = fmaxf(mx1, u.y); mx2 = fmaxf(mx2, u.z);
+                }
+                const bool zInRange = (mx2 < 1.0f) && (mn2 > 0.0f);
+                if (zInRange && (mn0 >= 1.0f || mn1 >= 1.0f || mx0 <= 0.0f || mx1 <= 0.0f)) visible = false;
+                if (visible && zInRange) {
+                    const float u0 = fminf(fmaxf(mn0, 0.0f), 1.0f), v0 = fminf(fmaxf(mn1, 0.0f), 1.0f);
+                    const float u1 = fminf(fmaxf(mx0, 0.0f), 1.0f), v1 = fminf(fmaxf(mx1, 0.0f), 1.0f);
+                    int rx0 = __float2int_rz(__fmaf_rn(u0, W, 0.5f)), ry0 = __float2int_rz(__fmaf_rn(v0, H, 0.5f));
+                    int rx1 = __float2int_rz(__fmaf_rn(u1, W, -0.5f)), ry1 = __float2int_rz(__fmaf_rn(v1, H, -0.5f));
+                    rx0 = max(rx0, 0); ry0 = max(ry0, 0);
+                    rx1 = __float2int_rz(fminf(__fsub_rn(W, 1.0f), __int2float_rn(rx1)));
+                    ry1 = __float2int_rz(fminf(__fsub_rn(H, 1.0f), __int2float_rn(ry1)));
+                    if (rx1 < rx0 || ry1 < ry0) {
+                        visible = false;
+                    } else {
+                        const int hx0 = rx0 >> 1, hy0 = ry0 >> 1, hx1 = rx1 >> 1, hy1 = ry1 >> 1;
+                        const int dxv = hx1 - hx0, dyv = hy1 - hy0;
+                        const int mlx = dxv > 0 ? 31 - __clz(dxv) : -1, mly = dyv > 0 ? 31 - __clz(dyv) : -1;
+                        int mip = max(0, max(mlx, mly) - 1);
+                        if (((hx1 >> mip) - (hx0 >> mip) >= 4) || ((hy1 >> mip) - (hy0 >> mip) >= 4)) mip += 1;
+                        const int cx0 = hx0 >> mip, cy0 = hy0 >> mip, cx1 = hx1 >> mip, cy1 = hy1 >> mip;
+                        const uint32_t pitch = hzb.mip0W >> mip;
+                        const __half* mp = hzb.minChain + hzb.mipOffset[mip];
+                        float zMin = 10.0f;
+#pragma unroll
+                        for (int x = 0; x < 4; x++)
+#pragma unroll
+                            for (int y = 0; y < 4; y++) {
+                                const int sx = min(cx1, cx0 + x), sy = min(cy1, cy0 + y);
+                                zMin = fminf(zMin, __half2float(mp[(size_t)sy * pitch + (uint32_t)sx]));
+                            }
+                        if (zMin > mx2) visible = false;
+                    }
+                }
+            }
+        }
+        const uint32_t vbit = (active && visible) ? 1u : 0u;
+        const uint32_t rbit = (kFirstStage && active && !visible) ? 1u : 0u;
+        const uint32_t vmask = __ballot_sync(0xffffffffu, vbit), rmask = __ballot_sync(0xffffffffu, rbit);
+        const uint32_t lt = (1u << lane) - 1u;
+        if (lane == 0) { sWarpV[warp] = __popc(vmask); sWarpR[warp] = __popc(rmask); }
+        __syncthreads();
+        uint32_t baseV = 0, baseR = 0, totV = 0, totR = 0;
+#pragma unroll
+        for (int w = 0; w < kCullBlock / 32; w++) {
+            const uint32_t a = sWarpV[w], b = sWarpR[w];
+            if (w < (int)warp) { baseV += a; baseR += b; }
+            totV += a; totR += b;
+        }
+        if (warp == 0) {
+            unsigned long long ex = scan_tile_exclusive_prefix(scanStatus, tile, (unsigned long long)totV | ((unsigned long long)totR << 31));
+            if (lane == 0) {
+                sBaseV = (uint32_t)(ex & 0x7FFFFFFFull); sBaseR = (uint32_t)((ex >> 31) & 0x7FFFFFFFull);
+                if ((unsigned long long)(tile + 1) * kCullBlock >= total) {
+                    *outVisCount = sBaseV + totV;
+                    if (kFirstStage) *outRejCount = sBaseR + totR;
+                }
+            }
+        }
+        __syncthreads();
+        if (vbit) outVis[sBaseV + baseV + __popc(vmask & lt)] = cmd;
+        if (rbit) outRej[sBaseR + baseR + __popc(rmask & lt)] = cmd;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ launchers
+int launch_object_prepare(chord_frame* fr)
+{
+    chord_ctx* ctx = fr->ctx;
+    FrameDev f = make_frame_dev(fr);
+    k_object_prepare<<<fr->objectCount, 64, 0, ctx->stream>>>(f, fr->dDerived);
+    ctx->launches++;
+    CHORD_CUDA(cudaGetLastError());
+    return CHORD_OK;
+}
+
+int launch_instance_culling(chord_frame* fr, chord_cmdlist* out)
+{
+    chord_ctx* ctx = fr->ctx;
+    FrameDev f = make_frame_dev(fr);
+    const uint32_t tiles = (fr->meshletGroupCount + kCullBlock - 1) / kCullBlock + 1;
+    int rc = scan_reset(ctx, tiles);
+    if (rc) return rc;
+    CHORD_CUDA(cudaMemsetAsync(out->count, 0, 4, ctx->stream));
+    k_object_cull<<<(fr->objectCount + 127) / 128, 128, 0, ctx->stream>>>(f, fr->objGroupCount);
+    k_object_scan<<<1, 1024, 0, ctx->stream>>>(fr->objGroupCount, fr->objGroupBase, fr->objectCount, fr->totalGroups);
+    uint32_t grid = tiles < (uint32_t)ctx->smCount * 8u ? tiles : (uint32_t)ctx->smCount * 8u;
+    k_group_cull<<<grid, kCullBlock, 0, ctx->stream>>>(f, fr->objGroupBase, fr->totalGroups, ctx->scanStatus, ctx->scanTicket,
+                                                       out->cmds, out->count, out->capacity);
+    ctx->launches += 3;
+    CHORD_CUDA(cudaGetLastError());
+    return CHORD_OK;
+}
+
+int launch_hzb_culling(chord_frame* fr, const chord_hzb* hzb, int firstStage, chord_cmdlist* in, chord_cmdlist* outVis, chord_cmdlist* outRej)
+{
+    chord_ctx* ctx = fr->ctx;
+    FrameDev f = make_frame_dev(fr);
+    HzbDev h;
+    h.minChain = hzb->minChain; h.mip0W = hzb->mip0W; h.mip0H = hzb->mip0H; h.mipCount = hzb->mipCount;
+    for (int i = 0; i < CHORD_HZB_MAX_MIP_COUNT; i++) h.mipOffset[i] = hzb->mipOffset[i];
+    const uint32_t tiles = (in->capacity + kCullBlock - 1) / kCullBlock + 1;
+    int rc = scan_reset(ctx, tiles);
+    if (rc) return rc;
+    CHORD_CUDA(cudaMemsetAsync(outVis->count, 0, 4, ctx->stream));
+    if (outRej) CHORD_CUDA(cudaMemsetAsync(outRej->count, 0, 4, ctx->stream));
+    uint32_t grid = tiles < (uint32_t)ctx->smCount * 8u ? tiles : (uint32_t)ctx->smCount * 8u;
+    if (firstStage)
+        k_hzb_cull<true><<<grid, kCullBlock, 0, ctx->stream>>>(f, h, in->cmds, in->count, in->capacity, ctx->scanStatus, ctx->scanTicket,
+                                                               outVis->cmds, outVis->count, outRej->cmds, outRej->count);
+    else
+        k_hzb_cull<false><<<grid, kCullBlock, 0, ctx->stream>>>(f, h, in->cmds, in->count, in->capacity, ctx->scanStatus, ctx->scanTicket,
+                                                                outVis->cmds, outVis->count, nullptr, nullptr);
+    ctx->launches++;
+    CHORD_CUDA(cudaGetLastError());
+    return CHORD_OK;
+}
+
+}  // namespace chordb

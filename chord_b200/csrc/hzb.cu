@@ -1,0 +1,184 @@
+// hzb.cu — hierarchical-Z build (K8: hzb.hlsl:127-389, hzb_one.hlsl; host hzb.cpp:38-227) for sm_100a.
+//
+// Same single-pass shape as the reference: a 256-thread block reduces a 64x64 depth region to mips 0..5 through
+// shared memory, a device counter elects the last block which finishes mips 6.. from mip 5.  Depth comes from the
+// high word of the packed 64-bit visibility texels.  Storage is R16F: min is stored round-toward-zero (conservative
+// for reversed-Z, hzb.hlsl:69), max is stored RTZ for mips 0-4 and as half_bits(RTZ(v)) + 1 at mip 5 (hzb.hlsl:70),
+// with mips 6.. derived from the stored mip 5.  fp32->fp16 RTZ is monotonic, so reducing stored fp16 values equals
+// storing the fp32 reduction.
+#include "common.cuh"
+
+namespace chordb {
+
+struct HzbBuildParams {
+    const unsigned long long* vis64;
+    uint32_t width, height;
+    __half* minChain; __half* maxChain;     // either may be null
+    uint64_t mipOffset[CHORD_HZB_MAX_MIP_COUNT];
+    uint32_t mip0W, mip0H, mipCount;
+    uint32_t* validRange;                    // null unless requested
+    uint32_t* counter;
+    uint32_t numBlocks;
+    uint32_t blockX0, blockY0;               // first 64x64 block of the dispatched region (tile-restricted builds)
+    int finishTop;                           // run mips 6.. in the last block
+};
+
+__device__ __forceinline__ __half to_half_rtz(float v) { return __float2half_rz(v); }
+__device__ __forceinline__ __half half_plus_ulp(__half h) { return __ushort_as_half((unsigned short)(__half_as_ushort(h) + 1)); }
+
+__device__ __forceinline__ uint32_t mip_dim(uint32_t d0, uint32_t mip) { uint32_t d = d0 >> mip; return d ? d : 1u; }
+
+// mips 6.. from the stored mip 5; executed by one block
+__device__ void hzb_top_levels(const HzbBuildParams& p, float* __restrict__ sMinP, float* __restrict__ sMinQ,
+                               float* __restrict__ sMaxP, float* __restrict__ sMaxQ)
+{
+    if (p.mipCount <= 6) return;
+    uint32_t w = mip_dim(p.mip0W, 5), h = mip_dim(p.mip0H, 5);
+    for (uint32_t i = threadIdx.x; i < w * h; i += blockDim.x) {
+        if (p.minChain) sMinP[i] = __half2float(__ldcg(&p.minChain[p.mipOffset[5] + i]));
+        if (p.maxChain) sMaxP[i] = __half2float(__ldcg(&p.maxChain[p.mipOffset[5] + i]));
+    }
+    __syncthreads();
+    float* srcMin = sMinP; float* dstMin = sMinQ; float* srcMax = sMaxP; float* dstMax = sMaxQ;
+    for (uint32_t mip = 6; mip < p.mipCount; mip++) {
+        const uint32_t nw = mip_dim(p.mip0W, mip), nh = mip_dim(p.mip0H, mip);
+        for (uint32_t i = threadIdx.x; i < nw * nh; i += blockDim.x) {
+            const uint32_t x = i % nw, y = i / nw;
+            const uint32_t x0 = (w > 1) ? 2 * x : 0, x1 = (w > 1) ? 2 * x + 1 : 0, y0 = (h > 1) ? 2 * y : 0, y1 = (h > 1) ? 2 * y + 1 : 0;
+            if (p.minChain) {
+                const float v = fminf(fminf(fminf(srcMin[y0 * w + x0], srcMin[y0 * w + x1]), srcMin[y1 * w + x0]), srcMin[y1 * w + x1]);
+                dstMin[i] = v; p.minChain[p.mipOffset[mip] + i] = to_half_rtz(v);
+            }
+            if (p.maxChain) {
+                const float v = fmaxf(fmaxf(fmaxf(srcMax[y0 * w + x0], srcMax[y0 * w + x1]), srcMax[y1 * w + x0]), srcMax[y1 * w + x1]);
+                dstMax[i] = v; p.maxChain[p.mipOffset[mip] + i] = to_half_rtz(v);
+            }
+        }
+        __syncthreads();
+        float* t = srcMin; srcMin = dstMin; dstMin = t; t = srcMax; srcMax = dstMax; dstMax = t;
+        w = nw; h = nh;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_hzb_build(HzbBuildParams p)
+{
+    __shared__ float sMinP[4096], sMinQ[1024], sMaxP[4096], sMaxQ[1024];
+    __shared__ uint32_t sTicket;
+    const uint32_t bx = p.blockX0 + blockIdx.x, by = p.blockY0 + blockIdx.y;
+    const uint32_t tid = threadIdx.x;
+    const bool doMin = p.minChain != nullptr, doMax = p.maxChain != nullptr;
+
+    // ---- mip 0: 32x32 texels of this block, 4 per thread (hzb.hlsl:134-173)
+    float vMin = 10.0f, vMax = -10.0f;      // valid-range accumulators
+    for (uint32_t k = 0; k < 4; k++) {
+        const uint32_t l = tid + k * 256, lx = l & 31u, ly = l >> 5;
+        const uint32_t x = bx * 32 + lx, y = by * 32 + ly;
+        float mn = 0.0f, mx = 0.0f;
+#pragma unroll
+        for (int s = 0; s < 4; s++) {
+            const uint32_t sx = min(2 * x + (uint32_t)(s >> 1), p.width - 1), sy = min(2 * y + (uint32_t)(s & 1), p.height - 1);
+            const float d = __uint_as_float((uint32_t)(p.vis64[(size_t)sy * p.width + sx] >> 32));
+            if (s == 0) { mn = d; mx = d; } else { mn = fminf(mn, d); mx = fmaxf(mx, d); }
+            if (d > 0.0f) { vMax = fmaxf(vMax, d); vMin = fminf(vMin, d); }
+        }
+        sMinP[l] = mn; sMaxP[l] = mx;
+        if (x < p.mip0W && y < p.mip0H) {
+            const size_t o = p.mipOffset[0] + (size_t)y * p.mip0W + x;
+            if (doMin) p.minChain[o] = to_half_rtz(mn);
+            if (doMax) p.maxChain[o] = to_half_rtz(mx);
+        }
+    }
+    if (p.validRange) {
+        // hzb.hlsl:165-172: wave min/max, then InterlockedMin/Max on the raw bits with the <1 / >0 guards
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { vMin = fminf(vMin, __shfl_xor_sync(0xffffffffu, vMin, o)); vMax = fmaxf(vMax, __shfl_xor_sync(0xffffffffu, vMax, o)); }
+        if ((tid & 31u) == 0) {
+            if (vMin < 1.0f) atomicMin(&p.validRange[0], __float_as_uint(vMin));
+            if (vMax > 0.0f) atomicMax(&p.validRange[1], __float_as_uint(vMax));
+        }
+    }
+    __syncthreads();
+
+    // ---- mips 1..5 through shared memory (ping-pong P <-> Q)
+    float* srcMin = sMinP; float* dstMin = sMinQ; float* srcMax = sMaxP; float* dstMax = sMaxQ;
+    uint32_t w = 32;
+    for (uint32_t mip = 1; mip <= 5 && mip < p.mipCount; mip++) {
+        const uint32_t nw = w >> 1;
+        if (tid < nw * nw) {
+            const uint32_t lx = tid % nw, ly = tid / nw;
+            const uint32_t a = (2 * ly) * w + 2 * lx, b = a + 1, c = a + w, d = c + 1;
+            const float mn = fminf(fminf(fminf(srcMin[a], srcMin[b]), srcMin[c]), srcMin[d]);
+            const float mx = fmaxf(fmaxf(fmaxf(srcMax[a], srcMax[b]), srcMax[c]), srcMax[d]);
+            dstMin[tid] = mn; dstMax[tid] = mx;
+            const uint32_t mw = mip_dim(p.mip0W, mip), mh = mip_dim(p.mip0H, mip);
+            const uint32_t x = bx * nw + lx, y = by * nw + ly;
+            if (x < mw && y < mh) {
+                const size_t o = p.mipOffset[mip] + (size_t)y * mw + x;
+                if (doMin) p.minChain[o] = to_half_rtz(mn);
+                if (doMax) p.maxChain[o] = (mip == 5) ? half_plus_ulp(to_half_rtz(mx)) : to_half_rtz(mx);
+            }
+        }
+        __syncthreads();
+        float* t = srcMin; srcMin = dstMin; dstMin = t; t = srcMax; srcMax = dstMax; dstMax = t;
+        w = nw;
+    }
+    if (!p.finishTop || p.mipCount <= 6) return;
+
+    // ---- elect the last block (hzb.hlsl:289-300)
+    __threadfence();
+    if (tid == 0) sTicket = atomicAdd(p.counter, 1u);
+    __syncthreads();
+    if (sTicket != p.numBlocks - 1) return;
+    __threadfence();
+    hzb_top_levels(p, sMinP, sMinQ, sMaxP, sMaxQ);
+}
+
+__global__ void __launch_bounds__(256) k_hzb_top(HzbBuildParams p)
+{
+    __shared__ float sMinP[4096], sMinQ[1024], sMaxP[4096], sMaxQ[1024];
+    hzb_top_levels(p, sMinP, sMinQ, sMaxP, sMaxQ);
+}
+
+static HzbBuildParams make_params(chord_frame* fr, int bMin, int bMax, int bRange, chord_hzb* dst)
+{
+    HzbBuildParams p;
+    p.vis64 = fr->vis64; p.width = fr->width; p.height = fr->height;
+    p.minChain = bMin ? dst->minChain : nullptr; p.maxChain = bMax ? dst->maxChain : nullptr;
+    for (int i = 0; i < CHORD_HZB_MAX_MIP_COUNT; i++) p.mipOffset[i] = dst->mipOffset[i];
+    p.mip0W = dst->mip0W; p.mip0H = dst->mip0H; p.mipCount = dst->mipCount;
+    p.validRange = bRange ? dst->validRange : nullptr;
+    p.counter = dst->counter;
+    p.blockX0 = p.blockY0 = 0; p.finishTop = 1; p.numBlocks = 0;
+    return p;
+}
+
+int launch_build_hzb(chord_frame* fr, int bMin, int bMax, int bRange, chord_hzb* dst)
+{
+    chord_ctx* ctx = fr->ctx;
+    HzbBuildParams p = make_params(fr, bMin, bMax, bRange, dst);
+    const dim3 grid((dst->mip0W + 31) / 32, (dst->mip0H + 31) / 32);      // hzb.cpp:74
+    p.numBlocks = grid.x * grid.y;
+    CHORD_CUDA(cudaMemsetAsync(dst->counter, 0, 4, ctx->stream));
+    if (bRange) {
+        const uint32_t init[2] = { ~0u, 0u };                               // hzb.cpp:105-106
+        CHORD_CUDA(cudaMemcpyAsync(dst->validRange, init, 8, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    k_hzb_build<<<grid, 256, 0, ctx->stream>>>(p);
+    ctx->launches++;
+    CHORD_CUDA(cudaGetLastError());
+    return CHORD_OK;
+}
+
+}  // namespace chordb
+
+// Multi-GPU helper: after the mips 0..5 of every tile have been gathered into dst, rebuild mips 6...
+extern "C" int chord_hzb_finish_top(chord_frame* fr, int bMin, int bMax, chord_hzb* dst)
+{
+    using namespace chordb;
+    CHORD_REQUIRE(fr && dst, "null");
+    HzbBuildParams p = make_params(fr, bMin, bMax, 0, dst);
+    k_hzb_top<<<1, 256, 0, fr->ctx->stream>>>(p);
+    fr->ctx->launches++;
+    CHORD_CUDA(cudaGetLastError());
+    return CHORD_OK;
+}

@@ -1,0 +1,147 @@
+"""Host mirror of the reference's pass graph for the visibility-buffer path.
+
+Same free functions, same argument meaning and same sequencing as source/renderer (gltf_rendering.h:37-108,
+postprocessing.h:41-54, visibility_tile.h:22-34, lighting.h:37, renderer.cpp:311-363 + history at :489), with
+``GraphicsQueue&`` -> the context stream and pooled buffers/textures -> objects from a small pool.  Every pass is
+one call into libchord_b200.so; nothing is computed on the host.
+"""
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import abi, camera as cam
+from .runtime import CmdList, Context, Frame, Hzb
+
+
+class _Pool:
+    """getContext().getBufferPool()/getTexturePool() stand-in: reuse lists / HZBs of the same shape across frames."""
+
+    def __init__(self, ctx):
+        self.ctx = ctx
+        self.free_lists, self.free_hzb = {}, {}
+
+    def cmdlist(self, capacity):
+        b = self.free_lists.get(capacity)
+        return b.pop() if b else CmdList(self.ctx, capacity)
+
+    def hzb(self, w, h):
+        b = self.free_hzb.get((w, h))
+        return b.pop() if b else Hzb(self.ctx, w, h)
+
+    def release(self, obj):
+        if obj is None:
+            return
+        if isinstance(obj, CmdList):
+            self.free_lists.setdefault(obj.capacity, []).append(obj)
+        else:
+            self.free_hzb.setdefault((obj.width, obj.height), []).append(obj)
+
+
+@dataclass
+class GLTFRenderContext:
+    """gltf_rendering.h:15-35."""
+    frame: Frame
+    gltfObjectCount: int
+    lod0MeshletCount: int
+    meshletGroupCount: int
+    pool: _Pool
+    timers: list = field(default_factory=list)
+
+
+def shouldRenderGLTF(ctx: GLTFRenderContext):
+    """mesh_raster.cpp:45-48."""
+    return ctx.gltfObjectCount != 0
+
+
+def instanceCulling(ctx: GLTFRenderContext):
+    """instance_culling.cpp:83-161 -> CountAndCmdBuffer sized by lod0MeshletCount (:140-141)."""
+    if not shouldRenderGLTF(ctx):
+        return None
+    out = ctx.pool.cmdlist(ctx.lod0MeshletCount)
+    ctx.frame.instance_culling(out)
+    return out
+
+
+def gltfVisibilityRenderingStage0(ctx: GLTFRenderContext, hzb_last, in_list):
+    """mesh_raster.cpp:269-312. Returns (bShouldInvokeStage1, rejected CountAndCmdBuffer)."""
+    if not shouldRenderGLTF(ctx):
+        return False, None
+    if hzb_last is not None and hzb_last.valid and (ctx.frame.ctx.switch_flags & abi.FLAG_HZB):
+        visible = ctx.pool.cmdlist(ctx.lod0MeshletCount)
+        rejected = ctx.pool.cmdlist(ctx.lod0MeshletCount)
+        need = ctx.frame.visibility_stage0(hzb_last, in_list, visible, rejected)
+        ctx.pool.release(visible)        # stream-ordered: the next user is enqueued after the raster that reads it
+        return need, rejected
+    ctx.frame.visibility_stage0(None, in_list, None, None)
+    return False, None
+
+
+def gltfVisibilityRenderingStage1(ctx: GLTFRenderContext, hzb_this, rejected):
+    """mesh_raster.cpp:314-329."""
+    visible = ctx.pool.cmdlist(ctx.lod0MeshletCount)
+    ctx.frame.visibility_stage1(hzb_this, rejected, visible)
+    ctx.pool.release(visible)
+
+
+def buildHZB(ctx: GLTFRenderContext, bBuildMin, bBuildMax, bBuildValidRange):
+    """hzb.cpp:38-227 -> HZBContext."""
+    h = ctx.pool.hzb(ctx.frame.width, ctx.frame.height)
+    ctx.frame.build_hzb(h, bBuildMin, bBuildMax, bBuildValidRange)
+    return h
+
+
+def visibilityMark(ctx: GLTFRenderContext, drawMeshletCmdBuffer):
+    """visibility_tile.cpp:20-56."""
+    ctx.frame.visibility_mark(drawMeshletCmdBuffer)
+
+
+def lighting(ctx: GLTFRenderContext, drawMeshletCmdBuffer):
+    """lighting.cpp:193-246."""
+    ctx.frame.lighting(drawMeshletCmdBuffer)
+
+
+class DeferredRenderer:
+    """renderer.cpp:142-499 restricted to the visibility-buffer path, headless; keeps last frame's HZB as history."""
+
+    def __init__(self, ctx: Context, width, height, do_resolve=False):
+        self.ctx, self.width, self.height = ctx, width, height
+        self.frame = Frame(ctx, width, height)
+        self.pool = _Pool(ctx)
+        self.history_hzb = None            # m_rendererHistory.hzbCtx (renderer.cpp:326, :489)
+        self.last_view = None
+        self.post_cull = None
+        self.do_resolve = do_resolve
+        self.frame_counter = 0
+
+    def clear_history(self):
+        """renderer.cpp:95-105 (resize / camera cut)."""
+        self.pool.release(self.history_hzb)
+        self.history_hzb = None
+        self.last_view = None
+
+    def render(self, camera, objects, lod0_meshlet_count, meshlet_group_count, tile=None, view=None, iview=None):
+        if view is None:
+            view = cam.fill_view(camera, last_view=self.last_view, frame_counter=self.frame_counter)
+        if iview is None:
+            iview = cam.fill_instance_view(view)
+        f = self.frame
+        f.begin(view, iview, objects, lod0_meshlet_count, meshlet_group_count, tile)      # uniforms + addClearGbufferPass
+        rc = GLTFRenderContext(f, len(objects), lod0_meshlet_count, meshlet_group_count, self.pool)
+        self.pool.release(self.post_cull)
+        post = instanceCulling(rc)
+        need1, rejected = gltfVisibilityRenderingStage0(rc, self.history_hzb, post)
+        if need1:
+            tmp = buildHZB(rc, True, False, False)
+            gltfVisibilityRenderingStage1(rc, tmp, rejected)
+            self.pool.release(tmp)
+        self.pool.release(rejected)
+        hzb = buildHZB(rc, True, True, True)
+        if self.do_resolve:
+            visibilityMark(rc, post)
+            lighting(rc, post)
+        self.pool.release(self.history_hzb)
+        self.history_hzb = hzb
+        self.last_view = view
+        self.post_cull = post
+        self.frame_counter += 1
+        return post

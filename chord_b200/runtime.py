@@ -1,0 +1,333 @@
+"""ctypes bindings over libchord_b200.so (include/chord_b200.h).  No fallback path exists: a missing library or
+a missing sm_100 device raises."""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import abi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libchord_b200.so')
+
+# every symbol include/chord_b200.h declares (tests check the .so exports all of them)
+SYMBOLS = [
+    'chord_last_error', 'chord_abi_version',
+    'chord_ctx_create', 'chord_ctx_destroy', 'chord_ctx_stream', 'chord_ctx_sync', 'chord_ctx_set_switch_flags',
+    'chord_ctx_get_switch_flags', 'chord_ctx_kernel_launches', 'chord_scene_upload',
+    'chord_cmdlist_create', 'chord_cmdlist_destroy', 'chord_cmdlist_upload', 'chord_cmdlist_readback',
+    'chord_cmdlist_capacity', 'chord_cmdlist_count_ptr', 'chord_cmdlist_cmds_ptr',
+    'chord_hzb_create', 'chord_hzb_destroy', 'chord_hzb_info', 'chord_hzb_readback', 'chord_hzb_readback_valid_range',
+    'chord_hzb_chain_ptr', 'chord_hzb_chain_bytes', 'chord_hzb_mip_offset', 'chord_hzb_set_valid', 'chord_hzb_is_valid',
+    'chord_hzb_finish_top',
+    'chord_frame_create', 'chord_frame_destroy', 'chord_frame_begin', 'chord_instance_culling', 'chord_hzb_culling',
+    'chord_render_mesh', 'chord_visibility_stage0', 'chord_visibility_stage1', 'chord_build_hzb',
+    'chord_visibility_mark', 'chord_atmosphere_luts_upload', 'chord_lighting',
+    'chord_readback_vis64', 'chord_readback_visibility32', 'chord_readback_depth32', 'chord_readback_decoded',
+    'chord_readback_tile_marker', 'chord_readback_gbuffer_f32', 'chord_frame_vis64_ptr', 'chord_frame_dims',
+    'chord_frame_raster_stats', 'chord_frame_reset_stats',
+]
+
+_lib = None
+
+
+class ChordError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load libchord_b200.so.  Raises if it has not been built (python -m chord_b200.build)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ChordError(f'{LIB_PATH} is missing: build the CUDA library first (python -m chord_b200.build); '
+                             'there is no CPU fallback')
+        L = C.CDLL(LIB_PATH)
+        L.chord_last_error.restype = C.c_char_p
+        L.chord_ctx_stream.restype = C.c_void_p
+        L.chord_ctx_kernel_launches.restype = C.c_uint64
+        L.chord_ctx_get_switch_flags.restype = C.c_uint32
+        L.chord_cmdlist_capacity.restype = C.c_uint32
+        for n in ('chord_cmdlist_count_ptr', 'chord_cmdlist_cmds_ptr', 'chord_hzb_chain_ptr', 'chord_frame_vis64_ptr'):
+            getattr(L, n).restype = C.c_void_p
+        for n in ('chord_ctx_destroy', 'chord_cmdlist_destroy', 'chord_hzb_destroy', 'chord_frame_destroy'):
+            getattr(L, n).restype = None
+        L.chord_hzb_chain_bytes.restype = C.c_uint64
+        L.chord_hzb_mip_offset.restype = C.c_uint64
+        for n in SYMBOLS:
+            f = getattr(L, n)
+            if f.restype is C.c_int and n not in ('chord_abi_version', 'chord_hzb_is_valid'):
+                f.errcheck = _check
+        _lib = L
+    return _lib
+
+
+def _check(rc, func, args):
+    if rc != 0:
+        raise ChordError(f'{func.__name__} -> {rc}: {_lib.chord_last_error().decode()}')
+    return rc
+
+
+def _p(a):
+    return C.c_void_p(a.ctypes.data)
+
+
+class Context:
+    """graphics::Context + GraphicsQueue stand-in: one CUDA device, one stream."""
+
+    def __init__(self, device=0):
+        self.h = C.c_void_p()
+        lib().chord_ctx_create(C.c_int(device), C.byref(self.h))
+        self.device = device
+        self._scene = None
+
+    def close(self):
+        if self.h:
+            lib().chord_ctx_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def stream(self):
+        return lib().chord_ctx_stream(self.h)
+
+    def sync(self):
+        lib().chord_ctx_sync(self.h)
+
+    def set_switch_flags(self, flags):
+        lib().chord_ctx_set_switch_flags(self.h, C.c_uint32(flags))
+
+    @property
+    def switch_flags(self):
+        return lib().chord_ctx_get_switch_flags(self.h)
+
+    @property
+    def kernel_launches(self):
+        return int(lib().chord_ctx_kernel_launches(self.h))
+
+    def upload_scene(self, scene: abi.HostScene):
+        lib().chord_scene_upload(self.h, C.byref(scene.desc))
+        self._scene = scene
+
+    def upload_luts(self, transmittance, irradiance):
+        t = np.ascontiguousarray(transmittance, dtype=np.float16)
+        i = np.ascontiguousarray(irradiance, dtype=np.float16)
+        assert t.shape == (64, 256, 4) and i.shape == (16, 64, 4)
+        luts = abi.AtmosphereLuts(t.ctypes.data, i.ctypes.data)
+        lib().chord_atmosphere_luts_upload(self.h, C.byref(luts))
+
+
+class CmdList:
+    """CountAndCmdBuffer (postprocessing.h:48)."""
+
+    def __init__(self, ctx, capacity):
+        self.ctx, self.capacity = ctx, int(capacity)
+        self.h = C.c_void_p()
+        lib().chord_cmdlist_create(ctx.h, C.c_uint32(capacity), C.byref(self.h))
+
+    def close(self):
+        if self.h:
+            lib().chord_cmdlist_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def upload(self, cmds):
+        cmds = np.ascontiguousarray(cmds, dtype=abi.DrawCmd)
+        lib().chord_cmdlist_upload(self.h, _p(cmds), C.c_uint32(len(cmds)))
+
+    def readback(self):
+        n = C.c_uint32()
+        out = np.zeros(self.capacity, dtype=abi.DrawCmd)
+        lib().chord_cmdlist_readback(self.h, _p(out), C.c_uint32(self.capacity), C.byref(n))
+        return out[:n.value].copy()
+
+    def count(self):
+        n = C.c_uint32()
+        lib().chord_cmdlist_readback(self.h, None, C.c_uint32(0), C.byref(n))
+        return n.value
+
+    @property
+    def cmds_ptr(self):
+        return lib().chord_cmdlist_cmds_ptr(self.h)
+
+    @property
+    def count_ptr(self):
+        return lib().chord_cmdlist_count_ptr(self.h)
+
+
+class Hzb:
+    """HZBContext (render_helper.h:411-451)."""
+
+    def __init__(self, ctx, width, height):
+        self.ctx, self.width, self.height = ctx, int(width), int(height)
+        self.h = C.c_void_p()
+        lib().chord_hzb_create(ctx.h, C.c_uint32(width), C.c_uint32(height), C.byref(self.h))
+        a, b, c, d, e = (C.c_uint32() for _ in range(5))
+        lib().chord_hzb_info(self.h, C.byref(a), C.byref(b), C.byref(c), C.byref(d), C.byref(e))
+        self.mip0 = (a.value, b.value)
+        self.mips = c.value
+        self.valid_area = (d.value, e.value)
+
+    def close(self):
+        if self.h:
+            lib().chord_hzb_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def valid(self):
+        return bool(lib().chord_hzb_is_valid(self.h))
+
+    def set_valid(self, v):
+        lib().chord_hzb_set_valid(self.h, C.c_int(1 if v else 0))
+
+    def mip_dims(self, mip):
+        return max(self.mip0[0] >> mip, 1), max(self.mip0[1] >> mip, 1)
+
+    def readback(self, which='min', mip=0):
+        w, h = self.mip_dims(mip)
+        out = np.zeros((h, w), dtype=np.uint16)
+        lib().chord_hzb_readback(self.h, C.c_int(0 if which == 'min' else 1), C.c_uint32(mip), _p(out))
+        return out
+
+    def readback_chain(self, which='min'):
+        return np.concatenate([self.readback(which, m).reshape(-1) for m in range(self.mips)])
+
+    def valid_range(self):
+        out = np.zeros(2, dtype=np.uint32)
+        lib().chord_hzb_readback_valid_range(self.h, _p(out))
+        return out
+
+    def chain_ptr(self, which='min'):
+        return lib().chord_hzb_chain_ptr(self.h, C.c_int(0 if which == 'min' else 1))
+
+    @property
+    def chain_bytes(self):
+        return int(lib().chord_hzb_chain_bytes(self.h))
+
+    def mip_offset_bytes(self, mip):
+        return int(lib().chord_hzb_mip_offset(self.h, C.c_uint32(mip)))
+
+
+class Frame:
+    """GBufferTextures + per-view uniforms of one render dimension."""
+
+    def __init__(self, ctx, width, height):
+        self.ctx, self.width, self.height = ctx, int(width), int(height)
+        self.h = C.c_void_p()
+        lib().chord_frame_create(ctx.h, C.c_uint32(width), C.c_uint32(height), C.byref(self.h))
+        self._keep = None
+
+    def close(self):
+        if self.h:
+            lib().chord_frame_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def begin(self, view, iview, objects, lod0_meshlet_count, meshlet_group_count, tile=None):
+        view = np.ascontiguousarray(view, dtype=abi.PerframeCameraView).reshape(())
+        iview = np.ascontiguousarray(iview, dtype=abi.InstanceCullingViewInfo).reshape(())
+        objects = np.ascontiguousarray(objects, dtype=abi.GPUObjectGLTFPrimitive)
+        self._keep = (view, iview, objects)       # async copies read these
+        t = C.byref(abi.Rect(*tile)) if tile is not None else None
+        lib().chord_frame_begin(self.h, _p(view), _p(iview), _p(objects), C.c_uint32(len(objects)),
+                                C.c_uint32(lod0_meshlet_count), C.c_uint32(meshlet_group_count), t)
+
+    def instance_culling(self, out: CmdList):
+        lib().chord_instance_culling(self.h, out.h)
+
+    def hzb_culling(self, hzb: Hzb, first_stage, inp: CmdList, out_visible: CmdList, out_rejected: CmdList = None):
+        lib().chord_hzb_culling(self.h, hzb.h, C.c_int(1 if first_stage else 0), inp.h, out_visible.h,
+                                out_rejected.h if out_rejected is not None else None)
+
+    def render_mesh(self, lst: CmdList):
+        lib().chord_render_mesh(self.h, lst.h)
+
+    def visibility_stage0(self, last_hzb, inp, scratch_visible, out_rejected):
+        need = C.c_int(0)
+        lib().chord_visibility_stage0(self.h, last_hzb.h if last_hzb is not None else None, inp.h,
+                                      scratch_visible.h if scratch_visible is not None else None,
+                                      out_rejected.h if out_rejected is not None else None, C.byref(need))
+        return bool(need.value)
+
+    def visibility_stage1(self, hzb, rejected, scratch_visible):
+        lib().chord_visibility_stage1(self.h, hzb.h, rejected.h, scratch_visible.h)
+
+    def build_hzb(self, dst: Hzb, b_min=True, b_max=False, b_range=False):
+        lib().chord_build_hzb(self.h, C.c_int(b_min), C.c_int(b_max), C.c_int(b_range), dst.h)
+
+    def hzb_finish_top(self, dst: Hzb, b_min=True, b_max=False):
+        lib().chord_hzb_finish_top(self.h, C.c_int(b_min), C.c_int(b_max), dst.h)
+
+    def visibility_mark(self, post: CmdList):
+        lib().chord_visibility_mark(self.h, post.h)
+
+    def lighting(self, post: CmdList):
+        lib().chord_lighting(self.h, post.h)
+
+    # read-backs
+    def vis64(self):
+        out = np.zeros((self.height, self.width), dtype=np.uint64)
+        lib().chord_readback_vis64(self.h, _p(out))
+        return out
+
+    def readback_vis64_into(self, host_ptr):
+        lib().chord_readback_vis64(self.h, C.c_void_p(host_ptr))
+
+    def visibility32(self, out=None):
+        if out is None:
+            out = np.zeros((self.height, self.width), dtype=np.uint32)
+        lib().chord_readback_visibility32(self.h, _p(out))
+        return out
+
+    def depth32(self):
+        out = np.zeros((self.height, self.width), dtype=np.float32)
+        lib().chord_readback_depth32(self.h, _p(out))
+        return out
+
+    def decoded(self, post: CmdList):
+        out = np.zeros((self.height, self.width, 3), dtype=np.uint32)
+        lib().chord_readback_decoded(self.h, post.h, _p(out))
+        return out
+
+    def tile_marker(self):
+        out = np.zeros(((self.height + 7) // 8, (self.width + 7) // 8, 4), dtype=np.uint32)
+        lib().chord_readback_tile_marker(self.h, _p(out))
+        return out
+
+    def gbuffer(self, which):
+        out = np.zeros((self.height, self.width, 4), dtype=np.float32)
+        lib().chord_readback_gbuffer_f32(self.h, C.c_int(which), _p(out))
+        return out
+
+    def raster_stats(self):
+        s = abi.RasterStats()
+        lib().chord_frame_raster_stats(self.h, C.byref(s))
+        return s.as_dict()
+
+    def reset_stats(self):
+        lib().chord_frame_reset_stats(self.h)
+
+    @property
+    def vis64_ptr(self):
+        return lib().chord_frame_vis64_ptr(self.h)

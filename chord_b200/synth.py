@@ -212,7 +212,7 @@ def _face_lod_chain(origin, du, dv, patches, normal, vert_base, data_base, meshl
     def sph(level, j, i):
         pl = level_ids[level].shape[0]
         c = origin + ((i + 0.5) / pl) * du + ((j + 0.5) / pl) * dv
-        err = 0.5 * face_len / (level_ids[level - 1].shape[0] * q)      # detail removed going k-1 -> k
+        err = 0.05 * face_len / (level_ids[level - 1].shape[0] * q)     # nominal error of removing level k-1 detail
         return c, err
 
     for level in range(nl):
@@ -313,7 +313,7 @@ def city_scene(n_buildings=26, patches=4, lods=3, width=1920, height=1080, seed=
     protos = [b.add_primitive(_box_primitive(sz, patches, lods), patches, lods)
               for sz in ((10.0, 30.0, 10.0), (14.0, 18.0, 12.0), (8.0, 45.0, 8.0))]
     side = int(math.ceil(math.sqrt(n_buildings)))
-    pitch = 24.0
+    pitch = 40.0
     extent = side * pitch
     ground = b.add_primitive([((0, 0, extent), (extent, 0, 0), (0, 0, -extent), (0, 1, 0))], ground_patches, 1)
     mats = [default_material(base_color=(0.7, 0.7, 0.72, 1.0)),
@@ -321,7 +321,7 @@ def city_scene(n_buildings=26, patches=4, lods=3, width=1920, height=1080, seed=
             default_material(alpha_mode=1, alpha_cutoff=0.5, base_color=(0.6, 0.4, 0.3, 1.0)),
             default_material(base_color=(0.3, 0.3, 0.3, 1.0), roughness=0.9)]
     scene = b.finish(mats)
-    camera = cam.Camera((extent * 0.5 + 3.0, 1.7, extent + 6.0), (-0.12, 0.08, -1.0), width=width, height=height)
+    camera = cam.Camera((pitch - 7.0, 7.0, extent + 12.0), (0.06, -0.12, -1.0), width=width, height=height)
     objs = []
     transforms = []
     k = 0

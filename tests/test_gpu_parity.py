@@ -1,0 +1,178 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle, bit-exact (integer / byte / index work and
+depth bits).  Sizes are chosen so that the oracle finishes in seconds."""
+import numpy as np
+import pytest
+
+import oracle
+from chord_b200 import abi, camera as cam, renderer, runtime, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _assert_lists_equal(a, b, what):
+    assert len(a) == len(b), f'{what}: count {len(a)} != {len(b)}'
+    for k in ('objectId', 'meshletId', 'slot'):
+        assert np.array_equal(a[k], b[k]), f'{what}: field {k} differs'
+
+
+def _assert_vis_equal(gpu, ref, what):
+    if np.array_equal(gpu, ref):
+        return
+    bad = np.argwhere(gpu != ref)
+    y, x = bad[0]
+    raise AssertionError(f'{what}: {len(bad)} texels differ, first at ({x},{y}): gpu={int(gpu[y, x]):#018x} ref={int(ref[y, x]):#018x}')
+
+
+def _assert_hzb_equal(h_gpu, h_ref, which='min'):
+    for m in range(h_ref['mips']):
+        g = h_gpu.readback(which, m).reshape(-1)
+        o = int(h_ref['offsets'][m])
+        r = h_ref[which][o:o + g.size]
+        assert np.array_equal(g, r), f'hzb {which} mip {m}: {int((g != r).sum())} texels differ'
+
+
+def test_s1_single_meshlet(gpu_ctx):
+    scene, camera, objects = synth.single_meshlet_scene()
+    view = cam.fill_view(camera)
+    iview = cam.fill_instance_view(view)
+    gpu_ctx.upload_scene(scene)
+    for flags in (0b101, 0b111, 0b000):
+        gpu_ctx.set_switch_flags(flags)
+        fr = runtime.Frame(gpu_ctx, 256, 256)
+        fr.begin(view, iview, objects, 1, 1)
+        post = runtime.CmdList(gpu_ctx, 4)
+        fr.instance_culling(post)
+        ofr = oracle.Frame(scene, view, iview, objects, 256, 256, flags)
+        opost = ofr.instance_culling(4)
+        _assert_lists_equal(post.readback(), opost, 'post-cull list')
+        fr.render_mesh(post)
+        ovis, ostats = ofr.render_mesh(opost)
+        _assert_vis_equal(fr.vis64(), ovis, 'vis64')
+        st = fr.raster_stats()
+        for k in ('trianglesSubmitted', 'trianglesCulled', 'trianglesClipped', 'meshletsRastered'):
+            assert st[k] == ostats[k], (k, st, ostats)
+        hz = runtime.Hzb(gpu_ctx, 256, 256)
+        fr.build_hzb(hz, True, True, True)
+        oh = ofr.build_hzb(ovis, True, True, True)
+        assert hz.mip0 == oh['mip0'] and hz.mips == oh['mips']
+        _assert_hzb_equal(hz, oh, 'min')
+        _assert_hzb_equal(hz, oh, 'max')
+        assert np.array_equal(hz.valid_range(), oh['range'])
+        # decode + split images
+        vis32 = fr.visibility32()
+        assert np.array_equal(vis32, (ovis & 0xFFFFFFFF).astype(np.uint32))
+        assert np.array_equal(fr.depth32().view(np.uint32), (ovis >> 32).astype(np.uint32))
+        assert np.array_equal(fr.decoded(post), oracle.decode(ovis, opost))
+        fr.visibility_mark(post)
+        assert np.array_equal(fr.tile_marker(), ofr.visibility_mark(ovis, opost))
+    gpu_ctx.set_switch_flags(0b111)
+
+
+@pytest.mark.parametrize('n,w,h,scale', [(3000, 640, 360, 1.0), (1500, 512, 512, 40.0), (600, 256, 256, 2000.0)])
+def test_patch_stream_raster(gpu_ctx, n, w, h, scale):
+    """raster-only (S5 shape): tiny, medium and large triangles."""
+    scene, camera, objects, cmds = synth.patch_stream_scene(n, w, h, seed=5, overdraw_scale=scale)
+    view = cam.fill_view(camera)
+    iview = cam.fill_instance_view(view)
+    gpu_ctx.upload_scene(scene)
+    fr = runtime.Frame(gpu_ctx, w, h)
+    fr.begin(view, iview, objects, n, (n + 3) // 4)
+    lst = runtime.CmdList(gpu_ctx, n)
+    lst.upload(cmds)
+    fr.render_mesh(lst)
+    ofr = oracle.Frame(scene, view, iview, objects, w, h)
+    ovis, ostats = ofr.render_mesh(cmds)
+    _assert_vis_equal(fr.vis64(), ovis, f'vis64 n={n} scale={scale}')
+    st = fr.raster_stats()
+    for k in ('trianglesSubmitted', 'trianglesCulled', 'trianglesClipped', 'meshletsRastered'):
+        assert st[k] == ostats[k], (k, st, ostats)
+    assert st['largeQueueOverflow'] == 0
+    # the full instance-cull path must reproduce the prebuilt list for this scene (all LOD-0 roots, camera facing)
+    post = runtime.CmdList(gpu_ctx, n)
+    fr.instance_culling(post)
+    _assert_lists_equal(post.readback(), ofr.instance_culling(n), 'post-cull list')
+
+
+def test_city_frames(gpu_ctx):
+    """S2-shaped city: LOD-DAG cut, cone + frustum cull, two-phase HZB with genuine last-frame history, near-plane
+    clipping, large triangles; 4 frames of camera motion through the reference frame sequence."""
+    w, h = 640, 360
+    scene, camera, objects, info = synth.city_scene(n_buildings=9, patches=4, lods=3, width=w, height=h, seed=2)
+    gpu_ctx.upload_scene(scene)
+    gpu_ctx.set_switch_flags(0b111)
+    r = renderer.DeferredRenderer(gpu_ctx, w, h)
+    prev_hzb, last_view, last_cam = None, None, None
+    for fi in range(4):
+        c = cam.Camera(camera.position + np.array([0.6 * fi, 0.05 * fi, -1.5 * fi]), camera.front, width=w, height=h)
+        objs = synth.refill_objects(info['transforms'], c, camera_last=last_cam)
+        view = cam.fill_view(c, last_view=last_view, frame_counter=fi)
+        iview = cam.fill_instance_view(view)
+        post = r.render(c, objs, info['lod0MeshletCount'], info['meshletGroupCount'], view=view, iview=iview)
+        ref = oracle.run_frame(scene, view, iview, objs, w, h, info['lod0MeshletCount'], prev_hzb)
+        _assert_lists_equal(post.readback(), ref['post_cull'], f'frame {fi} post-cull')
+        _assert_vis_equal(r.frame.vis64(), ref['vis64'], f'frame {fi} vis64')
+        _assert_hzb_equal(r.history_hzb, ref['hzb'], 'min')
+        _assert_hzb_equal(r.history_hzb, ref['hzb'], 'max')
+        assert np.array_equal(r.history_hzb.valid_range(), ref['hzb']['range'])
+        if fi > 0:
+            assert 'stage0_visible' in ref and len(ref['stage0_rejected']) > 0, 'scene should exercise occlusion'
+        assert len(ref['post_cull']) > 0
+        prev_hzb, last_view, last_cam = ref['hzb'], view, c
+
+
+def test_hzb_culling_lists(gpu_ctx):
+    """K3 in isolation: both phases, visible and rejected lists in canonical order."""
+    w, h = 512, 288
+    scene, camera, objects, info = synth.city_scene(n_buildings=6, patches=4, lods=2, width=w, height=h, seed=11)
+    gpu_ctx.upload_scene(scene)
+    view = cam.fill_view(camera)
+    iview = cam.fill_instance_view(view)
+    cap = info['lod0MeshletCount']
+    fr = runtime.Frame(gpu_ctx, w, h)
+    fr.begin(view, iview, objects, cap, info['meshletGroupCount'])
+    post = runtime.CmdList(gpu_ctx, cap)
+    fr.instance_culling(post)
+    fr.render_mesh(post)
+    hz = runtime.Hzb(gpu_ctx, w, h)
+    fr.build_hzb(hz, True, False, False)
+    ofr = oracle.Frame(scene, view, iview, objects, w, h)
+    opost = ofr.instance_culling(cap)
+    ovis, _ = ofr.render_mesh(opost)
+    oh = ofr.build_hzb(ovis, True, False, False)
+    _assert_hzb_equal(hz, oh, 'min')
+    for first in (True, False):
+        vis, rej = runtime.CmdList(gpu_ctx, cap), runtime.CmdList(gpu_ctx, cap)
+        fr.hzb_culling(hz, first, post, vis, rej if first else None)
+        ov, orj = ofr.hzb_culling(oh, first, opost)
+        _assert_lists_equal(vis.readback(), ov, f'visible first={first}')
+        if first:
+            _assert_lists_equal(rej.readback(), orj, 'rejected')
+            assert len(orj) > 0 and len(ov) > 0
+
+
+def test_tile_scissor(gpu_ctx):
+    """screen-tile partition: union of tile renders == full render."""
+    w, h = 512, 256
+    scene, camera, objects, cmds = synth.patch_stream_scene(800, w, h, seed=9, overdraw_scale=30.0)
+    view = cam.fill_view(camera)
+    iview = cam.fill_instance_view(view)
+    gpu_ctx.upload_scene(scene)
+    lst = runtime.CmdList(gpu_ctx, len(cmds))
+    lst.upload(cmds)
+    fr = runtime.Frame(gpu_ctx, w, h)
+    fr.begin(view, iview, objects, len(cmds), (len(cmds) + 3) // 4)
+    fr.render_mesh(lst)
+    full = fr.vis64()
+    acc = np.zeros_like(full)
+    for tile in ((0, 0, 256, 128), (256, 0, 512, 128), (0, 128, 256, 256), (256, 128, 512, 256)):
+        fr.begin(view, iview, objects, len(cmds), (len(cmds) + 3) // 4, tile=tile)
+        fr.render_mesh(lst)
+        part = fr.vis64()
+        x0, y0, x1, y1 = tile
+        mask = np.zeros_like(full, dtype=bool)
+        mask[y0:y1, x0:x1] = True
+        assert not part[~mask].any(), 'wrote outside the tile'
+        acc |= part
+        ot, _ = oracle.Frame(scene, view, iview, objects, w, h, tile=tile).render_mesh(cmds)
+        _assert_vis_equal(part, ot, f'tile {tile}')
+    _assert_vis_equal(acc, full, 'union of tiles')
