@@ -199,6 +199,7 @@ struct chord_frame {
     // raster
     void* largeTris; uint32_t* largeCounters; uint32_t largeTriCapacity, largeItemCapacity; void* largeItems;
     unsigned long long* stats;   // device chord_raster_stats
+    void* works; uint32_t worksCapacity; uint32_t* redoList; void* deferred; uint32_t deferredCapacity;
     // resolve
     uint32_t* tileMarker; uint32_t* tileList; uint32_t* tileCount; float* gbuffer[CHORD_GBUF_COUNT];
     chord_PerframeCameraView hView;   // host copy

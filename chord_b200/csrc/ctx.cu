@@ -56,7 +56,7 @@ static int upload(chord_ctx* ctx, std::vector<void*>& allocs, const T* host, siz
     const size_t bytes = sizeof(T) * count;
     CHORD_CUDA(cudaMalloc(&d, bytes + padBytes));                 // pad: kernels may read aligned supersets
     CHORD_CUDA(cudaMemsetAsync((char*)d + bytes, 0, padBytes, ctx->stream));
-    CHORD_CUDA(cudaMemcpyAsync(d, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CHORD_CUDA(cudaMemcpyAsync(d, host, bytes, cudaMemcpyDefault, ctx->stream));   // host or device source (UVA)
     allocs.push_back(d);
     *out = (const T*)d;
     return CHORD_OK;
@@ -283,6 +283,7 @@ int chord_hzb_is_valid(const chord_hzb* h) { return h ? h->valid : 0; }
 // ---------------------------------------------------------------------------------------------- frames
 static const uint32_t kLargeTriCapacity = 1u << 18;      // 256 k queued large triangles per render_mesh call
 static const uint32_t kLargeItemCapacity = 1u << 22;     // 4 M (triangle, tile-row) work items
+static const uint32_t kDeferredCapacity = 1u << 22;      // 4 M deferred triangles (64 B each); overflow -> k_raster_general
 
 int chord_frame_create(chord_ctx* ctx, uint32_t width, uint32_t height, chord_frame** out)
 {
@@ -300,6 +301,8 @@ int chord_frame_create(chord_ctx* ctx, uint32_t width, uint32_t height, chord_fr
     CHORD_CUDA(cudaMalloc(&f->largeTris, (size_t)48 * f->largeTriCapacity));
     CHORD_CUDA(cudaMalloc(&f->largeItems, (size_t)8 * f->largeItemCapacity));
     CHORD_CUDA(cudaMalloc(&f->largeCounters, 64));
+    f->deferredCapacity = kDeferredCapacity;
+    CHORD_CUDA(cudaMalloc(&f->deferred, (size_t)64 * f->deferredCapacity));
     CHORD_CUDA(cudaMalloc(&f->stats, sizeof(chord_raster_stats)));
     CHORD_CUDA(cudaMemsetAsync(f->stats, 0, sizeof(chord_raster_stats), ctx->stream));
     CHORD_CUDA(cudaMemsetAsync(f->largeCounters, 0, 64, ctx->stream));
@@ -317,6 +320,7 @@ void chord_frame_destroy(chord_frame* f)
     cudaStreamSynchronize(f->ctx->stream);
     cudaFree(f->vis64); cudaFree(f->dView); cudaFree(f->dIView); cudaFree(f->dObjects); cudaFree(f->dDerived);
     cudaFree(f->objGroupCount); cudaFree(f->objGroupBase); cudaFree(f->totalGroups);
+    cudaFree(f->works); cudaFree(f->redoList); cudaFree(f->deferred);
     cudaFree(f->largeTris); cudaFree(f->largeItems); cudaFree(f->largeCounters); cudaFree(f->stats);
     cudaFree(f->tileMarker); cudaFree(f->tileList); cudaFree(f->tileCount);
     for (int i = 0; i < CHORD_GBUF_COUNT; i++) cudaFree(f->gbuffer[i]);

@@ -96,56 +96,69 @@ def single_meshlet_scene(width=256, height=256, seed=1):
 
 
 def patch_stream_scene(n_meshlets, width=3840, height=2160, seed=5, area_range=(0.5, 1.5), depth_range=(1.0, 100.0),
-                       overdraw_scale=1.0):
+                       overdraw_scale=1.0, chunk=16384):
     """S5: ``n_meshlets`` camera-facing 8x8-quad patches (V=81, T=128) whose projected triangle area is uniform in
     ``area_range`` px^2, patch centres uniform over the viewport, depth uniform in ``depth_range`` metres; one
-    opaque one-sided object, identity matrix, camera at the origin looking down -Z."""
-    rng = np.random.default_rng(seed)
+    opaque one-sided object, identity matrix, camera at the origin looking down -Z.  Generated in chunks into
+    preallocated arrays (the full stream is 1.5 GB)."""
     q, V, T = 8, 81, 128
     fovy = math.radians(45.0)
     tan_half = math.tan(fovy * 0.5)
     M = int(n_meshlets)
-    depth = rng.uniform(depth_range[0], depth_range[1], M)
-    area = rng.uniform(area_range[0], area_range[1], M) * overdraw_scale
-    side_px = np.sqrt(2.0 * area)                       # quad side in pixels
-    px_world = 2.0 * depth * tan_half / height          # world units per pixel at that depth
-    cx = rng.uniform(0, width, M)
-    cy = rng.uniform(0, height, M)
-    ang = rng.uniform(0, 2 * math.pi, M)
-    # patch-local grid, rotated in the view plane
+    stride = V + T
+    pos = np.empty((M, V, 3), dtype=F)
+    data = np.empty((M, stride), dtype=np.uint32)
+    meshlets = np.zeros(M, dtype=abi.GPUGLTFMeshlet)
+    centers = np.empty((M, 3), dtype=F)
     g = (np.arange(q + 1) - q / 2.0)
-    gx, gy = np.meshgrid(g, g)                           # (9, 9)
-    gx, gy = gx.reshape(-1), gy.reshape(-1)
-    ca, sa = np.cos(ang)[:, None], np.sin(ang)[:, None]
-    ox = (gx[None] * ca - gy[None] * sa) * side_px[:, None]   # pixels
-    oy = (gx[None] * sa + gy[None] * ca) * side_px[:, None]
-    sx = cx[:, None] + ox
-    sy = cy[:, None] + oy
-    wx = (sx - width / 2.0) * px_world[:, None]
-    wy = -(sy - height / 2.0) * px_world[:, None]
-    wz = -depth[:, None] + (rng.random((M, V)) - 0.5) * 0.05 * (side_px * px_world)[:, None]
-    pos = np.stack([wx, wy, np.broadcast_to(wz, wx.shape)], axis=-1).astype(F)       # (M, V, 3)
-    # the patch was built with screen-y down; flip winding so the camera-facing side is CCW in y-up NDC
+    gx, gy = np.meshgrid(g, g)
+    gx, gy = gx.reshape(-1).astype(F), gy.reshape(-1).astype(F)
+    # the patch is laid out with screen-y down; flip winding so the camera-facing side is CCW in y-up NDC
     topo = _patch_topology(q)
     i0, i1, i2 = topo & 0xFF, (topo >> 8) & 0xFF, (topo >> 16) & 0xFF
     topo = (i0 | (i2 << 8) | (i1 << 16)).astype(np.uint32)
-    stride = V + T
-    data = np.empty((M, stride), dtype=np.uint32)
-    data[:, :V] = (np.arange(M, dtype=np.uint32)[:, None] * V + np.arange(V, dtype=np.uint32)[None])
-    data[:, V:] = topo[None]
-    offsets = (np.arange(M, dtype=np.uint64) * stride).astype(np.uint32)
-    meshlets = _meshlet_records(pos, offsets, V, T, 0, (0, 0, 1))
+    lane = np.arange(V, dtype=np.uint32)[None]
+    for c0 in range(0, M, chunk):
+        c1 = min(M, c0 + chunk)
+        n = c1 - c0
+        rng = np.random.default_rng([seed, c0 // chunk])
+        depth = rng.uniform(depth_range[0], depth_range[1], n).astype(F)
+        area = (rng.uniform(area_range[0], area_range[1], n) * overdraw_scale).astype(F)
+        side_px = np.sqrt(F(2.0) * area)                    # quad side in pixels
+        px_world = (F(2.0 * tan_half / height) * depth)     # world units per pixel at that depth
+        cx = rng.uniform(0, width, n).astype(F)
+        cy = rng.uniform(0, height, n).astype(F)
+        ang = rng.uniform(0, 2 * math.pi, n).astype(F)
+        ca, sa = np.cos(ang)[:, None], np.sin(ang)[:, None]
+        sx = cx[:, None] + (gx[None] * ca - gy[None] * sa) * side_px[:, None]
+        sy = cy[:, None] + (gx[None] * sa + gy[None] * ca) * side_px[:, None]
+        p = pos[c0:c1]
+        p[:, :, 0] = (sx - F(width / 2.0)) * px_world[:, None]
+        p[:, :, 1] = -(sy - F(height / 2.0)) * px_world[:, None]
+        p[:, :, 2] = -depth[:, None] + (rng.random((n, V), dtype=F) - F(0.5)) * (F(0.05) * side_px * px_world)[:, None]
+        data[c0:c1, :V] = (np.arange(c0, c1, dtype=np.uint32)[:, None] * np.uint32(V) + lane)
+        data[c0:c1, V:] = topo[None]
+        m = meshlets[c0:c1]
+        m['posMin'] = p.min(axis=1)
+        m['posMax'] = p.max(axis=1)
+        centers[c0:c1] = p.mean(axis=1)
+    meshlets['dataOffset'] = (np.arange(M, dtype=np.uint64) * stride).astype(np.uint32)
+    meshlets['vertexTriangleCount'] = abi.pack_vertex_triangle_count(V, T)
+    meshlets['coneAxis'] = (0, 0, 1)
+    meshlets['coneCutOff'] = 0.0
+    meshlets['coneApex'] = centers
     G = (M + 3) // 4
     groups = np.zeros(G, dtype=abi.GPUGLTFMeshletGroup)
     groups['error'], groups['parentError'] = -1.0, FLT_MAX
     groups['meshletOffset'] = np.arange(G, dtype=np.uint32) * 4
     groups['meshletCount'] = np.minimum(4, M - np.arange(G) * 4)
-    centers = pos.mean(axis=1)
     groups['clusterPosCenter'] = centers[::4][:G]
     groups['parentPosCenter'] = centers[::4][:G]
     flat = pos.reshape(-1, 3)
     prim = np.zeros(1, dtype=abi.GLTFPrimitiveBuffer)
-    prim['posMin'], prim['posMax'], prim['posAverage'] = flat.min(axis=0), flat.max(axis=0), flat.mean(axis=0)
+    prim['posMin'] = meshlets['posMin'].min(axis=0)
+    prim['posMax'] = meshlets['posMax'].max(axis=0)
+    prim['posAverage'] = centers.mean(axis=0)
     prim['vertexCount'], prim['meshletGroupCount'] = len(flat), G
     scene = abi.HostScene([dict(meshlets=meshlets, positions=flat, meshletData=data.reshape(-1), groups=groups,
                                 groupIndices=np.arange(M, dtype=np.uint32))],

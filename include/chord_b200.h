@@ -78,7 +78,8 @@ typedef struct {
     const chord_GLTFMaterialGPUData*  materials;  uint32_t materialCount;
 } chord_scene_desc;
 
-/* Copies everything to HBM (host pointers in, synchronous on return). Replaces any previous scene. */
+/* Copies everything to HBM (synchronous on return). The big arrays may be host or device pointers (copied with
+ * cudaMemcpyDefault); the desc structs themselves, primitives and materials are host memory. Replaces any previous scene. */
 int chord_scene_upload(chord_ctx* ctx, const chord_scene_desc* desc);
 
 /* ---- pooled work lists: CountAndCmdBuffer = {uint count, uint3 cmd[capacity]}
