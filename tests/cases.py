@@ -1,0 +1,41 @@
+"""Seeded parity cases shared by the golden-fixture generator, the CPU tests and the GPU tests."""
+import hashlib
+
+import numpy as np
+
+from chord_b200 import camera as cam, synth
+
+
+def digest(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def case_s1():
+    scene, camera, objects = synth.single_meshlet_scene()
+    view = cam.fill_view(camera)
+    return dict(name='s1', scene=scene, view=view, iview=cam.fill_instance_view(view), objects=objects, w=256, h=256,
+                lod0=1, groups=1)
+
+
+def case_stream(n=3000, w=640, h=360, scale=1.0, seed=5):
+    scene, camera, objects, cmds = synth.patch_stream_scene(n, w, h, seed=seed, overdraw_scale=scale)
+    view = cam.fill_view(camera)
+    return dict(name=f'stream_{n}_{w}x{h}_{scale}', scene=scene, view=view, iview=cam.fill_instance_view(view),
+                objects=objects, w=w, h=h, lod0=n, groups=(n + 3) // 4, cmds=cmds)
+
+
+def city_frames(n_buildings=9, w=640, h=360, frames=4, seed=2, lods=3, low=False):
+    """camera path through the procedural city; yields per-frame inputs with genuine last-frame data."""
+    scene, camera, objects, info = synth.city_scene(n_buildings=n_buildings, patches=4, lods=lods, width=w, height=h, seed=seed)
+    out, last_view, last_cam = [], None, None
+    for fi in range(frames):
+        if low:   # skim the ground inside the city: ground triangles cross the near plane, walls fill the view
+            pos = np.array([30.0 + 1.5 * fi, 0.35, 60.0 - 2.0 * fi])
+            c = cam.Camera(pos, (0.25, -0.05, -1.0), width=w, height=h)
+        else:
+            c = cam.Camera(camera.position + np.array([0.6 * fi, 0.05 * fi, -1.5 * fi]), camera.front, width=w, height=h)
+        objs = synth.refill_objects(info['transforms'], c, camera_last=last_cam)
+        view = cam.fill_view(c, last_view=last_view, frame_counter=fi)
+        out.append(dict(view=view, iview=cam.fill_instance_view(view), objects=objs, camera=c))
+        last_view, last_cam = view, c
+    return scene, info, out
