@@ -91,13 +91,8 @@ class ClockSampler:
 
 
 def tile_for_rank(rank, n, w, h):
-    """Screen-tile partition: 2 -> halves, 4 -> 2x2, 8 -> 4x2; tile edges on multiples of 64 px."""
-    cols, rows = {1: (1, 1), 2: (2, 1), 4: (2, 2), 8: (4, 2)}[n]
-    cx, cy = rank % cols, rank // cols
-
-    def cut(i, k, dim):
-        return min(dim, ((dim * i // k) + 63) // 64 * 64) if i < k else dim
-    return (cut(cx, cols, w), cut(cy, rows, h), cut(cx + 1, cols, w), cut(cy + 1, rows, h))
+    from chord_b200 import multigpu
+    return multigpu.tile_for_rank(rank, n, w, h)
 
 
 def run_reference(args):

@@ -152,11 +152,34 @@ static HzbBuildParams make_params(chord_frame* fr, int bMin, int bMax, int bRang
     return p;
 }
 
+// 64x64-pixel block range a screen tile owns (tiles touching the right / bottom frame edge also own the clamped
+// off-screen blocks up to the power-of-two extent, so that the union of all tiles is the reference's full dispatch)
+static void tile_blocks(const chord_hzb* h, const chord_rect& t, uint32_t frameW, uint32_t frameH, uint32_t& bx0, uint32_t& by0, uint32_t& bx1, uint32_t& by1)
+{
+    const uint32_t gw = (h->mip0W + 31) / 32, gh = (h->mip0H + 31) / 32;
+    bx0 = t.x0 / 64; by0 = t.y0 / 64;
+    bx1 = (t.x1 >= frameW) ? gw : t.x1 / 64;
+    by1 = (t.y1 >= frameH) ? gh : t.y1 / 64;
+}
+
+static bool tile_aligned(const chord_rect& t, uint32_t w, uint32_t h)
+{ return (t.x0 % 64 == 0) && (t.y0 % 64 == 0) && (t.x1 % 64 == 0 || t.x1 == w) && (t.y1 % 64 == 0 || t.y1 == h); }
+
 int launch_build_hzb(chord_frame* fr, int bMin, int bMax, int bRange, chord_hzb* dst)
 {
     chord_ctx* ctx = fr->ctx;
     HzbBuildParams p = make_params(fr, bMin, bMax, bRange, dst);
-    const dim3 grid((dst->mip0W + 31) / 32, (dst->mip0H + 31) / 32);      // hzb.cpp:74
+    dim3 grid((dst->mip0W + 31) / 32, (dst->mip0H + 31) / 32);            // hzb.cpp:74
+    const bool fullFrame = fr->tile.x0 == 0 && fr->tile.y0 == 0 && fr->tile.x1 == fr->width && fr->tile.y1 == fr->height;
+    if (!fullFrame) {
+        // screen-tile partition: build only the blocks this tile owns; everything else reads as 0 (= far,
+        // never occludes) until the tiles of the other GPUs are gathered in and chord_hzb_finish_top rebuilds mips 6..
+        CHORD_REQUIRE(tile_aligned(fr->tile, fr->width, fr->height), "tile rect must be cut on multiples of 64 px for a tiled HZB build");
+        uint32_t bx0, by0, bx1, by1; tile_blocks(dst, fr->tile, fr->width, fr->height, bx0, by0, bx1, by1);
+        p.blockX0 = bx0; p.blockY0 = by0; grid = dim3(bx1 - bx0, by1 - by0);
+        if (bMin) CHORD_CUDA(cudaMemsetAsync(dst->minChain, 0, sizeof(__half) * dst->totalTexels, ctx->stream));
+        if (bMax) CHORD_CUDA(cudaMemsetAsync(dst->maxChain, 0, sizeof(__half) * dst->totalTexels, ctx->stream));
+    }
     p.numBlocks = grid.x * grid.y;
     CHORD_CUDA(cudaMemsetAsync(dst->counter, 0, 4, ctx->stream));
     if (bRange) {
@@ -170,6 +193,82 @@ int launch_build_hzb(chord_frame* fr, int bMin, int bMax, int bRange, chord_hzb*
 }
 
 }  // namespace chordb
+
+namespace chordb {
+
+struct TileRegion { uint32_t bx0, by0, bx1, by1; };
+
+__device__ __forceinline__ uint64_t tile_region_texels(const TileRegion& r, uint32_t mip)
+{ return (uint64_t)(((r.bx1 - r.bx0) * 32u) >> mip) * (((r.by1 - r.by0) * 32u) >> mip); }
+
+// one thread per packed texel of mips 0..5 of one tile; pack = chain -> contiguous, unpack = contiguous -> chain
+template <bool kPack>
+__global__ void k_hzb_tile_copy(__half* __restrict__ chain, const uint64_t* __restrict__ mipOffset6, uint32_t mip0W,
+                                const TileRegion* __restrict__ regions, uint32_t nRegions, __half* __restrict__ packed, uint64_t slotTexels)
+{
+    const uint32_t ri = blockIdx.y;
+    if (ri >= nRegions) return;
+    const TileRegion r = regions[ri];
+    uint64_t total = 0;
+#pragma unroll
+    for (uint32_t m = 0; m < 6; m++) total += tile_region_texels(r, m);
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t k = i; uint32_t mip = 0;
+        while (k >= tile_region_texels(r, mip)) { k -= tile_region_texels(r, mip); mip++; }
+        const uint32_t rw = ((r.bx1 - r.bx0) * 32u) >> mip;
+        const uint32_t x = ((r.bx0 * 32u) >> mip) + (uint32_t)(k % rw), y = ((r.by0 * 32u) >> mip) + (uint32_t)(k / rw);
+        __half* c = chain + mipOffset6[mip] + (uint64_t)y * (mip0W >> mip) + x;
+        __half* p = packed + (uint64_t)ri * slotTexels + i;
+        if (kPack) *p = *c; else *c = *p;
+    }
+}
+
+}  // namespace chordb
+
+extern "C" int chord_hzb_tile_bytes(const chord_hzb* h, const chord_rect* tile, uint64_t* bytes)
+{
+    using namespace chordb;
+    CHORD_REQUIRE(h && tile && bytes, "null");
+    CHORD_REQUIRE(tile_aligned(*tile, h->depthW, h->depthH), "tile rect must be cut on multiples of 64 px");
+    uint32_t bx0, by0, bx1, by1; tile_blocks(h, *tile, h->depthW, h->depthH, bx0, by0, bx1, by1);
+    uint64_t t = 0;
+    for (uint32_t m = 0; m < 6; m++) t += (uint64_t)(((bx1 - bx0) * 32u) >> m) * (((by1 - by0) * 32u) >> m);
+    *bytes = t * sizeof(__half);
+    return CHORD_OK;
+}
+
+static int hzb_tile_copy(chord_hzb* h, int which, const chord_rect* tiles, uint32_t n, void* packed, uint64_t slotBytes, bool pack)
+{
+    using namespace chordb;
+    CHORD_REQUIRE(h && tiles && packed && n > 0 && n <= 64, "args");
+    CHORD_REQUIRE(h->mipCount >= 6, "mips");
+    chord_ctx* ctx = h->ctx;
+    TileRegion regs[64];
+    for (uint32_t i = 0; i < n; i++) {
+        CHORD_REQUIRE(tile_aligned(tiles[i], h->depthW, h->depthH), "tile rect must be cut on multiples of 64 px");
+        tile_blocks(h, tiles[i], h->depthW, h->depthH, regs[i].bx0, regs[i].by0, regs[i].bx1, regs[i].by1);
+    }
+    TileRegion* dRegs = nullptr; uint64_t* dOff = nullptr;
+    CHORD_CUDA(cudaMallocAsync(&dRegs, sizeof(TileRegion) * n, ctx->stream));
+    CHORD_CUDA(cudaMallocAsync(&dOff, sizeof(uint64_t) * 6, ctx->stream));
+    CHORD_CUDA(cudaMemcpyAsync(dRegs, regs, sizeof(TileRegion) * n, cudaMemcpyHostToDevice, ctx->stream));
+    CHORD_CUDA(cudaMemcpyAsync(dOff, h->mipOffset, sizeof(uint64_t) * 6, cudaMemcpyHostToDevice, ctx->stream));
+    __half* chain = which ? h->maxChain : h->minChain;
+    const dim3 grid(256, n);
+    if (pack) k_hzb_tile_copy<true><<<grid, 256, 0, ctx->stream>>>(chain, dOff, h->mip0W, dRegs, n, (__half*)packed, slotBytes / 2);
+    else      k_hzb_tile_copy<false><<<grid, 256, 0, ctx->stream>>>(chain, dOff, h->mip0W, dRegs, n, (__half*)packed, slotBytes / 2);
+    ctx->launches++;
+    CHORD_CUDA(cudaGetLastError());
+    CHORD_CUDA(cudaFreeAsync(dRegs, ctx->stream));
+    CHORD_CUDA(cudaFreeAsync(dOff, ctx->stream));
+    return CHORD_OK;
+}
+
+extern "C" int chord_hzb_pack_tile(chord_hzb* h, int which, const chord_rect* tile, void* dstDevice)
+{ return hzb_tile_copy(h, which, tile, 1, dstDevice, 0, true); }
+
+extern "C" int chord_hzb_unpack_tiles(chord_hzb* h, int which, const chord_rect* tiles, uint32_t n, const void* srcDevice, uint64_t slotBytes)
+{ return hzb_tile_copy(h, which, tiles, n, (void*)srcDevice, slotBytes, false); }
 
 // Multi-GPU helper: after the mips 0..5 of every tile have been gathered into dst, rebuild mips 6...
 extern "C" int chord_hzb_finish_top(chord_frame* fr, int bMin, int bMax, chord_hzb* dst)

@@ -19,7 +19,7 @@ SYMBOLS = [
     'chord_cmdlist_capacity', 'chord_cmdlist_count_ptr', 'chord_cmdlist_cmds_ptr',
     'chord_hzb_create', 'chord_hzb_destroy', 'chord_hzb_info', 'chord_hzb_readback', 'chord_hzb_readback_valid_range',
     'chord_hzb_chain_ptr', 'chord_hzb_chain_bytes', 'chord_hzb_mip_offset', 'chord_hzb_set_valid', 'chord_hzb_is_valid',
-    'chord_hzb_finish_top',
+    'chord_hzb_finish_top', 'chord_hzb_tile_bytes', 'chord_hzb_pack_tile', 'chord_hzb_unpack_tiles',
     'chord_frame_create', 'chord_frame_destroy', 'chord_frame_begin', 'chord_instance_culling', 'chord_hzb_culling',
     'chord_render_mesh', 'chord_visibility_stage0', 'chord_visibility_stage1', 'chord_build_hzb',
     'chord_visibility_mark', 'chord_atmosphere_luts_upload', 'chord_lighting',
@@ -212,6 +212,19 @@ class Hzb:
         out = np.zeros(2, dtype=np.uint32)
         lib().chord_hzb_readback_valid_range(self.h, _p(out))
         return out
+
+    def tile_bytes(self, tile):
+        b = C.c_uint64()
+        lib().chord_hzb_tile_bytes(self.h, C.byref(abi.Rect(*tile)), C.byref(b))
+        return int(b.value)
+
+    def pack_tile(self, which, tile, dst_ptr):
+        lib().chord_hzb_pack_tile(self.h, C.c_int(0 if which == 'min' else 1), C.byref(abi.Rect(*tile)), C.c_void_p(dst_ptr))
+
+    def unpack_tiles(self, which, tiles, src_ptr, slot_bytes):
+        arr = (abi.Rect * len(tiles))(*[abi.Rect(*t) for t in tiles])
+        lib().chord_hzb_unpack_tiles(self.h, C.c_int(0 if which == 'min' else 1), arr, C.c_uint32(len(tiles)),
+                                     C.c_void_p(src_ptr), C.c_uint64(slot_bytes))
 
     def chain_ptr(self, which='min'):
         return lib().chord_hzb_chain_ptr(self.h, C.c_int(0 if which == 'min' else 1))

@@ -30,6 +30,7 @@ typedef struct chord_ctx     chord_ctx;
 typedef struct chord_frame   chord_frame;
 typedef struct chord_cmdlist chord_cmdlist;
 typedef struct chord_hzb     chord_hzb;
+typedef struct { uint32_t x0, y0, x1, y1; } chord_rect;   /* pixel rect [x0,x1) x [y0,y1) */
 
 enum {
     CHORD_OK = 0,
@@ -108,13 +109,19 @@ void*    chord_hzb_chain_ptr(chord_hzb* hzb, int which);
 uint64_t chord_hzb_chain_bytes(const chord_hzb* hzb);
 /* Byte offset of a mip inside the chain allocation. */
 uint64_t chord_hzb_mip_offset(const chord_hzb* hzb, uint32_t mip);
+/* ---- screen-tile partition across GPUs. A tile rect is cut on multiples of 64 px, so every 64x64 depth
+ * block (one texel of mip 5) belongs to exactly one tile. chord_build_hzb on a tiled frame fills only the tile's part
+ * of mips 0..5; the parts are exchanged with one all-gather of the packed regions (NCCL over NVLink, issued by the
+ * host on chord_ctx_stream) and mips 6.. are then rebuilt locally by chord_hzb_finish_top. */
+int chord_hzb_tile_bytes(const chord_hzb* hzb, const chord_rect* tile, uint64_t* bytes);
+int chord_hzb_pack_tile(chord_hzb* hzb, int which, const chord_rect* tile, void* dstDevice);
+int chord_hzb_unpack_tiles(chord_hzb* hzb, int which, const chord_rect* tiles, uint32_t n, const void* srcDevice, uint64_t slotBytes);
+int chord_hzb_finish_top(chord_frame* frame, int bMin, int bMax, chord_hzb* dst);
 /* Mark a chain filled from outside (after an all-gather) as valid history. */
 int  chord_hzb_set_valid(chord_hzb* hzb, int valid);
 int  chord_hzb_is_valid(const chord_hzb* hzb);
 
 /* ---- frame: GBufferTextures + per-view uniforms (renderer.cpp:175-263, render_textures.cpp:20-102) */
-typedef struct { uint32_t x0, y0, x1, y1; } chord_rect;   /* pixel rect [x0,x1) x [y0,y1) */
-
 int  chord_frame_create(chord_ctx* ctx, uint32_t width, uint32_t height, chord_frame** out);
 void chord_frame_destroy(chord_frame* frame);
 
