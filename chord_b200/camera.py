@@ -130,7 +130,17 @@ def fill_view(camera, jitter=(0.0, 0.0), last_view=None, frame_counter=0, sun_di
     bd['frameCounter'] = frame_counter
     bd['frameCounterMod8'] = frame_counter % 8
     bd['sunInfo']['direction'] = _normalize(sun_direction)
-    bd['atmosphere']['earthCenterKm'] = earth_center_km
+    at = bd['atmosphere']
+    at['earthCenterKm'] = earth_center_km
+    # Bruneton earth defaults (manager_atmosphere.cpp:518-544 units: km); only the fields lighting.hlsl reads matter
+    at['solar_irradiance'] = (1.474, 1.8504, 1.91198)
+    at['sun_angular_radius'] = 0.004675
+    at['bottom_radius'], at['top_radius'] = 6360.0, 6420.0
+    at['luminanceMode'] = 0
+    at['skySpectralRadianceToLumiance'] = (114974.9, 71305.95, 65310.55)
+    at['sunSpectralRadianceToLumiance'] = (98242.79, 69954.4, 66475.0)
+    at['ground_albedo'] = (0.1, 0.1, 0.1)
+    at['mu_s_min'] = -0.2
     if last_view is None:
         last_view = v
         v['bCameraCut'] = 1

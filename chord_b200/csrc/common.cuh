@@ -40,6 +40,8 @@ struct ObjectDerived {
     chord_float4x4 localToView;        // view.translatedWorldToView  * localToTranslatedWorld
     chord_float4x4 localToClipHzb0;    // view.translatedWorldToClipLastFrame * localToTranslatedWorldLastFrame
     chord_float4x4 localToClipHzb1;    // view.translatedWorldToClip * localToTranslatedWorld
+    chord_float4x4 localToClipNoJitter;      // view.translatedWorldToClip_NoJitter * localToTranslatedWorld
+    chord_float4x4 localToClipLastNoJitter;  // view.translatedWorldToClipLastFrame_NoJitter * localToTranslatedWorldLastFrame
 };
 
 struct FrameDev {

@@ -128,9 +128,9 @@ __device__ bool is_meshlet_visible(uint32_t switchFlags, const chord_float4* __r
 }
 
 // ------------------------------------------------------------------------------------------------ per-object prepare
-__global__ void __launch_bounds__(64) k_object_prepare(FrameDev f, ObjectDerived* __restrict__ out)
+__global__ void __launch_bounds__(96) k_object_prepare(FrameDev f, ObjectDerived* __restrict__ out)
 {
-    // one object per block, 64 threads = 4 matrices x 16 elements
+    // one object per block, 96 threads = 6 matrices x 16 elements
     const uint32_t o = blockIdx.x;
     const uint32_t which = threadIdx.x >> 4, e = threadIdx.x & 15u, c = e >> 2, r = e & 3u;
     const chord_GPUObjectGLTFPrimitive& obj = f.objects[o];
@@ -139,6 +139,8 @@ __global__ void __launch_bounds__(64) k_object_prepare(FrameDev f, ObjectDerived
     case 0:  A = f.iview->translatedWorldToClip.m;          B = obj.basicData.localToTranslatedWorld.m;          dst = out[o].localToClip.m; break;
     case 1:  A = f.view->translatedWorldToView.m;           B = obj.basicData.localToTranslatedWorld.m;          dst = out[o].localToView.m; break;
     case 2:  A = f.view->translatedWorldToClipLastFrame.m;  B = obj.basicData.localToTranslatedWorldLastFrame.m; dst = out[o].localToClipHzb0.m; break;
+    case 4:  A = f.view->translatedWorldToClip_NoJitter.m;  B = obj.basicData.localToTranslatedWorld.m;          dst = out[o].localToClipNoJitter.m; break;
+    case 5:  A = f.view->translatedWorldToClipLastFrame_NoJitter.m; B = obj.basicData.localToTranslatedWorldLastFrame.m; dst = out[o].localToClipLastNoJitter.m; break;
     default: A = f.view->translatedWorldToClip.m;           B = obj.basicData.localToTranslatedWorld.m;          dst = out[o].localToClipHzb1.m; break;
     }
     dst[c * 4 + r] = dot4f(A[r], A[4 + r], A[8 + r], A[12 + r], B[c * 4], B[c * 4 + 1], B[c * 4 + 2], B[c * 4 + 3]);
@@ -377,7 +379,7 @@ int launch_object_prepare(chord_frame* fr)
 {
     chord_ctx* ctx = fr->ctx;
     FrameDev f = make_frame_dev(fr);
-    k_object_prepare<<<fr->objectCount, 64, 0, ctx->stream>>>(f, fr->dDerived);
+    k_object_prepare<<<fr->objectCount, 96, 0, ctx->stream>>>(f, fr->dDerived);
     ctx->launches++;
     CHORD_CUDA(cudaGetLastError());
     return CHORD_OK;

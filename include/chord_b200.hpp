@@ -1,0 +1,123 @@
+// chord_b200.hpp — header-only C++17 shim over the C ABI (chord_b200.h), shaped like the reference's pass-graph API
+// (source/renderer/mesh/gltf_rendering.h:37-108, postprocessing/postprocessing.h:41-54, visibility_tile.h:22-34,
+// lighting.h:37).  RAII handles replace chord's ref-counted pool resources; errors throw std::runtime_error carrying
+// chord_last_error() (the reference would check()-crash).  No CUDA headers needed by the includer.
+#pragma once
+
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <utility>
+
+#include "chord_b200.h"
+
+namespace chord_b200 {
+
+inline void check(int rc, const char* what)
+{
+    if (rc != CHORD_OK) throw std::runtime_error(std::string(what) + ": " + chord_last_error());
+}
+
+struct CmdListDeleter { void operator()(chord_cmdlist* p) const { chord_cmdlist_destroy(p); } };
+struct HzbDeleter { void operator()(chord_hzb* p) const { chord_hzb_destroy(p); } };
+using CmdListRef = std::shared_ptr<chord_cmdlist>;     // CountAndCmdBuffer
+using HzbRef = std::shared_ptr<chord_hzb>;             // HZBContext
+
+class Frame;
+
+class Context {
+public:
+    explicit Context(int device) { check(chord_ctx_create(device, &m_ctx), "chord_ctx_create"); }
+    ~Context() { chord_ctx_destroy(m_ctx); }
+    Context(const Context&) = delete;
+    Context& operator=(const Context&) = delete;
+
+    void uploadScene(const chord_scene_desc& desc) { check(chord_scene_upload(m_ctx, &desc), "chord_scene_upload"); }
+    void setSwitchFlags(uint32_t f) { check(chord_ctx_set_switch_flags(m_ctx, f), "chord_ctx_set_switch_flags"); }
+    void sync() { check(chord_ctx_sync(m_ctx), "chord_ctx_sync"); }
+    void* stream() const { return chord_ctx_stream(m_ctx); }
+    chord_ctx* handle() const { return m_ctx; }
+
+    CmdListRef createCmdList(uint32_t capacity) const
+    {
+        chord_cmdlist* l = nullptr;
+        check(chord_cmdlist_create(m_ctx, capacity, &l), "chord_cmdlist_create");
+        return CmdListRef(l, CmdListDeleter{});
+    }
+    HzbRef createHzb(uint32_t w, uint32_t h) const
+    {
+        chord_hzb* z = nullptr;
+        check(chord_hzb_create(m_ctx, w, h, &z), "chord_hzb_create");
+        return HzbRef(z, HzbDeleter{});
+    }
+    inline std::unique_ptr<Frame> createFrame(uint32_t w, uint32_t h) const;
+
+private:
+    chord_ctx* m_ctx = nullptr;
+};
+
+class Frame {
+public:
+    Frame(const Context& ctx, uint32_t w, uint32_t h) : m_ctx(ctx), m_w(w), m_h(h)
+    { check(chord_frame_create(ctx.handle(), w, h, &m_frame), "chord_frame_create"); }
+    ~Frame() { chord_frame_destroy(m_frame); }
+    Frame(const Frame&) = delete;
+    Frame& operator=(const Frame&) = delete;
+    uint32_t width() const { return m_w; }
+    uint32_t height() const { return m_h; }
+    chord_frame* handle() const { return m_frame; }
+
+    // uniforms + addClearGbufferPass
+    void begin(const chord_PerframeCameraView& view, const chord_InstanceCullingViewInfo& iview,
+               const chord_GPUObjectGLTFPrimitive* objects, uint32_t objectCount,
+               uint32_t lod0MeshletCount, uint32_t meshletGroupCount, const chord_rect* tile = nullptr)
+    {
+        m_lod0 = lod0MeshletCount;
+        check(chord_frame_begin(m_frame, &view, &iview, objects, objectCount, lod0MeshletCount, meshletGroupCount, tile), "chord_frame_begin");
+    }
+    // instanceCulling
+    CmdListRef instanceCulling()
+    {
+        auto out = m_ctx.createCmdList(m_lod0);
+        check(chord_instance_culling(m_frame, out.get()), "chord_instance_culling");
+        return out;
+    }
+    // gltfVisibilityRenderingStage0: returns bShouldInvokeStage1, fills outRejected
+    bool visibilityStage0(const chord_hzb* lastFrameHzb, const CmdListRef& in, CmdListRef& outRejected)
+    {
+        int need = 0;
+        CmdListRef scratch, rejected;
+        if (lastFrameHzb && chord_hzb_is_valid(lastFrameHzb)) { scratch = m_ctx.createCmdList(m_lod0); rejected = m_ctx.createCmdList(m_lod0); }
+        check(chord_visibility_stage0(m_frame, lastFrameHzb, in.get(), scratch.get(), rejected.get(), &need), "chord_visibility_stage0");
+        m_keep[0] = scratch;                       // stream-ordered: keep alive until the next frame
+        outRejected = need ? rejected : CmdListRef();
+        return need != 0;
+    }
+    // gltfVisibilityRenderingStage1
+    void visibilityStage1(const HzbRef& thisFrameHzb, const CmdListRef& rejected)
+    {
+        auto scratch = m_ctx.createCmdList(m_lod0);
+        check(chord_visibility_stage1(m_frame, thisFrameHzb.get(), rejected.get(), scratch.get()), "chord_visibility_stage1");
+        m_keep[1] = scratch; m_keep[2] = rejected;
+    }
+    // buildHZB
+    HzbRef buildHZB(bool bMin, bool bMax, bool bValidRange)
+    {
+        auto h = m_ctx.createHzb(m_w, m_h);
+        check(chord_build_hzb(m_frame, bMin, bMax, bValidRange, h.get()), "chord_build_hzb");
+        return h;
+    }
+    void renderMesh(const CmdListRef& list) { check(chord_render_mesh(m_frame, list.get()), "chord_render_mesh"); }
+    void visibilityMark(const CmdListRef& post) { check(chord_visibility_mark(m_frame, post.get()), "chord_visibility_mark"); }
+    void lighting(const CmdListRef& post) { check(chord_lighting(m_frame, post.get()), "chord_lighting"); }
+
+private:
+    const Context& m_ctx;
+    chord_frame* m_frame = nullptr;
+    uint32_t m_w, m_h, m_lod0 = 0;
+    CmdListRef m_keep[3];
+};
+
+inline std::unique_ptr<Frame> Context::createFrame(uint32_t w, uint32_t h) const { return std::make_unique<Frame>(*this, w, h); }
+
+}  // namespace chord_b200

@@ -124,6 +124,18 @@ class Frame:
         return out
 
 
+def lighting(frame, vis64, post_cull, transmittance, irradiance):
+    """K11 on the CPU; returns (6, H, W, 4) float32 planes in CHORD_GBUF_* order."""
+    post_cull = np.ascontiguousarray(post_cull, dtype=abi.DrawCmd)
+    tr = np.ascontiguousarray(transmittance, dtype=np.float16)
+    ir = np.ascontiguousarray(irradiance, dtype=np.float16)
+    out = np.zeros((6, frame.height, frame.width, 4), dtype=np.float32)
+    ptrs = (C.c_void_p * 6)(*[out[i].ctypes.data for i in range(6)])
+    lib().oracle_lighting(C.byref(frame.c), C.c_void_p(vis64.ctypes.data), C.c_void_p(post_cull.ctypes.data),
+                          C.c_uint32(len(post_cull)), C.c_void_p(tr.ctypes.data), C.c_void_p(ir.ctypes.data), ptrs)
+    return out
+
+
 def decode(vis64, post_cull):
     post_cull = np.ascontiguousarray(post_cull, dtype=abi.DrawCmd)
     out = np.zeros(vis64.shape + (3,), dtype=np.uint32)

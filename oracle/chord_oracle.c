@@ -684,3 +684,208 @@ void oracle_visibility_mark(const oracle_frame* f, const uint64_t* vis64,
             memcpy(&markerUint4[4 * ((size_t)ty * mw + tx)], mk, 16);
         }
 }
+
+/* ------------------------------------------------------------------ K11: lighting.hlsl:270-381 (PBR branch)
+ * Floating point within 1e-5 (north_star), so plain fp32 expressions in the HLSL's order; no bit-exactness claim.
+ * Pins chosen where the reference leaves it to the GPU: LUT SampleLevel = exact fp32 bilinear with clamp-to-edge on the
+ * RGBA16F texels; pow(x,5) = repeated multiplication; sRGB_2_AP1 folded in double and rounded to float. */
+typedef struct { float x, y, z; } v3;
+static inline v3 v3_(float x, float y, float z) { v3 r = {x, y, z}; return r; }
+static inline v3 v3add(v3 a, v3 b) { return v3_(a.x + b.x, a.y + b.y, a.z + b.z); }
+static inline v3 v3sub(v3 a, v3 b) { return v3_(a.x - b.x, a.y - b.y, a.z - b.z); }
+static inline v3 v3mul(v3 a, v3 b) { return v3_(a.x * b.x, a.y * b.y, a.z * b.z); }
+static inline v3 v3s(v3 a, float s) { return v3_(a.x * s, a.y * s, a.z * s); }
+static inline float v3dot(v3 a, v3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+static inline v3 v3norm(v3 a) { float l = sqrtf(v3dot(a, a)); return v3_(a.x / l, a.y / l, a.z / l); }
+static inline float clampf(float v, float lo, float hi) { return fminf(fmaxf(v, lo), hi); }
+
+static void srgb_to_ap1_matrix(float m[9])
+{
+    /* colorspace.h:109: XYZ_2_AP1 * (D65_2_D60 * sRGB_2_XYZ) */
+    static const double X2A[9] = { 1.6410233797, -0.3248032942, -0.2364246952, -0.6636628587, 1.6153315917, 0.0167563477, 0.0117218943, -0.0082844420, 0.9883948585 };
+    static const double CAT[9] = { 1.0130349146, 0.0061052578, -0.0149709436, 0.0076982301, 0.9981633521, -0.0050320385, -0.0028413174, 0.0046851567, 0.9245061375 };
+    static const double S2X[9] = { 0.4123907993, 0.3575843394, 0.1804807884, 0.2126390059, 0.7151686788, 0.0721923154, 0.0193308187, 0.1191947798, 0.9505321522 };
+    double t[9], o[9];
+    for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) { t[r * 3 + c] = 0; for (int k = 0; k < 3; k++) t[r * 3 + c] += CAT[r * 3 + k] * S2X[k * 3 + c]; }
+    for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) { o[r * 3 + c] = 0; for (int k = 0; k < 3; k++) o[r * 3 + c] += X2A[r * 3 + k] * t[k * 3 + c]; }
+    for (int i = 0; i < 9; i++) m[i] = (float)o[i];
+}
+static inline v3 mat3_mul(const float m[9], v3 v)
+{ return v3_(m[0] * v.x + m[1] * v.y + m[2] * v.z, m[3] * v.x + m[4] * v.y + m[5] * v.z, m[6] * v.x + m[7] * v.y + m[8] * v.z); }
+
+static v3 sample_lut_bilinear(const uint16_t* lut, int W, int H, float u, float v)
+{
+    float x = u * (float)W - 0.5f, y = v * (float)H - 0.5f;
+    float fx0 = floorf(x), fy0 = floorf(y);
+    float fx = x - fx0, fy = y - fy0;
+    int x0 = (int)fx0, y0 = (int)fy0, x1 = x0 + 1, y1 = y0 + 1;
+    if (x0 < 0) x0 = 0; if (x0 > W - 1) x0 = W - 1; if (x1 < 0) x1 = 0; if (x1 > W - 1) x1 = W - 1;
+    if (y0 < 0) y0 = 0; if (y0 > H - 1) y0 = H - 1; if (y1 < 0) y1 = 0; if (y1 > H - 1) y1 = H - 1;
+    float o[3];
+    for (int c = 0; c < 3; c++) {
+        float a = oracle_f16_to_f32(lut[(y0 * W + x0) * 4 + c]), b = oracle_f16_to_f32(lut[(y0 * W + x1) * 4 + c]);
+        float d = oracle_f16_to_f32(lut[(y1 * W + x0) * 4 + c]), e = oracle_f16_to_f32(lut[(y1 * W + x1) * 4 + c]);
+        float top = a + (b - a) * fx, bot = d + (e - d) * fx;
+        o[c] = top + (bot - top) * fy;
+    }
+    return v3_(o[0], o[1], o[2]);
+}
+
+static inline float tex_coord_from_unit(float x, int size) { return 0.5f / (float)size + x * (1.0f - 1.0f / (float)size); }
+
+/* atmosphere.hlsli:1063-1088 */
+static v3 sun_and_sky_irradiance(const chord_AtmosphereParameters* at, const uint16_t* trLut, const uint16_t* irLut, const float ap1[9],
+                                 v3 p, v3 normal, v3 sunDir, v3* skyOut)
+{
+    float r = sqrtf(v3dot(p, p));
+    float mu_s = v3dot(p, sunDir) / r;
+    v3 skyL = at->luminanceMode != 0 ? v3_(at->skySpectralRadianceToLumiance.x, at->skySpectralRadianceToLumiance.y, at->skySpectralRadianceToLumiance.z) : v3_(1, 1, 1);
+    /* GetIrradiance (atmosphere.hlsli:894-902, :847-856) */
+    float x_r = (r - at->bottom_radius) / (at->top_radius - at->bottom_radius);
+    float x_mu_s = mu_s * 0.5f + 0.5f;
+    v3 irr = sample_lut_bilinear(irLut, 64, 16, tex_coord_from_unit(x_mu_s, 64), tex_coord_from_unit(x_r, 16));
+    v3 sky = v3s(v3s(irr, 1.0f + v3dot(normal, p) / r), 0.5f);
+    sky = v3mul(sky, skyL);
+    *skyOut = mat3_mul(ap1, sky);
+    v3 sunL = at->luminanceMode != 0 ? v3_(at->sunSpectralRadianceToLumiance.x, at->sunSpectralRadianceToLumiance.y, at->sunSpectralRadianceToLumiance.z) : v3_(1, 1, 1);
+    /* GetTransmittanceToSun (atmosphere.hlsli:315-324) + GetTransmittanceTextureUvFromRMu (:193-215) */
+    float sin_h = at->bottom_radius / r;
+    float cos_h = -sqrtf(fmaxf(1.0f - sin_h * sin_h, 0.0f));
+    float Hh = sqrtf(at->top_radius * at->top_radius - at->bottom_radius * at->bottom_radius);
+    float rho = sqrtf(fmaxf(r * r - at->bottom_radius * at->bottom_radius, 0.0f));
+    float disc = r * r * (mu_s * mu_s - 1.0f) + at->top_radius * at->top_radius;
+    float d = fmaxf(-r * mu_s + sqrtf(fmaxf(disc, 0.0f)), 0.0f);
+    float d_min = at->top_radius - r, d_max = rho + Hh;
+    float x_mu = (d - d_min) / (d_max - d_min), xr = rho / Hh;
+    v3 tr = sample_lut_bilinear(trLut, 256, 64, tex_coord_from_unit(x_mu, 256), tex_coord_from_unit(xr, 64));
+    float e0 = -sin_h * at->sun_angular_radius, e1 = sin_h * at->sun_angular_radius;
+    float t = clampf(((mu_s - cos_h) - e0) / (e1 - e0), 0.0f, 1.0f);
+    float sm = t * t * (3.0f - 2.0f * t);
+    v3 trs = v3s(tr, sm);
+    v3 sunRad = v3s(v3mul(v3_(at->solar_irradiance.x, at->solar_irradiance.y, at->solar_irradiance.z), trs), fmaxf(v3dot(normal, sunDir), 0.0f));
+    return mat3_mul(ap1, v3mul(sunL, sunRad));
+}
+
+static inline double storage_to_double(chord_uint2 u) { uint64_t b = (uint64_t)u.x | ((uint64_t)u.y << 32); double d; memcpy(&d, &b, 8); return d; }
+
+void oracle_lighting(const oracle_frame* f, const uint64_t* vis64, const chord_draw_cmd* postCull, uint32_t postCullCount,
+                     const uint16_t* trLut, const uint16_t* irLut, float* const planes[6])
+{
+    (void)postCullCount;
+    float ap1[9]; srgb_to_ap1_matrix(ap1);
+    const chord_PerframeCameraView* view = f->view;
+    const chord_AtmosphereParameters* at = &view->basicData.atmosphere;
+    const float tsx = 1.0f / (float)f->width, tsy = 1.0f / (float)f->height;     /* visibilityTexelSize (lighting.cpp) */
+    const size_t npx = (size_t)f->width * f->height;
+    for (int k = 0; k < 6; k++) memset(planes[k], 0, npx * 16);
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic, 4)
+#endif
+    for (uint32_t py = f->tile.y0; py < f->tile.y1; py++)
+        for (uint32_t px = f->tile.x0; px < f->tile.x1; px++) {
+            const size_t pi = (size_t)py * f->width + px;
+            uint32_t id = (uint32_t)(vis64[pi] & 0xFFFFFFFFu);
+            if (id == 0) continue;
+            uint32_t tri, inst; chord_decode_triangle_instance(id, &tri, &inst);
+            const chord_draw_cmd cmd = postCull[inst];
+            object_refs o = get_object(f, cmd.objectId);
+            if (o.material->materialType != CHORD_LIGHTING_TYPE_GLTF_PBR) continue;
+            const chord_float4x4* l2w = &o.object->basicData.localToTranslatedWorld;
+            chord_float4x4 l2c, l2cNJ, l2cLast;
+            mat_mul(&view->translatedWorldToClip, l2w, &l2c);
+            mat_mul(&view->translatedWorldToClip_NoJitter, l2w, &l2cNJ);
+            mat_mul(&view->translatedWorldToClipLastFrame_NoJitter, &o.object->basicData.localToTranslatedWorldLastFrame, &l2cLast);
+            /* getTriangleMiscInfo (nanite_shared.hlsli:111-179) */
+            const chord_GPUGLTFMeshlet* m = &o.datas->meshlets[cmd.meshletId];
+            const uint32_t V = m->vertexTriangleCount & 0xFFu;
+            const uint32_t idx = o.datas->meshletData[m->dataOffset + V + tri];
+            v3 posRS[3], nrm[3]; f4 hs[3]; v3 hsNJ[3], hsLast[3]; float uv[3][2];
+            for (int i = 0; i < 3; i++) {
+                uint32_t vi = o.prim->vertexOffset + o.datas->meshletData[m->dataOffset + ((idx >> (i * 8)) & 0xFFu)];
+                const float* p = &o.datas->positions[(size_t)vi * 3];
+                f4 w = mat_mul_vec(l2w, p[0], p[1], p[2], 1.0f);
+                posRS[i] = v3_(w.x, w.y, w.z);
+                hs[i] = mat_mul_vec(&l2c, p[0], p[1], p[2], 1.0f);
+                f4 a = mat_mul_vec(&l2cNJ, p[0], p[1], p[2], 1.0f); hsNJ[i] = v3_(a.x, a.y, a.w);
+                f4 b = mat_mul_vec(&l2cLast, p[0], p[1], p[2], 1.0f); hsLast[i] = v3_(b.x, b.y, b.w);
+                uv[i][0] = o.datas->uv0 ? o.datas->uv0[(size_t)vi * 2] : 0.0f; uv[i][1] = o.datas->uv0 ? o.datas->uv0[(size_t)vi * 2 + 1] : 0.0f;
+                const float* n = &o.datas->normals[(size_t)vi * 3];
+                /* mul(float4(n,0), translatedWorldToLocal): row vector times matrix */
+                const float* M = o.object->basicData.translatedWorldToLocal.m;
+                v3 nn = v3_(n[0] * M[0] + n[1] * M[1] + n[2] * M[2], n[0] * M[4] + n[1] * M[5] + n[2] * M[6], n[0] * M[8] + n[1] * M[9] + n[2] * M[10]);
+                nrm[i] = v3norm(nn);
+            }
+            (void)uv;
+            /* calculateTriangleBarycentrics (base.hlsli:457-498) */
+            const float su = ((float)px + 0.5f) * tsx, sv = ((float)py + 0.5f) * tsy;
+            const float pcx = 2.0f * (su - 0.5f), pcy = 2.0f * (0.5f - sv);
+            const float rw0 = 1.0f / hs[0].w, rw1 = 1.0f / hs[1].w, rw2 = 1.0f / hs[2].w;
+            const float p0x = hs[0].x * rw0, p0y = hs[0].y * rw0, p1x = hs[1].x * rw1, p1y = hs[1].y * rw1, p2x = hs[2].x * rw2, p2y = hs[2].y * rw2;
+            const float cdx0 = p2y - p1y, cdx1 = p0y - p2y, cdx2 = p1y - p0y;          /* Pos201Y - Pos120Y */
+            const float cdy0 = p1x - p2x, cdy1 = p2x - p0x, cdy2 = p0x - p1x;          /* Pos120X - Pos201X */
+            const float C0 = cdx0 * (pcx - p1x) + cdy0 * (pcy - p1y);
+            const float C1 = cdx1 * (pcx - p2x) + cdy1 * (pcy - p2y);
+            const float C2 = cdx2 * (pcx - p0x) + cdy2 * (pcy - p0y);
+            const float G0 = C0 * rw0, G1 = C1 * rw1, G2 = C2 * rw2;
+            const float Hs = C0 * rw0 + C1 * rw1 + C2 * rw2;
+            const float rH = 1.0f / Hs;
+            const float b0 = G0 * rH, b1 = G1 * rH, b2 = G2 * rH;
+            /* motion vector */
+            v3 mp = v3add(v3add(v3s(hsNJ[0], b0), v3s(hsNJ[1], b1)), v3s(hsNJ[2], b2));
+            v3 ml = v3add(v3add(v3s(hsLast[0], b0), v3s(hsLast[1], b1)), v3s(hsLast[2], b2));
+            const float mvx = (ml.x / ml.z - mp.x / mp.z) * 0.5f, mvy = (ml.y / ml.z - mp.y / mp.z) * -0.5f;
+            v3 posR = v3add(v3add(v3s(posRS[0], b0), v3s(posRS[1], b1)), v3s(posRS[2], b2));
+            /* material (untextured: builtin white base colour, transparent emissive) */
+            const chord_GLTFMaterialGPUData* mat = o.material;
+            v3 base = mat3_mul(ap1, v3_(1.0f * mat->baseColorFactor.x, 1.0f * mat->baseColorFactor.y, 1.0f * mat->baseColorFactor.z));
+            v3 vnrm = v3add(v3add(v3s(nrm[0], b0), v3s(nrm[1], b1)), v3s(nrm[2], b2));
+            v3 pnrm = vnrm;
+            const float rough = mat->roughnessFactor;
+            const float metal = mat->metallicFactor >= 1.0f ? 0.0f : mat->metallicFactor;      /* getFallbackMetallic, gltf.h:53-58 */
+            const float ao = 1.0f;
+            /* gltfMetallicRoughnessPBR_Lighting (lighting.hlsl:203-268) */
+            const v3 f0 = v3_(0.04f, 0.04f, 0.04f);
+            v3 diffuseColor = v3s(v3mul(base, v3_(1.0f - f0.x, 1.0f - f0.y, 1.0f - f0.z)), 1.0f - metal);
+            v3 specColor = v3_(f0.x + (base.x - f0.x) * metal, f0.y + (base.y - f0.y) * metal, f0.z + (base.z - f0.z) * metal);
+            const float reflectance = fmaxf(fmaxf(specColor.x, specColor.y), specColor.z);
+            const float r90 = clampf(reflectance * 50.0f, 0.0f, 1.0f);
+            v3 pix2cam = v3norm(posR);
+            const double ckx = storage_to_double(view->cameraPositionWS_km.x), cky = storage_to_double(view->cameraPositionWS_km.y), ckz = storage_to_double(view->cameraPositionWS_km.z);
+            v3 pkm = v3_((float)((double)(posR.x / 1000.0f) + ckx), (float)((double)(posR.y / 1000.0f) + cky), (float)((double)(posR.z / 1000.0f) + ckz));
+            v3 sunDirTo = v3_(-view->basicData.sunInfo.direction.x, -view->basicData.sunInfo.direction.y, -view->basicData.sunInfo.direction.z);
+            v3 sky;
+            v3 sun = sun_and_sky_irradiance(at, trLut, irLut, ap1, v3sub(pkm, v3_(at->earthCenterKm.x, at->earthCenterKm.y, at->earthCenterKm.z)), pnrm, sunDirTo, &sky);
+            v3 radiance = v3add(sun, sky);
+            /* evaluateDirectionalDirectLight (lighting.hlsli:166-184): pointToLight = -direction, view = -pixelToCamera */
+            v3 n = v3norm(pnrm), vv = v3norm(v3s(pix2cam, -1.0f)), l = v3norm(sunDirTo), hh = v3norm(v3add(l, vv));
+            const float NdotL = clampf(v3dot(n, l), 0, 1), NdotV = clampf(v3dot(n, vv), 0, 1), NdotH = clampf(v3dot(n, hh), 0, 1), VdotH = clampf(v3dot(vv, hh), 0, 1);
+            v3 diff = v3_(0, 0, 0), spec = v3_(0, 0, 0);
+            if (NdotL > 0.0f || NdotV > 0.0f) {
+                float om = clampf(1.0f - VdotH, 0.0f, 1.0f); float om2 = om * om; float p5 = om2 * om2 * om;
+                v3 F = v3_(specColor.x + (r90 - specColor.x) * p5, specColor.y + (r90 - specColor.y) * p5, specColor.z + (r90 - specColor.z) * p5);
+                float a2 = rough * rough;
+                /* V_SmithGGXCorrelated(NdotL, NdotV, roughness): first parameter is named NoV in bsdf.hlsli:30 */
+                float GGXV = NdotV * sqrtf(NdotL * NdotL * (1.0f - a2) + a2);
+                float GGXL = NdotL * sqrtf(NdotV * NdotV * (1.0f - a2) + a2);
+                float GGX = GGXV + GGXL;
+                float Vis = GGX > 0.0f ? 0.5f / GGX : 0.0f;
+                float ff = (NdotH * a2 - NdotH) * NdotH + 1.0f;
+                float D = a2 / (3.14159265358979323846f * ff * ff + 0.000001f);
+                v3 lam = v3s(diffuseColor, 1.0f / 3.14159265358979323846f);
+                v3 dc = v3mul(v3_(1.0f - F.x, 1.0f - F.y, 1.0f - F.z), lam);
+                v3 sc = v3s(F, Vis * D);
+                diff = v3s(dc, NdotL); spec = v3s(sc, NdotL);
+            }
+            diff = v3mul(diff, radiance); spec = v3mul(spec, radiance);
+            const float expo = 10.0f * (at->luminanceMode == 0 ? 1.0f : 1e-5f);
+            diff = v3s(diff, expo); spec = v3s(spec, expo);
+            v3 color = v3add(diff, spec);
+            if (isnan(color.x) || isnan(color.y) || isnan(color.z)) color = v3_(0, 0, 0);
+            float* o0 = planes[0] + pi * 4; o0[0] = color.x; o0[1] = color.y; o0[2] = color.z; o0[3] = 0.0f;
+            float* o1 = planes[1] + pi * 4; o1[0] = base.x; o1[1] = base.y; o1[2] = base.z; o1[3] = 0.0f;
+            float* o2 = planes[2] + pi * 4; o2[0] = vnrm.x * 0.5f + 0.5f; o2[1] = vnrm.y * 0.5f + 0.5f; o2[2] = vnrm.z * 0.5f + 0.5f; o2[3] = 1.0f;
+            float* o3 = planes[3] + pi * 4; o3[0] = pnrm.x * 0.5f + 0.5f; o3[1] = pnrm.y * 0.5f + 0.5f; o3[2] = pnrm.z * 0.5f + 0.5f; o3[3] = 1.0f;
+            float* o4 = planes[4] + pi * 4; o4[0] = mvx; o4[1] = mvy; o4[2] = 0.0f; o4[3] = 0.0f;
+            float* o5 = planes[5] + pi * 4; o5[0] = ao; o5[1] = rough; o5[2] = metal; o5[3] = 0.0f;
+        }
+}

@@ -60,6 +60,11 @@ void oracle_build_hzb(const uint64_t* vis64, uint32_t width, uint32_t height,
 void oracle_visibility_mark(const oracle_frame* f, const uint64_t* vis64,
                             const chord_draw_cmd* postCull, uint32_t postCullCount, uint32_t* markerUint4);
 
+/* K11: lighting.hlsl:270-381, PBR branch, untextured materials.  planes[6] = CHORD_GBUF_* order, 4 floats per pixel,
+ * pre-quantisation fp32 values; untouched pixels are 0.  LUTs are RGBA16F bit patterns (256x64 and 64x16). */
+void oracle_lighting(const oracle_frame* f, const uint64_t* vis64, const chord_draw_cmd* postCull, uint32_t postCullCount,
+                     const uint16_t* transmittanceLut, const uint16_t* irradianceLut, float* const planes[6]);
+
 /* decode through the post-instance-cull list: (object, meshlet, tri) or 0xFFFFFFFF x3 */
 void oracle_decode(const uint64_t* vis64, uint32_t pixelCount, const chord_draw_cmd* postCull, uint32_t postCullCount,
                    uint32_t* triples);

@@ -87,3 +87,25 @@ def test_product_never_imports_oracle():
             if f.endswith(('.py', '.cu', '.cuh', '.h')):
                 text = open(os.path.join(dirpath, f)).read()
                 assert 'import oracle' not in text and 'from oracle' not in text and 'chord_oracle' not in text, f
+
+
+def test_cpp_shim_compiles_and_links(tmp_path):
+    """include/chord_b200.hpp (the binding INTEGRATION.md hands to a chord maintainer) builds against the .so with g++."""
+    src = tmp_path / 'shim.cpp'
+    src.write_text('''
+#include <chord_b200.hpp>
+#include <cstdio>
+int main() {
+    if (chord_abi_version() != CHORD_B200_ABI_VERSION) return 2;
+    try { chord_b200::Context ctx(0); }                       // no GPU here: must throw, not fall back
+    catch (const std::exception& e) { std::printf("threw: %s\\n", e.what()); return 0; }
+    return 0;
+}
+''')
+    exe = tmp_path / 'shim'
+    cxx = '/usr/bin/g++' if os.path.exists('/usr/bin/g++') else 'g++'
+    libdir = os.path.join(ROOT, 'chord_b200')
+    subprocess.check_call([cxx, '-std=c++17', '-I', os.path.join(ROOT, 'include'), str(src), '-o', str(exe),
+                           '-L', libdir, '-l:libchord_b200.so', f'-Wl,-rpath,{libdir}'])
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr

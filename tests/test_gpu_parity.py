@@ -176,3 +176,31 @@ def test_tile_scissor(gpu_ctx):
         ot, _ = oracle.Frame(scene, view, iview, objects, w, h, tile=tile).render_mesh(cmds)
         _assert_vis_equal(part, ot, f'tile {tile}')
     _assert_vis_equal(acc, full, 'union of tiles')
+
+
+def test_lighting_resolve(gpu_ctx):
+    """K9-K11: tile classification + PBR resolve. Floating point: |gpu - oracle| <= 1e-5 (north_star tolerance) on the
+    pre-quantisation fp32 G-buffer planes; untouched pixels must stay cleared."""
+    from cases import city_frames
+    w, h = 640, 360
+    scene, info, frames = city_frames(frames=2, w=w, h=h)
+    gpu_ctx.upload_scene(scene)
+    tr, ir = synth.synthetic_luts()
+    gpu_ctx.upload_luts(tr, ir)
+    r = renderer.DeferredRenderer(gpu_ctx, w, h, do_resolve=True)
+    prev = None
+    for f in frames:
+        post = r.render(f['camera'], f['objects'], info['lod0MeshletCount'], info['meshletGroupCount'], view=f['view'], iview=f['iview'])
+        ref = oracle.run_frame(scene, f['view'], f['iview'], f['objects'], w, h, info['lod0MeshletCount'], prev)
+        _assert_vis_equal(r.frame.vis64(), ref['vis64'], 'vis64')
+        assert np.array_equal(r.frame.tile_marker(), ref['frame'].visibility_mark(ref['vis64'], ref['post_cull']))
+        g = oracle.lighting(ref['frame'], ref['vis64'], ref['post_cull'], tr, ir)
+        names = ['color', 'baseColor', 'vertexNormal', 'pixelNormal', 'motion', 'aoRoughMetal']
+        for i, name in enumerate(names):
+            got = r.frame.gbuffer(i)
+            err = np.abs(got - g[i])
+            tol = 1e-5 + 1e-5 * np.abs(g[i])
+            assert (err <= tol).all(), f'{name}: max err {err.max()} at {np.unravel_index(err.argmax(), err.shape)}'
+            assert np.array_equal(got.any(axis=-1), g[i].any(axis=-1)), f'{name}: coverage differs'
+        assert g[0].max() > 0.05 and np.abs(g[4]).max() > 0 or prev is None
+        prev = ref['hzb']
