@@ -44,6 +44,8 @@ def parse():
     ap.add_argument('--impl', default='chord_b200', choices=['chord_b200', 'reference'])
     ap.add_argument('--meshlets', type=int, default=N_MESHLETS, help='override the stream length (debug only)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-frame', action='store_true', help='skip the secondary full-frame (S3 stand-in) measurement')
+    ap.add_argument('--frame-only', action='store_true', help='profiling aid: run only the full-frame workload and print its dict')
     return ap.parse_args()
 
 
@@ -165,6 +167,67 @@ def cpu_baseline(dev_scene, view, iview, objects, budget_s=12.0):
                       f'OpenMP over meshlets; CPU restatement of chord (reference not runnable offline)'}
 
 
+def frame_benchmark(ctx, stream, torch, steps=20, width=W4K, height=H4K, n_buildings=371):
+    """S3 stand-in (BASELINE configs[2]): procedural city, ~3.8 M LOD-0 triangles, full reference frame sequence
+    (instance cull -> stage 0 on last frame's HZB -> HZB -> stage 1 -> HZB -> tile mark -> PBR resolve) along a camera
+    path; per-pass CUDA-event times at the reference's timer cut points (renderer.cpp:322-363)."""
+    from chord_b200 import camera as cam, renderer, synth
+    scene, camera, objects, info = synth.city_scene(n_buildings=n_buildings, patches=4, lods=3, width=width, height=height, seed=3, n_protos=48)
+    ctx.upload_scene(scene)
+    tr, ir = synth.synthetic_luts()
+    ctx.upload_luts(tr, ir)
+    r = renderer.DeferredRenderer(ctx, width, height, do_resolve=True)
+    labels = ['GLTF Instance Culling', 'GLTF Visibility Stage0', 'BuildHZB Post Prepass Stage0', 'GLTF Visibility Stage1',
+              'BuildHZB', 'VisibilityTileMarker', 'lightingTile']
+    acc = {k: 0.0 for k in labels}
+    frames = []
+    last_view, last_cam = None, None
+    total = steps + 3
+    for fi in range(total):
+        c = cam.Camera(camera.position + np.array([0.15 * fi, 0.01 * fi, -0.6 * fi]), camera.front, width=width, height=height)
+        objs = synth.refill_objects(info['transforms'], c, camera_last=last_cam)
+        view = cam.fill_view(c, last_view=last_view, frame_counter=fi)
+        frames.append((c, objs, view, cam.fill_instance_view(view)))
+        last_view, last_cam = view, c
+    f = r.frame
+    lod0, groups = info['lod0MeshletCount'], info['meshletGroupCount']
+    t_frames = []
+    for fi, (c, objs, view, iview) in enumerate(frames):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(9)]
+        ev[0].record(stream)
+        f.begin(view, iview, objs, lod0, groups)
+        rc = renderer.GLTFRenderContext(f, len(objs), lod0, groups, r.pool)
+        ev[1].record(stream)
+        r.pool.release(r.post_cull)
+        post = renderer.instanceCulling(rc); ev[2].record(stream)
+        need1, rejected = renderer.gltfVisibilityRenderingStage0(rc, r.history_hzb, post); ev[3].record(stream)
+        if need1:
+            tmp = renderer.buildHZB(rc, True, False, False); ev[4].record(stream)
+            renderer.gltfVisibilityRenderingStage1(rc, tmp, rejected); ev[5].record(stream)
+            r.pool.release(tmp)
+        else:
+            ev[4].record(stream); ev[5].record(stream)
+        r.pool.release(rejected)
+        hzb = renderer.buildHZB(rc, True, True, True); ev[6].record(stream)
+        renderer.visibilityMark(rc, post); ev[7].record(stream)
+        renderer.lighting(rc, post); ev[8].record(stream)
+        r.pool.release(r.history_hzb)
+        r.history_hzb, r.last_view, r.post_cull = hzb, view, post
+        torch.cuda.synchronize()
+        if fi >= 3:
+            for k, lab in enumerate(labels):
+                acc[lab] += ev[k + 1].elapsed_time(ev[k + 2])
+            t_frames.append(ev[0].elapsed_time(ev[8]))
+    n = len(t_frames)
+    ms = float(np.mean(t_frames))
+    stats = f.raster_stats()
+    return {'workload': f'S3 stand-in: procedural city, {scene.total_triangles} triangles in {scene.total_meshlets} meshlets (all LODs), '
+                        f'{len(frames[0][1])} objects, {width}x{height}, two-phase HZB + resolve, camera path',
+            'frames_per_s': 1000.0 / ms, 'ms_per_frame': ms, 'frames_timed': n,
+            'pass_us': {k: 1000.0 * v / n for k, v in acc.items()},
+            'post_cull_meshlets_last_frame': int(post.count()), 'raster_stats_total': stats}
+
+
 def main():
     args = parse()
     if args.impl == 'reference':
@@ -188,6 +251,9 @@ def main():
     torch.cuda.set_device(local_rank)
     stream = torch.cuda.ExternalStream(ctx.stream, device=local_rank)
 
+    if args.frame_only:
+        print(json.dumps(frame_benchmark(ctx, stream, torch, steps=args.steps)), flush=True)
+        return
     M = args.meshlets
     from chord_b200 import synth_device
     scene, camera, objects, cmds = synth_device.patch_stream_scene_device(M, W4K, H4K, seed=5, device=f'cuda:{local_rank}')
@@ -320,6 +386,11 @@ def main():
         }
         if not args.no_cpu_baseline and n_gpus == 1:
             line['cpu_baseline'] = cpu_baseline(scene, view, iview, objects)
+        if n_gpus == 1 and not args.no_frame:
+            try:
+                line['frame'] = frame_benchmark(ctx, stream, torch)
+            except Exception as e:      # the headline metric must not depend on the secondary workload
+                line['frame'] = {'error': repr(e)}
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()

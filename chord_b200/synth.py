@@ -317,14 +317,17 @@ class _PrimBuilder:
         return abi.HostScene([datas], np.array(self.prims), np.array(materials))
 
 
-def city_scene(n_buildings=26, patches=4, lods=3, width=1920, height=1080, seed=2, ground_patches=8):
+def city_scene(n_buildings=26, patches=4, lods=3, width=1920, height=1080, seed=2, ground_patches=8, n_protos=3):
     """S2/S3 stand-in: a grid of box buildings (instanced from 3 prototypes with a quadtree LOD DAG per face) on a
     coarse ground slab, camera at street level so that near-plane clipping, large triangles, LOD cuts and occlusion
     all occur.  ``n_buildings=26, patches=4`` ~ 266 k LOD-0 triangles (S2); ``n_buildings=371`` ~ 3.8 M (S3)."""
     rng = np.random.default_rng(seed)
     b = _PrimBuilder()
-    protos = [b.add_primitive(_box_primitive(sz, patches, lods), patches, lods)
-              for sz in ((10.0, 30.0, 10.0), (14.0, 18.0, 12.0), (8.0, 45.0, 8.0))]
+    sizes = [(10.0, 30.0, 10.0), (14.0, 18.0, 12.0), (8.0, 45.0, 8.0)]
+    if n_protos > 3:
+        prng = np.random.default_rng(seed + 1000)
+        sizes += [(float(prng.uniform(7, 15)), float(prng.uniform(12, 50)), float(prng.uniform(7, 15))) for _ in range(n_protos - 3)]
+    protos = [b.add_primitive(_box_primitive(sz, patches, lods), patches, lods) for sz in sizes[:max(n_protos, 1)]]
     side = int(math.ceil(math.sqrt(n_buildings)))
     pitch = 40.0
     extent = side * pitch
