@@ -198,6 +198,7 @@ struct chord_frame {
     float tanHalfFovy;
     // instance culling scratch
     uint32_t* objGroupCount; uint32_t* objGroupBase; uint32_t* totalGroups;
+    void* bvhEntries; uint32_t* bvhBits; uint32_t* bvhCtrl; uint32_t bvhCapacity, bvhWords;
     // raster
     void* largeTris; uint32_t* largeCounters; uint32_t largeTriCapacity, largeItemCapacity; void* largeItems;
     unsigned long long* stats;   // device chord_raster_stats
@@ -213,6 +214,7 @@ FrameDev make_frame_dev(const chord_frame* f);
 // kernels' host launchers (each returns a CHORD_* status)
 int launch_object_prepare(chord_frame* f);
 int launch_instance_culling(chord_frame* f, chord_cmdlist* out);
+int launch_instance_culling_bvh(chord_frame* f, chord_cmdlist* out);
 int launch_hzb_culling(chord_frame* f, const chord_hzb* hzb, int firstStage, chord_cmdlist* in, chord_cmdlist* outVis, chord_cmdlist* outRej);
 int launch_render_mesh(chord_frame* f, chord_cmdlist* list);
 int launch_build_hzb(chord_frame* f, int bMin, int bMax, int bRange, chord_hzb* dst);

@@ -297,6 +297,8 @@ int chord_frame_create(chord_ctx* ctx, uint32_t width, uint32_t height, chord_fr
     CHORD_CUDA(cudaMalloc(&f->dView, sizeof(chord_PerframeCameraView)));
     CHORD_CUDA(cudaMalloc(&f->dIView, sizeof(chord_InstanceCullingViewInfo)));
     CHORD_CUDA(cudaMalloc(&f->totalGroups, 16));
+    CHORD_CUDA(cudaMalloc(&f->bvhCtrl, 32));
+    CHORD_CUDA(cudaMemsetAsync(f->bvhCtrl, 0, 32, ctx->stream));
     f->largeTriCapacity = kLargeTriCapacity; f->largeItemCapacity = kLargeItemCapacity;
     CHORD_CUDA(cudaMalloc(&f->largeTris, (size_t)48 * f->largeTriCapacity));
     CHORD_CUDA(cudaMalloc(&f->largeItems, (size_t)8 * f->largeItemCapacity));
@@ -320,6 +322,7 @@ void chord_frame_destroy(chord_frame* f)
     cudaStreamSynchronize(f->ctx->stream);
     cudaFree(f->vis64); cudaFree(f->dView); cudaFree(f->dIView); cudaFree(f->dObjects); cudaFree(f->dDerived);
     cudaFree(f->objGroupCount); cudaFree(f->objGroupBase); cudaFree(f->totalGroups);
+    cudaFree(f->bvhEntries); cudaFree(f->bvhBits); cudaFree(f->bvhCtrl);
     cudaFree(f->works); cudaFree(f->redoList); cudaFree(f->deferred);
     cudaFree(f->largeTris); cudaFree(f->largeItems); cudaFree(f->largeCounters); cudaFree(f->stats);
     cudaFree(f->tileMarker); cudaFree(f->tileList); cudaFree(f->tileCount);
@@ -371,6 +374,22 @@ int chord_instance_culling(chord_frame* f, chord_cmdlist* out)
 {
     CHORD_REQUIRE(f && out && f->begun, "frame not begun");
     return launch_instance_culling(f, out);
+}
+
+int chord_instance_culling_bvh(chord_frame* f, chord_cmdlist* out)
+{
+    CHORD_REQUIRE(f && out && f->begun, "frame not begun");
+    return launch_instance_culling_bvh(f, out);
+}
+
+int chord_readback_bvh_candidates(chord_frame* f, uint32_t* hostBits, uint32_t words, uint32_t* outCtrl5)
+{
+    CHORD_REQUIRE(f && hostBits && f->bvhBits, "no BVH traversal has run on this frame");
+    CHORD_REQUIRE(words <= f->bvhWords, "words");
+    CHORD_CUDA(cudaMemcpyAsync(hostBits, f->bvhBits, sizeof(uint32_t) * (size_t)words, cudaMemcpyDeviceToHost, f->ctx->stream));
+    if (outCtrl5) CHORD_CUDA(cudaMemcpyAsync(outCtrl5, f->bvhCtrl, 20, cudaMemcpyDeviceToHost, f->ctx->stream));
+    CHORD_CUDA(cudaStreamSynchronize(f->ctx->stream));
+    return CHORD_OK;
 }
 
 int chord_hzb_culling(chord_frame* f, const chord_hzb* hzb, int firstStage, chord_cmdlist* in, chord_cmdlist* outVisible, chord_cmdlist* outRejected)

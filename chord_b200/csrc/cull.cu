@@ -200,8 +200,11 @@ __global__ void __launch_bounds__(1024) k_object_scan(const uint32_t* __restrict
 // ------------------------------------------------------------------------------------------------ K2
 __global__ void __launch_bounds__(kCullBlock) k_group_cull(FrameDev f, const uint32_t* __restrict__ objGroupBase, const uint32_t* __restrict__ totalGroups,
                                                            unsigned long long* __restrict__ scanStatus, uint32_t* __restrict__ ticket,
-                                                           chord_draw_cmd* __restrict__ outCmds, uint32_t* __restrict__ outCount, uint32_t outCapacity)
+                                                           chord_draw_cmd* __restrict__ outCmds, uint32_t* __restrict__ outCount, uint32_t outCapacity,
+                                                           const uint32_t* __restrict__ candidateBits, const uint32_t* __restrict__ bvhCtrl)
 {
+    // candidateBits != null: only groups the BVH traversal reached are evaluated (bvhCtrl[4] != 0: queue overflowed, ignore the bits)
+    const bool useBits = candidateBits != nullptr && bvhCtrl[4] == 0u;
     __shared__ uint32_t sTile;
     __shared__ uint32_t sWarp[kCullBlock / 32];
     __shared__ uint32_t sBase;
@@ -216,7 +219,7 @@ __global__ void __launch_bounds__(kCullBlock) k_group_cull(FrameDev f, const uin
         const uint32_t t = tile * kCullBlock + threadIdx.x;
 
         uint32_t visCount = 0, visId[CHORD_CLUSTER_GROUP_MERGE_MAX], objectId = 0;
-        if (t < total) {
+        if (t < total && (!useBits || ((candidateBits[t >> 5] >> (t & 31u)) & 1u))) {
             // canonical order: thread t <-> (object, group) through the scanned bases (binary search: last base <= t)
             uint32_t lo = 0, hi = f.objectCount;
             while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (objGroupBase[mid] <= t) lo = mid; else hi = mid; }
@@ -374,6 +377,77 @@ __global__ void __launch_bounds__(kCullBlock) k_hzb_cull(FrameDev f, HzbDev hzb,
     }
 }
 
+// ------------------------------------------------------------------------------------------------ N4: BVH traversal
+// Persistent-warp traversal of the 8-ary cluster-group BVH (gltf.h:16-24; builder nanite_builder.cpp:77-416), which the
+// reference uploads but never walks.  One warp per node: lanes 0..7 test the eight child spheres,
+// a ballot compacts the survivors into a global work queue, all 32 lanes mark the node's leaf groups as candidates.
+// ctrl = {head, tail, pending, done, overflow}.  A node sphere bounds the PARENT-error spheres below it, so a node that
+// projects to <= 1 px (minus a 1e-4 margin) cannot contain a group that passes the LOD test: pruning never changes the
+// final list, the exact per-group test still runs in k_group_cull on the candidates.
+constexpr float kBvhPruneThreshold = CHORD_ERROR_PIXEL_THRESHOLD * (1.0f - 1e-4f);
+
+__global__ void __launch_bounds__(128) k_bvh_seed(FrameDev f, const uint32_t* __restrict__ objGroupCount, unsigned long long* __restrict__ entries,
+                                                  uint32_t capacity, uint32_t* __restrict__ ctrl)
+{
+    const uint32_t o = blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= f.objectCount || objGroupCount[o] == 0u) return;
+    const uint32_t slot = atomicAdd(&ctrl[1], 1u);
+    if (slot >= capacity) { ctrl[4] = 1u; return; }
+    atomicAdd(&ctrl[2], 1u);
+    st_volatile_u64(&entries[slot], (unsigned long long)o);           // node 0 in the high word
+}
+
+__global__ void __launch_bounds__(128) k_bvh_traverse(FrameDev f, const uint32_t* __restrict__ objGroupBase, unsigned long long* __restrict__ entries,
+                                                      uint32_t capacity, uint32_t* __restrict__ ctrl, uint32_t* __restrict__ bits)
+{
+    const uint32_t lane = threadIdx.x & 31u;
+    volatile uint32_t* vctrl = ctrl;
+    while (true) {
+        uint32_t idx = 0;
+        if (lane == 0) idx = atomicAdd(&ctrl[0], 1u);
+        idx = __shfl_sync(0xffffffffu, idx, 0);
+        if (idx >= capacity) return;
+        unsigned long long e;
+        while (true) {
+            e = ld_volatile_u64(&entries[idx]);
+            if (e != ~0ull) break;
+            if (vctrl[3] != 0u || vctrl[2] == 0u) return;               // traversal finished: this slot will never be filled
+            __nanosleep(64);
+        }
+        const uint32_t objectId = (uint32_t)(e & 0xFFFFFFFFull), nodeIndex = (uint32_t)(e >> 32);
+        const chord_GPUObjectGLTFPrimitive& obj = f.objects[objectId];
+        const chord_GLTFPrimitiveBuffer& prim = f.scene.prims[obj.GLTFPrimitiveDetail];
+        const DatasDev& datas = f.scene.datas[prim.primitiveDatasBufferId];
+        const chord_GPUBVHNode* node = &datas.bvhNodes[prim.bvhNodeOffset + nodeIndex];
+        // leaves -> candidate bits (canonical index = base of the object + group index inside the primitive)
+        const uint32_t leafOffset = node->leafMeshletGroupOffset, leafCount = node->leafMeshletGroupCount;
+        const uint32_t base = objGroupBase[objectId] + leafOffset;
+        for (uint32_t k = lane; k < leafCount; k += 32u) { const uint32_t b = base + k; atomicOr(&bits[b >> 5], 1u << (b & 31u)); }
+        // children
+        uint32_t child = CHORD_UNVALID_ID; bool keep = false;
+        if (lane < CHORD_BVH_LEVEL_NODE_COUNT) child = node->children[lane];
+        if (child != CHORD_UNVALID_ID) {
+            const chord_float4 sp = datas.bvhNodes[prim.bvhNodeOffset + child].sphere;
+            const f4 v = mat_mul_vec(f.derived[objectId].localToView.m, sp.x, sp.y, sp.z, 1.0f);
+            const float pe = project_sphere_to_screen(v.x, v.y, v.z, __fmul_rn(obj.basicData.scaleExtractFromMatrix.w, sp.w), f.view->renderDimension.y, f.tanHalfFovy);
+            keep = !(pe > 0.0f && pe <= kBvhPruneThreshold);
+        }
+        const uint32_t mask = __ballot_sync(0xffffffffu, keep);
+        uint32_t n = (uint32_t)__popc(mask), slotBase = 0;
+        if (n) {
+            if (lane == 0) slotBase = atomicAdd(&ctrl[1], n);
+            slotBase = __shfl_sync(0xffffffffu, slotBase, 0);
+            if (slotBase + n > capacity) { if (lane == 0) ctrl[4] = 1u; n = 0; }
+            else if (keep) st_volatile_u64(&entries[slotBase + __popc(mask & ((1u << lane) - 1u))], (unsigned long long)objectId | ((unsigned long long)child << 32));
+        }
+        if (lane == 0) {
+            // pending += n children, -= 1 for this node (two's complement add)
+            const uint32_t after = atomicAdd(&ctrl[2], n - 1u) + (n - 1u);
+            if (after == 0u) { __threadfence(); vctrl[3] = 1u; }
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ launchers
 int launch_object_prepare(chord_frame* fr)
 {
@@ -385,7 +459,11 @@ int launch_object_prepare(chord_frame* fr)
     return CHORD_OK;
 }
 
-int launch_instance_culling(chord_frame* fr, chord_cmdlist* out)
+static int launch_instance_culling_impl(chord_frame* fr, chord_cmdlist* out, bool useBvh);
+int launch_instance_culling(chord_frame* fr, chord_cmdlist* out) { return launch_instance_culling_impl(fr, out, false); }
+int launch_instance_culling_bvh(chord_frame* fr, chord_cmdlist* out) { return launch_instance_culling_impl(fr, out, true); }
+
+static int launch_instance_culling_impl(chord_frame* fr, chord_cmdlist* out, bool useBvh)
 {
     chord_ctx* ctx = fr->ctx;
     FrameDev f = make_frame_dev(fr);
@@ -395,9 +473,29 @@ int launch_instance_culling(chord_frame* fr, chord_cmdlist* out)
     CHORD_CUDA(cudaMemsetAsync(out->count, 0, 4, ctx->stream));
     k_object_cull<<<(fr->objectCount + 127) / 128, 128, 0, ctx->stream>>>(f, fr->objGroupCount);
     k_object_scan<<<1, 1024, 0, ctx->stream>>>(fr->objGroupCount, fr->objGroupBase, fr->objectCount, fr->totalGroups);
+    const uint32_t* bits = nullptr;
+    if (useBvh) {
+        for (uint32_t i = 0; i < ctx->scene.nDatas; i++) CHORD_REQUIRE(ctx->datasHost[i].bvhNodes != nullptr, "scene was uploaded without BVH nodes");
+        const uint32_t cap = 2u * fr->meshletGroupCount + fr->objectCount + 64u;
+        const uint32_t words = (fr->meshletGroupCount + 31u) / 32u + 1u;
+        if (cap > fr->bvhCapacity) {
+            cudaFree(fr->bvhEntries); cudaFree(fr->bvhBits); fr->bvhEntries = nullptr; fr->bvhBits = nullptr; fr->bvhCapacity = 0;
+            CHORD_CUDA(cudaMalloc(&fr->bvhEntries, sizeof(unsigned long long) * (size_t)cap));
+            CHORD_CUDA(cudaMalloc(&fr->bvhBits, sizeof(uint32_t) * (size_t)words));
+            if (!fr->bvhCtrl) CHORD_CUDA(cudaMalloc(&fr->bvhCtrl, 32));
+            fr->bvhCapacity = cap; fr->bvhWords = words;
+        }
+        CHORD_CUDA(cudaMemsetAsync(fr->bvhEntries, 0xFF, sizeof(unsigned long long) * (size_t)cap, ctx->stream));
+        CHORD_CUDA(cudaMemsetAsync(fr->bvhBits, 0, sizeof(uint32_t) * (size_t)words, ctx->stream));
+        CHORD_CUDA(cudaMemsetAsync(fr->bvhCtrl, 0, 32, ctx->stream));
+        k_bvh_seed<<<(fr->objectCount + 127) / 128, 128, 0, ctx->stream>>>(f, fr->objGroupCount, (unsigned long long*)fr->bvhEntries, cap, fr->bvhCtrl);
+        k_bvh_traverse<<<(uint32_t)ctx->smCount * 2u, 128, 0, ctx->stream>>>(f, fr->objGroupBase, (unsigned long long*)fr->bvhEntries, cap, fr->bvhCtrl, fr->bvhBits);
+        ctx->launches += 2;
+        bits = fr->bvhBits;
+    }
     uint32_t grid = tiles < (uint32_t)ctx->smCount * 8u ? tiles : (uint32_t)ctx->smCount * 8u;
     k_group_cull<<<grid, kCullBlock, 0, ctx->stream>>>(f, fr->objGroupBase, fr->totalGroups, ctx->scanStatus, ctx->scanTicket,
-                                                       out->cmds, out->count, out->capacity);
+                                                       out->cmds, out->count, out->capacity, bits, fr->bvhCtrl);
     ctx->launches += 3;
     CHORD_CUDA(cudaGetLastError());
     return CHORD_OK;

@@ -20,7 +20,8 @@ SYMBOLS = [
     'chord_hzb_create', 'chord_hzb_destroy', 'chord_hzb_info', 'chord_hzb_readback', 'chord_hzb_readback_valid_range',
     'chord_hzb_chain_ptr', 'chord_hzb_chain_bytes', 'chord_hzb_mip_offset', 'chord_hzb_set_valid', 'chord_hzb_is_valid',
     'chord_hzb_finish_top', 'chord_hzb_tile_bytes', 'chord_hzb_pack_tile', 'chord_hzb_unpack_tiles',
-    'chord_frame_create', 'chord_frame_destroy', 'chord_frame_begin', 'chord_instance_culling', 'chord_hzb_culling',
+    'chord_frame_create', 'chord_frame_destroy', 'chord_frame_begin', 'chord_instance_culling', 'chord_instance_culling_bvh',
+    'chord_readback_bvh_candidates', 'chord_hzb_culling',
     'chord_render_mesh', 'chord_visibility_stage0', 'chord_visibility_stage1', 'chord_build_hzb',
     'chord_visibility_mark', 'chord_atmosphere_luts_upload', 'chord_lighting',
     'chord_readback_vis64', 'chord_readback_visibility32', 'chord_readback_depth32', 'chord_readback_decoded',
@@ -268,6 +269,16 @@ class Frame:
 
     def instance_culling(self, out: CmdList):
         lib().chord_instance_culling(self.h, out.h)
+
+    def instance_culling_bvh(self, out: CmdList):
+        lib().chord_instance_culling_bvh(self.h, out.h)
+
+    def bvh_candidates(self, total_groups):
+        words = (total_groups + 31) // 32 + 1
+        bits = np.zeros(words, dtype=np.uint32)
+        ctrl = np.zeros(5, dtype=np.uint32)
+        lib().chord_readback_bvh_candidates(self.h, _p(bits), C.c_uint32(words), _p(ctrl))
+        return bits, ctrl
 
     def hzb_culling(self, hzb: Hzb, first_stage, inp: CmdList, out_visible: CmdList, out_rejected: CmdList = None):
         lib().chord_hzb_culling(self.h, hzb.h, C.c_int(1 if first_stage else 0), inp.h, out_visible.h,

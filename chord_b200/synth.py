@@ -47,6 +47,98 @@ def default_material(two_sided=0, alpha_mode=0, material_type=abi.LIGHTING_TYPE_
     return m
 
 
+def build_bvh(groups, group_indices):
+    """Cluster-group BVH over the parent-error spheres, restating NaniteBuilder::buildBVHTree
+    (source/asset/nanite_builder.cpp:77-416): groups without a parent (parentError == FLT_MAX) are leaves of the
+    root; the others are split 2x2x2 by median along the longest axis of their parent-sphere bounds until fewer than
+    8 remain (or depth 13); nodes are flattened breadth-first and the GROUP ARRAY IS REORDERED so that every node's
+    leaves are contiguous (flattenBVH :215-311).  Returns (groups, group_indices, nodes) in the flattened order."""
+    groups = np.asarray(groups, dtype=abi.GPUGLTFMeshletGroup)
+    n = len(groups)
+    pc = groups['parentPosCenter'].astype(np.float32)
+    pe = groups['parentError'].astype(np.float32)
+    has_parent = pe < np.float32(3e38)
+    ids = np.nonzero(has_parent)[0]
+
+    class Node:
+        __slots__ = ('mn', 'mx', 'children', 'leaves', 'depth', 'flat')
+
+        def __init__(self, depth):
+            self.mn = np.full(3, FLT_MAX, dtype=np.float32); self.mx = np.full(3, -FLT_MAX, dtype=np.float32)
+            self.children, self.leaves, self.depth, self.flat = [], [], depth, -1
+
+    def bounds(sel):
+        if len(sel) == 0:
+            return np.full(3, FLT_MAX, dtype=np.float32), np.full(3, -FLT_MAX, dtype=np.float32)
+        return (pc[sel] - pe[sel, None]).min(axis=0), (pc[sel] + pe[sel, None]).max(axis=0)
+
+    def longest(mn, mx):
+        d = mx - mn
+        ax = 0
+        if d[1] >= d[0] and d[1] >= d[2]:
+            ax = 1
+        if d[2] >= d[0] and d[2] >= d[1]:
+            ax = 2
+        return ax
+
+    def halves(sel, mn, mx):
+        ax = longest(mn, mx)
+        order = sel[np.argsort(pc[sel, ax], kind='stable')]
+        m = len(order)
+        return [order[i * m // 2:(i + 1) * m // 2] for i in range(2)]
+
+    root = Node(0)
+    root.leaves = list(np.nonzero(~has_parent)[0])
+    root.mn, root.mx = bounds(ids)
+    queue = [(root, ids)]
+    while queue:
+        node, sel = queue.pop(0)
+        if len(sel) == 0:
+            continue
+        if len(sel) < 8 or node.depth == 13:
+            node.leaves += list(sel)
+            continue
+        for h0 in halves(sel, node.mn, node.mx):
+            mn0, mx0 = bounds(h0)
+            for h1 in halves(h0, mn0, mx0):
+                mn1, mx1 = bounds(h1)
+                for h2 in halves(h1, mn1, mx1):
+                    c = Node(node.depth + 1)
+                    c.mn, c.mx = bounds(h2)
+                    node.children.append(c)
+                    queue.append((c, h2))
+    # flatten breadth-first; leaves of each node become contiguous in the new group array
+    order, flat, q = [], [], [root]
+    while q:
+        nd = q.pop(0)
+        nd.flat = len(flat)
+        flat.append(nd)
+        q += nd.children
+    nodes = np.zeros(len(flat), dtype=abi.GPUBVHNode)
+    new_groups, new_indices = [], []
+    for nd in flat:
+        rec = nodes[nd.flat]
+        with np.errstate(over='ignore', invalid='ignore'):
+            c = np.float32(0.5) * (nd.mx + nd.mn)
+        with np.errstate(over='ignore', invalid='ignore'):       # a root without parented groups has infinite bounds
+            rec['sphere'] = (c[0], c[1], c[2], np.float32(0.5) * np.float32(np.linalg.norm((nd.mx - nd.mn).astype(np.float32))))
+        rec['leafMeshletGroupOffset'], rec['leafMeshletGroupCount'] = len(new_groups), len(nd.leaves)
+        for gi in nd.leaves:
+            g = groups[gi].copy()
+            idx = group_indices[g['meshletOffset']:g['meshletOffset'] + g['meshletCount']]
+            g['meshletOffset'] = len(new_indices)
+            new_indices += list(idx)
+            new_groups.append(g)
+        ch = np.full(8, abi.UNVALID_ID, dtype=np.uint32)
+        for k, cnode in enumerate(nd.children):
+            ch[k] = cnode.flat
+        rec['children'] = ch
+    for nd in reversed(flat):
+        nodes[nd.flat]['bvhNodeCount'] = 1 + sum(int(nodes[c.flat]['bvhNodeCount']) for c in nd.children)
+    assert nodes[0]['bvhNodeCount'] == len(flat) and len(new_groups) == n
+    return np.array(new_groups, dtype=abi.GPUGLTFMeshletGroup), np.array(new_indices, dtype=np.uint32), nodes
+
+
 def _meshlet_records(pos_by_meshlet, data_offsets, V, T, lod, normal):
     """Bounds / cone for meshlets given their vertex positions (M, V, 3)."""
     M = pos_by_meshlet.shape[0]
@@ -87,8 +179,9 @@ def single_meshlet_scene(width=256, height=256, seed=1):
     prim = np.zeros(1, dtype=abi.GLTFPrimitiveBuffer)
     prim['posMin'], prim['posMax'], prim['posAverage'] = pos.min(axis=0), pos.max(axis=0), pos.mean(axis=0)
     prim['vertexCount'], prim['meshletGroupCount'] = V, 1
+    groups, gidx, nodes = build_bvh(groups, np.zeros(1, dtype=np.uint32))
     scene = abi.HostScene([dict(meshlets=meshlets, positions=pos, normals=normals, uv0=uv, tangents=tang,
-                                meshletData=data, groups=groups, groupIndices=np.zeros(1, dtype=np.uint32))],
+                                meshletData=data, groups=groups, groupIndices=gidx, bvhNodes=nodes)],
                           prim, np.array([default_material()]))
     camera = cam.Camera((0, 0, 0), (0, 0, -1), width=width, height=height)
     objects = np.array([cam.fill_object(np.eye(4), camera, 0, 0)])
@@ -160,8 +253,11 @@ def patch_stream_scene(n_meshlets, width=3840, height=2160, seed=5, area_range=(
     prim['posMax'] = meshlets['posMax'].max(axis=0)
     prim['posAverage'] = centers.mean(axis=0)
     prim['vertexCount'], prim['meshletGroupCount'] = len(flat), G
+    nodes = np.zeros(1, dtype=abi.GPUBVHNode)          # every group is a root-level leaf (no parent): one node
+    nodes['children'] = abi.UNVALID_ID
+    nodes['bvhNodeCount'], nodes['leafMeshletGroupOffset'], nodes['leafMeshletGroupCount'] = 1, 0, G
     scene = abi.HostScene([dict(meshlets=meshlets, positions=flat, meshletData=data.reshape(-1), groups=groups,
-                                groupIndices=np.arange(M, dtype=np.uint32))],
+                                groupIndices=np.arange(M, dtype=np.uint32), bvhNodes=nodes)],
                           prim, np.array([default_material()]))
     camera = cam.Camera((0, 0, 0), (0, 0, -1), fovy=fovy, width=width, height=height)
     objects = np.array([cam.fill_object(np.eye(4), camera, 0, 0)])
@@ -277,13 +373,15 @@ class _PrimBuilder:
         self.pos, self.nrm, self.uv, self.tan, self.data, self.meshlets = [], [], [], [], [], []
         self.groups, self.group_indices = [], []
         self.prims = []
-        self.nv = self.nd = self.nm = self.ng = self.ngi = 0
+        self.nv = self.nd = self.nm = self.ng = self.ngi = self.nn = 0
+        self.nodes = []
         self.lod0 = []
 
     def add_primitive(self, faces, patches, lods):
         v0, m0, g0, gi0 = self.nv, self.nm, self.ng, self.ngi
         lod0 = 0
         allpos = []
+        pgroups, pindices = [], []
         for (o, du, dv, nrm) in faces:
             f = _face_lod_chain(o, du, dv, patches, nrm, self.nv - v0, self.nd, self.nm - m0, lods)
             self.pos.append(f['positions']); self.nrm.append(f['normals']); self.uv.append(f['uv0'])
@@ -295,16 +393,23 @@ class _PrimBuilder:
                 g = np.zeros((), dtype=abi.GPUGLTFMeshletGroup)
                 g['clusterPosCenter'], g['error'] = oc, oe
                 g['parentPosCenter'], g['parentError'] = pc, pe
-                g['meshletOffset'], g['meshletCount'] = self.ngi - gi0, len(mids)
-                self.groups.append(g)
-                self.group_indices.append(mids)
-                self.ng += 1; self.ngi += len(mids)
+                g['meshletOffset'], g['meshletCount'] = sum(len(x) for x in pindices), len(mids)
+                pgroups.append(g)
+                pindices.append(mids)
+        # cluster-group BVH of this primitive; the builder reorders the groups (nanite_builder.cpp:215-311)
+        bg, bi, bn = build_bvh(np.array(pgroups), np.concatenate(pindices))
+        self.groups += list(bg)
+        self.group_indices.append(bi)
+        self.nodes.append(bn)
+        self.ng += len(bg); self.ngi += len(bi)
         ap = np.concatenate(allpos)
         p = np.zeros((), dtype=abi.GLTFPrimitiveBuffer)
         p['posMin'], p['posMax'], p['posAverage'] = ap.min(axis=0), ap.max(axis=0), ap.mean(axis=0)
         p['vertexOffset'], p['vertexCount'] = v0, self.nv - v0
         p['meshletOffset'] = m0
         p['meshletGroupOffset'], p['meshletGroupIndicesOffset'], p['meshletGroupCount'] = g0, gi0, self.ng - g0
+        p['bvhNodeOffset'] = self.nn
+        self.nn += len(bn)
         self.prims.append(p)
         self.lod0.append(lod0)
         return len(self.prims) - 1
@@ -313,7 +418,7 @@ class _PrimBuilder:
         datas = dict(meshlets=np.concatenate(self.meshlets), positions=np.concatenate(self.pos),
                      normals=np.concatenate(self.nrm), uv0=np.concatenate(self.uv), tangents=np.concatenate(self.tan),
                      meshletData=np.concatenate(self.data), groups=np.array(self.groups),
-                     groupIndices=np.concatenate(self.group_indices))
+                     groupIndices=np.concatenate(self.group_indices), bvhNodes=np.concatenate(self.nodes))
         return abi.HostScene([datas], np.array(self.prims), np.array(materials))
 
 

@@ -142,6 +142,13 @@ int chord_frame_begin(chord_frame* frame,
  * in canonical order (object, group, meshlet-in-group); slot == index. */
 int chord_instance_culling(chord_frame* frame, chord_cmdlist* out);
 
+/* Same result through a persistent-warp traversal of the 8-ary cluster-group BVH (GPUBVHNode, gltf.h:16-24; built by
+ * nanite_builder.cpp:313-416 and uploaded by the reference, but never walked there: instance_culling.hlsl:96-99). Nodes
+ * whose parent-error bound projects below one pixel are skipped; the list is identical to chord_instance_culling. */
+int chord_instance_culling_bvh(chord_frame* frame, chord_cmdlist* out);
+/* candidate bit per (visible object, group) in canonical order + {head, tail, pending, done, overflow} of the traversal */
+int chord_readback_bvh_candidates(chord_frame* frame, uint32_t* hostBits, uint32_t words, uint32_t* outCtrl5);
+
 /* detail::hzbCulling (instance_culling.cpp:286-351; hzb_mainview_culling.hlsl:35-213).
  * phase 0: last frame's matrices + HZB, also writes the rejected list. phase 1: this frame's. */
 int chord_hzb_culling(chord_frame* frame, const chord_hzb* hzb, int firstStage,

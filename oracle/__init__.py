@@ -82,6 +82,23 @@ class Frame:
         assert n <= capacity, f'oracle_instance_culling overflow {n} > {capacity}'
         return out[:n].copy()
 
+    def instance_culling_bvh(self, capacity):
+        """Same list through the cluster-group BVH; returns (cmds, candidate group count)."""
+        out = np.zeros(max(capacity, 1), dtype=abi.DrawCmd)
+        cand = C.c_uint32()
+        lib().oracle_instance_culling_bvh.restype = C.c_uint32
+        n = lib().oracle_instance_culling_bvh(C.byref(self.c), C.c_void_p(out.ctypes.data), C.c_uint32(capacity), C.byref(cand))
+        assert n <= capacity
+        return out[:n].copy(), cand.value
+
+    def bvh_candidates(self, total_groups):
+        words = (total_groups + 31) // 32 + 1
+        bits = np.zeros(words, dtype=np.uint32)
+        tot = C.c_uint32()
+        lib().oracle_bvh_candidates.restype = C.c_uint32
+        n = lib().oracle_bvh_candidates(C.byref(self.c), C.c_void_p(bits.ctypes.data), C.c_uint32(words), C.byref(tot))
+        return bits, n, tot.value
+
     def render_mesh(self, cmds, vis64=None):
         cmds = np.ascontiguousarray(cmds, dtype=abi.DrawCmd)
         if vis64 is None:

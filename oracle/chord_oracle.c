@@ -250,6 +250,106 @@ uint32_t oracle_instance_culling(const oracle_frame* f, chord_draw_cmd* out, uin
     return count;
 }
 
+/* ------------------------------------------------------------------ N4: cluster-group BVH traversal
+ * The reference builds and uploads the BVH (nanite_builder.cpp:313-416) but never traverses it.  A node's
+ * sphere bounds the PARENT-error spheres of every group below it, so when it projects to <= 1 px (with a 1e-4 safety
+ * margin against rounding) every such group fails the "parent still too coarse" half of the LOD test and the subtree is
+ * skipped.  Groups of visited nodes are only CANDIDATES; the exact per-group test stays the flat one, so the final list
+ * is identical to oracle_instance_culling. bits[] has one bit per (visible-object, group) in canonical order. */
+#define BVH_PRUNE_THRESHOLD (CHORD_ERROR_PIXEL_THRESHOLD * (1.0f - 1e-4f))
+
+static void bvh_visit(const oracle_frame* f, const object_refs* o, const chord_float4x4* localToView, float tanHalfFovy,
+                      uint32_t nodeIndex, uint32_t groupBase, uint32_t* bits)
+{
+    const chord_GPUBVHNode* n = &o->datas->bvhNodes[o->prim->bvhNodeOffset + nodeIndex];
+    for (uint32_t k = 0; k < n->leafMeshletGroupCount; k++) {
+        uint32_t b = groupBase + n->leafMeshletGroupOffset + k;
+        bits[b >> 5] |= 1u << (b & 31u);
+    }
+    for (int c = 0; c < CHORD_BVH_LEVEL_NODE_COUNT; c++) {
+        if (n->children[c] == CHORD_UNVALID_ID) continue;
+        const chord_GPUBVHNode* ch = &o->datas->bvhNodes[o->prim->bvhNodeOffset + n->children[c]];
+        f4 v = mat_mul_vec(localToView, ch->sphere.x, ch->sphere.y, ch->sphere.z, 1.0f);
+        f4 s = { v.x, v.y, v.z, o->object->basicData.scaleExtractFromMatrix.w * ch->sphere.w };
+        float e = project_sphere_to_screen(s, f->view->renderDimension.y, tanHalfFovy);
+        if (e > 0.0f && e <= BVH_PRUNE_THRESHOLD) continue;      /* whole subtree: parent error below one pixel */
+        bvh_visit(f, o, localToView, tanHalfFovy, n->children[c], groupBase, bits);
+    }
+}
+
+/* returns the number of candidate groups; totalGroups receives the number of (visible-object, group) slots */
+uint32_t oracle_bvh_candidates(const oracle_frame* f, uint32_t* bits, uint32_t bitWords, uint32_t* totalGroups)
+{
+    const float tanHalfFovy = tanf(0.5f * f->view->cameraFovy);
+    memset(bits, 0, sizeof(uint32_t) * bitWords);
+    uint32_t base = 0;
+    for (uint32_t objectId = 0; objectId < f->objectCount; objectId++) {
+        object_refs o = get_object(f, objectId);
+        const chord_float4x4* l2w = &o.object->basicData.localToTranslatedWorld;
+        chord_float4x4 localToClip; mat_mul(&f->iview->translatedWorldToClip, l2w, &localToClip);
+        int visible = 1;
+        f3 c = { (o.prim->posMin.x + o.prim->posMax.x) * 0.5f, (o.prim->posMin.y + o.prim->posMax.y) * 0.5f, (o.prim->posMin.z + o.prim->posMax.z) * 0.5f };
+        f3 e = { o.prim->posMax.x - c.x, o.prim->posMax.y - c.y, o.prim->posMax.z - c.z };
+        if (has_flag(f->switchFlags, CHORD_FLAG_FRUSTUM_CULL_BIT)) {
+            if (is_ortho(&localToClip)) visible = !ortho_frustum_culling(c, e, &localToClip);
+            else                         visible = !frustum_culling(f->iview->frustumPlanesRS, c, e, l2w);
+        }
+        if (!visible) continue;
+        chord_float4x4 localToView; mat_mul(&f->view->translatedWorldToView, l2w, &localToView);
+        if (o.datas->bvhNodes) bvh_visit(f, &o, &localToView, tanHalfFovy, 0, base, bits);
+        base += o.prim->meshletGroupCount;
+    }
+    if (totalGroups) *totalGroups = base;
+    uint32_t n = 0;
+    for (uint32_t w = 0; w < bitWords; w++) n += (uint32_t)__builtin_popcount(bits[w]);
+    return n;
+}
+
+/* instance culling through the BVH: identical output to oracle_instance_culling */
+uint32_t oracle_instance_culling_bvh(const oracle_frame* f, chord_draw_cmd* out, uint32_t capacity, uint32_t* candidateGroups)
+{
+    uint32_t total = 0;
+    for (uint32_t i = 0; i < f->objectCount; i++) total += get_object(f, i).prim->meshletGroupCount;
+    const uint32_t words = (total + 31) / 32 + 1;
+    uint32_t* bits = (uint32_t*)calloc(words, 4);
+    uint32_t cand = oracle_bvh_candidates(f, bits, words, NULL);
+    if (candidateGroups) *candidateGroups = cand;
+    const float tanHalfFovy = tanf(0.5f * f->view->cameraFovy);
+    uint32_t count = 0, base = 0;
+    for (uint32_t objectId = 0; objectId < f->objectCount; objectId++) {
+        object_refs o = get_object(f, objectId);
+        const chord_float4x4* l2w = &o.object->basicData.localToTranslatedWorld;
+        chord_float4x4 localToClip; mat_mul(&f->iview->translatedWorldToClip, l2w, &localToClip);
+        int visible = 1;
+        f3 c = { (o.prim->posMin.x + o.prim->posMax.x) * 0.5f, (o.prim->posMin.y + o.prim->posMax.y) * 0.5f, (o.prim->posMin.z + o.prim->posMax.z) * 0.5f };
+        f3 e = { o.prim->posMax.x - c.x, o.prim->posMax.y - c.y, o.prim->posMax.z - c.z };
+        if (has_flag(f->switchFlags, CHORD_FLAG_FRUSTUM_CULL_BIT)) {
+            if (is_ortho(&localToClip)) visible = !ortho_frustum_culling(c, e, &localToClip);
+            else                         visible = !frustum_culling(f->iview->frustumPlanesRS, c, e, l2w);
+        }
+        if (!visible) continue;
+        chord_float4x4 localToView; mat_mul(&f->view->translatedWorldToView, l2w, &localToView);
+        for (uint32_t g = 0; g < o.prim->meshletGroupCount; g++) {
+            const uint32_t b = base + g;
+            if (!(bits[b >> 5] & (1u << (b & 31u)))) continue;
+            const chord_GPUGLTFMeshletGroup* grp = &o.datas->groups[o.prim->meshletGroupOffset + g];
+            if (!is_meshlet_group_visible(f->view->renderDimension.y, tanHalfFovy, o.object, &localToView, grp)) continue;
+            for (uint32_t i = 0; i < grp->meshletCount; i++) {
+                uint32_t idx = o.datas->groupIndices[i + grp->meshletOffset + o.prim->meshletGroupIndicesOffset];
+                uint32_t meshletIndex = o.prim->meshletOffset + idx;
+                const chord_GPUGLTFMeshlet* m = &o.datas->meshlets[meshletIndex];
+                if (is_meshlet_visible(f->switchFlags, f->iview->frustumPlanesRS, o.object, l2w, &localToClip, m, o.material)) {
+                    if (count < capacity) { out[count].objectId = objectId; out[count].meshletId = meshletIndex; out[count].slot = count; }
+                    count++;
+                }
+            }
+        }
+        base += o.prim->meshletGroupCount;
+    }
+    free(bits);
+    return count;
+}
+
 /* ------------------------------------------------------------------ K3 */
 static inline int firstbithigh_i(int32_t v)
 {

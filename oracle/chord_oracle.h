@@ -33,6 +33,10 @@ typedef struct {
 /* K1+K2: instance_culling.hlsl:47-208 in canonical (object, group, meshlet) order. returns count. */
 uint32_t oracle_instance_culling(const oracle_frame* f, chord_draw_cmd* out, uint32_t capacity);
 
+/* N4: the same list through the cluster-group BVH (nanite_builder.cpp:313-416 layout). */
+uint32_t oracle_bvh_candidates(const oracle_frame* f, uint32_t* bits, uint32_t bitWords, uint32_t* totalGroups);
+uint32_t oracle_instance_culling_bvh(const oracle_frame* f, chord_draw_cmd* out, uint32_t capacity, uint32_t* candidateGroups);
+
 /* K3: hzb_mainview_culling.hlsl:35-213.  hzbMin = mip chain (fp16 bits), mip m at hzbMipOffsets[m] (in texels),
  * row pitch = mip0Width >> m. */
 void oracle_hzb_culling(const oracle_frame* f, int firstStage,

@@ -204,3 +204,36 @@ def test_lighting_resolve(gpu_ctx):
             assert np.array_equal(got.any(axis=-1), g[i].any(axis=-1)), f'{name}: coverage differs'
         assert g[0].max() > 0.05 and np.abs(g[4]).max() > 0 or prev is None
         prev = ref['hzb']
+
+
+def test_bvh_traversal(gpu_ctx):
+    """N4: persistent-warp BVH traversal -> same post-cull list as the flat kernel and as the oracle; same candidate set."""
+    from cases import case_stream, city_frames
+    w, h = 640, 360
+    scene, info, frames = city_frames(frames=3, n_buildings=16, w=w, h=h)
+    gpu_ctx.upload_scene(scene)
+    cap, groups = info['lod0MeshletCount'], info['meshletGroupCount']
+    fr = runtime.Frame(gpu_ctx, w, h)
+    for f in frames:
+        for flags in (0b111, 0b000):
+            gpu_ctx.set_switch_flags(flags)
+            fr.begin(f['view'], f['iview'], f['objects'], cap, groups)
+            a, b = runtime.CmdList(gpu_ctx, cap), runtime.CmdList(gpu_ctx, cap)
+            fr.instance_culling(a)
+            fr.instance_culling_bvh(b)
+            ofr = oracle.Frame(scene, f['view'], f['iview'], f['objects'], w, h, flags)
+            ref, cand = ofr.instance_culling_bvh(cap)
+            _assert_lists_equal(a.readback(), ref, 'flat')
+            _assert_lists_equal(b.readback(), ref, 'bvh')
+            bits, ctrl = fr.bvh_candidates(groups)
+            obits, n, total = ofr.bvh_candidates(groups)
+            assert ctrl[4] == 0 and ctrl[2] == 0 and ctrl[3] == 1, ctrl        # no overflow, nothing pending, finished
+            assert np.array_equal(bits, obits)
+    gpu_ctx.set_switch_flags(0b111)
+    # a primitive whose groups are all root-level leaves (S5 shape): one node, every group a candidate
+    c = case_stream(3000, 640, 360, 1.0)
+    gpu_ctx.upload_scene(c['scene'])
+    fr.begin(c['view'], c['iview'], c['objects'], 3000, 750)
+    b = runtime.CmdList(gpu_ctx, 3000)
+    fr.instance_culling_bvh(b)
+    _assert_lists_equal(b.readback(), oracle.Frame(c['scene'], c['view'], c['iview'], c['objects'], 640, 360).instance_culling(3000), 'stream bvh')

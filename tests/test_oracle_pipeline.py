@@ -167,3 +167,27 @@ def test_empty_and_ragged_inputs():
     assert not vis.any() and st['meshletsRastered'] == 0
     one, _ = fr.render_mesh(c['cmds'][:1])
     assert one.any()
+
+
+def test_bvh_traversal_equals_flat_loop():
+    """N4: walking the cluster-group BVH (never traversed by the reference) must give the flat loop's list."""
+    scene, info, frames = city_frames(frames=3, n_buildings=16)
+    pruned_any = False
+    for f in frames:
+        for flags in (0b111, 0b000):
+            fr = oracle.Frame(scene, f['view'], f['iview'], f['objects'], 640, 360, flags)
+            flat = fr.instance_culling(info['lod0MeshletCount'])
+            via_bvh, cand = fr.instance_culling_bvh(info['lod0MeshletCount'])
+            assert np.array_equal(flat, via_bvh)
+            bits, n, total = fr.bvh_candidates(info['meshletGroupCount'])
+            assert n == cand and n <= total
+            pruned_any |= n < total
+    assert pruned_any, 'the case should prune at least one subtree'
+    # the builder's invariants (nanite_builder.cpp:415): root counts every node; children are all-or-none
+    nodes = scene.datas[0]['bvhNodes']
+    for p in scene.primitives:
+        root = nodes[p['bvhNodeOffset']]
+        sub = nodes[p['bvhNodeOffset']:p['bvhNodeOffset'] + root['bvhNodeCount']]
+        assert sub['leafMeshletGroupCount'].sum() == p['meshletGroupCount']
+        valid = (sub['children'] != 0xFFFFFFFF).sum(axis=1)
+        assert set(valid.tolist()) <= {0, 8}
