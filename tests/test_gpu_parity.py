@@ -211,9 +211,13 @@ def test_bvh_traversal(gpu_ctx):
     from cases import case_stream, city_frames
     w, h = 640, 360
     scene, info, frames = city_frames(frames=3, n_buildings=16, w=w, h=h)
+    far = cam.Camera((80.0, 900.0, 5200.0), (0.0, -0.17, -1.0), width=w, height=h)      # sub-pixel sub-trees get pruned
+    fview = cam.fill_view(far)
+    frames = frames + [dict(view=fview, iview=cam.fill_instance_view(fview), objects=synth.refill_objects(info['transforms'], far), camera=far)]
     gpu_ctx.upload_scene(scene)
     cap, groups = info['lod0MeshletCount'], info['meshletGroupCount']
     fr = runtime.Frame(gpu_ctx, w, h)
+    pruned = False
     for f in frames:
         for flags in (0b111, 0b000):
             gpu_ctx.set_switch_flags(flags)
@@ -229,6 +233,8 @@ def test_bvh_traversal(gpu_ctx):
             obits, n, total = ofr.bvh_candidates(groups)
             assert ctrl[4] == 0 and ctrl[2] == 0 and ctrl[3] == 1, ctrl        # no overflow, nothing pending, finished
             assert np.array_equal(bits, obits)
+            pruned |= n < total
+    assert pruned
     gpu_ctx.set_switch_flags(0b111)
     # a primitive whose groups are all root-level leaves (S5 shape): one node, every group a candidate
     c = case_stream(3000, 640, 360, 1.0)
@@ -237,3 +243,77 @@ def test_bvh_traversal(gpu_ctx):
     b = runtime.CmdList(gpu_ctx, 3000)
     fr.instance_culling_bvh(b)
     _assert_lists_equal(b.readback(), oracle.Frame(c['scene'], c['view'], c['iview'], c['objects'], 640, 360).instance_culling(3000), 'stream bvh')
+
+
+def test_full_size_s5_properties(gpu_ctx):
+    """BASELINE configs[4] at FULL size (781 250 meshlets x 128 tri, 3840x2160), size-independent properties:
+    run-to-run determinism (unordered work lists + atomics must not leak into the result), idempotence, union of screen
+    tiles == full frame, and bit-exact parity with the oracle on the head of the stream rendered alone."""
+    import torch
+    from chord_b200 import synth_device
+    M, W, H = 781250, 3840, 2160
+    scene, camera, objects, cmds = synth_device.patch_stream_scene_device(M, W, H, seed=5, device='cuda:0')
+    view = cam.fill_view(camera)
+    iview = cam.fill_instance_view(view)
+    gpu_ctx.upload_scene(scene)
+    fr = runtime.Frame(gpu_ctx, W, H)
+    lst = runtime.CmdList(gpu_ctx, M)
+    lst.upload(cmds)
+    groups = (M + 3) // 4
+    fr.begin(view, iview, objects, M, groups)
+    fr.render_mesh(lst)
+    a = fr.vis64()
+    st = fr.raster_stats()
+    assert st['trianglesSubmitted'] == M * 128 and st['largeQueueOverflow'] == 0
+    fr.render_mesh(lst)                                   # idempotent: a second pass over the same list changes nothing
+    assert np.array_equal(fr.vis64(), a)
+    fr.begin(view, iview, objects, M, groups)
+    fr.render_mesh(lst)
+    assert np.array_equal(fr.vis64(), a), 'two runs of the same frame differ'
+    acc = np.zeros_like(a)
+    for tile in ((0, 0, 1920, 1088), (1920, 0, 3840, 1088), (0, 1088, 1920, 2160), (1920, 1088, 3840, 2160)):
+        fr.begin(view, iview, objects, M, groups, tile=tile)
+        fr.render_mesh(lst)
+        acc |= fr.vis64()
+    assert np.array_equal(acc, a), 'union of 4 screen tiles differs from the full frame'
+    # the full instance-cull path reproduces the prebuilt list (all groups are LOD-0 roots facing the camera)
+    post = runtime.CmdList(gpu_ctx, M)
+    fr.begin(view, iview, objects, M, groups)
+    fr.instance_culling(post)
+    got = post.readback()
+    assert len(got) == M and np.array_equal(got['meshletId'], np.arange(M, dtype=np.uint32)) and np.array_equal(got['slot'], got['meshletId'])
+    # oracle parity on the first 60 000 meshlets (7.7 M triangles) at full resolution
+    n = 60000
+    hs = scene.host_prefix(n)
+    head = runtime.CmdList(gpu_ctx, n)
+    head.upload(cmds[:n])
+    fr.begin(view, iview, objects, M, groups)
+    fr.render_mesh(head)
+    ovis, ostats = oracle.Frame(hs, view, iview, objects, W, H).render_mesh(cmds[:n])
+    _assert_vis_equal(fr.vis64(), ovis, 'head of the S5 stream at 4K')
+    assert fr.raster_stats()['trianglesCulled'] - 0 >= ostats['trianglesCulled']
+    del scene
+    torch.cuda.empty_cache()
+
+
+def test_city_4k_frame(gpu_ctx):
+    """BASELINE configs[2] shape at FULL resolution: 371-building city (3.8 M LOD-0 triangles), 3840x2160, two frames
+    through the whole pass graph (two-phase HZB with history, HZB builds, tile marker) bit-exact against the oracle."""
+    w, h = 3840, 2160
+    scene, camera, objects, info = synth.city_scene(n_buildings=371, patches=4, lods=3, width=w, height=h, seed=3, n_protos=48)
+    gpu_ctx.upload_scene(scene)
+    r = renderer.DeferredRenderer(gpu_ctx, w, h)
+    prev, last_view, last_cam = None, None, None
+    for fi in range(2):
+        c = cam.Camera(camera.position + np.array([0.15 * fi, 0.01 * fi, -0.6 * fi]), camera.front, width=w, height=h)
+        objs = synth.refill_objects(info['transforms'], c, camera_last=last_cam)
+        view = cam.fill_view(c, last_view=last_view, frame_counter=fi)
+        iview = cam.fill_instance_view(view)
+        post = r.render(c, objs, info['lod0MeshletCount'], info['meshletGroupCount'], view=view, iview=iview)
+        ref = oracle.run_frame(scene, view, iview, objs, w, h, info['lod0MeshletCount'], prev)
+        _assert_lists_equal(post.readback(), ref['post_cull'], f'4K frame {fi} post-cull')
+        _assert_vis_equal(r.frame.vis64(), ref['vis64'], f'4K frame {fi} vis64')
+        _assert_hzb_equal(r.history_hzb, ref['hzb'], 'min')
+        _assert_hzb_equal(r.history_hzb, ref['hzb'], 'max')
+        assert r.frame.raster_stats()['largeQueueOverflow'] == 0
+        prev, last_view, last_cam = ref['hzb'], view, c

@@ -171,7 +171,12 @@ def test_empty_and_ragged_inputs():
 
 def test_bvh_traversal_equals_flat_loop():
     """N4: walking the cluster-group BVH (never traversed by the reference) must give the flat loop's list."""
+    from chord_b200 import camera as cam, synth
     scene, info, frames = city_frames(frames=3, n_buildings=16)
+    # a distant view: whole sub-trees of the node hierarchy fall below one pixel and are skipped
+    far = cam.Camera((80.0, 900.0, 5200.0), (0.0, -0.17, -1.0), width=640, height=360)
+    fview = cam.fill_view(far)
+    frames = frames + [dict(view=fview, iview=cam.fill_instance_view(fview), objects=synth.refill_objects(info['transforms'], far), camera=far)]
     pruned_any = False
     for f in frames:
         for flags in (0b111, 0b000):
