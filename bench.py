@@ -176,7 +176,7 @@ def frame_benchmark(ctx, stream, torch, steps=20, width=W4K, height=H4K, n_build
     ctx.upload_scene(scene)
     tr, ir = synth.synthetic_luts()
     ctx.upload_luts(tr, ir)
-    r = renderer.DeferredRenderer(ctx, width, height, do_resolve=True)
+    r = renderer.DeferredRenderer(ctx, width, height, do_resolve=True, packed_gbuffer=True)     # reference storage formats, 28 B/px
     labels = ['GLTF Instance Culling', 'GLTF Visibility Stage0', 'BuildHZB Post Prepass Stage0', 'GLTF Visibility Stage1',
               'BuildHZB', 'VisibilityTileMarker', 'lightingTile']
     acc = {k: 0.0 for k in labels}

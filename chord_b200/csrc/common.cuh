@@ -205,6 +205,7 @@ struct chord_frame {
     void* works; uint32_t worksCapacity; uint32_t* redoList; void* deferred; uint32_t deferredCapacity;
     // resolve
     uint32_t* tileMarker; uint32_t* tileList; uint32_t* tileCount; float* gbuffer[CHORD_GBUF_COUNT];
+    void* gbufferPackedBuf[CHORD_GBUF_COUNT]; int gbufferPacked;
     chord_PerframeCameraView hView;   // host copy
     bool begun;
 };

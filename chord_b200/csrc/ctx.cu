@@ -326,7 +326,7 @@ void chord_frame_destroy(chord_frame* f)
     cudaFree(f->works); cudaFree(f->redoList); cudaFree(f->deferred);
     cudaFree(f->largeTris); cudaFree(f->largeItems); cudaFree(f->largeCounters); cudaFree(f->stats);
     cudaFree(f->tileMarker); cudaFree(f->tileList); cudaFree(f->tileCount);
-    for (int i = 0; i < CHORD_GBUF_COUNT; i++) cudaFree(f->gbuffer[i]);
+    for (int i = 0; i < CHORD_GBUF_COUNT; i++) { cudaFree(f->gbuffer[i]); cudaFree(f->gbufferPackedBuf[i]); }
     free(f);
 }
 
@@ -520,6 +520,23 @@ int chord_readback_gbuffer_f32(chord_frame* f, int which, float* host)
     CHORD_REQUIRE(f && host && which >= 0 && which < CHORD_GBUF_COUNT, "args");
     CHORD_REQUIRE(f->gbuffer[which] != nullptr, "lighting has not run on this frame");
     CHORD_CUDA(cudaMemcpyAsync(host, f->gbuffer[which], sizeof(float) * 4 * (size_t)f->width * f->height, cudaMemcpyDeviceToHost, f->ctx->stream));
+    CHORD_CUDA(cudaStreamSynchronize(f->ctx->stream));
+    return CHORD_OK;
+}
+
+int chord_frame_set_gbuffer_packed(chord_frame* f, int packed)
+{
+    CHORD_REQUIRE(f, "null");
+    f->gbufferPacked = packed ? 1 : 0;
+    return CHORD_OK;
+}
+
+int chord_readback_gbuffer_packed(chord_frame* f, int which, void* host)
+{
+    static const size_t kPackedBytes[CHORD_GBUF_COUNT] = { 8, 4, 4, 4, 4, 4 };
+    CHORD_REQUIRE(f && host && which >= 0 && which < CHORD_GBUF_COUNT, "args");
+    CHORD_REQUIRE(f->gbufferPackedBuf[which] != nullptr, "lighting has not run in packed mode on this frame");
+    CHORD_CUDA(cudaMemcpyAsync(host, f->gbufferPackedBuf[which], kPackedBytes[which] * (size_t)f->width * f->height, cudaMemcpyDeviceToHost, f->ctx->stream));
     CHORD_CUDA(cudaStreamSynchronize(f->ctx->stream));
     return CHORD_OK;
 }

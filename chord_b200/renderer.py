@@ -53,12 +53,16 @@ def shouldRenderGLTF(ctx: GLTFRenderContext):
     return ctx.gltfObjectCount != 0
 
 
-def instanceCulling(ctx: GLTFRenderContext):
-    """instance_culling.cpp:83-161 -> CountAndCmdBuffer sized by lod0MeshletCount (:140-141)."""
+def instanceCulling(ctx: GLTFRenderContext, use_bvh=False):
+    """instance_culling.cpp:83-161 -> CountAndCmdBuffer sized by lod0MeshletCount (:140-141).  ``use_bvh`` walks the
+    cluster-group BVH first (same list; the reference builds the BVH but loops flat)."""
     if not shouldRenderGLTF(ctx):
         return None
     out = ctx.pool.cmdlist(ctx.lod0MeshletCount)
-    ctx.frame.instance_culling(out)
+    if use_bvh:
+        ctx.frame.instance_culling_bvh(out)
+    else:
+        ctx.frame.instance_culling(out)
     return out
 
 
@@ -103,9 +107,11 @@ def lighting(ctx: GLTFRenderContext, drawMeshletCmdBuffer):
 class DeferredRenderer:
     """renderer.cpp:142-499 restricted to the visibility-buffer path, headless; keeps last frame's HZB as history."""
 
-    def __init__(self, ctx: Context, width, height, do_resolve=False):
+    def __init__(self, ctx: Context, width, height, do_resolve=False, packed_gbuffer=False, use_bvh=False):
         self.ctx, self.width, self.height = ctx, width, height
         self.frame = Frame(ctx, width, height)
+        self.frame.set_gbuffer_packed(packed_gbuffer)
+        self.use_bvh = use_bvh
         self.pool = _Pool(ctx)
         self.history_hzb = None            # m_rendererHistory.hzbCtx (renderer.cpp:326, :489)
         self.last_view = None
@@ -128,7 +134,7 @@ class DeferredRenderer:
         f.begin(view, iview, objects, lod0_meshlet_count, meshlet_group_count, tile)      # uniforms + addClearGbufferPass
         rc = GLTFRenderContext(f, len(objects), lod0_meshlet_count, meshlet_group_count, self.pool)
         self.pool.release(self.post_cull)
-        post = instanceCulling(rc)
+        post = instanceCulling(rc, self.use_bvh)
         need1, rejected = gltfVisibilityRenderingStage0(rc, self.history_hzb, post)
         if need1:
             tmp = buildHZB(rc, True, False, False)

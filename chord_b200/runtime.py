@@ -25,7 +25,7 @@ SYMBOLS = [
     'chord_render_mesh', 'chord_visibility_stage0', 'chord_visibility_stage1', 'chord_build_hzb',
     'chord_visibility_mark', 'chord_atmosphere_luts_upload', 'chord_lighting',
     'chord_readback_vis64', 'chord_readback_visibility32', 'chord_readback_depth32', 'chord_readback_decoded',
-    'chord_readback_tile_marker', 'chord_readback_gbuffer_f32', 'chord_frame_vis64_ptr', 'chord_frame_dims',
+    'chord_readback_tile_marker', 'chord_readback_gbuffer_f32', 'chord_frame_set_gbuffer_packed', 'chord_readback_gbuffer_packed', 'chord_frame_vis64_ptr', 'chord_frame_dims',
     'chord_frame_raster_stats', 'chord_frame_reset_stats',
 ]
 
@@ -342,6 +342,18 @@ class Frame:
     def gbuffer(self, which):
         out = np.zeros((self.height, self.width, 4), dtype=np.float32)
         lib().chord_readback_gbuffer_f32(self.h, C.c_int(which), _p(out))
+        return out
+
+    def set_gbuffer_packed(self, packed):
+        lib().chord_frame_set_gbuffer_packed(self.h, C.c_int(1 if packed else 0))
+
+    def gbuffer_packed(self, which):
+        """Reference storage formats: which 0 -> (H, W, 4) float16; 1..3 -> (H, W) uint32 A2B10G10R10; 4 -> (H, W, 2) float16; 5 -> (H, W, 4) uint8."""
+        shapes = {0: ((self.height, self.width, 4), np.float16), 4: ((self.height, self.width, 2), np.float16),
+                  5: ((self.height, self.width, 4), np.uint8)}
+        shape, dt = shapes.get(which, ((self.height, self.width), np.uint32))
+        out = np.zeros(shape, dtype=dt)
+        lib().chord_readback_gbuffer_packed(self.h, C.c_int(which), _p(out))
         return out
 
     def raster_stats(self):

@@ -193,6 +193,11 @@ enum { CHORD_GBUF_COLOR = 0, CHORD_GBUF_BASECOLOR, CHORD_GBUF_VERTEX_NORMAL, CHO
        CHORD_GBUF_MOTION, CHORD_GBUF_AO_ROUGH_METAL, CHORD_GBUF_COUNT };
 /* pre-quantisation fp32 planes, 4 floats per pixel */
 int chord_readback_gbuffer_f32(chord_frame* frame, int which, float* host);
+/* packed = 1: chord_lighting writes the reference's storage formats (render_textures.h:21-59, lighting.hlsl:62-73):
+ * colour RGBA16F (8 B/px), baseColor / vertexNormal / pixelNormal A2B10G10R10_UNORM, motion RG16F, aoRoughMetal RGBA8
+ * (28 B/px); packed = 0 (default) writes the pre-quantisation fp32 planes used for the 1e-5 parity check. */
+int chord_frame_set_gbuffer_packed(chord_frame* frame, int packed);
+int chord_readback_gbuffer_packed(chord_frame* frame, int which, void* host);
 void* chord_frame_vis64_ptr(chord_frame* frame);
 int   chord_frame_dims(const chord_frame* frame, uint32_t* w, uint32_t* h);
 

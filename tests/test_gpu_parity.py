@@ -317,3 +317,36 @@ def test_city_4k_frame(gpu_ctx):
         _assert_hzb_equal(r.history_hzb, ref['hzb'], 'max')
         assert r.frame.raster_stats()['largeQueueOverflow'] == 0
         prev, last_view, last_cam = ref['hzb'], view, c
+
+
+def test_lighting_packed_formats(gpu_ctx):
+    """The reference's storage formats (RGBA16F, A2B10G10R10, RG16F, RGBA8): GPU packed output vs the oracle's fp32
+    planes quantised the same way, at most one code value / one fp16 ulp apart (the fp32 inputs agree to 1e-5)."""
+    from cases import city_frames
+    w, h = 640, 360
+    scene, info, frames = city_frames(frames=2, w=w, h=h)
+    gpu_ctx.upload_scene(scene)
+    tr, ir = synth.synthetic_luts()
+    gpu_ctx.upload_luts(tr, ir)
+    r = renderer.DeferredRenderer(gpu_ctx, w, h, do_resolve=True, packed_gbuffer=True, use_bvh=True)
+    prev = None
+    for f in frames:
+        r.render(f['camera'], f['objects'], info['lod0MeshletCount'], info['meshletGroupCount'], view=f['view'], iview=f['iview'])
+        ref = oracle.run_frame(scene, f['view'], f['iview'], f['objects'], w, h, info['lod0MeshletCount'], prev)
+        _assert_vis_equal(r.frame.vis64(), ref['vis64'], 'vis64 (BVH cull path)')
+        g = oracle.lighting(ref['frame'], ref['vis64'], ref['post_cull'], tr, ir)
+        prev = ref['hzb']
+
+    def half_ulps(a, b):
+        a16, b16 = a.astype(np.float16).view(np.int16).astype(np.int32), b.view(np.int16).astype(np.int32)
+        return np.abs(a16 - b16).max()
+    assert half_ulps(g[0], r.frame.gbuffer_packed(0)) <= 1
+    assert half_ulps(g[4][..., :2], r.frame.gbuffer_packed(4)) <= 1
+    for which in (1, 2, 3):
+        p = r.frame.gbuffer_packed(which)
+        want = np.rint(np.clip(g[which][..., :3], 0, 1) * 1023.0).astype(np.int32)
+        got = np.stack([p & 0x3FF, (p >> 10) & 0x3FF, (p >> 20) & 0x3FF], axis=-1).astype(np.int32)
+        assert np.abs(got - want).max() <= 1, which
+        assert np.array_equal((p >> 30) & 3, np.rint(np.clip(g[which][..., 3], 0, 1) * 3).astype(np.uint32))
+    p8 = r.frame.gbuffer_packed(5).astype(np.int32)
+    assert np.abs(p8 - np.rint(np.clip(g[5], 0, 1) * 255.0).astype(np.int32)).max() <= 1
