@@ -524,6 +524,17 @@ int chord_readback_gbuffer_f32(chord_frame* f, int which, float* host)
     return CHORD_OK;
 }
 
+int chord_frame_set_queue_limits(chord_frame* f, uint32_t deferredTriangles, uint32_t largeTriangles, uint32_t largeItems)
+{
+    // test / tuning knob: shrink the logical capacities of the raster queues (never beyond the allocation) to exercise the
+    // overflow fallbacks (deferred queue -> k_raster_general redo, large queues -> in-thread rasterisation)
+    CHORD_REQUIRE(f, "null");
+    if (deferredTriangles) f->deferredCapacity = deferredTriangles < kDeferredCapacity ? deferredTriangles : kDeferredCapacity;
+    if (largeTriangles) f->largeTriCapacity = largeTriangles < kLargeTriCapacity ? largeTriangles : kLargeTriCapacity;
+    if (largeItems) f->largeItemCapacity = largeItems < kLargeItemCapacity ? largeItems : kLargeItemCapacity;
+    return CHORD_OK;
+}
+
 int chord_frame_set_gbuffer_packed(chord_frame* f, int packed)
 {
     CHORD_REQUIRE(f, "null");

@@ -26,7 +26,7 @@ SYMBOLS = [
     'chord_visibility_mark', 'chord_atmosphere_luts_upload', 'chord_lighting',
     'chord_readback_vis64', 'chord_readback_visibility32', 'chord_readback_depth32', 'chord_readback_decoded',
     'chord_readback_tile_marker', 'chord_readback_gbuffer_f32', 'chord_frame_set_gbuffer_packed', 'chord_readback_gbuffer_packed', 'chord_frame_vis64_ptr', 'chord_frame_dims',
-    'chord_frame_raster_stats', 'chord_frame_reset_stats',
+    'chord_frame_raster_stats', 'chord_frame_reset_stats', 'chord_frame_set_queue_limits',
 ]
 
 _lib = None
@@ -343,6 +343,9 @@ class Frame:
         out = np.zeros((self.height, self.width, 4), dtype=np.float32)
         lib().chord_readback_gbuffer_f32(self.h, C.c_int(which), _p(out))
         return out
+
+    def set_queue_limits(self, deferred=0, large_tris=0, large_items=0):
+        lib().chord_frame_set_queue_limits(self.h, C.c_uint32(deferred), C.c_uint32(large_tris), C.c_uint32(large_items))
 
     def set_gbuffer_packed(self, packed):
         lib().chord_frame_set_gbuffer_packed(self.h, C.c_int(1 if packed else 0))

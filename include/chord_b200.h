@@ -211,6 +211,9 @@ typedef struct {
     uint64_t meshletsRastered;
 } chord_raster_stats;
 int chord_frame_raster_stats(chord_frame* frame, chord_raster_stats* out);
+/* Shrink the logical capacities of the raster work queues (0 = keep). Overflow never changes the image: deferred
+ * triangles that do not fit make their meshlet go through the all-in-one kernel, large triangles are rasterised in place. */
+int chord_frame_set_queue_limits(chord_frame* frame, uint32_t deferredTriangles, uint32_t largeTriangles, uint32_t largeItems);
 int chord_frame_reset_stats(chord_frame* frame);
 
 #ifdef __cplusplus

@@ -350,3 +350,45 @@ def test_lighting_packed_formats(gpu_ctx):
         assert np.array_equal((p >> 30) & 3, np.rint(np.clip(g[which][..., 3], 0, 1) * 3).astype(np.uint32))
     p8 = r.frame.gbuffer_packed(5).astype(np.int32)
     assert np.abs(p8 - np.rint(np.clip(g[5], 0, 1) * 255.0).astype(np.int32)).max() <= 1
+
+
+def test_queue_overflow_fallbacks(gpu_ctx):
+    """Overflowing the deferred / large-triangle queues must not change a single texel (redo through the all-in-one kernel,
+    in-thread rasterisation); error paths return CHORD_ERR_* instead of crashing."""
+    from cases import case_stream, city_frames
+    for (n, w, h, scale) in ((1500, 512, 512, 40.0), (600, 256, 256, 2000.0)):
+        c = case_stream(n, w, h, scale)
+        gpu_ctx.upload_scene(c['scene'])
+        ovis, _ = oracle.Frame(c['scene'], c['view'], c['iview'], c['objects'], w, h).render_mesh(c['cmds'])
+        lst = runtime.CmdList(gpu_ctx, n)
+        lst.upload(c['cmds'])
+        for limits in (dict(deferred=64), dict(large_tris=8, large_items=16), dict(deferred=1, large_tris=1, large_items=1)):
+            fr = runtime.Frame(gpu_ctx, w, h)
+            fr.set_queue_limits(**limits)
+            fr.begin(c['view'], c['iview'], c['objects'], n, (n + 3) // 4)
+            fr.render_mesh(lst)
+            _assert_vis_equal(fr.vis64(), ovis, f'overflow {limits} scale {scale}')
+            assert fr.raster_stats()['largeQueueOverflow'] > 0, limits
+    # city with near-plane clipping + big triangles through the overflow paths
+    scene, info, frames = city_frames(frames=1, low=True)
+    f = frames[0]
+    gpu_ctx.upload_scene(scene)
+    fr = runtime.Frame(gpu_ctx, 640, 360)
+    fr.set_queue_limits(deferred=16, large_tris=4, large_items=8)
+    fr.begin(f['view'], f['iview'], f['objects'], info['lod0MeshletCount'], info['meshletGroupCount'])
+    post = runtime.CmdList(gpu_ctx, info['lod0MeshletCount'])
+    fr.instance_culling(post)
+    fr.render_mesh(post)
+    ref = oracle.run_frame(scene, f['view'], f['iview'], f['objects'], 640, 360, info['lod0MeshletCount'], None)
+    _assert_vis_equal(fr.vis64(), ref['vis64'], 'city through overflow paths')
+    # error behaviour (the reference check()-crashes): statuses + messages, never a crash
+    with pytest.raises(runtime.ChordError, match='capacity'):
+        small = runtime.CmdList(gpu_ctx, 4)
+        small.upload(np.zeros(8, dtype=abi.DrawCmd))
+    with pytest.raises(runtime.ChordError, match='64, 4096'):
+        runtime.Frame(gpu_ctx, 32, 32)
+    with pytest.raises(runtime.ChordError):
+        fr.begin(f['view'], f['iview'], f['objects'][:0], 1, 1)          # shouldRenderGLTF: no objects
+    with pytest.raises(runtime.ChordError, match='render dimension'):
+        bad = runtime.Hzb(gpu_ctx, 256, 256)
+        fr.build_hzb(bad)
