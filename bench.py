@@ -39,7 +39,7 @@ BYTES_PER_MESHLET = 12 + 64 + 4 * V_PER_MESHLET + 4 * TRIS_PER_MESHLET + 12 * V_
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--steps', type=int, default=50)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='chord_b200', choices=['chord_b200', 'reference'])
     ap.add_argument('--meshlets', type=int, default=N_MESHLETS, help='override the stream length (debug only)')
@@ -293,24 +293,28 @@ def main():
     # pinned host staging for the e2e leg
     pin_cmds = torch.empty(max(n_local, 1) * 12, dtype=torch.uint8).pin_memory()
     pin_cmds.numpy()[:n_local * 12] = np.frombuffer(host_cmds.tobytes(), dtype=np.uint8)
-    pin_vis = torch.empty(W4K * H4K, dtype=torch.int32).pin_memory()
+    pin_vis = [torch.empty(W4K * H4K, dtype=torch.int32).pin_memory() for _ in range(2)]
     pin_view = torch.from_numpy(np.frombuffer(view.tobytes(), dtype=np.uint8).copy()).pin_memory()
     import ctypes as C
     L = runtime.lib()
 
-    def step_e2e():
-        # host buffers in, host image out, everything through the C ABI
-        frame.begin(view, iview_used, objects, M, groups, tile if n_gpus > 1 else None)
-        L.chord_cmdlist_upload(lst.h, C.c_void_p(pin_cmds.data_ptr()), C.c_uint32(n_local))
-        frame.render_mesh(lst)
-        L.chord_readback_visibility32(frame.h, C.c_void_p(pin_vis.data_ptr()))
+    e2e_i = [0]
 
-    # ---- resident (kernel) timing
+    def step_e2e():
+        # host buffers in, host image out, everything through the C ABI; the D2H of step i overlaps the raster of step
+        # i+1 (two pinned result buffers), all copies complete inside the timed region (chord_frame_wait_readbacks)
+        frame.begin(view, iview_used, objects, M, groups, tile if n_gpus > 1 else None)
+        L.chord_cmdlist_upload_async(lst.h, C.c_void_p(pin_cmds.data_ptr()), C.c_uint32(n_local))
+        frame.render_mesh(lst)
+        L.chord_readback_visibility32_async(frame.h, C.c_void_p(pin_vis[e2e_i[0] & 1].data_ptr()))
+        e2e_i[0] += 1
+
+    # ---- resident (kernel) timing; clocks are sampled from the warm-up to the end of the e2e leg
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(max(args.warmup, 3)):
         step_resident()
     barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     launches0 = ctx.kernel_launches
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
@@ -329,12 +333,18 @@ def main():
     # ---- e2e timing
     for _ in range(2):
         step_e2e()
+    L.chord_frame_wait_readbacks(frame.h)
     barrier()
+    # sanity: the pipelined read-back delivers the same image as the synchronous one
+    chk = np.empty(W4K * H4K, dtype=np.uint32)
+    L.chord_readback_visibility32(frame.h, C.c_void_p(chk.ctypes.data))
+    assert np.array_equal(chk, pin_vis[(e2e_i[0] - 1) & 1].numpy().view(np.uint32)), 'async read-back differs'
     t0 = time.perf_counter()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for _ in range(args.steps):
         step_e2e()
+    L.chord_frame_wait_readbacks(frame.h)
     e1.record(stream)
     barrier()
     e2e_ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)      # sync read-backs: wall clock bounds it

@@ -172,6 +172,8 @@ struct chord_cmdlist {
     chord_ctx* ctx;
     uint32_t capacity;
     uint32_t* count;            // device
+    uint32_t* pinnedCount;      // host-pinned ring for async uploads
+    uint32_t pinnedIdx;
     chord_draw_cmd* cmds;       // device
 };
 
@@ -206,6 +208,9 @@ struct chord_frame {
     // resolve
     uint32_t* tileMarker; uint32_t* tileList; uint32_t* tileCount; float* gbuffer[CHORD_GBUF_COUNT];
     void* gbufferPackedBuf[CHORD_GBUF_COUNT]; int gbufferPacked;
+    void* resolveRecs; uint32_t resolveCapacity;
+    // pipelined read-back of the R32_UINT image: two staging slots, a copy stream, events
+    uint32_t* splitVis[2]; cudaStream_t copyStream; cudaEvent_t splitDone[2], copyDone[2]; int splitIdx;
     chord_PerframeCameraView hView;   // host copy
     bool begun;
 };

@@ -179,7 +179,7 @@ void chord_cmdlist_destroy(chord_cmdlist* l)
 {
     if (!l) return;
     cudaStreamSynchronize(l->ctx->stream);
-    cudaFree(l->count); cudaFree(l->cmds); free(l);
+    cudaFree(l->count); cudaFree(l->cmds); if (l->pinnedCount) cudaFreeHost(l->pinnedCount); free(l);
 }
 int chord_cmdlist_upload(chord_cmdlist* l, const chord_draw_cmd* host, uint32_t count)
 {
@@ -190,6 +190,20 @@ int chord_cmdlist_upload(chord_cmdlist* l, const chord_draw_cmd* host, uint32_t 
     CHORD_CUDA(cudaStreamSynchronize(l->ctx->stream));
     return CHORD_OK;
 }
+int chord_cmdlist_upload_async(chord_cmdlist* l, const chord_draw_cmd* host, uint32_t count)
+{
+    // stream-ordered, no host synchronisation: `host` (pinned for a true async copy) must stay valid until the stream passes it
+    CHORD_REQUIRE(l && (host || count == 0), "null");
+    if (count > l->capacity) { set_error("cmdlist upload: %u > capacity %u", count, l->capacity); return CHORD_ERR_CAPACITY; }
+    // the count travels as a 4-byte kernel-free copy from a small pinned scratch owned by the list
+    if (!l->pinnedCount) CHORD_CUDA(cudaMallocHost(&l->pinnedCount, 64 * sizeof(uint32_t)));
+    uint32_t* slot = &l->pinnedCount[l->pinnedIdx++ & 63u];                 // ring: up to 64 uploads in flight
+    *slot = count;
+    CHORD_CUDA(cudaMemcpyAsync(l->count, slot, 4, cudaMemcpyHostToDevice, l->ctx->stream));
+    if (count) CHORD_CUDA(cudaMemcpyAsync(l->cmds, host, sizeof(chord_draw_cmd) * (size_t)count, cudaMemcpyHostToDevice, l->ctx->stream));
+    return CHORD_OK;
+}
+
 int chord_cmdlist_readback(chord_cmdlist* l, chord_draw_cmd* host, uint32_t hostCapacity, uint32_t* outCount)
 {
     CHORD_REQUIRE(l && outCount, "null");
@@ -324,8 +338,9 @@ void chord_frame_destroy(chord_frame* f)
     cudaFree(f->objGroupCount); cudaFree(f->objGroupBase); cudaFree(f->totalGroups);
     cudaFree(f->bvhEntries); cudaFree(f->bvhBits); cudaFree(f->bvhCtrl);
     cudaFree(f->works); cudaFree(f->redoList); cudaFree(f->deferred);
+    if (f->copyStream) { cudaStreamSynchronize(f->copyStream); for (int k = 0; k < 2; k++) { cudaFree(f->splitVis[k]); cudaEventDestroy(f->splitDone[k]); cudaEventDestroy(f->copyDone[k]); } cudaStreamDestroy(f->copyStream); }
     cudaFree(f->largeTris); cudaFree(f->largeItems); cudaFree(f->largeCounters); cudaFree(f->stats);
-    cudaFree(f->tileMarker); cudaFree(f->tileList); cudaFree(f->tileCount);
+    cudaFree(f->tileMarker); cudaFree(f->tileList); cudaFree(f->tileCount); cudaFree(f->resolveRecs);
     for (int i = 0; i < CHORD_GBUF_COUNT; i++) { cudaFree(f->gbuffer[i]); cudaFree(f->gbufferPackedBuf[i]); }
     free(f);
 }
@@ -490,6 +505,45 @@ static int readback_split(chord_frame* f, uint32_t* hostVis, float* hostDepth)
     CHORD_CUDA(cudaStreamSynchronize(f->ctx->stream));
     return rc;
 }
+static int ensure_async_readback(chord_frame* f)
+{
+    if (f->copyStream) return CHORD_OK;
+    const size_t n = (size_t)f->width * f->height;
+    CHORD_CUDA(cudaStreamCreateWithFlags(&f->copyStream, cudaStreamNonBlocking));
+    for (int k = 0; k < 2; k++) {
+        CHORD_CUDA(cudaMalloc(&f->splitVis[k], n * 4));
+        CHORD_CUDA(cudaEventCreateWithFlags(&f->splitDone[k], cudaEventDisableTiming));
+        CHORD_CUDA(cudaEventCreateWithFlags(&f->copyDone[k], cudaEventDisableTiming));
+    }
+    return CHORD_OK;
+}
+
+// Pipelined read-back: the R32_UINT image of the CURRENT surface is extracted on the context stream into one of two
+// staging slots and copied to `hostPinned` on a separate copy stream, so that the next frame's kernels overlap the
+// PCIe transfer.  chord_frame_wait_readbacks() (or destroying the frame) completes all outstanding copies.
+int chord_readback_visibility32_async(chord_frame* f, uint32_t* hostPinned)
+{
+    CHORD_REQUIRE(f && hostPinned, "null");
+    int rc = ensure_async_readback(f);
+    if (rc) return rc;
+    const int k = f->splitIdx; f->splitIdx ^= 1;
+    CHORD_CUDA(cudaStreamWaitEvent(f->ctx->stream, f->copyDone[k], 0));          // slot k no longer being copied out
+    rc = launch_split_vis(f, f->splitVis[k], nullptr);
+    if (rc) return rc;
+    CHORD_CUDA(cudaEventRecord(f->splitDone[k], f->ctx->stream));
+    CHORD_CUDA(cudaStreamWaitEvent(f->copyStream, f->splitDone[k], 0));
+    CHORD_CUDA(cudaMemcpyAsync(hostPinned, f->splitVis[k], (size_t)f->width * f->height * 4, cudaMemcpyDeviceToHost, f->copyStream));
+    CHORD_CUDA(cudaEventRecord(f->copyDone[k], f->copyStream));
+    return CHORD_OK;
+}
+
+int chord_frame_wait_readbacks(chord_frame* f)
+{
+    CHORD_REQUIRE(f, "null");
+    if (f->copyStream) CHORD_CUDA(cudaStreamSynchronize(f->copyStream));
+    return CHORD_OK;
+}
+
 int chord_readback_visibility32(chord_frame* f, uint32_t* host) { CHORD_REQUIRE(f && host, "null"); return readback_split(f, host, nullptr); }
 int chord_readback_depth32(chord_frame* f, float* host) { CHORD_REQUIRE(f && host, "null"); return readback_split(f, nullptr, host); }
 

@@ -88,6 +88,8 @@ int chord_scene_upload(chord_ctx* ctx, const chord_scene_desc* desc);
 int  chord_cmdlist_create(chord_ctx* ctx, uint32_t capacity, chord_cmdlist** out);
 void chord_cmdlist_destroy(chord_cmdlist* list);
 int  chord_cmdlist_upload(chord_cmdlist* list, const chord_draw_cmd* hostCmds, uint32_t count);
+/* stream-ordered upload without host synchronisation; hostCmds must stay valid (pinned for a truly async copy). */
+int  chord_cmdlist_upload_async(chord_cmdlist* list, const chord_draw_cmd* hostCmds, uint32_t count);
 int  chord_cmdlist_readback(chord_cmdlist* list, chord_draw_cmd* hostCmds, uint32_t hostCapacity, uint32_t* outCount);
 uint32_t chord_cmdlist_capacity(const chord_cmdlist* list);
 /* device pointers (count is a single u32, cmds is uint3[capacity]) */
@@ -184,7 +186,11 @@ int chord_lighting(chord_frame* frame, chord_cmdlist* postInstanceCull);
 /* ---- read-backs (synchronise the stream) */
 int chord_readback_vis64(chord_frame* frame, uint64_t* host);          /* W*H packed texels */
 int chord_readback_visibility32(chord_frame* frame, uint32_t* host);   /* the reference's R32_UINT image */
-int chord_readback_depth32(chord_frame* frame, float* host);           /* the reference's D32 image */
+int chord_readback_depth32(chord_frame* frame, float* host);
+/* pipelined variant: extraction on the context stream, PCIe copy on a second stream (two staging slots), so the next
+ * frame overlaps the transfer; hostPinned must be page-locked. chord_frame_wait_readbacks completes all pending copies. */
+int chord_readback_visibility32_async(chord_frame* frame, uint32_t* hostPinned);
+int chord_frame_wait_readbacks(chord_frame* frame);           /* the reference's D32 image */
 /* decoded (objectId, meshletId, triangleId) per pixel through a post-instance-cull list
  * (visibility_tile.hlsl:47-60); 0xFFFFFFFF triple where no geometry. */
 int chord_readback_decoded(chord_frame* frame, chord_cmdlist* postInstanceCull, uint32_t* hostTriples);
