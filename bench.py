@@ -338,7 +338,8 @@ def main():
     # sanity: the pipelined read-back delivers the same image as the synchronous one
     chk = np.empty(W4K * H4K, dtype=np.uint32)
     L.chord_readback_visibility32(frame.h, C.c_void_p(chk.ctypes.data))
-    assert np.array_equal(chk, pin_vis[(e2e_i[0] - 1) & 1].numpy().view(np.uint32)), 'async read-back differs'
+    a_img = pin_vis[(e2e_i[0] - 1) & 1].numpy().view(np.uint32).reshape(H4K, W4K)[tile[1]:tile[3], tile[0]:tile[2]]
+    assert np.array_equal(chk.reshape(H4K, W4K)[tile[1]:tile[3], tile[0]:tile[2]], a_img), 'async read-back differs'
     t0 = time.perf_counter()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
@@ -383,7 +384,8 @@ def main():
                        'triangles_per_step': tris, 'l2': 'inputs (1.5 GB) exceed the 126 MB L2; no explicit flush',
                        'parallelism': 'single GPU' if n_gpus == 1 else f'{n_gpus} screen tiles, one per GPU, per-tile sub-frustum cull'},
             'e2e': {'value': e2e_value, 'unit': 'Mtri/s', 'h2d_bytes_per_step': int(n_local * 12 + 1728 + 288 + 224),
-                    'd2h_bytes_per_step': int(W4K * H4K * 4), 'ms_per_step': e2e_ms / args.steps},
+                    'd2h_bytes_per_step': int((tile[2] - tile[0]) * (tile[3] - tile[1]) * 4), 'ms_per_step': e2e_ms / args.steps,
+                    'note': 'per rank: its draw list H2D + its screen tile of the R32_UINT image D2H, D2H of step i overlapped with step i+1'},
             'gpu_launches': int(launches),
             'clocks': clocks,
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,

@@ -532,7 +532,11 @@ int chord_readback_visibility32_async(chord_frame* f, uint32_t* hostPinned)
     if (rc) return rc;
     CHORD_CUDA(cudaEventRecord(f->splitDone[k], f->ctx->stream));
     CHORD_CUDA(cudaStreamWaitEvent(f->copyStream, f->splitDone[k], 0));
-    CHORD_CUDA(cudaMemcpyAsync(hostPinned, f->splitVis[k], (size_t)f->width * f->height * 4, cudaMemcpyDeviceToHost, f->copyStream));
+    // only the frame's screen tile travels (the other tiles belong to other GPUs): a pitched copy into the same
+    // position of the host image
+    const size_t pitch = (size_t)f->width * 4, off = (size_t)f->tile.y0 * f->width + f->tile.x0;
+    CHORD_CUDA(cudaMemcpy2DAsync(hostPinned + off, pitch, f->splitVis[k] + off, pitch, (size_t)(f->tile.x1 - f->tile.x0) * 4,
+                                 f->tile.y1 - f->tile.y0, cudaMemcpyDeviceToHost, f->copyStream));
     CHORD_CUDA(cudaEventRecord(f->copyDone[k], f->copyStream));
     return CHORD_OK;
 }
