@@ -231,6 +231,41 @@ def frame_benchmark(ctx, stream, torch, steps=20, width=W4K, height=H4K, n_build
             'post_cull_meshlets_last_frame': int(post.count()), 'raster_stats_total': stats}
 
 
+def frame_benchmark_tiled(ctx, stream, torch, dist, rank, world, steps=20, width=W4K, height=H4K, n_buildings=371):
+    """BASELINE configs[3]: the same city frame split into `world` screen tiles, one per GPU: tile sub-frustum cull, scissored
+    raster, tile-local phase-1 HZB, ONE NCCL all-gather of the packed min-HZB tile parts per frame (history for the next
+    frame's phase 0), local rebuild of mips 6.., tile-local resolve.  Frame time = max over ranks (device events)."""
+    from chord_b200 import camera as cam, multigpu, renderer, synth
+    scene, camera, objects, info = synth.city_scene(n_buildings=n_buildings, patches=4, lods=3, width=width, height=height, seed=3, n_protos=48)
+    ctx.upload_scene(scene)
+    tr, ir = synth.synthetic_luts()
+    ctx.upload_luts(tr, ir)
+    tr_ = multigpu.TileRenderer(ctx, width, height, rank, world, dist)
+    tr_.r.do_resolve = True
+    tr_.r.frame.set_gbuffer_packed(True)
+    lod0, groups = info['lod0MeshletCount'], info['meshletGroupCount']
+    last_cam, times = None, []
+    for fi in range(steps + 3):
+        c = cam.Camera(camera.position + np.array([0.15 * fi, 0.01 * fi, -0.6 * fi]), camera.front, width=width, height=height)
+        objs = synth.refill_objects(info['transforms'], c, camera_last=last_cam)
+        view = cam.fill_view(c, last_view=tr_.r.last_view, frame_counter=fi)
+        dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        tr_.render(c, objs, lod0, groups, view=view)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        if fi >= 3:
+            times.append(e0.elapsed_time(e1))
+        last_cam = c
+    t = torch.tensor([float(np.mean(times))], dtype=torch.float64, device=f'cuda:{ctx.device}')
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    return {'workload': f'S3 stand-in city at {width}x{height} split into {world} screen tiles (one per GPU), NCCL all-gather of the '
+                        f'min-HZB tile parts per frame', 'frames_per_s': 1000.0 / ms, 'ms_per_frame': ms, 'frames_timed': len(times),
+            'tile_rank0': list(tr_.tile), 'hzb_allgather_bytes': int(sum(tr_.r.history_hzb.tile_bytes(t_) for t_ in multigpu.all_tiles(world, width, height)))}
+
+
 def main():
     args = parse()
     if args.impl == 'reference':
@@ -354,6 +389,12 @@ def main():
     e2e_ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)      # sync read-backs: wall clock bounds it
     clocks = sampler.stop()
 
+    frame_tiled = None
+    if dist is not None and not args.no_frame:
+        try:
+            frame_tiled = frame_benchmark_tiled(ctx, stream, torch, dist, rank, world)
+        except Exception as e:
+            frame_tiled = {'error': repr(e)}
     times = torch.tensor([total_ms, kern_ms, e2e_ms], dtype=torch.float64, device=f'cuda:{local_rank}')
     if dist is not None:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
@@ -400,6 +441,8 @@ def main():
         }
         if not args.no_cpu_baseline and n_gpus == 1:
             line['cpu_baseline'] = cpu_baseline(scene, view, iview, objects)
+        if frame_tiled is not None:
+            line['frame'] = frame_tiled
         if n_gpus == 1 and not args.no_frame:
             try:
                 line['frame'] = frame_benchmark(ctx, stream, torch)
