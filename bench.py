@@ -222,7 +222,7 @@ def frame_benchmark(ctx, stream, torch, steps=20, width=W4K, height=H4K, n_build
                 acc[lab] += ev[k + 1].elapsed_time(ev[k + 2])
             t_frames.append(ev[0].elapsed_time(ev[8]))
     n = len(t_frames)
-    ms = float(np.mean(t_frames))
+    ms = float(np.median(t_frames))
     stats = f.raster_stats()
     return {'workload': f'S3 stand-in: procedural city, {scene.total_triangles} triangles in {scene.total_meshlets} meshlets (all LODs), '
                         f'{len(frames[0][1])} objects, {width}x{height}, two-phase HZB + resolve, camera path',
@@ -258,12 +258,13 @@ def frame_benchmark_tiled(ctx, stream, torch, dist, rank, world, steps=20, width
         if fi >= 3:
             times.append(e0.elapsed_time(e1))
         last_cam = c
-    t = torch.tensor([float(np.mean(times))], dtype=torch.float64, device=f'cuda:{ctx.device}')
+    # median over frames (NCCL sets up its channels lazily, the first collectives of a new size are outliers), max over ranks
+    t = torch.tensor([float(np.median(times)), float(np.mean(times)), float(np.max(times))], dtype=torch.float64, device=f'cuda:{ctx.device}')
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
+    ms, ms_mean, ms_max = (float(x) for x in t.tolist())
     return {'workload': f'S3 stand-in city at {width}x{height} split into {world} screen tiles (one per GPU), NCCL all-gather of the '
-                        f'min-HZB tile parts per frame', 'frames_per_s': 1000.0 / ms, 'ms_per_frame': ms, 'frames_timed': len(times),
-            'tile_rank0': list(tr_.tile), 'hzb_allgather_bytes': int(sum(tr_.r.history_hzb.tile_bytes(t_) for t_ in multigpu.all_tiles(world, width, height)))}
+                        f'min-HZB tile parts per frame', 'frames_per_s': 1000.0 / ms, 'ms_per_frame': ms, 'ms_per_frame_mean': ms_mean, 'ms_per_frame_max': ms_max,
+            'frames_timed': len(times), 'tile_rank0': list(tr_.tile), 'hzb_allgather_bytes': int(sum(tr_.r.history_hzb.tile_bytes(t_) for t_ in multigpu.all_tiles(world, width, height)))}
 
 
 def main():
