@@ -202,13 +202,15 @@ __device__ __forceinline__ uint64_t tile_region_texels(const TileRegion& r, uint
 { return (uint64_t)(((r.bx1 - r.bx0) * 32u) >> mip) * (((r.by1 - r.by0) * 32u) >> mip); }
 
 // one thread per packed texel of mips 0..5 of one tile; pack = chain -> contiguous, unpack = contiguous -> chain
+struct TileCopyParams { TileRegion regions[16]; uint64_t mipOffset6[6]; uint32_t nRegions; };
+
 template <bool kPack>
-__global__ void k_hzb_tile_copy(__half* __restrict__ chain, const uint64_t* __restrict__ mipOffset6, uint32_t mip0W,
-                                const TileRegion* __restrict__ regions, uint32_t nRegions, __half* __restrict__ packed, uint64_t slotTexels)
+__global__ void k_hzb_tile_copy(__half* __restrict__ chain, TileCopyParams prm, uint32_t mip0W, __half* __restrict__ packed, uint64_t slotTexels)
 {
     const uint32_t ri = blockIdx.y;
-    if (ri >= nRegions) return;
-    const TileRegion r = regions[ri];
+    if (ri >= prm.nRegions) return;
+    const TileRegion r = prm.regions[ri];
+    const uint64_t* mipOffset6 = prm.mipOffset6;
     uint64_t total = 0;
 #pragma unroll
     for (uint32_t m = 0; m < 6; m++) total += tile_region_texels(r, m);
@@ -240,27 +242,22 @@ extern "C" int chord_hzb_tile_bytes(const chord_hzb* h, const chord_rect* tile, 
 static int hzb_tile_copy(chord_hzb* h, int which, const chord_rect* tiles, uint32_t n, void* packed, uint64_t slotBytes, bool pack)
 {
     using namespace chordb;
-    CHORD_REQUIRE(h && tiles && packed && n > 0 && n <= 64, "args");
+    CHORD_REQUIRE(h && tiles && packed && n > 0 && n <= 16, "args (at most 16 tiles)");
     CHORD_REQUIRE(h->mipCount >= 6, "mips");
     chord_ctx* ctx = h->ctx;
-    TileRegion regs[64];
+    TileCopyParams prm;                                  // by value: no allocation, no copy, one launch
+    prm.nRegions = n;
     for (uint32_t i = 0; i < n; i++) {
         CHORD_REQUIRE(tile_aligned(tiles[i], h->depthW, h->depthH), "tile rect must be cut on multiples of 64 px");
-        tile_blocks(h, tiles[i], h->depthW, h->depthH, regs[i].bx0, regs[i].by0, regs[i].bx1, regs[i].by1);
+        tile_blocks(h, tiles[i], h->depthW, h->depthH, prm.regions[i].bx0, prm.regions[i].by0, prm.regions[i].bx1, prm.regions[i].by1);
     }
-    TileRegion* dRegs = nullptr; uint64_t* dOff = nullptr;
-    CHORD_CUDA(cudaMallocAsync(&dRegs, sizeof(TileRegion) * n, ctx->stream));
-    CHORD_CUDA(cudaMallocAsync(&dOff, sizeof(uint64_t) * 6, ctx->stream));
-    CHORD_CUDA(cudaMemcpyAsync(dRegs, regs, sizeof(TileRegion) * n, cudaMemcpyHostToDevice, ctx->stream));
-    CHORD_CUDA(cudaMemcpyAsync(dOff, h->mipOffset, sizeof(uint64_t) * 6, cudaMemcpyHostToDevice, ctx->stream));
+    for (int m = 0; m < 6; m++) prm.mipOffset6[m] = h->mipOffset[m];
     __half* chain = which ? h->maxChain : h->minChain;
-    const dim3 grid(256, n);
-    if (pack) k_hzb_tile_copy<true><<<grid, 256, 0, ctx->stream>>>(chain, dOff, h->mip0W, dRegs, n, (__half*)packed, slotBytes / 2);
-    else      k_hzb_tile_copy<false><<<grid, 256, 0, ctx->stream>>>(chain, dOff, h->mip0W, dRegs, n, (__half*)packed, slotBytes / 2);
+    const dim3 grid(128, n);
+    if (pack) k_hzb_tile_copy<true><<<grid, 256, 0, ctx->stream>>>(chain, prm, h->mip0W, (__half*)packed, slotBytes / 2);
+    else      k_hzb_tile_copy<false><<<grid, 256, 0, ctx->stream>>>(chain, prm, h->mip0W, (__half*)packed, slotBytes / 2);
     ctx->launches++;
     CHORD_CUDA(cudaGetLastError());
-    CHORD_CUDA(cudaFreeAsync(dRegs, ctx->stream));
-    CHORD_CUDA(cudaFreeAsync(dOff, ctx->stream));
     return CHORD_OK;
 }
 

@@ -149,14 +149,14 @@ def allgather_hzb(frame, hzb, rank, world, dist, which=('min',), staging=None):
     ``dist`` is torch.distributed (NCCL); the collective is enqueued on the library's stream via an ExternalStream so
     that pack -> all-gather -> unpack -> finish_top is stream-ordered without host synchronisation."""
     import torch
-    tiles = all_tiles(world, frame.width, frame.height)
-    slot = max(hzb.tile_bytes(t) for t in tiles)
-    slot = (slot + 255) // 256 * 256
-    dev = torch.device('cuda', frame.ctx.device)
-    stream = torch.cuda.ExternalStream(frame.ctx.stream, device=dev)
-    if staging is None or staging[0].numel() != slot:
-        staging = (torch.zeros(slot, dtype=torch.uint8, device=dev), torch.zeros(slot * world, dtype=torch.uint8, device=dev))
-    send, recv = staging
+    if staging is None:
+        tiles = all_tiles(world, frame.width, frame.height)
+        slot = max(hzb.tile_bytes(t) for t in tiles)
+        slot = (slot + 255) // 256 * 256
+        dev = torch.device('cuda', frame.ctx.device)
+        staging = dict(tiles=tiles, slot=slot, stream=torch.cuda.ExternalStream(frame.ctx.stream, device=dev),
+                       send=torch.zeros(slot, dtype=torch.uint8, device=dev), recv=torch.zeros(slot * world, dtype=torch.uint8, device=dev))
+    tiles, slot, stream, send, recv = staging['tiles'], staging['slot'], staging['stream'], staging['send'], staging['recv']
     with torch.cuda.stream(stream):
         for w in which:
             hzb.pack_tile(w, tiles[rank], send.data_ptr())
