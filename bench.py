@@ -170,12 +170,15 @@ def cpu_baseline(dev_scene, view, iview, objects, budget_s=12.0):
                       f'OpenMP over meshlets; CPU restatement of chord (reference not runnable offline)'}
 
 
-def frame_benchmark(ctx, stream, torch, steps=20, width=W4K, height=H4K, n_buildings=371):
+CITY = dict(n_buildings=24, patches=16, lods=5, n_protos=6, err_scale=0.5, seed=3)     # 30 784 LOD-0 meshlets = 3.94 M triangles
+
+
+def frame_benchmark(ctx, stream, torch, steps=20, width=W4K, height=H4K):
     """S3 stand-in (BASELINE configs[2]): procedural city, ~3.8 M LOD-0 triangles, full reference frame sequence
     (instance cull -> stage 0 on last frame's HZB -> HZB -> stage 1 -> HZB -> tile mark -> PBR resolve) along a camera
     path; per-pass CUDA-event times at the reference's timer cut points (renderer.cpp:322-363)."""
     from chord_b200 import camera as cam, renderer, synth
-    scene, camera, objects, info = synth.city_scene(n_buildings=n_buildings, patches=4, lods=3, width=width, height=height, seed=3, n_protos=48)
+    scene, camera, objects, info = synth.city_scene(width=width, height=height, **CITY)
     ctx.upload_scene(scene)
     tr, ir = synth.synthetic_luts()
     ctx.upload_luts(tr, ir)
@@ -224,19 +227,20 @@ def frame_benchmark(ctx, stream, torch, steps=20, width=W4K, height=H4K, n_build
     n = len(t_frames)
     ms = float(np.median(t_frames))
     stats = f.raster_stats()
-    return {'workload': f'S3 stand-in: procedural city, {scene.total_triangles} triangles in {scene.total_meshlets} meshlets (all LODs), '
-                        f'{len(frames[0][1])} objects, {width}x{height}, two-phase HZB + resolve, camera path',
+    return {'workload': f'S3 stand-in (Bistro-sized): procedural city, {lod0} LOD-0 meshlet instances = {lod0 * 128} triangles '
+                        f'({scene.total_meshlets} unique meshlets over 5 LODs, {len(frames[0][1])} objects), {width}x{height}, '
+                        f'LOD cut at 1 px error, two-phase HZB, HZB builds, tile classify + PBR resolve (packed G-buffer), camera path',
             'frames_per_s': 1000.0 / ms, 'ms_per_frame': ms, 'frames_timed': n,
             'pass_us': {k: 1000.0 * v / n for k, v in acc.items()},
             'post_cull_meshlets_last_frame': int(post.count()), 'raster_stats_total': stats}
 
 
-def frame_benchmark_tiled(ctx, stream, torch, dist, rank, world, steps=20, width=W4K, height=H4K, n_buildings=371):
+def frame_benchmark_tiled(ctx, stream, torch, dist, rank, world, steps=20, width=W4K, height=H4K):
     """BASELINE configs[3]: the same city frame split into `world` screen tiles, one per GPU: tile sub-frustum cull, scissored
     raster, tile-local phase-1 HZB, ONE NCCL all-gather of the packed min-HZB tile parts per frame (history for the next
     frame's phase 0), local rebuild of mips 6.., tile-local resolve.  Frame time = max over ranks (device events)."""
     from chord_b200 import camera as cam, multigpu, renderer, synth
-    scene, camera, objects, info = synth.city_scene(n_buildings=n_buildings, patches=4, lods=3, width=width, height=height, seed=3, n_protos=48)
+    scene, camera, objects, info = synth.city_scene(width=width, height=height, **CITY)
     ctx.upload_scene(scene)
     tr, ir = synth.synthetic_luts()
     ctx.upload_luts(tr, ir)
@@ -262,8 +266,8 @@ def frame_benchmark_tiled(ctx, stream, torch, dist, rank, world, steps=20, width
     t = torch.tensor([float(np.median(times)), float(np.mean(times)), float(np.max(times))], dtype=torch.float64, device=f'cuda:{ctx.device}')
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, ms_mean, ms_max = (float(x) for x in t.tolist())
-    return {'workload': f'S3 stand-in city at {width}x{height} split into {world} screen tiles (one per GPU), NCCL all-gather of the '
-                        f'min-HZB tile parts per frame', 'frames_per_s': 1000.0 / ms, 'ms_per_frame': ms, 'ms_per_frame_mean': ms_mean, 'ms_per_frame_max': ms_max,
+    return {'workload': f'S3 stand-in city ({lod0 * 128} LOD-0 triangles) at {width}x{height} split into {world} screen tiles (one per GPU), '
+                        f'NCCL all-gather of the min-HZB tile parts per frame', 'frames_per_s': 1000.0 / ms, 'ms_per_frame': ms, 'ms_per_frame_mean': ms_mean, 'ms_per_frame_max': ms_max,
             'frames_timed': len(times), 'tile_rank0': list(tr_.tile), 'hzb_allgather_bytes': int(sum(tr_.r.history_hzb.tile_bytes(t_) for t_ in multigpu.all_tiles(world, width, height)))}
 
 

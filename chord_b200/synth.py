@@ -268,7 +268,7 @@ def patch_stream_scene(n_meshlets, width=3840, height=2160, seed=5, area_range=(
 
 
 # ----------------------------------------------------------------------------------------------- city (S2/S3)
-def _face_lod_chain(origin, du, dv, patches, normal, vert_base, data_base, meshlet_base, lods):
+def _face_lod_chain(origin, du, dv, patches, normal, vert_base, data_base, meshlet_base, lods, err_scale=0.05):
     """One planar face of ``patches x patches`` LOD-0 patches (8x8 quads each) with a quadtree LOD chain.
 
     Returns dict of arrays to append: positions/normals/uv/tangents, meshletData, meshlets, and a list of group
@@ -321,7 +321,7 @@ def _face_lod_chain(origin, du, dv, patches, normal, vert_base, data_base, meshl
     def sph(level, j, i):
         pl = level_ids[level].shape[0]
         c = origin + ((i + 0.5) / pl) * du + ((j + 0.5) / pl) * dv
-        err = 0.05 * face_len / (level_ids[level - 1].shape[0] * q)     # nominal error of removing level k-1 detail
+        err = err_scale * face_len / (level_ids[level - 1].shape[0] * q)     # nominal error of removing level k-1 detail
         return c, err
 
     for level in range(nl):
@@ -377,13 +377,13 @@ class _PrimBuilder:
         self.nodes = []
         self.lod0 = []
 
-    def add_primitive(self, faces, patches, lods):
+    def add_primitive(self, faces, patches, lods, err_scale=0.05):
         v0, m0, g0, gi0 = self.nv, self.nm, self.ng, self.ngi
         lod0 = 0
         allpos = []
         pgroups, pindices = [], []
         for (o, du, dv, nrm) in faces:
-            f = _face_lod_chain(o, du, dv, patches, nrm, self.nv - v0, self.nd, self.nm - m0, lods)
+            f = _face_lod_chain(o, du, dv, patches, nrm, self.nv - v0, self.nd, self.nm - m0, lods, err_scale)
             self.pos.append(f['positions']); self.nrm.append(f['normals']); self.uv.append(f['uv0'])
             self.tan.append(f['tangents']); self.data.append(f['meshletData']); self.meshlets.append(f['meshlets'])
             allpos.append(f['positions'])
@@ -422,7 +422,7 @@ class _PrimBuilder:
         return abi.HostScene([datas], np.array(self.prims), np.array(materials))
 
 
-def city_scene(n_buildings=26, patches=4, lods=3, width=1920, height=1080, seed=2, ground_patches=8, n_protos=3):
+def city_scene(n_buildings=26, patches=4, lods=3, width=1920, height=1080, seed=2, ground_patches=8, n_protos=3, err_scale=0.05):
     """S2/S3 stand-in: a grid of box buildings (instanced from 3 prototypes with a quadtree LOD DAG per face) on a
     coarse ground slab, camera at street level so that near-plane clipping, large triangles, LOD cuts and occlusion
     all occur.  ``n_buildings=26, patches=4`` ~ 266 k LOD-0 triangles (S2); ``n_buildings=371`` ~ 3.8 M (S3)."""
@@ -432,7 +432,7 @@ def city_scene(n_buildings=26, patches=4, lods=3, width=1920, height=1080, seed=
     if n_protos > 3:
         prng = np.random.default_rng(seed + 1000)
         sizes += [(float(prng.uniform(7, 15)), float(prng.uniform(12, 50)), float(prng.uniform(7, 15))) for _ in range(n_protos - 3)]
-    protos = [b.add_primitive(_box_primitive(sz, patches, lods), patches, lods) for sz in sizes[:max(n_protos, 1)]]
+    protos = [b.add_primitive(_box_primitive(sz, patches, lods), patches, lods, err_scale) for sz in sizes[:max(n_protos, 1)]]
     side = int(math.ceil(math.sqrt(n_buildings)))
     pitch = 40.0
     extent = side * pitch

@@ -18,7 +18,7 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     w, h = 3840, 2160
-    scene, camera, objects, info = synth.city_scene(n_buildings=371, patches=4, lods=3, width=w, height=h, seed=3, n_protos=48)
+    scene, camera, objects, info = synth.city_scene(n_buildings=24, patches=16, lods=5, n_protos=6, err_scale=0.5, seed=3, width=w, height=h)
     ctx = runtime.Context(local)
     ctx.upload_scene(scene)
     tr, ir = synth.synthetic_luts()
