@@ -1,0 +1,346 @@
+"""Meshlet-DAG builder: triangle mesh -> chord's GPU asset layout.
+
+Restates the pipeline of source/asset/nanite_builder.cpp:432-921 (NaniteBuilder::build) with self-contained pieces where
+the reference calls third-party code that is not available offline:
+
+    reference                                            here
+    ------------------------------------------------    ---------------------------------------------------------
+    meshopt_buildMeshlets (255 verts / 128 tris)          greedy region growing over triangle adjacency
+    METIS_PartGraphKway groups of <= 4 meshlets (:584)    greedy grouping by shared boundary edges
+    meshopt_simplifyWithAttributes, LockBorder (:806)     quadric edge collapse onto existing vertices, group border locked
+    accept if <= 80 % of the triangles remain (:840)      same
+    parent error = simplify error + max child (:851)      same; centre = AABB centre of the simplified vertices (:857-866)
+    meshopt_computeMeshletBounds (cone)                   normal cone with meshopt's apex construction
+    buildBVHTree (:313-416)                               synth.build_bvh
+
+Offline tool (the reference runs it at asset-import time), numpy + heapq; sized for meshes of a few 10^4 triangles.
+The per-frame path never calls it.  METIS / meshopt are not bit-reproduced (parity unpinned there too):
+any valid DAG exercises the same per-frame kernels.
+"""
+import heapq
+from collections import defaultdict
+
+import numpy as np
+
+from . import abi
+from .synth import FLT_MAX, build_bvh, default_material
+
+MAX_V, MAX_T = abi.MESHLET_MAX_VERTICES, abi.MESHLET_MAX_TRIANGLES
+SIMPLIFY_TARGET, MIN_REDUCE, MAX_LODS = 0.5, 0.8, 12
+
+
+def _tri_adjacency(tris):
+    """triangle -> neighbours across shared edges."""
+    edge = defaultdict(list)
+    for t, (a, b, c) in enumerate(tris):
+        for e in ((a, b), (b, c), (c, a)):
+            edge[(min(e), max(e))].append(t)
+    adj = [[] for _ in range(len(tris))]
+    for ts in edge.values():
+        for i in ts:
+            for j in ts:
+                if i != j:
+                    adj[i].append(j)
+    return adj, edge
+
+
+def build_meshlets(tris):
+    """Greedy region growing: contiguous clusters of <= 128 triangles / <= 255 vertices. Returns list of triangle-index arrays."""
+    tris = np.asarray(tris)
+    adj, _ = _tri_adjacency(tris)
+    used = np.zeros(len(tris), dtype=bool)
+    out = []
+    order = np.argsort(tris.min(axis=1), kind='stable')          # deterministic seeds
+    for seed in order:
+        if used[seed]:
+            continue
+        cluster, verts, frontier = [], set(), [seed]
+        while frontier and len(cluster) < MAX_T:
+            t = frontier.pop(0)
+            if used[t]:
+                continue
+            nv = verts | set(tris[t].tolist())
+            if len(nv) > MAX_V:
+                continue
+            used[t] = True
+            cluster.append(t)
+            verts = nv
+            frontier += [n for n in adj[t] if not used[n]]
+        out.append(np.array(cluster, dtype=np.int64))
+    return out
+
+
+def _group_meshlets(meshlet_tris, tris):
+    """Groups of <= 4 meshlets sharing the most boundary edges (METIS stand-in, nanite_builder.cpp:584-726)."""
+    edge_owner = defaultdict(set)
+    for m, ts in enumerate(meshlet_tris):
+        for t in ts:
+            a, b, c = tris[t]
+            for e in ((a, b), (b, c), (c, a)):
+                edge_owner[(min(e), max(e))].add(m)
+    link = defaultdict(lambda: defaultdict(int))
+    for owners in edge_owner.values():
+        owners = list(owners)
+        for i in owners:
+            for j in owners:
+                if i != j:
+                    link[i][j] += 1
+    free = set(range(len(meshlet_tris)))
+    groups = []
+    for m in range(len(meshlet_tris)):
+        if m not in free:
+            continue
+        free.discard(m)
+        g = [m]
+        while len(g) < abi.CLUSTER_GROUP_MERGE_MAX:
+            cand = defaultdict(int)
+            for i in g:
+                for j, w in link[i].items():
+                    if j in free:
+                        cand[j] += w
+            if not cand:
+                break
+            best = max(sorted(cand), key=lambda j: cand[j])
+            free.discard(best)
+            g.append(best)
+        groups.append(g)
+    return groups
+
+
+def _simplify(pos, tris, target_count):
+    """Quadric-error edge collapse onto existing vertices with the open border locked (meshopt_SimplifyLockBorder).
+    Returns (new triangle array, error in object units)."""
+    tris = [tuple(int(v) for v in t) for t in tris]
+    edge_count = defaultdict(int)
+    for a, b, c in tris:
+        for e in ((a, b), (b, c), (c, a)):
+            edge_count[(min(e), max(e))] += 1
+    locked = set()
+    for (a, b), n in edge_count.items():
+        if n == 1:
+            locked.add(a); locked.add(b)
+    verts = sorted({v for t in tris for v in t})
+    Q = {v: np.zeros((4, 4)) for v in verts}
+    for a, b, c in tris:
+        p0, p1, p2 = pos[a].astype(np.float64), pos[b].astype(np.float64), pos[c].astype(np.float64)
+        n = np.cross(p1 - p0, p2 - p0)
+        area = np.linalg.norm(n)
+        if area == 0:
+            continue
+        n /= area
+        pl = np.append(n, -np.dot(n, p0))
+        K = np.outer(pl, pl) * area
+        for v in (a, b, c):
+            Q[v] += K
+    vt = defaultdict(set)
+    for i, t in enumerate(tris):
+        for v in t:
+            vt[v].add(i)
+    alive = [True] * len(tris)
+
+    def cost(src, dst):
+        """area-weighted squared distance of dst to the planes accumulated around src and dst"""
+        q = Q[src] + Q[dst]
+        p = np.append(pos[dst].astype(np.float64), 1.0)
+        return float(max(p @ q @ p, 0.0)), 0.0
+
+    heap = []
+    for (a, b) in edge_count:
+        for src, dst in ((a, b), (b, a)):
+            if src in locked:
+                continue
+            c, _ = cost(src, dst)
+            heapq.heappush(heap, (c, src, dst))
+    remap = {}
+
+    def find(v):
+        while v in remap:
+            v = remap[v]
+        return v
+
+    n_alive, max_err = len(tris), 0.0
+    while heap and n_alive > target_count:
+        c, src, dst = heapq.heappop(heap)
+        if src in remap or find(dst) != dst or src == dst:
+            continue
+        # reject collapses that flip a surviving triangle
+        flip = False
+        for ti in vt[src]:
+            if not alive[ti]:
+                continue
+            t = [find(v) for v in tris[ti]]
+            if dst in t:
+                continue
+            old = [pos[v].astype(np.float64) for v in t]
+            new = [pos[dst if v == src else v].astype(np.float64) for v in t]
+            n0 = np.cross(old[1] - old[0], old[2] - old[0]); n1 = np.cross(new[1] - new[0], new[2] - new[0])
+            if np.dot(n0, n1) <= 1e-12 * max(np.dot(n0, n0), 1e-30):
+                flip = True
+                break
+        if flip:
+            continue
+        for ti in list(vt[src]):
+            if not alive[ti]:
+                continue
+            t = [find(v) for v in tris[ti]]
+            if dst in t:
+                alive[ti] = False
+                n_alive -= 1
+            else:
+                vt[dst].add(ti)
+        remap[src] = dst
+        Q[dst] = Q[dst] + Q[src]
+        max_err = max(max_err, c)
+        nb = set()
+        for ti in vt[dst]:
+            if alive[ti]:
+                nb |= {find(v) for v in tris[ti]}
+        nb.discard(dst)
+        for v in nb:
+            if v not in locked:
+                heapq.heappush(heap, (cost(v, dst)[0], v, dst))
+            if dst not in locked:
+                heapq.heappush(heap, (cost(dst, v)[0], dst, v))
+    out = []
+    for i, t in enumerate(tris):
+        if alive[i]:
+            a, b, c = (find(v) for v in t)
+            if a != b and b != c and a != c:
+                out.append((a, b, c))
+    # quadric cost is area-weighted squared distance; report a length (meshopt_SimplifyErrorAbsolute)
+    total_area = sum(np.linalg.norm(np.cross(pos[b] - pos[a], pos[c] - pos[a])) for a, b, c in tris) * 0.5 + 1e-30
+    return np.array(out, dtype=np.int64).reshape(-1, 3), float(np.sqrt(max_err / total_area))
+
+
+def _cone(pos, tris):
+    """meshopt_computeMeshletBounds normal cone: (axis, cutoff, apex)."""
+    p0, p1, p2 = pos[tris[:, 0]], pos[tris[:, 1]], pos[tris[:, 2]]
+    n = np.cross(p1 - p0, p2 - p0).astype(np.float64)
+    ln = np.linalg.norm(n, axis=1)
+    ok = ln > 0
+    center = 0.5 * (pos[np.unique(tris)].min(axis=0) + pos[np.unique(tris)].max(axis=0)).astype(np.float64)
+    if not ok.any():
+        return np.zeros(3), 1.0, center
+    n = n[ok] / ln[ok, None]
+    axis = n.sum(axis=0)
+    la = np.linalg.norm(axis)
+    if la < 1e-12:
+        return np.zeros(3), 1.0, center
+    axis /= la
+    dp = n @ axis
+    mindp = dp.min()
+    if mindp <= 0.1:
+        return np.zeros(3), 1.0, center          # degenerate cone: never culls (dot(..., 0) >= 1 is false)
+    c0 = p0[ok].astype(np.float64)
+    maxt = np.max(((center[None] - c0) * n).sum(axis=1) / dp)
+    return axis, float(np.sqrt(max(1.0 - mindp * mindp, 0.0))), center - axis * maxt
+
+
+class NaniteAsset:
+    """Result: arrays in the reference layout (one GLTFPrimitiveBuffer worth of data)."""
+
+
+def build(positions, triangles, normals=None, uv0=None, max_lods=MAX_LODS):
+    """positions (N,3) f32, triangles (T,3) -> dict ready for abi.HostScene (one primitive) + stats."""
+    pos = np.ascontiguousarray(positions, dtype=np.float32)
+    tris = np.ascontiguousarray(triangles, dtype=np.int64)
+    if normals is None:
+        nacc = np.zeros_like(pos, dtype=np.float64)
+        fn = np.cross(pos[tris[:, 1]] - pos[tris[:, 0]], pos[tris[:, 2]] - pos[tris[:, 0]])
+        for k in range(3):
+            np.add.at(nacc, tris[:, k], fn)
+        normals = (nacc / np.maximum(np.linalg.norm(nacc, axis=1, keepdims=True), 1e-30)).astype(np.float32)
+    if uv0 is None:
+        uv0 = np.zeros((len(pos), 2), dtype=np.float32)
+    meshlets = []          # dict(tris (k,3) global vertex ids, lod, error, center, parent_error, parent_center)
+    cur = [dict(tris=tris[ts], lod=0, error=-1.0, center=np.zeros(3)) for ts in build_meshlets(tris)]
+    stats = []
+    for lod in range(max_lods - 1):
+        stats.append((lod, len(cur), int(sum(len(m['tris']) for m in cur))))
+        if len(cur) <= 1:
+            break
+        all_tris = np.concatenate([m['tris'] for m in cur])
+        offs = np.cumsum([0] + [len(m['tris']) for m in cur])
+        groups = _group_meshlets([np.arange(offs[i], offs[i + 1]) for i in range(len(cur))], all_tris)
+        nxt = []
+        for g in groups:
+            gt = np.concatenate([cur[i]['tris'] for i in g])
+            simp, err = _simplify(pos, gt, int(len(gt) * SIMPLIFY_TARGET))
+            if 0 < len(simp) < len(gt) * MIN_REDUCE:
+                passed = max([0.0] + [cur[i]['error'] for i in g])
+                cerr = err + passed
+                used = np.unique(simp)
+                center = 0.5 * (pos[used].max(axis=0) + pos[used].min(axis=0))
+                for i in g:
+                    cur[i]['parent_error'], cur[i]['parent_center'] = cerr, center
+                for ts in build_meshlets(simp):
+                    nxt.append(dict(tris=simp[ts], lod=lod + 1, error=cerr, center=center))
+        meshlets += cur
+        if not nxt:
+            cur = []
+            break
+        cur = nxt
+    meshlets += cur
+    # ---- pack (asset_gltf_helper.cpp:522-548)
+    recs = np.zeros(len(meshlets), dtype=abi.GPUGLTFMeshlet)
+    data, off = [], 0
+    for i, m in enumerate(meshlets):
+        vs, inv = np.unique(m['tris'], return_inverse=True)
+        local = inv.reshape(-1, 3).astype(np.uint32)
+        assert len(vs) <= MAX_V and len(local) <= MAX_T
+        data.append(vs.astype(np.uint32))
+        data.append((local[:, 0] | (local[:, 1] << 8) | (local[:, 2] << 16)).astype(np.uint32))
+        axis, cutoff, apex = _cone(pos, m['tris'])
+        r = recs[i]
+        r['posMin'], r['posMax'] = pos[vs].min(axis=0), pos[vs].max(axis=0)
+        r['dataOffset'], r['vertexTriangleCount'] = off, abi.pack_vertex_triangle_count(len(vs), len(local))
+        r['coneAxis'], r['coneCutOff'], r['coneApex'], r['lod'] = axis, cutoff, apex, m['lod']
+        off += len(vs) + len(local)
+    # ---- cluster groups: meshlets sharing own + parent spheres, <= 4 each (nanite_builder.cpp:330-395)
+    gmap, glist = {}, []
+    for i, m in enumerate(meshlets):
+        pe = m.get('parent_error', FLT_MAX)
+        pc = m.get('parent_center', m['center'])
+        key = (np.float32(m['error']).tobytes(), np.asarray(m['center'], np.float32).tobytes(), np.float32(pe).tobytes(), np.asarray(pc, np.float32).tobytes())
+        gi = gmap.get(key)
+        if gi is None or len(glist[gi][0]) >= abi.CLUSTER_GROUP_MERGE_MAX:
+            gmap[key] = len(glist)
+            glist.append(([i], m['error'], m['center'], pe, pc))
+        else:
+            glist[gi][0].append(i)
+    groups = np.zeros(len(glist), dtype=abi.GPUGLTFMeshletGroup)
+    gidx = []
+    for k, (ms, e, c, pe, pc) in enumerate(glist):
+        groups[k]['clusterPosCenter'], groups[k]['error'] = c, e
+        groups[k]['parentPosCenter'], groups[k]['parentError'] = pc, pe
+        groups[k]['meshletOffset'], groups[k]['meshletCount'] = len(gidx), len(ms)
+        gidx += ms
+    groups, gidx, nodes = build_bvh(groups, np.array(gidx, dtype=np.uint32))
+    prim = np.zeros(1, dtype=abi.GLTFPrimitiveBuffer)
+    prim['posMin'], prim['posMax'], prim['posAverage'] = pos.min(axis=0), pos.max(axis=0), pos.mean(axis=0)
+    prim['vertexCount'], prim['meshletGroupCount'] = len(pos), len(groups)
+    tang = np.tile(np.array([1, 0, 0, 1], dtype=np.float32), (len(pos), 1))
+    datas = dict(meshlets=recs, positions=pos, normals=normals, uv0=uv0, tangents=tang, meshletData=np.concatenate(data),
+                 groups=groups, groupIndices=gidx, bvhNodes=nodes)
+    lod0 = int((recs['lod'] == 0).sum())
+    return dict(datas=datas, primitive=prim, lod0MeshletCount=lod0, meshletGroupCount=len(groups), lod_stats=stats,
+                lods=int(recs['lod'].max()) + 1)
+
+
+def host_scene(asset, materials=None):
+    return abi.HostScene([asset['datas']], asset['primitive'], np.array(materials if materials is not None else [default_material()]))
+
+
+def terrain_mesh(n=64, size=40.0, seed=1):
+    """Seeded height-field test mesh: (n+1)^2 vertices, 2 n^2 triangles, CCW seen from +y."""
+    rng = np.random.default_rng(seed)
+    g = np.linspace(-size / 2, size / 2, n + 1)
+    xx, zz = np.meshgrid(g, g)
+    ph = rng.uniform(0, 6.28, 4)
+    yy = 1.5 * np.sin(xx * 0.35 + ph[0]) * np.cos(zz * 0.27 + ph[1]) + 0.6 * np.sin(xx * 0.9 + ph[2]) * np.sin(zz * 1.1 + ph[3])
+    pos = np.stack([xx, yy, zz], axis=-1).reshape(-1, 3).astype(np.float32)
+    idx = np.arange((n + 1) * (n + 1)).reshape(n + 1, n + 1)
+    a, b, c, d = idx[:-1, :-1].ravel(), idx[:-1, 1:].ravel(), idx[1:, :-1].ravel(), idx[1:, 1:].ravel()
+    tris = np.concatenate([np.stack([a, c, b], axis=1), np.stack([b, c, d], axis=1)])
+    uv = np.stack([(xx / size + 0.5), (zz / size + 0.5)], axis=-1).reshape(-1, 2).astype(np.float32)
+    return pos, tris, uv

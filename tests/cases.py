@@ -39,3 +39,18 @@ def city_frames(n_buildings=9, w=640, h=360, frames=4, seed=2, lods=3, low=False
         out.append(dict(view=view, iview=cam.fill_instance_view(view), objects=objs, camera=c))
         last_view, last_cam = view, c
     return scene, info, out
+
+
+def terrain_case(n=48, w=640, h=360, seed=1):
+    """A curved mesh through the meshlet-DAG builder (chord_b200/nanite_builder.py): genuine multi-level DAG
+    with geometric simplification, three cameras from close to far so that the LOD cut moves through the levels."""
+    from chord_b200 import nanite_builder as nb
+    pos, tris, uv = nb.terrain_mesh(n=n, seed=seed)
+    asset = nb.build(pos, tris, uv0=uv)
+    scene = nb.host_scene(asset)
+    frames = []
+    for (p, f) in (((2.0, 6.0, 14.0), (0.0, -0.45, -1.0)), ((6.0, 30.0, 70.0), (-0.05, -0.4, -1.0)), ((0.0, 90.0, 260.0), (0.0, -0.33, -1.0))):
+        c = cam.Camera(p, f, width=w, height=h)
+        view = cam.fill_view(c)
+        frames.append(dict(view=view, iview=cam.fill_instance_view(view), objects=np.array([cam.fill_object(np.eye(4), c, 0, 0)]), camera=c))
+    return scene, asset, frames

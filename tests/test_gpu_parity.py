@@ -432,3 +432,36 @@ def test_native_cpp_host(gpu_ctx, tmp_path):
         vis = np.frombuffer(raw[8 + 12 * n:], dtype=np.uint64).reshape(h, w)
         _assert_lists_equal(cmds, ref['post_cull'], f'native host {mode}')
         _assert_vis_equal(vis, ref['vis64'], f'native host {mode}')
+
+
+def test_builder_asset_parity(gpu_ctx):
+    """A curved mesh through the meshlet-DAG builder: per camera the flat and BVH post-cull lists, the packed
+    surface and the HZB chain must equal the oracle bit for bit, with the LOD cut moving through >= 3 levels."""
+    from cases import terrain_case
+    w, h = 640, 360
+    scene, asset, frames = terrain_case(w=w, h=h)
+    gpu_ctx.upload_scene(scene)
+    cap, groups = asset['lod0MeshletCount'] * 2, asset['meshletGroupCount']
+    lods = set()
+    for flags in (0b111, 0b000):
+        gpu_ctx.set_switch_flags(flags)
+        for f in frames:
+            fr = runtime.Frame(gpu_ctx, w, h)
+            fr.begin(f['view'], f['iview'], f['objects'], cap, groups)
+            a, b = runtime.CmdList(gpu_ctx, cap), runtime.CmdList(gpu_ctx, cap)
+            fr.instance_culling(a)
+            fr.instance_culling_bvh(b)
+            ofr = oracle.Frame(scene, f['view'], f['iview'], f['objects'], w, h, flags)
+            ref = ofr.instance_culling(cap)
+            _assert_lists_equal(a.readback(), ref, 'terrain flat')
+            _assert_lists_equal(b.readback(), ref, 'terrain bvh')
+            lods |= set(scene.datas[0]['meshlets']['lod'][ref['meshletId']].tolist())
+            fr.render_mesh(a)
+            ovis, ost = ofr.render_mesh(ref)
+            _assert_vis_equal(fr.vis64(), ovis, 'terrain vis64')
+            assert fr.raster_stats()['trianglesCulled'] == ost['trianglesCulled']
+            hz = runtime.Hzb(gpu_ctx, w, h)
+            fr.build_hzb(hz, True, True, True)
+            _assert_hzb_equal(hz, ofr.build_hzb(ovis, True, True, True), 'min')
+    gpu_ctx.set_switch_flags(0b111)
+    assert len(lods) >= 3
