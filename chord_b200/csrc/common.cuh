@@ -193,8 +193,12 @@ struct chord_frame {
     uint32_t width, height;
     chord_rect tile;
     unsigned long long* vis64;
+    // per-frame inputs: ONE device block [view | iview | objects...] fed by ONE H2D copy per chord_frame_begin from a
+    // pinned staging ring (dView / dIView / dObjects point into it)
+    unsigned char* dInputs; unsigned char* hInputs[4]; cudaEvent_t inputsCopied[4]; uint32_t inputsSlot; size_t inputsBytes;
     chord_PerframeCameraView* dView; chord_InstanceCullingViewInfo* dIView;
     chord_GPUObjectGLTFPrimitive* dObjects; uint32_t objectCapacity, objectCount;
+    chord_rect clearedTile; bool clearedValid;     // region that may hold non-zero texels (tile-only clears)
     chordb::ObjectDerived* dDerived;
     uint32_t lod0MeshletCount, meshletGroupCount;
     float tanHalfFovy;
@@ -208,6 +212,7 @@ struct chord_frame {
     // resolve
     uint32_t* tileMarker; uint32_t* tileList; uint32_t* tileCount; float* gbuffer[CHORD_GBUF_COUNT];
     void* gbufferPackedBuf[CHORD_GBUF_COUNT]; int gbufferPacked;
+    chord_rect gbufTile; bool gbufValid; int gbufPackedMode;     // rect the resolve planes were last fully written for
     void* resolveRecs; uint32_t resolveCapacity;
     // pipelined read-back of the R32_UINT image: two staging slots, a copy stream, events
     uint32_t* splitVis[2]; cudaStream_t copyStream; cudaEvent_t splitDone[2], copyDone[2]; int splitIdx;

@@ -308,8 +308,6 @@ int chord_frame_create(chord_ctx* ctx, uint32_t width, uint32_t height, chord_fr
     f->ctx = ctx; f->width = width; f->height = height;
     f->tile = chord_rect{0, 0, width, height};
     CHORD_CUDA(cudaMalloc(&f->vis64, sizeof(unsigned long long) * (size_t)width * height));
-    CHORD_CUDA(cudaMalloc(&f->dView, sizeof(chord_PerframeCameraView)));
-    CHORD_CUDA(cudaMalloc(&f->dIView, sizeof(chord_InstanceCullingViewInfo)));
     CHORD_CUDA(cudaMalloc(&f->totalGroups, 16));
     CHORD_CUDA(cudaMalloc(&f->bvhCtrl, 32));
     CHORD_CUDA(cudaMemsetAsync(f->bvhCtrl, 0, 32, ctx->stream));
@@ -334,7 +332,8 @@ void chord_frame_destroy(chord_frame* f)
 {
     if (!f) return;
     cudaStreamSynchronize(f->ctx->stream);
-    cudaFree(f->vis64); cudaFree(f->dView); cudaFree(f->dIView); cudaFree(f->dObjects); cudaFree(f->dDerived);
+    cudaFree(f->vis64); cudaFree(f->dInputs); cudaFree(f->dDerived);
+    for (int k = 0; k < 4; k++) { if (f->hInputs[k]) cudaFreeHost(f->hInputs[k]); if (f->inputsCopied[k]) cudaEventDestroy(f->inputsCopied[k]); }
     cudaFree(f->objGroupCount); cudaFree(f->objGroupBase); cudaFree(f->totalGroups);
     cudaFree(f->bvhEntries); cudaFree(f->bvhBits); cudaFree(f->bvhCtrl);
     cudaFree(f->works); cudaFree(f->redoList); cudaFree(f->deferred);
@@ -362,11 +361,23 @@ int chord_frame_begin(chord_frame* f, const chord_PerframeCameraView* view, cons
     } else {
         f->tile = chord_rect{0, 0, f->width, f->height};
     }
+    constexpr size_t kViewBytes = sizeof(chord_PerframeCameraView), kIViewBytes = (sizeof(chord_InstanceCullingViewInfo) + 15) & ~(size_t)15;
+    static_assert(sizeof(chord_PerframeCameraView) % 16 == 0, "view block alignment");
     if (objectCount > f->objectCapacity) {
-        cudaFree(f->dObjects); cudaFree(f->dDerived); cudaFree(f->objGroupCount); cudaFree(f->objGroupBase);
-        f->dObjects = nullptr; f->dDerived = nullptr; f->objGroupCount = nullptr; f->objGroupBase = nullptr; f->objectCapacity = 0;
+        CHORD_CUDA(cudaStreamSynchronize(ctx->stream));
+        cudaFree(f->dInputs); cudaFree(f->dDerived); cudaFree(f->objGroupCount); cudaFree(f->objGroupBase);
+        for (int k = 0; k < 4; k++) { if (f->hInputs[k]) cudaFreeHost(f->hInputs[k]); f->hInputs[k] = nullptr; }
+        f->dInputs = nullptr; f->dDerived = nullptr; f->objGroupCount = nullptr; f->objGroupBase = nullptr; f->objectCapacity = 0;
         uint32_t cap = objectCount + objectCount / 4 + 16;
-        CHORD_CUDA(cudaMalloc(&f->dObjects, sizeof(chord_GPUObjectGLTFPrimitive) * (size_t)cap));
+        f->inputsBytes = kViewBytes + kIViewBytes + sizeof(chord_GPUObjectGLTFPrimitive) * (size_t)cap;
+        CHORD_CUDA(cudaMalloc(&f->dInputs, f->inputsBytes));
+        for (int k = 0; k < 4; k++) {
+            CHORD_CUDA(cudaHostAlloc((void**)&f->hInputs[k], f->inputsBytes, cudaHostAllocDefault));
+            if (!f->inputsCopied[k]) CHORD_CUDA(cudaEventCreateWithFlags(&f->inputsCopied[k], cudaEventDisableTiming));
+        }
+        f->dView = (chord_PerframeCameraView*)f->dInputs;
+        f->dIView = (chord_InstanceCullingViewInfo*)(f->dInputs + kViewBytes);
+        f->dObjects = (chord_GPUObjectGLTFPrimitive*)(f->dInputs + kViewBytes + kIViewBytes);
         CHORD_CUDA(cudaMalloc(&f->dDerived, sizeof(ObjectDerived) * (size_t)cap));
         CHORD_CUDA(cudaMalloc(&f->objGroupCount, sizeof(uint32_t) * (size_t)(cap + 1)));
         CHORD_CUDA(cudaMalloc(&f->objGroupBase, sizeof(uint32_t) * (size_t)(cap + 1)));
@@ -376,11 +387,35 @@ int chord_frame_begin(chord_frame* f, const chord_PerframeCameraView* view, cons
     f->lod0MeshletCount = lod0MeshletCount; f->meshletGroupCount = meshletGroupCount;
     f->hView = *view;
     f->tanHalfFovy = tanf(0.5f * view->cameraFovy);
-    CHORD_CUDA(cudaMemcpyAsync(f->dView, view, sizeof(*view), cudaMemcpyHostToDevice, ctx->stream));
-    CHORD_CUDA(cudaMemcpyAsync(f->dIView, iview, sizeof(*iview), cudaMemcpyHostToDevice, ctx->stream));
-    CHORD_CUDA(cudaMemcpyAsync(f->dObjects, objects, sizeof(chord_GPUObjectGLTFPrimitive) * (size_t)objectCount, cudaMemcpyHostToDevice, ctx->stream));
-    // addClearGbufferPass (render_textures.cpp:74-102): visibility = 0, depth = 0.0 -> packed texel 0
-    CHORD_CUDA(cudaMemsetAsync(f->vis64, 0, sizeof(unsigned long long) * (size_t)f->width * f->height, ctx->stream));
+    {
+        // one H2D copy for view + iview + objects, staged through a 4-slot pinned ring (a slot is reused only after
+        // the copy that read it has completed)
+        const uint32_t slot = f->inputsSlot++ & 3u;
+        CHORD_CUDA(cudaEventSynchronize(f->inputsCopied[slot]));
+        unsigned char* h = f->hInputs[slot];
+        memcpy(h, view, sizeof(*view));
+        memcpy(h + kViewBytes, iview, sizeof(*iview));
+        memcpy(h + kViewBytes + kIViewBytes, objects, sizeof(chord_GPUObjectGLTFPrimitive) * (size_t)objectCount);
+        const size_t bytes = kViewBytes + kIViewBytes + sizeof(chord_GPUObjectGLTFPrimitive) * (size_t)objectCount;
+        CHORD_CUDA(cudaMemcpyAsync(f->dInputs, h, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        CHORD_CUDA(cudaEventRecord(f->inputsCopied[slot], ctx->stream));
+    }
+    // addClearGbufferPass (render_textures.cpp:74-102): visibility = 0, depth = 0.0 -> packed texel 0.  Only texels inside
+    // the region that can be non-zero are rewritten: a rank that renders the same screen tile every frame clears just
+    // that tile (1/N of the surface); everything outside stays 0.
+    {
+        const chord_rect& t = f->tile;
+        const bool same = f->clearedValid && f->clearedTile.x0 == t.x0 && f->clearedTile.y0 == t.y0 && f->clearedTile.x1 == t.x1 && f->clearedTile.y1 == t.y1;
+        if (same && t.x1 - t.x0 < f->width) {
+            CHORD_CUDA(cudaMemset2DAsync(f->vis64 + (size_t)t.y0 * f->width + t.x0, sizeof(unsigned long long) * (size_t)f->width, 0,
+                                         sizeof(unsigned long long) * (size_t)(t.x1 - t.x0), t.y1 - t.y0, ctx->stream));
+        } else if (same) {
+            CHORD_CUDA(cudaMemsetAsync(f->vis64 + (size_t)t.y0 * f->width, 0, sizeof(unsigned long long) * (size_t)f->width * (t.y1 - t.y0), ctx->stream));
+        } else {
+            CHORD_CUDA(cudaMemsetAsync(f->vis64, 0, sizeof(unsigned long long) * (size_t)f->width * f->height, ctx->stream));
+        }
+        f->clearedTile = t; f->clearedValid = true;
+    }
     f->begun = true;
     return launch_object_prepare(f);
 }
