@@ -154,10 +154,60 @@ class Rect(C.Structure):
 class RasterStats(C.Structure):
     _fields_ = [('trianglesSubmitted', C.c_uint64), ('trianglesCulled', C.c_uint64),
                 ('trianglesClipped', C.c_uint64), ('trianglesLarge', C.c_uint64),
-                ('largeQueueOverflow', C.c_uint64), ('meshletsRastered', C.c_uint64)]
+                ('largeQueueOverflow', C.c_uint64), ('meshletsRastered', C.c_uint64),
+                ('fragmentsAlphaKilled', C.c_uint64), ('pad0', C.c_uint64)]
 
     def as_dict(self):
         return {k: int(getattr(self, k)) for k, _ in self._fields_}
+
+
+ADDRESS_REPEAT, ADDRESS_CLAMP_TO_EDGE, ADDRESS_MIRRORED_REPEAT = 0, 1, 2
+
+
+class TextureDesc(C.Structure):
+    _fields_ = [('rgba8', C.c_void_p), ('width', C.c_uint32), ('height', C.c_uint32), ('mipCount', C.c_uint32)]
+
+
+class SamplerDesc(C.Structure):
+    _fields_ = [('addressU', C.c_uint32), ('addressV', C.c_uint32)]
+
+
+def box_mip_chain(level0):
+    """RGBA8 mip chain of an (h, w, 4) uint8 image by 2x2 box filtering (round half up), down to 1x1."""
+    levels = [np.ascontiguousarray(level0, dtype=np.uint8)]
+    while levels[-1].shape[0] > 1 or levels[-1].shape[1] > 1:
+        a = levels[-1].astype(np.uint32)
+        h, w = a.shape[:2]
+        nh, nw = max(h // 2, 1), max(w // 2, 1)
+        ys = np.minimum(np.arange(nh)[:, None] * 2 + np.array([0, 1])[None], h - 1)
+        xs = np.minimum(np.arange(nw)[:, None] * 2 + np.array([0, 1])[None], w - 1)
+        s = a[ys[:, 0]][:, xs[:, 0]] + a[ys[:, 0]][:, xs[:, 1]] + a[ys[:, 1]][:, xs[:, 0]] + a[ys[:, 1]][:, xs[:, 1]]
+        levels.append(((s + 2) // 4).astype(np.uint8))
+    return levels
+
+
+class TextureTable:
+    """The material texture table chord_textures_upload takes: ``textures`` is a list whose entries are None (builtin
+    white) or a list of (h, w, 4) uint8 mip levels (level k is max(1, w >> k) x max(1, h >> k)); ``samplers`` is a list
+    of (addressU, addressV)."""
+
+    def __init__(self, textures, samplers=((ADDRESS_REPEAT, ADDRESS_REPEAT),)):
+        self._keep = []
+        self.tex = (TextureDesc * max(len(textures), 1))()
+        self.n_tex = len(textures)
+        for i, t in enumerate(textures):
+            if t is None:
+                continue
+            h, w = t[0].shape[:2]
+            for k, lv in enumerate(t):
+                assert lv.shape == (max(h >> k, 1), max(w >> k, 1), 4) and lv.dtype == np.uint8, (k, lv.shape)
+            blob = np.concatenate([np.ascontiguousarray(lv).reshape(-1) for lv in t])
+            self._keep.append(blob)
+            self.tex[i].rgba8, self.tex[i].width, self.tex[i].height, self.tex[i].mipCount = blob.ctypes.data, w, h, len(t)
+        self.smp = (SamplerDesc * max(len(samplers), 1))()
+        self.n_smp = len(samplers)
+        for i, (u, v) in enumerate(samplers):
+            self.smp[i].addressU, self.smp[i].addressV = u, v
 
 
 class AtmosphereLuts(C.Structure):
@@ -176,8 +226,9 @@ class HostScene:
     groups (GPUGLTFMeshletGroup), groupIndices u32.
     """
 
-    def __init__(self, datas, primitives, materials):
+    def __init__(self, datas, primitives, materials, textures=None):
         self.datas = datas
+        self.textures = textures          # optional TextureTable (masked bucket)
         self.primitives = np.ascontiguousarray(primitives, dtype=GLTFPrimitiveBuffer)
         self.materials = np.ascontiguousarray(materials, dtype=GLTFMaterialGPUData)
         for d in self.datas:

@@ -44,8 +44,13 @@ struct ObjectDerived {
     chord_float4x4 localToClipLastNoJitter;  // view.translatedWorldToClipLastFrame_NoJitter * localToTranslatedWorldLastFrame
 };
 
+// material texture table of the masked raster bucket (chord_textures_upload): alpha channel only, A8 mip chain
+struct TextureDev { const uint8_t* alpha; uint32_t width, height, mipCount, pad; };     // alpha == nullptr: builtin white
+struct SamplerDev { uint32_t addressU, addressV; };
+
 struct FrameDev {
     SceneDev scene;
+    const TextureDev* textures; const SamplerDev* samplers; uint32_t nTextures, nSamplers;
     const chord_PerframeCameraView*       view;
     const chord_InstanceCullingViewInfo*  iview;
     const chord_GPUObjectGLTFPrimitive*   objects;
@@ -166,6 +171,8 @@ struct chord_ctx {
     uint32_t* scanTicket;
     // atmosphere LUTs
     __half* lutTransmittance; __half* lutIrradiance;
+    // material textures (masked bucket)
+    chordb::TextureDev* dTextures; chordb::SamplerDev* dSamplers; uint8_t* dTexels; uint32_t nTextures, nSamplers;
 };
 
 struct chord_cmdlist {
@@ -208,7 +215,7 @@ struct chord_frame {
     // raster
     void* largeTris; uint32_t* largeCounters; uint32_t largeTriCapacity, largeItemCapacity; void* largeItems;
     unsigned long long* stats;   // device chord_raster_stats
-    void* works; uint32_t worksCapacity; uint32_t* redoList; void* deferred; uint32_t deferredCapacity;
+    void* works; uint32_t worksCapacity; uint32_t* redoList; uint32_t* maskedList; void* deferred; uint32_t deferredCapacity;
     // resolve
     uint32_t* tileMarker; uint32_t* tileList; uint32_t* tileCount; float* gbuffer[CHORD_GBUF_COUNT];
     void* gbufferPackedBuf[CHORD_GBUF_COUNT]; int gbufferPacked;

@@ -30,6 +30,7 @@ FrameDev make_frame_dev(const chord_frame* f)
     d.switchFlags = f->ctx->switchFlags;
     d.tanHalfFovy = f->tanHalfFovy;
     d.vis64 = f->vis64;
+    d.textures = f->ctx->dTextures; d.samplers = f->ctx->dSamplers; d.nTextures = f->ctx->nTextures; d.nSamplers = f->ctx->nSamplers;
     return d;
 }
 
@@ -110,6 +111,7 @@ void chord_ctx_destroy(chord_ctx* ctx)
     if (ctx->scanTicket) cudaFree(ctx->scanTicket);
     if (ctx->lutTransmittance) cudaFree(ctx->lutTransmittance);
     if (ctx->lutIrradiance) cudaFree(ctx->lutIrradiance);
+    cudaFree(ctx->dTextures); cudaFree(ctx->dSamplers); cudaFree(ctx->dTexels);
     cudaStreamDestroy(ctx->stream);
     free(ctx);
 }
@@ -336,7 +338,7 @@ void chord_frame_destroy(chord_frame* f)
     for (int k = 0; k < 4; k++) { if (f->hInputs[k]) cudaFreeHost(f->hInputs[k]); if (f->inputsCopied[k]) cudaEventDestroy(f->inputsCopied[k]); }
     cudaFree(f->objGroupCount); cudaFree(f->objGroupBase); cudaFree(f->totalGroups);
     cudaFree(f->bvhEntries); cudaFree(f->bvhBits); cudaFree(f->bvhCtrl);
-    cudaFree(f->works); cudaFree(f->redoList); cudaFree(f->deferred);
+    cudaFree(f->works); cudaFree(f->redoList); cudaFree(f->maskedList); cudaFree(f->deferred);
     if (f->copyStream) { cudaStreamSynchronize(f->copyStream); for (int k = 0; k < 2; k++) { cudaFree(f->splitVis[k]); cudaEventDestroy(f->splitDone[k]); cudaEventDestroy(f->copyDone[k]); } cudaStreamDestroy(f->copyStream); }
     cudaFree(f->largeTris); cudaFree(f->largeItems); cudaFree(f->largeCounters); cudaFree(f->stats);
     cudaFree(f->tileMarker); cudaFree(f->tileList); cudaFree(f->tileCount); cudaFree(f->resolveRecs);
@@ -507,6 +509,56 @@ int chord_atmosphere_luts_upload(chord_ctx* ctx, const chord_atmosphere_luts* lu
     CHORD_CUDA(cudaMemcpyAsync(ctx->lutTransmittance, luts->transmittance, 256 * 64 * 4 * sizeof(__half), cudaMemcpyHostToDevice, ctx->stream));
     CHORD_CUDA(cudaMemcpyAsync(ctx->lutIrradiance, luts->irradiance, 64 * 16 * 4 * sizeof(__half), cudaMemcpyHostToDevice, ctx->stream));
     CHORD_CUDA(cudaStreamSynchronize(ctx->stream));
+    return CHORD_OK;
+}
+
+int chord_textures_upload(chord_ctx* ctx, const chord_texture_desc* textures, uint32_t textureCount,
+                          const chord_sampler_desc* samplers, uint32_t samplerCount)
+{
+    CHORD_REQUIRE(ctx, "null");
+    CHORD_REQUIRE(textureCount == 0 || textures, "textures");
+    CHORD_REQUIRE(samplerCount == 0 || samplers, "samplers");
+    CHORD_CUDA(cudaSetDevice(ctx->device));
+    CHORD_CUDA(cudaStreamSynchronize(ctx->stream));
+    cudaFree(ctx->dTextures); cudaFree(ctx->dSamplers); cudaFree(ctx->dTexels);
+    ctx->dTextures = nullptr; ctx->dSamplers = nullptr; ctx->dTexels = nullptr; ctx->nTextures = ctx->nSamplers = 0;
+    if (textureCount == 0) return CHORD_OK;
+    // keep the alpha channel only (the raster path reads nothing else): one A8 mip chain per texture, 16-byte aligned
+    std::vector<TextureDev> table(textureCount);
+    std::vector<size_t> offset(textureCount, 0);
+    size_t total = 0;
+    for (uint32_t i = 0; i < textureCount; i++) {
+        const chord_texture_desc& t = textures[i];
+        table[i] = TextureDev{nullptr, t.width, t.height, t.mipCount, 0u};
+        if (!t.rgba8) continue;
+        CHORD_REQUIRE(t.width >= 1 && t.height >= 1 && t.width <= 16384 && t.height <= 16384 && t.mipCount >= 1 && t.mipCount <= 15, "texture dimensions / mip count");
+        size_t texels = 0; uint32_t w = t.width, h = t.height;
+        for (uint32_t l = 0; l < t.mipCount; l++) { texels += (size_t)w * h; w = w > 1 ? w >> 1 : 1; h = h > 1 ? h >> 1 : 1; }
+        offset[i] = total; total += (texels + 15) & ~(size_t)15;
+    }
+    std::vector<uint8_t> alpha(total + 16, 0);
+    for (uint32_t i = 0; i < textureCount; i++) {
+        const chord_texture_desc& t = textures[i];
+        if (!t.rgba8) continue;
+        size_t texels = 0; uint32_t w = t.width, h = t.height;
+        for (uint32_t l = 0; l < t.mipCount; l++) { texels += (size_t)w * h; w = w > 1 ? w >> 1 : 1; h = h > 1 ? h >> 1 : 1; }
+        for (size_t k = 0; k < texels; k++) alpha[offset[i] + k] = t.rgba8[4 * k + 3];
+    }
+    CHORD_CUDA(cudaMalloc(&ctx->dTexels, alpha.size()));
+    CHORD_CUDA(cudaMemcpy(ctx->dTexels, alpha.data(), alpha.size(), cudaMemcpyHostToDevice));
+    for (uint32_t i = 0; i < textureCount; i++) if (textures[i].rgba8) table[i].alpha = ctx->dTexels + offset[i];
+    CHORD_CUDA(cudaMalloc(&ctx->dTextures, sizeof(TextureDev) * textureCount));
+    CHORD_CUDA(cudaMemcpy(ctx->dTextures, table.data(), sizeof(TextureDev) * textureCount, cudaMemcpyHostToDevice));
+    if (samplerCount) {
+        std::vector<SamplerDev> st(samplerCount);
+        for (uint32_t i = 0; i < samplerCount; i++) {
+            CHORD_REQUIRE(samplers[i].addressU <= CHORD_ADDRESS_MIRRORED_REPEAT && samplers[i].addressV <= CHORD_ADDRESS_MIRRORED_REPEAT, "sampler address mode");
+            st[i] = SamplerDev{samplers[i].addressU, samplers[i].addressV};
+        }
+        CHORD_CUDA(cudaMalloc(&ctx->dSamplers, sizeof(SamplerDev) * samplerCount));
+        CHORD_CUDA(cudaMemcpy(ctx->dSamplers, st.data(), sizeof(SamplerDev) * samplerCount, cudaMemcpyHostToDevice));
+    }
+    ctx->nTextures = textureCount; ctx->nSamplers = samplerCount;
     return CHORD_OK;
 }
 

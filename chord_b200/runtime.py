@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, 'libchord_b200.so')
 SYMBOLS = [
     'chord_last_error', 'chord_abi_version',
     'chord_ctx_create', 'chord_ctx_destroy', 'chord_ctx_stream', 'chord_ctx_sync', 'chord_ctx_set_switch_flags',
-    'chord_ctx_get_switch_flags', 'chord_ctx_kernel_launches', 'chord_scene_upload',
+    'chord_ctx_get_switch_flags', 'chord_ctx_kernel_launches', 'chord_scene_upload', 'chord_textures_upload',
     'chord_cmdlist_create', 'chord_cmdlist_destroy', 'chord_cmdlist_upload', 'chord_cmdlist_readback',
     'chord_cmdlist_upload_async', 'chord_readback_visibility32_async', 'chord_frame_wait_readbacks', 'chord_cmdlist_capacity', 'chord_cmdlist_count_ptr', 'chord_cmdlist_cmds_ptr',
     'chord_hzb_create', 'chord_hzb_destroy', 'chord_hzb_info', 'chord_hzb_readback', 'chord_hzb_readback_valid_range',
@@ -114,6 +114,14 @@ class Context:
     def upload_scene(self, scene: abi.HostScene):
         lib().chord_scene_upload(self.h, C.byref(scene.desc))
         self._scene = scene
+        self.upload_textures(getattr(scene, 'textures', None))
+
+    def upload_textures(self, table):
+        """Material texture table of the masked bucket (abi.TextureTable); None = every id is builtin white."""
+        if table is None:
+            lib().chord_textures_upload(self.h, None, C.c_uint32(0), None, C.c_uint32(0))
+        else:
+            lib().chord_textures_upload(self.h, C.byref(table.tex), C.c_uint32(table.n_tex), C.byref(table.smp), C.c_uint32(table.n_smp))
 
     def upload_luts(self, transmittance, irradiance):
         t = np.ascontiguousarray(transmittance, dtype=np.float16)

@@ -486,3 +486,116 @@ def synthetic_luts(seed=7):
     ir = (0.02 + 0.1 * u * (1.0 - 0.5 * v)) * np.array([0.6, 0.8, 1.0])
     ir = np.concatenate([ir, np.ones((16, 64, 1))], axis=-1).astype(np.float16)
     return np.ascontiguousarray(tr), np.ascontiguousarray(ir)
+
+
+# ----------------------------------------------------------------------------------------------- masked bucket (N2)
+def alpha_test_textures(seed=7):
+    """Procedural RGBA8 alpha-test textures with full box-filtered mip chains: [None (builtin white), 64x64 leaf blobs,
+    128x32 chain-link stripes (non-square), 16x16 checker]."""
+    rng = np.random.default_rng(seed)
+
+    def finish(alpha):
+        h, w = alpha.shape
+        img = np.empty((h, w, 4), dtype=np.uint8)
+        img[..., :3] = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        img[..., 3] = alpha
+        return abi.box_mip_chain(img)
+
+    yy, xx = np.mgrid[0:64, 0:64]
+    blobs = np.zeros((64, 64), dtype=np.float64)
+    for _ in range(14):
+        cx, cy, r = rng.uniform(0, 64), rng.uniform(0, 64), rng.uniform(5, 12)
+        d = np.hypot((xx - cx + 32) % 64 - 32, (yy - cy + 32) % 64 - 32)
+        blobs = np.maximum(blobs, np.clip(1.5 - d / r, 0.0, 1.0))
+    leaf = (blobs * 255.0 + 0.5).astype(np.uint8)
+    yy, xx = np.mgrid[0:32, 0:128]
+    link = (((xx + 2 * yy) % 16 < 5) | ((xx - 2 * yy) % 16 < 5)).astype(np.uint8) * np.uint8(255)
+    link = np.where(link > 0, link, rng.integers(0, 90, link.shape).astype(np.uint8)).astype(np.uint8)
+    yy, xx = np.mgrid[0:16, 0:16]
+    checker = (((xx // 2 + yy // 2) % 2) * 200 + 30).astype(np.uint8)
+    return [None, finish(leaf), finish(link), finish(checker)]
+
+
+def masked_scene(width=512, height=384, seed=11, n_random=24):
+    """N2 test scene: instances of one 8x8-quad patch (uv 0..1) with alpha-tested textured materials at varied distance
+    (all mip levels incl. the 1x1 tail), tilt (perspective-correct uv), uv scale via per-material sampler address modes
+    (repeat / clamp / mirror), sidedness, cut-offs; one instance crosses the near plane (clip path with uv), one fills
+    the screen (CTA-cooperative path); untextured masked, blend and opaque materials share the frame."""
+    rng = np.random.default_rng(seed)
+    q = 8
+    g = np.linspace(-1.0, 1.0, q + 1, dtype=F)
+    xx, yy = np.meshgrid(g, g)
+    V, T = (q + 1) ** 2, 2 * q * q
+
+    def patch(uv_scale, uv_offset):
+        pos = np.stack([xx, yy, np.zeros_like(xx)], axis=-1).reshape(-1, 3).astype(F)
+        uv = (np.stack([xx * 0.5 + 0.5, 0.5 - yy * 0.5], axis=-1).reshape(-1, 2) * uv_scale + uv_offset).astype(F)
+        return pos, uv
+
+    # two primitives in one asset: uv in [0, 1] and uv in [-1.3, 2.9] (exercises the address modes)
+    p0, uv0 = patch(1.0, 0.0)
+    p1, uv1 = patch(4.2, -1.3)
+    pos = np.concatenate([p0, p1])
+    uv = np.concatenate([uv0, uv1])
+    topo = _patch_topology(q)
+    data = np.concatenate([np.arange(V, dtype=np.uint32), topo, np.arange(V, dtype=np.uint32), topo])
+    meshlets = np.concatenate([_meshlet_records(p0[None], np.array([0], dtype=np.uint32), V, T, 0, (0, 0, 1)),
+                               _meshlet_records(p1[None], np.array([V + T], dtype=np.uint32), V, T, 0, (0, 0, 1))])
+    groups = np.zeros(2, dtype=abi.GPUGLTFMeshletGroup)
+    groups['clusterPosCenter'] = 0.0
+    groups['parentPosCenter'] = 0.0
+    groups['error'], groups['parentError'] = -1.0, FLT_MAX
+    groups['meshletOffset'], groups['meshletCount'] = 0, 1            # index into the primitive's own groupIndices range
+    normals = np.tile(np.array([0, 0, 1], dtype=F), (2 * V, 1))
+    tang = np.tile(np.array([1, 0, 0, 1], dtype=F), (2 * V, 1))
+    prim = np.zeros(2, dtype=abi.GLTFPrimitiveBuffer)
+    for k in range(2):
+        prim[k]['posMin'], prim[k]['posMax'], prim[k]['posAverage'] = (-1, -1, 0), (1, 1, 0), (0, 0, 0)
+        prim[k]['vertexOffset'], prim[k]['vertexCount'] = k * V, V
+        prim[k]['meshletGroupOffset'], prim[k]['meshletGroupIndicesOffset'], prim[k]['meshletGroupCount'] = k, k, 1
+        prim[k]['meshletOffset'], prim[k]['bvhNodeOffset'] = k, k
+    mats = []
+    for tex, smp, two, cut, fac in ((1, 0, 0, 0.5, 1.0), (1, 1, 1, 0.35, 1.0), (2, 2, 1, 0.5, 0.9), (3, 0, 0, 0.45, 1.0),
+                                    (2, 1, 0, 0.6, 1.0), (3, 2, 1, 0.2, 0.7)):
+        m = default_material(two_sided=two, alpha_mode=1, alpha_cutoff=cut, base_color=(0.8, 0.8, 0.8, fac))
+        m['baseColorId'], m['baseColorSampler'] = tex, smp
+        mats.append(m)
+    mats.append(default_material(alpha_mode=1, alpha_cutoff=0.5))                                   # masked, builtin white: kept
+    mats.append(default_material(alpha_mode=1, alpha_cutoff=0.5, base_color=(1, 1, 1, 0.4)))        # masked, builtin white: dropped
+    mats.append(default_material(alpha_mode=2))                                                     # blend: never drawn
+    mats.append(default_material())                                                                 # opaque
+    mats = np.array(mats)
+    table = abi.TextureTable(alpha_test_textures(), samplers=((abi.ADDRESS_REPEAT, abi.ADDRESS_REPEAT),
+                                                              (abi.ADDRESS_CLAMP_TO_EDGE, abi.ADDRESS_MIRRORED_REPEAT),
+                                                              (abi.ADDRESS_MIRRORED_REPEAT, abi.ADDRESS_CLAMP_TO_EDGE)))
+    parts = [build_bvh(groups[k:k + 1], np.zeros(1, dtype=np.uint32)) for k in range(2)]
+    groups = np.concatenate([p_[0] for p_ in parts]); gidx = np.concatenate([p_[1] for p_ in parts]); nodes = np.concatenate([p_[2] for p_ in parts])
+    scene = abi.HostScene([dict(meshlets=meshlets, positions=pos, normals=normals, uv0=uv, tangents=tang,
+                                meshletData=data, groups=groups, groupIndices=gidx, bvhNodes=nodes)], prim, mats, textures=table)
+    camera = cam.Camera((0, 0, 0), (0, 0, -1), width=width, height=height)
+
+    def xform(center, scale, yaw, pitch, roll=0.0):
+        cy_, sy_, cp, sp, cr, sr = math.cos(yaw), math.sin(yaw), math.cos(pitch), math.sin(pitch), math.cos(roll), math.sin(roll)
+        ry = np.array([[cy_, 0, sy_], [0, 1, 0], [-sy_, 0, cy_]])
+        rx = np.array([[1, 0, 0], [0, cp, -sp], [0, sp, cp]])
+        rz = np.array([[cr, -sr, 0], [sr, cr, 0], [0, 0, 1]])
+        m = np.eye(4)
+        m[:3, :3] = (ry @ rx @ rz) * scale
+        m[:3, 3] = center
+        return m
+
+    objs = []
+    # screen-filling masked quad far back (CTA-cooperative path, low mips), a ground plane through the near plane (clip path)
+    objs.append(cam.fill_object(xform((0, 0, -30.0), 22.0, 0.1, -0.05), camera, 1, 0))
+    objs.append(cam.fill_object(xform((0, -0.6, -1.0), 30.0, 0.3, -1.45), camera, 1, 1))
+    objs.append(cam.fill_object(xform((0.5, 0.2, -20.0), 0.5, 0.4, 0.3), camera, 1, 2))         # ~23 texels / px: level 4..5
+    objs.append(cam.fill_object(xform((-2.0, 1.0, -20.0), 0.13, 0.2, -0.3), camera, 1, 3))      # a few pixels: the 1x1 mip tail
+    for i in range(n_random):
+        z = -float(rng.uniform(1.5, 60.0))
+        ext = -z * 0.45
+        c = (float(rng.uniform(-ext, ext)), float(rng.uniform(-ext * 0.7, ext * 0.7)), z)
+        objs.append(cam.fill_object(xform(c, float(rng.uniform(0.3, 2.5)) * (-z) * 0.12, float(rng.uniform(-1.2, 1.2)),
+                                          float(rng.uniform(-1.2, 1.2)), float(rng.uniform(0, 6.28))),
+                                    camera, int(rng.integers(0, 2)), int(rng.integers(0, len(mats)))))
+    objects = np.array(objs)
+    return scene, camera, objects

@@ -83,6 +83,20 @@ typedef struct {
  * cudaMemcpyDefault); the desc structs themselves, primitives and materials are host memory. Replaces any previous scene. */
 int chord_scene_upload(chord_ctx* ctx, const chord_scene_desc* desc);
 
+/* ---- material textures for the masked (alpha-tested) raster bucket: replaces the bindless Texture2D / SamplerState ids of
+ * GLTFMaterialGPUData.baseColorId / baseColorSampler (gltf.h:118-153; mesh_raster.hlsl:107-112, :198-204) by an index
+ * into the table uploaded here.  Texels are uncompressed RGBA8 unorm (asset_gltf_material.cpp:80-112 also knows BC
+ * formats; decompress before upload), mip k is max(1, w >> k) x max(1, h >> k), mips tightly packed from 0 down.
+ * Only the alpha channel is kept in HBM (one byte per texel): the raster path reads nothing else.
+ * An id that is out of range, CHORD_UNVALID_ID or whose desc has rgba8 == NULL is the builtin white texture
+ * (alpha 1; asset_gltf.cpp:295-326), which makes the alpha test a per-meshlet constant.
+ * The sampler is specified in DESIGN.md section 3 (trilinear, LOD from forward-differenced perspective-correct uv). */
+enum { CHORD_ADDRESS_REPEAT = 0, CHORD_ADDRESS_CLAMP_TO_EDGE = 1, CHORD_ADDRESS_MIRRORED_REPEAT = 2 };
+typedef struct { const uint8_t* rgba8; uint32_t width, height, mipCount; } chord_texture_desc;
+typedef struct { uint32_t addressU, addressV; } chord_sampler_desc;
+int chord_textures_upload(chord_ctx* ctx, const chord_texture_desc* textures, uint32_t textureCount,
+                          const chord_sampler_desc* samplers, uint32_t samplerCount);
+
 /* ---- pooled work lists: CountAndCmdBuffer = {uint count, uint3 cmd[capacity]}
  * (instance_culling.cpp:140-141 sizes them by lod0MeshletCount). */
 int  chord_cmdlist_create(chord_ctx* ctx, uint32_t capacity, chord_cmdlist** out);
@@ -215,6 +229,8 @@ typedef struct {
     uint64_t trianglesLarge;       /* routed through the tile queue */
     uint64_t largeQueueOverflow;   /* handled inline because the queue was full */
     uint64_t meshletsRastered;
+    uint64_t fragmentsAlphaKilled; /* covered samples discarded by the masked bucket's clip() (mesh_raster.hlsl:203) */
+    uint64_t pad0;
 } chord_raster_stats;
 int chord_frame_raster_stats(chord_frame* frame, chord_raster_stats* out);
 /* Shrink the logical capacities of the raster work queues (0 = keep). Overflow never changes the image: deferred

@@ -25,7 +25,8 @@ def build(force=False):
 class _Frame(C.Structure):
     _fields_ = [('scene', C.c_void_p), ('view', C.c_void_p), ('iview', C.c_void_p), ('objects', C.c_void_p),
                 ('objectCount', C.c_uint32), ('width', C.c_uint32), ('height', C.c_uint32),
-                ('tile', abi.Rect), ('switchFlags', C.c_uint32), ('threads', C.c_int)]
+                ('tile', abi.Rect), ('switchFlags', C.c_uint32), ('threads', C.c_int),
+                ('textures', C.c_void_p), ('textureCount', C.c_uint32), ('samplers', C.c_void_p), ('samplerCount', C.c_uint32)]
 
 
 _lib = None
@@ -74,6 +75,10 @@ class Frame:
         t = tile if tile is not None else (0, 0, self.width, self.height)
         f.tile = abi.Rect(*t)
         f.switchFlags, f.threads = switch_flags, threads
+        tt = getattr(scene, 'textures', None)
+        if tt is not None:
+            f.textures, f.textureCount = C.addressof(tt.tex), tt.n_tex
+            f.samplers, f.samplerCount = C.addressof(tt.smp), tt.n_smp
         self.c = f
 
     def instance_culling(self, capacity):
@@ -151,6 +156,16 @@ def lighting(frame, vis64, post_cull, transmittance, irradiance):
     lib().oracle_lighting(C.byref(frame.c), C.c_void_p(vis64.ctypes.data), C.c_void_p(post_cull.ctypes.data),
                           C.c_uint32(len(post_cull)), C.c_void_p(tr.ctypes.data), C.c_void_p(ir.ctypes.data), ptrs)
     return out
+
+
+def sample_alpha(table, tex_id, smp_id, u, v, dudx, dvdx, dudy, dvdy):
+    """The specified sampler of the masked bucket on one sample."""
+    fn = lib().oracle_sample_alpha
+    fn.restype = C.c_float
+    fn.argtypes = [C.c_void_p, C.c_void_p] + [C.c_float] * 6
+    t = C.addressof(table.tex[tex_id]) if tex_id < table.n_tex else None
+    s_ = C.addressof(table.smp[smp_id]) if smp_id < table.n_smp else None
+    return fn(t, s_, u, v, dudx, dvdx, dudy, dvdy)
 
 
 def decode(vis64, post_cull):

@@ -432,6 +432,94 @@ void oracle_hzb_culling(const oracle_frame* f, int firstStage,
     if (outRejectedCount) *outRejectedCount = nr;
 }
 
+/* ------------------------------------------------------------------ K7 masked bucket: the specified sampler
+ * mesh_raster.hlsl:198-204: sampleColor = baseColorTexture.Sample(baseColorSampler, uv); clip(sampleColor.w * factor - cutoff).
+ * Sample() with implicit derivatives is implementation defined on a GPU; pinned here as: trilinear over RGBA8 unorm,
+ * rho^2 = max(|d(uv*dim0)/dx|^2, |d(uv*dim0)/dy|^2); rho <= 1 -> level 0; level = floor(log2 rho) read from the exponent,
+ * fraction = mantissa - 1 (piecewise-linear log2); texel centre convention x = u*w - 0.5; all arithmetic fp32, one
+ * rounding per written operation (fmaf where written). */
+static inline int wrap_texel(int x, int size, uint32_t mode)
+{
+    if (mode == CHORD_ADDRESS_CLAMP_TO_EDGE) return x < 0 ? 0 : (x >= size ? size - 1 : x);
+    if (mode == CHORD_ADDRESS_MIRRORED_REPEAT) {
+        const int p = 2 * size; int m = x % p; if (m < 0) m += p;
+        return m < size ? m : p - 1 - m;
+    }
+    int m = x % size; if (m < 0) m += size;
+    return m;
+}
+
+static float alpha_bilinear(const uint8_t* rgba8, int w, int h, uint32_t modeU, uint32_t modeV, float u, float v)
+{
+    const float x = fmaf(u, (float)w, -0.5f), y = fmaf(v, (float)h, -0.5f);
+    /* clamp before the integer conversion: |x| <= 2^24 keeps floor exact and the conversion defined; NaN -> -2^24 */
+    const float fx0 = fminf(fmaxf(floorf(x), -16777216.0f), 16777216.0f), fy0 = fminf(fmaxf(floorf(y), -16777216.0f), 16777216.0f);
+    float fx = x - fx0, fy = y - fy0;
+    if (!(fx >= 0.0f && fx <= 1.0f)) fx = 0.0f;        /* out-of-range / NaN coordinates: nearest of the clamped texel */
+    if (!(fy >= 0.0f && fy <= 1.0f)) fy = 0.0f;
+    const int x0 = wrap_texel((int)fx0, w, modeU), x1 = wrap_texel((int)fx0 + 1, w, modeU);
+    const int y0 = wrap_texel((int)fy0, h, modeV), y1 = wrap_texel((int)fy0 + 1, h, modeV);
+    const float a00 = (float)rgba8[((size_t)y0 * w + x0) * 4 + 3] / 255.0f, a10 = (float)rgba8[((size_t)y0 * w + x1) * 4 + 3] / 255.0f;
+    const float a01 = (float)rgba8[((size_t)y1 * w + x0) * 4 + 3] / 255.0f, a11 = (float)rgba8[((size_t)y1 * w + x1) * 4 + 3] / 255.0f;
+    const float top = fmaf(fx, a10 - a00, a00), bot = fmaf(fx, a11 - a01, a01);
+    return fmaf(fy, bot - top, top);
+}
+
+static inline const uint8_t* mip_texels(const chord_texture_desc* t, uint32_t level, int* w, int* h)
+{
+    const uint8_t* p = t->rgba8;
+    uint32_t lw = t->width, lh = t->height;
+    for (uint32_t l = 0; l < level; l++) { p += (size_t)lw * lh * 4; lw = lw > 1 ? lw >> 1 : 1; lh = lh > 1 ? lh >> 1 : 1; }
+    *w = (int)lw; *h = (int)lh;
+    return p;
+}
+
+float oracle_sample_alpha(const chord_texture_desc* tex, const chord_sampler_desc* smp, float u, float v,
+                          float dudx, float dvdx, float dudy, float dvdy)
+{
+    if (!tex || !tex->rgba8 || tex->width == 0 || tex->height == 0 || tex->mipCount == 0) return 1.0f;   /* builtin white */
+    const uint32_t modeU = smp ? smp->addressU : CHORD_ADDRESS_REPEAT, modeV = smp ? smp->addressV : CHORD_ADDRESS_REPEAT;
+    const float W0 = (float)tex->width, H0 = (float)tex->height;
+    const float ax = dudx * W0, bx = dvdx * H0, ay = dudy * W0, by = dvdy * H0;
+    const float rx2 = fmaf(bx, bx, ax * ax), ry2 = fmaf(by, by, ay * ay);
+    const float r2 = fmaxf(rx2, ry2);
+    uint32_t level = 0; float frac = 0.0f;
+    if (r2 > 1.0f) {
+        const float rho = sqrtf(r2);
+        const uint32_t bits = f2u(rho);
+        const uint32_t e = (bits >> 23) & 0xFFu;                      /* rho > 1 and not NaN: e >= 127 */
+        if (e - 127u >= tex->mipCount - 1u) { level = tex->mipCount - 1u; frac = 0.0f; }
+        else { level = e - 127u; frac = u2f((bits & 0x007FFFFFu) | 0x3F800000u) - 1.0f; }
+    }
+    int w, h;
+    const uint8_t* t0 = mip_texels(tex, level, &w, &h);
+    float a = alpha_bilinear(t0, w, h, modeU, modeV, u, v);
+    if (frac > 0.0f) {
+        const uint8_t* t1 = mip_texels(tex, level + 1u, &w, &h);
+        const float a1 = alpha_bilinear(t1, w, h, modeU, modeV, u, v);
+        a = fmaf(frac, a1 - a, a);
+    }
+    return a;
+}
+
+/* per-triangle attributes of the masked bucket: 1/w and uv0 per (possibly clipped) vertex + the material's test */
+typedef struct {
+    const chord_texture_desc* tex; const chord_sampler_desc* smp;
+    float alphaFactor, alphaCutOff;
+    float rw[3], uv[3][2];
+    uint64_t* killed;
+} masked_attrs;
+
+/* perspective-correct uv from the three oriented edge values (E[k] = weight numerator of vertex (k+2)%3) */
+static inline void masked_uv(const masked_attrs* m, const int64_t E[3], float invA, float* u, float* v)
+{
+    const float b0 = (float)E[1] * invA, b1 = (float)E[2] * invA, b2 = (float)E[0] * invA;
+    const float q0 = b0 * m->rw[0], q1 = b1 * m->rw[1], q2 = b2 * m->rw[2];
+    const float S = (q0 + q1) + q2;
+    *u = fmaf(q2, m->uv[2][0], fmaf(q1, m->uv[1][0], q0 * m->uv[0][0])) / S;
+    *v = fmaf(q2, m->uv[2][1], fmaf(q1, m->uv[1][1], q0 * m->uv[0][1])) / S;
+}
+
 /* ------------------------------------------------------------------ K6' fixed-function rasteriser (specified) */
 typedef struct {
     uint32_t width, height;
@@ -450,7 +538,7 @@ static inline int64_t ceil_div256(int64_t a) { return -((-a) >> 8); }
 
 /* screen-space triangle: sx, sy in pixels (y down), sz = z/w */
 static void raster_screen_triangle(const raster_target* rt, const float sx[3], const float sy[3], const float sz[3],
-                                   uint32_t visId, int twoSided)
+                                   uint32_t visId, int twoSided, const masked_attrs* masked)
 {
     int64_t X[3], Y[3];
     for (int i = 0; i < 3; i++) {
@@ -497,6 +585,24 @@ static void raster_screen_triangle(const raster_target* rt, const float sx[3], c
                 if (!(E[i] > 0 || (E[i] == 0 && tl[i]))) { inside = 0; break; }
             }
             if (!inside) continue;
+            if (masked) {
+                /* K7 (mesh_raster.hlsl:198-204): uv here and at the +x / +y neighbour samples (forward differences
+                 * stand in for the quad derivatives), specified sampler, clip() */
+                int64_t Ex[3], Ey[3];
+                for (int i = 0; i < 3; i++) {
+                    Ex[i] = s * (dx[i] * (SY - Y[i]) - dy[i] * (SX + 256 - X[i]));
+                    Ey[i] = s * (dx[i] * (SY + 256 - Y[i]) - dy[i] * (SX - X[i]));
+                }
+                float u, v, ux, vx, uy, vy;
+                masked_uv(masked, E, invA, &u, &v);
+                masked_uv(masked, Ex, invA, &ux, &vx);
+                masked_uv(masked, Ey, invA, &uy, &vy);
+                const float a = oracle_sample_alpha(masked->tex, masked->smp, u, v, ux - u, vx - v, uy - u, vy - v);
+                if (fmaf(a, masked->alphaFactor, -masked->alphaCutOff) < 0.0f) {
+                    if (masked->killed) __atomic_fetch_add(masked->killed, 1, __ATOMIC_RELAXED);
+                    continue;
+                }
+            }
             /* weights: w1 = E of edge 2 (v2->v0), w2 = E of edge 0 (v0->v1) */
             float b1 = (float)E[2] * invA;
             float b2 = (float)E[0] * invA;
@@ -532,8 +638,9 @@ static int to_screen(const raster_target* rt, const float c[4], float* sx, float
     return (fabsf(*sx) <= SCREEN_LIMIT) && (fabsf(*sy) <= SCREEN_LIMIT);   /* false for NaN / inf */
 }
 
-/* returns 1 if the clip path was taken */
-static int raster_clip_triangle(const raster_target* rt, const float c[3][4], uint32_t visId, int twoSided)
+/* returns 1 if the clip path was taken.  uv (masked bucket only, else NULL) rides along as two more coordinates */
+static int raster_clip_triangle(const raster_target* rt, const float c[3][4], uint32_t visId, int twoSided,
+                                const masked_attrs* masked)
 {
     int needClip = 0;
     float sx[3], sy[3], sz[3];
@@ -542,12 +649,25 @@ static int raster_clip_triangle(const raster_target* rt, const float c[3][4], ui
     if (!needClip)
         for (int i = 0; i < 3; i++)
             if (!to_screen(rt, c[i], &sx[i], &sy[i], &sz[i])) needClip = 1;
-    if (!needClip) { raster_screen_triangle(rt, sx, sy, sz, visId, twoSided); return 0; }
+    if (!needClip) {
+        if (masked) {
+            masked_attrs m = *masked;
+            for (int i = 0; i < 3; i++) m.rw[i] = 1.0f / c[i][3];
+            raster_screen_triangle(rt, sx, sy, sz, visId, twoSided, &m);
+        } else {
+            raster_screen_triangle(rt, sx, sy, sz, visId, twoSided, NULL);
+        }
+        return 0;
+    }
 
     /* Sutherland-Hodgman in clip space; new vertices are always interpolated from the inside
      * vertex towards the outside one so that a shared edge clips identically in both triangles. */
-    float poly[2][12][4]; int n = 3, cur = 0;
-    memcpy(poly[0], c, sizeof(float) * 12);
+    float poly[2][12][6]; int n = 3, cur = 0;
+    const int nc = masked ? 6 : 4;
+    for (int i = 0; i < 3; i++) {
+        memcpy(poly[0][i], c[i], 16);
+        poly[0][i][4] = masked ? masked->uv[i][0] : 0.0f; poly[0][i][5] = masked ? masked->uv[i][1] : 0.0f;
+    }
     for (int k = 0; k < 6 && n >= 3; k++) {
         int m = 0;
         for (int i = 0; i < n; i++) {
@@ -555,12 +675,12 @@ static int raster_clip_triangle(const raster_target* rt, const float c[3][4], ui
             const float* b = poly[cur][(i + 1) % n];
             float da = clip_plane_dist(a, k), db = clip_plane_dist(b, k);
             int ina = (da >= 0.0f), inb = (db >= 0.0f);
-            if (ina) { memcpy(poly[cur ^ 1][m++], a, 16); }
+            if (ina) { memcpy(poly[cur ^ 1][m++], a, 24); }
             if (ina != inb) {
                 const float* pin = ina ? a : b; const float* pout = ina ? b : a;
                 float din = ina ? da : db, dout = ina ? db : da;
                 float t = din / (din - dout);
-                for (int j = 0; j < 4; j++) poly[cur ^ 1][m][j] = fmaf(t, pout[j] - pin[j], pin[j]);
+                for (int j = 0; j < nc; j++) poly[cur ^ 1][m][j] = fmaf(t, pout[j] - pin[j], pin[j]);
                 m++;
             }
         }
@@ -572,7 +692,17 @@ static int raster_clip_triangle(const raster_target* rt, const float c[3][4], ui
     for (int i = 1; i + 1 < n; i++) {
         if (!(ok[0] && ok[i] && ok[i + 1])) continue;
         float tx[3] = { px[0], px[i], px[i + 1] }, ty[3] = { py[0], py[i], py[i + 1] }, tz[3] = { pz[0], pz[i], pz[i + 1] };
-        raster_screen_triangle(rt, tx, ty, tz, visId, twoSided);
+        if (masked) {
+            masked_attrs m = *masked;
+            const int id[3] = { 0, i, i + 1 };
+            for (int k = 0; k < 3; k++) {
+                m.rw[k] = 1.0f / poly[cur][id[k]][3];
+                m.uv[k][0] = poly[cur][id[k]][4]; m.uv[k][1] = poly[cur][id[k]][5];
+            }
+            raster_screen_triangle(rt, tx, ty, tz, visId, twoSided, &m);
+        } else {
+            raster_screen_triangle(rt, tx, ty, tz, visId, twoSided, NULL);
+        }
     }
     return 1;
 }
@@ -583,7 +713,7 @@ void oracle_raster_clip_triangle(uint32_t width, uint32_t height, const chord_re
     raster_target rt = { width, height, {0, 0, width, height}, vis64 };
     if (tile) rt.tile = *tile;
     float c[3][4]; memcpy(c, clip, sizeof(c));
-    raster_clip_triangle(&rt, c, visId, twoSided);
+    raster_clip_triangle(&rt, c, visId, twoSided, NULL);
 }
 
 /* 3x3 determinant of rows (x,y,w): mesh_raster.hlsl:147 */
@@ -601,11 +731,11 @@ void oracle_render_mesh(const oracle_frame* f, const chord_draw_cmd* cmds, uint3
                         chord_raster_stats* stats)
 {
     raster_target rt = { f->width, f->height, f->tile, vis64 };
-    uint64_t nSub = 0, nCull = 0, nClip = 0, nMesh = 0;
+    uint64_t nSub = 0, nCull = 0, nClip = 0, nMesh = 0, nKilled = 0;
     const float dimW = f->iview->renderDimension.x, dimH = f->iview->renderDimension.y;
 #ifdef _OPENMP
     int nthreads = f->threads > 0 ? f->threads : omp_get_max_threads();
-#pragma omp parallel for schedule(dynamic, 16) num_threads(nthreads) reduction(+:nSub,nCull,nClip,nMesh)
+#pragma omp parallel for schedule(dynamic, 16) num_threads(nthreads) reduction(+:nSub,nCull,nClip,nMesh,nKilled)
 #endif
     for (uint32_t ci = 0; ci < count; ci++) {
         const chord_draw_cmd cmd = cmds[ci];
@@ -613,20 +743,33 @@ void oracle_render_mesh(const oracle_frame* f, const chord_draw_cmd* cmds, uint3
         /* pipeline filter (pipeline_filter.hlsl:41-130; mesh_raster.cpp:224-253): alphaMode 0/1 only */
         if (o.material->alphaMode > 1u) continue;
         const int twoSided = o.material->bTwoSided != 0;
+        masked_attrs mattr; const masked_attrs* masked = NULL;
         if (o.material->alphaMode == 1u) {
-            /* masked, untextured: builtin white texel alpha 1.0 (asset_gltf.cpp:295-326); clip(a*factor - cutoff) */
-            float a = fmaf(1.0f, o.material->baseColorFactor.w, -o.material->alphaCutOff);
-            if (a < 0.0f) continue;
+            const uint32_t tid = o.material->baseColorId;
+            const chord_texture_desc* tex = (f->textures && tid < f->textureCount && f->textures[tid].rgba8) ? &f->textures[tid] : NULL;
+            if (!tex || !o.datas->uv0) {
+                /* masked, untextured: builtin white texel alpha 1.0 (asset_gltf.cpp:295-326); clip(a*factor - cutoff) */
+                float a = fmaf(1.0f, o.material->baseColorFactor.w, -o.material->alphaCutOff);
+                if (a < 0.0f) continue;
+            } else {
+                const uint32_t sid = o.material->baseColorSampler;
+                memset(&mattr, 0, sizeof(mattr));
+                mattr.tex = tex; mattr.smp = (f->samplers && sid < f->samplerCount) ? &f->samplers[sid] : NULL;
+                mattr.alphaFactor = o.material->baseColorFactor.w; mattr.alphaCutOff = o.material->alphaCutOff;
+                mattr.killed = &nKilled;
+                masked = &mattr;
+            }
         }
         const chord_GPUGLTFMeshlet* m = &o.datas->meshlets[cmd.meshletId];
         const uint32_t V = m->vertexTriangleCount & 0xFFu, T = (m->vertexTriangleCount >> 8) & 0xFFu;
         chord_float4x4 mvp; mat_mul(&f->iview->translatedWorldToClip, &o.object->basicData.localToTranslatedWorld, &mvp);
-        float hs[CHORD_MESHLET_MAX_VERTICES + 1][4];
+        float hs[CHORD_MESHLET_MAX_VERTICES + 1][4], huv[CHORD_MESHLET_MAX_VERTICES + 1][2];
         for (uint32_t i = 0; i < V; i++) {
             uint32_t vi = o.prim->vertexOffset + o.datas->meshletData[m->dataOffset + i];
             const float* p = &o.datas->positions[(uint64_t)vi * 3];
             f4 h = mat_mul_vec(&mvp, p[0], p[1], p[2], 1.0f);
             hs[i][0] = h.x; hs[i][1] = h.y; hs[i][2] = h.z; hs[i][3] = h.w;
+            if (masked) { huv[i][0] = o.datas->uv0[(uint64_t)vi * 2]; huv[i][1] = o.datas->uv0[(uint64_t)vi * 2 + 1]; }   /* mesh_raster.hlsl:107-112 */
         }
         nMesh++; nSub += T;
         for (uint32_t t = 0; t < T; t++) {
@@ -653,12 +796,19 @@ void oracle_render_mesh(const oracle_frame* f, const chord_draw_cmd* cmds, uint3
                 { hs[i0][0], hs[i0][1], hs[i0][2], hs[i0][3] },
                 { hs[i1][0], hs[i1][1], hs[i1][2], hs[i1][3] },
                 { hs[i2][0], hs[i2][1], hs[i2][2], hs[i2][3] } };
-            nClip += (uint64_t)raster_clip_triangle(&rt, c, chord_encode_triangle_instance(t, cmd.slot), twoSided);
+            if (masked) {
+                masked_attrs mt = *masked;
+                mt.uv[0][0] = huv[i0][0]; mt.uv[0][1] = huv[i0][1]; mt.uv[1][0] = huv[i1][0]; mt.uv[1][1] = huv[i1][1];
+                mt.uv[2][0] = huv[i2][0]; mt.uv[2][1] = huv[i2][1];
+                nClip += (uint64_t)raster_clip_triangle(&rt, c, chord_encode_triangle_instance(t, cmd.slot), twoSided, &mt);
+            } else {
+                nClip += (uint64_t)raster_clip_triangle(&rt, c, chord_encode_triangle_instance(t, cmd.slot), twoSided, NULL);
+            }
         }
     }
     if (stats) {
         stats->trianglesSubmitted += nSub; stats->trianglesCulled += nCull; stats->trianglesClipped += nClip;
-        stats->meshletsRastered += nMesh;
+        stats->meshletsRastered += nMesh; stats->fragmentsAlphaKilled += nKilled;
     }
 }
 

@@ -28,6 +28,9 @@ typedef struct {
     chord_rect tile;            /* scissor; full frame = {0,0,w,h} */
     uint32_t switchFlags;
     int threads;                /* OpenMP threads (<=0: default) */
+    /* material texture table of the masked bucket (chord_textures_upload); may be NULL / 0 = everything builtin white */
+    const chord_texture_desc* textures; uint32_t textureCount;
+    const chord_sampler_desc* samplers; uint32_t samplerCount;
 } oracle_frame;
 
 /* K1+K2: instance_culling.hlsl:47-208 in canonical (object, group, meshlet) order. returns count. */
@@ -52,6 +55,11 @@ void oracle_render_mesh(const oracle_frame* f, const chord_draw_cmd* cmds, uint3
 /* Rasterise one clip-space triangle (exposed for the exact-arithmetic cross-check tests). */
 void oracle_raster_clip_triangle(uint32_t width, uint32_t height, const chord_rect* tile,
                                  const float clip[12], uint32_t visId, int twoSided, uint64_t* vis64);
+
+/* The specified texture sampler of the masked bucket, exposed for the sampler unit tests: alpha of
+ * `tex` at (u, v) with screen-space derivatives (dudx, dvdx, dudy, dvdy) in uv units. */
+float oracle_sample_alpha(const chord_texture_desc* tex, const chord_sampler_desc* smp, float u, float v,
+                          float dudx, float dvdx, float dudy, float dvdy);
 
 /* K8: hzb.hlsl / hzb_one.hlsl.  Chains receive fp16 bit patterns; offsets as above. */
 void oracle_hzb_dims(uint32_t depthW, uint32_t depthH, uint32_t* mip0W, uint32_t* mip0H, uint32_t* mipCount);

@@ -54,3 +54,11 @@ def terrain_case(n=48, w=640, h=360, seed=1):
         view = cam.fill_view(c)
         frames.append(dict(view=view, iview=cam.fill_instance_view(view), objects=np.array([cam.fill_object(np.eye(4), c, 0, 0)]), camera=c))
     return scene, asset, frames
+
+
+def case_masked(w=512, h=384, seed=11):
+    """SURVEY §8f N2: alpha-tested textured materials (masked raster bucket), chord_b200/synth.py::masked_scene."""
+    scene, camera, objects = synth.masked_scene(w, h, seed)
+    view = cam.fill_view(camera)
+    return dict(name='masked', scene=scene, view=view, iview=cam.fill_instance_view(view), objects=objects, w=w, h=h,
+                lod0=len(objects), groups=len(objects), camera=camera)

@@ -16,7 +16,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 sys.path.insert(0, os.path.dirname(HERE))
 
 import oracle  # noqa: E402
-from cases import case_s1, case_stream, city_frames, digest  # noqa: E402
+from cases import case_masked, case_s1, case_stream, city_frames, digest  # noqa: E402
 
 
 def entry_static(c, flags=0b111, prebuilt=False):
@@ -28,7 +28,8 @@ def entry_static(c, flags=0b111, prebuilt=False):
     return dict(post=digest(post), post_count=len(post), vis64=digest(vis), covered=int((vis != 0).sum()),
                 hzb_min=digest(hz['min']), hzb_max=digest(hz['max']), valid_range=[int(x) for x in hz['range']],
                 marker=digest(fr.visibility_mark(vis, post)) if not prebuilt else None,
-                culled=stats['trianglesCulled'], clipped=stats['trianglesClipped'], submitted=stats['trianglesSubmitted'])
+                culled=stats['trianglesCulled'], clipped=stats['trianglesClipped'], submitted=stats['trianglesSubmitted'],
+                alpha_killed=stats['fragmentsAlphaKilled'])
 
 
 def main():
@@ -37,6 +38,7 @@ def main():
         g[f's1_flags{flags}'] = entry_static(case_s1(), flags)
     for (n, w, h, s) in ((3000, 640, 360, 1.0), (1500, 512, 512, 40.0), (600, 256, 256, 2000.0)):
         g[f'stream_{n}_{w}x{h}_{s}'] = entry_static(case_stream(n, w, h, s), prebuilt=True)
+    g['masked'] = entry_static(case_masked())
     for low in (False, True):
         scene, info, frames = city_frames(low=low)
         prev = None

@@ -465,3 +465,61 @@ def test_builder_asset_parity(gpu_ctx):
             _assert_hzb_equal(hz, ofr.build_hzb(ovis, True, True, True), 'min')
     gpu_ctx.set_switch_flags(0b111)
     assert len(lods) >= 3
+
+
+def test_masked_bucket(gpu_ctx):
+    """alpha-tested textured materials (mesh_raster.hlsl:107-112, :198-204) — per-fragment clip() with the
+    sampler pinned in DESIGN.md section 3.  Bit-exact ids + depth against the oracle for the whole frame, for every
+    meshlet rendered alone (so that hidden instances are checked too), per screen tile, at two resolutions, and with
+    the texture table removed (every masked material falls back to the builtin white constant)."""
+    from cases import case_masked
+    for (w, h) in ((512, 384), (1920, 1080)):
+        c = case_masked(w, h)
+        scene = c['scene']
+        gpu_ctx.upload_scene(scene)
+        n = c['lod0']
+        fr = runtime.Frame(gpu_ctx, w, h)
+        post = runtime.CmdList(gpu_ctx, n)
+        ofr = oracle.Frame(scene, c['view'], c['iview'], c['objects'], w, h)
+        opost = ofr.instance_culling(n)
+        fr.begin(c['view'], c['iview'], c['objects'], n, n)
+        fr.instance_culling(post)
+        _assert_lists_equal(post.readback(), opost, 'post-cull list')
+        fr.reset_stats()
+        fr.render_mesh(post)
+        ovis, ostats = ofr.render_mesh(opost)
+        _assert_vis_equal(fr.vis64(), ovis, f'masked frame {w}x{h}')
+        st = fr.raster_stats()
+        for k in ('trianglesSubmitted', 'trianglesCulled', 'trianglesClipped', 'meshletsRastered', 'fragmentsAlphaKilled'):
+            assert st[k] == ostats[k], (k, st, ostats)
+        assert st['fragmentsAlphaKilled'] > 10000 and st['trianglesClipped'] > 0
+        if (w, h) == (512, 384):
+            one = runtime.CmdList(gpu_ctx, 1)
+            for k in range(len(opost)):
+                one.upload(opost[k:k + 1])
+                fr.begin(c['view'], c['iview'], c['objects'], n, n)
+                fr.render_mesh(one)
+                ov, _ = ofr.render_mesh(opost[k:k + 1])
+                _assert_vis_equal(fr.vis64(), ov, f'meshlet {k} alone (material {int(c["objects"][opost[k]["objectId"]]["GLTFMaterialData"])})')
+            acc = np.zeros((h, w), dtype=np.uint64)
+            for tile in ((0, 0, 256, 192), (256, 0, 512, 192), (0, 192, 256, 384), (256, 192, 512, 384)):
+                fr.begin(c['view'], c['iview'], c['objects'], n, n, tile=tile)
+                fr.render_mesh(post)
+                part = fr.vis64()
+                ot, _ = oracle.Frame(scene, c['view'], c['iview'], c['objects'], w, h, tile=tile).render_mesh(opost)
+                _assert_vis_equal(part, ot, f'masked tile {tile}')
+                acc = np.maximum(acc, part)
+            _assert_vis_equal(acc, ovis, 'union of masked tiles')
+            # no texture table: builtin white everywhere
+            gpu_ctx.upload_textures(None)
+            saved, scene.textures = scene.textures, None
+            try:
+                fr.begin(c['view'], c['iview'], c['objects'], n, n)
+                fr.reset_stats()
+                fr.render_mesh(post)
+                ow, ows = oracle.Frame(scene, c['view'], c['iview'], c['objects'], w, h).render_mesh(opost)
+                _assert_vis_equal(fr.vis64(), ow, 'masked frame without a texture table')
+                assert fr.raster_stats()['fragmentsAlphaKilled'] == 0 == ows['fragmentsAlphaKilled']
+            finally:
+                scene.textures = saved
+    gpu_ctx.upload_textures(None)
