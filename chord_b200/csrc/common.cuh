@@ -171,8 +171,17 @@ struct chord_ctx {
     uint32_t* scanTicket;
     // atmosphere LUTs
     __half* lutTransmittance; __half* lutIrradiance;
+    // graph capture (chord_graph_begin_capture .. end_capture): pinned snapshots made while capturing
+    bool capturing; void** captureAllocs; uint32_t nCaptureAllocs;
     // material textures (masked bucket)
     chordb::TextureDev* dTextures; chordb::SamplerDev* dSamplers; uint8_t* dTexels; uint32_t nTextures, nSamplers;
+};
+
+struct chord_graph {
+    chord_ctx* ctx;
+    cudaGraph_t graph; cudaGraphExec_t exec;
+    uint32_t kernelNodes;
+    void** pinned; uint32_t nPinned;
 };
 
 struct chord_cmdlist {

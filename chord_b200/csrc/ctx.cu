@@ -389,7 +389,18 @@ int chord_frame_begin(chord_frame* f, const chord_PerframeCameraView* view, cons
     f->lod0MeshletCount = lod0MeshletCount; f->meshletGroupCount = meshletGroupCount;
     f->hView = *view;
     f->tanHalfFovy = tanf(0.5f * view->cameraFovy);
-    {
+    const size_t inputBytes = kViewBytes + kIViewBytes + sizeof(chord_GPUObjectGLTFPrimitive) * (size_t)objectCount;
+    if (ctx->capturing) {
+        // captured frame: the uniforms are snapshotted into pinned memory owned by the graph; every replay re-uploads them
+        unsigned char* h = nullptr;
+        CHORD_CUDA(cudaHostAlloc((void**)&h, inputBytes, cudaHostAllocDefault));
+        ctx->captureAllocs = (void**)realloc(ctx->captureAllocs, sizeof(void*) * (ctx->nCaptureAllocs + 1));
+        ctx->captureAllocs[ctx->nCaptureAllocs++] = h;
+        memcpy(h, view, sizeof(*view));
+        memcpy(h + kViewBytes, iview, sizeof(*iview));
+        memcpy(h + kViewBytes + kIViewBytes, objects, sizeof(chord_GPUObjectGLTFPrimitive) * (size_t)objectCount);
+        CHORD_CUDA(cudaMemcpyAsync(f->dInputs, h, inputBytes, cudaMemcpyHostToDevice, ctx->stream));
+    } else {
         // one H2D copy for view + iview + objects, staged through a 4-slot pinned ring (a slot is reused only after
         // the copy that read it has completed)
         const uint32_t slot = f->inputsSlot++ & 3u;
@@ -398,8 +409,7 @@ int chord_frame_begin(chord_frame* f, const chord_PerframeCameraView* view, cons
         memcpy(h, view, sizeof(*view));
         memcpy(h + kViewBytes, iview, sizeof(*iview));
         memcpy(h + kViewBytes + kIViewBytes, objects, sizeof(chord_GPUObjectGLTFPrimitive) * (size_t)objectCount);
-        const size_t bytes = kViewBytes + kIViewBytes + sizeof(chord_GPUObjectGLTFPrimitive) * (size_t)objectCount;
-        CHORD_CUDA(cudaMemcpyAsync(f->dInputs, h, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        CHORD_CUDA(cudaMemcpyAsync(f->dInputs, h, inputBytes, cudaMemcpyHostToDevice, ctx->stream));
         CHORD_CUDA(cudaEventRecord(f->inputsCopied[slot], ctx->stream));
     }
     // addClearGbufferPass (render_textures.cpp:74-102): visibility = 0, depth = 0.0 -> packed texel 0.  Only texels inside
@@ -510,6 +520,70 @@ int chord_atmosphere_luts_upload(chord_ctx* ctx, const chord_atmosphere_luts* lu
     CHORD_CUDA(cudaMemcpyAsync(ctx->lutIrradiance, luts->irradiance, 64 * 16 * 4 * sizeof(__half), cudaMemcpyHostToDevice, ctx->stream));
     CHORD_CUDA(cudaStreamSynchronize(ctx->stream));
     return CHORD_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- graphs
+int chord_graph_begin_capture(chord_ctx* ctx)
+{
+    CHORD_REQUIRE(ctx && !ctx->capturing, "null / already capturing");
+    CHORD_CUDA(cudaSetDevice(ctx->device));
+    CHORD_CUDA(cudaStreamSynchronize(ctx->stream));
+    // relaxed: the captured calls may touch pinned / device allocations (uniform snapshots) without invalidating the capture
+    CHORD_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed));
+    ctx->capturing = true; ctx->captureAllocs = nullptr; ctx->nCaptureAllocs = 0;
+    return CHORD_OK;
+}
+
+int chord_graph_end_capture(chord_ctx* ctx, chord_graph** out)
+{
+    CHORD_REQUIRE(ctx && out && ctx->capturing, "null / not capturing");
+    *out = nullptr;
+    ctx->capturing = false;
+    cudaGraph_t graph = nullptr;
+    const cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
+    if (e != cudaSuccess || !graph) {
+        for (uint32_t i = 0; i < ctx->nCaptureAllocs; i++) cudaFreeHost(ctx->captureAllocs[i]);
+        free(ctx->captureAllocs); ctx->captureAllocs = nullptr; ctx->nCaptureAllocs = 0;
+        set_error("cudaStreamEndCapture failed: %s (a captured call synchronised or failed)", cudaGetErrorString(e));
+        cudaGetLastError();
+        return CHORD_ERR_CUDA;
+    }
+    chord_graph* g = (chord_graph*)calloc(1, sizeof(chord_graph));
+    g->ctx = ctx; g->graph = graph;
+    g->pinned = ctx->captureAllocs; g->nPinned = ctx->nCaptureAllocs;
+    ctx->captureAllocs = nullptr; ctx->nCaptureAllocs = 0;
+    size_t n = 0;
+    CHORD_CUDA(cudaGraphGetNodes(graph, nullptr, &n));
+    std::vector<cudaGraphNode_t> nodes(n);
+    if (n) CHORD_CUDA(cudaGraphGetNodes(graph, nodes.data(), &n));
+    for (size_t i = 0; i < n; i++) {
+        cudaGraphNodeType t;
+        if (cudaGraphNodeGetType(nodes[i], &t) == cudaSuccess && t == cudaGraphNodeTypeKernel) g->kernelNodes++;
+    }
+    CHORD_CUDA(cudaGraphInstantiate(&g->exec, graph, 0));
+    *out = g;
+    return CHORD_OK;
+}
+
+int chord_graph_launch(chord_graph* g)
+{
+    CHORD_REQUIRE(g && g->exec && !g->ctx->capturing, "null / capturing");
+    CHORD_CUDA(cudaGraphLaunch(g->exec, g->ctx->stream));
+    g->ctx->launches += g->kernelNodes;
+    return CHORD_OK;
+}
+
+uint32_t chord_graph_kernel_nodes(const chord_graph* g) { return g ? g->kernelNodes : 0u; }
+
+void chord_graph_destroy(chord_graph* g)
+{
+    if (!g) return;
+    cudaStreamSynchronize(g->ctx->stream);
+    if (g->exec) cudaGraphExecDestroy(g->exec);
+    if (g->graph) cudaGraphDestroy(g->graph);
+    for (uint32_t i = 0; i < g->nPinned; i++) cudaFreeHost(g->pinned[i]);
+    free(g->pinned);
+    free(g);
 }
 
 int chord_textures_upload(chord_ctx* ctx, const chord_texture_desc* textures, uint32_t textureCount,

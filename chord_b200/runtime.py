@@ -27,6 +27,7 @@ SYMBOLS = [
     'chord_readback_vis64', 'chord_readback_visibility32', 'chord_readback_depth32', 'chord_readback_decoded',
     'chord_readback_tile_marker', 'chord_readback_gbuffer_f32', 'chord_frame_set_gbuffer_packed', 'chord_readback_gbuffer_packed', 'chord_frame_vis64_ptr', 'chord_frame_dims',
     'chord_frame_raster_stats', 'chord_frame_reset_stats', 'chord_frame_set_queue_limits',
+    'chord_graph_begin_capture', 'chord_graph_end_capture', 'chord_graph_launch', 'chord_graph_kernel_nodes', 'chord_graph_destroy',
 ]
 
 _lib = None
@@ -51,7 +52,8 @@ def lib():
         L.chord_cmdlist_capacity.restype = C.c_uint32
         for n in ('chord_cmdlist_count_ptr', 'chord_cmdlist_cmds_ptr', 'chord_hzb_chain_ptr', 'chord_frame_vis64_ptr'):
             getattr(L, n).restype = C.c_void_p
-        for n in ('chord_ctx_destroy', 'chord_cmdlist_destroy', 'chord_hzb_destroy', 'chord_frame_destroy'):
+        L.chord_graph_kernel_nodes.restype = C.c_uint32
+        for n in ('chord_ctx_destroy', 'chord_cmdlist_destroy', 'chord_hzb_destroy', 'chord_frame_destroy', 'chord_graph_destroy'):
             getattr(L, n).restype = None
         L.chord_hzb_chain_bytes.restype = C.c_uint64
         L.chord_hzb_mip_offset.restype = C.c_uint64
@@ -129,6 +131,50 @@ class Context:
         assert t.shape == (64, 256, 4) and i.shape == (16, 64, 4)
         luts = abi.AtmosphereLuts(t.ctypes.data, i.ctypes.data)
         lib().chord_atmosphere_luts_upload(self.h, C.byref(luts))
+
+
+class Graph:
+    """A recorded sequence of calls on one context (chord_graph_*): ``with Graph.capture(ctx) as g: ...calls...`` then
+    ``g.launch()``."""
+
+    def __init__(self, ctx):
+        self.ctx, self.h = ctx, C.c_void_p()
+
+    @classmethod
+    def capture(cls, ctx):
+        return cls(ctx)
+
+    def __enter__(self):
+        lib().chord_graph_begin_capture(self.ctx.h)
+        return self
+
+    def __exit__(self, et, ev, tb):
+        if et is not None:
+            try:
+                lib().chord_graph_end_capture(self.ctx.h, C.byref(self.h))
+            except ChordError:
+                pass
+            return False
+        lib().chord_graph_end_capture(self.ctx.h, C.byref(self.h))
+        return False
+
+    @property
+    def kernel_nodes(self):
+        return int(lib().chord_graph_kernel_nodes(self.h))
+
+    def launch(self):
+        lib().chord_graph_launch(self.h)
+
+    def close(self):
+        if self.h:
+            lib().chord_graph_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class CmdList:

@@ -57,6 +57,21 @@ uint32_t chord_ctx_get_switch_flags(const chord_ctx* ctx);
 /* Number of kernels this context has launched since creation (for gpu_launches accounting). */
 uint64_t chord_ctx_kernel_launches(const chord_ctx* ctx);
 
+/* ---- record once / replay many: the reference records its passes into a command buffer every frame
+ * (graphics::CommandList, command_list.h:23-38); here a fixed sequence of chord_* calls on one context (typically
+ * chord_frame_begin .. chord_lighting of one frame) is captured into a CUDA graph and replayed with one launch, which
+ * removes the per-launch gaps of a ~10..30 kernel frame.  Rules: run the sequence once eagerly first (lazy buffers get
+ * sized), then chord_graph_begin_capture, the same calls, chord_graph_end_capture.  Calls that synchronise (read-backs,
+ * chord_ctx_sync, uploads of scenes / textures / LUTs) are invalid while capturing.  The per-frame uniforms given to
+ * chord_frame_begin during capture are snapshotted into pinned memory owned by the graph and re-uploaded by every
+ * replay; work lists, HZBs and frames referenced by the captured calls must outlive the graph. */
+typedef struct chord_graph chord_graph;
+int  chord_graph_begin_capture(chord_ctx* ctx);
+int  chord_graph_end_capture(chord_ctx* ctx, chord_graph** out);
+int  chord_graph_launch(chord_graph* graph);                 /* stream-ordered, asynchronous */
+uint32_t chord_graph_kernel_nodes(const chord_graph* graph); /* kernels one replay launches */
+void chord_graph_destroy(chord_graph* graph);
+
 /* ---- scene: replaces gpu_scene.{h,cpp} pools + the asset GPU buffers
  * (gltf.h:65-153; packing asset_gltf_helper.cpp:522-548, :572-584).  Arrays are the
  * reference structs byte-for-byte.  One chord_primitive_datas_desc corresponds to one

@@ -58,14 +58,30 @@ def main():
                 kev[i][1].record(stream)
             e1.record(stream)
             torch.cuda.synchronize()
+            with runtime.Graph.capture(ctx) as g:
+                frame.begin(view, iv, objects, M, groups, tl)
+                frame.render_mesh(lst)
+            for _ in range(3):
+                g.launch()
+            torch.cuda.synchronize()
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record(stream)
+            for i in range(steps):
+                g.launch()
+            g1.record(stream)
+            torch.cuda.synchronize()
             per_rank.append({'rank': rank, 'tile': list(tile), 'meshlets': int(n_local), 'ms_per_step': e0.elapsed_time(e1) / steps,
-                             'render_mesh_ms': float(np.mean([a.elapsed_time(b) for a, b in kev]))})
+                             'render_mesh_ms': float(np.mean([a.elapsed_time(b) for a, b in kev])),
+                             'graph_ms_per_step': g0.elapsed_time(g1) / steps, 'graph_kernel_nodes': g.kernel_nodes})
+            g.close()
             lst.close()
         out[n] = per_rank
     t1 = out[1][0]['ms_per_step']
     summary = {n: {'max_ms_per_step': max(r['ms_per_step'] for r in out[n]), 'max_render_mesh_ms': max(r['render_mesh_ms'] for r in out[n]),
                    'sum_meshlets': sum(r['meshlets'] for r in out[n]),
-                   'predicted_speedup': t1 / max(r['ms_per_step'] for r in out[n])} for n in out}
+                   'predicted_speedup': t1 / max(r['ms_per_step'] for r in out[n]),
+                   'max_graph_ms_per_step': max(r['graph_ms_per_step'] for r in out[n]),
+                   'predicted_speedup_graph': out[1][0]['graph_ms_per_step'] / max(r['graph_ms_per_step'] for r in out[n])} for n in out}
     print(json.dumps({'summary': summary, 'per_rank': out}), flush=True)
 
 

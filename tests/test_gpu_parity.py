@@ -523,3 +523,49 @@ def test_masked_bucket(gpu_ctx):
             finally:
                 scene.textures = saved
     gpu_ctx.upload_textures(None)
+
+
+def test_graph_replay_matches_eager(gpu_ctx):
+    """chord_graph_*: a recorded frame (uniform upload, clear, cull, raster, HZB, tile mark) replayed as one CUDA graph gives
+    the same bytes as the eager calls, replay after replay, and picks up nothing from the calls made in between."""
+    from cases import case_stream, case_s1
+    c = case_stream(3000, 640, 360, 40.0)
+    gpu_ctx.upload_scene(c['scene'])
+    n, w, h = c['lod0'], c['w'], c['h']
+    fr = runtime.Frame(gpu_ctx, w, h)
+    post = runtime.CmdList(gpu_ctx, n)
+    hz = runtime.Hzb(gpu_ctx, w, h)
+
+    def frame_calls():
+        fr.begin(c['view'], c['iview'], c['objects'], n, c['groups'])
+        fr.instance_culling(post)
+        fr.render_mesh(post)
+        fr.build_hzb(hz, True, True, True)
+        fr.visibility_mark(post)
+
+    frame_calls()
+    ref = dict(vis=fr.vis64(), post=post.readback(), hzb=hz.readback_chain('min'), marker=fr.tile_marker())
+    with runtime.Graph.capture(gpu_ctx) as g:
+        frame_calls()
+    assert g.kernel_nodes >= 8
+    # dirty everything the graph writes, then replay
+    other = cam.fill_view(cam.Camera((0.3, 0.1, 0.5), (0.1, 0.0, -1.0), width=w, height=h))
+    fr.begin(other, cam.fill_instance_view(other), c['objects'], n, c['groups'])
+    fr.instance_culling(post)
+    fr.render_mesh(post)
+    assert not np.array_equal(fr.vis64(), ref['vis'])
+    for rep in range(3):
+        k0 = gpu_ctx.kernel_launches
+        g.launch()
+        assert gpu_ctx.kernel_launches - k0 == g.kernel_nodes
+        _assert_vis_equal(fr.vis64(), ref['vis'], f'graph replay {rep}')
+        _assert_lists_equal(post.readback(), ref['post'], 'post-cull list (graph)')
+        assert np.array_equal(hz.readback_chain('min'), ref['hzb']) and np.array_equal(fr.tile_marker(), ref['marker'])
+    g.close()
+    # a synchronising call inside a capture is reported as an error, and the context stays usable
+    with pytest.raises(runtime.ChordError):
+        with runtime.Graph.capture(gpu_ctx) as bad:
+            frame_calls()
+            fr.vis64()
+    frame_calls()
+    _assert_vis_equal(fr.vis64(), ref['vis'], 'eager after a failed capture')
