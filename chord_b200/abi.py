@@ -162,6 +162,7 @@ class RasterStats(C.Structure):
 
 
 ADDRESS_REPEAT, ADDRESS_CLAMP_TO_EDGE, ADDRESS_MIRRORED_REPEAT = 0, 1, 2
+PASS_DEPTH, PASS_DEPTH_CLAMP = 1, 2
 
 
 class TextureDesc(C.Structure):

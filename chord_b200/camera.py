@@ -179,3 +179,143 @@ def fill_object(local_to_world, camera, primitive_detail, material, local_to_wor
     o['localToTranslatedWorldLastFrame'] = ml.astype(F).T
     o['GLTFPrimitiveDetail'], o['GLTFMaterialData'] = primitive_detail, material
     return o
+
+
+# ----------------------------------------------------------------------------------------------- cascade shadow views (N3)
+class CascadeShadowMapConfig:
+    """render_helper.h:464-500 (only the fields the depth path reads)."""
+
+    def __init__(self, cascadeCount=8, realtimeCascadeCount=3, cascadeDim=2048, cascadeStartDistance=0.0, cascadeEndDistance=80.0,
+                 farCascadeEndDistance=800.0, splitLambda=0.8, farCascadeSplitLambda=0.8, radiusScaleFixed=10.0):
+        self.cascadeCount, self.realtimeCascadeCount, self.cascadeDim = int(cascadeCount), int(realtimeCascadeCount), int(cascadeDim)
+        self.cascadeStartDistance, self.cascadeEndDistance = float(cascadeStartDistance), float(cascadeEndDistance)
+        self.farCascadeEndDistance, self.splitLambda = float(farCascadeEndDistance), float(splitLambda)
+        self.farCascadeSplitLambda, self.radiusScaleFixed = float(farCascadeSplitLambda), float(radiusScaleFixed)
+
+
+def is_cascade_cache_valid(cache_valid, realtime_count, cascade_count, tick, cascade_id):
+    """cascade_setup.hlsl:8-22."""
+    if (not cache_valid) or cascade_id < realtime_count:
+        return False
+    return (tick % (cascade_count - realtime_count)) != (cascade_id - realtime_count)
+
+
+def ortho_rh_zo(left, right, bottom, top, z_near, z_far):
+    """base.hlsli:668-682 ortho_RH_ZeroOne (math convention)."""
+    m = np.zeros((4, 4), dtype=F)
+    m[0, 0] = F(2.0) / (F(right) - F(left))
+    m[1, 1] = F(2.0) / (F(top) - F(bottom))
+    m[2, 2] = F(-1.0) / (F(z_far) - F(z_near))
+    m[0, 3] = -(F(right) + F(left)) / (F(right) - F(left))
+    m[1, 3] = -(F(top) + F(bottom)) / (F(top) - F(bottom))
+    m[2, 3] = -F(z_near) / (F(z_far) - F(z_near))
+    m[3, 3] = F(1.0)
+    return m
+
+
+def cascade_views(view, light_dir, cfg, valid_depth_range=None, previous=None, cache_valid=False):
+    """cascade_setup.hlsl:89-371 cascadeComputeCS on the host: one InstanceCullingViewInfo per cascade (orthographic,
+    reversed z, texel-snapped).  float32 arithmetic in the shader's order; pow() keeps this tolerance-level only, which
+    is why the views are INPUTS of the parity-checked depth path (the reference computes them in a one-workgroup kernel
+    so that the SDSM range never leaves the GPU).  ``valid_depth_range`` = (minBits, maxBits) of buildHZB's valid range
+    or None (kUnvalidIdUint32); ``previous`` = last frame's views, kept where the cascade cache is valid."""
+    near_z, far_z = F(view['zNear']), F(view['zFar'])
+    clip_range = far_z - near_z
+    tick = int(view['basicData']['frameCounter'])
+    n_c, n_rt = cfg.cascadeCount, cfg.realtimeCascadeCount
+    inv = view['clipToTranslatedWorldWithZFar_NoJitter'].T.astype(F)
+    light = _normalize(light_dir)
+
+    def log_split(far_plane, near_plane, cid, count, lam):
+        rng, ratio = F(far_plane) - F(near_plane), F(far_plane) / F(near_plane)
+        p = F(cid + 1) / F(count)
+        log_scale = F(near_plane) * F(np.power(np.abs(ratio), p, dtype=F))
+        uniform = F(near_plane) + rng * p
+        d = F(lam) * (log_scale - uniform) + uniform
+        return (d - near_z) / clip_range
+
+    corners_ndc = np.array([[-1, 1, 1], [1, 1, 1], [1, -1, 1], [-1, -1, 1], [-1, 1, 0], [1, 1, 0], [1, -1, 0], [-1, -1, 0]], dtype=F)
+    base = np.empty((8, 3), dtype=F)
+    for i in range(8):
+        h = inv @ np.append(corners_ndc[i], F(1.0)).astype(F)
+        base[i] = h[:3] / h[3]
+    per = []
+    for cid in range(n_c):
+        if cid < n_rt:
+            min_z, max_z = near_z + F(cfg.cascadeStartDistance), near_z + F(cfg.cascadeEndDistance)
+            lam, count, sid = cfg.splitLambda, n_rt, cid
+            if valid_depth_range is not None:
+                vmin, vmax = (np.array(valid_depth_range, dtype=np.uint32).view(F))
+                if vmax > 0:
+                    min_z = max(min_z, near_z / vmax)
+                if vmin > 0:
+                    stable = F(cfg.cascadeEndDistance) - F(cfg.cascadeStartDistance)
+                    max_z = max(max_z, min_z * F(1.1))
+                    max_z = min(max_z, min_z + stable)
+                    max_z = min(max_z, near_z / vmin)
+                assert max_z > min_z
+            split_start = min_z - near_z
+        else:
+            max_z, lam = near_z + F(cfg.farCascadeEndDistance), cfg.farCascadeSplitLambda
+            min_z, split_start = near_z + F(cfg.cascadeEndDistance), F(cfg.cascadeEndDistance)
+            count, sid = n_c - n_rt, cid - n_rt
+        split = log_split(max_z, min_z, sid, count, lam)
+        prev = split_start / clip_range if sid == 0 else log_split(max_z, min_z, sid - 1, count, lam)
+        split0 = log_split(near_z, near_z + F(cfg.farCascadeEndDistance), 0, n_c, cfg.farCascadeSplitLambda)
+        c, c0 = base.copy(), np.empty((8, 3), dtype=F)
+        for i in range(4):
+            ray = base[i + 4] - base[i]
+            c0[i + 4], c0[i] = base[i] + ray * split0, base[i] + ray * F(0.0)
+            c[i + 4], c[i] = base[i] + ray * split, base[i] + ray * prev
+        center, center0 = c.sum(axis=0, dtype=F) / F(8.0), c0.sum(axis=0, dtype=F) / F(8.0)
+        radius = max(F(np.sqrt(np.dot(p_ - center, p_ - center))) for p_ in c)
+        radius0 = max(F(np.sqrt(np.dot(p_ - center0, p_ - center0))) for p_ in c0)
+        per.append(dict(center=center, radius=F(radius), radius0=F(radius0), min_z=min_z,
+                        csr=F(np.ceil(F(radius) * F(16.0))) / F(16.0)))
+    max_csr = max(p_['csr'] for p_ in per)                 # WaveActiveMax over the cascades
+    out = np.zeros(n_c, dtype=abi.InstanceCullingViewInfo)
+    dim = F(cfg.cascadeDim)
+    for cid, p_ in enumerate(per):
+        if previous is not None and is_cascade_cache_valid(cache_valid, n_rt, n_c, tick, cid):
+            out[cid] = previous[cid]
+            continue
+        ext_xy, ext_z = p_['csr'], max_csr * F(2.0)
+        if cid >= n_rt:
+            radius_scale, z_bias_scale = p_['radius0'] / p_['radius'], F(1.0)
+        else:
+            radius_scale = F(10.0) * F(cfg.radiusScaleFixed) / p_['radius']
+            radius_scale = radius_scale / (radius_scale + F(1.0))
+            z_bias_scale = F(0.25) + (p_['min_z'] - near_z) / (F(cfg.cascadeEndDistance) - F(cfg.cascadeStartDistance))
+        radius_scale = min(radius_scale, F(1.0))
+        cam_pos = (p_['center'] - light * ext_z * F(0.5)).astype(F)
+        sview = look_at_rh(cam_pos, p_['center'], np.array([0, 1, 0], dtype=F))
+        sproj = ortho_rh_zo(-ext_xy, ext_xy, -ext_xy, ext_xy, ext_z, F(0.0))       # near / far swapped: reversed z
+        origin = ((sproj @ sview).astype(F) @ np.array([0, 0, 0, 1], dtype=F)) * (dim / F(2.0))
+        rounded = np.rint(origin[:3]).astype(F)
+        off = (rounded - origin[:3]) * (F(2.0) / dim)
+        sproj[0, 3] += off[0]
+        sproj[1, 3] += off[1]
+        vp = (sproj @ sview).astype(F)
+        inv_vp = np.linalg.inv(vp.astype(np.float64)).astype(F)
+        p = np.empty((8, 3), dtype=F)
+        for i in range(8):
+            h = inv_vp @ np.append(corners_ndc[i], F(1.0)).astype(F)
+            p[i] = h[:3] / h[3]
+
+        def plane(a, b, o, d=None):
+            n = _normalize(np.cross(a - o, b - o))
+            return np.array([n[0], n[1], n[2], -np.dot(n if d is None else d, o)], dtype=F), n
+
+        left, _ = plane(p[4], p[3], p[7])
+        down, _ = plane(p[6], p[3], p[2])
+        right, _ = plane(p[6], p[1], p[5])
+        top, _ = plane(p[5], p[0], p[4])
+        front, front_n = plane(p[1], p[3], p[0])
+        back, _ = plane(p[5], p[7], p[6], d=front_n)       # cascade_setup.hlsl:349 uses frontN in the distance term
+        iv = out[cid]
+        iv['translatedWorldToClip'], iv['clipToTranslatedWorld'] = vp.T, inv_vp.T
+        iv['cameraWorldPos'] = view['cameraWorldPos']
+        iv['orthoDepthConvertToView'] = [sproj[2, 2], sproj[2, 3], z_bias_scale, radius_scale]
+        iv['renderDimension'] = [dim, dim, F(1.0) / dim, F(1.0) / dim]
+        iv['frustumPlanesRS'] = np.stack([left, down, right, top, front, back])
+    return out

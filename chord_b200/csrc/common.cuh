@@ -59,6 +59,7 @@ struct FrameDev {
     uint32_t width, height;
     chord_rect tile;
     uint32_t switchFlags;
+    uint32_t passFlags;                 // CHORD_PASS_* of the raster call in flight (renderMeshDepth)
     float tanHalfFovy;                  // tanf(0.5f * cameraFovy) evaluated on the host (libm), see DESIGN.md §3
     unsigned long long* vis64;          // width*height packed texels
 };
@@ -218,6 +219,7 @@ struct chord_frame {
     chordb::ObjectDerived* dDerived;
     uint32_t lod0MeshletCount, meshletGroupCount;
     float tanHalfFovy;
+    uint32_t passFlags; bool hIViewOrtho;
     // instance culling scratch
     uint32_t* objGroupCount; uint32_t* objGroupBase; uint32_t* totalGroups;
     void* bvhEntries; uint32_t* bvhBits; uint32_t* bvhCtrl; uint32_t bvhCapacity, bvhWords;
@@ -244,6 +246,8 @@ int launch_instance_culling(chord_frame* f, chord_cmdlist* out);
 int launch_instance_culling_bvh(chord_frame* f, chord_cmdlist* out);
 int launch_hzb_culling(chord_frame* f, const chord_hzb* hzb, int firstStage, chord_cmdlist* in, chord_cmdlist* outVis, chord_cmdlist* outRej);
 int launch_render_mesh(chord_frame* f, chord_cmdlist* list);
+int launch_hzb_culling_generic(chord_frame* f, const chord_hzb* hzb, const chord_InstanceCullingViewInfo* hzbView, float extentScale,
+                               int useLastFrame, chord_cmdlist* in, chord_cmdlist* outVis);
 int launch_build_hzb(chord_frame* f, int bMin, int bMax, int bRange, chord_hzb* dst);
 int launch_visibility_mark(chord_frame* f, chord_cmdlist* post);
 int launch_lighting(chord_frame* f, chord_cmdlist* post);

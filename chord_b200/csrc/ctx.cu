@@ -28,6 +28,7 @@ FrameDev make_frame_dev(const chord_frame* f)
     d.objectCount = f->objectCount;
     d.width = f->width; d.height = f->height; d.tile = f->tile;
     d.switchFlags = f->ctx->switchFlags;
+    d.passFlags = f->passFlags;
     d.tanHalfFovy = f->tanHalfFovy;
     d.vis64 = f->vis64;
     d.textures = f->ctx->dTextures; d.samplers = f->ctx->dSamplers; d.nTextures = f->ctx->nTextures; d.nSamplers = f->ctx->nSamplers;
@@ -354,7 +355,8 @@ int chord_frame_begin(chord_frame* f, const chord_PerframeCameraView* view, cons
     CHORD_REQUIRE(objectCount > 0, "objectCount (shouldRenderGLTF, mesh_raster.cpp:45-48)");
     CHORD_REQUIRE(lod0MeshletCount > 0 && meshletGroupCount > 0, "lod0MeshletCount/meshletGroupCount (instance_culling.cpp:108)");
     CHORD_REQUIRE(f->ctx->scene.datas != nullptr, "no scene uploaded");
-    CHORD_REQUIRE((uint32_t)view->renderDimension.x == f->width && (uint32_t)view->renderDimension.y == f->height, "view.renderDimension != frame size");
+    // the raster target is sized by the INSTANCE view (main view: == view.renderDimension; cascade views: cascadeDim)
+    CHORD_REQUIRE((uint32_t)iview->renderDimension.x == f->width && (uint32_t)iview->renderDimension.y == f->height, "instanceView.renderDimension != frame size");
     chord_ctx* ctx = f->ctx;
     CHORD_CUDA(cudaSetDevice(ctx->device));
     if (tile) {
@@ -388,6 +390,7 @@ int chord_frame_begin(chord_frame* f, const chord_PerframeCameraView* view, cons
     f->objectCount = objectCount;
     f->lod0MeshletCount = lod0MeshletCount; f->meshletGroupCount = meshletGroupCount;
     f->hView = *view;
+    f->hIViewOrtho = iview->translatedWorldToClip.m[15] == 1.0f;       // base.hlsli:241-244
     f->tanHalfFovy = tanf(0.5f * view->cameraFovy);
     const size_t inputBytes = kViewBytes + kIViewBytes + sizeof(chord_GPUObjectGLTFPrimitive) * (size_t)objectCount;
     if (ctx->capturing) {
@@ -466,7 +469,29 @@ int chord_hzb_culling(chord_frame* f, const chord_hzb* hzb, int firstStage, chor
 int chord_render_mesh(chord_frame* f, chord_cmdlist* list)
 {
     CHORD_REQUIRE(f && list && f->begun, "null / frame not begun");
+    f->passFlags = 0u;
     return launch_render_mesh(f, list);
+}
+
+int chord_render_mesh_depth(chord_frame* f, chord_cmdlist* list, uint32_t passFlags)
+{
+    CHORD_REQUIRE(f && list && f->begun, "null / frame not begun");
+    CHORD_REQUIRE((passFlags & ~(uint32_t)(CHORD_PASS_DEPTH | CHORD_PASS_DEPTH_CLAMP)) == 0u, "passFlags");
+    // depth clamp drops the near / far clip planes: only defined here for orthographic instance views (w == 1)
+    CHORD_REQUIRE(!(passFlags & CHORD_PASS_DEPTH_CLAMP) || f->hIViewOrtho, "CHORD_PASS_DEPTH_CLAMP needs an orthographic instance view");
+    f->passFlags = passFlags;
+    const int rc = launch_render_mesh(f, list);
+    f->passFlags = 0u;
+    return rc;
+}
+
+int chord_hzb_culling_generic(chord_frame* f, const chord_hzb* hzb, const chord_InstanceCullingViewInfo* hzbView, float extentScale,
+                              int bObjectUseLastFrameProject, chord_cmdlist* in, chord_cmdlist* outVisible)
+{
+    CHORD_REQUIRE(f && hzb && hzbView && in && outVisible && f->begun, "null / frame not begun");
+    CHORD_REQUIRE(hzb->depthW == (uint32_t)hzbView->renderDimension.x && hzb->depthH == (uint32_t)hzbView->renderDimension.y, "hzb was not built for hzbView's render dimension");
+    CHORD_REQUIRE(outVisible->capacity >= in->capacity, "output list capacity");
+    return launch_hzb_culling_generic(f, hzb, hzbView, extentScale, bObjectUseLastFrameProject, in, outVisible);
 }
 
 int chord_visibility_stage0(chord_frame* f, const chord_hzb* lastFrameHzb, chord_cmdlist* in, chord_cmdlist* scratchVisible,

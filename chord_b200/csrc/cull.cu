@@ -11,6 +11,8 @@
 //  while staying one pass over the data.
 #include "common.cuh"
 
+#include <cstring>
+
 namespace chordb {
 
 constexpr int kCullBlock = 256;
@@ -377,6 +379,110 @@ __global__ void __launch_bounds__(kCullBlock) k_hzb_cull(FrameDev f, HzbDev hzb,
     }
 }
 
+// ------------------------------------------------------------------------------------------------ N3: hzbCullingGeneric
+// hzb_culling_generic.hlsl:37-172: one-pass 2x2 test against the HZB of another view (previous cascade / cached cascade)
+struct GenericCullParams {
+    chord_float4x4 viewProj;            // hzbView.translatedWorldToClip
+    float rel[3];                       // float3(perView.cameraWorldPos - hzbView.cameraWorldPos)
+    float W, H, lo, hi;                 // hzbView.renderDimension.xy, extentScale * -/+ 0.5
+    uint32_t useLastFrame;
+};
+
+__global__ void __launch_bounds__(kCullBlock) k_hzb_cull_generic(FrameDev f, HzbDev hzb, GenericCullParams prm,
+                                                                 const chord_draw_cmd* __restrict__ inCmds, const uint32_t* __restrict__ inCount, uint32_t inCapacity,
+                                                                 unsigned long long* __restrict__ scanStatus, uint32_t* __restrict__ ticket,
+                                                                 chord_draw_cmd* __restrict__ outVis, uint32_t* __restrict__ outVisCount)
+{
+    __shared__ uint32_t sTile;
+    __shared__ uint32_t sWarpV[kCullBlock / 32];
+    __shared__ uint32_t sBaseV;
+    uint32_t total = *inCount; if (total > inCapacity) total = inCapacity;
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    while (true) {
+        __syncthreads();
+        if (threadIdx.x == 0) sTile = atomicAdd(ticket, 1u);
+        __syncthreads();
+        const uint32_t tile = sTile;
+        if ((unsigned long long)tile * kCullBlock >= total) break;
+        const uint32_t t = tile * kCullBlock + threadIdx.x;
+        bool active = t < total, visible = true;
+        chord_draw_cmd cmd = chord_draw_cmd{0, 0, 0};
+        if (active) {
+            cmd = inCmds[t];
+            if (has_flag(f.switchFlags, CHORD_FLAG_HZB_CULL_BIT)) {
+                const chord_GPUObjectGLTFPrimitive& obj = f.objects[cmd.objectId];
+                const chord_GLTFPrimitiveBuffer& prim = f.scene.prims[obj.GLTFPrimitiveDetail];
+                const DatasDev& datas = f.scene.datas[prim.primitiveDatasBufferId];
+                const chord_GPUGLTFMeshlet m = datas.meshlets[cmd.meshletId];
+                f3 c, e; meshlet_center_extent(m, false, c, e);
+                float l2w[16], mvp[16];
+                const float* src = prm.useLastFrame ? obj.basicData.localToTranslatedWorldLastFrame.m : obj.basicData.localToTranslatedWorld.m;
+#pragma unroll
+                for (int i = 0; i < 16; i++) l2w[i] = src[i];
+                l2w[12] = __fadd_rn(l2w[12], prm.rel[0]); l2w[13] = __fadd_rn(l2w[13], prm.rel[1]); l2w[14] = __fadd_rn(l2w[14], prm.rel[2]);
+                mat_mul(prm.viewProj.m, l2w, mvp);
+                float mn0 = 10.0f, mn1 = 10.0f, mn2 = 10.0f, mx0 = -10.0f, mx1 = -10.0f, mx2 = -10.0f;
+                bool can = true;
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    float x = __fmaf_rn(e.x, kExtentApplyFactor[i][0], c.x);
+                    float y = __fmaf_rn(e.y, kExtentApplyFactor[i][1], c.y);
+                    float z = __fmaf_rn(e.z, kExtentApplyFactor[i][2], c.z);
+                    UVZ u = project_pos_to_uvz(mvp, x, y, z);
+                    mn0 = fminf(mn0, u.x); mn1 = fminf(mn1, u.y); mn2 = fminf(mn2, u.z);
+                    mx0 = fmaxf(mx0, u.x); mx1 = fmaxf(mx1, u.y); mx2 = fmaxf(mx2, u.z);
+                    can = can && (u.x < 1.0f && u.y < 1.0f && u.z < 1.0f) && (u.x > 0.0f && u.y > 0.0f && u.z > 0.0f);
+                }
+                if (can) {
+                    int rx0 = __float2int_rz(__fmaf_rn(mn0, prm.W, prm.lo)), ry0 = __float2int_rz(__fmaf_rn(mn1, prm.H, prm.lo));
+                    int rx1 = __float2int_rz(__fmaf_rn(mx0, prm.W, prm.hi)), ry1 = __float2int_rz(__fmaf_rn(mx1, prm.H, prm.hi));
+                    rx0 = max(rx0, 0); ry0 = max(ry0, 0);
+                    rx1 = __float2int_rz(fminf(__fsub_rn(prm.W, 1.0f), __int2float_rn(rx1)));
+                    ry1 = __float2int_rz(fminf(__fsub_rn(prm.H, 1.0f), __int2float_rn(ry1)));
+                    if (rx1 < rx0 || ry1 < ry0) {
+                        visible = false;
+                    } else {
+                        const int hx0 = rx0 >> 1, hy0 = ry0 >> 1, hx1 = rx1 >> 1, hy1 = ry1 >> 1;
+                        const int dxv = hx1 - hx0, dyv = hy1 - hy0;
+                        const int mlx = dxv > 0 ? 31 - __clz(dxv) : -1, mly = dyv > 0 ? 31 - __clz(dyv) : -1;
+                        int mip = max(0, max(mlx, mly));
+                        if (((hx1 >> mip) - (hx0 >> mip) >= 2) || ((hy1 >> mip) - (hy0 >> mip) >= 2)) mip += 1;     // 2x2 sample: bias one level
+                        const int cx0 = hx0 >> mip, cy0 = hy0 >> mip, cx1 = hx1 >> mip, cy1 = hy1 >> mip;
+                        const uint32_t pitch = hzb.mip0W >> mip;
+                        const __half* mp = hzb.minChain + hzb.mipOffset[mip];
+                        float zMin = 10.0f;
+#pragma unroll
+                        for (int x = 0; x < 2; x++)
+#pragma unroll
+                            for (int y = 0; y < 2; y++) {
+                                const int sx = min(cx1, cx0 + x), sy = min(cy1, cy0 + y);
+                                zMin = fminf(zMin, __half2float(mp[(size_t)sy * pitch + (uint32_t)sx]));
+                            }
+                        if (zMin > mx2) visible = false;
+                    }
+                }
+            }
+        }
+        const uint32_t vbit = (active && visible) ? 1u : 0u;
+        const uint32_t vmask = __ballot_sync(0xffffffffu, vbit);
+        const uint32_t lt = (1u << lane) - 1u;
+        if (lane == 0) sWarpV[warp] = __popc(vmask);
+        __syncthreads();
+        uint32_t baseV = 0, totV = 0;
+#pragma unroll
+        for (int w = 0; w < kCullBlock / 32; w++) { const uint32_t a = sWarpV[w]; if (w < (int)warp) baseV += a; totV += a; }
+        if (warp == 0) {
+            unsigned long long ex = scan_tile_exclusive_prefix(scanStatus, tile, (unsigned long long)totV);
+            if (lane == 0) {
+                sBaseV = (uint32_t)ex;
+                if ((unsigned long long)(tile + 1) * kCullBlock >= total) *outVisCount = sBaseV + totV;
+            }
+        }
+        __syncthreads();
+        if (vbit) outVis[sBaseV + baseV + __popc(vmask & lt)] = cmd;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ N4: BVH traversal
 // Persistent-warp traversal of the 8-ary cluster-group BVH (gltf.h:16-24; builder nanite_builder.cpp:77-416), which the
 // reference uploads but never walks.  One warp per node: lanes 0..7 test the eight child spheres,
@@ -520,6 +626,37 @@ int launch_hzb_culling(chord_frame* fr, const chord_hzb* hzb, int firstStage, ch
     else
         k_hzb_cull<false><<<grid, kCullBlock, 0, ctx->stream>>>(f, h, in->cmds, in->count, in->capacity, ctx->scanStatus, ctx->scanTicket,
                                                                 outVis->cmds, outVis->count, nullptr, nullptr);
+    ctx->launches++;
+    CHORD_CUDA(cudaGetLastError());
+    return CHORD_OK;
+}
+
+int launch_hzb_culling_generic(chord_frame* fr, const chord_hzb* hzb, const chord_InstanceCullingViewInfo* hzbView, float extentScale,
+                               int useLastFrame, chord_cmdlist* in, chord_cmdlist* outVis)
+{
+    chord_ctx* ctx = fr->ctx;
+    FrameDev f = make_frame_dev(fr);
+    HzbDev h;
+    h.minChain = hzb->minChain; h.mip0W = hzb->mip0W; h.mip0H = hzb->mip0H; h.mipCount = hzb->mipCount;
+    for (int i = 0; i < CHORD_HZB_MAX_MIP_COUNT; i++) h.mipOffset[i] = hzb->mipOffset[i];
+    GenericCullParams prm;
+    prm.viewProj = hzbView->translatedWorldToClip;
+    const chord_uint2* a = &fr->hView.cameraWorldPos.x; const chord_uint2* b = &hzbView->cameraWorldPos.x;
+    for (int k = 0; k < 3; k++) {
+        const uint64_t ua = (uint64_t)a[k].x | ((uint64_t)a[k].y << 32), ub = (uint64_t)b[k].x | ((uint64_t)b[k].y << 32);
+        double da, db; memcpy(&da, &ua, 8); memcpy(&db, &ub, 8);
+        prm.rel[k] = (float)(da - db);             // float3(perView.cameraWorldPos - instanceView.cameraWorldPos), hzb_culling_generic.hlsl:78
+    }
+    prm.W = hzbView->renderDimension.x; prm.H = hzbView->renderDimension.y;
+    prm.lo = extentScale * -0.5f; prm.hi = extentScale * 0.5f;
+    prm.useLastFrame = useLastFrame ? 1u : 0u;
+    const uint32_t tiles = (in->capacity + kCullBlock - 1) / kCullBlock + 1;
+    int rc = scan_reset(ctx, tiles);
+    if (rc) return rc;
+    CHORD_CUDA(cudaMemsetAsync(outVis->count, 0, 4, ctx->stream));
+    uint32_t grid = tiles < (uint32_t)ctx->smCount * 8u ? tiles : (uint32_t)ctx->smCount * 8u;
+    k_hzb_cull_generic<<<grid, kCullBlock, 0, ctx->stream>>>(f, h, prm, in->cmds, in->count, in->capacity, ctx->scanStatus, ctx->scanTicket,
+                                                             outVis->cmds, outVis->count);
     ctx->launches++;
     CHORD_CUDA(cudaGetLastError());
     return CHORD_OK;

@@ -151,3 +151,75 @@ class DeferredRenderer:
         self.post_cull = post
         self.frame_counter += 1
         return post
+
+
+# ----------------------------------------------------------------------------------------------- cascade shadow depth (N3)
+kShadowHZBCullingEnable = True              # r.shadow.hzbCulling (mesh_raster.cpp:28-33)
+kShadowExtentScaleForHZBCulling = 1.5       # mesh_raster.cpp:35-40
+
+
+@dataclass
+class CascadeShadowContext:
+    """render_helper.h CascadeShadowContext / CascadeShadowHistory: per-cascade depth targets (chord_frames of
+    cascadeDim^2 whose packed surface holds the D32 depth in its high word), the cascade views, the light direction."""
+    config: object
+    direction: np.ndarray
+    views: np.ndarray
+    depths: list
+    lists: list = field(default_factory=list)      # post-cull lists per cascade (kept for inspection / tests)
+
+
+def hzbCullingGeneric(frame: Frame, pool: _Pool, hzb, extent_scale, hzb_view, use_last_frame, in_list):
+    """detail::hzbCullingGeneric (hzb_culling_generic.hlsl:37-172) -> new CountAndCmdBuffer."""
+    out = pool.cmdlist(in_list.capacity)
+    frame.hzb_culling_generic(hzb, hzb_view, extent_scale, use_last_frame, in_list, out)
+    return out
+
+
+def renderShadow(ctx: Context, pool: _Pool, view, objects, lod0_meshlet_count, meshlet_group_count, history, config, light_direction,
+                 valid_depth_range=None):
+    """chord::renderShadow (mesh_raster.cpp:332-546): cascade views (cascade_setup.hlsl, host mirror), then for every
+    cascade that is not cache-valid, far to near: instanceCulling with the cascade view -> hzbCullingGeneric against the
+    previous (farther) cascade's HZB, or against the cached depth of the same cascade when there is none -> clear ->
+    renderMeshDepth (two-sided, depth clamp) -> buildHZB(min) for the next cascade.  ``history`` is the
+    CascadeShadowContext of the last frame or None."""
+    cfg = config
+    direction = np.asarray(light_direction, dtype=np.float32)
+    cache_valid = (history is not None and len(history.depths) == cfg.cascadeCount
+                   and np.array_equal(history.direction, direction) and history.config is cfg)
+    tick = int(view['basicData']['frameCounter'])
+    views = cam.cascade_views(view, direction, cfg, valid_depth_range, history.views if cache_valid else None, cache_valid)
+    depths = list(history.depths) if cache_valid else [Frame(ctx, cfg.cascadeDim, cfg.cascadeDim) for _ in range(cfg.cascadeCount)]
+    out = CascadeShadowContext(cfg, direction, views, depths, [None] * cfg.cascadeCount)
+    prev_hzb, prev_id = None, None
+    for cid in range(cfg.cascadeCount - 1, -1, -1):
+        if cam.is_cascade_cache_valid(cache_valid, cfg.realtimeCascadeCount, cfg.cascadeCount, tick, cid):
+            continue
+        f = depths[cid]
+        cached_hzb = None
+        if prev_hzb is None and cache_valid and kShadowHZBCullingEnable:
+            # the cascade's depth of last frame is still in f: build its HZB before the target is cleared
+            cached_hzb = pool.hzb(cfg.cascadeDim, cfg.cascadeDim)
+            f.build_hzb(cached_hzb, True, False, False)
+        f.begin(view, views[cid], objects, lod0_meshlet_count, meshlet_group_count)        # uniforms + clearDepthStencil(0.0)
+        post = pool.cmdlist(lod0_meshlet_count)
+        f.instance_culling(post)
+        if prev_hzb is None:
+            if cached_hzb is not None:
+                # mesh_raster.cpp:463-479 passes cascadeHistory.viewsSRV, which is the SAME buffer CascadeSetupCS has just
+                # rewritten for this cascade (mesh_raster.cpp:411-414): the cached depth is tested with the NEW view
+                culled = hzbCullingGeneric(f, pool, cached_hzb, kShadowExtentScaleForHZBCulling, views[cid], False, post)
+                pool.release(post); post = culled
+                pool.release(cached_hzb)
+        elif kShadowHZBCullingEnable:
+            culled = hzbCullingGeneric(f, pool, prev_hzb, kShadowExtentScaleForHZBCulling, views[prev_id], False, post)
+            pool.release(post); post = culled
+        f.render_mesh_depth(post, abi.PASS_DEPTH | abi.PASS_DEPTH_CLAMP)
+        out.lists[cid] = post
+        if cid != 0:
+            pool.release(prev_hzb)
+            prev_hzb = pool.hzb(cfg.cascadeDim, cfg.cascadeDim)
+            f.build_hzb(prev_hzb, True, False, False)
+            prev_id = cid
+    pool.release(prev_hzb)
+    return out

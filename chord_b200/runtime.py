@@ -22,7 +22,7 @@ SYMBOLS = [
     'chord_hzb_finish_top', 'chord_hzb_tile_bytes', 'chord_hzb_pack_tile', 'chord_hzb_unpack_tiles',
     'chord_frame_create', 'chord_frame_destroy', 'chord_frame_begin', 'chord_instance_culling', 'chord_instance_culling_bvh',
     'chord_readback_bvh_candidates', 'chord_hzb_culling',
-    'chord_render_mesh', 'chord_visibility_stage0', 'chord_visibility_stage1', 'chord_build_hzb',
+    'chord_render_mesh', 'chord_render_mesh_depth', 'chord_hzb_culling_generic', 'chord_visibility_stage0', 'chord_visibility_stage1', 'chord_build_hzb',
     'chord_visibility_mark', 'chord_atmosphere_luts_upload', 'chord_lighting',
     'chord_readback_vis64', 'chord_readback_visibility32', 'chord_readback_depth32', 'chord_readback_decoded',
     'chord_readback_tile_marker', 'chord_readback_gbuffer_f32', 'chord_frame_set_gbuffer_packed', 'chord_readback_gbuffer_packed', 'chord_frame_vis64_ptr', 'chord_frame_dims',
@@ -337,6 +337,13 @@ class Frame:
     def hzb_culling(self, hzb: Hzb, first_stage, inp: CmdList, out_visible: CmdList, out_rejected: CmdList = None):
         lib().chord_hzb_culling(self.h, hzb.h, C.c_int(1 if first_stage else 0), inp.h, out_visible.h,
                                 out_rejected.h if out_rejected is not None else None)
+
+    def render_mesh_depth(self, lst: CmdList, pass_flags=abi.PASS_DEPTH | abi.PASS_DEPTH_CLAMP):
+        lib().chord_render_mesh_depth(self.h, lst.h, C.c_uint32(pass_flags))
+
+    def hzb_culling_generic(self, hzb: Hzb, hzb_view, extent_scale, use_last_frame, inp: CmdList, out_visible: CmdList):
+        hv = np.ascontiguousarray(hzb_view, dtype=abi.InstanceCullingViewInfo).reshape(())
+        lib().chord_hzb_culling_generic(self.h, hzb.h, _p(hv), C.c_float(extent_scale), C.c_int(1 if use_last_frame else 0), inp.h, out_visible.h)
 
     def render_mesh(self, lst: CmdList):
         lib().chord_render_mesh(self.h, lst.h)

@@ -189,6 +189,24 @@ int chord_hzb_culling(chord_frame* frame, const chord_hzb* hzb, int firstStage,
  * list into the frame's visibility/depth surface (K4+K6+K6'+K7 fused). */
 int chord_render_mesh(chord_frame* frame, chord_cmdlist* list);
 
+/* ---- depth-only views (cascade shadow maps): renderMeshDepth (mesh_raster.cpp:159-206, PASS_TYPE_DEPTH)
+ * through the same cull + raster kernels.  A depth view is a chord_frame of cascadeDim x cascadeDim begun with the
+ * cascade's InstanceCullingViewInfo (cascade_setup.hlsl:89-371; frame size == instanceView.renderDimension); its depth is
+ * the high word of the packed surface (chord_readback_depth32), chord_build_hzb builds the cascade HZB from it.
+ *   CHORD_PASS_DEPTH        every material is rasterised two-sided (mesh_raster.cpp:187-189: cull NONE, no cull #0)
+ *   CHORD_PASS_DEPTH_CLAMP  vkCmdSetDepthClampEnableEXT (mesh_raster.cpp:147-150): no near / far clipping, z clamped to
+ *                           [0, 1]; valid for orthographic instance views (w == 1).
+ * The reference also records vkCmdSetDepthBias(const, 0, slope) but never enables depth bias (helper.h:405 leaves
+ * vkCmdSetDepthBiasEnable FALSE, defaults 0.0 render_helper.h:481-482), so no bias is applied on either side. */
+enum { CHORD_PASS_DEPTH = 1u, CHORD_PASS_DEPTH_CLAMP = 2u };
+int chord_render_mesh_depth(chord_frame* frame, chord_cmdlist* list, uint32_t passFlags);
+
+/* detail::hzbCullingGeneric (instance_culling.cpp; hzb_culling_generic.hlsl:37-172): one-pass 2x2 HZB test of the list
+ * against the HZB of ANOTHER view (the previous cascade, or the cached cascade of last frame) with the box rect widened
+ * by extentScale pixels.  hzbView = that view's InstanceCullingViewInfo (host pointer).  Survivors keep input order. */
+int chord_hzb_culling_generic(chord_frame* frame, const chord_hzb* hzb, const chord_InstanceCullingViewInfo* hzbView,
+                              float extentScale, int bObjectUseLastFrameProject, chord_cmdlist* in, chord_cmdlist* outVisible);
+
 /* gltfVisibilityRenderingStage0 (mesh_raster.cpp:269-312).  needStage1 mirrors the bool result.
  * scratchVisible is the pooled list that receives the phase-0 survivors. */
 int chord_visibility_stage0(chord_frame* frame, const chord_hzb* lastFrameHzb /* may be NULL / invalid */,

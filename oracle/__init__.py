@@ -26,7 +26,8 @@ class _Frame(C.Structure):
     _fields_ = [('scene', C.c_void_p), ('view', C.c_void_p), ('iview', C.c_void_p), ('objects', C.c_void_p),
                 ('objectCount', C.c_uint32), ('width', C.c_uint32), ('height', C.c_uint32),
                 ('tile', abi.Rect), ('switchFlags', C.c_uint32), ('threads', C.c_int),
-                ('textures', C.c_void_p), ('textureCount', C.c_uint32), ('samplers', C.c_void_p), ('samplerCount', C.c_uint32)]
+                ('textures', C.c_void_p), ('textureCount', C.c_uint32), ('samplers', C.c_void_p), ('samplerCount', C.c_uint32),
+                ('passFlags', C.c_uint32)]
 
 
 _lib = None
@@ -103,6 +104,25 @@ class Frame:
         lib().oracle_bvh_candidates.restype = C.c_uint32
         n = lib().oracle_bvh_candidates(C.byref(self.c), C.c_void_p(bits.ctypes.data), C.c_uint32(words), C.byref(tot))
         return bits, n, tot.value
+
+    def hzb_culling_generic(self, hzb, hzb_view, extent_scale, use_last_frame, cmds):
+        """hzbCullingGeneric against the HZB of another view (hzb_culling_generic.hlsl:37-172)."""
+        cmds = np.ascontiguousarray(cmds, dtype=abi.DrawCmd)
+        hv = np.ascontiguousarray(hzb_view, dtype=abi.InstanceCullingViewInfo).reshape(())
+        vis = np.zeros(max(len(cmds), 1), dtype=abi.DrawCmd)
+        nv = C.c_uint32()
+        lib().oracle_hzb_culling_generic(C.byref(self.c), C.c_void_p(hv.ctypes.data), C.c_float(extent_scale), C.c_int(1 if use_last_frame else 0),
+                                         C.c_void_p(hzb['min'].ctypes.data), C.c_void_p(hzb['offsets'].ctypes.data), C.c_uint32(hzb['mip0'][0]),
+                                         C.c_void_p(cmds.ctypes.data), C.c_uint32(len(cmds)), C.c_void_p(vis.ctypes.data), C.byref(nv))
+        return vis[:nv.value].copy()
+
+    def render_mesh_depth(self, cmds, vis64=None, pass_flags=abi.PASS_DEPTH | abi.PASS_DEPTH_CLAMP):
+        """renderMeshDepth (mesh_raster.cpp:159-206): PASS_TYPE_DEPTH, always two-sided, depth clamp."""
+        self.c.passFlags = pass_flags
+        try:
+            return self.render_mesh(cmds, vis64)
+        finally:
+            self.c.passFlags = 0
 
     def render_mesh(self, cmds, vis64=None):
         cmds = np.ascontiguousarray(cmds, dtype=abi.DrawCmd)

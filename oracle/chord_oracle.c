@@ -432,6 +432,78 @@ void oracle_hzb_culling(const oracle_frame* f, int firstStage,
     if (outRejectedCount) *outRejectedCount = nr;
 }
 
+/* ------------------------------------------------------------------ hzbCullingGeneric (hzb_culling_generic.hlsl:37-172) */
+static inline double storage_double(chord_uint2 u) { uint64_t b = (uint64_t)u.x | ((uint64_t)u.y << 32); double d; memcpy(&d, &b, 8); return d; }
+
+void oracle_hzb_culling_generic(const oracle_frame* f, const chord_InstanceCullingViewInfo* hzbView, float extentScale,
+                                int bObjectUseLastFrameProject,
+                                const uint16_t* hzbMin, const uint64_t* hzbMipOffsets, uint32_t mip0Width,
+                                const chord_draw_cmd* in, uint32_t inCount, chord_draw_cmd* outVisible, uint32_t* outVisibleCount)
+{
+    uint32_t nv = 0;
+    /* :78-81 relativeOffset = float3(perView.cameraWorldPos - instanceView.cameraWorldPos), per component */
+    const float rel[3] = {
+        (float)(storage_double(f->view->cameraWorldPos.x) - storage_double(hzbView->cameraWorldPos.x)),
+        (float)(storage_double(f->view->cameraWorldPos.y) - storage_double(hzbView->cameraWorldPos.y)),
+        (float)(storage_double(f->view->cameraWorldPos.z) - storage_double(hzbView->cameraWorldPos.z)) };
+    for (uint32_t t = 0; t < inCount; t++) {
+        const chord_draw_cmd cmd = in[t];
+        object_refs o = get_object(f, cmd.objectId);
+        const chord_GPUGLTFMeshlet* m = &o.datas->meshlets[cmd.meshletId];
+        f3 c = { (m->posMin.x + m->posMax.x) * 0.5f, (m->posMin.y + m->posMax.y) * 0.5f, (m->posMin.z + m->posMax.z) * 0.5f };
+        f3 e = { m->posMax.x - c.x, m->posMax.y - c.y, m->posMax.z - c.z };
+        int visible = 1;
+        if (has_flag(f->switchFlags, CHORD_FLAG_HZB_CULL_BIT)) {
+            float mx[3] = {-10.0f, -10.0f, -10.0f}, mn[3] = {10.0f, 10.0f, 10.0f};
+            chord_float4x4 l2w = bObjectUseLastFrameProject ? o.object->basicData.localToTranslatedWorldLastFrame : o.object->basicData.localToTranslatedWorld;
+            l2w.m[12] += rel[0]; l2w.m[13] += rel[1]; l2w.m[14] += rel[2];       /* [0][3], [1][3], [2][3] (column-major storage) */
+            chord_float4x4 mvp; mat_mul(&hzbView->translatedWorldToClip, &l2w, &mvp);
+            int can = 1;
+            for (int i = 0; i < 8; i++) {
+                float x = fmaf(e.x, kExtentApplyFactor[i][0], c.x);
+                float y = fmaf(e.y, kExtentApplyFactor[i][1], c.y);
+                float z = fmaf(e.z, kExtentApplyFactor[i][2], c.z);
+                f3 uvz = project_pos_to_uvz(x, y, z, &mvp);
+                mn[0] = fminf(mn[0], uvz.x); mn[1] = fminf(mn[1], uvz.y); mn[2] = fminf(mn[2], uvz.z);
+                mx[0] = fmaxf(mx[0], uvz.x); mx[1] = fmaxf(mx[1], uvz.y); mx[2] = fmaxf(mx[2], uvz.z);
+                can = can && (uvz.x < 1.0f && uvz.y < 1.0f && uvz.z < 1.0f) && (uvz.x > 0.0f && uvz.y > 0.0f && uvz.z > 0.0f);
+            }
+            if (can) {
+                const float W = hzbView->renderDimension.x, H = hzbView->renderDimension.y;
+                /* int4(uvRect * dim.xyxy + extentScale * (-.5, -.5, .5, .5)): mad per component, truncation */
+                const float lo = extentScale * -0.5f, hi = extentScale * 0.5f;      /* exact */
+                int32_t rx0 = (int32_t)fmaf(mn[0], W, lo), ry0 = (int32_t)fmaf(mn[1], H, lo);
+                int32_t rx1 = (int32_t)fmaf(mx[0], W, hi), ry1 = (int32_t)fmaf(mx[1], H, hi);
+                if (rx0 < 0) rx0 = 0; if (ry0 < 0) ry0 = 0;
+                float fx1 = fminf(W - 1.0f, (float)rx1), fy1 = fminf(H - 1.0f, (float)ry1);
+                rx1 = (int32_t)fx1; ry1 = (int32_t)fy1;
+                if (rx1 < rx0 || ry1 < ry0) {
+                    visible = 0;
+                } else {
+                    int32_t hx0 = rx0 >> 1, hy0 = ry0 >> 1, hx1 = rx1 >> 1, hy1 = ry1 >> 1;
+                    int mlx = firstbithigh_i(hx1 - hx0), mly = firstbithigh_i(hy1 - hy0);
+                    int mipLevel = mlx > mly ? mlx : mly;
+                    if (mipLevel < 0) mipLevel = 0;
+                    if (((hx1 >> mipLevel) - (hx0 >> mipLevel) >= 2) || ((hy1 >> mipLevel) - (hy0 >> mipLevel) >= 2)) mipLevel += 1;
+                    int32_t cx0 = hx0 >> mipLevel, cy0 = hy0 >> mipLevel, cx1 = hx1 >> mipLevel, cy1 = hy1 >> mipLevel;
+                    float zMin = 10.0f;
+                    const uint32_t pitch = mip0Width >> mipLevel;
+                    const uint16_t* mip = hzbMin + hzbMipOffsets[mipLevel];
+                    for (int x = 0; x < 2; x++)
+                        for (int y = 0; y < 2; y++) {
+                            int32_t sx = cx0 + x; if (sx > cx1) sx = cx1;
+                            int32_t sy = cy0 + y; if (sy > cy1) sy = cy1;
+                            zMin = fminf(zMin, oracle_f16_to_f32(mip[(uint64_t)sy * pitch + (uint32_t)sx]));
+                        }
+                    if (zMin > mx[2]) visible = 0;
+                }
+            }
+        }
+        if (visible) outVisible[nv++] = cmd;
+    }
+    *outVisibleCount = nv;
+}
+
 /* ------------------------------------------------------------------ K7 masked bucket: the specified sampler
  * mesh_raster.hlsl:198-204: sampleColor = baseColorTexture.Sample(baseColorSampler, uv); clip(sampleColor.w * factor - cutoff).
  * Sample() with implicit derivatives is implementation defined on a GPU; pinned here as: trilinear over RGBA8 unorm,
@@ -525,6 +597,7 @@ typedef struct {
     uint32_t width, height;
     chord_rect tile;
     uint64_t* vis64;
+    int depthClamp;             /* CHORD_PASS_DEPTH_CLAMP: no near / far clipping (orthographic views), z clamped to [0, 1] */
 } raster_target;
 
 static inline void vis_atomic_max(uint64_t* p, uint64_t key)
@@ -645,7 +718,7 @@ static int raster_clip_triangle(const raster_target* rt, const float c[3][4], ui
     int needClip = 0;
     float sx[3], sy[3], sz[3];
     for (int i = 0; i < 3; i++)
-        if (!(c[i][2] >= 0.0f && c[i][2] <= c[i][3])) needClip = 1;
+        if (rt->depthClamp ? !(c[i][3] > 0.0f) : !(c[i][2] >= 0.0f && c[i][2] <= c[i][3])) needClip = 1;
     if (!needClip)
         for (int i = 0; i < 3; i++)
             if (!to_screen(rt, c[i], &sx[i], &sy[i], &sz[i])) needClip = 1;
@@ -668,7 +741,7 @@ static int raster_clip_triangle(const raster_target* rt, const float c[3][4], ui
         memcpy(poly[0][i], c[i], 16);
         poly[0][i][4] = masked ? masked->uv[i][0] : 0.0f; poly[0][i][5] = masked ? masked->uv[i][1] : 0.0f;
     }
-    for (int k = 0; k < 6 && n >= 3; k++) {
+    for (int k = rt->depthClamp ? 2 : 0; k < 6 && n >= 3; k++) {       /* depth clamp: the z planes are not clipped against */
         int m = 0;
         for (int i = 0; i < n; i++) {
             const float* a = poly[cur][i];
@@ -710,7 +783,7 @@ static int raster_clip_triangle(const raster_target* rt, const float c[3][4], ui
 void oracle_raster_clip_triangle(uint32_t width, uint32_t height, const chord_rect* tile,
                                  const float clip[12], uint32_t visId, int twoSided, uint64_t* vis64)
 {
-    raster_target rt = { width, height, {0, 0, width, height}, vis64 };
+    raster_target rt = { width, height, {0, 0, width, height}, vis64, 0 };
     if (tile) rt.tile = *tile;
     float c[3][4]; memcpy(c, clip, sizeof(c));
     raster_clip_triangle(&rt, c, visId, twoSided, NULL);
@@ -730,7 +803,7 @@ static inline float det3(const float r0[3], const float r1[3], const float r2[3]
 void oracle_render_mesh(const oracle_frame* f, const chord_draw_cmd* cmds, uint32_t count, uint64_t* vis64,
                         chord_raster_stats* stats)
 {
-    raster_target rt = { f->width, f->height, f->tile, vis64 };
+    raster_target rt = { f->width, f->height, f->tile, vis64, (f->passFlags & CHORD_PASS_DEPTH_CLAMP) != 0 };
     uint64_t nSub = 0, nCull = 0, nClip = 0, nMesh = 0, nKilled = 0;
     const float dimW = f->iview->renderDimension.x, dimH = f->iview->renderDimension.y;
 #ifdef _OPENMP
@@ -742,7 +815,7 @@ void oracle_render_mesh(const oracle_frame* f, const chord_draw_cmd* cmds, uint3
         object_refs o = get_object(f, cmd.objectId);
         /* pipeline filter (pipeline_filter.hlsl:41-130; mesh_raster.cpp:224-253): alphaMode 0/1 only */
         if (o.material->alphaMode > 1u) continue;
-        const int twoSided = o.material->bTwoSided != 0;
+        const int twoSided = o.material->bTwoSided != 0 || (f->passFlags & CHORD_PASS_DEPTH) != 0;   /* mesh_raster.cpp:187-189 */
         masked_attrs mattr; const masked_attrs* masked = NULL;
         if (o.material->alphaMode == 1u) {
             const uint32_t tid = o.material->baseColorId;

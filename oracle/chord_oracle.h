@@ -31,6 +31,7 @@ typedef struct {
     /* material texture table of the masked bucket (chord_textures_upload); may be NULL / 0 = everything builtin white */
     const chord_texture_desc* textures; uint32_t textureCount;
     const chord_sampler_desc* samplers; uint32_t samplerCount;
+    uint32_t passFlags;         /* CHORD_PASS_DEPTH | CHORD_PASS_DEPTH_CLAMP for oracle_render_mesh (renderMeshDepth) */
 } oracle_frame;
 
 /* K1+K2: instance_culling.hlsl:47-208 in canonical (object, group, meshlet) order. returns count. */
@@ -47,6 +48,12 @@ void oracle_hzb_culling(const oracle_frame* f, int firstStage,
                         const chord_draw_cmd* in, uint32_t inCount,
                         chord_draw_cmd* outVisible, uint32_t* outVisibleCount,
                         chord_draw_cmd* outRejected, uint32_t* outRejectedCount);
+
+/* hzbCullingGeneric: hzb_culling_generic.hlsl:37-172.  hzbView = view the HZB was built for. */
+void oracle_hzb_culling_generic(const oracle_frame* f, const chord_InstanceCullingViewInfo* hzbView, float extentScale,
+                                int bObjectUseLastFrameProject,
+                                const uint16_t* hzbMin, const uint64_t* hzbMipOffsets, uint32_t mip0Width,
+                                const chord_draw_cmd* in, uint32_t inCount, chord_draw_cmd* outVisible, uint32_t* outVisibleCount);
 
 /* K4+K6+K6'+K7: mesh_raster.hlsl:51-210 + Vulkan fixed-function rules into a packed 64-bit surface (W*H). */
 void oracle_render_mesh(const oracle_frame* f, const chord_draw_cmd* cmds, uint32_t count, uint64_t* vis64,

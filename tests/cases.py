@@ -62,3 +62,36 @@ def case_masked(w=512, h=384, seed=11):
     view = cam.fill_view(camera)
     return dict(name='masked', scene=scene, view=view, iview=cam.fill_instance_view(view), objects=objects, w=w, h=h,
                 lod0=len(objects), groups=len(objects), camera=camera)
+
+
+def oracle_render_shadow(scene, view, objects, lod0, cfg, light, history=None, valid_depth_range=None, hzb_culling=True, extent_scale=1.5):
+    """chord::renderShadow (mesh_raster.cpp:332-546) on the CPU oracle, same sequencing as chord_b200/renderer.py::renderShadow.
+    ``history`` / result: dict(views, depth=[vis64 per cascade], lists, direction, cfg)."""
+    import oracle
+    direction = np.asarray(light, dtype=np.float32)
+    cache_valid = history is not None and np.array_equal(history['direction'], direction) and history['cfg'] is cfg
+    tick = int(view['basicData']['frameCounter'])
+    views = cam.cascade_views(view, direction, cfg, valid_depth_range, history['views'] if cache_valid else None, cache_valid)
+    dim = cfg.cascadeDim
+    depth = list(history['depth']) if cache_valid else [np.zeros((dim, dim), dtype=np.uint64) for _ in range(cfg.cascadeCount)]
+    lists = [None] * cfg.cascadeCount
+    hzbs = [None] * cfg.cascadeCount
+    prev_hzb, prev_id = None, None
+    for cid in range(cfg.cascadeCount - 1, -1, -1):
+        if cam.is_cascade_cache_valid(cache_valid, cfg.realtimeCascadeCount, cfg.cascadeCount, tick, cid):
+            continue
+        fr = oracle.Frame(scene, view, views[cid], objects, dim, dim)
+        post = fr.instance_culling(lod0)
+        if prev_hzb is None:
+            if cache_valid and hzb_culling:
+                cached = fr.build_hzb(depth[cid], True, False, False)
+                post = fr.hzb_culling_generic(cached, views[cid], extent_scale, False, post)
+        elif hzb_culling:
+            post = fr.hzb_culling_generic(prev_hzb, views[prev_id], extent_scale, False, post)
+        depth[cid] = np.zeros((dim, dim), dtype=np.uint64)
+        fr.render_mesh_depth(post, depth[cid])
+        lists[cid] = post
+        if cid != 0:
+            prev_hzb, prev_id = fr.build_hzb(depth[cid], True, False, False), cid
+            hzbs[cid] = prev_hzb
+    return dict(views=views, depth=depth, lists=lists, hzbs=hzbs, direction=direction, cfg=cfg)

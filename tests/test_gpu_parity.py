@@ -569,3 +569,63 @@ def test_graph_replay_matches_eager(gpu_ctx):
             fr.vis64()
     frame_calls()
     _assert_vis_equal(fr.vis64(), ref['vis'], 'eager after a failed capture')
+
+
+def _depth_bits(vis64):
+    return (vis64 >> np.uint64(32)).astype(np.uint32)
+
+
+def test_cascade_shadow_depth(gpu_ctx):
+    """renderShadow (mesh_raster.cpp:332-546) — cascade views -> instance cull with the orthographic view ->
+    hzbCullingGeneric against the previous cascade (or the cached depth) -> depth-only raster (two-sided, depth clamp)
+    -> HZB.  Per cascade: lists identical, D32 depth bit-exact (and the packed ids), HZB bit-exact; three frames so
+    that the cascade cache (round-robin far cascades, history HZB path) is exercised; plus the occluding patch stream."""
+    from cases import case_stream, city_frames, oracle_render_shadow
+    from chord_b200 import camera as cam_
+    light = (0.3, -0.8, 0.2)
+    scene, info, frames = city_frames(frames=3)
+    gpu_ctx.upload_scene(scene)
+    cfg = cam_.CascadeShadowMapConfig(cascadeCount=4, realtimeCascadeCount=2, cascadeDim=512, cascadeEndDistance=80.0, farCascadeEndDistance=400.0)
+    pool = renderer._Pool(gpu_ctx)
+    hist_g, hist_o = None, None
+    lod0, groups = info['lod0MeshletCount'], info['meshletGroupCount']
+    for fi, f in enumerate(frames):
+        g = renderer.renderShadow(gpu_ctx, pool, f['view'], f['objects'], lod0, groups, hist_g, cfg, light)
+        o = oracle_render_shadow(scene, f['view'], f['objects'], lod0, cfg, light, hist_o)
+        for cid in range(cfg.cascadeCount):
+            assert (g.lists[cid] is None) == (o['lists'][cid] is None), (fi, cid)
+            if g.lists[cid] is not None:
+                _assert_lists_equal(g.lists[cid].readback(), o['lists'][cid], f'frame {fi} cascade {cid} list')
+            _assert_vis_equal(g.depths[cid].vis64(), o['depth'][cid], f'frame {fi} cascade {cid} depth')
+            assert np.array_equal(g.depths[cid].depth32().view(np.uint32), _depth_bits(o['depth'][cid]))
+        hist_g, hist_o = g, o
+    # a valid SDSM range (buildHZB's validRange of the main view) moves the realtime cascades only
+    vr = np.array([0.00002, 0.0005], dtype=np.float32).view(np.uint32)
+    g = renderer.renderShadow(gpu_ctx, pool, frames[0]['view'], frames[0]['objects'], lod0, groups, None, cfg, light, valid_depth_range=vr)
+    o = oracle_render_shadow(scene, frames[0]['view'], frames[0]['objects'], lod0, cfg, light, None, valid_depth_range=vr)
+    for cid in range(cfg.cascadeCount):
+        _assert_vis_equal(g.depths[cid].vis64(), o['depth'][cid], f'SDSM cascade {cid} depth')
+    # occlusion along the light: hzbCullingGeneric really rejects, and the HZB it reads is the previous cascade's
+    c = case_stream(3000, 256, 256, 100.0)
+    gpu_ctx.upload_scene(c['scene'])
+    cfg2 = cam_.CascadeShadowMapConfig(cascadeCount=4, realtimeCascadeCount=2, cascadeDim=256, cascadeEndDistance=30.0, farCascadeEndDistance=120.0)
+    sl = (0.05, -0.05, -1.0)
+    g = renderer.renderShadow(gpu_ctx, pool, c['view'], c['objects'], c['lod0'], c['groups'], None, cfg2, sl)
+    o = oracle_render_shadow(c['scene'], c['view'], c['objects'], c['lod0'], cfg2, sl, None)
+    rejected = 0
+    for cid in range(4):
+        _assert_lists_equal(g.lists[cid].readback(), o['lists'][cid], f'stream cascade {cid} list')
+        _assert_vis_equal(g.depths[cid].vis64(), o['depth'][cid], f'stream cascade {cid} depth')
+        full = oracle.Frame(c['scene'], c['view'], o['views'][cid], c['objects'], 256, 256).instance_culling(c['lod0'])
+        rejected += len(full) - len(o['lists'][cid])
+    assert rejected > 300
+    # the depth-clamp pass is refused for a perspective instance view
+    fr = runtime.Frame(gpu_ctx, 256, 256)
+    fr.begin(c['view'], c['iview'], c['objects'], c['lod0'], c['groups'])
+    lst = runtime.CmdList(gpu_ctx, c['lod0'])
+    lst.upload(c['cmds'])
+    with pytest.raises(runtime.ChordError):
+        fr.render_mesh_depth(lst, abi.PASS_DEPTH | abi.PASS_DEPTH_CLAMP)
+    fr.render_mesh_depth(lst, abi.PASS_DEPTH)
+    ovis, _ = oracle.Frame(c['scene'], c['view'], c['iview'], c['objects'], 256, 256).render_mesh_depth(c['cmds'], pass_flags=abi.PASS_DEPTH)
+    _assert_vis_equal(fr.vis64(), ovis, 'two-sided depth pass through the perspective view')
