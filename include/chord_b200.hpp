@@ -33,6 +33,9 @@ public:
     Context& operator=(const Context&) = delete;
 
     void uploadScene(const chord_scene_desc& desc) { check(chord_scene_upload(m_ctx, &desc), "chord_scene_upload"); }
+    // material textures of the masked bucket (bindless Texture2D / SamplerState ids -> table indices)
+    void uploadTextures(const chord_texture_desc* tex, uint32_t nTex, const chord_sampler_desc* smp, uint32_t nSmp)
+    { check(chord_textures_upload(m_ctx, tex, nTex, smp, nSmp), "chord_textures_upload"); }
     void setSwitchFlags(uint32_t f) { check(chord_ctx_set_switch_flags(m_ctx, f), "chord_ctx_set_switch_flags"); }
     void sync() { check(chord_ctx_sync(m_ctx), "chord_ctx_sync"); }
     void* stream() const { return chord_ctx_stream(m_ctx); }
@@ -108,6 +111,17 @@ public:
         return h;
     }
     void renderMesh(const CmdListRef& list) { check(chord_render_mesh(m_frame, list.get()), "chord_render_mesh"); }
+    // renderMeshDepth (PASS_TYPE_DEPTH: two-sided, optional depth clamp) into this frame used as a cascade depth target
+    void renderMeshDepth(const CmdListRef& list, uint32_t passFlags = CHORD_PASS_DEPTH | CHORD_PASS_DEPTH_CLAMP)
+    { check(chord_render_mesh_depth(m_frame, list.get(), passFlags), "chord_render_mesh_depth"); }
+    // detail::hzbCullingGeneric against the HZB of another view (previous cascade / cached cascade)
+    CmdListRef hzbCullingGeneric(const HzbRef& hzb, const chord_InstanceCullingViewInfo& hzbView, float extentScale,
+                                 bool bObjectUseLastFrameProject, const CmdListRef& in)
+    {
+        auto out = m_ctx.createCmdList(chord_cmdlist_capacity(in.get()));
+        check(chord_hzb_culling_generic(m_frame, hzb.get(), &hzbView, extentScale, bObjectUseLastFrameProject ? 1 : 0, in.get(), out.get()), "chord_hzb_culling_generic");
+        return out;
+    }
     void visibilityMark(const CmdListRef& post) { check(chord_visibility_mark(m_frame, post.get()), "chord_visibility_mark"); }
     void lighting(const CmdListRef& post) { check(chord_lighting(m_frame, post.get()), "chord_lighting"); }
 
@@ -116,6 +130,22 @@ private:
     chord_frame* m_frame = nullptr;
     uint32_t m_w, m_h, m_lod0 = 0;
     CmdListRef m_keep[3];
+};
+
+// Record once / replay many (the reference records a command buffer per frame): construct, issue the frame's calls,
+// call end(); launch() replays them with one CUDA-graph launch.
+class Graph {
+public:
+    explicit Graph(const Context& ctx) : m_ctx(ctx) { check(chord_graph_begin_capture(ctx.handle()), "chord_graph_begin_capture"); }
+    void end() { check(chord_graph_end_capture(m_ctx.handle(), &m_graph), "chord_graph_end_capture"); }
+    void launch() { check(chord_graph_launch(m_graph), "chord_graph_launch"); }
+    uint32_t kernelNodes() const { return chord_graph_kernel_nodes(m_graph); }
+    ~Graph() { chord_graph_destroy(m_graph); }
+    Graph(const Graph&) = delete;
+    Graph& operator=(const Graph&) = delete;
+private:
+    const Context& m_ctx;
+    chord_graph* m_graph = nullptr;
 };
 
 inline std::unique_ptr<Frame> Context::createFrame(uint32_t w, uint32_t h) const { return std::make_unique<Frame>(*this, w, h); }
