@@ -286,9 +286,23 @@ def main():
     n_gpus = args.gpus
     dist = None
     if world > 1:
+        # keep stdout to the one JSON line: NCCL prints its version banner there when NCCL_DEBUG is VERSION
+        if os.environ.get('NCCL_DEBUG', '').upper() in ('', 'VERSION'):
+            os.environ['NCCL_DEBUG'] = 'WARN'
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
-        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+        # anything NCCL / c10d prints while the communicator comes up goes to stderr, not into the JSON stream
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
     assert n_gpus == world, f'--gpus {n_gpus} but WORLD_SIZE {world} (launch with torch.distributed.run)'
 
     ctx = runtime.Context(local_rank)
