@@ -246,7 +246,6 @@ int launch_instance_culling(chord_frame* f, chord_cmdlist* out);
 int launch_instance_culling_bvh(chord_frame* f, chord_cmdlist* out);
 int launch_hzb_culling(chord_frame* f, const chord_hzb* hzb, int firstStage, chord_cmdlist* in, chord_cmdlist* outVis, chord_cmdlist* outRej);
 int launch_render_mesh(chord_frame* f, chord_cmdlist* list);
-void set_early_z_mode(int m);
 int launch_hzb_culling_generic(chord_frame* f, const chord_hzb* hzb, const chord_InstanceCullingViewInfo* hzbView, float extentScale,
                                int useLastFrame, chord_cmdlist* in, chord_cmdlist* outVis);
 int launch_build_hzb(chord_frame* f, int bMin, int bMax, int bRange, chord_hzb* dst);

@@ -98,7 +98,6 @@ int chord_ctx_create(int device, chord_ctx** out)
     c->smCount = prop.multiProcessorCount;
     CHORD_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CHORD_CUDA(cudaMalloc(&c->scanTicket, sizeof(uint32_t)));
-    if (const char* ez = getenv("CHORD_EARLYZ")) set_early_z_mode(atoi(ez));
     *out = c;
     return CHORD_OK;
 }
