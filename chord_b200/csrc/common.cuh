@@ -160,6 +160,7 @@ void set_error(const char* fmt, ...);
 struct chord_ctx {
     int device;
     cudaStream_t stream;
+    cudaStream_t uploadStream;          // created by the first chord_cmdlist_upload_async
     uint32_t switchFlags;
     uint64_t launches;
     int smCount;
@@ -192,6 +193,9 @@ struct chord_cmdlist {
     uint32_t* pinnedCount;      // host-pinned ring for async uploads
     uint32_t pinnedIdx;
     chord_draw_cmd* cmds;       // device
+    // overlapped uploads (chord_cmdlist_upload_async runs on the context's upload stream): `uploaded` gates the next
+    // consumer on the main stream, `lastUse` (recorded after every consumer) gates the next upload (write after read)
+    cudaEvent_t uploaded, lastUse; bool uploadPending, asyncUser;
 };
 
 struct chord_hzb {

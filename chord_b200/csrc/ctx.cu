@@ -113,6 +113,7 @@ void chord_ctx_destroy(chord_ctx* ctx)
     if (ctx->lutTransmittance) cudaFree(ctx->lutTransmittance);
     if (ctx->lutIrradiance) cudaFree(ctx->lutIrradiance);
     cudaFree(ctx->dTextures); cudaFree(ctx->dSamplers); cudaFree(ctx->dTexels);
+    if (ctx->uploadStream) { cudaStreamSynchronize(ctx->uploadStream); cudaStreamDestroy(ctx->uploadStream); }
     cudaStreamDestroy(ctx->stream);
     free(ctx);
 }
@@ -121,6 +122,7 @@ void* chord_ctx_stream(chord_ctx* ctx) { return ctx ? (void*)ctx->stream : nullp
 int chord_ctx_sync(chord_ctx* ctx)
 {
     CHORD_REQUIRE(ctx, "ctx");
+    if (ctx->uploadStream) CHORD_CUDA(cudaStreamSynchronize(ctx->uploadStream));
     CHORD_CUDA(cudaStreamSynchronize(ctx->stream));
     return CHORD_OK;
 }
@@ -182,12 +184,31 @@ void chord_cmdlist_destroy(chord_cmdlist* l)
 {
     if (!l) return;
     cudaStreamSynchronize(l->ctx->stream);
+    if (l->ctx->uploadStream) cudaStreamSynchronize(l->ctx->uploadStream);
+    if (l->uploaded) cudaEventDestroy(l->uploaded);
+    if (l->lastUse) cudaEventDestroy(l->lastUse);
     cudaFree(l->count); cudaFree(l->cmds); if (l->pinnedCount) cudaFreeHost(l->pinnedCount); free(l);
 }
+// a list that has an overlapped upload in flight: the main stream waits for it before the first consumer
+static int list_acquire(chord_cmdlist* l)
+{
+    if (l && l->uploadPending) { CHORD_CUDA(cudaStreamWaitEvent(l->ctx->stream, l->uploaded, 0)); l->uploadPending = false; }
+    return CHORD_OK;
+}
+// after a consumer: the next overlapped upload into this list must not overtake it
+static int list_release(chord_cmdlist* l)
+{
+    if (l && l->asyncUser && !l->ctx->capturing) CHORD_CUDA(cudaEventRecord(l->lastUse, l->ctx->stream));
+    return CHORD_OK;
+}
+#define CHORD_ACQUIRE(l) do { int rc__ = list_acquire(l); if (rc__) return rc__; } while (0)
+#define CHORD_RELEASE(l) do { int rc__ = list_release(l); if (rc__) return rc__; } while (0)
+
 int chord_cmdlist_upload(chord_cmdlist* l, const chord_draw_cmd* host, uint32_t count)
 {
     CHORD_REQUIRE(l && (host || count == 0), "null");
     if (count > l->capacity) { set_error("cmdlist upload: %u > capacity %u", count, l->capacity); return CHORD_ERR_CAPACITY; }
+    CHORD_ACQUIRE(l);
     CHORD_CUDA(cudaMemcpyAsync(l->count, &count, 4, cudaMemcpyHostToDevice, l->ctx->stream));
     if (count) CHORD_CUDA(cudaMemcpyAsync(l->cmds, host, sizeof(chord_draw_cmd) * (size_t)count, cudaMemcpyHostToDevice, l->ctx->stream));
     CHORD_CUDA(cudaStreamSynchronize(l->ctx->stream));
@@ -202,14 +223,27 @@ int chord_cmdlist_upload_async(chord_cmdlist* l, const chord_draw_cmd* host, uin
     if (!l->pinnedCount) CHORD_CUDA(cudaMallocHost(&l->pinnedCount, 64 * sizeof(uint32_t)));
     uint32_t* slot = &l->pinnedCount[l->pinnedIdx++ & 63u];                 // ring: up to 64 uploads in flight
     *slot = count;
-    CHORD_CUDA(cudaMemcpyAsync(l->count, slot, 4, cudaMemcpyHostToDevice, l->ctx->stream));
-    if (count) CHORD_CUDA(cudaMemcpyAsync(l->cmds, host, sizeof(chord_draw_cmd) * (size_t)count, cudaMemcpyHostToDevice, l->ctx->stream));
+    chord_ctx* ctx = l->ctx;
+    cudaStream_t st = ctx->stream;
+    if (!ctx->capturing) {
+        // the copy runs on the context's upload stream so that it overlaps whatever the main stream is executing (the
+        // raster of the previous list); events order it after the last consumer of this list and before the next one
+        if (!ctx->uploadStream) CHORD_CUDA(cudaStreamCreateWithFlags(&ctx->uploadStream, cudaStreamNonBlocking));
+        if (!l->uploaded) { CHORD_CUDA(cudaEventCreateWithFlags(&l->uploaded, cudaEventDisableTiming)); CHORD_CUDA(cudaEventCreateWithFlags(&l->lastUse, cudaEventDisableTiming)); }
+        if (!l->asyncUser) { l->asyncUser = true; CHORD_CUDA(cudaEventRecord(l->lastUse, ctx->stream)); }   // everything enqueued so far may touch the list
+        st = ctx->uploadStream;
+        CHORD_CUDA(cudaStreamWaitEvent(st, l->lastUse, 0));
+    }
+    CHORD_CUDA(cudaMemcpyAsync(l->count, slot, 4, cudaMemcpyHostToDevice, st));
+    if (count) CHORD_CUDA(cudaMemcpyAsync(l->cmds, host, sizeof(chord_draw_cmd) * (size_t)count, cudaMemcpyHostToDevice, st));
+    if (!ctx->capturing) { CHORD_CUDA(cudaEventRecord(l->uploaded, st)); l->uploadPending = true; }
     return CHORD_OK;
 }
 
 int chord_cmdlist_readback(chord_cmdlist* l, chord_draw_cmd* host, uint32_t hostCapacity, uint32_t* outCount)
 {
     CHORD_REQUIRE(l && outCount, "null");
+    CHORD_ACQUIRE(l);
     uint32_t n = 0;
     CHORD_CUDA(cudaMemcpyAsync(&n, l->count, 4, cudaMemcpyDeviceToHost, l->ctx->stream));
     CHORD_CUDA(cudaStreamSynchronize(l->ctx->stream));
@@ -438,13 +472,19 @@ int chord_frame_begin(chord_frame* f, const chord_PerframeCameraView* view, cons
 int chord_instance_culling(chord_frame* f, chord_cmdlist* out)
 {
     CHORD_REQUIRE(f && out && f->begun, "frame not begun");
-    return launch_instance_culling(f, out);
+    CHORD_ACQUIRE(out);
+    const int rc = launch_instance_culling(f, out);
+    CHORD_RELEASE(out);
+    return rc;
 }
 
 int chord_instance_culling_bvh(chord_frame* f, chord_cmdlist* out)
 {
     CHORD_REQUIRE(f && out && f->begun, "frame not begun");
-    return launch_instance_culling_bvh(f, out);
+    CHORD_ACQUIRE(out);
+    const int rc = launch_instance_culling_bvh(f, out);
+    CHORD_RELEASE(out);
+    return rc;
 }
 
 int chord_readback_bvh_candidates(chord_frame* f, uint32_t* hostBits, uint32_t words, uint32_t* outCtrl5)
@@ -463,14 +503,20 @@ int chord_hzb_culling(chord_frame* f, const chord_hzb* hzb, int firstStage, chor
     CHORD_REQUIRE(!firstStage || outRejected, "phase 0 needs a rejected list");
     CHORD_REQUIRE(hzb->depthW == f->width && hzb->depthH == f->height, "hzb built for another render dimension");
     CHORD_REQUIRE(outVisible->capacity >= in->capacity && (!outRejected || outRejected->capacity >= in->capacity), "output list capacity");
-    return launch_hzb_culling(f, hzb, firstStage, in, outVisible, firstStage ? outRejected : nullptr);
+    CHORD_ACQUIRE(in); CHORD_ACQUIRE(outVisible); CHORD_ACQUIRE(outRejected);
+    const int rc = launch_hzb_culling(f, hzb, firstStage, in, outVisible, firstStage ? outRejected : nullptr);
+    CHORD_RELEASE(in); CHORD_RELEASE(outVisible); CHORD_RELEASE(outRejected);
+    return rc;
 }
 
 int chord_render_mesh(chord_frame* f, chord_cmdlist* list)
 {
     CHORD_REQUIRE(f && list && f->begun, "null / frame not begun");
     f->passFlags = 0u;
-    return launch_render_mesh(f, list);
+    CHORD_ACQUIRE(list);
+    const int rc = launch_render_mesh(f, list);
+    CHORD_RELEASE(list);
+    return rc;
 }
 
 int chord_render_mesh_depth(chord_frame* f, chord_cmdlist* list, uint32_t passFlags)
@@ -480,8 +526,10 @@ int chord_render_mesh_depth(chord_frame* f, chord_cmdlist* list, uint32_t passFl
     // depth clamp drops the near / far clip planes: only defined here for orthographic instance views (w == 1)
     CHORD_REQUIRE(!(passFlags & CHORD_PASS_DEPTH_CLAMP) || f->hIViewOrtho, "CHORD_PASS_DEPTH_CLAMP needs an orthographic instance view");
     f->passFlags = passFlags;
+    CHORD_ACQUIRE(list);
     const int rc = launch_render_mesh(f, list);
     f->passFlags = 0u;
+    CHORD_RELEASE(list);
     return rc;
 }
 
@@ -491,7 +539,10 @@ int chord_hzb_culling_generic(chord_frame* f, const chord_hzb* hzb, const chord_
     CHORD_REQUIRE(f && hzb && hzbView && in && outVisible && f->begun, "null / frame not begun");
     CHORD_REQUIRE(hzb->depthW == (uint32_t)hzbView->renderDimension.x && hzb->depthH == (uint32_t)hzbView->renderDimension.y, "hzb was not built for hzbView's render dimension");
     CHORD_REQUIRE(outVisible->capacity >= in->capacity, "output list capacity");
-    return launch_hzb_culling_generic(f, hzb, hzbView, extentScale, bObjectUseLastFrameProject, in, outVisible);
+    CHORD_ACQUIRE(in); CHORD_ACQUIRE(outVisible);
+    const int rc = launch_hzb_culling_generic(f, hzb, hzbView, extentScale, bObjectUseLastFrameProject, in, outVisible);
+    CHORD_RELEASE(in); CHORD_RELEASE(outVisible);
+    return rc;
 }
 
 int chord_visibility_stage0(chord_frame* f, const chord_hzb* lastFrameHzb, chord_cmdlist* in, chord_cmdlist* scratchVisible,
@@ -505,9 +556,12 @@ int chord_visibility_stage0(chord_frame* f, const chord_hzb* lastFrameHzb, chord
         *needStage1 = 1;
         int rc = chord_hzb_culling(f, lastFrameHzb, 1, in, scratchVisible, outRejected);
         if (rc) return rc;
-        return launch_render_mesh(f, scratchVisible);
+        f->passFlags = 0u;
+        rc = launch_render_mesh(f, scratchVisible);
+        CHORD_RELEASE(scratchVisible);
+        return rc;
     }
-    return launch_render_mesh(f, in);
+    return chord_render_mesh(f, in);
 }
 
 int chord_visibility_stage1(chord_frame* f, const chord_hzb* thisFrameHzb, chord_cmdlist* rejected, chord_cmdlist* scratchVisible)
@@ -515,7 +569,10 @@ int chord_visibility_stage1(chord_frame* f, const chord_hzb* thisFrameHzb, chord
     CHORD_REQUIRE(f && thisFrameHzb && rejected && scratchVisible && f->begun, "null / frame not begun");
     int rc = chord_hzb_culling(f, thisFrameHzb, 0, rejected, scratchVisible, nullptr);
     if (rc) return rc;
-    return launch_render_mesh(f, scratchVisible);
+    f->passFlags = 0u;
+    rc = launch_render_mesh(f, scratchVisible);
+    CHORD_RELEASE(scratchVisible);
+    return rc;
 }
 
 int chord_build_hzb(chord_frame* f, int bMin, int bMax, int bValidRange, chord_hzb* dst)
@@ -532,7 +589,10 @@ int chord_build_hzb(chord_frame* f, int bMin, int bMax, int bValidRange, chord_h
 int chord_visibility_mark(chord_frame* f, chord_cmdlist* post)
 {
     CHORD_REQUIRE(f && post && f->begun, "null / frame not begun");
-    return launch_visibility_mark(f, post);
+    CHORD_ACQUIRE(post);
+    const int rc = launch_visibility_mark(f, post);
+    CHORD_RELEASE(post);
+    return rc;
 }
 
 int chord_atmosphere_luts_upload(chord_ctx* ctx, const chord_atmosphere_luts* luts)
@@ -665,7 +725,10 @@ int chord_lighting(chord_frame* f, chord_cmdlist* post)
 {
     CHORD_REQUIRE(f && post && f->begun, "null / frame not begun");
     CHORD_REQUIRE(f->ctx->lutTransmittance && f->ctx->lutIrradiance, "atmosphere LUTs not uploaded");
-    return launch_lighting(f, post);
+    CHORD_ACQUIRE(post);
+    const int rc = launch_lighting(f, post);
+    CHORD_RELEASE(post);
+    return rc;
 }
 
 // ---------------------------------------------------------------------------------------------- read-backs
@@ -740,6 +803,7 @@ int chord_readback_depth32(chord_frame* f, float* host) { CHORD_REQUIRE(f && hos
 int chord_readback_decoded(chord_frame* f, chord_cmdlist* post, uint32_t* hostTriples)
 {
     CHORD_REQUIRE(f && post && hostTriples, "null");
+    CHORD_ACQUIRE(post);
     const size_t n = (size_t)f->width * f->height;
     uint32_t* d = nullptr;
     CHORD_CUDA(cudaMallocAsync(&d, n * 12, f->ctx->stream));

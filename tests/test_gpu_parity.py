@@ -629,3 +629,37 @@ def test_cascade_shadow_depth(gpu_ctx):
     fr.render_mesh_depth(lst, abi.PASS_DEPTH)
     ovis, _ = oracle.Frame(c['scene'], c['view'], c['iview'], c['objects'], 256, 256).render_mesh_depth(c['cmds'], pass_flags=abi.PASS_DEPTH)
     _assert_vis_equal(fr.vis64(), ovis, 'two-sided depth pass through the perspective view')
+
+
+def test_overlapped_list_uploads(gpu_ctx):
+    """chord_cmdlist_upload_async runs on the context's upload stream: events keep it behind the last consumer of the list
+    and ahead of the next one.  Alternate two lists with different contents; the next upload is always in flight while the current list is rasterised."""
+    import ctypes as C
+    import torch
+    from cases import case_stream
+    c = case_stream(3000, 640, 360, 1.0)
+    gpu_ctx.upload_scene(c['scene'])
+    n = c['lod0']
+    L = runtime.lib()
+    fr = runtime.Frame(gpu_ctx, 640, 360)
+    lists = [runtime.CmdList(gpu_ctx, n), runtime.CmdList(gpu_ctx, n)]
+    subsets = [c['cmds'][k::4].copy() for k in range(4)] + [c['cmds'][:0].copy()]      # incl. an empty list
+    pins = []
+    for s in subsets:
+        t = torch.empty(max(len(s), 1) * 12, dtype=torch.uint8).pin_memory()
+        t.numpy()[:len(s) * 12] = np.frombuffer(s.tobytes(), dtype=np.uint8)
+        pins.append(t)
+    ofr = oracle.Frame(c['scene'], c['view'], c['iview'], c['objects'], 640, 360)
+    want = [ofr.render_mesh(s)[0] for s in subsets]
+    order = [0, 1, 2, 3, 4, 2, 0, 3, 1, 4, 0]
+    imgs = [np.empty((360, 640), dtype=np.uint64) for _ in order]
+    L.chord_cmdlist_upload_async(lists[0].h, C.c_void_p(pins[order[0]].data_ptr()), C.c_uint32(len(subsets[order[0]])))
+    for i, k in enumerate(order):
+        if i + 1 < len(order):
+            nk = order[i + 1]
+            L.chord_cmdlist_upload_async(lists[(i + 1) & 1].h, C.c_void_p(pins[nk].data_ptr()), C.c_uint32(len(subsets[nk])))
+        fr.begin(c['view'], c['iview'], c['objects'], n, c['groups'])
+        fr.render_mesh(lists[i & 1])
+        fr.readback_vis64_into(imgs[i].ctypes.data)
+    for i, k in enumerate(order):
+        _assert_vis_equal(imgs[i], want[k], f'step {i} (subset {k})')
