@@ -237,7 +237,7 @@ struct chord_frame {
     chord_rect gbufTile; bool gbufValid; int gbufPackedMode;     // rect the resolve planes were last fully written for
     void* resolveRecs; uint32_t resolveCapacity;
     // pipelined read-back of the R32_UINT image: two staging slots, a copy stream, events
-    uint32_t* splitVis[2]; cudaStream_t copyStream; cudaEvent_t splitDone[2], copyDone[2]; int splitIdx;
+    uint32_t* splitVis[2]; cudaStream_t copyStream; bool copyStreamShared; cudaEvent_t splitDone[2], copyDone[2]; int splitIdx;
     chord_PerframeCameraView hView;   // host copy
     bool begun;
 };
