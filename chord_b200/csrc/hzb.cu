@@ -1,7 +1,9 @@
 // hzb.cu — hierarchical-Z build (K8: hzb.hlsl:127-389, hzb_one.hlsl; host hzb.cpp:38-227) for sm_100a.
 //
-// Same single-pass shape as the reference: a 256-thread block reduces a 64x64 depth region to mips 0..5 through
-// shared memory, a device counter elects the last block which finishes mips 6.. from mip 5.  Depth comes from the
+// A 256-thread block reduces a 64x64 depth region to mips 0..5 through shared memory (10 KB, 8 blocks / SM); mips 6.. are
+// finished from the stored mip 5 by a one-block kernel launched right behind (the reference elects the last workgroup
+// with a device counter instead, hzb.hlsl:289-300: same values, but the election would make every block carry the top
+// levels' 40 KB of shared memory).  Depth comes from the
 // high word of the packed 64-bit visibility texels.  Storage is R16F: min is stored round-toward-zero (conservative
 // for reversed-Z, hzb.hlsl:69), max is stored RTZ for mips 0-4 and as half_bits(RTZ(v)) + 1 at mip 5 (hzb.hlsl:70),
 // with mips 6.. derived from the stored mip 5.  fp32->fp16 RTZ is monotonic, so reducing stored fp16 values equals
@@ -20,7 +22,6 @@ struct HzbBuildParams {
     uint32_t* counter;
     uint32_t numBlocks;
     uint32_t blockX0, blockY0;               // first 64x64 block of the dispatched region (tile-restricted builds)
-    int finishTop;                           // run mips 6.. in the last block
 };
 
 __device__ __forceinline__ __half to_half_rtz(float v) { return __float2half_rz(v); }
@@ -62,24 +63,37 @@ __device__ void hzb_top_levels(const HzbBuildParams& p, float* __restrict__ sMin
 
 __global__ void __launch_bounds__(256) k_hzb_build(HzbBuildParams p)
 {
-    __shared__ float sMinP[4096], sMinQ[1024], sMaxP[4096], sMaxQ[1024];
-    __shared__ uint32_t sTicket;
+    __shared__ float sMinP[1024], sMinQ[256], sMaxP[1024], sMaxQ[256];
     const uint32_t bx = p.blockX0 + blockIdx.x, by = p.blockY0 + blockIdx.y;
     const uint32_t tid = threadIdx.x;
     const bool doMin = p.minChain != nullptr, doMax = p.maxChain != nullptr;
+    const bool evenWidth = (p.width & 1u) == 0u;
 
     // ---- mip 0: 32x32 texels of this block, 4 per thread (hzb.hlsl:134-173)
     float vMin = 10.0f, vMax = -10.0f;      // valid-range accumulators
     for (uint32_t k = 0; k < 4; k++) {
         const uint32_t l = tid + k * 256, lx = l & 31u, ly = l >> 5;
         const uint32_t x = bx * 32 + lx, y = by * 32 + ly;
-        float mn = 0.0f, mx = 0.0f;
+        float d[4];
+        const uint32_t sy0 = min(2 * y, p.height - 1), sy1 = min(2 * y + 1, p.height - 1);
+        if (evenWidth && 2 * x + 1 < p.width) {
+            // both pixels of a row in one 16-byte load (the row start is 16-byte aligned when the width is even)
+            const ulonglong2 r0 = *reinterpret_cast<const ulonglong2*>(p.vis64 + (size_t)sy0 * p.width + 2 * x);
+            const ulonglong2 r1 = *reinterpret_cast<const ulonglong2*>(p.vis64 + (size_t)sy1 * p.width + 2 * x);
+            d[0] = __uint_as_float((uint32_t)(r0.x >> 32)); d[1] = __uint_as_float((uint32_t)(r1.x >> 32));
+            d[2] = __uint_as_float((uint32_t)(r0.y >> 32)); d[3] = __uint_as_float((uint32_t)(r1.y >> 32));
+        } else {
+#pragma unroll
+            for (int s = 0; s < 4; s++) {
+                const uint32_t sx = min(2 * x + (uint32_t)(s >> 1), p.width - 1), sy = (s & 1) ? sy1 : sy0;
+                d[s] = __uint_as_float((uint32_t)(p.vis64[(size_t)sy * p.width + sx] >> 32));
+            }
+        }
+        float mn = d[0], mx = d[0];
 #pragma unroll
         for (int s = 0; s < 4; s++) {
-            const uint32_t sx = min(2 * x + (uint32_t)(s >> 1), p.width - 1), sy = min(2 * y + (uint32_t)(s & 1), p.height - 1);
-            const float d = __uint_as_float((uint32_t)(p.vis64[(size_t)sy * p.width + sx] >> 32));
-            if (s == 0) { mn = d; mx = d; } else { mn = fminf(mn, d); mx = fmaxf(mx, d); }
-            if (d > 0.0f) { vMax = fmaxf(vMax, d); vMin = fminf(vMin, d); }
+            if (s) { mn = fminf(mn, d[s]); mx = fmaxf(mx, d[s]); }
+            if (d[s] > 0.0f) { vMax = fmaxf(vMax, d[s]); vMin = fminf(vMin, d[s]); }
         }
         sMinP[l] = mn; sMaxP[l] = mx;
         if (x < p.mip0W && y < p.mip0H) {
@@ -122,15 +136,6 @@ __global__ void __launch_bounds__(256) k_hzb_build(HzbBuildParams p)
         float* t = srcMin; srcMin = dstMin; dstMin = t; t = srcMax; srcMax = dstMax; dstMax = t;
         w = nw;
     }
-    if (!p.finishTop || p.mipCount <= 6) return;
-
-    // ---- elect the last block (hzb.hlsl:289-300)
-    __threadfence();
-    if (tid == 0) sTicket = atomicAdd(p.counter, 1u);
-    __syncthreads();
-    if (sTicket != p.numBlocks - 1) return;
-    __threadfence();
-    hzb_top_levels(p, sMinP, sMinQ, sMaxP, sMaxQ);
 }
 
 __global__ void __launch_bounds__(256) k_hzb_top(HzbBuildParams p)
@@ -148,7 +153,7 @@ static HzbBuildParams make_params(chord_frame* fr, int bMin, int bMax, int bRang
     p.mip0W = dst->mip0W; p.mip0H = dst->mip0H; p.mipCount = dst->mipCount;
     p.validRange = bRange ? dst->validRange : nullptr;
     p.counter = dst->counter;
-    p.blockX0 = p.blockY0 = 0; p.finishTop = 1; p.numBlocks = 0;
+    p.blockX0 = p.blockY0 = 0; p.numBlocks = 0;
     return p;
 }
 
@@ -181,13 +186,13 @@ int launch_build_hzb(chord_frame* fr, int bMin, int bMax, int bRange, chord_hzb*
         if (bMax) CHORD_CUDA(cudaMemsetAsync(dst->maxChain, 0, sizeof(__half) * dst->totalTexels, ctx->stream));
     }
     p.numBlocks = grid.x * grid.y;
-    CHORD_CUDA(cudaMemsetAsync(dst->counter, 0, 4, ctx->stream));
     if (bRange) {
-        const uint32_t init[2] = { ~0u, 0u };                               // hzb.cpp:105-106
-        CHORD_CUDA(cudaMemcpyAsync(dst->validRange, init, 8, cudaMemcpyHostToDevice, ctx->stream));
+        static const uint32_t kInit[2] = { ~0u, 0u };                       // hzb.cpp:105-106 (static: a captured graph re-reads it)
+        CHORD_CUDA(cudaMemcpyAsync(dst->validRange, kInit, 8, cudaMemcpyHostToDevice, ctx->stream));
     }
     k_hzb_build<<<grid, 256, 0, ctx->stream>>>(p);
     ctx->launches++;
+    if (dst->mipCount > 6) { k_hzb_top<<<1, 256, 0, ctx->stream>>>(p); ctx->launches++; }     // tiled builds: from the tile-local mip 5, like the phase-1 HZB wants
     CHORD_CUDA(cudaGetLastError());
     return CHORD_OK;
 }

@@ -544,7 +544,8 @@ def test_graph_replay_matches_eager(gpu_ctx):
         fr.visibility_mark(post)
 
     frame_calls()
-    ref = dict(vis=fr.vis64(), post=post.readback(), hzb=hz.readback_chain('min'), marker=fr.tile_marker())
+    ref = dict(vis=fr.vis64(), post=post.readback(), hzb=hz.readback_chain('min'), marker=fr.tile_marker(), hmax=hz.readback_chain('max'),
+               rng=hz.valid_range().copy())
     with runtime.Graph.capture(gpu_ctx) as g:
         frame_calls()
     assert g.kernel_nodes >= 8
@@ -561,6 +562,7 @@ def test_graph_replay_matches_eager(gpu_ctx):
         _assert_vis_equal(fr.vis64(), ref['vis'], f'graph replay {rep}')
         _assert_lists_equal(post.readback(), ref['post'], 'post-cull list (graph)')
         assert np.array_equal(hz.readback_chain('min'), ref['hzb']) and np.array_equal(fr.tile_marker(), ref['marker'])
+        assert np.array_equal(hz.readback_chain('max'), ref['hmax']) and np.array_equal(hz.valid_range(), ref['rng'])
     g.close()
     # a synchronising call inside a capture is reported as an error, and the context stays usable
     with pytest.raises(runtime.ChordError):
