@@ -103,10 +103,17 @@ __global__ void __launch_bounds__(256) k_hzb_build(HzbBuildParams p)
         }
     }
     if (p.validRange) {
-        // hzb.hlsl:165-172: wave min/max, then InterlockedMin/Max on the raw bits with the <1 / >0 guards
+        // hzb.hlsl:165-172: wave min/max, then InterlockedMin/Max on the raw bits with the <1 / >0 guards.  min / max are
+        // associative, so the eight waves of the block are combined in shared memory first and ONE pair of atomics per
+        // block reaches the two global words (65 k same-address atomics per 4K build otherwise).
+        __shared__ float sRange[2][8];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) { vMin = fminf(vMin, __shfl_xor_sync(0xffffffffu, vMin, o)); vMax = fmaxf(vMax, __shfl_xor_sync(0xffffffffu, vMax, o)); }
-        if ((tid & 31u) == 0) {
+        if ((tid & 31u) == 0) { sRange[0][tid >> 5] = vMin; sRange[1][tid >> 5] = vMax; }
+        __syncthreads();
+        if (tid == 0) {
+#pragma unroll
+            for (int w = 1; w < 8; w++) { vMin = fminf(vMin, sRange[0][w]); vMax = fmaxf(vMax, sRange[1][w]); }
             if (vMin < 1.0f) atomicMin(&p.validRange[0], __float_as_uint(vMin));
             if (vMax > 0.0f) atomicMax(&p.validRange[1], __float_as_uint(vMax));
         }
