@@ -228,12 +228,98 @@ def frame_benchmark(ctx, stream, torch, steps=20, width=W4K, height=H4K):
     n = len(t_frames)
     ms = float(np.median(t_frames))
     stats = f.raster_stats()
-    return {'workload': f'S3 stand-in (Bistro-sized): procedural city, {lod0} LOD-0 meshlet instances = {lod0 * 128} triangles '
+    extras = {}
+    try:
+        extras['shadow'] = shadow_benchmark(ctx, stream, torch, (scene, info, frames[-1][2], frames[-1][1]))
+    except Exception as e:
+        extras['shadow'] = {'error': repr(e)}
+    try:
+        extras['masked'] = masked_benchmark(ctx, stream, torch)
+    except Exception as e:
+        extras['masked'] = {'error': repr(e)}
+    return {'next_rows': extras, 'workload': f'S3 stand-in (Bistro-sized): procedural city, {lod0} LOD-0 meshlet instances = {lod0 * 128} triangles '
                         f'({scene.total_meshlets} unique meshlets over 5 LODs, {len(frames[0][1])} objects), {width}x{height}, '
                         f'LOD cut at 1 px error, two-phase HZB, HZB builds, tile classify + PBR resolve (packed G-buffer), camera path',
             'frames_per_s': 1000.0 / ms, 'ms_per_frame': ms, 'frames_timed': n,
             'pass_us': {k: 1000.0 * v / n for k, v in acc.items()},
             'post_cull_meshlets_last_frame': int(post.count()), 'raster_stats_total': stats}
+
+
+def shadow_benchmark(ctx, stream, torch, scene_pack, steps=8, dim=2048, cascades=4):
+    """SURVEY 8f N3 measurement: renderShadow on the city (mesh_raster.cpp:332-546), every cascade re-rendered (no cache):
+    per cascade instance cull with the orthographic view -> hzbCullingGeneric against the farther cascade -> depth-only
+    raster (two-sided, depth clamp) -> HZB.  CUDA-event time of the whole pass."""
+    from chord_b200 import camera as cam, renderer
+    scene, info, view, objs = scene_pack
+    cfg = cam.CascadeShadowMapConfig(cascadeCount=cascades, realtimeCascadeCount=2, cascadeDim=dim, cascadeEndDistance=80.0, farCascadeEndDistance=800.0)
+    pool = renderer._Pool(ctx)
+    light = (0.3, -0.8, 0.2)
+    lod0, groups = info['lod0MeshletCount'], info['meshletGroupCount']
+    from chord_b200 import runtime
+    targets = [runtime.Frame(ctx, dim, dim) for _ in range(cascades)]
+    res = None
+    times = []
+    for i in range(steps + 2):
+        if res is not None:
+            for l in res.lists:
+                pool.release(l)
+        if i == steps + 1:
+            for t in targets:
+                t.reset_stats()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        res = renderer.renderShadow(ctx, pool, view, objs, lod0, groups, None, cfg, light, depth_targets=targets)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        if i >= 2:
+            times.append(e0.elapsed_time(e1))
+    meshlets = [int(l.count()) for l in res.lists]
+    stats = [f.raster_stats() for f in res.depths]
+    return {'workload': f'cascade shadow depth: {cascades} cascades x {dim}^2 over the same city, all re-rendered per pass (host cascade setup inside the timed region)',
+            'ms_per_pass': float(np.median(times)), 'meshlets_per_cascade': meshlets,
+            'triangles_submitted_per_pass': int(sum(s_['trianglesSubmitted'] for s_ in stats))}
+
+
+def masked_benchmark(ctx, stream, torch, n_meshlets=100000, steps=10):
+    """SURVEY 8f N2 measurement: the S5-style patch stream drawn with an alpha-tested textured material (every fragment
+    evaluates 3 perspective-correct uv samples + a trilinear A8 fetch before its RED): k_raster_masked throughput."""
+    from chord_b200 import abi, camera as cam, runtime, synth
+    scene, camera, objects, cmds = synth.patch_stream_scene(n_meshlets, W4K, H4K, seed=5)
+    V = 81
+    g = (np.arange(9, dtype=np.float32) / 8.0)
+    gx, gy = np.meshgrid(g, g)
+    uv = np.tile(np.stack([gx.reshape(-1), gy.reshape(-1)], axis=-1), (n_meshlets, 1)).astype(np.float32)
+    d = scene.datas[0]
+    m = synth.default_material(alpha_mode=1, alpha_cutoff=0.5)
+    m['baseColorId'], m['baseColorSampler'] = 1, 0
+    table = abi.TextureTable(synth.alpha_test_textures())
+    scene = abi.HostScene([dict(meshlets=d['meshlets'], positions=d['positions'], normals=None, uv0=uv, tangents=None, meshletData=d['meshletData'],
+                                groups=d['groups'], groupIndices=d['groupIndices'], bvhNodes=d['bvhNodes'])], scene.primitives, np.array([m]), textures=table)
+    view = cam.fill_view(camera)
+    iview = cam.fill_instance_view(view)
+    ctx.upload_scene(scene)
+    fr = runtime.Frame(ctx, W4K, H4K)
+    lst = runtime.CmdList(ctx, n_meshlets)
+    lst.upload(cmds)
+    groups = (n_meshlets + 3) // 4
+    for _ in range(3):
+        fr.begin(view, iview, objects, n_meshlets, groups)
+        fr.render_mesh(lst)
+    torch.cuda.synchronize()
+    fr.reset_stats()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for a, b in ev:
+        fr.begin(view, iview, objects, n_meshlets, groups)
+        a.record(stream)
+        fr.render_mesh(lst)
+        b.record(stream)
+    torch.cuda.synchronize()
+    ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
+    st = fr.raster_stats()
+    ctx.upload_textures(None)
+    return {'workload': f'{n_meshlets} meshlets x 128 ~1 px^2 triangles, alpha-tested 64x64 leaf texture (repeat), 3840x2160, k_raster_masked',
+            'mtri_per_s': n_meshlets * TRIS_PER_MESHLET / (ms * 1e-3) / 1e6, 'ms': ms,
+            'fragments_alpha_killed_per_step': int(st['fragmentsAlphaKilled'] // steps)}
 
 
 def frame_benchmark_tiled(ctx, stream, torch, dist, rank, world, steps=20, width=W4K, height=H4K):

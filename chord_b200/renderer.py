@@ -177,7 +177,7 @@ def hzbCullingGeneric(frame: Frame, pool: _Pool, hzb, extent_scale, hzb_view, us
 
 
 def renderShadow(ctx: Context, pool: _Pool, view, objects, lod0_meshlet_count, meshlet_group_count, history, config, light_direction,
-                 valid_depth_range=None):
+                 valid_depth_range=None, depth_targets=None):
     """chord::renderShadow (mesh_raster.cpp:332-546): cascade views (cascade_setup.hlsl, host mirror), then for every
     cascade that is not cache-valid, far to near: instanceCulling with the cascade view -> hzbCullingGeneric against the
     previous (farther) cascade's HZB, or against the cached depth of the same cascade when there is none -> clear ->
@@ -189,7 +189,12 @@ def renderShadow(ctx: Context, pool: _Pool, view, objects, lod0_meshlet_count, m
                    and np.array_equal(history.direction, direction) and history.config is cfg)
     tick = int(view['basicData']['frameCounter'])
     views = cam.cascade_views(view, direction, cfg, valid_depth_range, history.views if cache_valid else None, cache_valid)
-    depths = list(history.depths) if cache_valid else [Frame(ctx, cfg.cascadeDim, cfg.cascadeDim) for _ in range(cfg.cascadeCount)]
+    if cache_valid:
+        depths = list(history.depths)
+    elif depth_targets is not None:              # pooled depth textures (getTexturePool().create, mesh_raster.cpp:381-389)
+        depths = list(depth_targets)
+    else:
+        depths = [Frame(ctx, cfg.cascadeDim, cfg.cascadeDim) for _ in range(cfg.cascadeCount)]
     out = CascadeShadowContext(cfg, direction, views, depths, [None] * cfg.cascadeCount)
     prev_hzb, prev_id = None, None
     for cid in range(cfg.cascadeCount - 1, -1, -1):
