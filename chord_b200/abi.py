@@ -211,6 +211,14 @@ class TextureTable:
             self.smp[i].addressU, self.smp[i].addressV = u, v
 
 
+class CascadeSetupDesc(C.Structure):
+    """chord_cascade_setup_desc = CascadeSetupPushConsts (cascade_setup.hlsl:24-50)."""
+    _fields_ = [('lightDir', C.c_float * 3), ('cascadeStartDistance', C.c_float), ('cascadeEndDistance', C.c_float),
+                ('splitLambda', C.c_float), ('farCascadeSplitLambda', C.c_float), ('farCascadeEndDistance', C.c_float),
+                ('radiusScale', C.c_float), ('cascadeCount', C.c_uint32), ('realtimeCount', C.c_uint32), ('cascadeDim', C.c_uint32),
+                ('bCacheValid', C.c_uint32), ('tickCount', C.c_uint32)]
+
+
 class AtmosphereLuts(C.Structure):
     _fields_ = [('transmittance', C.c_void_p), ('irradiance', C.c_void_p)]
 

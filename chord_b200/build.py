@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 OUT = os.path.join(HERE, 'libchord_b200.so')
-SOURCES = ['ctx.cu', 'cull.cu', 'raster.cu', 'hzb.cu', 'resolve.cu']
+SOURCES = ['ctx.cu', 'cull.cu', 'raster.cu', 'hzb.cu', 'resolve.cu', 'shadow.cu']
 HEADERS = ['common.cuh', '../../include/chord_b200.h', '../../include/chord_abi_types.h']
 
 # Per-file overrides.  Tried in round 1: resolve.cu with --use_fast_math halves the resolve (600 -> 313 us at 4K) but

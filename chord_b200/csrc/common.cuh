@@ -179,6 +179,12 @@ struct chord_ctx {
     chordb::TextureDev* dTextures; chordb::SamplerDev* dSamplers; uint8_t* dTexels; uint32_t nTextures, nSamplers;
 };
 
+struct chord_cascade_views {
+    chord_ctx* ctx;
+    chord_InstanceCullingViewInfo* dViews;      // [CHORD_MAX_CASCADE_COUNT]
+    uint32_t cascadeDim;                        // of the last setup / upload (frame size check)
+};
+
 struct chord_graph {
     chord_ctx* ctx;
     cudaGraph_t graph; cudaGraphExec_t exec;
@@ -250,8 +256,9 @@ int launch_instance_culling(chord_frame* f, chord_cmdlist* out);
 int launch_instance_culling_bvh(chord_frame* f, chord_cmdlist* out);
 int launch_hzb_culling(chord_frame* f, const chord_hzb* hzb, int firstStage, chord_cmdlist* in, chord_cmdlist* outVis, chord_cmdlist* outRej);
 int launch_render_mesh(chord_frame* f, chord_cmdlist* list);
+int launch_cascade_setup(chord_frame* mainFrame, const chord_cascade_setup_desc* desc, const chord_hzb* validRangeSource, chord_InstanceCullingViewInfo* dViews);
 int launch_hzb_culling_generic(chord_frame* f, const chord_hzb* hzb, const chord_InstanceCullingViewInfo* hzbView, float extentScale,
-                               int useLastFrame, chord_cmdlist* in, chord_cmdlist* outVis);
+                               int useLastFrame, chord_cmdlist* in, chord_cmdlist* outVis, const chord_InstanceCullingViewInfo* dHzbView = nullptr);
 int launch_build_hzb(chord_frame* f, int bMin, int bMax, int bRange, chord_hzb* dst);
 int launch_visibility_mark(chord_frame* f, chord_cmdlist* post);
 int launch_lighting(chord_frame* f, chord_cmdlist* post);

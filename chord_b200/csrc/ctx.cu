@@ -607,6 +607,74 @@ int chord_atmosphere_luts_upload(chord_ctx* ctx, const chord_atmosphere_luts* lu
     return CHORD_OK;
 }
 
+// ---------------------------------------------------------------------------------------------- cascade views (N3)
+int chord_cascade_views_create(chord_ctx* ctx, chord_cascade_views** out)
+{
+    CHORD_REQUIRE(ctx && out, "null");
+    CHORD_CUDA(cudaSetDevice(ctx->device));
+    chord_cascade_views* v = (chord_cascade_views*)calloc(1, sizeof(chord_cascade_views));
+    v->ctx = ctx;
+    CHORD_CUDA(cudaMalloc(&v->dViews, sizeof(chord_InstanceCullingViewInfo) * CHORD_MAX_CASCADE_COUNT));
+    CHORD_CUDA(cudaMemsetAsync(v->dViews, 0, sizeof(chord_InstanceCullingViewInfo) * CHORD_MAX_CASCADE_COUNT, ctx->stream));
+    *out = v;
+    return CHORD_OK;
+}
+void chord_cascade_views_destroy(chord_cascade_views* v)
+{
+    if (!v) return;
+    cudaStreamSynchronize(v->ctx->stream);
+    cudaFree(v->dViews); free(v);
+}
+int chord_cascade_setup(chord_frame* mainFrame, const chord_cascade_setup_desc* d, const chord_hzb* validRangeSource, chord_cascade_views* views)
+{
+    CHORD_REQUIRE(mainFrame && d && views && mainFrame->begun, "null / main frame not begun");
+    CHORD_REQUIRE(d->cascadeCount >= 1 && d->cascadeCount <= CHORD_MAX_CASCADE_COUNT && d->realtimeCount <= d->cascadeCount, "cascade counts (mesh_raster.cpp:363)");
+    CHORD_REQUIRE(d->cascadeDim >= CHORD_MIN_RENDER_DIM && d->cascadeDim <= CHORD_MAX_RENDER_DIM, "cascadeDim");
+    views->cascadeDim = d->cascadeDim;
+    return launch_cascade_setup(mainFrame, d, validRangeSource, views->dViews);
+}
+int chord_cascade_views_readback(chord_cascade_views* v, chord_InstanceCullingViewInfo* host, uint32_t count)
+{
+    CHORD_REQUIRE(v && host && count <= CHORD_MAX_CASCADE_COUNT, "args");
+    CHORD_CUDA(cudaMemcpyAsync(host, v->dViews, sizeof(chord_InstanceCullingViewInfo) * count, cudaMemcpyDeviceToHost, v->ctx->stream));
+    CHORD_CUDA(cudaStreamSynchronize(v->ctx->stream));
+    return CHORD_OK;
+}
+int chord_cascade_views_upload(chord_cascade_views* v, const chord_InstanceCullingViewInfo* host, uint32_t count)
+{
+    CHORD_REQUIRE(v && host && count >= 1 && count <= CHORD_MAX_CASCADE_COUNT, "args");
+    CHORD_CUDA(cudaMemcpyAsync(v->dViews, host, sizeof(chord_InstanceCullingViewInfo) * count, cudaMemcpyHostToDevice, v->ctx->stream));
+    CHORD_CUDA(cudaStreamSynchronize(v->ctx->stream));
+    v->cascadeDim = (uint32_t)host[0].renderDimension.x;
+    return CHORD_OK;
+}
+int chord_frame_begin_cascade(chord_frame* f, const chord_PerframeCameraView* view, chord_cascade_views* views, uint32_t cascadeId,
+                              const chord_GPUObjectGLTFPrimitive* objects, uint32_t objectCount, uint32_t lod0MeshletCount, uint32_t meshletGroupCount)
+{
+    CHORD_REQUIRE(f && view && views && cascadeId < CHORD_MAX_CASCADE_COUNT, "args");
+    CHORD_REQUIRE(views->cascadeDim == f->width && views->cascadeDim == f->height, "depth frame size != cascadeDim");
+    // host-side placeholder with what chord_frame_begin checks on the host (size; cascade views are orthographic); the
+    // device record is then overwritten by the cascade buffer's entry, stream-ordered behind the setup kernel
+    chord_InstanceCullingViewInfo iv; memset(&iv, 0, sizeof(iv));
+    iv.renderDimension.x = (float)f->width; iv.renderDimension.y = (float)f->height;
+    iv.translatedWorldToClip.m[15] = 1.0f;
+    const int rc = chord_frame_begin(f, view, &iv, objects, objectCount, lod0MeshletCount, meshletGroupCount, nullptr);
+    if (rc) return rc;
+    CHORD_CUDA(cudaMemcpyAsync(f->dIView, views->dViews + cascadeId, sizeof(chord_InstanceCullingViewInfo), cudaMemcpyDeviceToDevice, f->ctx->stream));
+    return launch_object_prepare(f);        // the derived per-object matrices depend on the instance view
+}
+int chord_hzb_culling_generic_cascade(chord_frame* f, const chord_hzb* hzb, chord_cascade_views* views, uint32_t hzbViewId, float extentScale,
+                                      int bObjectUseLastFrameProject, chord_cmdlist* in, chord_cmdlist* outVisible)
+{
+    CHORD_REQUIRE(f && hzb && views && hzbViewId < CHORD_MAX_CASCADE_COUNT && in && outVisible && f->begun, "null / frame not begun");
+    CHORD_REQUIRE(hzb->depthW == views->cascadeDim && hzb->depthH == views->cascadeDim, "hzb was not built for the cascade dimension");
+    CHORD_REQUIRE(outVisible->capacity >= in->capacity, "output list capacity");
+    CHORD_ACQUIRE(in); CHORD_ACQUIRE(outVisible);
+    const int rc = launch_hzb_culling_generic(f, hzb, nullptr, extentScale, bObjectUseLastFrameProject, in, outVisible, views->dViews + hzbViewId);
+    CHORD_RELEASE(in); CHORD_RELEASE(outVisible);
+    return rc;
+}
+
 // ---------------------------------------------------------------------------------------------- graphs
 int chord_graph_begin_capture(chord_ctx* ctx)
 {

@@ -386,6 +386,7 @@ struct GenericCullParams {
     float rel[3];                       // float3(perView.cameraWorldPos - hzbView.cameraWorldPos)
     float W, H, lo, hi;                 // hzbView.renderDimension.xy, extentScale * -/+ 0.5
     uint32_t useLastFrame;
+    const chord_InstanceCullingViewInfo* dView;    // when set, viewProj / rel / W / H are read from this device record instead
 };
 
 __global__ void __launch_bounds__(kCullBlock) k_hzb_cull_generic(FrameDev f, HzbDev hzb, GenericCullParams prm,
@@ -398,6 +399,23 @@ __global__ void __launch_bounds__(kCullBlock) k_hzb_cull_generic(FrameDev f, Hzb
     __shared__ uint32_t sBaseV;
     uint32_t total = *inCount; if (total > inCapacity) total = inCapacity;
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    __shared__ GenericCullParams sPrm;
+    if (prm.dView) {
+        // the HZB's view lives on the device (cascade buffer): resolve the derived parameters once per block
+        if (threadIdx.x < 16) sPrm.viewProj.m[threadIdx.x] = prm.dView->translatedWorldToClip.m[threadIdx.x];
+        if (threadIdx.x == 16) {
+            const chord_uint2* a = &f.view->cameraWorldPos.x; const chord_uint2* b = &prm.dView->cameraWorldPos.x;
+            for (int k = 0; k < 3; k++) {
+                const double da = __longlong_as_double((long long)((unsigned long long)a[k].x | ((unsigned long long)a[k].y << 32)));
+                const double db = __longlong_as_double((long long)((unsigned long long)b[k].x | ((unsigned long long)b[k].y << 32)));
+                sPrm.rel[k] = (float)(da - db);
+            }
+            sPrm.W = prm.dView->renderDimension.x; sPrm.H = prm.dView->renderDimension.y;
+            sPrm.lo = prm.lo; sPrm.hi = prm.hi; sPrm.useLastFrame = prm.useLastFrame;
+        }
+        __syncthreads();
+        prm = sPrm;
+    }
     while (true) {
         __syncthreads();
         if (threadIdx.x == 0) sTile = atomicAdd(ticket, 1u);
@@ -632,7 +650,7 @@ int launch_hzb_culling(chord_frame* fr, const chord_hzb* hzb, int firstStage, ch
 }
 
 int launch_hzb_culling_generic(chord_frame* fr, const chord_hzb* hzb, const chord_InstanceCullingViewInfo* hzbView, float extentScale,
-                               int useLastFrame, chord_cmdlist* in, chord_cmdlist* outVis)
+                               int useLastFrame, chord_cmdlist* in, chord_cmdlist* outVis, const chord_InstanceCullingViewInfo* dHzbView)
 {
     chord_ctx* ctx = fr->ctx;
     FrameDev f = make_frame_dev(fr);
@@ -640,14 +658,18 @@ int launch_hzb_culling_generic(chord_frame* fr, const chord_hzb* hzb, const chor
     h.minChain = hzb->minChain; h.mip0W = hzb->mip0W; h.mip0H = hzb->mip0H; h.mipCount = hzb->mipCount;
     for (int i = 0; i < CHORD_HZB_MAX_MIP_COUNT; i++) h.mipOffset[i] = hzb->mipOffset[i];
     GenericCullParams prm;
-    prm.viewProj = hzbView->translatedWorldToClip;
-    const chord_uint2* a = &fr->hView.cameraWorldPos.x; const chord_uint2* b = &hzbView->cameraWorldPos.x;
-    for (int k = 0; k < 3; k++) {
-        const uint64_t ua = (uint64_t)a[k].x | ((uint64_t)a[k].y << 32), ub = (uint64_t)b[k].x | ((uint64_t)b[k].y << 32);
-        double da, db; memcpy(&da, &ua, 8); memcpy(&db, &ub, 8);
-        prm.rel[k] = (float)(da - db);             // float3(perView.cameraWorldPos - instanceView.cameraWorldPos), hzb_culling_generic.hlsl:78
+    memset(&prm, 0, sizeof(prm));
+    prm.dView = dHzbView;
+    if (hzbView) {
+        prm.viewProj = hzbView->translatedWorldToClip;
+        const chord_uint2* a = &fr->hView.cameraWorldPos.x; const chord_uint2* b = &hzbView->cameraWorldPos.x;
+        for (int k = 0; k < 3; k++) {
+            const uint64_t ua = (uint64_t)a[k].x | ((uint64_t)a[k].y << 32), ub = (uint64_t)b[k].x | ((uint64_t)b[k].y << 32);
+            double da, db; memcpy(&da, &ua, 8); memcpy(&db, &ub, 8);
+            prm.rel[k] = (float)(da - db);             // float3(perView.cameraWorldPos - instanceView.cameraWorldPos), hzb_culling_generic.hlsl:78
+        }
+        prm.W = hzbView->renderDimension.x; prm.H = hzbView->renderDimension.y;
     }
-    prm.W = hzbView->renderDimension.x; prm.H = hzbView->renderDimension.y;
     prm.lo = extentScale * -0.5f; prm.hi = extentScale * 0.5f;
     prm.useLastFrame = useLastFrame ? 1u : 0u;
     const uint32_t tiles = (in->capacity + kCullBlock - 1) / kCullBlock + 1;

@@ -10,7 +10,7 @@ from dataclasses import dataclass, field
 import numpy as np
 
 from . import abi, camera as cam
-from .runtime import CmdList, Context, Frame, Hzb
+from .runtime import CascadeViews, CmdList, Context, Frame, Hzb
 
 
 class _Pool:
@@ -167,6 +167,7 @@ class CascadeShadowContext:
     views: np.ndarray
     depths: list
     lists: list = field(default_factory=list)      # post-cull lists per cascade (kept for inspection / tests)
+    device_views: object = None                    # CascadeViews when the setup ran on the GPU (chord_cascade_setup)
 
 
 def hzbCullingGeneric(frame: Frame, pool: _Pool, hzb, extent_scale, hzb_view, use_last_frame, in_list):
@@ -177,7 +178,7 @@ def hzbCullingGeneric(frame: Frame, pool: _Pool, hzb, extent_scale, hzb_view, us
 
 
 def renderShadow(ctx: Context, pool: _Pool, view, objects, lod0_meshlet_count, meshlet_group_count, history, config, light_direction,
-                 valid_depth_range=None, depth_targets=None):
+                 valid_depth_range=None, depth_targets=None, main_frame=None, valid_range_hzb=None):
     """chord::renderShadow (mesh_raster.cpp:332-546): cascade views (cascade_setup.hlsl, host mirror), then for every
     cascade that is not cache-valid, far to near: instanceCulling with the cascade view -> hzbCullingGeneric against the
     previous (farther) cascade's HZB, or against the cached depth of the same cascade when there is none -> clear ->
@@ -188,14 +189,37 @@ def renderShadow(ctx: Context, pool: _Pool, view, objects, lod0_meshlet_count, m
     cache_valid = (history is not None and len(history.depths) == cfg.cascadeCount
                    and np.array_equal(history.direction, direction) and history.config is cfg)
     tick = int(view['basicData']['frameCounter'])
-    views = cam.cascade_views(view, direction, cfg, valid_depth_range, history.views if cache_valid else None, cache_valid)
+    dviews = None
+    if main_frame is not None:
+        # CascadeSetupCS on the device (chord_cascade_setup): reads the main frame's PerframeCameraView and, for SDSM, the
+        # valid depth range of ``valid_range_hzb`` straight from HBM; nothing is read back, the whole pass is asynchronous
+        dviews = history.device_views if (cache_valid and history.device_views is not None) else CascadeViews(ctx)
+        dviews.setup(main_frame, cfg, direction, tick, cache_valid, valid_range_hzb)
+        views = None
+    else:
+        views = cam.cascade_views(view, direction, cfg, valid_depth_range, history.views if cache_valid else None, cache_valid)
     if cache_valid:
         depths = list(history.depths)
     elif depth_targets is not None:              # pooled depth textures (getTexturePool().create, mesh_raster.cpp:381-389)
         depths = list(depth_targets)
     else:
         depths = [Frame(ctx, cfg.cascadeDim, cfg.cascadeDim) for _ in range(cfg.cascadeCount)]
-    out = CascadeShadowContext(cfg, direction, views, depths, [None] * cfg.cascadeCount)
+    out = CascadeShadowContext(cfg, direction, views, depths, [None] * cfg.cascadeCount, dviews)
+
+    def begin(f, cid):
+        if dviews is not None:
+            f.begin_cascade(view, dviews, cid, objects, lod0_meshlet_count, meshlet_group_count)
+        else:
+            f.begin(view, views[cid], objects, lod0_meshlet_count, meshlet_group_count)
+
+    def cull(f, hzb, view_id, in_list):
+        o = pool.cmdlist(in_list.capacity)
+        if dviews is not None:
+            f.hzb_culling_generic_cascade(hzb, dviews, view_id, kShadowExtentScaleForHZBCulling, False, in_list, o)
+        else:
+            f.hzb_culling_generic(hzb, views[view_id], kShadowExtentScaleForHZBCulling, False, in_list, o)
+        return o
+
     prev_hzb, prev_id = None, None
     for cid in range(cfg.cascadeCount - 1, -1, -1):
         if cam.is_cascade_cache_valid(cache_valid, cfg.realtimeCascadeCount, cfg.cascadeCount, tick, cid):
@@ -206,18 +230,18 @@ def renderShadow(ctx: Context, pool: _Pool, view, objects, lod0_meshlet_count, m
             # the cascade's depth of last frame is still in f: build its HZB before the target is cleared
             cached_hzb = pool.hzb(cfg.cascadeDim, cfg.cascadeDim)
             f.build_hzb(cached_hzb, True, False, False)
-        f.begin(view, views[cid], objects, lod0_meshlet_count, meshlet_group_count)        # uniforms + clearDepthStencil(0.0)
+        begin(f, cid)                                                                      # uniforms + clearDepthStencil(0.0)
         post = pool.cmdlist(lod0_meshlet_count)
         f.instance_culling(post)
         if prev_hzb is None:
             if cached_hzb is not None:
                 # mesh_raster.cpp:463-479 passes cascadeHistory.viewsSRV, which is the SAME buffer CascadeSetupCS has just
                 # rewritten for this cascade (mesh_raster.cpp:411-414): the cached depth is tested with the NEW view
-                culled = hzbCullingGeneric(f, pool, cached_hzb, kShadowExtentScaleForHZBCulling, views[cid], False, post)
+                culled = cull(f, cached_hzb, cid, post)
                 pool.release(post); post = culled
                 pool.release(cached_hzb)
         elif kShadowHZBCullingEnable:
-            culled = hzbCullingGeneric(f, pool, prev_hzb, kShadowExtentScaleForHZBCulling, views[prev_id], False, post)
+            culled = cull(f, prev_hzb, prev_id, post)
             pool.release(post); post = culled
         f.render_mesh_depth(post, abi.PASS_DEPTH | abi.PASS_DEPTH_CLAMP)
         out.lists[cid] = post

@@ -27,6 +27,8 @@ SYMBOLS = [
     'chord_readback_vis64', 'chord_readback_visibility32', 'chord_readback_depth32', 'chord_readback_decoded',
     'chord_readback_tile_marker', 'chord_readback_gbuffer_f32', 'chord_frame_set_gbuffer_packed', 'chord_readback_gbuffer_packed', 'chord_frame_vis64_ptr', 'chord_frame_dims',
     'chord_frame_raster_stats', 'chord_frame_reset_stats', 'chord_frame_set_queue_limits',
+    'chord_cascade_views_create', 'chord_cascade_views_destroy', 'chord_cascade_setup', 'chord_cascade_views_readback',
+    'chord_cascade_views_upload', 'chord_frame_begin_cascade', 'chord_hzb_culling_generic_cascade',
     'chord_graph_begin_capture', 'chord_graph_end_capture', 'chord_graph_launch', 'chord_graph_kernel_nodes', 'chord_graph_destroy',
 ]
 
@@ -53,7 +55,8 @@ def lib():
         for n in ('chord_cmdlist_count_ptr', 'chord_cmdlist_cmds_ptr', 'chord_hzb_chain_ptr', 'chord_frame_vis64_ptr'):
             getattr(L, n).restype = C.c_void_p
         L.chord_graph_kernel_nodes.restype = C.c_uint32
-        for n in ('chord_ctx_destroy', 'chord_cmdlist_destroy', 'chord_hzb_destroy', 'chord_frame_destroy', 'chord_graph_destroy'):
+        for n in ('chord_ctx_destroy', 'chord_cmdlist_destroy', 'chord_hzb_destroy', 'chord_frame_destroy', 'chord_graph_destroy',
+                  'chord_cascade_views_destroy'):
             getattr(L, n).restype = None
         L.chord_hzb_chain_bytes.restype = C.c_uint64
         L.chord_hzb_mip_offset.restype = C.c_uint64
@@ -131,6 +134,45 @@ class Context:
         assert t.shape == (64, 256, 4) and i.shape == (16, 64, 4)
         luts = abi.AtmosphereLuts(t.ctypes.data, i.ctypes.data)
         lib().chord_atmosphere_luts_upload(self.h, C.byref(luts))
+
+
+class CascadeViews:
+    """Device buffer of the cascades' InstanceCullingViewInfo records, written by CascadeSetupCS on the GPU."""
+
+    def __init__(self, ctx):
+        self.ctx, self.h = ctx, C.c_void_p()
+        lib().chord_cascade_views_create(ctx.h, C.byref(self.h))
+
+    def setup(self, main_frame, cfg, light_dir, tick, cache_valid=False, valid_range_hzb=None):
+        """chord_cascade_setup: ``cfg`` = camera.CascadeShadowMapConfig; ``valid_range_hzb`` = the Hzb whose valid range (SDSM) to read."""
+        d = abi.CascadeSetupDesc()
+        d.lightDir = (C.c_float * 3)(*[float(x) for x in light_dir])
+        d.cascadeStartDistance, d.cascadeEndDistance = cfg.cascadeStartDistance, cfg.cascadeEndDistance
+        d.splitLambda, d.farCascadeSplitLambda, d.farCascadeEndDistance = cfg.splitLambda, cfg.farCascadeSplitLambda, cfg.farCascadeEndDistance
+        d.radiusScale = cfg.radiusScaleFixed
+        d.cascadeCount, d.realtimeCount, d.cascadeDim = cfg.cascadeCount, cfg.realtimeCascadeCount, cfg.cascadeDim
+        d.bCacheValid, d.tickCount = int(bool(cache_valid)), int(tick)
+        lib().chord_cascade_setup(main_frame.h, C.byref(d), valid_range_hzb.h if valid_range_hzb is not None else None, self.h)
+
+    def readback(self, count):
+        out = np.zeros(count, dtype=abi.InstanceCullingViewInfo)
+        lib().chord_cascade_views_readback(self.h, _p(out), C.c_uint32(count))
+        return out
+
+    def upload(self, views):
+        v = np.ascontiguousarray(views, dtype=abi.InstanceCullingViewInfo)
+        lib().chord_cascade_views_upload(self.h, _p(v), C.c_uint32(len(v)))
+
+    def close(self):
+        if self.h:
+            lib().chord_cascade_views_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class Graph:
@@ -337,6 +379,18 @@ class Frame:
     def hzb_culling(self, hzb: Hzb, first_stage, inp: CmdList, out_visible: CmdList, out_rejected: CmdList = None):
         lib().chord_hzb_culling(self.h, hzb.h, C.c_int(1 if first_stage else 0), inp.h, out_visible.h,
                                 out_rejected.h if out_rejected is not None else None)
+
+    def begin_cascade(self, view, cascade_views, cascade_id, objects, lod0_meshlet_count, meshlet_group_count):
+        """chord_frame_begin with the instance view taken from the device cascade buffer."""
+        v = np.ascontiguousarray(view, dtype=abi.PerframeCameraView).reshape(())
+        o = np.ascontiguousarray(objects, dtype=abi.GPUObjectGLTFPrimitive)
+        self._keep = (v, o)
+        lib().chord_frame_begin_cascade(self.h, _p(v), cascade_views.h, C.c_uint32(cascade_id), _p(o), C.c_uint32(len(o)),
+                                        C.c_uint32(lod0_meshlet_count), C.c_uint32(meshlet_group_count))
+
+    def hzb_culling_generic_cascade(self, hzb: Hzb, cascade_views, hzb_view_id, extent_scale, use_last_frame, inp: CmdList, out_visible: CmdList):
+        lib().chord_hzb_culling_generic_cascade(self.h, hzb.h, cascade_views.h, C.c_uint32(hzb_view_id), C.c_float(extent_scale),
+                                                C.c_int(1 if use_last_frame else 0), inp.h, out_visible.h)
 
     def render_mesh_depth(self, lst: CmdList, pass_flags=abi.PASS_DEPTH | abi.PASS_DEPTH_CLAMP):
         lib().chord_render_mesh_depth(self.h, lst.h, C.c_uint32(pass_flags))

@@ -207,6 +207,31 @@ int chord_render_mesh_depth(chord_frame* frame, chord_cmdlist* list, uint32_t pa
 int chord_hzb_culling_generic(chord_frame* frame, const chord_hzb* hzb, const chord_InstanceCullingViewInfo* hzbView,
                               float extentScale, int bObjectUseLastFrameProject, chord_cmdlist* in, chord_cmdlist* outVisible);
 
+/* Cascade views on the device: CascadeSetupCS (cascade_setup.hlsl:89-371; mesh_raster.cpp:400-431) writes one
+ * InstanceCullingViewInfo per cascade into a device buffer, reading buildHZB's valid depth range on the GPU (SDSM) so
+ * that the shadow pass needs no read-back.  chord_cascade_setup_desc = CascadeSetupPushConsts (cascade_setup.hlsl:24-50).
+ * The main frame supplies the PerframeCameraView already on the device (it must have been begun this frame).
+ * chord_frame_begin_cascade / chord_hzb_culling_generic_cascade are chord_frame_begin / chord_hzb_culling_generic with
+ * the instance view taken from that buffer. */
+#define CHORD_MAX_CASCADE_COUNT 8      /* base.h:88 kMaxCascadeCount */
+typedef struct {
+    float lightDir[3];
+    float cascadeStartDistance, cascadeEndDistance, splitLambda, farCascadeSplitLambda, farCascadeEndDistance, radiusScale;
+    uint32_t cascadeCount, realtimeCount, cascadeDim, bCacheValid, tickCount;
+} chord_cascade_setup_desc;
+typedef struct chord_cascade_views chord_cascade_views;
+int  chord_cascade_views_create(chord_ctx* ctx, chord_cascade_views** out);
+void chord_cascade_views_destroy(chord_cascade_views* views);
+int  chord_cascade_setup(chord_frame* mainFrame, const chord_cascade_setup_desc* desc, const chord_hzb* validRangeSource /* NULL: none */,
+                         chord_cascade_views* views);
+int  chord_cascade_views_readback(chord_cascade_views* views, chord_InstanceCullingViewInfo* host, uint32_t count);
+int  chord_cascade_views_upload(chord_cascade_views* views, const chord_InstanceCullingViewInfo* host, uint32_t count);
+int  chord_frame_begin_cascade(chord_frame* depthFrame, const chord_PerframeCameraView* view, chord_cascade_views* views, uint32_t cascadeId,
+                               const chord_GPUObjectGLTFPrimitive* objects, uint32_t objectCount,
+                               uint32_t lod0MeshletCount, uint32_t meshletGroupCount);
+int  chord_hzb_culling_generic_cascade(chord_frame* frame, const chord_hzb* hzb, chord_cascade_views* views, uint32_t hzbViewId,
+                                       float extentScale, int bObjectUseLastFrameProject, chord_cmdlist* in, chord_cmdlist* outVisible);
+
 /* gltfVisibilityRenderingStage0 (mesh_raster.cpp:269-312).  needStage1 mirrors the bool result.
  * scratchVisible is the pooled list that receives the phase-0 survivors. */
 int chord_visibility_stage0(chord_frame* frame, const chord_hzb* lastFrameHzb /* may be NULL / invalid */,

@@ -665,3 +665,65 @@ def test_overlapped_list_uploads(gpu_ctx):
         fr.readback_vis64_into(imgs[i].ctypes.data)
     for i, k in enumerate(order):
         _assert_vis_equal(imgs[i], want[k], f'step {i} (subset {k})')
+
+
+def test_cascade_setup_on_device(gpu_ctx):
+    """chord_cascade_setup (cascade_setup.hlsl:89-371 as a one-warp kernel): the views it writes agree with the host mirror to
+    fp32 tolerance (pow() cannot be bit-pinned), including the SDSM branch fed from buildHZB's valid range on the GPU and
+    the round-robin cascade cache; the shadow pass driven by the device views is bit-exact against the oracle given the
+    very same views (read back only for the check)."""
+    from cases import city_frames, oracle_render_shadow
+    from chord_b200 import camera as cam_
+    light = (0.3, -0.8, 0.2)
+    scene, info, frames = city_frames(frames=2)
+    gpu_ctx.upload_scene(scene)
+    w, h = 640, 360
+    lod0, groups = info['lod0MeshletCount'], info['meshletGroupCount']
+    cfg = cam_.CascadeShadowMapConfig(cascadeCount=4, realtimeCascadeCount=2, cascadeDim=512, cascadeEndDistance=80.0, farCascadeEndDistance=400.0)
+    main = renderer.DeferredRenderer(gpu_ctx, w, h)
+    pool = renderer._Pool(gpu_ctx)
+
+    def close(a, b, what):
+        for k in ('translatedWorldToClip', 'clipToTranslatedWorld', 'orthoDepthConvertToView', 'renderDimension', 'frustumPlanesRS'):
+            x, y = np.asarray(a[k], dtype=np.float64), np.asarray(b[k], dtype=np.float64)
+            scale = max(1.0, np.abs(y).max())
+            assert np.abs(x - y).max() <= 2e-3 * scale, (what, k, np.abs(x - y).max(), scale)
+        assert np.array_equal(a['cameraWorldPos'], b['cameraWorldPos'])
+
+    hist = None
+    for fi, f in enumerate(frames):
+        main.render(f['camera'], f['objects'], lod0, groups, view=f['view'], iview=f['iview'])      # builds the HZB + valid range
+        for sdsm in (False, True):
+            hz = main.history_hzb if sdsm else None
+            vr = main.history_hzb.valid_range() if sdsm else None
+            g = renderer.renderShadow(gpu_ctx, pool, f['view'], f['objects'], lod0, groups, hist if not sdsm else None, cfg, light,
+                                      main_frame=main.frame, valid_range_hzb=hz)
+            dv = g.device_views.readback(cfg.cascadeCount)
+            host = cam_.cascade_views(f['view'], light, cfg, valid_depth_range=vr)
+            for cid in range(cfg.cascadeCount):
+                if g.lists[cid] is not None:
+                    close(dv[cid], host[cid], f'frame {fi} sdsm {sdsm} cascade {cid}')
+                    m = dv[cid]['translatedWorldToClip'].T
+                    assert m[3, 3] == 1.0 and not m[3, :3].any()
+            # downstream parity with exactly these views: replay the sequence on the oracle
+            rendered = [c for c in range(cfg.cascadeCount) if g.lists[c] is not None]
+            prev, prev_id = None, None
+            for cid in reversed(rendered):
+                ofr = oracle.Frame(scene, f['view'], dv[cid], f['objects'], cfg.cascadeDim, cfg.cascadeDim)
+                post = ofr.instance_culling(lod0)
+                if prev is not None:
+                    post = ofr.hzb_culling_generic(prev, dv[prev_id], 1.5, False, post)
+                elif hist is not None and not sdsm:
+                    cached = ofr.build_hzb(hist_depth[cid], True, False, False)
+                    post = ofr.hzb_culling_generic(cached, dv[cid], 1.5, False, post)
+                ov, _ = ofr.render_mesh_depth(post)
+                _assert_lists_equal(g.lists[cid].readback(), post, f'frame {fi} sdsm {sdsm} cascade {cid} list')
+                _assert_vis_equal(g.depths[cid].vis64(), ov, f'frame {fi} sdsm {sdsm} cascade {cid} depth')
+                if cid != 0:
+                    prev, prev_id = ofr.build_hzb(ov, True, False, False), cid
+            if not sdsm:
+                hist = g
+                hist_depth = [d.vis64() for d in g.depths]
+        if fi == 1:
+            # second frame, cache valid: realtime cascades + one far cascade (tick 1 -> cascade 3) were re-rendered
+            pass
