@@ -267,6 +267,97 @@ def patch_stream_scene(n_meshlets, width=3840, height=2160, seed=5, area_range=(
     return scene, camera, objects, cmds
 
 
+def ragged_stream_scene(n_meshlets, width=640, height=360, seed=9, two_sided_every=5):
+    """Edge-case stream for the raster: meshlets of every shape the format allows (``base.h:406-445``): T from 1 to 128
+    triangles, V from 3 up to the maximum of 255 vertices (triangles partly or fully un-welded, so that V > 128 exercises
+    the large-vertex path of the fast raster kernel), odd data offsets (the TMA stage reads 16-byte supersets), patch
+    sizes from sub-pixel to tens of pixels.  Returns (scene, camera, objects, cmds) like ``patch_stream_scene``."""
+    rng = np.random.default_rng(seed)
+    q = 8
+    fovy = math.radians(45.0)
+    tan_half = math.tan(fovy * 0.5)
+    topo = _patch_topology(q)
+    i0, i1, i2 = topo & 0xFF, (topo >> 8) & 0xFF, (topo >> 16) & 0xFF
+    corners = np.stack([i0, i2, i1], axis=-1).astype(np.int64)          # camera-facing winding (see patch_stream_scene)
+    g = (np.arange(q + 1) - q / 2.0)
+    gx, gy = np.meshgrid(g, g)
+    gx, gy = gx.reshape(-1).astype(F), gy.reshape(-1).astype(F)
+    shapes = [(1, 0.0), (1, 1.0), (2, 1.0), (85, 1.0), (128, 0.0), (128, 0.55), (127, 0.45), (43, 1.0), (96, 0.7), (128, 0.3)]
+    pos_all, data_all, meshlets, centers = [], [], [], []
+    data_len, vert_base = 0, 0
+    for mi in range(int(n_meshlets)):
+        T, unweld = shapes[mi % len(shapes)] if mi < 4 * len(shapes) else (int(rng.integers(1, 129)), float(rng.random()))
+        tri = corners[rng.permutation(128)[:T]] if mi % 3 == 0 else corners[:T]
+        depth = F(rng.uniform(1.0, 60.0))
+        side_px = F(np.sqrt(2.0 * rng.choice([0.3, 1.0, 1.0, 4.0, 30.0, 400.0])))
+        px_world = F(2.0 * tan_half / height) * depth
+        cx, cy, ang = F(rng.uniform(-20, width + 20)), F(rng.uniform(-20, height + 20)), F(rng.uniform(0, 2 * math.pi))
+        sx = cx + (gx * np.cos(ang) - gy * np.sin(ang)) * side_px
+        sy = cy + (gx * np.sin(ang) + gy * np.cos(ang)) * side_px
+        grid = np.stack([(sx - F(width / 2.0)) * px_world, -(sy - F(height / 2.0)) * px_world,
+                         -depth + (rng.random(81).astype(F) - F(0.5)) * F(0.05) * side_px * px_world], axis=-1).astype(F)
+        # local vertex list: welded grid vertices first come first served, then duplicates for un-welded corners
+        local, verts, idx = {}, [], np.zeros((T, 3), dtype=np.uint32)
+        for t in range(T):
+            for c in range(3):
+                gv = int(tri[t, c])
+                fresh = rng.random() < unweld and len(verts) + 3 * (T - t) - c <= 255     # keep V <= 255 whatever comes
+                if not fresh and gv in local:
+                    idx[t, c] = local[gv]
+                    continue
+                if len(verts) >= 255:
+                    idx[t, c] = local.get(gv, 0)
+                    continue
+                idx[t, c] = len(verts)
+                if not fresh:
+                    local[gv] = len(verts)
+                verts.append(grid[gv])
+        V = len(verts)
+        verts = np.asarray(verts, dtype=F)
+        if mi % 7 == 3:                                                  # odd data offset
+            data_all.append(np.full(int(rng.integers(1, 4)), 0xDEADBEEF, dtype=np.uint32)); data_len += len(data_all[-1])
+        rec = np.zeros(1, dtype=abi.GPUGLTFMeshlet)
+        rec['posMin'], rec['posMax'] = verts.min(axis=0), verts.max(axis=0)
+        rec['dataOffset'] = data_len
+        rec['vertexTriangleCount'] = abi.pack_vertex_triangle_count(V, T)
+        rec['coneAxis'], rec['coneCutOff'], rec['coneApex'] = (0, 0, 1), 0.0, verts.mean(axis=0)
+        meshlets.append(rec)
+        centers.append(verts.mean(axis=0))
+        data_all.append(np.arange(vert_base, vert_base + V, dtype=np.uint32))
+        data_all.append((idx[:, 0] | (idx[:, 1] << 8) | (idx[:, 2] << 16)).astype(np.uint32))
+        data_len += V + T
+        vert_base += V
+        pos_all.append(verts)
+    M = int(n_meshlets)
+    meshlets = np.concatenate(meshlets)
+    centers = np.asarray(centers, dtype=F)
+    flat = np.concatenate(pos_all)
+    G = (M + 3) // 4
+    groups = np.zeros(G, dtype=abi.GPUGLTFMeshletGroup)
+    groups['error'], groups['parentError'] = -1.0, FLT_MAX
+    groups['meshletOffset'] = np.arange(G, dtype=np.uint32) * 4
+    groups['meshletCount'] = np.minimum(4, M - np.arange(G) * 4)
+    groups['clusterPosCenter'] = centers[::4][:G]
+    groups['parentPosCenter'] = centers[::4][:G]
+    prims = np.zeros(2, dtype=abi.GLTFPrimitiveBuffer)
+    prims['posMin'], prims['posMax'], prims['posAverage'] = flat.min(axis=0), flat.max(axis=0), flat.mean(axis=0)
+    prims['vertexCount'], prims['meshletGroupCount'] = len(flat), G
+    nodes = np.zeros(1, dtype=abi.GPUBVHNode)
+    nodes['children'] = abi.UNVALID_ID
+    nodes['bvhNodeCount'], nodes['leafMeshletGroupOffset'], nodes['leafMeshletGroupCount'] = 1, 0, G
+    scene = abi.HostScene([dict(meshlets=meshlets, positions=flat, meshletData=np.concatenate(data_all), groups=groups,
+                                groupIndices=np.arange(M, dtype=np.uint32), bvhNodes=nodes)],
+                          prims, np.array([default_material(), default_material(two_sided=1)]))
+    camera = cam.Camera((0, 0, 0), (0, 0, -1), fovy=fovy, width=width, height=height)
+    # object 0 one-sided, object 1 two-sided (same asset): every ``two_sided_every``-th command draws through object 1
+    objects = np.array([cam.fill_object(np.eye(4), camera, 0, 0), cam.fill_object(np.eye(4), camera, 1, 1)])
+    cmds = np.zeros(M, dtype=abi.DrawCmd)
+    cmds['meshletId'] = np.arange(M, dtype=np.uint32)
+    cmds['slot'] = np.arange(M, dtype=np.uint32)
+    cmds['objectId'] = (np.arange(M) % two_sided_every == two_sided_every - 1).astype(np.uint32)
+    return scene, camera, objects, cmds
+
+
 # ----------------------------------------------------------------------------------------------- city (S2/S3)
 def _face_lod_chain(origin, du, dv, patches, normal, vert_base, data_base, meshlet_base, lods, err_scale=0.05):
     """One planar face of ``patches x patches`` LOD-0 patches (8x8 quads each) with a quadtree LOD chain.

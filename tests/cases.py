@@ -24,6 +24,14 @@ def case_stream(n=3000, w=640, h=360, scale=1.0, seed=5):
                 objects=objects, w=w, h=h, lod0=n, groups=(n + 3) // 4, cmds=cmds)
 
 
+def case_ragged(n=400, w=640, h=360, seed=9):
+    """Every meshlet shape the format allows (1..128 triangles, 3..255 vertices, odd data offsets, one- and two-sided)."""
+    scene, camera, objects, cmds = synth.ragged_stream_scene(n, w, h, seed=seed)
+    view = cam.fill_view(camera)
+    return dict(name=f'ragged_{n}', scene=scene, view=view, iview=cam.fill_instance_view(view), objects=objects, w=w, h=h,
+                lod0=2 * n, groups=(n + 3) // 4, cmds=cmds)
+
+
 def city_frames(n_buildings=9, w=640, h=360, frames=4, seed=2, lods=3, low=False):
     """camera path through the procedural city; yields per-frame inputs with genuine last-frame data."""
     scene, camera, objects, info = synth.city_scene(n_buildings=n_buildings, patches=4, lods=lods, width=w, height=h, seed=seed)

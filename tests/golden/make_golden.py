@@ -16,7 +16,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 sys.path.insert(0, os.path.dirname(HERE))
 
 import oracle  # noqa: E402
-from cases import case_masked, case_s1, case_stream, city_frames, digest  # noqa: E402
+from cases import case_masked, case_ragged, case_s1, case_stream, city_frames, digest  # noqa: E402
 
 
 def entry_static(c, flags=0b111, prebuilt=False):
@@ -39,6 +39,7 @@ def main():
     for (n, w, h, s) in ((3000, 640, 360, 1.0), (1500, 512, 512, 40.0), (600, 256, 256, 2000.0)):
         g[f'stream_{n}_{w}x{h}_{s}'] = entry_static(case_stream(n, w, h, s), prebuilt=True)
     g['masked'] = entry_static(case_masked())
+    g['ragged_400'] = entry_static(case_ragged(), prebuilt=True)
     for low in (False, True):
         scene, info, frames = city_frames(low=low)
         prev = None

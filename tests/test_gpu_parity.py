@@ -93,6 +93,30 @@ def test_patch_stream_raster(gpu_ctx, n, w, h, scale):
     _assert_lists_equal(post.readback(), ofr.instance_culling(n), 'post-cull list')
 
 
+def test_ragged_meshlets(gpu_ctx):
+    """Edge cases of the meshlet format: 1..128 triangles, 3..255 vertices (V > 128 takes the large-vertex instantiation of the
+    fast raster kernel through the second work list), odd data offsets, one- and two-sided materials in one list."""
+    from cases import case_ragged
+    c = case_ragged()
+    V = c['scene'].datas[0]['meshlets']['vertexTriangleCount'] & 0xFF
+    assert (V > 128).sum() > 50 and V.max() == 255 and V.min() == 3
+    gpu_ctx.upload_scene(c['scene'])
+    ofr = oracle.Frame(c['scene'], c['view'], c['iview'], c['objects'], c['w'], c['h'])
+    n = len(c['cmds'])
+    for cmds in (c['cmds'], c['cmds'][::-1].copy(), c['cmds'][V[c['cmds']['meshletId']] > 128].copy(), c['cmds'][:1].copy()):
+        fr = runtime.Frame(gpu_ctx, c['w'], c['h'])
+        fr.begin(c['view'], c['iview'], c['objects'], c['lod0'], c['groups'])
+        lst = runtime.CmdList(gpu_ctx, n)
+        lst.upload(cmds)
+        fr.render_mesh(lst)
+        ovis, ostats = ofr.render_mesh(cmds)
+        _assert_vis_equal(fr.vis64(), ovis, f'ragged list of {len(cmds)}')
+        st = fr.raster_stats()
+        for k in ('trianglesSubmitted', 'trianglesCulled', 'trianglesClipped', 'meshletsRastered'):
+            assert st[k] == ostats[k], (k, st, ostats)
+        assert st['largeQueueOverflow'] == 0
+
+
 def test_city_frames(gpu_ctx):
     """S2-shaped city: LOD-DAG cut, cone + frustum cull, two-phase HZB with genuine last-frame history, near-plane
     clipping, large triangles; 4 frames of camera motion through the reference frame sequence."""
