@@ -264,5 +264,6 @@ int launch_visibility_mark(chord_frame* f, chord_cmdlist* post);
 int launch_lighting(chord_frame* f, chord_cmdlist* post);
 int launch_split_vis(chord_frame* f, uint32_t* vis32, float* depth32);
 int launch_decode(chord_frame* f, chord_cmdlist* post, uint32_t* triples);
+int launch_selftest_vertex_records(chord_ctx* ctx, uint32_t n, uint32_t seed, uint32_t width, uint32_t height, uint32_t clampZ, unsigned long long* dOut);
 int scan_reset(chord_ctx* ctx, uint32_t tilesNeeded);
 }

@@ -872,6 +872,20 @@ int chord_frame_wait_readbacks(chord_frame* f)
 int chord_readback_visibility32(chord_frame* f, uint32_t* host) { CHORD_REQUIRE(f && host, "null"); return readback_split(f, host, nullptr); }
 int chord_readback_depth32(chord_frame* f, float* host) { CHORD_REQUIRE(f && host, "null"); return readback_split(f, nullptr, host); }
 
+int chord_selftest_vertex_records(chord_ctx* ctx, uint32_t n, uint32_t seed, uint32_t width, uint32_t height, uint32_t depthClamp, uint64_t* hostOut3)
+{
+    CHORD_REQUIRE(ctx && hostOut3 && n > 0 && width > 0 && height > 0, "bad arguments");
+    unsigned long long* d = nullptr;
+    CHORD_CUDA(cudaMallocAsync(&d, 24, ctx->stream));
+    const unsigned long long init[3] = { 0ull, ~0ull, 0ull };
+    CHORD_CUDA(cudaMemcpyAsync(d, init, 24, cudaMemcpyHostToDevice, ctx->stream));
+    int rc = launch_selftest_vertex_records(ctx, n, seed, width, height, depthClamp, d);
+    if (rc == CHORD_OK) CHORD_CUDA(cudaMemcpyAsync(hostOut3, d, 24, cudaMemcpyDeviceToHost, ctx->stream));
+    CHORD_CUDA(cudaFreeAsync(d, ctx->stream));
+    CHORD_CUDA(cudaStreamSynchronize(ctx->stream));
+    return rc;
+}
+
 int chord_readback_decoded(chord_frame* f, chord_cmdlist* post, uint32_t* hostTriples)
 {
     CHORD_REQUIRE(f && post && hostTriples, "null");

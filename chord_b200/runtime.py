@@ -29,6 +29,7 @@ SYMBOLS = [
     'chord_frame_raster_stats', 'chord_frame_reset_stats', 'chord_frame_set_queue_limits',
     'chord_cascade_views_create', 'chord_cascade_views_destroy', 'chord_cascade_setup', 'chord_cascade_views_readback',
     'chord_cascade_views_upload', 'chord_frame_begin_cascade', 'chord_hzb_culling_generic_cascade',
+    'chord_selftest_vertex_records',
     'chord_graph_begin_capture', 'chord_graph_end_capture', 'chord_graph_launch', 'chord_graph_kernel_nodes', 'chord_graph_destroy',
 ]
 

@@ -266,6 +266,12 @@ int chord_frame_wait_readbacks(chord_frame* frame);           /* the reference's
 /* decoded (objectId, meshletId, triangleId) per pixel through a post-instance-cull list
  * (visibility_tile.hlsl:47-60); 0xFFFFFFFF triple where no geometry. */
 int chord_readback_decoded(chord_frame* frame, chord_cmdlist* postInstanceCull, uint32_t* hostTriples);
+
+/* Self test of the raster's per-vertex arithmetic (no reference counterpart): n pseudo-random clip-space vertices (arbitrary
+ * bit patterns, extreme exponents, exact pixel boundaries, frame-like distributions) go through the shared-reciprocal vertex
+ * record k_raster_fast uses and through the plain statement of mesh_raster.hlsl:84-119 + the viewport transform (three IEEE
+ * divisions); hostOut3 = { records that differ, index of the first, records that were inside the guard band }. */
+int chord_selftest_vertex_records(chord_ctx* ctx, uint32_t n, uint32_t seed, uint32_t width, uint32_t height, uint32_t depthClamp, uint64_t* hostOut3);
 int chord_readback_tile_marker(chord_frame* frame, uint32_t* hostUint4PerTile);
 enum { CHORD_GBUF_COLOR = 0, CHORD_GBUF_BASECOLOR, CHORD_GBUF_VERTEX_NORMAL, CHORD_GBUF_PIXEL_NORMAL,
        CHORD_GBUF_MOTION, CHORD_GBUF_AO_ROUGH_METAL, CHORD_GBUF_COUNT };

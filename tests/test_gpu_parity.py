@@ -93,6 +93,21 @@ def test_patch_stream_raster(gpu_ctx, n, w, h, scale):
     _assert_lists_equal(post.readback(), ofr.instance_culling(n), 'post-cull list')
 
 
+def test_vertex_record_selftest(gpu_ctx):
+    """k_raster_fast shares ONE reciprocal between x / w, y / w and z / w (the fast path of the IEEE division with a range
+    guard); its packed per-vertex record must equal the plain three-division statement bit for bit on
+    arbitrary inputs: 2^24 pseudo-random clip-space vertices per configuration incl. NaN / infinities / denormals, extreme
+    exponent gaps and vertices exactly on pixel boundaries."""
+    import ctypes as C
+    L = runtime.lib()
+    n = 1 << 24
+    for seed, (w, h, clamp) in enumerate(((3840, 2160, 0), (640, 360, 0), (2048, 2048, 1), (4096, 64, 0))):
+        out = (C.c_uint64 * 3)()
+        L.chord_selftest_vertex_records(gpu_ctx.h, C.c_uint32(n), C.c_uint32(1000 + seed), C.c_uint32(w), C.c_uint32(h), C.c_uint32(clamp), out)
+        assert out[0] == 0, f'{out[0]} vertex records differ at {w}x{h} clamp={clamp}, first at index {out[1]}'
+        assert out[2] > n // 8, 'the sample must contain plenty of vertices inside the guard band'
+
+
 def test_ragged_meshlets(gpu_ctx):
     """Edge cases of the meshlet format: 1..128 triangles, 3..255 vertices (V > 128 takes the large-vertex instantiation of the
     fast raster kernel through the second work list), odd data offsets, one- and two-sided materials in one list."""
