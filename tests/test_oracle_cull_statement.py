@@ -239,3 +239,69 @@ def test_two_phase_hzb_lists_match_the_hlsl_statement(low):
             occluded += len(r1)
         prev = ref['hzb']
     assert occluded > 0 or low
+
+
+# ------------------------------------------------------------------------------------------------ K6 triangle culls
+def triangle_cull_statement(scene, iview, objects, cmds):
+    """mesh_raster.hlsl:84-184: the four per-triangle culls of the mesh shader (#0 homogeneous back face on (x, y, w), #1 all
+    w <= 0, #2 uv box outside [0, 1], #3 no pixel centre between the rounded box corners); returns (submitted, culled).
+    ``determinant`` is pinned as the cofactor expansion along the first row with fma-fused minors."""
+    iview = np.asarray(iview).reshape(())
+    dim = np.asarray(iview['renderDimension'], dtype=F)[:2]
+    w2c = mat(iview['translatedWorldToClip'])
+    submitted = culled = 0
+    for cmd in cmds:
+        obj = objects[cmd['objectId']]
+        material = scene.materials[obj['GLTFMaterialData']]
+        if material['alphaMode'] > 1:                                                   # blend is never drawn (mesh_raster.cpp:224)
+            continue
+        if material['alphaMode'] == 1 and fma(F(1.0), F(material['baseColorFactor'][3]), -F(material['alphaCutOff'])) < 0:
+            continue                                                                    # clip() on the builtin white texture
+        prim = scene.primitives[obj['GLTFPrimitiveDetail']]
+        datas = scene.datas[prim['primitiveDatasBufferId']]
+        m = datas['meshlets'][cmd['meshletId']]
+        V, T = int(m['vertexTriangleCount'] & 0xFF), int((m['vertexTriangleCount'] >> 8) & 0xFF)
+        data = datas['meshletData'][int(m['dataOffset']):int(m['dataOffset']) + V + T]
+        pos = datas['positions'][int(prim['vertexOffset']) + data[:V].astype(np.int64)].astype(F)
+        mvp = mul_mm(w2c, mat(obj['localToTranslatedWorld']))
+        hs = mul_mv(mvp, point4(pos))                                                   # (V, 4)
+        tri = np.stack([data[V:] & 0xFF, (data[V:] >> 8) & 0xFF, (data[V:] >> 16) & 0xFF], axis=-1).astype(np.int64)
+        p = hs[tri][..., [0, 1, 3]]                                                     # (T, 3 vertices, (x, y, w))
+        c = np.zeros(T, dtype=bool)
+        if material['bTwoSided'] == 0:
+            def minor(a, b, cc, d):
+                return fma(a, b, -(cc * d).astype(F))
+            m0 = minor(p[:, 1, 1], p[:, 2, 2], p[:, 1, 2], p[:, 2, 1])
+            m1 = minor(p[:, 1, 0], p[:, 2, 2], p[:, 1, 2], p[:, 2, 0])
+            m2 = minor(p[:, 1, 0], p[:, 2, 1], p[:, 1, 1], p[:, 2, 0])
+            det = fma(p[:, 0, 2], m2, fma(-p[:, 0, 1], m1, (p[:, 0, 0] * m0).astype(F)))
+            c |= det <= 0
+        c |= (p[:, :, 2] <= 0).all(axis=1)
+        with np.errstate(invalid='ignore', divide='ignore', over='ignore'):
+            q = (p[:, :, :2] / np.abs(p[:, :, 2:3])).astype(F)
+        uv = np.stack([fma(q[..., 0], F(0.5), F(0.5)), fma(q[..., 1], F(-0.5), F(0.5))], axis=-1)
+        mx = np.fmax(uv[:, 0], np.fmax(uv[:, 1], uv[:, 2])); mn = np.fmin(uv[:, 0], np.fmin(uv[:, 1], uv[:, 2]))
+        with np.errstate(invalid='ignore'):
+            c |= (mn >= 1).any(axis=1) | (mx <= 0).any(axis=1)
+            c |= (np.rint((mn * dim).astype(F)) == np.rint((mx * dim).astype(F))).any(axis=1)      # round(): half to even
+        submitted += T
+        culled += int(c.sum())
+    return submitted, culled
+
+
+def test_triangle_cull_counts_match_the_hlsl_statement():
+    from cases import case_ragged, case_stream
+    cases = [case_stream(600, 640, 360, 1.0), case_stream(300, 512, 512, 40.0), case_stream(150, 256, 256, 2000.0), case_ragged(200)]
+    for c in cases:
+        _, st = oracle.Frame(c['scene'], c['view'], c['iview'], c['objects'], c['w'], c['h']).render_mesh(c['cmds'])
+        sub, cul = triangle_cull_statement(c['scene'], c['iview'], c['objects'], c['cmds'])
+        assert (sub, cul) == (st['trianglesSubmitted'], st['trianglesCulled']), (c['name'], sub, cul, st)
+    for low in (False, True):
+        scene, info, frames = city_frames(frames=2, low=low)
+        for f in frames:
+            fr = oracle.Frame(scene, f['view'], f['iview'], f['objects'], 640, 360)
+            post = fr.instance_culling(info['lod0MeshletCount'])
+            _, st = fr.render_mesh(post)
+            sub, cul = triangle_cull_statement(scene, f['iview'], f['objects'], post)
+            assert (sub, cul) == (st['trianglesSubmitted'], st['trianglesCulled']), (low, sub, cul, st)
+            assert cul > 0
