@@ -305,3 +305,30 @@ def test_triangle_cull_counts_match_the_hlsl_statement():
             sub, cul = triangle_cull_statement(scene, f['iview'], f['objects'], post)
             assert (sub, cul) == (st['trianglesSubmitted'], st['trianglesCulled']), (low, sub, cul, st)
             assert cul > 0
+
+
+# ------------------------------------------------------------------------------------------------------ K9 tile marker
+def test_tile_marker_matches_the_hlsl_statement():
+    """visibility_tile.hlsl:39-131: a 64-thread group gathers 32x32 px, every 2x2 threads OR their 4x4 px into one uint4 ->
+    marker texel (tx, ty) = OR of 1 << shadingType over pixels [8 tx, 8 tx + 8) x [8 ty, 8 ty + 8), clamp-to-edge gather."""
+    from chord_b200 import abi
+    scene, info, frames = city_frames(frames=2)
+    w, h = 640, 360
+    for f in frames:
+        fr = oracle.Frame(scene, f['view'], f['iview'], f['objects'], w, h)
+        post = fr.instance_culling(info['lod0MeshletCount'])
+        vis, _ = fr.render_mesh(post)
+        got = fr.visibility_mark(vis, post)
+        ids = (vis & np.uint64(0xFFFFFFFF)).astype(np.uint32)
+        _, inst = abi.decode_triangle_instance(ids)
+        inst = np.where(ids != 0, inst, 0).astype(np.int64)
+        types = np.where(ids != 0, scene.materials['materialType'][f['objects']['GLTFMaterialData'][post['objectId'][inst]]], abi.LIGHTING_TYPE_NONE)
+        mh, mw = (h + 7) // 8, (w + 7) // 8
+        ys = np.minimum(np.arange(mh * 8), h - 1); xs = np.minimum(np.arange(mw * 8), w - 1)
+        t = types[np.ix_(ys, xs)].reshape(mh, 8, mw, 8).transpose(0, 2, 1, 3).reshape(mh, mw, 64).astype(np.uint64)
+        want = np.zeros((mh, mw, 4), dtype=np.uint32)
+        for k in range(4):
+            sel = (t // 32) == k
+            want[..., k] = np.bitwise_or.reduce(np.where(sel, np.uint64(1) << (t % 32), 0), axis=-1).astype(np.uint32)
+        assert np.array_equal(got, want)
+        assert (want[..., 0] & 2).any() and (want[..., 0] & 1).any()         # PBR tiles and empty (sky) tiles both present
