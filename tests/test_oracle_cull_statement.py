@@ -332,3 +332,78 @@ def test_tile_marker_matches_the_hlsl_statement():
             want[..., k] = np.bitwise_or.reduce(np.where(sel, np.uint64(1) << (t % 32), 0), axis=-1).astype(np.uint32)
         assert np.array_equal(got, want)
         assert (want[..., 0] & 2).any() and (want[..., 0] & 1).any()         # PBR tiles and empty (sky) tiles both present
+
+
+# ------------------------------------------------------------------------------------- hzbCullingGeneric (shadow views)
+def hzb_cull_generic_statement(scene, view, hzb_view, objects, cmds, hzb, extent_scale, use_last_frame=False, flags=0b111):
+    """hzb_culling_generic.hlsl:37-172: the list against the HZB of ANOTHER view; the object matrix is re-based from the
+    main camera's translated world to that view's (double subtraction of the two camera positions, then float)."""
+    view = np.asarray(view).reshape(())
+    hv = np.asarray(hzb_view).reshape(())
+    dim = np.asarray(hv['renderDimension'], dtype=F)
+    w2c = mat(hv['translatedWorldToClip'])
+    rel = (np.asarray(view['cameraWorldPos'], dtype=np.uint32).view(np.float64)[:3, 0] - np.asarray(hv['cameraWorldPos'], dtype=np.uint32).view(np.float64)[:3, 0]).astype(F)
+    chain = hzb['min'].view(np.float16)
+    mip0w = hzb['mip0'][0]
+    out = []
+    for cmd in cmds:
+        obj = objects[cmd['objectId']]
+        prim = scene.primitives[obj['GLTFPrimitiveDetail']]
+        m = scene.datas[prim['primitiveDatasBufferId']]['meshlets'][cmd['meshletId']]
+        visible = True
+        if flags & 2:
+            pmin, pmax = m['posMin'].astype(F), m['posMax'].astype(F)
+            center = ((pmin + pmax) * F(0.5)).astype(F)
+            extent = (pmax - center).astype(F)
+            l2w = mat(obj['localToTranslatedWorldLastFrame'] if use_last_frame else obj['localToTranslatedWorld']).copy()
+            l2w[:3, 3] = (l2w[:3, 3] + rel).astype(F)
+            hs = mul_mv(mul_mm(w2c, l2w), point4(fma(extent[None, :], EXTENT_FACTOR, center[None, :])))
+            with np.errstate(invalid='ignore', divide='ignore', over='ignore'):
+                ndc = (hs[:, :3] / hs[:, 3:4]).astype(F)
+            uvz = np.stack([fma(ndc[:, 0], F(0.5), F(0.5)), fma(ndc[:, 1], F(-0.5), F(0.5)), ndc[:, 2]], axis=-1)
+            mn = np.full(3, 10.0, dtype=F); mx = np.full(3, -10.0, dtype=F)
+            for k in range(8):
+                mn = np.fmin(mn, uvz[k]); mx = np.fmax(mx, uvz[k])
+            if bool(((uvz < 1.0) & (uvz > 0.0)).all()):
+                es = F(extent_scale)
+                rect = np.concatenate([fma(mn[:2], dim[:2], (es * F(-0.5))), fma(mx[:2], dim[:2], (es * F(0.5)))]).astype(np.int64)
+                rect[:2] = np.maximum(0, rect[:2])
+                rect[2:] = np.minimum((dim[:2] - F(1.0)).astype(np.int64), rect[2:])
+                if (rect[2:] < rect[:2]).any():
+                    visible = False
+                else:
+                    c0 = rect >> 1
+                    level = max(0, max(_firstbithigh(c0[2] - c0[0]), _firstbithigh(c0[3] - c0[1])))
+                    if (((c0[2:] >> level) - (c0[:2] >> level)) >= 2).any():
+                        level += 1
+                    c = c0 >> level
+                    mw = max(mip0w >> level, 1)
+                    base = int(hzb['offsets'][level])
+                    zmin = F(10.0)
+                    for x in range(2):
+                        for y in range(2):
+                            zmin = min(zmin, F(chain[base + int(min(c[3], c[1] + y)) * mw + int(min(c[2], c[0] + x))]))
+                    if zmin > mx[2]:
+                        visible = False
+        if visible:
+            out.append((cmd['objectId'], cmd['meshletId'], cmd['slot']))
+    return np.array(out, dtype=np.uint32).reshape(-1, 3)
+
+
+def test_generic_hzb_lists_match_the_hlsl_statement():
+    from cases import case_stream
+    from chord_b200 import camera as cam
+    from test_oracle_shadow import STREAM_LIGHT, _stream_cfg
+    c = case_stream(1200, 256, 256, 100.0)
+    scene, lod0 = c['scene'], c['lod0']
+    views = cam.cascade_views(c['view'], STREAM_LIGHT, _stream_cfg())
+    far = oracle.Frame(scene, c['view'], views[3], c['objects'], 256, 256)
+    depth_far, _ = far.render_mesh_depth(far.instance_culling(lod0))
+    hzb = far.build_hzb(depth_far, True, False, False)
+    near = oracle.Frame(scene, c['view'], views[2], c['objects'], 256, 256)
+    post = near.instance_culling(lod0)
+    for scale in (1.5, 8.0):
+        got = _as_triples(near.hzb_culling_generic(hzb, views[3], scale, False, post))
+        want = hzb_cull_generic_statement(scene, c['view'], views[3], c['objects'], post, hzb, scale)
+        assert np.array_equal(got, want), (scale, len(got), len(want))
+        assert 0 < len(got) < len(post)
