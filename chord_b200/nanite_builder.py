@@ -44,23 +44,43 @@ def _tri_adjacency(tris):
     return adj, edge
 
 
-def build_meshlets(tris):
-    """Greedy region growing: contiguous clusters of <= 128 triangles / <= 255 vertices. Returns list of triangle-index arrays."""
+def build_meshlets(tris, pos=None):
+    """Greedy region growing: clusters of <= 128 triangles / <= 255 vertices, grown breadth first over shared edges.  When the
+    frontier runs dry before the meshlet is full and positions are given, growth continues from the nearest unused triangle
+    (meshopt_buildMeshlets does the same through its kd-tree), which keeps the fill rate near 100 % -- one meshlet is one warp
+    iteration of the raster, so half-empty meshlets cost throughput.  Returns a list of triangle-index arrays."""
     tris = np.asarray(tris)
     adj, _ = _tri_adjacency(tris)
     used = np.zeros(len(tris), dtype=bool)
+    cent = None if pos is None else np.asarray(pos, dtype=np.float64)[tris].mean(axis=1)
     out = []
     order = np.argsort(tris.min(axis=1), kind='stable')          # deterministic seeds
-    for seed in order:
-        if used[seed]:
-            continue
+    cursor = 0
+    while True:
+        while cursor < len(order) and used[order[cursor]]:
+            cursor += 1
+        if cursor >= len(order):
+            break
+        seed = order[cursor]
+        if cent is not None and out:                              # start next to the previous meshlet: compact neighbours
+            free = np.nonzero(~used)[0]
+            seed = free[np.argmin(((cent[free] - cent[out[-1]].mean(axis=0)) ** 2).sum(axis=1))]
         cluster, verts, frontier = [], set(), [seed]
-        while frontier and len(cluster) < MAX_T:
+        while len(cluster) < MAX_T:
+            if not frontier:
+                if cent is None or not cluster:
+                    break
+                free = np.nonzero(~used)[0]
+                if len(free) == 0:
+                    break
+                frontier = [free[np.argmin(((cent[free] - cent[cluster].mean(axis=0)) ** 2).sum(axis=1))]]
             t = frontier.pop(0)
             if used[t]:
                 continue
             nv = verts | set(tris[t].tolist())
             if len(nv) > MAX_V:
+                if not frontier:
+                    break
                 continue
             used[t] = True
             cluster.append(t)
@@ -121,6 +141,7 @@ def _simplify(pos, tris, target_count):
             locked.add(a); locked.add(b)
     verts = sorted({v for t in tris for v in t})
     Q = {v: np.zeros((4, 4)) for v in verts}
+    W = {v: 0.0 for v in verts}
     for a, b, c in tris:
         p0, p1, p2 = pos[a].astype(np.float64), pos[b].astype(np.float64), pos[c].astype(np.float64)
         n = np.cross(p1 - p0, p2 - p0)
@@ -129,9 +150,11 @@ def _simplify(pos, tris, target_count):
             continue
         n /= area
         pl = np.append(n, -np.dot(n, p0))
-        K = np.outer(pl, pl) * area
+        wgt = np.sqrt(area)                       # meshoptimizer's quadricFromTriangle: sqrt(|cross|) so that the error scales linearly
+        K = np.outer(pl, pl) * wgt
         for v in (a, b, c):
             Q[v] += K
+            W[v] += wgt
     vt = defaultdict(set)
     for i, t in enumerate(tris):
         for v in t:
@@ -139,10 +162,12 @@ def _simplify(pos, tris, target_count):
     alive = [True] * len(tris)
 
     def cost(src, dst):
-        """area-weighted squared distance of dst to the planes accumulated around src and dst"""
+        """weighted MEAN squared distance of dst to the planes accumulated around src and dst (meshoptimizer's quadricError:
+        v Q v / Q.w), so that its square root is a length in object units"""
         q = Q[src] + Q[dst]
+        w = W[src] + W[dst]
         p = np.append(pos[dst].astype(np.float64), 1.0)
-        return float(max(p @ q @ p, 0.0)), 0.0
+        return (float(abs(p @ q @ p)) / w if w > 0 else 0.0), 0.0
 
     heap = []
     for (a, b) in edge_count:
@@ -190,6 +215,7 @@ def _simplify(pos, tris, target_count):
                 vt[dst].add(ti)
         remap[src] = dst
         Q[dst] = Q[dst] + Q[src]
+        W[dst] = W[dst] + W[src]
         max_err = max(max_err, c)
         nb = set()
         for ti in vt[dst]:
@@ -207,33 +233,56 @@ def _simplify(pos, tris, target_count):
             a, b, c = (find(v) for v in t)
             if a != b and b != c and a != c:
                 out.append((a, b, c))
-    # quadric cost is area-weighted squared distance; report a length (meshopt_SimplifyErrorAbsolute)
-    total_area = sum(np.linalg.norm(np.cross(pos[b] - pos[a], pos[c] - pos[a])) for a, b, c in tris) * 0.5 + 1e-30
-    return np.array(out, dtype=np.int64).reshape(-1, 3), float(np.sqrt(max_err / total_area))
+    # the collapse cost is a mean squared distance: report its root, a length in object units (meshopt_SimplifyErrorAbsolute)
+    return np.array(out, dtype=np.int64).reshape(-1, 3), float(np.sqrt(max_err))
+
+
+def _bounding_sphere(points):
+    """meshoptimizer's computeBoundingSphere (Ritter: the most distant pair of the six axis extrema, then grown point by point
+    in input order), float32 like the original."""
+    F = np.float32
+    p = np.asarray(points, dtype=F)
+    pmin, pmax = p.argmin(axis=0), p.argmax(axis=0)                       # first extremum per axis, like the strict < / > scan
+    d2 = [F(((p[pmax[k]] - p[pmin[k]]) ** 2).sum()) for k in range(3)]
+    k = 0
+    for axis in range(3):
+        if d2[axis] > d2[k]:
+            k = axis
+    center = ((p[pmin[k]] + p[pmax[k]]) / F(2)).astype(F)
+    radius = F(np.sqrt(d2[k]) / F(2)) if d2[k] > 0 else F(0)
+    for q in p:
+        dd = F(((q - center) ** 2).sum())
+        if dd > radius * radius:
+            d = F(np.sqrt(dd))
+            kk = F(0.5) + (radius / d) / F(2)
+            center = (center * kk + q * (F(1) - kk)).astype(F)
+            radius = F((radius + d) / F(2))
+    return center, radius
 
 
 def _cone(pos, tris):
-    """meshopt_computeMeshletBounds normal cone: (axis, cutoff, apex)."""
-    p0, p1, p2 = pos[tris[:, 0]], pos[tris[:, 1]], pos[tris[:, 2]]
-    n = np.cross(p1 - p0, p2 - p0).astype(np.float64)
-    ln = np.linalg.norm(n, axis=1)
-    ok = ln > 0
-    center = 0.5 * (pos[np.unique(tris)].min(axis=0) + pos[np.unique(tris)].max(axis=0)).astype(np.float64)
+    """meshopt_computeClusterBounds normal cone, restated (meshopt_clusterizer.cpp:712-850; checked against the reference's
+    own build of it in tests/test_nanite_builder_ref.py): the axis is the centre of the bounding sphere of the triangle
+    normals, the apex lies on the ray from the bounding-sphere centre of the corners against the axis.  -> (axis, cutoff, apex)."""
+    F = np.float32
+    p0, p1, p2 = pos[tris[:, 0]].astype(F), pos[tris[:, 1]].astype(F), pos[tris[:, 2]].astype(F)
+    n = np.cross(p1 - p0, p2 - p0).astype(F)
+    area = np.sqrt((n * n).sum(axis=1)).astype(F)
+    ok = area > 0
     if not ok.any():
-        return np.zeros(3), 1.0, center
-    n = n[ok] / ln[ok, None]
-    axis = n.sum(axis=0)
-    la = np.linalg.norm(axis)
-    if la < 1e-12:
-        return np.zeros(3), 1.0, center
-    axis /= la
-    dp = n @ axis
-    mindp = dp.min()
-    if mindp <= 0.1:
-        return np.zeros(3), 1.0, center          # degenerate cone: never culls (dot(..., 0) >= 1 is false)
-    c0 = p0[ok].astype(np.float64)
-    maxt = np.max(((center[None] - c0) * n).sum(axis=1) / dp)
-    return axis, float(np.sqrt(max(1.0 - mindp * mindp, 0.0))), center - axis * maxt
+        return np.zeros(3), 0.0, np.zeros(3)                          # degenerate cluster: cone data is 0 (trivial reject upstream)
+    n = (n[ok] / area[ok, None]).astype(F)
+    corners = np.stack([p0[ok], p1[ok], p2[ok]], axis=1).reshape(-1, 3)
+    center, _ = _bounding_sphere(corners)
+    axis, _ = _bounding_sphere(n)
+    la = F(np.sqrt((axis * axis).sum()))
+    axis = (axis * (F(0) if la == 0 else F(1) / la)).astype(F)
+    dp = (n * axis).sum(axis=1).astype(F)
+    mindp = min(F(1), dp.min())
+    if mindp <= F(0.1):
+        return np.zeros(3), 1.0, np.zeros(3)                          # wider than ~168 degrees: never culls (cutoff 1, axis 0)
+    maxt = max(F(0), F((((center[None] - p0[ok]) * n).sum(axis=1) / dp).max()))
+    return axis.astype(np.float64), float(np.sqrt(F(1) - mindp * mindp)), (center - axis * maxt).astype(np.float64)
 
 
 class NaniteAsset:
@@ -253,7 +302,7 @@ def build(positions, triangles, normals=None, uv0=None, max_lods=MAX_LODS):
     if uv0 is None:
         uv0 = np.zeros((len(pos), 2), dtype=np.float32)
     meshlets = []          # dict(tris (k,3) global vertex ids, lod, error, center, parent_error, parent_center)
-    cur = [dict(tris=tris[ts], lod=0, error=-1.0, center=np.zeros(3)) for ts in build_meshlets(tris)]
+    cur = [dict(tris=tris[ts], lod=0, error=-1.0, center=np.zeros(3)) for ts in build_meshlets(tris, pos)]
     stats = []
     for lod in range(max_lods - 1):
         stats.append((lod, len(cur), int(sum(len(m['tris']) for m in cur))))
@@ -273,7 +322,7 @@ def build(positions, triangles, normals=None, uv0=None, max_lods=MAX_LODS):
                 center = 0.5 * (pos[used].max(axis=0) + pos[used].min(axis=0))
                 for i in g:
                     cur[i]['parent_error'], cur[i]['parent_center'] = cerr, center
-                for ts in build_meshlets(simp):
+                for ts in build_meshlets(simp, pos):
                     nxt.append(dict(tris=simp[ts], lod=lod + 1, error=cerr, center=center))
         meshlets += cur
         if not nxt:

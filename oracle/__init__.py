@@ -22,6 +22,44 @@ def build(force=False):
     return _SO
 
 
+REFERENCE = os.environ.get('CHORD_REFERENCE', '/root/reference')
+_REF_SO = os.path.join(_HERE, '_ref', 'libmeshopt_ref.so')
+
+
+def build_ref(force=False):
+    """oracle/_ref/libmeshopt_ref.so: the reference's vendored meshoptimizer 0.21 compiled from its sources in place (the
+    only part of the reference that builds offline) + oracle/meshopt_ref_wrapper.cpp.  Returns the path, or None when
+    neither the reference tree nor a prebuilt library is there (the GPU box only has what travelled with the repo)."""
+    have_src = os.path.isdir(os.path.join(REFERENCE, 'source', 'asset', 'meshoptimizer'))
+    wrapper = os.path.join(_HERE, 'meshopt_ref_wrapper.cpp')
+    stale = os.path.exists(_REF_SO) and os.path.getmtime(wrapper) > os.path.getmtime(_REF_SO)
+    if have_src and (force or stale or not os.path.exists(_REF_SO)):
+        try:
+            subprocess.check_call(['make', '-C', _HERE, '-s', 'ref', f'REFERENCE={REFERENCE}'])
+        except (subprocess.CalledProcessError, OSError) as e:        # a checker that cannot be built is skipped, never fatal
+            print(f'oracle/_ref not built: {e}')
+    return _REF_SO if os.path.exists(_REF_SO) else None
+
+
+_ref_lib = None
+
+
+def meshopt_ref():
+    """ctypes handle of oracle/_ref/libmeshopt_ref.so or None (tests skip then)."""
+    global _ref_lib
+    if _ref_lib is None:
+        so = build_ref()
+        if so is None:
+            return None
+        L = C.CDLL(so)
+        L.meshopt_ref_build_meshlets.restype = C.c_size_t
+        L.meshopt_ref_build_meshlets_bound.restype = C.c_size_t
+        L.meshopt_ref_simplify.restype = C.c_size_t
+        L.meshopt_ref_simplify_scale.restype = C.c_float
+        _ref_lib = L
+    return _ref_lib
+
+
 class _Frame(C.Structure):
     _fields_ = [('scene', C.c_void_p), ('view', C.c_void_p), ('iview', C.c_void_p), ('objects', C.c_void_p),
                 ('objectCount', C.c_uint32), ('width', C.c_uint32), ('height', C.c_uint32),
