@@ -31,9 +31,9 @@ def build_ref(force=False):
     only part of the reference that builds offline) + oracle/meshopt_ref_wrapper.cpp.  Returns the path, or None when
     neither the reference tree nor a prebuilt library is there (the GPU box only has what travelled with the repo)."""
     have_src = os.path.isdir(os.path.join(REFERENCE, 'source', 'asset', 'meshoptimizer'))
-    wrapper = os.path.join(_HERE, 'meshopt_ref_wrapper.cpp')
-    stale = os.path.exists(_REF_SO) and os.path.getmtime(wrapper) > os.path.getmtime(_REF_SO)
-    if have_src and (force or stale or not os.path.exists(_REF_SO)):
+    pairs = ((os.path.join(_HERE, 'meshopt_ref_wrapper.cpp'), _REF_SO), (os.path.join(_HERE, 'tinygltf_ref_wrapper.cpp'), os.path.join(_HERE, '_ref', 'libtinygltf_ref.so')))
+    stale = any(not os.path.exists(so) or os.path.getmtime(src) > os.path.getmtime(so) for src, so in pairs)
+    if have_src and (force or stale):
         try:
             subprocess.check_call(['make', '-C', _HERE, '-s', 'ref', f'REFERENCE={REFERENCE}'])
         except (subprocess.CalledProcessError, OSError) as e:        # a checker that cannot be built is skipped, never fatal
@@ -58,6 +58,24 @@ def meshopt_ref():
         L.meshopt_ref_simplify_scale.restype = C.c_float
         _ref_lib = L
     return _ref_lib
+
+
+_TG_SO = os.path.join(_HERE, '_ref', 'libtinygltf_ref.so')
+_tg_lib = None
+
+
+def tinygltf_ref():
+    """ctypes handle of oracle/_ref/libtinygltf_ref.so (the reference's glTF parser behind oracle/tinygltf_ref_wrapper.cpp) or None."""
+    global _tg_lib
+    if _tg_lib is None:
+        build_ref()
+        if not os.path.exists(_TG_SO):
+            return None
+        L = C.CDLL(_TG_SO)
+        L.tg_last_error.restype = C.c_char_p
+        L.tg_accessor_read.restype = C.c_longlong
+        _tg_lib = L
+    return _tg_lib
 
 
 class _Frame(C.Structure):
