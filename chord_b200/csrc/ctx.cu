@@ -79,6 +79,7 @@ using namespace chordb;
 extern "C" {
 
 const char* chord_last_error(void) { return g_error; }
+
 int chord_abi_version(void) { return CHORD_B200_ABI_VERSION; }
 
 int chord_ctx_create(int device, chord_ctx** out)
@@ -93,11 +94,16 @@ int chord_ctx_create(int device, chord_ctx** out)
     CHORD_CUDA(cudaGetDeviceProperties(&prop, device));
     if (prop.major != 10) { set_error("libchord_b200 is built for sm_100a only; device is sm_%d%d", prop.major, prop.minor); return CHORD_ERR_NO_DEVICE; }
     chord_ctx* c = (chord_ctx*)calloc(1, sizeof(chord_ctx));
+    CHORD_REQUIRE(c != nullptr, "out of host memory");
     c->device = device;
     c->switchFlags = 0b111;
     c->smCount = prop.multiProcessorCount;
-    CHORD_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-    CHORD_CUDA(cudaMalloc(&c->scanTicket, sizeof(uint32_t)));
+    const int rc = [&]() -> int {
+        CHORD_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        CHORD_CUDA(cudaMalloc(&c->scanTicket, sizeof(uint32_t)));
+        return CHORD_OK;
+    }();
+    if (rc != CHORD_OK) { chord_ctx_destroy(c); return rc; }      // nothing half-built survives a failed create
     *out = c;
     return CHORD_OK;
 }
@@ -106,7 +112,7 @@ void chord_ctx_destroy(chord_ctx* ctx)
 {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    cudaStreamSynchronize(ctx->stream);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     free_scene(ctx);
     if (ctx->scanStatus) cudaFree(ctx->scanStatus);
     if (ctx->scanTicket) cudaFree(ctx->scanTicket);
@@ -114,7 +120,7 @@ void chord_ctx_destroy(chord_ctx* ctx)
     if (ctx->lutIrradiance) cudaFree(ctx->lutIrradiance);
     cudaFree(ctx->dTextures); cudaFree(ctx->dSamplers); cudaFree(ctx->dTexels);
     if (ctx->uploadStream) { cudaStreamSynchronize(ctx->uploadStream); cudaStreamDestroy(ctx->uploadStream); }
-    cudaStreamDestroy(ctx->stream);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
     free(ctx);
 }
 
@@ -172,11 +178,17 @@ int chord_cmdlist_create(chord_ctx* ctx, uint32_t capacity, chord_cmdlist** out)
     CHORD_REQUIRE(ctx && out, "null");
     CHORD_REQUIRE(capacity > 0, "capacity");
     CHORD_CUDA(cudaSetDevice(ctx->device));
+    *out = nullptr;
     chord_cmdlist* l = (chord_cmdlist*)calloc(1, sizeof(chord_cmdlist));
+    CHORD_REQUIRE(l != nullptr, "out of host memory");
     l->ctx = ctx; l->capacity = capacity;
-    CHORD_CUDA(cudaMalloc(&l->count, 16));
-    CHORD_CUDA(cudaMalloc(&l->cmds, sizeof(chord_draw_cmd) * (size_t)capacity + 64));
-    CHORD_CUDA(cudaMemsetAsync(l->count, 0, 16, ctx->stream));
+    const int rc = [&]() -> int {
+        CHORD_CUDA(cudaMalloc(&l->count, 16));
+        CHORD_CUDA(cudaMalloc(&l->cmds, sizeof(chord_draw_cmd) * (size_t)capacity + 64));
+        CHORD_CUDA(cudaMemsetAsync(l->count, 0, 16, ctx->stream));
+        return CHORD_OK;
+    }();
+    if (rc != CHORD_OK) { chord_cmdlist_destroy(l); return rc; }
     *out = l;
     return CHORD_OK;
 }
@@ -268,7 +280,9 @@ int chord_hzb_create(chord_ctx* ctx, uint32_t depthW, uint32_t depthH, chord_hzb
     CHORD_REQUIRE(ctx && out, "null");
     CHORD_REQUIRE(depthW >= CHORD_MIN_RENDER_DIM && depthH >= CHORD_MIN_RENDER_DIM && depthW <= CHORD_MAX_RENDER_DIM && depthH <= CHORD_MAX_RENDER_DIM, "render dimension outside [64, 4096] (renderer.h:52-53)");
     CHORD_CUDA(cudaSetDevice(ctx->device));
+    *out = nullptr;
     chord_hzb* h = (chord_hzb*)calloc(1, sizeof(chord_hzb));
+    CHORD_REQUIRE(h != nullptr, "out of host memory");
     h->ctx = ctx; h->depthW = depthW; h->depthH = depthH;
     // hzb.cpp:49-56
     uint32_t tw = next_pot(depthW) / 2, th = next_pot(depthH) / 2;
@@ -286,12 +300,16 @@ int chord_hzb_create(chord_ctx* ctx, uint32_t depthW, uint32_t depthH, chord_hzb
         o += (uint64_t)w * hh;
     }
     h->totalTexels = o;
-    CHORD_CUDA(cudaMalloc(&h->minChain, sizeof(__half) * o));
-    CHORD_CUDA(cudaMalloc(&h->maxChain, sizeof(__half) * o));
-    CHORD_CUDA(cudaMalloc(&h->validRange, 16));
-    CHORD_CUDA(cudaMalloc(&h->counter, 16));
-    CHORD_CUDA(cudaMemsetAsync(h->minChain, 0, sizeof(__half) * o, ctx->stream));
-    CHORD_CUDA(cudaMemsetAsync(h->maxChain, 0, sizeof(__half) * o, ctx->stream));
+    const int rc = [&]() -> int {
+        CHORD_CUDA(cudaMalloc(&h->minChain, sizeof(__half) * o));
+        CHORD_CUDA(cudaMalloc(&h->maxChain, sizeof(__half) * o));
+        CHORD_CUDA(cudaMalloc(&h->validRange, 16));
+        CHORD_CUDA(cudaMalloc(&h->counter, 16));
+        CHORD_CUDA(cudaMemsetAsync(h->minChain, 0, sizeof(__half) * o, ctx->stream));
+        CHORD_CUDA(cudaMemsetAsync(h->maxChain, 0, sizeof(__half) * o, ctx->stream));
+        return CHORD_OK;
+    }();
+    if (rc != CHORD_OK) { chord_hzb_destroy(h); return rc; }
     *out = h;
     return CHORD_OK;
 }
@@ -341,26 +359,32 @@ int chord_frame_create(chord_ctx* ctx, uint32_t width, uint32_t height, chord_fr
     CHORD_REQUIRE(ctx && out, "null");
     CHORD_REQUIRE(width >= CHORD_MIN_RENDER_DIM && height >= CHORD_MIN_RENDER_DIM && width <= CHORD_MAX_RENDER_DIM && height <= CHORD_MAX_RENDER_DIM, "render dimension outside [64, 4096] (renderer.h:52-53)");
     CHORD_CUDA(cudaSetDevice(ctx->device));
+    *out = nullptr;
     chord_frame* f = (chord_frame*)calloc(1, sizeof(chord_frame));
+    CHORD_REQUIRE(f != nullptr, "out of host memory");
     f->ctx = ctx; f->width = width; f->height = height;
     f->tile = chord_rect{0, 0, width, height};
-    CHORD_CUDA(cudaMalloc(&f->vis64, sizeof(unsigned long long) * (size_t)width * height));
-    CHORD_CUDA(cudaMalloc(&f->totalGroups, 16));
-    CHORD_CUDA(cudaMalloc(&f->bvhCtrl, 32));
-    CHORD_CUDA(cudaMemsetAsync(f->bvhCtrl, 0, 32, ctx->stream));
-    f->largeTriCapacity = kLargeTriCapacity; f->largeItemCapacity = kLargeItemCapacity;
-    CHORD_CUDA(cudaMalloc(&f->largeTris, (size_t)48 * f->largeTriCapacity));
-    CHORD_CUDA(cudaMalloc(&f->largeItems, (size_t)8 * f->largeItemCapacity));
-    CHORD_CUDA(cudaMalloc(&f->largeCounters, 64));
-    f->deferredCapacity = kDeferredCapacity;
-    CHORD_CUDA(cudaMalloc(&f->deferred, (size_t)64 * f->deferredCapacity));
-    CHORD_CUDA(cudaMalloc(&f->stats, sizeof(chord_raster_stats)));
-    CHORD_CUDA(cudaMemsetAsync(f->stats, 0, sizeof(chord_raster_stats), ctx->stream));
-    CHORD_CUDA(cudaMemsetAsync(f->largeCounters, 0, 64, ctx->stream));
-    const uint32_t mw = (width + 7) / 8, mh = (height + 7) / 8;
-    CHORD_CUDA(cudaMalloc(&f->tileMarker, (size_t)16 * mw * mh));
-    CHORD_CUDA(cudaMalloc(&f->tileList, (size_t)8 * mw * mh));
-    CHORD_CUDA(cudaMalloc(&f->tileCount, 16));
+    const int rc = [&]() -> int {
+        CHORD_CUDA(cudaMalloc(&f->vis64, sizeof(unsigned long long) * (size_t)width * height));
+        CHORD_CUDA(cudaMalloc(&f->totalGroups, 16));
+        CHORD_CUDA(cudaMalloc(&f->bvhCtrl, 32));
+        CHORD_CUDA(cudaMemsetAsync(f->bvhCtrl, 0, 32, ctx->stream));
+        f->largeTriCapacity = kLargeTriCapacity; f->largeItemCapacity = kLargeItemCapacity;
+        CHORD_CUDA(cudaMalloc(&f->largeTris, (size_t)48 * f->largeTriCapacity));
+        CHORD_CUDA(cudaMalloc(&f->largeItems, (size_t)8 * f->largeItemCapacity));
+        CHORD_CUDA(cudaMalloc(&f->largeCounters, 64));
+        f->deferredCapacity = kDeferredCapacity;
+        CHORD_CUDA(cudaMalloc(&f->deferred, (size_t)64 * f->deferredCapacity));
+        CHORD_CUDA(cudaMalloc(&f->stats, sizeof(chord_raster_stats)));
+        CHORD_CUDA(cudaMemsetAsync(f->stats, 0, sizeof(chord_raster_stats), ctx->stream));
+        CHORD_CUDA(cudaMemsetAsync(f->largeCounters, 0, 64, ctx->stream));
+        const uint32_t mw = (width + 7) / 8, mh = (height + 7) / 8;
+        CHORD_CUDA(cudaMalloc(&f->tileMarker, (size_t)16 * mw * mh));
+        CHORD_CUDA(cudaMalloc(&f->tileList, (size_t)8 * mw * mh));
+        CHORD_CUDA(cudaMalloc(&f->tileCount, 16));
+        return CHORD_OK;
+    }();
+    if (rc != CHORD_OK) { chord_frame_destroy(f); return rc; }
     *out = f;
     return CHORD_OK;
 }
@@ -612,10 +636,16 @@ int chord_cascade_views_create(chord_ctx* ctx, chord_cascade_views** out)
 {
     CHORD_REQUIRE(ctx && out, "null");
     CHORD_CUDA(cudaSetDevice(ctx->device));
+    *out = nullptr;
     chord_cascade_views* v = (chord_cascade_views*)calloc(1, sizeof(chord_cascade_views));
+    CHORD_REQUIRE(v != nullptr, "out of host memory");
     v->ctx = ctx;
-    CHORD_CUDA(cudaMalloc(&v->dViews, sizeof(chord_InstanceCullingViewInfo) * CHORD_MAX_CASCADE_COUNT));
-    CHORD_CUDA(cudaMemsetAsync(v->dViews, 0, sizeof(chord_InstanceCullingViewInfo) * CHORD_MAX_CASCADE_COUNT, ctx->stream));
+    const int rc = [&]() -> int {
+        CHORD_CUDA(cudaMalloc(&v->dViews, sizeof(chord_InstanceCullingViewInfo) * CHORD_MAX_CASCADE_COUNT));
+        CHORD_CUDA(cudaMemsetAsync(v->dViews, 0, sizeof(chord_InstanceCullingViewInfo) * CHORD_MAX_CASCADE_COUNT, ctx->stream));
+        return CHORD_OK;
+    }();
+    if (rc != CHORD_OK) { chord_cascade_views_destroy(v); return rc; }
     *out = v;
     return CHORD_OK;
 }
@@ -705,15 +735,19 @@ int chord_graph_end_capture(chord_ctx* ctx, chord_graph** out)
     g->ctx = ctx; g->graph = graph;
     g->pinned = ctx->captureAllocs; g->nPinned = ctx->nCaptureAllocs;
     ctx->captureAllocs = nullptr; ctx->nCaptureAllocs = 0;
-    size_t n = 0;
-    CHORD_CUDA(cudaGraphGetNodes(graph, nullptr, &n));
-    std::vector<cudaGraphNode_t> nodes(n);
-    if (n) CHORD_CUDA(cudaGraphGetNodes(graph, nodes.data(), &n));
-    for (size_t i = 0; i < n; i++) {
-        cudaGraphNodeType t;
-        if (cudaGraphNodeGetType(nodes[i], &t) == cudaSuccess && t == cudaGraphNodeTypeKernel) g->kernelNodes++;
-    }
-    CHORD_CUDA(cudaGraphInstantiate(&g->exec, graph, 0));
+    const int rc = [&]() -> int {
+        size_t n = 0;
+        CHORD_CUDA(cudaGraphGetNodes(graph, nullptr, &n));
+        std::vector<cudaGraphNode_t> nodes(n);
+        if (n) CHORD_CUDA(cudaGraphGetNodes(graph, nodes.data(), &n));
+        for (size_t i = 0; i < n; i++) {
+            cudaGraphNodeType t;
+            if (cudaGraphNodeGetType(nodes[i], &t) == cudaSuccess && t == cudaGraphNodeTypeKernel) g->kernelNodes++;
+        }
+        CHORD_CUDA(cudaGraphInstantiate(&g->exec, graph, 0));
+        return CHORD_OK;
+    }();
+    if (rc != CHORD_OK) { chord_graph_destroy(g); return rc; }     // frees the graph and the pinned uniform snapshots
     *out = g;
     return CHORD_OK;
 }
