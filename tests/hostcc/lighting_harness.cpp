@@ -7,8 +7,6 @@
 
 #include <vector>
 
-uint3 threadIdx, blockIdx;
-dim3 blockDim, gridDim;
 namespace chordb { void set_error(const char*, ...) {} }
 
 #include "resolve_device.inc"
@@ -16,12 +14,7 @@ namespace chordb { void set_error(const char*, ...) {} }
 using namespace chordb;
 
 template <typename K>
-static void run_grid(unsigned grid, unsigned block, K&& body)
-{
-    gridDim.x = grid; blockDim.x = block;
-    for (unsigned b = 0; b < grid; b++)
-        for (unsigned t = 0; t < block; t++) { blockIdx.x = b; threadIdx.x = t; body(); }
-}
+static void run_grid(unsigned grid, unsigned block, K&& body) { hostcc::launch(dim3(grid), dim3(block), body); }
 
 extern "C" int hostcc_lighting(const chord_scene_desc* desc, const chord_PerframeCameraView* view, const chord_InstanceCullingViewInfo* iview,
                                const chord_GPUObjectGLTFPrimitive* objects, uint32_t nObjects, uint32_t W, uint32_t H,

@@ -1,0 +1,118 @@
+"""The GPU parity cases (tests/test_gpu_parity.py), executed WITHOUT a GPU on the source text of the CUDA kernels.
+
+TEST INFRASTRUCTURE, not a fallback: tests/hostcc/ translates chord_b200/csrc/*.cu for g++ (kernel launches become a
+coroutine-per-CUDA-thread executor, the inline-PTX helpers become what the instruction does) and builds a scratch library
+with the same C ABI in a pytest temporary directory; for the duration of this module chord_b200.runtime is pointed at that
+scratch library, afterwards at libchord_b200.so again.  The product never loads it and fails loudly without a GPU
+(tests/test_abi.py::test_no_cpu_fallback_without_gpu).
+
+What a pass here means: the kernels' algebra, their integer / fixed-point work, their queues, tickets, look-back scans and
+barrier protocols produce the oracle's bits when every IEEE-pinned operation is IEEE.  What it does not cover: the GPU's
+approximate instructions (replaced by the exact operation), the memory model, performance - the `-m gpu` run on a B200
+remains the parity gate.  Its use: a kernel rewrite can be checked here in seconds before GPU minutes are spent on it.
+
+The cheap cases run by default; CHORD_HOSTCC_FULL=1 adds the slow ones (overflow fallbacks, cascade shadow passes, scissor
+tiles, medium / large triangle streams: ~4 more minutes)."""
+import os
+import sys
+
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, 'hostcc'))
+FULL = os.environ.get('CHORD_HOSTCC_FULL') == '1'
+slow = pytest.mark.skipif(not FULL, reason='slow on the host executor: set CHORD_HOSTCC_FULL=1')
+
+
+@pytest.fixture(scope='module')
+def host_ctx(tmp_path_factory):
+    import hostcc_build
+    from chord_b200 import runtime
+    so = hostcc_build.build(tmp_path_factory.mktemp('hostcc_lib'))
+    saved = (runtime.LIB_PATH, runtime._lib)
+    runtime.LIB_PATH, runtime._lib = so, None
+    try:
+        ctx = runtime.Context(0)
+        yield ctx
+        ctx.close()
+    finally:
+        runtime.LIB_PATH, runtime._lib = saved
+
+
+@pytest.fixture(scope='module')
+def cases():
+    import test_gpu_parity
+    return test_gpu_parity
+
+
+def test_scratch_library_is_not_the_product(host_ctx):
+    from chord_b200 import runtime
+    assert 'hostcc_scratch' in runtime.LIB_PATH and not runtime.LIB_PATH.startswith(os.path.dirname(HERE) + '/chord_b200')
+    # graphs are not modelled: the call reports it instead of pretending
+    with pytest.raises(runtime.ChordError):
+        runtime.lib().chord_graph_begin_capture(host_ctx.h)
+
+
+def test_s1_single_meshlet(host_ctx, cases):
+    cases.test_s1_single_meshlet(host_ctx)
+
+
+def test_patch_stream_small_triangles(host_ctx, cases):
+    cases.test_patch_stream_raster(host_ctx, 3000, 640, 360, 1.0)
+
+
+@slow
+@pytest.mark.parametrize('n,w,h,scale', [(1500, 512, 512, 40.0), (600, 256, 256, 2000.0)])
+def test_patch_stream_medium_and_large_triangles(host_ctx, cases, n, w, h, scale):
+    cases.test_patch_stream_raster(host_ctx, n, w, h, scale)
+
+
+def test_ragged_meshlets(host_ctx, cases):
+    cases.test_ragged_meshlets(host_ctx)
+
+
+def test_city_frames(host_ctx, cases):
+    cases.test_city_frames(host_ctx)
+
+
+def test_hzb_culling_lists(host_ctx, cases):
+    cases.test_hzb_culling_lists(host_ctx)
+
+
+@slow
+def test_tile_scissor(host_ctx, cases):
+    cases.test_tile_scissor(host_ctx)
+
+
+def test_lighting_resolve(host_ctx, cases):
+    cases.test_lighting_resolve(host_ctx)
+
+
+def test_lighting_packed_formats(host_ctx, cases):
+    cases.test_lighting_packed_formats(host_ctx)
+
+
+def test_bvh_traversal(host_ctx, cases):
+    cases.test_bvh_traversal(host_ctx)
+
+
+def test_builder_asset_parity(host_ctx, cases):
+    cases.test_builder_asset_parity(host_ctx)
+
+
+def test_masked_bucket(host_ctx, cases):
+    cases.test_masked_bucket(host_ctx)
+
+
+def test_cascade_setup_on_device(host_ctx, cases):
+    cases.test_cascade_setup_on_device(host_ctx)
+
+
+@slow
+def test_queue_overflow_fallbacks(host_ctx, cases):
+    cases.test_queue_overflow_fallbacks(host_ctx)
+
+
+@slow
+def test_cascade_shadow_depth(host_ctx, cases):
+    cases.test_cascade_shadow_depth(host_ctx)

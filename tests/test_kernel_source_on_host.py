@@ -38,7 +38,7 @@ def hostlib(tmp_path_factory):
     # -ffp-contract=off: only the explicit __fmaf_rn calls fuse, as under nvcc --fmad=false; -mfma makes those one instruction
     subprocess.check_call([cxx, '-O2', '-std=c++17', '-shared', '-fPIC', '-ffp-contract=off', '-mfma', '-mf16c', '-fno-fast-math',
                            '-I', HOSTCC, '-I', os.path.join(ROOT, 'chord_b200', 'csrc'), '-I', str(d),
-                           os.path.join(HOSTCC, 'lighting_harness.cpp'), '-o', so])
+                           os.path.join(HOSTCC, 'lighting_harness.cpp'), os.path.join(HOSTCC, 'hostcc_rt.cpp'), '-o', so])
     lib = C.CDLL(so)
     lib.hostcc_div_uniform_mismatches.restype = C.c_ulonglong
     return lib
