@@ -71,24 +71,7 @@ __global__ void __launch_bounds__(256) k_hzb_build(HzbBuildParams p)
 
     // ---- mip 0: 32x32 texels of this block, 4 per thread (hzb.hlsl:134-173)
     float vMin = 10.0f, vMax = -10.0f;      // valid-range accumulators
-    for (uint32_t k = 0; k < 4; k++) {
-        const uint32_t l = tid + k * 256, lx = l & 31u, ly = l >> 5;
-        const uint32_t x = bx * 32 + lx, y = by * 32 + ly;
-        float d[4];
-        const uint32_t sy0 = min(2 * y, p.height - 1), sy1 = min(2 * y + 1, p.height - 1);
-        if (evenWidth && 2 * x + 1 < p.width) {
-            // both pixels of a row in one 16-byte load (the row start is 16-byte aligned when the width is even)
-            const ulonglong2 r0 = *reinterpret_cast<const ulonglong2*>(p.vis64 + (size_t)sy0 * p.width + 2 * x);
-            const ulonglong2 r1 = *reinterpret_cast<const ulonglong2*>(p.vis64 + (size_t)sy1 * p.width + 2 * x);
-            d[0] = __uint_as_float((uint32_t)(r0.x >> 32)); d[1] = __uint_as_float((uint32_t)(r1.x >> 32));
-            d[2] = __uint_as_float((uint32_t)(r0.y >> 32)); d[3] = __uint_as_float((uint32_t)(r1.y >> 32));
-        } else {
-#pragma unroll
-            for (int s = 0; s < 4; s++) {
-                const uint32_t sx = min(2 * x + (uint32_t)(s >> 1), p.width - 1), sy = (s & 1) ? sy1 : sy0;
-                d[s] = __uint_as_float((uint32_t)(p.vis64[(size_t)sy * p.width + sx] >> 32));
-            }
-        }
+    auto mip0_texel = [&](uint32_t l, uint32_t x, uint32_t y, const float (&d)[4]) {
         float mn = d[0], mx = d[0];
 #pragma unroll
         for (int s = 0; s < 4; s++) {
@@ -100,6 +83,43 @@ __global__ void __launch_bounds__(256) k_hzb_build(HzbBuildParams p)
             const size_t o = p.mipOffset[0] + (size_t)y * p.mip0W + x;
             if (doMin) p.minChain[o] = to_half_rtz(mn);
             if (doMax) p.maxChain[o] = to_half_rtz(mx);
+        }
+    };
+    if (evenWidth && bx * 64 + 64 <= p.width && by * 64 + 64 <= p.height) {
+        // block entirely inside the image (uniform per block): all eight 16-byte loads of the thread are issued before the
+        // first one is consumed - with the edge handling in the way the compiler serialises the four texels, i.e. four
+        // dependent round trips to HBM per thread instead of one
+        ulonglong2 r0[4], r1[4];
+#pragma unroll
+        for (uint32_t k = 0; k < 4; k++) {
+            const uint32_t l = tid + k * 256, x = bx * 32 + (l & 31u), y = by * 32 + (l >> 5);
+            r0[k] = *reinterpret_cast<const ulonglong2*>(p.vis64 + (size_t)(2 * y) * p.width + 2 * x);
+            r1[k] = *reinterpret_cast<const ulonglong2*>(p.vis64 + (size_t)(2 * y + 1) * p.width + 2 * x);
+        }
+#pragma unroll
+        for (uint32_t k = 0; k < 4; k++) {
+            const uint32_t l = tid + k * 256, x = bx * 32 + (l & 31u), y = by * 32 + (l >> 5);
+            const float d[4] = { __uint_as_float((uint32_t)(r0[k].x >> 32)), __uint_as_float((uint32_t)(r1[k].x >> 32)),
+                                 __uint_as_float((uint32_t)(r0[k].y >> 32)), __uint_as_float((uint32_t)(r1[k].y >> 32)) };
+            mip0_texel(l, x, y, d);
+        }
+    } else {
+        // edge / off-screen block: clamp-to-edge gather (hzb.hlsl:139-150), again every load before the first use
+        float g[4][4];
+#pragma unroll
+        for (uint32_t k = 0; k < 4; k++) {
+            const uint32_t l = tid + k * 256, x = bx * 32 + (l & 31u), y = by * 32 + (l >> 5);
+            const uint32_t sy0 = min(2 * y, p.height - 1), sy1 = min(2 * y + 1, p.height - 1);
+#pragma unroll
+            for (int s = 0; s < 4; s++) {
+                const uint32_t sx = min(2 * x + (uint32_t)(s >> 1), p.width - 1), sy = (s & 1) ? sy1 : sy0;
+                g[k][s] = __uint_as_float((uint32_t)(p.vis64[(size_t)sy * p.width + sx] >> 32));
+            }
+        }
+#pragma unroll
+        for (uint32_t k = 0; k < 4; k++) {
+            const uint32_t l = tid + k * 256;
+            mip0_texel(l, bx * 32 + (l & 31u), by * 32 + (l >> 5), g[k]);
         }
     }
     if (p.validRange) {
