@@ -96,6 +96,12 @@ __device__ __forceinline__ void mat_mul(const float* __restrict__ A, const float
 __device__ __forceinline__ uint32_t enc_vis(uint32_t tri, uint32_t inst) { return (((inst + 1u) & CHORD_MAX_INSTANCE_ID_COUNT) << 8) | (tri & 0xFFu); }
 __device__ __forceinline__ void dec_vis(uint32_t pack, uint32_t& tri, uint32_t& inst) { tri = pack & 0xFFu; inst = ((pack >> 8) & CHORD_MAX_INSTANCE_ID_COUNT) - 1u; }
 
+// Scheduling fence for four independent dependent-load chains: the four values must be in flight (their loads issued) before
+// anything after this point is issued; no instruction is emitted.  Without it the compiler interleaves the chains so that
+// chain 2's first load waits behind chain 1's second round trip.
+__device__ __forceinline__ void loads_issued(uint32_t& a, uint32_t& b, uint32_t& c, uint32_t& d)
+{ asm volatile("" : "+r"(a), "+r"(b), "+r"(c), "+r"(d)); }
+
 __device__ __forceinline__ bool has_flag(uint32_t flags, uint32_t bit) { return (flags & (1u << bit)) != 0u; }
 
 __device__ __constant__ const float kExtentApplyFactor[8][3] = {

@@ -18,6 +18,7 @@ SOURCES = ['ctx.cu', 'cull.cu', 'raster.cu', 'hzb.cu', 'resolve.cu', 'shadow.cu'
 
 # helper name -> host body (the signature stays the product's)
 PTX_HELPERS = {
+    'loads_issued': '{ (void)a; (void)b; (void)c; (void)d; }',
     'ld_volatile_u64': '{ hostcc::yield(); return *(const volatile unsigned long long*)p; }',
     'st_volatile_u64': '{ *(volatile unsigned long long*)p = v; }',
     'smem_u32': '{ return (uint32_t)(uintptr_t)p; }',
