@@ -217,6 +217,26 @@ def test_tile_scissor(gpu_ctx):
     _assert_vis_equal(acc, full, 'union of tiles')
 
 
+@pytest.mark.parametrize('w,h', [(264, 72), (72, 264), (200, 200)])
+def test_tile_marker_odd_tile_counts(gpu_ctx, w, h):
+    """K9 classifies two 8x8 tiles per warp: frames whose tile count is odd / whose edges cut tiles (clamp-to-edge gather)."""
+    n = 300
+    scene, camera, objects, cmds = synth.patch_stream_scene(n, w, h, seed=5, overdraw_scale=20.0)
+    view = cam.fill_view(camera)
+    iview = cam.fill_instance_view(view)
+    gpu_ctx.upload_scene(scene)
+    fr = runtime.Frame(gpu_ctx, w, h)
+    fr.begin(view, iview, objects, n, (n + 3) // 4)
+    lst = runtime.CmdList(gpu_ctx, n)
+    lst.upload(cmds)
+    fr.render_mesh(lst)
+    fr.visibility_mark(lst)
+    ofr = oracle.Frame(scene, view, iview, objects, w, h)
+    ovis, _ = ofr.render_mesh(cmds)
+    _assert_vis_equal(fr.vis64(), ovis, f'vis64 {w}x{h}')
+    assert np.array_equal(fr.tile_marker(), ofr.visibility_mark(ovis, cmds))
+
+
 def test_lighting_resolve(gpu_ctx):
     """K9-K11: tile classification + PBR resolve. Floating point: |gpu - oracle| <= 1e-5 (north_star tolerance) on the
     pre-quantisation fp32 G-buffer planes; untouched pixels must stay cleared."""
