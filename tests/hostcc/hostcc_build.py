@@ -87,8 +87,10 @@ def translate(text, name):
     return text
 
 
-def build(outdir, opt='-O1'):
-    """Translate + compile; returns the path of the scratch library (same exported C ABI as libchord_b200.so)."""
+def build(outdir, opt='-O1', extra=()):
+    """Translate + compile; returns the path of the scratch library (same exported C ABI as libchord_b200.so).
+    ``extra``: more compiler / linker flags, e.g. ('-fsanitize=undefined', '-fno-sanitize-recover=undefined') to run the
+    kernels under UBSan (signed overflow of the int32 edge functions, misaligned vector loads, shifts)."""
     outdir = str(outdir)
     inc = os.path.join(outdir, 'csrc')
     os.makedirs(inc, exist_ok=True)
@@ -96,7 +98,7 @@ def build(outdir, opt='-O1'):
         translate(open(os.path.join(CSRC, 'common.cuh')).read().replace('"../../include/chord_b200.h"', '<chord_b200.h>'), 'common.cuh'))
     cxx = '/usr/bin/g++' if os.path.exists('/usr/bin/g++') else 'g++'
     flags = [opt, '-std=c++17', '-fPIC', '-ffp-contract=off', '-mfma', '-mf16c', '-fno-fast-math', '-w',
-             '-I', HERE, '-I', inc, '-I', os.path.join(ROOT, 'include')]
+             '-I', HERE, '-I', inc, '-I', os.path.join(ROOT, 'include')] + list(extra)
     objs, procs = [], []
     for s in SOURCES:
         cpp = os.path.join(inc, s.replace('.cu', '.cpp'))
@@ -112,10 +114,10 @@ def build(outdir, opt='-O1'):
         if p.returncode != 0:
             raise RuntimeError(f'hostcc: {s} does not compile for the host:\n{out[-6000:]}')
     so = os.path.join(outdir, 'libchord_b200_hostcc_scratch.so')
-    subprocess.check_call([cxx, '-shared', '-o', so] + objs)
+    subprocess.check_call([cxx, '-shared', '-o', so] + objs + list(extra))
     return so
 
 
 if __name__ == '__main__':
     import sys
-    print(build(sys.argv[1] if len(sys.argv) > 1 else '/tmp/hostcc_build'))
+    print(build(sys.argv[1] if len(sys.argv) > 1 else '/tmp/hostcc_build', extra=sys.argv[2:]))

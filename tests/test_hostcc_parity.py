@@ -121,3 +121,23 @@ def test_queue_overflow_fallbacks(host_ctx, cases):
 @slow
 def test_cascade_shadow_depth(host_ctx, cases):
     cases.test_cascade_shadow_depth(host_ctx)
+
+
+@slow
+def test_kernels_under_ubsan(tmp_path_factory):
+    """The same sources built with -fsanitize=undefined (no recovery): signed overflow in the int32 / int64 edge functions,
+    out-of-range float -> int conversions, bad shifts would abort the process.  Runs a raster-heavy subset."""
+    import subprocess
+    import hostcc_build
+    so = hostcc_build.build(tmp_path_factory.mktemp('hostcc_ubsan'), extra=('-fsanitize=undefined', '-fno-sanitize-recover=undefined'))
+    script = (
+        "import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "from chord_b200 import runtime\n"
+        "runtime.LIB_PATH, runtime._lib = %r, None\n"
+        "import test_gpu_parity as G\n"
+        "ctx = runtime.Context(0)\n"
+        "G.test_s1_single_meshlet(ctx); G.test_patch_stream_raster(ctx, 3000, 640, 360, 1.0); G.test_patch_stream_raster(ctx, 600, 256, 256, 2000.0)\n"
+        "G.test_ragged_meshlets(ctx); G.test_city_frames(ctx); G.test_masked_bucket(ctx)\n"
+        "print('ubsan-clean')\n") % (os.path.dirname(HERE), HERE, so)
+    r = subprocess.run([sys.executable, '-c', script], capture_output=True, text=True, timeout=1200)
+    assert r.returncode == 0 and 'ubsan-clean' in r.stdout, r.stderr[-3000:]
