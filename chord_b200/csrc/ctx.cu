@@ -890,8 +890,13 @@ int chord_readback_visibility32_async(chord_frame* f, uint32_t* hostPinned)
     // only the frame's screen tile travels (the other tiles belong to other GPUs): a pitched copy into the same
     // position of the host image
     const size_t pitch = (size_t)f->width * 4, off = (size_t)f->tile.y0 * f->width + f->tile.x0;
-    CHORD_CUDA(cudaMemcpy2DAsync(hostPinned + off, pitch, f->splitVis[k] + off, pitch, (size_t)(f->tile.x1 - f->tile.x0) * 4,
-                                 f->tile.y1 - f->tile.y0, cudaMemcpyDeviceToHost, f->copyStream));
+    if (f->tile.x0 == 0 && f->tile.x1 == f->width) {
+        // full-width tile (always the case on one GPU): the rows are contiguous, one linear copy instead of a pitched one
+        CHORD_CUDA(cudaMemcpyAsync(hostPinned + off, f->splitVis[k] + off, pitch * (size_t)(f->tile.y1 - f->tile.y0), cudaMemcpyDeviceToHost, f->copyStream));
+    } else {
+        CHORD_CUDA(cudaMemcpy2DAsync(hostPinned + off, pitch, f->splitVis[k] + off, pitch, (size_t)(f->tile.x1 - f->tile.x0) * 4,
+                                     f->tile.y1 - f->tile.y0, cudaMemcpyDeviceToHost, f->copyStream));
+    }
     CHORD_CUDA(cudaEventRecord(f->copyDone[k], f->copyStream));
     return CHORD_OK;
 }
