@@ -61,12 +61,15 @@ __device__ void hzb_top_levels(const HzbBuildParams& p, float* __restrict__ sMin
     }
 }
 
+// Specialised on what the call builds: the min-only build between the two visibility stages (renderer.cpp:334) carries
+// neither the max chain's reductions / shared-memory traffic nor the valid-range accumulation.
+template <bool kMin, bool kMax, bool kRange>
 __global__ void __launch_bounds__(256) k_hzb_build(HzbBuildParams p)
 {
-    __shared__ float sMinP[1024], sMinQ[256], sMaxP[1024], sMaxQ[256];
+    __shared__ float sMinP[kMin ? 1024 : 1], sMinQ[kMin ? 256 : 1], sMaxP[kMax ? 1024 : 1], sMaxQ[kMax ? 256 : 1];
     const uint32_t bx = p.blockX0 + blockIdx.x, by = p.blockY0 + blockIdx.y;
     const uint32_t tid = threadIdx.x;
-    const bool doMin = p.minChain != nullptr, doMax = p.maxChain != nullptr;
+    constexpr bool doMin = kMin, doMax = kMax;
     const bool evenWidth = (p.width & 1u) == 0u;
 
     // ---- mip 0: 32x32 texels of this block, 4 per thread (hzb.hlsl:134-173)
@@ -75,10 +78,11 @@ __global__ void __launch_bounds__(256) k_hzb_build(HzbBuildParams p)
         float mn = d[0], mx = d[0];
 #pragma unroll
         for (int s = 0; s < 4; s++) {
-            if (s) { mn = fminf(mn, d[s]); mx = fmaxf(mx, d[s]); }
-            if (d[s] > 0.0f) { vMax = fmaxf(vMax, d[s]); vMin = fminf(vMin, d[s]); }
+            if (s) { if (kMin) mn = fminf(mn, d[s]); if (kMax) mx = fmaxf(mx, d[s]); }
+            if (kRange) { if (d[s] > 0.0f) { vMax = fmaxf(vMax, d[s]); vMin = fminf(vMin, d[s]); } }
         }
-        sMinP[l] = mn; sMaxP[l] = mx;
+        if (kMin) sMinP[l] = mn;
+        if (kMax) sMaxP[l] = mx;
         if (x < p.mip0W && y < p.mip0H) {
             const size_t o = p.mipOffset[0] + (size_t)y * p.mip0W + x;
             if (doMin) p.minChain[o] = to_half_rtz(mn);
@@ -122,7 +126,7 @@ __global__ void __launch_bounds__(256) k_hzb_build(HzbBuildParams p)
             mip0_texel(l, bx * 32 + (l & 31u), by * 32 + (l >> 5), g[k]);
         }
     }
-    if (p.validRange) {
+    if (kRange) {
         // hzb.hlsl:165-172: wave min/max, then InterlockedMin/Max on the raw bits with the <1 / >0 guards.  min / max are
         // associative, so the eight waves of the block are combined in shared memory first and ONE pair of atomics per
         // block reaches the two global words (65 k same-address atomics per 4K build otherwise).
@@ -148,9 +152,9 @@ __global__ void __launch_bounds__(256) k_hzb_build(HzbBuildParams p)
         if (tid < nw * nw) {
             const uint32_t lx = tid % nw, ly = tid / nw;
             const uint32_t a = (2 * ly) * w + 2 * lx, b = a + 1, c = a + w, d = c + 1;
-            const float mn = fminf(fminf(fminf(srcMin[a], srcMin[b]), srcMin[c]), srcMin[d]);
-            const float mx = fmaxf(fmaxf(fmaxf(srcMax[a], srcMax[b]), srcMax[c]), srcMax[d]);
-            dstMin[tid] = mn; dstMax[tid] = mx;
+            float mn = 0.0f, mx = 0.0f;
+            if (kMin) { mn = fminf(fminf(fminf(srcMin[a], srcMin[b]), srcMin[c]), srcMin[d]); dstMin[tid] = mn; }
+            if (kMax) { mx = fmaxf(fmaxf(fmaxf(srcMax[a], srcMax[b]), srcMax[c]), srcMax[d]); dstMax[tid] = mx; }
             const uint32_t mw = mip_dim(p.mip0W, mip), mh = mip_dim(p.mip0H, mip);
             const uint32_t x = bx * nw + lx, y = by * nw + ly;
             if (x < mw && y < mh) {
@@ -217,7 +221,11 @@ int launch_build_hzb(chord_frame* fr, int bMin, int bMax, int bRange, chord_hzb*
         static const uint32_t kInit[2] = { ~0u, 0u };                       // hzb.cpp:105-106 (static: a captured graph re-reads it)
         CHORD_CUDA(cudaMemcpyAsync(dst->validRange, kInit, 8, cudaMemcpyHostToDevice, ctx->stream));
     }
-    k_hzb_build<<<grid, 256, 0, ctx->stream>>>(p);
+    // hzb.cpp:44-47: at least one of min / max, a valid range only with both
+    if (bMin && bMax && bRange) k_hzb_build<true, true, true><<<grid, 256, 0, ctx->stream>>>(p);
+    else if (bMin && bMax)      k_hzb_build<true, true, false><<<grid, 256, 0, ctx->stream>>>(p);
+    else if (bMin)              k_hzb_build<true, false, false><<<grid, 256, 0, ctx->stream>>>(p);
+    else                        k_hzb_build<false, true, false><<<grid, 256, 0, ctx->stream>>>(p);
     ctx->launches++;
     if (dst->mipCount > 6) { k_hzb_top<<<1, 256, 0, ctx->stream>>>(p); ctx->launches++; }     // tiled builds: from the tile-local mip 5, like the phase-1 HZB wants
     CHORD_CUDA(cudaGetLastError());

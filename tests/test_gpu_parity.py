@@ -217,6 +217,34 @@ def test_tile_scissor(gpu_ctx):
     _assert_vis_equal(acc, full, 'union of tiles')
 
 
+def test_hzb_chain_combinations(gpu_ctx):
+    """buildHZB(bMin, bMax, bValidRange) in every combination hzb.cpp:44-47 allows (each is its own kernel instantiation), on a
+    frame that is neither a power of two nor a multiple of 64: interior, edge and off-screen 64x64 blocks."""
+    w, h, n = 328, 200, 300
+    scene, camera, objects, cmds = synth.patch_stream_scene(n, w, h, seed=5, overdraw_scale=20.0)
+    view = cam.fill_view(camera)
+    iview = cam.fill_instance_view(view)
+    gpu_ctx.upload_scene(scene)
+    fr = runtime.Frame(gpu_ctx, w, h)
+    fr.begin(view, iview, objects, n, (n + 3) // 4)
+    lst = runtime.CmdList(gpu_ctx, n)
+    lst.upload(cmds)
+    fr.render_mesh(lst)
+    ofr = oracle.Frame(scene, view, iview, objects, w, h)
+    ovis, _ = ofr.render_mesh(cmds)
+    _assert_vis_equal(fr.vis64(), ovis, 'vis64')
+    for bmin, bmax, brange in ((True, False, False), (False, True, False), (True, True, False), (True, True, True)):
+        hz = runtime.Hzb(gpu_ctx, w, h)
+        fr.build_hzb(hz, bmin, bmax, brange)
+        oh = ofr.build_hzb(ovis, bmin, bmax, brange)
+        if bmin:
+            _assert_hzb_equal(hz, oh, 'min')
+        if bmax:
+            _assert_hzb_equal(hz, oh, 'max')
+        if brange:
+            assert np.array_equal(hz.valid_range(), oh['range'])
+
+
 @pytest.mark.parametrize('w,h', [(264, 72), (72, 264), (200, 200)])
 def test_tile_marker_odd_tile_counts(gpu_ctx, w, h):
     """K9 classifies two 8x8 tiles per warp: frames whose tile count is odd / whose edges cut tiles (clamp-to-edge gather)."""

@@ -84,6 +84,10 @@ def test_tile_scissor(host_ctx, cases):
     cases.test_tile_scissor(host_ctx)
 
 
+def test_hzb_chain_combinations(host_ctx, cases):
+    cases.test_hzb_chain_combinations(host_ctx)
+
+
 @pytest.mark.parametrize('w,h', [(264, 72), (72, 264), (200, 200)])
 def test_tile_marker_odd_tile_counts(host_ctx, cases, w, h):
     cases.test_tile_marker_odd_tile_counts(host_ctx, w, h)
