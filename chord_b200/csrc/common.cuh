@@ -175,6 +175,7 @@ struct chord_ctx {
     void** sceneAllocs; uint32_t nSceneAllocs;
     chordb::DatasDev* datasHost;
     // scratch for ordered compaction
+    unsigned long long* scanBlock;       // [ticket | status...], see scan_reset
     unsigned long long* scanStatus; uint32_t scanTiles;
     uint32_t* scanTicket;
     // atmosphere LUTs

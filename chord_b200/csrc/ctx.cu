@@ -35,17 +35,20 @@ FrameDev make_frame_dev(const chord_frame* f)
     return d;
 }
 
+// Scratch of the ordered compactions: ONE allocation [ticket word | status[0 .. tiles]] so that one memset per cull
+// kernel resets both (two stream operations per cull call, four cull calls per frame, were ~2 us each on the timeline).
 int scan_reset(chord_ctx* ctx, uint32_t tilesNeeded)
 {
-    if (tilesNeeded > ctx->scanTiles) {
-        if (ctx->scanStatus) cudaFree(ctx->scanStatus);
-        ctx->scanStatus = nullptr; ctx->scanTiles = 0;
+    if (tilesNeeded > ctx->scanTiles || !ctx->scanBlock) {
+        if (ctx->scanBlock) cudaFree(ctx->scanBlock);                           // (synchronises the device)
+        ctx->scanBlock = nullptr; ctx->scanStatus = nullptr; ctx->scanTicket = nullptr; ctx->scanTiles = 0;
         uint32_t n = tilesNeeded + 1024;
-        CHORD_CUDA(cudaMalloc(&ctx->scanStatus, sizeof(unsigned long long) * n));
+        CHORD_CUDA(cudaMalloc(&ctx->scanBlock, sizeof(unsigned long long) * ((size_t)n + 1)));
+        ctx->scanTicket = reinterpret_cast<uint32_t*>(ctx->scanBlock);        // low half of word 0
+        ctx->scanStatus = ctx->scanBlock + 1;
         ctx->scanTiles = n;
     }
-    CHORD_CUDA(cudaMemsetAsync(ctx->scanStatus, 0, sizeof(unsigned long long) * (size_t)(tilesNeeded + 1), ctx->stream));
-    CHORD_CUDA(cudaMemsetAsync(ctx->scanTicket, 0, sizeof(uint32_t), ctx->stream));
+    CHORD_CUDA(cudaMemsetAsync(ctx->scanBlock, 0, sizeof(unsigned long long) * ((size_t)tilesNeeded + 2), ctx->stream));
     return CHORD_OK;
 }
 
@@ -100,7 +103,6 @@ int chord_ctx_create(int device, chord_ctx** out)
     c->smCount = prop.multiProcessorCount;
     const int rc = [&]() -> int {
         CHORD_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-        CHORD_CUDA(cudaMalloc(&c->scanTicket, sizeof(uint32_t)));
         return CHORD_OK;
     }();
     if (rc != CHORD_OK) { chord_ctx_destroy(c); return rc; }      // nothing half-built survives a failed create
@@ -114,8 +116,7 @@ void chord_ctx_destroy(chord_ctx* ctx)
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     free_scene(ctx);
-    if (ctx->scanStatus) cudaFree(ctx->scanStatus);
-    if (ctx->scanTicket) cudaFree(ctx->scanTicket);
+    if (ctx->scanBlock) cudaFree(ctx->scanBlock);
     if (ctx->lutTransmittance) cudaFree(ctx->lutTransmittance);
     if (ctx->lutIrradiance) cudaFree(ctx->lutIrradiance);
     cudaFree(ctx->dTextures); cudaFree(ctx->dSamplers); cudaFree(ctx->dTexels);
