@@ -212,6 +212,9 @@ __global__ void __launch_bounds__(kCullBlock) k_group_cull(FrameDev f, const uin
     __shared__ uint32_t sBase;
     const uint32_t total = *totalGroups;
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    // the last tile publishes the list count (below); with nothing to do nobody would, so the count is zeroed here instead of
+    // by a memset in front of every cull kernel
+    if (total == 0u && blockIdx.x == 0 && threadIdx.x == 0) *outCount = 0u;
     while (true) {
         __syncthreads();
         if (threadIdx.x == 0) sTile = atomicAdd(ticket, 1u);
@@ -288,6 +291,7 @@ __global__ void __launch_bounds__(kCullBlock) k_hzb_cull(FrameDev f, HzbDev hzb,
     uint32_t total = *inCount; if (total > inCapacity) total = inCapacity;
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const float W = f.view->renderDimension.x, H = f.view->renderDimension.y;
+    if (total == 0u && blockIdx.x == 0 && threadIdx.x == 0) { *outVisCount = 0u; if (kFirstStage) *outRejCount = 0u; }      // see k_group_cull
     while (true) {
         __syncthreads();
         if (threadIdx.x == 0) sTile = atomicAdd(ticket, 1u);
@@ -399,6 +403,7 @@ __global__ void __launch_bounds__(kCullBlock) k_hzb_cull_generic(FrameDev f, Hzb
     __shared__ uint32_t sBaseV;
     uint32_t total = *inCount; if (total > inCapacity) total = inCapacity;
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    if (total == 0u && blockIdx.x == 0 && threadIdx.x == 0) *outVisCount = 0u;      // see k_group_cull
     __shared__ GenericCullParams sPrm;
     if (prm.dView) {
         // the HZB's view lives on the device (cascade buffer): resolve the derived parameters once per block
@@ -594,7 +599,6 @@ static int launch_instance_culling_impl(chord_frame* fr, chord_cmdlist* out, boo
     const uint32_t tiles = (fr->meshletGroupCount + kCullBlock - 1) / kCullBlock + 1;
     int rc = scan_reset(ctx, tiles);
     if (rc) return rc;
-    CHORD_CUDA(cudaMemsetAsync(out->count, 0, 4, ctx->stream));
     k_object_cull<<<(fr->objectCount + 127) / 128, 128, 0, ctx->stream>>>(f, fr->objGroupCount);
     k_object_scan<<<1, 1024, 0, ctx->stream>>>(fr->objGroupCount, fr->objGroupBase, fr->objectCount, fr->totalGroups);
     const uint32_t* bits = nullptr;
@@ -635,8 +639,6 @@ int launch_hzb_culling(chord_frame* fr, const chord_hzb* hzb, int firstStage, ch
     const uint32_t tiles = (in->capacity + kCullBlock - 1) / kCullBlock + 1;
     int rc = scan_reset(ctx, tiles);
     if (rc) return rc;
-    CHORD_CUDA(cudaMemsetAsync(outVis->count, 0, 4, ctx->stream));
-    if (outRej) CHORD_CUDA(cudaMemsetAsync(outRej->count, 0, 4, ctx->stream));
     uint32_t grid = tiles < (uint32_t)ctx->smCount * 8u ? tiles : (uint32_t)ctx->smCount * 8u;
     if (firstStage)
         k_hzb_cull<true><<<grid, kCullBlock, 0, ctx->stream>>>(f, h, in->cmds, in->count, in->capacity, ctx->scanStatus, ctx->scanTicket,
@@ -675,7 +677,6 @@ int launch_hzb_culling_generic(chord_frame* fr, const chord_hzb* hzb, const chor
     const uint32_t tiles = (in->capacity + kCullBlock - 1) / kCullBlock + 1;
     int rc = scan_reset(ctx, tiles);
     if (rc) return rc;
-    CHORD_CUDA(cudaMemsetAsync(outVis->count, 0, 4, ctx->stream));
     uint32_t grid = tiles < (uint32_t)ctx->smCount * 8u ? tiles : (uint32_t)ctx->smCount * 8u;
     k_hzb_cull_generic<<<grid, kCullBlock, 0, ctx->stream>>>(f, h, prm, in->cmds, in->count, in->capacity, ctx->scanStatus, ctx->scanTicket,
                                                              outVis->cmds, outVis->count);

@@ -217,6 +217,42 @@ def test_tile_scissor(gpu_ctx):
     _assert_vis_equal(acc, full, 'union of tiles')
 
 
+def test_empty_lists_publish_zero_counts(gpu_ctx):
+    """The cull kernels publish their list counts themselves (no memset in front of them): an empty input list and a frame in
+    which every object is culled must overwrite a stale count with zero."""
+    import ctypes as C
+    w, h, n = 256, 256, 200
+    scene, camera, objects, cmds = synth.patch_stream_scene(n, w, h, seed=5)
+    view = cam.fill_view(camera)
+    iview = cam.fill_instance_view(view)
+    gpu_ctx.upload_scene(scene)
+    fr = runtime.Frame(gpu_ctx, w, h)
+    fr.begin(view, iview, objects, n, (n + 3) // 4)
+    full = runtime.CmdList(gpu_ctx, n)
+    full.upload(cmds)
+    fr.render_mesh(full)
+    hz = runtime.Hzb(gpu_ctx, w, h)
+    fr.build_hzb(hz, True, False, False)
+    stale_v, stale_r, empty = runtime.CmdList(gpu_ctx, n), runtime.CmdList(gpu_ctx, n), runtime.CmdList(gpu_ctx, n)
+    stale_v.upload(cmds)
+    stale_r.upload(cmds)
+    empty.upload(cmds[:0])
+    L = runtime.lib()
+    L.chord_hzb_culling(fr.h, hz.h, C.c_int(1), empty.h, stale_v.h, stale_r.h)
+    assert stale_v.count() == 0 and stale_r.count() == 0
+    stale_v.upload(cmds)
+    L.chord_hzb_culling(fr.h, hz.h, C.c_int(0), empty.h, stale_v.h, None)
+    assert stale_v.count() == 0
+    away = cam.Camera(camera.position, -camera.front, width=w, height=h)
+    v2 = cam.fill_view(away)
+    iv2 = cam.fill_instance_view(v2)
+    fr.begin(v2, iv2, objects, n, (n + 3) // 4)
+    post = runtime.CmdList(gpu_ctx, n)
+    post.upload(cmds)
+    fr.instance_culling(post)
+    assert len(oracle.Frame(scene, v2, iv2, objects, w, h).instance_culling(n)) == 0 and post.count() == 0
+
+
 def test_hzb_chain_combinations(gpu_ctx):
     """buildHZB(bMin, bMax, bValidRange) in every combination hzb.cpp:44-47 allows (each is its own kernel instantiation), on a
     frame that is neither a power of two nor a multiple of 64: interior, edge and off-screen 64x64 blocks."""

@@ -84,6 +84,10 @@ def test_tile_scissor(host_ctx, cases):
     cases.test_tile_scissor(host_ctx)
 
 
+def test_empty_lists_publish_zero_counts(host_ctx, cases):
+    cases.test_empty_lists_publish_zero_counts(host_ctx)
+
+
 def test_hzb_chain_combinations(host_ctx, cases):
     cases.test_hzb_chain_combinations(host_ctx)
 
