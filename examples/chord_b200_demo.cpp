@@ -5,6 +5,8 @@
 //
 //   g++ -std=c++17 -Iinclude examples/chord_b200_demo.cpp -Lchord_b200 -l:libchord_b200.so -Wl,-rpath,$PWD/chord_b200 -o demo
 //   ./demo in.blob out.blob [bvh]
+//   ./demo in.blob out.blob path       every frame of the blob through chord_b200::DeferredRenderer (two-phase HZB culling against
+//                                      the previous frame's HZB, renderer.cpp:311-363 + :489); one {count, list, surface} per frame
 #include <chord_b200.hpp>
 
 #include <cstdio>
@@ -35,6 +37,7 @@ int main(int argc, char** argv)
 {
     if (argc < 3) { std::fprintf(stderr, "usage: %s in.blob out.blob [bvh]\n", argv[0]); return 2; }
     const bool useBvh = argc > 3 && std::strcmp(argv[3], "bvh") == 0;
+    const bool path = argc > 3 && std::strcmp(argv[3], "path") == 0;
     Reader r(argv[1]);
     // header: width, height, objectCount, lod0MeshletCount, meshletGroupCount, then array sizes
     const uint32_t width = (uint32_t)r.u64(), height = (uint32_t)r.u64(), objectCount = (uint32_t)r.u64();
@@ -56,6 +59,50 @@ int main(int argc, char** argv)
     const auto* view = (const chord_PerframeCameraView*)r.bytes(sizeof(chord_PerframeCameraView));
     const auto* iview = (const chord_InstanceCullingViewInfo*)r.bytes(sizeof(chord_InstanceCullingViewInfo));
     const auto* objects = (const chord_GPUObjectGLTFPrimitive*)r.bytes(sizeof(chord_GPUObjectGLTFPrimitive) * objectCount);
+
+    // optional tail of the blob: more frames of the same scene (count, then view / instance view / objects per frame)
+    struct FrameIn { const chord_PerframeCameraView* view; const chord_InstanceCullingViewInfo* iview; const chord_GPUObjectGLTFPrimitive* objects; };
+    std::vector<FrameIn> frames{FrameIn{view, iview, objects}};
+    if (r.off < r.buf.size()) {
+        const uint64_t more = r.u64();
+        for (uint64_t i = 0; i < more; i++) {
+            FrameIn fi;
+            fi.view = (const chord_PerframeCameraView*)r.bytes(sizeof(chord_PerframeCameraView));
+            fi.iview = (const chord_InstanceCullingViewInfo*)r.bytes(sizeof(chord_InstanceCullingViewInfo));
+            fi.objects = (const chord_GPUObjectGLTFPrimitive*)r.bytes(sizeof(chord_GPUObjectGLTFPrimitive) * objectCount);
+            frames.push_back(fi);
+        }
+    }
+
+    if (path) {
+        try {
+            chord_b200::Context ctx(0);
+            ctx.uploadScene(scene);
+            chord_b200::DeferredRenderer renderer(ctx, width, height);
+            FILE* o = std::fopen(argv[2], "wb");
+            if (!o) { std::perror(argv[2]); return 2; }
+            std::vector<uint64_t> vis((size_t)width * height);
+            std::vector<chord_draw_cmd> cmds(lod0);
+            for (size_t fi = 0; fi < frames.size(); fi++) {
+                auto post = renderer.render(*frames[fi].view, *frames[fi].iview, frames[fi].objects, objectCount, lod0, groups);
+                chord_b200::check(chord_readback_vis64(renderer.frame().handle(), vis.data()), "chord_readback_vis64");
+                uint32_t n = 0;
+                chord_b200::check(chord_cmdlist_readback(post.get(), cmds.data(), lod0, &n), "chord_cmdlist_readback");
+                const uint64_t n64 = n;
+                std::fwrite(&n64, 8, 1, o);
+                std::fwrite(cmds.data(), sizeof(chord_draw_cmd), n, o);
+                std::fwrite(vis.data(), 8, vis.size(), o);
+                size_t covered = 0; for (uint64_t v : vis) covered += v != 0;
+                std::printf("frame %zu: %u meshlets after culling, %zu px covered, history HZB %s\n", fi, n, covered, fi ? "used" : "none");
+            }
+            std::fclose(o);
+            std::printf("%llu kernel launches\n", (unsigned long long)chord_ctx_kernel_launches(ctx.handle()));
+        } catch (const std::exception& e) {
+            std::fprintf(stderr, "chord_b200 error: %s\n", e.what());
+            return 1;
+        }
+        return 0;
+    }
 
     try {
         chord_b200::Context ctx(0);

@@ -8,6 +8,7 @@
 #include <stdexcept>
 #include <string>
 #include <utility>
+#include <vector>
 
 #include "chord_b200.h"
 
@@ -149,5 +150,81 @@ private:
 };
 
 inline std::unique_ptr<Frame> Context::createFrame(uint32_t w, uint32_t h) const { return std::make_unique<Frame>(*this, w, h); }
+
+// DeferredRenderer::render between "Clear GBuffers" and "lightingTile" (source/renderer/renderer.cpp:311-363) plus the
+// history hand-off (:489, m_rendererHistory.hzbCtx): instanceCulling -> gltfVisibilityRenderingStage0 against LAST frame's HZB
+// -> buildHZB(min) -> gltfVisibilityRenderingStage1 -> buildHZB(min, max, range), kept as history -> visibilityMark -> lighting.
+// Headless: the frame stays in device memory (Frame), read it back with the chord_readback_* calls.
+class DeferredRenderer {
+public:
+    DeferredRenderer(const Context& ctx, uint32_t width, uint32_t height, bool doResolve = false, bool useBvh = false)
+        : m_ctx(ctx), m_frame(ctx.createFrame(width, height)), m_doResolve(doResolve), m_useBvh(useBvh) {}
+
+    Frame& frame() { return *m_frame; }
+    const HzbRef& historyHzb() const { return m_history; }
+    const CmdListRef& postCull() const { return m_post; }
+    // renderer.cpp:95-105 (resize / camera cut): the next frame culls without occlusion history
+    void clearHistory() { m_history.reset(); }
+
+    // one frame; returns the post-cull list (the drawMeshletCmdBuffer the resolve passes index).  Lists and HZBs come from a
+    // small pool (getContext().getBufferPool() / getTexturePool() stand-in): everything is stream-ordered, so an object can
+    // be handed out again as soon as the call that last used it has been enqueued - no per-frame allocation, no host sync.
+    CmdListRef render(const chord_PerframeCameraView& view, const chord_InstanceCullingViewInfo& iview,
+                      const chord_GPUObjectGLTFPrimitive* objects, uint32_t objectCount,
+                      uint32_t lod0MeshletCount, uint32_t meshletGroupCount, const chord_rect* tile = nullptr)
+    {
+        chord_frame* f = m_frame->handle();
+        m_frame->begin(view, iview, objects, objectCount, lod0MeshletCount, meshletGroupCount, tile);   // uniforms + addClearGbufferPass
+        releaseList(m_post);
+        CmdListRef post = acquireList(lod0MeshletCount);
+        if (m_useBvh) check(chord_instance_culling_bvh(f, post.get()), "chord_instance_culling_bvh");
+        else          check(chord_instance_culling(f, post.get()), "chord_instance_culling");
+        // gltfVisibilityRenderingStage0 (mesh_raster.cpp:269-312)
+        int needStage1 = 0;
+        CmdListRef visible, rejected;
+        const bool haveHistory = m_history && chord_hzb_is_valid(m_history.get());
+        if (haveHistory) { visible = acquireList(lod0MeshletCount); rejected = acquireList(lod0MeshletCount); }
+        check(chord_visibility_stage0(f, m_history.get(), post.get(), visible.get(), rejected.get(), &needStage1), "chord_visibility_stage0");
+        releaseList(visible);
+        if (needStage1) {                                                                               // bShouldStage1GLTF
+            HzbRef tmp = acquireHzb();
+            check(chord_build_hzb(f, 1, 0, 0, tmp.get()), "chord_build_hzb");
+            CmdListRef visible1 = acquireList(lod0MeshletCount);
+            check(chord_visibility_stage1(f, tmp.get(), rejected.get(), visible1.get()), "chord_visibility_stage1");
+            releaseList(visible1);
+            m_freeHzb.push_back(tmp);
+        }
+        releaseList(rejected);
+        HzbRef hzb = acquireHzb();
+        check(chord_build_hzb(f, 1, 1, 1, hzb.get()), "chord_build_hzb");
+        if (m_doResolve) { m_frame->visibilityMark(post); m_frame->lighting(post); }
+        if (m_history) m_freeHzb.push_back(m_history);
+        m_history = hzb;                                                                                // m_rendererHistory.hzbCtx = hzbCtx
+        m_post = post;
+        return post;
+    }
+
+private:
+    CmdListRef acquireList(uint32_t capacity)
+    {
+        for (size_t i = 0; i < m_freeLists.size(); i++)
+            if (chord_cmdlist_capacity(m_freeLists[i].get()) == capacity) { CmdListRef l = m_freeLists[i]; m_freeLists.erase(m_freeLists.begin() + (long)i); return l; }
+        return m_ctx.createCmdList(capacity);
+    }
+    void releaseList(CmdListRef& l) { if (l) { m_freeLists.push_back(l); l.reset(); } }
+    HzbRef acquireHzb()
+    {
+        if (!m_freeHzb.empty()) { HzbRef h = m_freeHzb.back(); m_freeHzb.pop_back(); return h; }
+        return m_ctx.createHzb(m_frame->width(), m_frame->height());
+    }
+
+    const Context& m_ctx;
+    std::unique_ptr<Frame> m_frame;
+    HzbRef m_history;
+    CmdListRef m_post;
+    std::vector<CmdListRef> m_freeLists;
+    std::vector<HzbRef> m_freeHzb;
+    bool m_doResolve, m_useBvh;
+};
 
 }  // namespace chord_b200

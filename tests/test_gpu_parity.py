@@ -520,41 +520,91 @@ def test_queue_overflow_fallbacks(gpu_ctx):
         fr.build_hzb(bad)
 
 
-def test_native_cpp_host(gpu_ctx, tmp_path):
-    """C++ host code -> C++ shim (include/chord_b200.hpp) -> C ABI -> CUDA: the path a chord maintainer would bind.
-    The demo is compiled by __graft_entry__.build(); here it renders a city frame natively and must match the oracle."""
+def _demo_exe():
     import os
-    import subprocess
-    from cases import city_frames
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     exe = os.path.join(root, 'examples', 'chord_b200_demo')
     if not os.path.exists(exe):
         import __graft_entry__
         __graft_entry__.build_cpp_demo()
-    w, h = 640, 360
-    scene, info, frames = city_frames(frames=1, w=w, h=h)
-    f = frames[0]
+    return exe
+
+
+def _write_demo_blob(path, scene, info, frames, w, h):
+    """examples/chord_b200_demo.cpp input: header, scene arrays, first frame, then (optionally) a count and more frames."""
     d = scene.datas[0]
-    blob = tmp_path / 'in.blob'
-    with open(blob, 'wb') as fh:
+    f = frames[0]
+    with open(path, 'wb') as fh:
         hdr = [w, h, len(f['objects']), info['lod0MeshletCount'], info['meshletGroupCount'], len(d['meshlets']), len(d['positions']),
                len(d['meshletData']), len(d['bvhNodes']), len(d['groups']), len(d['groupIndices']), len(scene.primitives), len(scene.materials)]
         fh.write(np.array(hdr, dtype=np.uint64).tobytes())
-        for a in (d['meshlets'], d['positions'], d['meshletData'], d['bvhNodes'], d['groups'], d['groupIndices'], scene.primitives,
-                  scene.materials, f['view'], f['iview'], f['objects']):
+
+        def put(a):
             b = np.ascontiguousarray(a).tobytes()
             fh.write(b + b'\0' * ((-len(b)) % 8))
+        for a in (d['meshlets'], d['positions'], d['meshletData'], d['bvhNodes'], d['groups'], d['groupIndices'], scene.primitives,
+                  scene.materials, f['view'], f['iview'], f['objects']):
+            put(a)
+        if len(frames) > 1:
+            fh.write(np.array([len(frames) - 1], dtype=np.uint64).tobytes())
+            for g in frames[1:]:
+                assert len(g['objects']) == len(f['objects'])
+                put(g['view']); put(g['iview']); put(g['objects'])
+
+
+def _read_demo_frames(path, n_frames, w, h):
+    raw, off, out = open(path, 'rb').read(), 0, []
+    for _ in range(n_frames):
+        n = int(np.frombuffer(raw[off:off + 8], dtype=np.uint64)[0]); off += 8
+        cmds = np.frombuffer(raw[off:off + 12 * n], dtype=abi.DrawCmd); off += 12 * n
+        vis = np.frombuffer(raw[off:off + 8 * w * h], dtype=np.uint64).reshape(h, w); off += 8 * w * h
+        out.append((cmds, vis))
+    assert off == len(raw)
+    return out
+
+
+def test_native_cpp_host(gpu_ctx, tmp_path, exe=None):
+    """C++ host code -> C++ shim (include/chord_b200.hpp) -> C ABI -> CUDA: the path a chord maintainer would bind.
+    The demo is compiled by __graft_entry__.build(); here it renders a city frame natively and must match the oracle."""
+    import subprocess
+    from cases import city_frames
+    exe = exe or _demo_exe()
+    w, h = 640, 360
+    scene, info, frames = city_frames(frames=1, w=w, h=h)
+    f = frames[0]
+    blob = tmp_path / 'in.blob'
+    _write_demo_blob(blob, scene, info, frames, w, h)
     ref = oracle.run_frame(scene, f['view'], f['iview'], f['objects'], w, h, info['lod0MeshletCount'], None)
     for mode in ([], ['bvh']):
         out = tmp_path / f'out{len(mode)}.blob'
-        res = subprocess.run([exe, str(blob), str(out)] + mode, capture_output=True, text=True, timeout=120)
+        res = subprocess.run([exe, str(blob), str(out)] + mode, capture_output=True, text=True, timeout=600)
         assert res.returncode == 0, res.stdout + res.stderr
-        raw = open(out, 'rb').read()
-        n = int(np.frombuffer(raw[:8], dtype=np.uint64)[0])
-        cmds = np.frombuffer(raw[8:8 + 12 * n], dtype=abi.DrawCmd)
-        vis = np.frombuffer(raw[8 + 12 * n:], dtype=np.uint64).reshape(h, w)
+        (cmds, vis), = _read_demo_frames(out, 1, w, h)
         _assert_lists_equal(cmds, ref['post_cull'], f'native host {mode}')
         _assert_vis_equal(vis, ref['vis64'], f'native host {mode}')
+
+
+def test_native_cpp_renderer_camera_path(gpu_ctx, tmp_path, exe=None):
+    """chord_b200::DeferredRenderer (include/chord_b200.hpp), the C++ mirror of renderer.cpp:311-363 + the history hand-off at
+    :489, driven by native host code over a camera path: from the second frame on stage 0 culls against the PREVIOUS frame's
+    HZB and stage 1 re-tests the rejects - every frame's post-cull list and packed surface must equal the oracle's, which is
+    run with the oracle's own history."""
+    import subprocess
+    from cases import city_frames
+    exe = exe or _demo_exe()
+    w, h = 640, 360
+    scene, info, frames = city_frames(frames=3, w=w, h=h)
+    blob, out = tmp_path / 'path.blob', tmp_path / 'path.out'
+    _write_demo_blob(blob, scene, info, frames, w, h)
+    res = subprocess.run([exe, str(blob), str(out), 'path'], capture_output=True, text=True, timeout=900)
+    assert res.returncode == 0, res.stdout + res.stderr
+    got = _read_demo_frames(out, len(frames), w, h)
+    prev = None
+    for i, (f, (cmds, vis)) in enumerate(zip(frames, got)):
+        ref = oracle.run_frame(scene, f['view'], f['iview'], f['objects'], w, h, info['lod0MeshletCount'], prev)
+        _assert_lists_equal(cmds, ref['post_cull'], f'C++ renderer frame {i}')
+        _assert_vis_equal(vis, ref['vis64'], f'C++ renderer frame {i}')
+        prev = ref['hzb']
 
 
 def test_builder_asset_parity(gpu_ctx):

@@ -149,3 +149,24 @@ def test_kernels_under_ubsan(tmp_path_factory):
         "print('ubsan-clean')\n") % (os.path.dirname(HERE), HERE, so)
     r = subprocess.run([sys.executable, '-c', script], capture_output=True, text=True, timeout=1200)
     assert r.returncode == 0 and 'ubsan-clean' in r.stdout, r.stderr[-3000:]
+
+
+@pytest.fixture(scope='module')
+def host_demo(host_ctx, tmp_path_factory):
+    """examples/chord_b200_demo.cpp (native C++ host over include/chord_b200.hpp) linked against the scratch library."""
+    import subprocess
+    from chord_b200 import runtime
+    root = os.path.dirname(HERE)
+    exe = str(tmp_path_factory.mktemp('hostcc_demo') / 'chord_b200_demo_hostcc')
+    libdir = os.path.dirname(runtime.LIB_PATH)
+    subprocess.check_call(['g++', '-O2', '-std=c++17', '-I', os.path.join(root, 'include'), os.path.join(root, 'examples', 'chord_b200_demo.cpp'),
+                           '-o', exe, '-L', libdir, '-l:' + os.path.basename(runtime.LIB_PATH), '-Wl,-rpath,' + libdir])
+    return exe
+
+
+def test_native_cpp_host(host_ctx, cases, host_demo, tmp_path):
+    cases.test_native_cpp_host(host_ctx, tmp_path, exe=host_demo)
+
+
+def test_native_cpp_renderer_camera_path(host_ctx, cases, host_demo, tmp_path):
+    cases.test_native_cpp_renderer_camera_path(host_ctx, tmp_path, exe=host_demo)
