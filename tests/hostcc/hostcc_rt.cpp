@@ -14,6 +14,14 @@
 
 #include <vector>
 
+// AddressSanitizer has to be told about every stack switch (hostcc_build.build(extra=('-fsanitize=address',)))
+#if defined(__SANITIZE_ADDRESS__)
+#include <sanitizer/common_interface_defs.h>
+#define HOSTCC_ASAN 1
+#else
+#define HOSTCC_ASAN 0
+#endif
+
 uint3 threadIdx, blockIdx;
 dim3 blockDim, gridDim;
 
@@ -50,7 +58,22 @@ const std::function<void()>* g_body = nullptr;
 unsigned g_blockAlive = 0, g_blockArrived = 0;
 unsigned long long g_blockGen = 0;
 
-void switch_out() { swapcontext(&g_cur->uc, &g_sched); }
+#if HOSTCC_ASAN
+void* g_schedFake = nullptr; const void* g_schedBottom = nullptr; size_t g_schedSize = 0;
+#endif
+
+void switch_out()
+{
+#if HOSTCC_ASAN
+    Lane* me = g_cur;
+    void* fake = nullptr;
+    __sanitizer_start_switch_fiber(me->done ? nullptr : &fake, g_schedBottom, g_schedSize);
+    swapcontext(&me->uc, &g_sched);
+    __sanitizer_finish_switch_fiber(fake, &g_schedBottom, &g_schedSize);
+#else
+    swapcontext(&g_cur->uc, &g_sched);
+#endif
+}
 
 void wait_for(const unsigned long long* gen, unsigned long long at)
 {
@@ -70,6 +93,9 @@ void finish_rendezvous(Warp& w)
 void lane_entry()
 {
     Lane* me = g_cur;
+#if HOSTCC_ASAN
+    __sanitizer_finish_switch_fiber(nullptr, &g_schedBottom, &g_schedSize);
+#endif
     (*g_body)();
     me->done = true;
     // a returned thread no longer takes part in barriers / collectives: it may complete the ones its siblings wait in
@@ -112,7 +138,13 @@ void run_block(dim3 block)
             if (l.done) continue;
             if (l.waitGen && *l.waitGen == l.waitAt) continue;           // still blocked
             g_cur = &l; threadIdx = l.tid;
+#if HOSTCC_ASAN
+            __sanitizer_start_switch_fiber(&g_schedFake, g_stacks + (size_t)i * kStackBytes, kStackBytes);
             swapcontext(&g_sched, &l.uc);
+            __sanitizer_finish_switch_fiber(g_schedFake, nullptr, nullptr);
+#else
+            swapcontext(&g_sched, &l.uc);
+#endif
             ran = true;
             if (l.done) remaining--;
         }

@@ -170,3 +170,28 @@ def test_native_cpp_host(host_ctx, cases, host_demo, tmp_path):
 
 def test_native_cpp_renderer_camera_path(host_ctx, cases, host_demo, tmp_path):
     cases.test_native_cpp_renderer_camera_path(host_ctx, tmp_path, exe=host_demo)
+
+
+@slow
+def test_kernels_under_asan(tmp_path_factory):
+    """The same sources built with -fsanitize=address (hostcc_rt.cpp announces every coroutine switch to the sanitizer): an
+    out-of-bounds access of a kernel to "device" memory (heap blocks here), to its shared-memory arrays or to its stack aborts
+    the process.  Covers the TMA superset reads of ragged meshlets (which rely on the 64 bytes of padding chord_scene_upload
+    gives every array), the HZB edge gathers, the tile marker's clamp and both resolve paths."""
+    import subprocess
+    import hostcc_build
+    so = hostcc_build.build(tmp_path_factory.mktemp('hostcc_asan'), extra=('-fsanitize=address', '-fno-omit-frame-pointer'))
+    asan = subprocess.check_output(['gcc', '-print-file-name=libasan.so'], text=True).strip()
+    script = (
+        "import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "from chord_b200 import runtime\n"
+        "runtime.LIB_PATH, runtime._lib = %r, None\n"
+        "import test_gpu_parity as G\n"
+        "ctx = runtime.Context(0)\n"
+        "G.test_s1_single_meshlet(ctx); G.test_patch_stream_raster(ctx, 3000, 640, 360, 1.0); G.test_ragged_meshlets(ctx)\n"
+        "G.test_city_frames(ctx); G.test_lighting_resolve(ctx); G.test_hzb_chain_combinations(ctx)\n"
+        "for wh in ((264, 72), (72, 264)): G.test_tile_marker_odd_tile_counts(ctx, *wh)\n"
+        "print('asan-clean')\n") % (os.path.dirname(HERE), HERE, so)
+    env = dict(os.environ, LD_PRELOAD=asan, ASAN_OPTIONS='detect_leaks=0:detect_stack_use_after_return=0:halt_on_error=1')
+    r = subprocess.run([sys.executable, '-c', script], capture_output=True, text=True, timeout=2400, env=env)
+    assert r.returncode == 0 and 'asan-clean' in r.stdout, r.stderr[-3000:]
