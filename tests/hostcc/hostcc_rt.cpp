@@ -12,6 +12,7 @@
 #include <sys/mman.h>
 #include <ucontext.h>
 
+#include <utility>
 #include <vector>
 
 // AddressSanitizer has to be told about every stack switch (hostcc_build.build(extra=('-fsanitize=address',)))
@@ -130,10 +131,19 @@ void run_block(dim3 block)
         l.uc.uc_link = nullptr;
         makecontext(&l.uc, lane_entry, 0);
     }
+    // Scheduling order of the runnable threads: a correctly synchronised kernel does not care.  HOSTCC_ORDER=reverse | random
+    // (seeded) runs them back to front / shuffled per round: a missing barrier shows up as a changed result.
+    static const int order = [] { const char* e = getenv("HOSTCC_ORDER"); return !e ? 0 : !strcmp(e, "reverse") ? 1 : !strcmp(e, "random") ? 2 : 0; }();
+    static unsigned long long rng = 0x9E3779B97F4A7C15ull;
+    std::vector<unsigned> perm(n);
+    for (unsigned i = 0; i < n; i++) perm[i] = order == 1 ? n - 1 - i : i;
     unsigned remaining = n;
     while (remaining) {
         bool ran = false;
-        for (unsigned i = 0; i < n; i++) {
+        if (order == 2)
+            for (unsigned i = n - 1; i > 0; i--) { rng = rng * 6364136223846793005ull + 1442695040888963407ull; std::swap(perm[i], perm[(unsigned)((rng >> 33) % (i + 1))]); }
+        for (unsigned k = 0; k < n; k++) {
+            const unsigned i = perm[k];
             Lane& l = g_lanes[i];
             if (l.done) continue;
             if (l.waitGen && *l.waitGen == l.waitAt) continue;           // still blocked

@@ -195,3 +195,25 @@ def test_kernels_under_asan(tmp_path_factory):
     env = dict(os.environ, LD_PRELOAD=asan, ASAN_OPTIONS='detect_leaks=0:detect_stack_use_after_return=0:halt_on_error=1')
     r = subprocess.run([sys.executable, '-c', script], capture_output=True, text=True, timeout=2400, env=env)
     assert r.returncode == 0 and 'asan-clean' in r.stdout, r.stderr[-3000:]
+
+
+@slow
+@pytest.mark.parametrize('order', ['reverse', 'random'])
+def test_results_do_not_depend_on_thread_order(host_ctx, order):
+    """The executor normally resumes a block's threads front to back; HOSTCC_ORDER runs them back to front / shuffled per round
+    (threads still run from one synchronisation point to the next).  A kernel that reads what a sibling writes without a
+    barrier / rendezvous between the two would now see a different value: every case must still produce the oracle's bits."""
+    import subprocess
+    from chord_b200 import runtime
+    script = (
+        "import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "from chord_b200 import runtime\n"
+        "runtime.LIB_PATH, runtime._lib = %r, None\n"
+        "import test_gpu_parity as G\n"
+        "ctx = runtime.Context(0)\n"
+        "G.test_s1_single_meshlet(ctx); G.test_patch_stream_raster(ctx, 3000, 640, 360, 1.0); G.test_ragged_meshlets(ctx)\n"
+        "G.test_city_frames(ctx); G.test_hzb_culling_lists(ctx); G.test_lighting_resolve(ctx); G.test_bvh_traversal(ctx)\n"
+        "G.test_masked_bucket(ctx); G.test_hzb_chain_combinations(ctx); G.test_cascade_setup_on_device(ctx)\n"
+        "print('order-independent')\n") % (os.path.dirname(HERE), HERE, runtime.LIB_PATH)
+    r = subprocess.run([sys.executable, '-c', script], capture_output=True, text=True, timeout=2400, env=dict(os.environ, HOSTCC_ORDER=order))
+    assert r.returncode == 0 and 'order-independent' in r.stdout, r.stderr[-3000:]
