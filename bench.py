@@ -507,6 +507,32 @@ def main():
     L.chord_readback_visibility32(frame.h, C.c_void_p(chk.ctypes.data))
     a_img = pin_vis[(e2e_i[0] - 1) & 1].numpy().view(np.uint32).reshape(H4K, W4K)[tile[1]:tile[3], tile[0]:tile[2]]
     assert np.array_equal(chk.reshape(H4K, W4K)[tile[1]:tile[3], tile[0]:tile[2]], a_img), 'async read-back differs'
+    # Untimed probe: list upload and image read-back on ONE transfer stream (one PCIe transfer at a time) or on two (full
+    # duplex)?  Two streams shorten the transfers but slow the raster they overlap; which one wins depends on how the raster
+    # time compares with the transfer time, i.e. on the kernel version and on the box's PCIe link.  The timed leg below uses
+    # the faster mode (chord_frame_set_readback_stream); both probe figures are reported.
+    def e2e_probe(own):
+        L.chord_frame_set_readback_stream(frame.h, C.c_int(own))
+        for _ in range(3):
+            step_e2e()
+        L.chord_frame_wait_readbacks(frame.h)
+        barrier()
+        tp = time.perf_counter()
+        for _ in range(10):
+            step_e2e()
+        L.chord_frame_wait_readbacks(frame.h)
+        ctx.sync()
+        return (time.perf_counter() - tp) / 10 * 1e3
+    probe = torch.tensor([e2e_probe(0), e2e_probe(1)], dtype=torch.float64, device=f'cuda:{local_rank}')
+    if dist is not None:
+        dist.all_reduce(probe, op=dist.ReduceOp.MAX)
+    probe_ms = [float(x) for x in probe.tolist()]
+    own_stream = 1 if probe_ms[1] < 0.97 * probe_ms[0] else 0          # switch only for a clear win
+    L.chord_frame_set_readback_stream(frame.h, C.c_int(own_stream))
+    for _ in range(2):
+        step_e2e()
+    L.chord_frame_wait_readbacks(frame.h)
+    barrier()
     t0 = time.perf_counter()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
@@ -566,7 +592,8 @@ def main():
                        'submission': 'eager launches' if graph is None else f'recorded step replayed as one CUDA graph ({graph.kernel_nodes} kernel nodes + uniform upload + clears)'},
             'e2e': {'value': e2e_value, 'unit': 'Mtri/s', 'h2d_bytes_per_step': int(n_local * 12 + 1728 + 288 + 224),
                     'd2h_bytes_per_step': int((tile[2] - tile[0]) * (tile[3] - tile[1]) * 4), 'ms_per_step': e2e_ms / args.steps,
-                    'note': 'per rank and step: its draw list H2D (pinned) + its screen tile of the R32_UINT image D2H, both pipelined against the raster (list of step i+1 up / image of step i-1 down while step i runs), all inside the timed region'},
+                    'transfer_streams': 2 if own_stream else 1, 'probe_ms_per_step': {'one_stream': probe_ms[0], 'two_streams': probe_ms[1]},
+                    'note': 'per rank and step: its draw list H2D (pinned) + its screen tile of the R32_UINT image D2H, both pipelined against the raster (list of step i+1 up / image of step i-1 down while step i runs), all inside the timed region; an untimed probe picks one transfer stream or two (full duplex) first'},
             'gpu_launches': int(launches),
             'clocks': clocks,
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,

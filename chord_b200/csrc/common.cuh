@@ -251,6 +251,7 @@ struct chord_frame {
     void* resolveRecs; uint32_t resolveCapacity;
     // pipelined read-back of the R32_UINT image: two staging slots, a copy stream, events
     uint32_t* splitVis[2]; cudaStream_t copyStream; bool copyStreamShared; cudaEvent_t splitDone[2], copyDone[2]; int splitIdx;
+    cudaStream_t ownCopyStream;       // chord_frame_set_readback_stream(frame, 1): read-backs on a stream of their own
     chord_PerframeCameraView hView;   // host copy
     bool begun;
 };

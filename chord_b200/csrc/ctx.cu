@@ -399,7 +399,8 @@ void chord_frame_destroy(chord_frame* f)
     cudaFree(f->objGroupCount); cudaFree(f->objGroupBase); cudaFree(f->totalGroups);
     cudaFree(f->bvhEntries); cudaFree(f->bvhBits); cudaFree(f->bvhCtrl);
     cudaFree(f->works); cudaFree(f->redoList); cudaFree(f->maskedList); cudaFree(f->deferred);
-    if (f->copyStream) { cudaStreamSynchronize(f->copyStream); for (int k = 0; k < 2; k++) { cudaFree(f->splitVis[k]); cudaEventDestroy(f->splitDone[k]); cudaEventDestroy(f->copyDone[k]); } if (!f->copyStreamShared) cudaStreamDestroy(f->copyStream); }
+    if (f->copyStream) { cudaStreamSynchronize(f->copyStream); for (int k = 0; k < 2; k++) { cudaFree(f->splitVis[k]); cudaEventDestroy(f->splitDone[k]); cudaEventDestroy(f->copyDone[k]); } }
+    if (f->ownCopyStream) { cudaStreamSynchronize(f->ownCopyStream); cudaStreamDestroy(f->ownCopyStream); }
     cudaFree(f->largeTris); cudaFree(f->largeItems); cudaFree(f->largeCounters); cudaFree(f->stats);
     cudaFree(f->tileMarker); cudaFree(f->tileList); cudaFree(f->tileCount); cudaFree(f->resolveRecs);
     for (int i = 0; i < CHORD_GBUF_COUNT; i++) { cudaFree(f->gbuffer[i]); cudaFree(f->gbufferPackedBuf[i]); }
@@ -899,6 +900,27 @@ int chord_readback_visibility32_async(chord_frame* f, uint32_t* hostPinned)
                                      f->tile.y1 - f->tile.y0, cudaMemcpyDeviceToHost, f->copyStream));
     }
     CHORD_CUDA(cudaEventRecord(f->copyDone[k], f->copyStream));
+    return CHORD_OK;
+}
+
+// Which stream carries the pipelined read-backs: 0 (default) = the context's transfer stream, shared with the work-list
+// uploads, so that only one PCIe transfer is in flight at a time; 1 = a stream of the frame's own, so that the upload of the
+// next list and the read-back of the last image overlap each other as well (full duplex).  Which one wins depends on how
+// the step compares with the transfers: concurrent transfers slow the overlapped raster down (measured once: 17 %), one
+// after the other they take longer - bench.py probes both before its timed e2e leg.  Completes pending copies first.
+int chord_frame_set_readback_stream(chord_frame* f, int ownStream)
+{
+    CHORD_REQUIRE(f, "null");
+    const int rc = ensure_async_readback(f);
+    if (rc) return rc;
+    CHORD_CUDA(cudaStreamSynchronize(f->copyStream));
+    CHORD_CUDA(cudaStreamSynchronize(f->ctx->stream));
+    if (ownStream) {
+        if (!f->ownCopyStream) CHORD_CUDA(cudaStreamCreateWithFlags(&f->ownCopyStream, cudaStreamNonBlocking));
+        f->copyStream = f->ownCopyStream; f->copyStreamShared = false;
+    } else {
+        f->copyStream = f->ctx->uploadStream; f->copyStreamShared = true;
+    }
     return CHORD_OK;
 }
 

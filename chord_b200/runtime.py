@@ -16,7 +16,7 @@ SYMBOLS = [
     'chord_ctx_create', 'chord_ctx_destroy', 'chord_ctx_stream', 'chord_ctx_sync', 'chord_ctx_set_switch_flags',
     'chord_ctx_get_switch_flags', 'chord_ctx_kernel_launches', 'chord_scene_upload', 'chord_textures_upload',
     'chord_cmdlist_create', 'chord_cmdlist_destroy', 'chord_cmdlist_upload', 'chord_cmdlist_readback',
-    'chord_cmdlist_upload_async', 'chord_readback_visibility32_async', 'chord_frame_wait_readbacks', 'chord_cmdlist_capacity', 'chord_cmdlist_count_ptr', 'chord_cmdlist_cmds_ptr',
+    'chord_cmdlist_upload_async', 'chord_readback_visibility32_async', 'chord_frame_wait_readbacks', 'chord_frame_set_readback_stream', 'chord_cmdlist_capacity', 'chord_cmdlist_count_ptr', 'chord_cmdlist_cmds_ptr',
     'chord_hzb_create', 'chord_hzb_destroy', 'chord_hzb_info', 'chord_hzb_readback', 'chord_hzb_readback_valid_range',
     'chord_hzb_chain_ptr', 'chord_hzb_chain_bytes', 'chord_hzb_mip_offset', 'chord_hzb_set_valid', 'chord_hzb_is_valid',
     'chord_hzb_finish_top', 'chord_hzb_tile_bytes', 'chord_hzb_pack_tile', 'chord_hzb_unpack_tiles',

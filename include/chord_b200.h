@@ -262,7 +262,10 @@ int chord_readback_depth32(chord_frame* frame, float* host);
 /* pipelined variant: extraction on the context stream, PCIe copy on a second stream (two staging slots), so the next
  * frame overlaps the transfer; hostPinned must be page-locked. chord_frame_wait_readbacks completes all pending copies. */
 int chord_readback_visibility32_async(chord_frame* frame, uint32_t* hostPinned);
-int chord_frame_wait_readbacks(chord_frame* frame);           /* the reference's D32 image */
+int chord_frame_wait_readbacks(chord_frame* frame);
+/* Stream of the pipelined read-backs: 0 (default) = the context's one transfer stream, shared with chord_cmdlist_upload_async
+ * (one PCIe transfer at a time); 1 = a stream of the frame's own (uploads and read-backs overlap each other too). */
+int chord_frame_set_readback_stream(chord_frame* frame, int ownStream);
 /* decoded (objectId, meshletId, triangleId) per pixel through a post-instance-cull list
  * (visibility_tile.hlsl:47-60); 0xFFFFFFFF triple where no geometry. */
 int chord_readback_decoded(chord_frame* frame, chord_cmdlist* postInstanceCull, uint32_t* hostTriples);

@@ -253,6 +253,33 @@ def test_empty_lists_publish_zero_counts(gpu_ctx):
     assert len(oracle.Frame(scene, v2, iv2, objects, w, h).instance_culling(n)) == 0 and post.count() == 0
 
 
+def test_readback_stream_modes(gpu_ctx):
+    """chord_readback_visibility32_async on the shared transfer stream and on a stream of the frame's own
+    (chord_frame_set_readback_stream), full frame and screen tiles (linear and pitched copies): the image that arrives is the
+    synchronous read-back's, and switching back and forth completes what is in flight."""
+    import ctypes as C
+    L = runtime.lib()
+    w, h, n = 640, 384, 150
+    scene, camera, objects, cmds = synth.patch_stream_scene(n, w, h, seed=5, overdraw_scale=12.0)
+    view = cam.fill_view(camera)
+    iview = cam.fill_instance_view(view)
+    gpu_ctx.upload_scene(scene)
+    lst = runtime.CmdList(gpu_ctx, n)
+    lst.upload(cmds)
+    for tile in (None, (0, 64, 640, 256), (128, 64, 512, 256)):
+        fr = runtime.Frame(gpu_ctx, w, h)
+        for own in (0, 1, 0):
+            L.chord_frame_set_readback_stream(fr.h, C.c_int(own))
+            fr.begin(view, iview, objects, n, (n + 3) // 4, tile)
+            fr.render_mesh(lst)
+            a = np.zeros(w * h, dtype=np.uint32)
+            L.chord_readback_visibility32_async(fr.h, C.c_void_p(a.ctypes.data))
+            L.chord_frame_wait_readbacks(fr.h)
+            b = fr.visibility32().reshape(h, w)
+            x0, y0, x1, y1 = tile or (0, 0, w, h)
+            assert np.array_equal(a.reshape(h, w)[y0:y1, x0:x1], b[y0:y1, x0:x1]) and (b[y0:y1, x0:x1] != 0).any()
+
+
 def test_hzb_chain_combinations(gpu_ctx):
     """buildHZB(bMin, bMax, bValidRange) in every combination hzb.cpp:44-47 allows (each is its own kernel instantiation), on a
     frame that is neither a power of two nor a multiple of 64: interior, edge and off-screen 64x64 blocks."""

@@ -88,6 +88,10 @@ def test_empty_lists_publish_zero_counts(host_ctx, cases):
     cases.test_empty_lists_publish_zero_counts(host_ctx)
 
 
+def test_readback_stream_modes(host_ctx, cases):
+    cases.test_readback_stream_modes(host_ctx)
+
+
 def test_hzb_chain_combinations(host_ctx, cases):
     cases.test_hzb_chain_combinations(host_ctx)
 
