@@ -80,11 +80,15 @@ def _worker(rank, world, port, so, out_dir):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize('world', [2, 4])
-def test_tiled_frames_on_host_executor_gloo(tmp_path, tmp_path_factory, world):
+@pytest.fixture(scope='module')
+def scratch_lib(tmp_path_factory):
     sys.path.insert(0, os.path.join(HERE, 'hostcc'))
     import hostcc_build
-    so = hostcc_build.build(tmp_path_factory.mktemp('hostcc_lib_mr'))
+    return hostcc_build.build(tmp_path_factory.mktemp('hostcc_lib_mr'))
+
+
+@pytest.mark.parametrize('world', [2, 4])
+def test_tiled_frames_on_host_executor_gloo(tmp_path, scratch_lib, world):
     port = _free_port()
-    mp.spawn(_worker, args=(world, port, so, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, port, scratch_lib, str(tmp_path)), nprocs=world, join=True)
     assert open(tmp_path / 'result').read() == '1'
