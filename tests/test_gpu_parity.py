@@ -217,117 +217,6 @@ def test_tile_scissor(gpu_ctx):
     _assert_vis_equal(acc, full, 'union of tiles')
 
 
-def test_empty_lists_publish_zero_counts(gpu_ctx):
-    """The cull kernels publish their list counts themselves (no memset in front of them): an empty input list and a frame in
-    which every object is culled must overwrite a stale count with zero."""
-    import ctypes as C
-    w, h, n = 256, 256, 200
-    scene, camera, objects, cmds = synth.patch_stream_scene(n, w, h, seed=5)
-    view = cam.fill_view(camera)
-    iview = cam.fill_instance_view(view)
-    gpu_ctx.upload_scene(scene)
-    fr = runtime.Frame(gpu_ctx, w, h)
-    fr.begin(view, iview, objects, n, (n + 3) // 4)
-    full = runtime.CmdList(gpu_ctx, n)
-    full.upload(cmds)
-    fr.render_mesh(full)
-    hz = runtime.Hzb(gpu_ctx, w, h)
-    fr.build_hzb(hz, True, False, False)
-    stale_v, stale_r, empty = runtime.CmdList(gpu_ctx, n), runtime.CmdList(gpu_ctx, n), runtime.CmdList(gpu_ctx, n)
-    stale_v.upload(cmds)
-    stale_r.upload(cmds)
-    empty.upload(cmds[:0])
-    L = runtime.lib()
-    L.chord_hzb_culling(fr.h, hz.h, C.c_int(1), empty.h, stale_v.h, stale_r.h)
-    assert stale_v.count() == 0 and stale_r.count() == 0
-    stale_v.upload(cmds)
-    L.chord_hzb_culling(fr.h, hz.h, C.c_int(0), empty.h, stale_v.h, None)
-    assert stale_v.count() == 0
-    away = cam.Camera(camera.position, -camera.front, width=w, height=h)
-    v2 = cam.fill_view(away)
-    iv2 = cam.fill_instance_view(v2)
-    fr.begin(v2, iv2, objects, n, (n + 3) // 4)
-    post = runtime.CmdList(gpu_ctx, n)
-    post.upload(cmds)
-    fr.instance_culling(post)
-    assert len(oracle.Frame(scene, v2, iv2, objects, w, h).instance_culling(n)) == 0 and post.count() == 0
-
-
-def test_readback_stream_modes(gpu_ctx):
-    """chord_readback_visibility32_async on the shared transfer stream and on a stream of the frame's own
-    (chord_frame_set_readback_stream), full frame and screen tiles (linear and pitched copies): the image that arrives is the
-    synchronous read-back's, and switching back and forth completes what is in flight."""
-    import ctypes as C
-    L = runtime.lib()
-    w, h, n = 640, 384, 150
-    scene, camera, objects, cmds = synth.patch_stream_scene(n, w, h, seed=5, overdraw_scale=12.0)
-    view = cam.fill_view(camera)
-    iview = cam.fill_instance_view(view)
-    gpu_ctx.upload_scene(scene)
-    lst = runtime.CmdList(gpu_ctx, n)
-    lst.upload(cmds)
-    for tile in (None, (0, 64, 640, 256), (128, 64, 512, 256)):
-        fr = runtime.Frame(gpu_ctx, w, h)
-        for own in (0, 1, 0):
-            L.chord_frame_set_readback_stream(fr.h, C.c_int(own))
-            fr.begin(view, iview, objects, n, (n + 3) // 4, tile)
-            fr.render_mesh(lst)
-            a = np.zeros(w * h, dtype=np.uint32)
-            L.chord_readback_visibility32_async(fr.h, C.c_void_p(a.ctypes.data))
-            L.chord_frame_wait_readbacks(fr.h)
-            b = fr.visibility32().reshape(h, w)
-            x0, y0, x1, y1 = tile or (0, 0, w, h)
-            assert np.array_equal(a.reshape(h, w)[y0:y1, x0:x1], b[y0:y1, x0:x1]) and (b[y0:y1, x0:x1] != 0).any()
-
-
-def test_hzb_chain_combinations(gpu_ctx):
-    """buildHZB(bMin, bMax, bValidRange) in every combination hzb.cpp:44-47 allows (each is its own kernel instantiation), on a
-    frame that is neither a power of two nor a multiple of 64: interior, edge and off-screen 64x64 blocks."""
-    w, h, n = 328, 200, 300
-    scene, camera, objects, cmds = synth.patch_stream_scene(n, w, h, seed=5, overdraw_scale=20.0)
-    view = cam.fill_view(camera)
-    iview = cam.fill_instance_view(view)
-    gpu_ctx.upload_scene(scene)
-    fr = runtime.Frame(gpu_ctx, w, h)
-    fr.begin(view, iview, objects, n, (n + 3) // 4)
-    lst = runtime.CmdList(gpu_ctx, n)
-    lst.upload(cmds)
-    fr.render_mesh(lst)
-    ofr = oracle.Frame(scene, view, iview, objects, w, h)
-    ovis, _ = ofr.render_mesh(cmds)
-    _assert_vis_equal(fr.vis64(), ovis, 'vis64')
-    for bmin, bmax, brange in ((True, False, False), (False, True, False), (True, True, False), (True, True, True)):
-        hz = runtime.Hzb(gpu_ctx, w, h)
-        fr.build_hzb(hz, bmin, bmax, brange)
-        oh = ofr.build_hzb(ovis, bmin, bmax, brange)
-        if bmin:
-            _assert_hzb_equal(hz, oh, 'min')
-        if bmax:
-            _assert_hzb_equal(hz, oh, 'max')
-        if brange:
-            assert np.array_equal(hz.valid_range(), oh['range'])
-
-
-@pytest.mark.parametrize('w,h', [(264, 72), (72, 264), (200, 200)])
-def test_tile_marker_odd_tile_counts(gpu_ctx, w, h):
-    """K9 classifies two 8x8 tiles per warp: frames whose tile count is odd / whose edges cut tiles (clamp-to-edge gather)."""
-    n = 300
-    scene, camera, objects, cmds = synth.patch_stream_scene(n, w, h, seed=5, overdraw_scale=20.0)
-    view = cam.fill_view(camera)
-    iview = cam.fill_instance_view(view)
-    gpu_ctx.upload_scene(scene)
-    fr = runtime.Frame(gpu_ctx, w, h)
-    fr.begin(view, iview, objects, n, (n + 3) // 4)
-    lst = runtime.CmdList(gpu_ctx, n)
-    lst.upload(cmds)
-    fr.render_mesh(lst)
-    fr.visibility_mark(lst)
-    ofr = oracle.Frame(scene, view, iview, objects, w, h)
-    ovis, _ = ofr.render_mesh(cmds)
-    _assert_vis_equal(fr.vis64(), ovis, f'vis64 {w}x{h}')
-    assert np.array_equal(fr.tile_marker(), ofr.visibility_mark(ovis, cmds))
-
-
 def test_lighting_resolve(gpu_ctx):
     """K9-K11: tile classification + PBR resolve. Floating point: |gpu - oracle| <= 1e-5 (north_star tolerance) on the
     pre-quantisation fp32 G-buffer planes; untouched pixels must stay cleared."""
@@ -609,29 +498,6 @@ def test_native_cpp_host(gpu_ctx, tmp_path, exe=None):
         (cmds, vis), = _read_demo_frames(out, 1, w, h)
         _assert_lists_equal(cmds, ref['post_cull'], f'native host {mode}')
         _assert_vis_equal(vis, ref['vis64'], f'native host {mode}')
-
-
-def test_native_cpp_renderer_camera_path(gpu_ctx, tmp_path, exe=None):
-    """chord_b200::DeferredRenderer (include/chord_b200.hpp), the C++ mirror of renderer.cpp:311-363 + the history hand-off at
-    :489, driven by native host code over a camera path: from the second frame on stage 0 culls against the PREVIOUS frame's
-    HZB and stage 1 re-tests the rejects - every frame's post-cull list and packed surface must equal the oracle's, which is
-    run with the oracle's own history."""
-    import subprocess
-    from cases import city_frames
-    exe = exe or _demo_exe()
-    w, h = 640, 360
-    scene, info, frames = city_frames(frames=3, w=w, h=h)
-    blob, out = tmp_path / 'path.blob', tmp_path / 'path.out'
-    _write_demo_blob(blob, scene, info, frames, w, h)
-    res = subprocess.run([exe, str(blob), str(out), 'path'], capture_output=True, text=True, timeout=900)
-    assert res.returncode == 0, res.stdout + res.stderr
-    got = _read_demo_frames(out, len(frames), w, h)
-    prev = None
-    for i, (f, (cmds, vis)) in enumerate(zip(frames, got)):
-        ref = oracle.run_frame(scene, f['view'], f['iview'], f['objects'], w, h, info['lod0MeshletCount'], prev)
-        _assert_lists_equal(cmds, ref['post_cull'], f'C++ renderer frame {i}')
-        _assert_vis_equal(vis, ref['vis64'], f'C++ renderer frame {i}')
-        prev = ref['hzb']
 
 
 def test_builder_asset_parity(gpu_ctx):
@@ -927,3 +793,170 @@ def test_cascade_setup_on_device(gpu_ctx):
         if fi == 1:
             # second frame, cache valid: realtime cascades + one far cascade (tick 1 -> cascade 3) were re-rendered
             pass
+
+
+# ---- cases added after the last GPU run of round 1 (host-executor verified); kept at the end of the file
+def test_empty_lists_publish_zero_counts(gpu_ctx):
+    """The cull kernels publish their list counts themselves (no memset in front of them): an empty input list and a frame in
+    which every object is culled must overwrite a stale count with zero."""
+    import ctypes as C
+    w, h, n = 256, 256, 200
+    scene, camera, objects, cmds = synth.patch_stream_scene(n, w, h, seed=5)
+    view = cam.fill_view(camera)
+    iview = cam.fill_instance_view(view)
+    gpu_ctx.upload_scene(scene)
+    fr = runtime.Frame(gpu_ctx, w, h)
+    fr.begin(view, iview, objects, n, (n + 3) // 4)
+    full = runtime.CmdList(gpu_ctx, n)
+    full.upload(cmds)
+    fr.render_mesh(full)
+    hz = runtime.Hzb(gpu_ctx, w, h)
+    fr.build_hzb(hz, True, False, False)
+    stale_v, stale_r, empty = runtime.CmdList(gpu_ctx, n), runtime.CmdList(gpu_ctx, n), runtime.CmdList(gpu_ctx, n)
+    stale_v.upload(cmds)
+    stale_r.upload(cmds)
+    empty.upload(cmds[:0])
+    L = runtime.lib()
+    L.chord_hzb_culling(fr.h, hz.h, C.c_int(1), empty.h, stale_v.h, stale_r.h)
+    assert stale_v.count() == 0 and stale_r.count() == 0
+    stale_v.upload(cmds)
+    L.chord_hzb_culling(fr.h, hz.h, C.c_int(0), empty.h, stale_v.h, None)
+    assert stale_v.count() == 0
+    away = cam.Camera(camera.position, -camera.front, width=w, height=h)
+    v2 = cam.fill_view(away)
+    iv2 = cam.fill_instance_view(v2)
+    fr.begin(v2, iv2, objects, n, (n + 3) // 4)
+    post = runtime.CmdList(gpu_ctx, n)
+    post.upload(cmds)
+    fr.instance_culling(post)
+    assert len(oracle.Frame(scene, v2, iv2, objects, w, h).instance_culling(n)) == 0 and post.count() == 0
+
+
+def test_readback_stream_modes(gpu_ctx):
+    """chord_readback_visibility32_async on the shared transfer stream and on a stream of the frame's own
+    (chord_frame_set_readback_stream), full frame and screen tiles (linear and pitched copies): the image that arrives is the
+    synchronous read-back's, and switching back and forth completes what is in flight."""
+    import ctypes as C
+    L = runtime.lib()
+    w, h, n = 640, 384, 150
+    scene, camera, objects, cmds = synth.patch_stream_scene(n, w, h, seed=5, overdraw_scale=12.0)
+    view = cam.fill_view(camera)
+    iview = cam.fill_instance_view(view)
+    gpu_ctx.upload_scene(scene)
+    lst = runtime.CmdList(gpu_ctx, n)
+    lst.upload(cmds)
+    for tile in (None, (0, 64, 640, 256), (128, 64, 512, 256)):
+        fr = runtime.Frame(gpu_ctx, w, h)
+        for own in (0, 1, 0):
+            L.chord_frame_set_readback_stream(fr.h, C.c_int(own))
+            fr.begin(view, iview, objects, n, (n + 3) // 4, tile)
+            fr.render_mesh(lst)
+            a = np.zeros(w * h, dtype=np.uint32)
+            L.chord_readback_visibility32_async(fr.h, C.c_void_p(a.ctypes.data))
+            L.chord_frame_wait_readbacks(fr.h)
+            b = fr.visibility32().reshape(h, w)
+            x0, y0, x1, y1 = tile or (0, 0, w, h)
+            assert np.array_equal(a.reshape(h, w)[y0:y1, x0:x1], b[y0:y1, x0:x1]) and (b[y0:y1, x0:x1] != 0).any()
+
+
+def test_hzb_chain_combinations(gpu_ctx):
+    """buildHZB(bMin, bMax, bValidRange) in every combination hzb.cpp:44-47 allows (each is its own kernel instantiation), on a
+    frame that is neither a power of two nor a multiple of 64: interior, edge and off-screen 64x64 blocks."""
+    w, h, n = 328, 200, 300
+    scene, camera, objects, cmds = synth.patch_stream_scene(n, w, h, seed=5, overdraw_scale=20.0)
+    view = cam.fill_view(camera)
+    iview = cam.fill_instance_view(view)
+    gpu_ctx.upload_scene(scene)
+    fr = runtime.Frame(gpu_ctx, w, h)
+    fr.begin(view, iview, objects, n, (n + 3) // 4)
+    lst = runtime.CmdList(gpu_ctx, n)
+    lst.upload(cmds)
+    fr.render_mesh(lst)
+    ofr = oracle.Frame(scene, view, iview, objects, w, h)
+    ovis, _ = ofr.render_mesh(cmds)
+    _assert_vis_equal(fr.vis64(), ovis, 'vis64')
+    for bmin, bmax, brange in ((True, False, False), (False, True, False), (True, True, False), (True, True, True)):
+        hz = runtime.Hzb(gpu_ctx, w, h)
+        fr.build_hzb(hz, bmin, bmax, brange)
+        oh = ofr.build_hzb(ovis, bmin, bmax, brange)
+        if bmin:
+            _assert_hzb_equal(hz, oh, 'min')
+        if bmax:
+            _assert_hzb_equal(hz, oh, 'max')
+        if brange:
+            assert np.array_equal(hz.valid_range(), oh['range'])
+
+
+@pytest.mark.parametrize('w,h', [(264, 72), (72, 264), (200, 200)])
+def test_tile_marker_odd_tile_counts(gpu_ctx, w, h):
+    """K9 classifies two 8x8 tiles per warp: frames whose tile count is odd / whose edges cut tiles (clamp-to-edge gather)."""
+    n = 300
+    scene, camera, objects, cmds = synth.patch_stream_scene(n, w, h, seed=5, overdraw_scale=20.0)
+    view = cam.fill_view(camera)
+    iview = cam.fill_instance_view(view)
+    gpu_ctx.upload_scene(scene)
+    fr = runtime.Frame(gpu_ctx, w, h)
+    fr.begin(view, iview, objects, n, (n + 3) // 4)
+    lst = runtime.CmdList(gpu_ctx, n)
+    lst.upload(cmds)
+    fr.render_mesh(lst)
+    fr.visibility_mark(lst)
+    ofr = oracle.Frame(scene, view, iview, objects, w, h)
+    ovis, _ = ofr.render_mesh(cmds)
+    _assert_vis_equal(fr.vis64(), ovis, f'vis64 {w}x{h}')
+    assert np.array_equal(fr.tile_marker(), ofr.visibility_mark(ovis, cmds))
+
+
+def test_native_cpp_renderer_camera_path(gpu_ctx, tmp_path, exe=None):
+    """chord_b200::DeferredRenderer (include/chord_b200.hpp), the C++ mirror of renderer.cpp:311-363 + the history hand-off at
+    :489, driven by native host code over a camera path: from the second frame on stage 0 culls against the PREVIOUS frame's
+    HZB and stage 1 re-tests the rejects - every frame's post-cull list and packed surface must equal the oracle's, which is
+    run with the oracle's own history."""
+    import subprocess
+    from cases import city_frames
+    exe = exe or _demo_exe()
+    w, h = 640, 360
+    scene, info, frames = city_frames(frames=3, w=w, h=h)
+    blob, out = tmp_path / 'path.blob', tmp_path / 'path.out'
+    _write_demo_blob(blob, scene, info, frames, w, h)
+    res = subprocess.run([exe, str(blob), str(out), 'path'], capture_output=True, text=True, timeout=900)
+    assert res.returncode == 0, res.stdout + res.stderr
+    got = _read_demo_frames(out, len(frames), w, h)
+    prev = None
+    for i, (f, (cmds, vis)) in enumerate(zip(frames, got)):
+        ref = oracle.run_frame(scene, f['view'], f['iview'], f['objects'], w, h, info['lod0MeshletCount'], prev)
+        _assert_lists_equal(cmds, ref['post_cull'], f'C++ renderer frame {i}')
+        _assert_vis_equal(vis, ref['vis64'], f'C++ renderer frame {i}')
+        prev = ref['hzb']
+
+
+def test_extreme_frame_shapes(gpu_ctx, shapes=((64, 64), (4096, 64), (64, 4096), (4096, 128))):
+    """Render dimensions at the limits renderer.h:52-53 allows: the 64 x 64 minimum (six HZB mips, the fewest hzb.cpp:119
+    accepts) and the 4096 maximum in one axis with the other tiny (twelve mips, the non-square tail of the chain where one
+    dimension has run out): instance cull, raster, HZB min / max / range and the tile marker against the oracle."""
+    for (w, h) in shapes:
+        n = 120
+        scene, camera, objects, cmds = synth.patch_stream_scene(n, w, h, seed=7, overdraw_scale=30.0)
+        view = cam.fill_view(camera)
+        iview = cam.fill_instance_view(view)
+        gpu_ctx.upload_scene(scene)
+        fr = runtime.Frame(gpu_ctx, w, h)
+        fr.begin(view, iview, objects, n, (n + 3) // 4)
+        post = runtime.CmdList(gpu_ctx, n)
+        fr.instance_culling(post)
+        ofr = oracle.Frame(scene, view, iview, objects, w, h)
+        opost = ofr.instance_culling(n)
+        _assert_lists_equal(post.readback(), opost, f'post-cull list {w}x{h}')
+        fr.render_mesh(post)
+        ovis, _ = ofr.render_mesh(opost)
+        _assert_vis_equal(fr.vis64(), ovis, f'vis64 {w}x{h}')
+        assert (ovis != 0).sum() > w * h // 8
+        hz = runtime.Hzb(gpu_ctx, w, h)
+        fr.build_hzb(hz, True, True, True)
+        oh = ofr.build_hzb(ovis, True, True, True)
+        assert hz.mips == oh['mips'] == (6 if max(w, h) == 64 else 12)
+        _assert_hzb_equal(hz, oh, 'min')
+        _assert_hzb_equal(hz, oh, 'max')
+        assert np.array_equal(hz.valid_range(), oh['range'])
+        fr.visibility_mark(post)
+        assert np.array_equal(fr.tile_marker(), ofr.visibility_mark(ovis, opost))

@@ -88,6 +88,10 @@ def test_empty_lists_publish_zero_counts(host_ctx, cases):
     cases.test_empty_lists_publish_zero_counts(host_ctx)
 
 
+def test_extreme_frame_shapes(host_ctx, cases):
+    cases.test_extreme_frame_shapes(host_ctx, **({} if FULL else {'shapes': ((64, 64), (4096, 64))}))
+
+
 def test_readback_stream_modes(host_ctx, cases):
     cases.test_readback_stream_modes(host_ctx)
 
