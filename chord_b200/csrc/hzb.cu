@@ -64,7 +64,7 @@ __device__ void hzb_top_levels(const HzbBuildParams& p, float* __restrict__ sMin
 // Specialised on what the call builds: the min-only build between the two visibility stages (renderer.cpp:334) carries
 // neither the max chain's reductions / shared-memory traffic nor the valid-range accumulation.
 template <bool kMin, bool kMax, bool kRange>
-__global__ void __launch_bounds__(256) k_hzb_build(HzbBuildParams p)
+__global__ void __launch_bounds__(256, (kMin && kMax) ? 6 : 8) k_hzb_build(HzbBuildParams p)
 {
     __shared__ float sMinP[kMin ? 1024 : 1], sMinQ[kMin ? 256 : 1], sMaxP[kMax ? 1024 : 1], sMaxQ[kMax ? 256 : 1];
     const uint32_t bx = p.blockX0 + blockIdx.x, by = p.blockY0 + blockIdx.y;
@@ -106,6 +106,21 @@ __global__ void __launch_bounds__(256) k_hzb_build(HzbBuildParams p)
             const float d[4] = { __uint_as_float((uint32_t)(r0[k].x >> 32)), __uint_as_float((uint32_t)(r1[k].x >> 32)),
                                  __uint_as_float((uint32_t)(r0[k].y >> 32)), __uint_as_float((uint32_t)(r1[k].y >> 32)) };
             mip0_texel(l, x, y, d);
+        }
+    } else if (by * 64u >= p.height) {
+        // block entirely below the image (at 4K: 30 of the 64 block rows of the power-of-two dispatch): every source row clamps
+        // to the last image row, so the four texels of a thread (same column, rows 8 apart) see the same four pixels
+        const uint32_t x = bx * 32 + (tid & 31u);
+        float g[4];
+#pragma unroll
+        for (int s = 0; s < 4; s++) {
+            const uint32_t sx = min(2 * x + (uint32_t)(s >> 1), p.width - 1);
+            g[s] = __uint_as_float((uint32_t)(p.vis64[(size_t)(p.height - 1) * p.width + sx] >> 32));
+        }
+#pragma unroll
+        for (uint32_t k = 0; k < 4; k++) {
+            const uint32_t l = tid + k * 256;
+            mip0_texel(l, x, by * 32 + (l >> 5), g);
         }
     } else {
         // edge / off-screen block: clamp-to-edge gather (hzb.hlsl:139-150), again every load before the first use
