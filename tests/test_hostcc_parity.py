@@ -225,3 +225,11 @@ def test_results_do_not_depend_on_thread_order(host_ctx, order):
         "print('order-independent')\n") % (os.path.dirname(HERE), HERE, runtime.LIB_PATH)
     r = subprocess.run([sys.executable, '-c', script], capture_output=True, text=True, timeout=2400, env=dict(os.environ, HOSTCC_ORDER=order))
     assert r.returncode == 0 and 'order-independent' in r.stdout, r.stderr[-3000:]
+
+
+@slow
+def test_committed_golden_fixtures(host_ctx):
+    """tests/golden/ (fixtures committed with their generating script) against the host run of the kernels: the body of
+    tests/test_golden.py::test_cuda_matches_golden."""
+    import test_golden
+    test_golden.test_cuda_matches_golden(host_ctx)
