@@ -960,3 +960,30 @@ def test_extreme_frame_shapes(gpu_ctx, shapes=((64, 64), (4096, 64), (64, 4096),
         assert np.array_equal(hz.valid_range(), oh['range'])
         fr.visibility_mark(post)
         assert np.array_equal(fr.tile_marker(), ofr.visibility_mark(ovis, opost))
+
+
+def test_random_raster_cases(gpu_ctx, count=48, seed=2024):
+    """Seeded random cases (tests/fuzz_cases.py): packed surface bit-equal to the oracle in every case; the cull / clip
+    counters too where no scissor tile is set (with a tile, whole meshlets are rejected before they are counted).  The set
+    must contain near-plane / guard-band clipping and large triangles."""
+    from fuzz_cases import random_raster_case
+    rng = np.random.default_rng(seed)
+    clipped = large = 0
+    for i in range(count):
+        c = random_raster_case(rng)
+        gpu_ctx.upload_scene(c['scene'])
+        fr = runtime.Frame(gpu_ctx, c['w'], c['h'])
+        fr.begin(c['view'], c['iview'], c['objects'], c['lod0'], c['groups'], c['tile'])
+        lst = runtime.CmdList(gpu_ctx, len(c['cmds']))
+        lst.upload(c['cmds'])
+        fr.render_mesh(lst)
+        ovis, ost = oracle.Frame(c['scene'], c['view'], c['iview'], c['objects'], c['w'], c['h'], tile=c['tile']).render_mesh(c['cmds'])
+        _assert_vis_equal(fr.vis64(), ovis, f'random case {i} {c["what"]}')
+        st = fr.raster_stats()
+        if c['tile'] is None:
+            for k in ('trianglesSubmitted', 'trianglesCulled', 'trianglesClipped', 'meshletsRastered'):
+                assert st[k] == ost[k], (k, c['what'], st, ost)
+        assert st['largeQueueOverflow'] == 0
+        clipped += ost['trianglesClipped']
+        large += st['trianglesLarge']
+    assert clipped > 0 and large > 0, (clipped, large)

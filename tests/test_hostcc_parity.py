@@ -233,3 +233,7 @@ def test_committed_golden_fixtures(host_ctx):
     tests/test_golden.py::test_cuda_matches_golden."""
     import test_golden
     test_golden.test_cuda_matches_golden(host_ctx)
+
+
+def test_random_raster_cases(host_ctx, cases):
+    cases.test_random_raster_cases(host_ctx, count=48 if FULL else 14)
