@@ -987,3 +987,37 @@ def test_random_raster_cases(gpu_ctx, count=48, seed=2024):
         clipped += ost['trianglesClipped']
         large += st['trianglesLarge']
     assert clipped > 0 and large > 0, (clipped, large)
+
+
+def test_random_camera_frames(gpu_ctx, sequences=10, seed=777):
+    """Seeded random camera sequences around the city (3 frames each, so that stage 0 culls against a genuine previous-frame
+    HZB), random switch flags, flat or BVH instance cull: post-cull list, packed surface and both HZB chains of every frame
+    against the oracle run with its own history."""
+    rng = np.random.default_rng(seed)
+    w, h = 320, 200
+    scene, camera0, _, info = synth.city_scene(n_buildings=9, patches=4, lods=3, width=w, height=h, seed=2)
+    gpu_ctx.upload_scene(scene)
+    lod0, groups = info['lod0MeshletCount'], info['meshletGroupCount']
+    try:
+        for si in range(sequences):
+            flags = int(rng.choice([0b111, 0b111, 0b101, 0b011, 0b000]))
+            gpu_ctx.set_switch_flags(flags)
+            r = renderer.DeferredRenderer(gpu_ctx, w, h, use_bvh=bool(rng.integers(0, 2)))
+            base = camera0.position + rng.normal(0, 1, 3) * np.array([25.0, 4.0, 25.0])
+            base[1] = max(base[1], 0.4)
+            front = np.asarray(camera0.front, dtype=np.float64) + rng.normal(0, 0.5, 3)
+            prev = last_view = last_cam = None
+            for fi in range(3):
+                c = cam.Camera(base + rng.normal(0, 1, 3) * np.array([1.5, 0.2, 1.5]) * fi, front + rng.normal(0, 0.05, 3) * fi, width=w, height=h)
+                objs = synth.refill_objects(info['transforms'], c, camera_last=last_cam)
+                view = cam.fill_view(c, last_view=last_view, frame_counter=fi)
+                iview = cam.fill_instance_view(view)
+                post = r.render(c, objs, lod0, groups, view=view, iview=iview)
+                ref = oracle.run_frame(scene, view, iview, objs, w, h, lod0, prev, flags)
+                _assert_lists_equal(post.readback(), ref['post_cull'], f'sequence {si} frame {fi} flags {flags:03b}')
+                _assert_vis_equal(r.frame.vis64(), ref['vis64'], f'sequence {si} frame {fi}')
+                _assert_hzb_equal(r.history_hzb, ref['hzb'], 'min')
+                _assert_hzb_equal(r.history_hzb, ref['hzb'], 'max')
+                prev, last_view, last_cam = ref['hzb'], view, c
+    finally:
+        gpu_ctx.set_switch_flags(0b111)

@@ -237,3 +237,7 @@ def test_committed_golden_fixtures(host_ctx):
 
 def test_random_raster_cases(host_ctx, cases):
     cases.test_random_raster_cases(host_ctx, count=48 if FULL else 14)
+
+
+def test_random_camera_frames(host_ctx, cases):
+    cases.test_random_camera_frames(host_ctx, sequences=10 if FULL else 4)
