@@ -158,22 +158,31 @@ __device__ __forceinline__ unsigned long long scan_tile_exclusive_prefix(unsigne
 void set_error(const char* fmt, ...);
 #define CHORD_CUDA(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { \
     chordb::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); return CHORD_ERR_CUDA; } } while (0)
+// A captured call must not (re)allocate or synchronise (either would invalidate the stream capture, or worse, free memory an
+// already-recorded node points at): the buffers are sized by the eager run the capture rules demand (chord_b200.h).
+#define CHORD_NO_RESIZE_IN_CAPTURE(ctx, what) do { if ((ctx)->capturing) { \
+    chordb::set_error("%s would have to be (re)allocated while a graph is being captured: run the same call sequence once eagerly before chord_graph_begin_capture", what); \
+    return CHORD_ERR_CAPACITY; } } while (0)
 #define CHORD_REQUIRE(cond, msg) do { if (!(cond)) { chordb::set_error("check(%s) failed: %s", #cond, msg); return CHORD_ERR_INVALID; } } while (0)
 
 }  // namespace chordb
 
 // ------------------------------------------------------------------------------------------------ opaque handles
 struct chord_ctx {
+    int refs;                           // owner + one per live child handle (ctx.cu: ctx_retain / ctx_release)
+    bool ownerReleased;                 // chord_ctx_destroy has been called; children keep the context alive
     int device;
     cudaStream_t stream;
     cudaStream_t uploadStream;          // created by the first chord_cmdlist_upload_async
     uint32_t switchFlags;
+    int rasterVariant, rasterCtasPerSm; uint32_t rasterWarpMin;    // chord_ctx_set_raster_tuning (defaults 11, 0 = built-in, 16384)
     uint64_t launches;
     int smCount;
     // scene
     chordb::SceneDev scene;
     void** sceneAllocs; uint32_t nSceneAllocs;
     chordb::DatasDev* datasHost;
+    uint32_t* primGroupCountHost;       // prims[i].meshletGroupCount, for the host-side check of chord_frame_begin's totals
     // scratch for ordered compaction
     unsigned long long* scanBlock;       // [ticket | status...], see scan_reset
     unsigned long long* scanStatus; uint32_t scanTiles;
@@ -274,4 +283,6 @@ int launch_split_vis(chord_frame* f, uint32_t* vis32, float* depth32);
 int launch_decode(chord_frame* f, chord_cmdlist* post, uint32_t* triples);
 int launch_selftest_vertex_records(chord_ctx* ctx, uint32_t n, uint32_t seed, uint32_t width, uint32_t height, uint32_t clampZ, unsigned long long* dOut);
 int scan_reset(chord_ctx* ctx, uint32_t tilesNeeded);
+void ctx_retain(chord_ctx* ctx);
+void ctx_release(chord_ctx* ctx);
 }

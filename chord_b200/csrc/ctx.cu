@@ -40,6 +40,7 @@ FrameDev make_frame_dev(const chord_frame* f)
 int scan_reset(chord_ctx* ctx, uint32_t tilesNeeded)
 {
     if (tilesNeeded > ctx->scanTiles || !ctx->scanBlock) {
+        CHORD_NO_RESIZE_IN_CAPTURE(ctx, "the compaction scratch");
         if (ctx->scanBlock) cudaFree(ctx->scanBlock);                           // (synchronises the device)
         ctx->scanBlock = nullptr; ctx->scanStatus = nullptr; ctx->scanTicket = nullptr; ctx->scanTiles = 0;
         uint32_t n = tilesNeeded + 1024;
@@ -67,12 +68,39 @@ static int upload(chord_ctx* ctx, std::vector<void*>& allocs, const T* host, siz
     return CHORD_OK;
 }
 
+// Handle lifetime (reference: pool refs kept alive by CommandBuffer::addReferenceResource, command_list.h:23-38,
+// render_helper.h:411-451): every child object (list, HZB, frame, graph, cascade views) holds one reference on its
+// context; chord_ctx_destroy only drops the owner's reference, the context is torn down when the last child is gone.
+void ctx_retain(chord_ctx* ctx) { __atomic_add_fetch(&ctx->refs, 1, __ATOMIC_ACQ_REL); }
+
+static void free_scene(chord_ctx* ctx);
+static void ctx_teardown(chord_ctx* ctx);
+void ctx_release(chord_ctx* ctx)
+{
+    if (__atomic_sub_fetch(&ctx->refs, 1, __ATOMIC_ACQ_REL) == 0) ctx_teardown(ctx);
+}
+
 static void free_scene(chord_ctx* ctx)
 {
     for (uint32_t i = 0; i < ctx->nSceneAllocs; i++) cudaFree(ctx->sceneAllocs[i]);
     free(ctx->sceneAllocs); ctx->sceneAllocs = nullptr; ctx->nSceneAllocs = 0;
     free(ctx->datasHost); ctx->datasHost = nullptr;
+    free(ctx->primGroupCountHost); ctx->primGroupCountHost = nullptr;
     memset(&ctx->scene, 0, sizeof(ctx->scene));
+}
+
+static void ctx_teardown(chord_ctx* ctx)
+{
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    free_scene(ctx);
+    if (ctx->scanBlock) cudaFree(ctx->scanBlock);
+    if (ctx->lutTransmittance) cudaFree(ctx->lutTransmittance);
+    if (ctx->lutIrradiance) cudaFree(ctx->lutIrradiance);
+    cudaFree(ctx->dTextures); cudaFree(ctx->dSamplers); cudaFree(ctx->dTexels);
+    if (ctx->uploadStream) { cudaStreamSynchronize(ctx->uploadStream); cudaStreamDestroy(ctx->uploadStream); }
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    free(ctx);
 }
 
 }  // namespace chordb
@@ -99,7 +127,9 @@ int chord_ctx_create(int device, chord_ctx** out)
     chord_ctx* c = (chord_ctx*)calloc(1, sizeof(chord_ctx));
     CHORD_REQUIRE(c != nullptr, "out of host memory");
     c->device = device;
+    c->refs = 1;                                                   // the owner's reference, dropped by chord_ctx_destroy
     c->switchFlags = 0b111;
+    c->rasterVariant = 11; c->rasterCtasPerSm = 0; c->rasterWarpMin = 16384u;
     c->smCount = prop.multiProcessorCount;
     const int rc = [&]() -> int {
         CHORD_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
@@ -112,18 +142,16 @@ int chord_ctx_create(int device, chord_ctx** out)
 
 void chord_ctx_destroy(chord_ctx* ctx)
 {
+    // Drops the owner's reference.  Children created from the context keep it (stream, scene, scratch) alive until the last
+    // of them is destroyed, in any order; a second chord_ctx_destroy on the same handle is a caller error, as with free().
     if (!ctx) return;
+    if (ctx->ownerReleased) return;                                // tolerated while children still hold the context
+    ctx->ownerReleased = true;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-    free_scene(ctx);
-    if (ctx->scanBlock) cudaFree(ctx->scanBlock);
-    if (ctx->lutTransmittance) cudaFree(ctx->lutTransmittance);
-    if (ctx->lutIrradiance) cudaFree(ctx->lutIrradiance);
-    cudaFree(ctx->dTextures); cudaFree(ctx->dSamplers); cudaFree(ctx->dTexels);
-    if (ctx->uploadStream) { cudaStreamSynchronize(ctx->uploadStream); cudaStreamDestroy(ctx->uploadStream); }
-    if (ctx->stream) cudaStreamDestroy(ctx->stream);
-    free(ctx);
+    ctx_release(ctx);
 }
+uint32_t chord_ctx_refcount(const chord_ctx* ctx) { return ctx ? (uint32_t)__atomic_load_n(&ctx->refs, __ATOMIC_ACQUIRE) : 0u; }
 
 void* chord_ctx_stream(chord_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 int chord_ctx_sync(chord_ctx* ctx)
@@ -135,6 +163,16 @@ int chord_ctx_sync(chord_ctx* ctx)
 }
 int chord_ctx_set_switch_flags(chord_ctx* ctx, uint32_t f) { CHORD_REQUIRE(ctx, "ctx"); ctx->switchFlags = f & 7u; return CHORD_OK; }
 uint32_t chord_ctx_get_switch_flags(const chord_ctx* ctx) { return ctx ? ctx->switchFlags : 0; }
+int chord_ctx_set_raster_tuning(chord_ctx* ctx, int variant, int ctasPerSm, int64_t warpMinMeshlets)
+{
+    CHORD_REQUIRE(ctx, "ctx");
+    CHORD_REQUIRE(variant < 0 || variant == 0 || variant == 11 || variant == 13, "variant (0, 11 or 13)");
+    CHORD_REQUIRE(ctasPerSm <= 32, "ctasPerSm");
+    if (variant >= 0) ctx->rasterVariant = variant;
+    if (ctasPerSm >= 0) ctx->rasterCtasPerSm = ctasPerSm;
+    if (warpMinMeshlets >= 0) ctx->rasterWarpMin = warpMinMeshlets > 0xFFFFFFFFll ? 0xFFFFFFFFu : (uint32_t)warpMinMeshlets;
+    return CHORD_OK;
+}
 uint64_t chord_ctx_kernel_launches(const chord_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 int chord_scene_upload(chord_ctx* ctx, const chord_scene_desc* desc)
@@ -165,6 +203,8 @@ int chord_scene_upload(chord_ctx* ctx, const chord_scene_desc* desc)
     if (rc == CHORD_OK) rc = upload(ctx, allocs, desc->primitives, desc->primitiveCount, &ctx->scene.prims);
     if (rc == CHORD_OK) rc = upload(ctx, allocs, desc->materials, desc->materialCount, &ctx->scene.mats);
     ctx->scene.nDatas = desc->datasCount; ctx->scene.nPrims = desc->primitiveCount; ctx->scene.nMats = desc->materialCount;
+    ctx->primGroupCountHost = (uint32_t*)malloc(sizeof(uint32_t) * desc->primitiveCount);
+    for (uint32_t i = 0; i < desc->primitiveCount; i++) ctx->primGroupCountHost[i] = desc->primitives[i].meshletGroupCount;
     ctx->sceneAllocs = (void**)malloc(sizeof(void*) * (allocs.size() + 1));
     ctx->nSceneAllocs = (uint32_t)allocs.size();
     for (size_t i = 0; i < allocs.size(); i++) ctx->sceneAllocs[i] = allocs[i];
@@ -182,7 +222,7 @@ int chord_cmdlist_create(chord_ctx* ctx, uint32_t capacity, chord_cmdlist** out)
     *out = nullptr;
     chord_cmdlist* l = (chord_cmdlist*)calloc(1, sizeof(chord_cmdlist));
     CHORD_REQUIRE(l != nullptr, "out of host memory");
-    l->ctx = ctx; l->capacity = capacity;
+    l->ctx = ctx; l->capacity = capacity; ctx_retain(ctx);
     const int rc = [&]() -> int {
         CHORD_CUDA(cudaMalloc(&l->count, 16));
         CHORD_CUDA(cudaMalloc(&l->cmds, sizeof(chord_draw_cmd) * (size_t)capacity + 64));
@@ -200,7 +240,8 @@ void chord_cmdlist_destroy(chord_cmdlist* l)
     if (l->ctx->uploadStream) cudaStreamSynchronize(l->ctx->uploadStream);
     if (l->uploaded) cudaEventDestroy(l->uploaded);
     if (l->lastUse) cudaEventDestroy(l->lastUse);
-    cudaFree(l->count); cudaFree(l->cmds); if (l->pinnedCount) cudaFreeHost(l->pinnedCount); free(l);
+    cudaFree(l->count); cudaFree(l->cmds); if (l->pinnedCount) cudaFreeHost(l->pinnedCount);
+    ctx_release(l->ctx); free(l);
 }
 // a list that has an overlapped upload in flight: the main stream waits for it before the first consumer
 static int list_acquire(chord_cmdlist* l)
@@ -233,10 +274,19 @@ int chord_cmdlist_upload_async(chord_cmdlist* l, const chord_draw_cmd* host, uin
     CHORD_REQUIRE(l && (host || count == 0), "null");
     if (count > l->capacity) { set_error("cmdlist upload: %u > capacity %u", count, l->capacity); return CHORD_ERR_CAPACITY; }
     // the count travels as a 4-byte kernel-free copy from a small pinned scratch owned by the list
-    if (!l->pinnedCount) CHORD_CUDA(cudaMallocHost(&l->pinnedCount, 64 * sizeof(uint32_t)));
-    uint32_t* slot = &l->pinnedCount[l->pinnedIdx++ & 63u];                 // ring: up to 64 uploads in flight
-    *slot = count;
     chord_ctx* ctx = l->ctx;
+    uint32_t* slot = nullptr;
+    if (ctx->capturing) {
+        // captured upload: the count is snapshotted into pinned memory OWNED BY THE GRAPH (like chord_frame_begin's uniforms);
+        // a slot of the list's ring would be overwritten by later uploads and every replay would copy whatever it holds then
+        CHORD_CUDA(cudaHostAlloc((void**)&slot, 64, cudaHostAllocDefault));
+        ctx->captureAllocs = (void**)realloc(ctx->captureAllocs, sizeof(void*) * (ctx->nCaptureAllocs + 1));
+        ctx->captureAllocs[ctx->nCaptureAllocs++] = slot;
+    } else {
+        if (!l->pinnedCount) CHORD_CUDA(cudaMallocHost(&l->pinnedCount, 64 * sizeof(uint32_t)));
+        slot = &l->pinnedCount[l->pinnedIdx++ & 63u];                       // ring: up to 64 uploads in flight
+    }
+    *slot = count;
     cudaStream_t st = ctx->stream;
     if (!ctx->capturing) {
         // the copy runs on the context's upload stream so that it overlaps whatever the main stream is executing (the
@@ -294,6 +344,7 @@ int chord_hzb_create(chord_ctx* ctx, uint32_t depthW, uint32_t depthH, chord_hzb
     while (mx > 1) { mx >>= 1; mips++; }
     h->mipCount = mips;
     if (mips < 6 || mips > CHORD_HZB_MAX_MIP_COUNT) { set_error("hzb mip count %u outside [6,12] (hzb.cpp:119)", mips); free(h); return CHORD_ERR_INVALID; }
+    ctx_retain(ctx);
     uint64_t o = 0;
     for (uint32_t m = 0; m < mips; m++) {
         h->mipOffset[m] = o;
@@ -318,7 +369,8 @@ void chord_hzb_destroy(chord_hzb* h)
 {
     if (!h) return;
     cudaStreamSynchronize(h->ctx->stream);
-    cudaFree(h->minChain); cudaFree(h->maxChain); cudaFree(h->validRange); cudaFree(h->counter); free(h);
+    cudaFree(h->minChain); cudaFree(h->maxChain); cudaFree(h->validRange); cudaFree(h->counter);
+    ctx_release(h->ctx); free(h);
 }
 int chord_hzb_info(const chord_hzb* h, uint32_t* w, uint32_t* hh, uint32_t* mips, uint32_t* vw, uint32_t* vh)
 {
@@ -363,7 +415,7 @@ int chord_frame_create(chord_ctx* ctx, uint32_t width, uint32_t height, chord_fr
     *out = nullptr;
     chord_frame* f = (chord_frame*)calloc(1, sizeof(chord_frame));
     CHORD_REQUIRE(f != nullptr, "out of host memory");
-    f->ctx = ctx; f->width = width; f->height = height;
+    f->ctx = ctx; f->width = width; f->height = height; ctx_retain(ctx);
     f->tile = chord_rect{0, 0, width, height};
     const int rc = [&]() -> int {
         CHORD_CUDA(cudaMalloc(&f->vis64, sizeof(unsigned long long) * (size_t)width * height));
@@ -404,7 +456,7 @@ void chord_frame_destroy(chord_frame* f)
     cudaFree(f->largeTris); cudaFree(f->largeItems); cudaFree(f->largeCounters); cudaFree(f->stats);
     cudaFree(f->tileMarker); cudaFree(f->tileList); cudaFree(f->tileCount); cudaFree(f->resolveRecs);
     for (int i = 0; i < CHORD_GBUF_COUNT; i++) { cudaFree(f->gbuffer[i]); cudaFree(f->gbufferPackedBuf[i]); }
-    free(f);
+    ctx_release(f->ctx); free(f);
 }
 
 int chord_frame_begin(chord_frame* f, const chord_PerframeCameraView* view, const chord_InstanceCullingViewInfo* iview,
@@ -418,6 +470,17 @@ int chord_frame_begin(chord_frame* f, const chord_PerframeCameraView* view, cons
     // the raster target is sized by the INSTANCE view (main view: == view.renderDimension; cascade views: cascadeDim)
     CHORD_REQUIRE((uint32_t)iview->renderDimension.x == f->width && (uint32_t)iview->renderDimension.y == f->height, "instanceView.renderDimension != frame size");
     chord_ctx* ctx = f->ctx;
+    {
+        // PerframeCollected totals (component_gltf_mesh.cpp:58-122) size the compaction scratch, the BVH candidate bitmask and
+        // the BVH queue, while the kernels walk sum(prim.meshletGroupCount) over the visible objects: an under-reported
+        // total would make them run past those buffers, so it is checked here (a few thousand objects at most)
+        uint64_t groups = 0;
+        for (uint32_t i = 0; i < objectCount; i++) {
+            CHORD_REQUIRE(objects[i].GLTFPrimitiveDetail < ctx->scene.nPrims && objects[i].GLTFMaterialData < ctx->scene.nMats, "object refers to a primitive / material outside the uploaded scene");
+            groups += ctx->primGroupCountHost[objects[i].GLTFPrimitiveDetail];
+        }
+        if (groups > meshletGroupCount) { set_error("meshletGroupCount %u is smaller than the %llu groups of the %u objects", meshletGroupCount, (unsigned long long)groups, objectCount); return CHORD_ERR_INVALID; }
+    }
     CHORD_CUDA(cudaSetDevice(ctx->device));
     if (tile) {
         CHORD_REQUIRE(tile->x0 < tile->x1 && tile->y0 < tile->y1 && tile->x1 <= f->width && tile->y1 <= f->height, "tile rect");
@@ -428,6 +491,7 @@ int chord_frame_begin(chord_frame* f, const chord_PerframeCameraView* view, cons
     constexpr size_t kViewBytes = sizeof(chord_PerframeCameraView), kIViewBytes = (sizeof(chord_InstanceCullingViewInfo) + 15) & ~(size_t)15;
     static_assert(sizeof(chord_PerframeCameraView) % 16 == 0, "view block alignment");
     if (objectCount > f->objectCapacity) {
+        CHORD_NO_RESIZE_IN_CAPTURE(ctx, "the frame's object buffers");
         CHORD_CUDA(cudaStreamSynchronize(ctx->stream));
         cudaFree(f->dInputs); cudaFree(f->dDerived); cudaFree(f->objGroupCount); cudaFree(f->objGroupBase);
         for (int k = 0; k < 4; k++) { if (f->hInputs[k]) cudaFreeHost(f->hInputs[k]); f->hInputs[k] = nullptr; }
@@ -641,7 +705,7 @@ int chord_cascade_views_create(chord_ctx* ctx, chord_cascade_views** out)
     *out = nullptr;
     chord_cascade_views* v = (chord_cascade_views*)calloc(1, sizeof(chord_cascade_views));
     CHORD_REQUIRE(v != nullptr, "out of host memory");
-    v->ctx = ctx;
+    v->ctx = ctx; ctx_retain(ctx);
     const int rc = [&]() -> int {
         CHORD_CUDA(cudaMalloc(&v->dViews, sizeof(chord_InstanceCullingViewInfo) * CHORD_MAX_CASCADE_COUNT));
         CHORD_CUDA(cudaMemsetAsync(v->dViews, 0, sizeof(chord_InstanceCullingViewInfo) * CHORD_MAX_CASCADE_COUNT, ctx->stream));
@@ -655,7 +719,7 @@ void chord_cascade_views_destroy(chord_cascade_views* v)
 {
     if (!v) return;
     cudaStreamSynchronize(v->ctx->stream);
-    cudaFree(v->dViews); free(v);
+    cudaFree(v->dViews); ctx_release(v->ctx); free(v);
 }
 int chord_cascade_setup(chord_frame* mainFrame, const chord_cascade_setup_desc* d, const chord_hzb* validRangeSource, chord_cascade_views* views)
 {
@@ -734,7 +798,7 @@ int chord_graph_end_capture(chord_ctx* ctx, chord_graph** out)
         return CHORD_ERR_CUDA;
     }
     chord_graph* g = (chord_graph*)calloc(1, sizeof(chord_graph));
-    g->ctx = ctx; g->graph = graph;
+    g->ctx = ctx; g->graph = graph; ctx_retain(ctx);
     g->pinned = ctx->captureAllocs; g->nPinned = ctx->nCaptureAllocs;
     ctx->captureAllocs = nullptr; ctx->nCaptureAllocs = 0;
     const int rc = [&]() -> int {
@@ -772,7 +836,7 @@ void chord_graph_destroy(chord_graph* g)
     if (g->graph) cudaGraphDestroy(g->graph);
     for (uint32_t i = 0; i < g->nPinned; i++) cudaFreeHost(g->pinned[i]);
     free(g->pinned);
-    free(g);
+    ctx_release(g->ctx); free(g);
 }
 
 int chord_textures_upload(chord_ctx* ctx, const chord_texture_desc* textures, uint32_t textureCount,

@@ -339,7 +339,7 @@ __global__ void __launch_bounds__(kCullBlock) k_hzb_cull(FrameDev f, HzbDev hzb,
                         int mip = max(0, max(mlx, mly) - 1);
                         if (((hx1 >> mip) - (hx0 >> mip) >= 4) || ((hy1 >> mip) - (hy0 >> mip) >= 4)) mip += 1;
                         const int cx0 = hx0 >> mip, cy0 = hy0 >> mip, cx1 = hx1 >> mip, cy1 = hy1 >> mip;
-                        const uint32_t pitch = hzb.mip0W >> mip;
+                        const uint32_t pitch = max(1u, hzb.mip0W >> mip);      // mips narrower than one texel are stored 1 wide (hzb.cu mip_dim)
                         const __half* mp = hzb.minChain + hzb.mipOffset[mip];
                         float zMin = 10.0f;
 #pragma unroll
@@ -471,7 +471,7 @@ __global__ void __launch_bounds__(kCullBlock) k_hzb_cull_generic(FrameDev f, Hzb
                         int mip = max(0, max(mlx, mly));
                         if (((hx1 >> mip) - (hx0 >> mip) >= 2) || ((hy1 >> mip) - (hy0 >> mip) >= 2)) mip += 1;     // 2x2 sample: bias one level
                         const int cx0 = hx0 >> mip, cy0 = hy0 >> mip, cx1 = hx1 >> mip, cy1 = hy1 >> mip;
-                        const uint32_t pitch = hzb.mip0W >> mip;
+                        const uint32_t pitch = max(1u, hzb.mip0W >> mip);      // mips narrower than one texel are stored 1 wide (hzb.cu mip_dim)
                         const __half* mp = hzb.minChain + hzb.mipOffset[mip];
                         float zMin = 10.0f;
 #pragma unroll
@@ -527,10 +527,16 @@ __global__ void __launch_bounds__(128) k_bvh_seed(FrameDev f, const uint32_t* __
 }
 
 __global__ void __launch_bounds__(128) k_bvh_traverse(FrameDev f, const uint32_t* __restrict__ objGroupBase, unsigned long long* __restrict__ entries,
-                                                      uint32_t capacity, uint32_t* __restrict__ ctrl, uint32_t* __restrict__ bits)
+                                                      uint32_t capacity, uint32_t* __restrict__ ctrl, uint32_t* __restrict__ bits, uint32_t bitWords)
 {
     const uint32_t lane = threadIdx.x & 31u;
     volatile uint32_t* vctrl = ctrl;
+    // Termination protocol: ctrl[2] (pending) counts queue entries that are published or about to be and not yet finished.
+    // A node RESERVES its children in pending before it publishes them and only then retires itself, so pending can reach 0
+    // exactly once - when every entry ever published has been processed; the warp that brings it to 0 raises ctrl[3] (done).
+    // Waiters leave on `done` alone (never on pending == 0, which a racing reader could see between a child's retirement and
+    // its parent's reservation under the old "publish, then count" order).
+    if (vctrl[1] == 0u) return;                                         // k_bvh_seed queued nothing: no warp will ever raise done
     while (true) {
         uint32_t idx = 0;
         if (lane == 0) idx = atomicAdd(&ctrl[0], 1u);
@@ -540,7 +546,11 @@ __global__ void __launch_bounds__(128) k_bvh_traverse(FrameDev f, const uint32_t
         while (true) {
             e = ld_volatile_u64(&entries[idx]);
             if (e != ~0ull) break;
-            if (vctrl[3] != 0u || vctrl[2] == 0u) return;               // traversal finished: this slot will never be filled
+            if (vctrl[3] != 0u) {                                       // traversal finished ...
+                e = ld_volatile_u64(&entries[idx]);                     // ... and this slot was never filled (re-read after done)
+                if (e == ~0ull) return;
+                break;
+            }
             __nanosleep(64);
         }
         const uint32_t objectId = (uint32_t)(e & 0xFFFFFFFFull), nodeIndex = (uint32_t)(e >> 32);
@@ -551,7 +561,10 @@ __global__ void __launch_bounds__(128) k_bvh_traverse(FrameDev f, const uint32_t
         // leaves -> candidate bits (canonical index = base of the object + group index inside the primitive)
         const uint32_t leafOffset = node->leafMeshletGroupOffset, leafCount = node->leafMeshletGroupCount;
         const uint32_t base = objGroupBase[objectId] + leafOffset;
-        for (uint32_t k = lane; k < leafCount; k += 32u) { const uint32_t b = base + k; atomicOr(&bits[b >> 5], 1u << (b & 31u)); }
+        for (uint32_t k = lane; k < leafCount; k += 32u) {
+            const uint32_t b = base + k;
+            if ((b >> 5) < bitWords) atomicOr(&bits[b >> 5], 1u << (b & 31u)); else ctrl[4] = 1u;     // caller under-reported meshletGroupCount
+        }
         // children
         uint32_t child = CHORD_UNVALID_ID; bool keep = false;
         if (lane < CHORD_BVH_LEVEL_NODE_COUNT) child = node->children[lane];
@@ -567,11 +580,16 @@ __global__ void __launch_bounds__(128) k_bvh_traverse(FrameDev f, const uint32_t
             if (lane == 0) slotBase = atomicAdd(&ctrl[1], n);
             slotBase = __shfl_sync(0xffffffffu, slotBase, 0);
             if (slotBase + n > capacity) { if (lane == 0) ctrl[4] = 1u; n = 0; }
-            else if (keep) st_volatile_u64(&entries[slotBase + __popc(mask & ((1u << lane) - 1u))], (unsigned long long)objectId | ((unsigned long long)child << 32));
+            else {
+                if (lane == 0) { atomicAdd(&ctrl[2], n); __threadfence(); }      // reserve BEFORE the entries become visible
+                __syncwarp();
+                if (keep) st_volatile_u64(&entries[slotBase + __popc(mask & ((1u << lane) - 1u))], (unsigned long long)objectId | ((unsigned long long)child << 32));
+            }
         }
+        __syncwarp();
         if (lane == 0) {
-            // pending += n children, -= 1 for this node (two's complement add)
-            const uint32_t after = atomicAdd(&ctrl[2], n - 1u) + (n - 1u);
+            __threadfence();
+            const uint32_t after = atomicAdd(&ctrl[2], 0xFFFFFFFFu) - 1u;       // retire this node
             if (after == 0u) { __threadfence(); vctrl[3] = 1u; }
         }
     }
@@ -607,6 +625,7 @@ static int launch_instance_culling_impl(chord_frame* fr, chord_cmdlist* out, boo
         const uint32_t cap = 2u * fr->meshletGroupCount + fr->objectCount + 64u;
         const uint32_t words = (fr->meshletGroupCount + 31u) / 32u + 1u;
         if (cap > fr->bvhCapacity) {
+            CHORD_NO_RESIZE_IN_CAPTURE(ctx, "the BVH traversal queue");
             cudaFree(fr->bvhEntries); cudaFree(fr->bvhBits); fr->bvhEntries = nullptr; fr->bvhBits = nullptr; fr->bvhCapacity = 0;
             CHORD_CUDA(cudaMalloc(&fr->bvhEntries, sizeof(unsigned long long) * (size_t)cap));
             CHORD_CUDA(cudaMalloc(&fr->bvhBits, sizeof(uint32_t) * (size_t)words));
@@ -617,7 +636,7 @@ static int launch_instance_culling_impl(chord_frame* fr, chord_cmdlist* out, boo
         CHORD_CUDA(cudaMemsetAsync(fr->bvhBits, 0, sizeof(uint32_t) * (size_t)words, ctx->stream));
         CHORD_CUDA(cudaMemsetAsync(fr->bvhCtrl, 0, 32, ctx->stream));
         k_bvh_seed<<<(fr->objectCount + 127) / 128, 128, 0, ctx->stream>>>(f, fr->objGroupCount, (unsigned long long*)fr->bvhEntries, cap, fr->bvhCtrl);
-        k_bvh_traverse<<<(uint32_t)ctx->smCount * 2u, 128, 0, ctx->stream>>>(f, fr->objGroupBase, (unsigned long long*)fr->bvhEntries, cap, fr->bvhCtrl, fr->bvhBits);
+        k_bvh_traverse<<<(uint32_t)ctx->smCount * 2u, 128, 0, ctx->stream>>>(f, fr->objGroupBase, (unsigned long long*)fr->bvhEntries, cap, fr->bvhCtrl, fr->bvhBits, fr->bvhWords);
         ctx->launches += 2;
         bits = fr->bvhBits;
     }

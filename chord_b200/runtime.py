@@ -13,8 +13,8 @@ LIB_PATH = os.path.join(_HERE, 'libchord_b200.so')
 # every symbol include/chord_b200.h declares (tests check the .so exports all of them)
 SYMBOLS = [
     'chord_last_error', 'chord_abi_version',
-    'chord_ctx_create', 'chord_ctx_destroy', 'chord_ctx_stream', 'chord_ctx_sync', 'chord_ctx_set_switch_flags',
-    'chord_ctx_get_switch_flags', 'chord_ctx_kernel_launches', 'chord_scene_upload', 'chord_textures_upload',
+    'chord_ctx_create', 'chord_ctx_destroy', 'chord_ctx_refcount', 'chord_ctx_stream', 'chord_ctx_sync', 'chord_ctx_set_switch_flags',
+    'chord_ctx_get_switch_flags', 'chord_ctx_set_raster_tuning', 'chord_ctx_kernel_launches', 'chord_scene_upload', 'chord_textures_upload',
     'chord_cmdlist_create', 'chord_cmdlist_destroy', 'chord_cmdlist_upload', 'chord_cmdlist_readback',
     'chord_cmdlist_upload_async', 'chord_readback_visibility32_async', 'chord_frame_wait_readbacks', 'chord_frame_set_readback_stream', 'chord_cmdlist_capacity', 'chord_cmdlist_count_ptr', 'chord_cmdlist_cmds_ptr',
     'chord_hzb_create', 'chord_hzb_destroy', 'chord_hzb_info', 'chord_hzb_readback', 'chord_hzb_readback_valid_range',
@@ -52,6 +52,7 @@ def lib():
         L.chord_ctx_stream.restype = C.c_void_p
         L.chord_ctx_kernel_launches.restype = C.c_uint64
         L.chord_ctx_get_switch_flags.restype = C.c_uint32
+        L.chord_ctx_refcount.restype = C.c_uint32
         L.chord_cmdlist_capacity.restype = C.c_uint32
         for n in ('chord_cmdlist_count_ptr', 'chord_cmdlist_cmds_ptr', 'chord_hzb_chain_ptr', 'chord_frame_vis64_ptr'):
             getattr(L, n).restype = C.c_void_p
@@ -100,6 +101,11 @@ class Context:
             pass
 
     @property
+    def refcount(self):
+        """owner + live child handles (chord_ctx_refcount)"""
+        return int(lib().chord_ctx_refcount(self.h))
+
+    @property
     def stream(self):
         return lib().chord_ctx_stream(self.h)
 
@@ -108,6 +114,10 @@ class Context:
 
     def set_switch_flags(self, flags):
         lib().chord_ctx_set_switch_flags(self.h, C.c_uint32(flags))
+
+    def set_raster_tuning(self, variant=-1, ctas_per_sm=-1, warp_min=-1):
+        """chord_ctx_set_raster_tuning: launch shape of the meshlet rasteriser (negative = keep)."""
+        lib().chord_ctx_set_raster_tuning(self.h, C.c_int(variant), C.c_int(ctas_per_sm), C.c_int64(warp_min))
 
     @property
     def switch_flags(self):

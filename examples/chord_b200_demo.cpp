@@ -12,6 +12,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <vector>
 
 namespace {
@@ -76,9 +77,14 @@ int main(int argc, char** argv)
 
     if (path) {
         try {
-            chord_b200::Context ctx(0);
-            ctx.uploadScene(scene);
-            chord_b200::DeferredRenderer renderer(ctx, width, height);
+            // Lifetime as in the reference (ref-counted pool resources, command_list.h:23-38): the Context OBJECT goes away right
+            // after the renderer has been created; the renderer's frame / lists / HZBs keep the chord_ctx alive and usable.
+            auto owner = std::make_unique<chord_b200::Context>(0);
+            owner->uploadScene(scene);
+            chord_b200::DeferredRenderer renderer(*owner, width, height);
+            chord_ctx* rawCtx = owner->handle();
+            owner.reset();                                                        // chord_ctx_destroy: drops the owner's reference only
+            if (chord_ctx_refcount(rawCtx) < 1) { std::fprintf(stderr, "context died with children alive\n"); return 3; }
             FILE* o = std::fopen(argv[2], "wb");
             if (!o) { std::perror(argv[2]); return 2; }
             std::vector<uint64_t> vis((size_t)width * height);
@@ -96,7 +102,7 @@ int main(int argc, char** argv)
                 std::printf("frame %zu: %u meshlets after culling, %zu px covered, history HZB %s\n", fi, n, covered, fi ? "used" : "none");
             }
             std::fclose(o);
-            std::printf("%llu kernel launches\n", (unsigned long long)chord_ctx_kernel_launches(ctx.handle()));
+            std::printf("%llu kernel launches, %u handles keep the context alive\n", (unsigned long long)chord_ctx_kernel_launches(rawCtx), chord_ctx_refcount(rawCtx));
         } catch (const std::exception& e) {
             std::fprintf(stderr, "chord_b200 error: %s\n", e.what());
             return 1;

@@ -46,7 +46,14 @@ int         chord_abi_version(void);
 
 /* ---- context: replaces graphics::Context + one GraphicsQueue (source/graphics/graphics.h) */
 int  chord_ctx_create(int device, chord_ctx** out);
+/* Handle lifetime mirrors the reference's ref-counted pool resources (CommandBuffer::addReferenceResource,
+ * source/graphics/command_list.h:23-38; PoolTextureRef / PoolBufferRef in render_helper.h:411-451): every object created
+ * from a context (chord_cmdlist, chord_hzb, chord_frame, chord_graph, chord_cascade_views) holds a reference on it.
+ * chord_ctx_destroy drops the OWNER's reference only; stream, scene and scratch stay alive - and the children stay fully
+ * usable - until the last child has been destroyed, in any order. */
 void chord_ctx_destroy(chord_ctx* ctx);
+/* owner (1 until chord_ctx_destroy) + live children; for tests / leak checks */
+uint32_t chord_ctx_refcount(const chord_ctx* ctx);
 /* cudaStream_t of the context, for callers that interleave their own work / events. */
 void* chord_ctx_stream(chord_ctx* ctx);
 int  chord_ctx_sync(chord_ctx* ctx);
@@ -54,6 +61,12 @@ int  chord_ctx_sync(chord_ctx* ctx);
  * switchFlags bits 0/1/2 (instance_culling.cpp:22-68, gltf.h:10-12). Default 0b111. */
 int  chord_ctx_set_switch_flags(chord_ctx* ctx, uint32_t switchFlags);
 uint32_t chord_ctx_get_switch_flags(const chord_ctx* ctx);
+/* Tuning of the meshlet rasteriser's launch shape (no reference counterpart; nothing in the library reads environment
+ * variables).  variant: 11 (default) = one warp per meshlet, 4 warps per CTA, 7 CTAs / SM; 13 = same with V <= 104 and 8 CTAs / SM;
+ * 0 = one CTA per meshlet.  ctasPerSm: 0 = the variant's own.  warpMinMeshlets: lists shorter than this are rasterised by
+ * the CTA-per-meshlet instantiation (default 16384).  A negative argument keeps the current value.  Every choice produces
+ * the same image. */
+int  chord_ctx_set_raster_tuning(chord_ctx* ctx, int variant, int ctasPerSm, int64_t warpMinMeshlets);
 /* Number of kernels this context has launched since creation (for gpu_launches accounting). */
 uint64_t chord_ctx_kernel_launches(const chord_ctx* ctx);
 

@@ -2,6 +2,9 @@
 // (source/renderer/mesh/gltf_rendering.h:37-108, postprocessing/postprocessing.h:41-54, visibility_tile.h:22-34,
 // lighting.h:37).  RAII handles replace chord's ref-counted pool resources; errors throw std::runtime_error carrying
 // chord_last_error() (the reference would check()-crash).  No CUDA headers needed by the includer.
+// Lifetime: the C ABI ref-counts the context from every child handle (chord_b200.h, chord_ctx_destroy), and the classes
+// below keep only the chord_ctx* - never a reference to the Context OBJECT - so a Frame, list, HZB, Graph or
+// DeferredRenderer may outlive the Context it was created from, exactly like a PoolTextureRef outliving its pool user.
 #pragma once
 
 #include <memory>
@@ -24,6 +27,19 @@ struct HzbDeleter { void operator()(chord_hzb* p) const { chord_hzb_destroy(p); 
 using CmdListRef = std::shared_ptr<chord_cmdlist>;     // CountAndCmdBuffer
 using HzbRef = std::shared_ptr<chord_hzb>;             // HZBContext
 
+inline CmdListRef makeCmdList(chord_ctx* ctx, uint32_t capacity)
+{
+    chord_cmdlist* l = nullptr;
+    check(chord_cmdlist_create(ctx, capacity, &l), "chord_cmdlist_create");
+    return CmdListRef(l, CmdListDeleter{});
+}
+inline HzbRef makeHzb(chord_ctx* ctx, uint32_t w, uint32_t h)
+{
+    chord_hzb* z = nullptr;
+    check(chord_hzb_create(ctx, w, h, &z), "chord_hzb_create");
+    return HzbRef(z, HzbDeleter{});
+}
+
 class Frame;
 
 class Context {
@@ -42,18 +58,8 @@ public:
     void* stream() const { return chord_ctx_stream(m_ctx); }
     chord_ctx* handle() const { return m_ctx; }
 
-    CmdListRef createCmdList(uint32_t capacity) const
-    {
-        chord_cmdlist* l = nullptr;
-        check(chord_cmdlist_create(m_ctx, capacity, &l), "chord_cmdlist_create");
-        return CmdListRef(l, CmdListDeleter{});
-    }
-    HzbRef createHzb(uint32_t w, uint32_t h) const
-    {
-        chord_hzb* z = nullptr;
-        check(chord_hzb_create(m_ctx, w, h, &z), "chord_hzb_create");
-        return HzbRef(z, HzbDeleter{});
-    }
+    CmdListRef createCmdList(uint32_t capacity) const { return makeCmdList(m_ctx, capacity); }
+    HzbRef createHzb(uint32_t w, uint32_t h) const { return makeHzb(m_ctx, w, h); }
     inline std::unique_ptr<Frame> createFrame(uint32_t w, uint32_t h) const;
 
 private:
@@ -62,8 +68,9 @@ private:
 
 class Frame {
 public:
-    Frame(const Context& ctx, uint32_t w, uint32_t h) : m_ctx(ctx), m_w(w), m_h(h)
-    { check(chord_frame_create(ctx.handle(), w, h, &m_frame), "chord_frame_create"); }
+    Frame(const Context& ctx, uint32_t w, uint32_t h) : m_ctx(ctx.handle()), m_w(w), m_h(h)
+    { check(chord_frame_create(m_ctx, w, h, &m_frame), "chord_frame_create"); }
+    chord_ctx* context() const { return m_ctx; }
     ~Frame() { chord_frame_destroy(m_frame); }
     Frame(const Frame&) = delete;
     Frame& operator=(const Frame&) = delete;
@@ -82,7 +89,7 @@ public:
     // instanceCulling
     CmdListRef instanceCulling()
     {
-        auto out = m_ctx.createCmdList(m_lod0);
+        auto out = makeCmdList(m_ctx, m_lod0);
         check(chord_instance_culling(m_frame, out.get()), "chord_instance_culling");
         return out;
     }
@@ -91,7 +98,7 @@ public:
     {
         int need = 0;
         CmdListRef scratch, rejected;
-        if (lastFrameHzb && chord_hzb_is_valid(lastFrameHzb)) { scratch = m_ctx.createCmdList(m_lod0); rejected = m_ctx.createCmdList(m_lod0); }
+        if (lastFrameHzb && chord_hzb_is_valid(lastFrameHzb)) { scratch = makeCmdList(m_ctx, m_lod0); rejected = makeCmdList(m_ctx, m_lod0); }
         check(chord_visibility_stage0(m_frame, lastFrameHzb, in.get(), scratch.get(), rejected.get(), &need), "chord_visibility_stage0");
         m_keep[0] = scratch;                       // stream-ordered: keep alive until the next frame
         outRejected = need ? rejected : CmdListRef();
@@ -100,14 +107,14 @@ public:
     // gltfVisibilityRenderingStage1
     void visibilityStage1(const HzbRef& thisFrameHzb, const CmdListRef& rejected)
     {
-        auto scratch = m_ctx.createCmdList(m_lod0);
+        auto scratch = makeCmdList(m_ctx, m_lod0);
         check(chord_visibility_stage1(m_frame, thisFrameHzb.get(), rejected.get(), scratch.get()), "chord_visibility_stage1");
         m_keep[1] = scratch; m_keep[2] = rejected;
     }
     // buildHZB
     HzbRef buildHZB(bool bMin, bool bMax, bool bValidRange)
     {
-        auto h = m_ctx.createHzb(m_w, m_h);
+        auto h = makeHzb(m_ctx, m_w, m_h);
         check(chord_build_hzb(m_frame, bMin, bMax, bValidRange, h.get()), "chord_build_hzb");
         return h;
     }
@@ -119,7 +126,7 @@ public:
     CmdListRef hzbCullingGeneric(const HzbRef& hzb, const chord_InstanceCullingViewInfo& hzbView, float extentScale,
                                  bool bObjectUseLastFrameProject, const CmdListRef& in)
     {
-        auto out = m_ctx.createCmdList(chord_cmdlist_capacity(in.get()));
+        auto out = makeCmdList(m_ctx, chord_cmdlist_capacity(in.get()));
         check(chord_hzb_culling_generic(m_frame, hzb.get(), &hzbView, extentScale, bObjectUseLastFrameProject ? 1 : 0, in.get(), out.get()), "chord_hzb_culling_generic");
         return out;
     }
@@ -127,7 +134,7 @@ public:
     void lighting(const CmdListRef& post) { check(chord_lighting(m_frame, post.get()), "chord_lighting"); }
 
 private:
-    const Context& m_ctx;
+    chord_ctx* m_ctx;                  // kept alive by m_frame's reference (chord_ctx_destroy only drops the owner's)
     chord_frame* m_frame = nullptr;
     uint32_t m_w, m_h, m_lod0 = 0;
     CmdListRef m_keep[3];
@@ -137,15 +144,15 @@ private:
 // call end(); launch() replays them with one CUDA-graph launch.
 class Graph {
 public:
-    explicit Graph(const Context& ctx) : m_ctx(ctx) { check(chord_graph_begin_capture(ctx.handle()), "chord_graph_begin_capture"); }
-    void end() { check(chord_graph_end_capture(m_ctx.handle(), &m_graph), "chord_graph_end_capture"); }
+    explicit Graph(const Context& ctx) : m_ctx(ctx.handle()) { check(chord_graph_begin_capture(m_ctx), "chord_graph_begin_capture"); }
+    void end() { check(chord_graph_end_capture(m_ctx, &m_graph), "chord_graph_end_capture"); }
     void launch() { check(chord_graph_launch(m_graph), "chord_graph_launch"); }
     uint32_t kernelNodes() const { return chord_graph_kernel_nodes(m_graph); }
     ~Graph() { chord_graph_destroy(m_graph); }
     Graph(const Graph&) = delete;
     Graph& operator=(const Graph&) = delete;
 private:
-    const Context& m_ctx;
+    chord_ctx* m_ctx;
     chord_graph* m_graph = nullptr;
 };
 
@@ -158,7 +165,7 @@ inline std::unique_ptr<Frame> Context::createFrame(uint32_t w, uint32_t h) const
 class DeferredRenderer {
 public:
     DeferredRenderer(const Context& ctx, uint32_t width, uint32_t height, bool doResolve = false, bool useBvh = false)
-        : m_ctx(ctx), m_frame(ctx.createFrame(width, height)), m_doResolve(doResolve), m_useBvh(useBvh) {}
+        : m_ctx(ctx.handle()), m_frame(ctx.createFrame(width, height)), m_doResolve(doResolve), m_useBvh(useBvh) {}
 
     Frame& frame() { return *m_frame; }
     const HzbRef& historyHzb() const { return m_history; }
@@ -209,16 +216,16 @@ private:
     {
         for (size_t i = 0; i < m_freeLists.size(); i++)
             if (chord_cmdlist_capacity(m_freeLists[i].get()) == capacity) { CmdListRef l = m_freeLists[i]; m_freeLists.erase(m_freeLists.begin() + (long)i); return l; }
-        return m_ctx.createCmdList(capacity);
+        return makeCmdList(m_ctx, capacity);
     }
     void releaseList(CmdListRef& l) { if (l) { m_freeLists.push_back(l); l.reset(); } }
     HzbRef acquireHzb()
     {
         if (!m_freeHzb.empty()) { HzbRef h = m_freeHzb.back(); m_freeHzb.pop_back(); return h; }
-        return m_ctx.createHzb(m_frame->width(), m_frame->height());
+        return makeHzb(m_ctx, m_frame->width(), m_frame->height());
     }
 
-    const Context& m_ctx;
+    chord_ctx* m_ctx;                  // kept alive by m_frame
     std::unique_ptr<Frame> m_frame;
     HzbRef m_history;
     CmdListRef m_post;

@@ -26,12 +26,26 @@ REFERENCE = os.environ.get('CHORD_REFERENCE', '/root/reference')
 _REF_SO = os.path.join(_HERE, '_ref', 'libmeshopt_ref.so')
 
 
+REF_LAYOUT_PROBE = os.path.join(_HERE, '_ref', 'ref_layout_probe')
+
+
+def ref_struct_layout():
+    """sizeof / offsetof of the a1 structs as the REFERENCE's own headers (install/resource/shader/base.h, gltf.h, compiled
+    with g++ + its glm, oracle/ref_layout_probe.cpp) declare them, or None when the probe was never built here."""
+    import json
+    build_ref()
+    if not os.path.exists(REF_LAYOUT_PROBE):
+        return None
+    return json.loads(subprocess.check_output([REF_LAYOUT_PROBE], text=True))
+
+
 def build_ref(force=False):
     """oracle/_ref/libmeshopt_ref.so: the reference's vendored meshoptimizer 0.21 compiled from its sources in place (the
     only part of the reference that builds offline) + oracle/meshopt_ref_wrapper.cpp.  Returns the path, or None when
     neither the reference tree nor a prebuilt library is there (the GPU box only has what travelled with the repo)."""
     have_src = os.path.isdir(os.path.join(REFERENCE, 'source', 'asset', 'meshoptimizer'))
-    pairs = ((os.path.join(_HERE, 'meshopt_ref_wrapper.cpp'), _REF_SO), (os.path.join(_HERE, 'tinygltf_ref_wrapper.cpp'), os.path.join(_HERE, '_ref', 'libtinygltf_ref.so')))
+    pairs = ((os.path.join(_HERE, 'meshopt_ref_wrapper.cpp'), _REF_SO), (os.path.join(_HERE, 'tinygltf_ref_wrapper.cpp'), os.path.join(_HERE, '_ref', 'libtinygltf_ref.so')),
+             (os.path.join(_HERE, 'ref_layout_probe.cpp'), REF_LAYOUT_PROBE))
     stale = any(not os.path.exists(so) or os.path.getmtime(src) > os.path.getmtime(so) for src, so in pairs)
     if have_src and (force or stale):
         try:

@@ -413,7 +413,7 @@ void oracle_hzb_culling(const oracle_frame* f, int firstStage,
                     if (((hx1 >> mipLevel) - (hx0 >> mipLevel) >= 4) || ((hy1 >> mipLevel) - (hy0 >> mipLevel) >= 4)) mipLevel += 1;
                     int32_t cx0 = hx0 >> mipLevel, cy0 = hy0 >> mipLevel, cx1 = hx1 >> mipLevel, cy1 = hy1 >> mipLevel;
                     float zMin = 10.0f;
-                    const uint32_t pitch = mip0Width >> mipLevel;
+                    const uint32_t pitch = (mip0Width >> mipLevel) ? (mip0Width >> mipLevel) : 1u;   /* mips narrower than one texel are stored 1 wide (Texture2D.Load reads the right row) */
                     const uint16_t* mip = hzbMin + hzbMipOffsets[mipLevel];
                     for (int x = 0; x < 4; x++)
                         for (int y = 0; y < 4; y++) {
@@ -487,7 +487,7 @@ void oracle_hzb_culling_generic(const oracle_frame* f, const chord_InstanceCulli
                     if (((hx1 >> mipLevel) - (hx0 >> mipLevel) >= 2) || ((hy1 >> mipLevel) - (hy0 >> mipLevel) >= 2)) mipLevel += 1;
                     int32_t cx0 = hx0 >> mipLevel, cy0 = hy0 >> mipLevel, cx1 = hx1 >> mipLevel, cy1 = hy1 >> mipLevel;
                     float zMin = 10.0f;
-                    const uint32_t pitch = mip0Width >> mipLevel;
+                    const uint32_t pitch = (mip0Width >> mipLevel) ? (mip0Width >> mipLevel) : 1u;   /* mips narrower than one texel are stored 1 wide (Texture2D.Load reads the right row) */
                     const uint16_t* mip = hzbMin + hzbMipOffsets[mipLevel];
                     for (int x = 0; x < 2; x++)
                         for (int y = 0; y < 2; y++) {

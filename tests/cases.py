@@ -29,7 +29,7 @@ def case_ragged(n=400, w=640, h=360, seed=9):
     scene, camera, objects, cmds = synth.ragged_stream_scene(n, w, h, seed=seed)
     view = cam.fill_view(camera)
     return dict(name=f'ragged_{n}', scene=scene, view=view, iview=cam.fill_instance_view(view), objects=objects, w=w, h=h,
-                lod0=2 * n, groups=(n + 3) // 4, cmds=cmds)
+                lod0=2 * n, groups=2 * ((n + 3) // 4), cmds=cmds)         # two objects instance the same primitive
 
 
 def city_frames(n_buildings=9, w=640, h=360, frames=4, seed=2, lods=3, low=False):
@@ -103,3 +103,32 @@ def oracle_render_shadow(scene, view, objects, lod0, cfg, light, history=None, v
             prev_hzb, prev_id = fr.build_hzb(depth[cid], True, False, False), cid
             hzbs[cid] = prev_hzb
     return dict(views=views, depth=depth, lists=lists, hzbs=hzbs, direction=direction, cfg=cfg)
+
+
+def case_tall_frame(w=64, h=4096):
+    """a 64 x 4096 frame (HZB mip 0 = 32 x 2048, mips 6.. are ONE texel wide) with a near occluder over the top rows
+    and a far, tall meshlet (> 1000 px high, so K3 selects a mip >= 6) lower down with nothing in front of it: it must stay
+    visible.  With `pitch = mip0W >> mip` (0 beyond mip 5) every fetch reads texel 0 of the mip - the occluder's depth - and
+    the meshlet is wrongly culled; `Texture2D.Load` in the reference reads the right row (hzb_mainview_culling.hlsl:150-185)."""
+    import math
+    scene, camera, objects, cmds = synth.patch_stream_scene(2, w, h, seed=3)
+    d = scene.datas[0]
+    pos = d['positions'].reshape(2, 81, 3)
+    tan_half = math.tan(math.radians(22.5))
+    g = np.linspace(0.0, 1.0, 9, dtype=np.float32)
+    gx, gy = np.meshgrid(g, g)
+    for m, (depth, y0, y1) in enumerate(((2.0, -40.0, 700.0), (50.0, 2000.0, 3200.0))):
+        pxw = 2.0 * tan_half / h * depth
+        sx = (-8.0 + gx.reshape(-1) * (w + 16.0)).astype(np.float32)
+        sy = (y0 + gy.reshape(-1) * (y1 - y0)).astype(np.float32)
+        pos[m, :, 0] = (sx - w / 2.0) * pxw
+        pos[m, :, 1] = -(sy - h / 2.0) * pxw
+        pos[m, :, 2] = -depth
+        d['meshlets']['posMin'][m] = pos[m].min(axis=0)
+        d['meshlets']['posMax'][m] = pos[m].max(axis=0)
+        d['meshlets']['coneApex'][m] = pos[m].mean(axis=0)
+    scene.primitives['posMin'][0] = pos.reshape(-1, 3).min(axis=0)
+    scene.primitives['posMax'][0] = pos.reshape(-1, 3).max(axis=0)
+    view = cam.fill_view(camera)
+    return dict(name='tall_frame', scene=scene, view=view, iview=cam.fill_instance_view(view), objects=objects, w=w, h=h,
+                lod0=2, groups=1, cmds=cmds)

@@ -27,4 +27,4 @@ def random_raster_case(rng):
     if rng.random() < 0.3 and w >= 256 and h >= 136:
         tile = (64, 64, w - 64 if (w - 64) % 64 == 0 else w, h)
     return dict(scene=scene, view=view, iview=cam.fill_instance_view(view), objects=objs, cmds=cmds, w=w, h=h, tile=tile,
-                lod0=len(cmds) if kind == 0 else 2 * n, groups=(n + 3) // 4, what=dict(seed=seed, w=w, h=h, kind=kind, n=n, tile=tile))
+                lod0=len(cmds) if kind == 0 else 2 * n, groups=((n + 3) // 4) * (1 if kind == 0 else 2), what=dict(seed=seed, w=w, h=h, kind=kind, n=n, tile=tile))

@@ -15,6 +15,12 @@ timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/gpu_tests.log 2>&1
 echo "gpu tests exit $?" >> gpurun_out/gpu_tests.log
 tail -5 gpurun_out/gpu_tests.log
 
+timeout 120 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1
+echo "smoke exit $?" >> gpurun_out/smoke.log
+tail -2 gpurun_out/smoke.log
+timeout 120 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/smoke_launches.csv python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke_ncu.log 2>&1
+echo "smoke under ncu exit $?" >> gpurun_out/smoke.log
+
 timeout 400 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err
 python - <<'PY'
 import json

@@ -48,6 +48,75 @@ def test_struct_sizes_match_c_header(tmp_path):
     assert int(out['draw']) == abi.DrawCmd.itemsize == 12
 
 
+def _chord_header_layout(tmp_path, ref):
+    """sizeof / offsetof of the same structs and fields from a C compile of include/chord_abi_types.h."""
+    lines = []
+    for name, rec in ref.items():
+        if name == 'constants':
+            continue
+        lines.append(f'printf("{name} sizeof %zu\\n", sizeof(chord_{name}));')
+        for fld in rec['fields']:
+            lines.append(f'printf("{name} {fld} %zu %zu\\n", offsetof(chord_{name}, {fld}), sizeof(((chord_{name}*)0)->{fld}));')
+    src = tmp_path / 'layout.c'
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "chord_abi_types.h"\nint main(){\n' + '\n'.join(lines) + '\nreturn 0;}\n')
+    exe = tmp_path / 'layout'
+    cc = '/usr/bin/gcc' if os.path.exists('/usr/bin/gcc') else 'gcc'
+    subprocess.check_call([cc, '-I', os.path.join(ROOT, 'include'), str(src), '-o', str(exe)])
+    out = {}
+    for l in subprocess.check_output([str(exe)], text=True).strip().splitlines():
+        t = l.split()
+        if t[1] == 'sizeof':
+            out.setdefault(t[0], {'fields': {}})['sizeof'] = int(t[2])
+        else:
+            out.setdefault(t[0], {'fields': {}})['fields'][t[1]] = [int(t[2]), int(t[3])]
+    return out
+
+
+def test_struct_layout_matches_reference_headers(tmp_path):
+    """Row a1 pinned against the REFERENCE ITSELF: tests/golden/ref_struct_layout.json holds sizeof / offsetof of every a1
+    struct as g++ sees them in the reference's own dual C++/HLSL headers (install/resource/shader/base.h, gltf.h compiled in
+    place with the reference's glm; oracle/ref_layout_probe.cpp, tests/golden/make_ref_layout.py).  include/chord_abi_types.h
+    must agree on every field offset, every field size, every struct size and the constants; where /root/reference exists the
+    probe is re-run and must reproduce the fixture."""
+    import json
+    ref = json.load(open(os.path.join(ROOT, 'tests', 'golden', 'ref_struct_layout.json')))
+    assert len(ref) == 15
+    import oracle
+    if os.path.isdir(os.path.join(oracle.REFERENCE, 'install', 'resource', 'shader')):
+        live = oracle.ref_struct_layout()
+        assert live == ref, 'tests/golden/ref_struct_layout.json is stale: rerun tests/golden/make_ref_layout.py'
+    ours = _chord_header_layout(tmp_path, ref)
+    n_fields = 0
+    for name, rec in ref.items():
+        if name == 'constants':
+            continue
+        assert ours[name]['sizeof'] == rec['sizeof'], f'sizeof({name})'
+        for fld, (off, size) in rec['fields'].items():
+            assert ours[name]['fields'][fld] == [off, size], f'{name}.{fld}: reference {off, size}, chord_abi_types.h {ours[name]["fields"][fld]}'
+            n_fields += 1
+        # the numpy mirror the tests and the bench build their inputs with
+        dt = getattr(abi, name, None)
+        if dt is not None and hasattr(dt, 'fields') and dt.fields:
+            assert dt.itemsize == rec['sizeof'], f'numpy {name}'
+            for fld, (off, size) in rec['fields'].items():
+                if fld in dt.fields:
+                    assert dt.fields[fld][1] == off, f'numpy {name}.{fld}'
+    assert n_fields >= 140
+    hdr = open(os.path.join(ROOT, 'include', 'chord_abi_types.h')).read()
+    consts = {'kNaniteMeshletMaxVertices': 'CHORD_MESHLET_MAX_VERTICES', 'kNaniteMeshletMaxTriangle': 'CHORD_MESHLET_MAX_TRIANGLES',
+              'kNaniteMaxLODCount': 'CHORD_NANITE_MAX_LOD_COUNT', 'kNaniteBVHLevelNodeCount': 'CHORD_BVH_LEVEL_NODE_COUNT',
+              'kClusterGroupMergeMaxCount': 'CHORD_CLUSTER_GROUP_MERGE_MAX', 'kHZBMaxMipmapCount': 'CHORD_HZB_MAX_MIP_COUNT',
+              'kMaxInstanceIdCount': 'CHORD_MAX_INSTANCE_ID_COUNT', 'subpixelPrecisionBits': 'CHORD_SUBPIXEL_BITS',
+              'kFrustumCullingEnableBit': 'CHORD_FLAG_FRUSTUM_CULL_BIT', 'kHZBCullingEnableBit': 'CHORD_FLAG_HZB_CULL_BIT',
+              'kMeshletConeCullEnableBit': 'CHORD_FLAG_CONE_CULL_BIT'}
+    for k, macro in consts.items():
+        m = re.search(rf'#define\s+{macro}\s+(0x[0-9A-Fa-f]+|\d+)', hdr)
+        assert m, macro
+        assert int(m.group(1), 0) == ref['constants'][k], f'{macro} != {k}'
+    m = re.search(r'#define\s+CHORD_MAX_CASCADE_COUNT\s+(\d+)', open(os.path.join(ROOT, 'include', 'chord_b200.h')).read())
+    assert int(m.group(1)) == ref['constants']['kMaxCascadeCount']
+
+
 def test_field_offsets_spot_checks():
     # offsets that kernels rely on (gltf.h:38-51, base.h:343-360)
     m = abi.GPUGLTFMeshlet

@@ -68,6 +68,46 @@ def test_s1_single_meshlet(gpu_ctx):
     gpu_ctx.set_switch_flags(0b111)
 
 
+def test_context_destroyed_before_its_children(gpu_ctx):
+    """Handle lifetime (reference: pool refs kept alive by CommandBuffer::addReferenceResource, command_list.h:23-38): a
+    context destroyed FIRST must stay alive - and its children fully usable - until the last child is gone, in any order.
+    Round 1 dereferenced a freed context here (the driver's smoke() died with SIGSEGV after printing its result)."""
+    make = type(gpu_ctx)                    # the same Context class the fixture uses (product library or host executor)
+    scene, camera, objects = synth.single_meshlet_scene()
+    view = cam.fill_view(camera)
+    iview = cam.fill_instance_view(view)
+    ofr = oracle.Frame(scene, view, iview, objects, 256, 256)
+    opost = ofr.instance_culling(4)
+    ovis, _ = ofr.render_mesh(opost)
+    for order in ((0, 1, 2, 3), (3, 2, 1, 0), (2, 0, 3, 1)):
+        ctx = make(gpu_ctx.device)
+        ctx.upload_scene(scene)
+        assert ctx.refcount == 1
+        fr = runtime.Frame(ctx, 256, 256)
+        post = runtime.CmdList(ctx, 4)
+        hz = runtime.Hzb(ctx, 256, 256)
+        cv = runtime.CascadeViews(ctx)
+        assert ctx.refcount == 5
+        L, raw = runtime.lib(), ctx.h.value
+        ctx.close()                                                    # owner's reference dropped; 4 children keep it
+        import ctypes as C
+        assert L.chord_ctx_refcount(C.c_void_p(raw)) == 4
+        # the children still work: a whole frame after the context handle is gone
+        fr.begin(view, iview, objects, 1, 1)
+        fr.instance_culling(post)
+        fr.render_mesh(post)
+        fr.build_hzb(hz, True, True, True)
+        fr.visibility_mark(post)
+        _assert_lists_equal(post.readback(), opost, 'post-cull list after chord_ctx_destroy')
+        _assert_vis_equal(fr.vis64(), ovis, 'vis64 after chord_ctx_destroy')
+        children = [fr, post, hz, cv]
+        for k, i in enumerate(order):
+            children[i].close()
+            if k < 3:
+                assert L.chord_ctx_refcount(C.c_void_p(raw)) == 3 - k
+        # the last close tore the context down; nothing left to touch
+
+
 @pytest.mark.parametrize('n,w,h,scale', [(3000, 640, 360, 1.0), (1500, 512, 512, 40.0), (600, 256, 256, 2000.0)])
 def test_patch_stream_raster(gpu_ctx, n, w, h, scale):
     """raster-only (S5 shape): tiny, medium and large triangles."""
@@ -327,10 +367,13 @@ def test_full_size_s5_properties(gpu_ctx):
     head = runtime.CmdList(gpu_ctx, n)
     head.upload(cmds[:n])
     fr.begin(view, iview, objects, M, groups)
+    fr.reset_stats()                                      # the counters accumulate over calls: count the head alone
     fr.render_mesh(head)
     ovis, ostats = oracle.Frame(hs, view, iview, objects, W, H).render_mesh(cmds[:n])
     _assert_vis_equal(fr.vis64(), ovis, 'head of the S5 stream at 4K')
-    assert fr.raster_stats()['trianglesCulled'] - 0 >= ostats['trianglesCulled']
+    st = fr.raster_stats()
+    for k in ('trianglesSubmitted', 'trianglesCulled', 'trianglesClipped', 'meshletsRastered'):
+        assert st[k] == ostats[k], (k, st, ostats)
     del scene
     torch.cuda.empty_cache()
 
@@ -960,6 +1003,37 @@ def test_extreme_frame_shapes(gpu_ctx, shapes=((64, 64), (4096, 64), (64, 4096),
         assert np.array_equal(hz.valid_range(), oh['range'])
         fr.visibility_mark(post)
         assert np.array_equal(fr.tile_marker(), ofr.visibility_mark(ovis, opost))
+
+
+def test_tall_frame_hzb_rows(gpu_ctx):
+    """64 x 4096: HZB mips 6.. are one texel wide; K3 must read row `sy` of such a mip (Texture2D.Load semantics), not texel 0.
+    A far, 1200 px tall meshlet below a near occluder must survive phase 1 - checked against the oracle AND against a
+    mip-independent brute-force test on the depth image itself (visible iff the farthest depth under its rect <= its nearest)."""
+    from cases import case_tall_frame
+    c = case_tall_frame()
+    w, h = c['w'], c['h']
+    gpu_ctx.upload_scene(c['scene'])
+    fr = runtime.Frame(gpu_ctx, w, h)
+    fr.begin(c['view'], c['iview'], c['objects'], c['lod0'], c['groups'])
+    occluder, both = runtime.CmdList(gpu_ctx, 2), runtime.CmdList(gpu_ctx, 2)
+    occluder.upload(c['cmds'][:1]); both.upload(c['cmds'])
+    fr.render_mesh(occluder)
+    hz = runtime.Hzb(gpu_ctx, w, h)
+    fr.build_hzb(hz, True, False, False)
+    vis_l = runtime.CmdList(gpu_ctx, 2)
+    fr.hzb_culling(hz, False, both, vis_l)
+    ofr = oracle.Frame(c['scene'], c['view'], c['iview'], c['objects'], w, h)
+    ovis, _ = ofr.render_mesh(c['cmds'][:1])
+    _assert_vis_equal(fr.vis64(), ovis, 'occluder surface')
+    oh = ofr.build_hzb(ovis, True, False, False)
+    _assert_hzb_equal(hz, oh, 'min')
+    ov, _ = ofr.hzb_culling(oh, False, c['cmds'])
+    got = vis_l.readback()
+    _assert_lists_equal(got, ov, 'phase-1 survivors on the tall frame')
+    # brute force on the depth image: rows 2000..3199 hold nothing (depth 0 = far), so the far meshlet cannot be occluded
+    depth = (ovis >> np.uint64(32)).astype(np.uint32).view(np.float32)
+    assert depth[2000:3200].max() == 0.0 and depth[:700].min() > 0.0
+    assert 1 in got['meshletId'], 'the tall far meshlet was occlusion-culled although nothing covers it'
 
 
 def test_random_raster_cases(gpu_ctx, count=48, seed=2024):

@@ -57,6 +57,10 @@ def test_s1_single_meshlet(host_ctx, cases):
     cases.test_s1_single_meshlet(host_ctx)
 
 
+def test_context_destroyed_before_its_children(host_ctx, cases):
+    cases.test_context_destroyed_before_its_children(host_ctx)
+
+
 def test_patch_stream_small_triangles(host_ctx, cases):
     cases.test_patch_stream_raster(host_ctx, 3000, 640, 360, 1.0)
 
@@ -90,6 +94,10 @@ def test_empty_lists_publish_zero_counts(host_ctx, cases):
 
 def test_extreme_frame_shapes(host_ctx, cases):
     cases.test_extreme_frame_shapes(host_ctx, **({} if FULL else {'shapes': ((64, 64), (4096, 64))}))
+
+
+def test_tall_frame_hzb_rows(host_ctx, cases):
+    cases.test_tall_frame_hzb_rows(host_ctx)
 
 
 def test_readback_stream_modes(host_ctx, cases):
