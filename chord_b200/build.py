@@ -11,14 +11,13 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 OUT = os.path.join(HERE, 'libchord_b200.so')
-SOURCES = ['ctx.cu', 'cull.cu', 'raster.cu', 'hzb.cu', 'resolve.cu', 'shadow.cu']
+SOURCES = ['ctx.cu', 'cull.cu', 'raster.cu', 'hzb.cu', 'resolve.cu', 'shadow.cu', 'renderer.cu']
 HEADERS = ['common.cuh', '../../include/chord_b200.h', '../../include/chord_abi_types.h']
 
-# Per-file overrides.  Tried in round 1: resolve.cu with --use_fast_math halves the resolve (600 -> 313 us at 4K) but
-# breaks the 1e-5 colour contract on a handful of pixels: the Bruneton radius r = |p - earthCentre| ~ 6360 km is
-# ill-conditioned in fp32 (1 ulp of r moves the transmittance LUT coordinate by 2e-4), so only identical IEEE
-# arithmetic on both sides agrees everywhere.  Kept precise; set CHORD_FAST_RESOLVE=1 to build the fast variant.
-PER_FILE_FLAGS = {'resolve.cu': ['--use_fast_math']} if os.environ.get('CHORD_FAST_RESOLVE') == '1' else {}
+# Per-file overrides: none.  (Tried in round 1: resolve.cu with --use_fast_math halves the resolve but breaks the colour
+# contract: the Bruneton radius r = |p - earthCentre| ~ 6360 km is ill-conditioned in fp32, only identical IEEE arithmetic on
+# both sides agrees everywhere.)
+PER_FILE_FLAGS = {}
 
 NVCC_FLAGS = [
     '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17', '--fmad=false',
@@ -67,7 +66,7 @@ def build(force=False, verbose=False, extra=()):
         failed |= p.returncode != 0
     if failed:
         raise RuntimeError('nvcc failed')
-    cmd = [nvcc, '-shared', '-gencode', 'arch=compute_100a,code=sm_100a', '-o', OUT] + objs
+    cmd = [nvcc, '-shared', '-gencode', 'arch=compute_100a,code=sm_100a', '-o', OUT] + objs + ['-ldl']
     subprocess.check_call(cmd)
     return OUT
 

@@ -64,6 +64,26 @@ struct FrameDev {
     unsigned long long* vis64;          // width*height packed texels
 };
 
+// ------------------------------------------------------------------------------------------------ multi-GPU exchange
+// One block of this layout per rank (one cudaMalloc, exported with CUDA IPC or reached through peer access): the header, then
+// the two history HZBs (min + max chains each).  Peers write into it: their part of mips 0..5, their valid range, their
+// arrival flag (hzb.cu: k_hzb_build epilogue / k_hzb_exchange_wait_top).
+#define CHORD_MAX_EXCHANGE_RANKS 16
+struct ExchangeHeader {
+    uint32_t arrived[CHORD_MAX_EXCHANGE_RANKS];          // [rank] = last frame sequence number whose stores into THIS block are complete
+    uint32_t localSeq; uint32_t pad[15];                 // this rank's own sequence number (advanced on the device: graph replays)
+    uint32_t ranges[2][CHORD_MAX_EXCHANGE_RANKS][2];     // [history slot][rank] = {minBits, maxBits} of that rank's tile
+};
+struct ExchangePeers {                                   // device-resident table: where this rank's texels / flags go on every peer
+    __half* min[CHORD_MAX_EXCHANGE_RANKS - 1]; __half* max[CHORD_MAX_EXCHANGE_RANKS - 1];
+    ExchangeHeader* header[CHORD_MAX_EXCHANGE_RANKS - 1];
+};
+struct HzbExchange {                                     // one build's exchange parameters (renderer.cu fills it)
+    uint32_t nPeers, rank, parity;
+    const ExchangePeers* dPeers;                         // table of the history slot `parity`
+    ExchangeHeader* localHeader;
+};
+
 // ------------------------------------------------------------------------------------------------ math
 struct f4 { float x, y, z, w; };
 struct f3 { float x, y, z; };
@@ -168,6 +188,8 @@ void set_error(const char* fmt, ...);
 }  // namespace chordb
 
 // ------------------------------------------------------------------------------------------------ opaque handles
+struct chord_graph_frame_inputs { chord_frame* frame; unsigned char* pinned; uint32_t objectCount; float tanHalfFovy; };
+
 struct chord_ctx {
     int refs;                           // owner + one per live child handle (ctx.cu: ctx_retain / ctx_release)
     bool ownerReleased;                 // chord_ctx_destroy has been called; children keep the context alive
@@ -175,6 +197,7 @@ struct chord_ctx {
     cudaStream_t stream;
     cudaStream_t uploadStream;          // created by the first chord_cmdlist_upload_async
     uint32_t switchFlags;
+    uint32_t lightingSlot;              // this context's slot of the resolve kernel's constant-bank uniforms (resolve.cu)
     int rasterVariant, rasterCtasPerSm; uint32_t rasterWarpMin;    // chord_ctx_set_raster_tuning (defaults 11, 0 = built-in, 16384)
     uint64_t launches;
     int smCount;
@@ -191,6 +214,7 @@ struct chord_ctx {
     __half* lutTransmittance; __half* lutIrradiance;
     // graph capture (chord_graph_begin_capture .. end_capture): pinned snapshots made while capturing
     bool capturing; void** captureAllocs; uint32_t nCaptureAllocs;
+    chord_graph_frame_inputs* captureFrames; uint32_t nCaptureFrames;     // chord_frame_begin calls recorded by the capture in flight
     // material textures (masked bucket)
     chordb::TextureDev* dTextures; chordb::SamplerDev* dSamplers; uint8_t* dTexels; uint32_t nTextures, nSamplers;
 };
@@ -206,6 +230,7 @@ struct chord_graph {
     cudaGraph_t graph; cudaGraphExec_t exec;
     uint32_t kernelNodes;
     void** pinned; uint32_t nPinned;
+    chord_graph_frame_inputs* frames; uint32_t nFrames;
 };
 
 struct chord_cmdlist {
@@ -229,6 +254,7 @@ struct chord_hzb {
     uint32_t* validRange;        // {minBits, maxBits}
     uint32_t* counter;
     int valid;
+    bool externalChains;         // chains live in a renderer's exchange block (not freed with the HZB)
 };
 
 struct chord_frame {
@@ -239,7 +265,7 @@ struct chord_frame {
     // per-frame inputs: ONE device block [view | iview | objects...] fed by ONE H2D copy per chord_frame_begin from a
     // pinned staging ring (dView / dIView / dObjects point into it)
     unsigned char* dInputs; unsigned char* hInputs[4]; cudaEvent_t inputsCopied[4]; uint32_t inputsSlot; size_t inputsBytes;
-    chord_PerframeCameraView* dView; chord_InstanceCullingViewInfo* dIView;
+    chord_PerframeCameraView* dView; chord_InstanceCullingViewInfo* dIView; void* dLightingView; size_t lightingViewOffset, objectsOffset;
     chord_GPUObjectGLTFPrimitive* dObjects; uint32_t objectCapacity, objectCount;
     chord_rect clearedTile; bool clearedValid;     // region that may hold non-zero texels (tile-only clears)
     chordb::ObjectDerived* dDerived;
@@ -276,13 +302,19 @@ int launch_render_mesh(chord_frame* f, chord_cmdlist* list);
 int launch_cascade_setup(chord_frame* mainFrame, const chord_cascade_setup_desc* desc, const chord_hzb* validRangeSource, chord_InstanceCullingViewInfo* dViews);
 int launch_hzb_culling_generic(chord_frame* f, const chord_hzb* hzb, const chord_InstanceCullingViewInfo* hzbView, float extentScale,
                                int useLastFrame, chord_cmdlist* in, chord_cmdlist* outVis, const chord_InstanceCullingViewInfo* dHzbView = nullptr);
-int launch_build_hzb(chord_frame* f, int bMin, int bMax, int bRange, chord_hzb* dst);
+int launch_build_hzb(chord_frame* f, int bMin, int bMax, int bRange, chord_hzb* dst, const HzbExchange* exchange = nullptr);
+int launch_hzb_exchange_wait_top(chord_frame* f, chord_hzb* dst, const HzbExchange* exchange, uint32_t world, uint32_t* status);
 int launch_visibility_mark(chord_frame* f, chord_cmdlist* post);
 int launch_lighting(chord_frame* f, chord_cmdlist* post);
 int launch_split_vis(chord_frame* f, uint32_t* vis32, float* depth32);
 int launch_decode(chord_frame* f, chord_cmdlist* post, uint32_t* triples);
 int launch_selftest_vertex_records(chord_ctx* ctx, uint32_t n, uint32_t seed, uint32_t width, uint32_t height, uint32_t clampZ, unsigned long long* dOut);
 int scan_reset(chord_ctx* ctx, uint32_t tilesNeeded);
+size_t lighting_view_bytes();                                                     // resolve.cu: sizeof(LightingView)
+void fill_lighting_view(const chord_PerframeCameraView& view, void* dst);         // host-side derivation of the resolve uniforms
+// one frame's inputs, staged as ONE block [view | instance view | LightingView | objects ...] (chord_frame_begin)
+void fill_frame_inputs(const chord_frame* f, unsigned char* dst, const chord_PerframeCameraView* view, const chord_InstanceCullingViewInfo* iview,
+                       const chord_GPUObjectGLTFPrimitive* objects, uint32_t objectCount);
 void ctx_retain(chord_ctx* ctx);
 void ctx_release(chord_ctx* ctx);
 }

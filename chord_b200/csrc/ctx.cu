@@ -89,6 +89,15 @@ static void free_scene(chord_ctx* ctx)
     memset(&ctx->scene, 0, sizeof(ctx->scene));
 }
 
+void fill_frame_inputs(const chord_frame* f, unsigned char* dst, const chord_PerframeCameraView* view, const chord_InstanceCullingViewInfo* iview,
+                       const chord_GPUObjectGLTFPrimitive* objects, uint32_t objectCount)
+{
+    memcpy(dst, view, sizeof(*view));
+    memcpy(dst + sizeof(chord_PerframeCameraView), iview, sizeof(*iview));
+    fill_lighting_view(*view, dst + f->lightingViewOffset);
+    memcpy(dst + f->objectsOffset, objects, sizeof(chord_GPUObjectGLTFPrimitive) * (size_t)objectCount);
+}
+
 static void ctx_teardown(chord_ctx* ctx)
 {
     cudaSetDevice(ctx->device);
@@ -129,6 +138,7 @@ int chord_ctx_create(int device, chord_ctx** out)
     c->device = device;
     c->refs = 1;                                                   // the owner's reference, dropped by chord_ctx_destroy
     c->switchFlags = 0b111;
+    { static int nextSlot = 0; c->lightingSlot = (uint32_t)(__atomic_fetch_add(&nextSlot, 1, __ATOMIC_RELAXED) & 7); }
     c->rasterVariant = 11; c->rasterCtasPerSm = 0; c->rasterWarpMin = 16384u;
     c->smCount = prop.multiProcessorCount;
     const int rc = [&]() -> int {
@@ -357,6 +367,7 @@ int chord_hzb_create(chord_ctx* ctx, uint32_t depthW, uint32_t depthH, chord_hzb
         CHORD_CUDA(cudaMalloc(&h->maxChain, sizeof(__half) * o));
         CHORD_CUDA(cudaMalloc(&h->validRange, 16));
         CHORD_CUDA(cudaMalloc(&h->counter, 16));
+        CHORD_CUDA(cudaMemsetAsync(h->counter, 0, 16, ctx->stream));
         CHORD_CUDA(cudaMemsetAsync(h->minChain, 0, sizeof(__half) * o, ctx->stream));
         CHORD_CUDA(cudaMemsetAsync(h->maxChain, 0, sizeof(__half) * o, ctx->stream));
         return CHORD_OK;
@@ -369,7 +380,8 @@ void chord_hzb_destroy(chord_hzb* h)
 {
     if (!h) return;
     cudaStreamSynchronize(h->ctx->stream);
-    cudaFree(h->minChain); cudaFree(h->maxChain); cudaFree(h->validRange); cudaFree(h->counter);
+    if (!h->externalChains) { cudaFree(h->minChain); cudaFree(h->maxChain); }
+    cudaFree(h->validRange); cudaFree(h->counter);
     ctx_release(h->ctx); free(h);
 }
 int chord_hzb_info(const chord_hzb* h, uint32_t* w, uint32_t* hh, uint32_t* mips, uint32_t* vw, uint32_t* vh)
@@ -490,6 +502,7 @@ int chord_frame_begin(chord_frame* f, const chord_PerframeCameraView* view, cons
     }
     constexpr size_t kViewBytes = sizeof(chord_PerframeCameraView), kIViewBytes = (sizeof(chord_InstanceCullingViewInfo) + 15) & ~(size_t)15;
     static_assert(sizeof(chord_PerframeCameraView) % 16 == 0, "view block alignment");
+    const size_t kLvBytes = (lighting_view_bytes() + 15) & ~(size_t)15;
     if (objectCount > f->objectCapacity) {
         CHORD_NO_RESIZE_IN_CAPTURE(ctx, "the frame's object buffers");
         CHORD_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -497,7 +510,8 @@ int chord_frame_begin(chord_frame* f, const chord_PerframeCameraView* view, cons
         for (int k = 0; k < 4; k++) { if (f->hInputs[k]) cudaFreeHost(f->hInputs[k]); f->hInputs[k] = nullptr; }
         f->dInputs = nullptr; f->dDerived = nullptr; f->objGroupCount = nullptr; f->objGroupBase = nullptr; f->objectCapacity = 0;
         uint32_t cap = objectCount + objectCount / 4 + 16;
-        f->inputsBytes = kViewBytes + kIViewBytes + sizeof(chord_GPUObjectGLTFPrimitive) * (size_t)cap;
+        f->lightingViewOffset = kViewBytes + kIViewBytes; f->objectsOffset = kViewBytes + kIViewBytes + kLvBytes;
+        f->inputsBytes = f->objectsOffset + sizeof(chord_GPUObjectGLTFPrimitive) * (size_t)cap;
         CHORD_CUDA(cudaMalloc(&f->dInputs, f->inputsBytes));
         for (int k = 0; k < 4; k++) {
             CHORD_CUDA(cudaHostAlloc((void**)&f->hInputs[k], f->inputsBytes, cudaHostAllocDefault));
@@ -505,7 +519,8 @@ int chord_frame_begin(chord_frame* f, const chord_PerframeCameraView* view, cons
         }
         f->dView = (chord_PerframeCameraView*)f->dInputs;
         f->dIView = (chord_InstanceCullingViewInfo*)(f->dInputs + kViewBytes);
-        f->dObjects = (chord_GPUObjectGLTFPrimitive*)(f->dInputs + kViewBytes + kIViewBytes);
+        f->dLightingView = f->dInputs + f->lightingViewOffset;
+        f->dObjects = (chord_GPUObjectGLTFPrimitive*)(f->dInputs + f->objectsOffset);
         CHORD_CUDA(cudaMalloc(&f->dDerived, sizeof(ObjectDerived) * (size_t)cap));
         CHORD_CUDA(cudaMalloc(&f->objGroupCount, sizeof(uint32_t) * (size_t)(cap + 1)));
         CHORD_CUDA(cudaMalloc(&f->objGroupBase, sizeof(uint32_t) * (size_t)(cap + 1)));
@@ -516,26 +531,25 @@ int chord_frame_begin(chord_frame* f, const chord_PerframeCameraView* view, cons
     f->hView = *view;
     f->hIViewOrtho = iview->translatedWorldToClip.m[15] == 1.0f;       // base.hlsli:241-244
     f->tanHalfFovy = tanf(0.5f * view->cameraFovy);
-    const size_t inputBytes = kViewBytes + kIViewBytes + sizeof(chord_GPUObjectGLTFPrimitive) * (size_t)objectCount;
+    const size_t inputBytes = f->objectsOffset + sizeof(chord_GPUObjectGLTFPrimitive) * (size_t)objectCount;
     if (ctx->capturing) {
         // captured frame: the uniforms are snapshotted into pinned memory owned by the graph; every replay re-uploads them
+        // (chord_graph_update_frame_inputs rewrites the snapshot between replays)
         unsigned char* h = nullptr;
         CHORD_CUDA(cudaHostAlloc((void**)&h, inputBytes, cudaHostAllocDefault));
         ctx->captureAllocs = (void**)realloc(ctx->captureAllocs, sizeof(void*) * (ctx->nCaptureAllocs + 1));
         ctx->captureAllocs[ctx->nCaptureAllocs++] = h;
-        memcpy(h, view, sizeof(*view));
-        memcpy(h + kViewBytes, iview, sizeof(*iview));
-        memcpy(h + kViewBytes + kIViewBytes, objects, sizeof(chord_GPUObjectGLTFPrimitive) * (size_t)objectCount);
+        ctx->captureFrames = (chord_graph_frame_inputs*)realloc(ctx->captureFrames, sizeof(chord_graph_frame_inputs) * (ctx->nCaptureFrames + 1));
+        ctx->captureFrames[ctx->nCaptureFrames++] = chord_graph_frame_inputs{f, h, objectCount, f->tanHalfFovy};
+        fill_frame_inputs(f, h, view, iview, objects, objectCount);
         CHORD_CUDA(cudaMemcpyAsync(f->dInputs, h, inputBytes, cudaMemcpyHostToDevice, ctx->stream));
     } else {
-        // one H2D copy for view + iview + objects, staged through a 4-slot pinned ring (a slot is reused only after
-        // the copy that read it has completed)
+        // one H2D copy for view + iview + resolve uniforms + objects, staged through a 4-slot pinned ring (a slot is reused
+        // only after the copy that read it has completed)
         const uint32_t slot = f->inputsSlot++ & 3u;
         CHORD_CUDA(cudaEventSynchronize(f->inputsCopied[slot]));
         unsigned char* h = f->hInputs[slot];
-        memcpy(h, view, sizeof(*view));
-        memcpy(h + kViewBytes, iview, sizeof(*iview));
-        memcpy(h + kViewBytes + kIViewBytes, objects, sizeof(chord_GPUObjectGLTFPrimitive) * (size_t)objectCount);
+        fill_frame_inputs(f, h, view, iview, objects, objectCount);
         CHORD_CUDA(cudaMemcpyAsync(f->dInputs, h, inputBytes, cudaMemcpyHostToDevice, ctx->stream));
         CHORD_CUDA(cudaEventRecord(f->inputsCopied[slot], ctx->stream));
     }
@@ -779,7 +793,7 @@ int chord_graph_begin_capture(chord_ctx* ctx)
     CHORD_CUDA(cudaStreamSynchronize(ctx->stream));
     // relaxed: the captured calls may touch pinned / device allocations (uniform snapshots) without invalidating the capture
     CHORD_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed));
-    ctx->capturing = true; ctx->captureAllocs = nullptr; ctx->nCaptureAllocs = 0;
+    ctx->capturing = true; ctx->captureAllocs = nullptr; ctx->nCaptureAllocs = 0; ctx->captureFrames = nullptr; ctx->nCaptureFrames = 0;
     return CHORD_OK;
 }
 
@@ -793,6 +807,7 @@ int chord_graph_end_capture(chord_ctx* ctx, chord_graph** out)
     if (e != cudaSuccess || !graph) {
         for (uint32_t i = 0; i < ctx->nCaptureAllocs; i++) cudaFreeHost(ctx->captureAllocs[i]);
         free(ctx->captureAllocs); ctx->captureAllocs = nullptr; ctx->nCaptureAllocs = 0;
+        free(ctx->captureFrames); ctx->captureFrames = nullptr; ctx->nCaptureFrames = 0;
         set_error("cudaStreamEndCapture failed: %s (a captured call synchronised or failed)", cudaGetErrorString(e));
         cudaGetLastError();
         return CHORD_ERR_CUDA;
@@ -801,6 +816,8 @@ int chord_graph_end_capture(chord_ctx* ctx, chord_graph** out)
     g->ctx = ctx; g->graph = graph; ctx_retain(ctx);
     g->pinned = ctx->captureAllocs; g->nPinned = ctx->nCaptureAllocs;
     ctx->captureAllocs = nullptr; ctx->nCaptureAllocs = 0;
+    g->frames = ctx->captureFrames; g->nFrames = ctx->nCaptureFrames;
+    ctx->captureFrames = nullptr; ctx->nCaptureFrames = 0;
     const int rc = [&]() -> int {
         size_t n = 0;
         CHORD_CUDA(cudaGraphGetNodes(graph, nullptr, &n));
@@ -826,6 +843,31 @@ int chord_graph_launch(chord_graph* g)
     return CHORD_OK;
 }
 
+int chord_graph_update_frame_inputs(chord_graph* g, chord_frame* f, const chord_PerframeCameraView* view, const chord_InstanceCullingViewInfo* iview,
+                                    const chord_GPUObjectGLTFPrimitive* objects, uint32_t objectCount)
+{
+    // Rewrites the pinned snapshot(s) the recorded chord_frame_begin call(s) on `f` upload, so that the next chord_graph_launch
+    // renders THIS camera / THESE object transforms.  Everything that was baked into kernel parameters at capture time must stay
+    // the same: object count, frame size / tile, field of view (tan(fovy / 2) is a kernel parameter of the cull kernels).
+    CHORD_REQUIRE(g && f && view && iview && objects, "null");
+    uint32_t hits = 0;
+    for (uint32_t i = 0; i < g->nFrames; i++) {
+        chord_graph_frame_inputs& r = g->frames[i];
+        if (r.frame != f) continue;
+        CHORD_REQUIRE(r.objectCount == objectCount, "object count differs from the recorded frame");
+        CHORD_REQUIRE(r.tanHalfFovy == tanf(0.5f * view->cameraFovy), "cameraFovy differs from the recorded frame (baked into the recorded kernels)");
+        CHORD_REQUIRE((uint32_t)iview->renderDimension.x == f->width && (uint32_t)iview->renderDimension.y == f->height, "instanceView.renderDimension != frame size");
+        // the previous launch of this graph must have consumed the snapshot: replays of one graph are stream-ordered, and the
+        // upload is the first node, so waiting for the context stream here would be too strong; callers alternate between
+        // graphs / keep one frame in flight (documented in chord_b200.h)
+        fill_frame_inputs(f, r.pinned, view, iview, objects, objectCount);
+        hits++;
+    }
+    CHORD_REQUIRE(hits > 0, "the graph recorded no chord_frame_begin on this frame");
+    f->hView = *view;
+    return CHORD_OK;
+}
+
 uint32_t chord_graph_kernel_nodes(const chord_graph* g) { return g ? g->kernelNodes : 0u; }
 
 void chord_graph_destroy(chord_graph* g)
@@ -835,7 +877,7 @@ void chord_graph_destroy(chord_graph* g)
     if (g->exec) cudaGraphExecDestroy(g->exec);
     if (g->graph) cudaGraphDestroy(g->graph);
     for (uint32_t i = 0; i < g->nPinned; i++) cudaFreeHost(g->pinned[i]);
-    free(g->pinned);
+    free(g->pinned); free(g->frames);
     ctx_release(g->ctx); free(g);
 }
 

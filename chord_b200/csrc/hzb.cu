@@ -22,6 +22,14 @@ struct HzbBuildParams {
     uint32_t* counter;
     uint32_t numBlocks;
     uint32_t blockX0, blockY0;               // first 64x64 block of the dispatched region (tile-restricted builds)
+    // ---- fused exchange (multi-GPU): every texel of mips 0..5 this launch stores is ALSO stored into the same
+    // position of every peer GPU's chain over NVLink (peer pointers: CUDA IPC / peer access), so that the next frame's
+    // phase-0 cull finds the whole min chain on every GPU without a pack -> all-gather -> unpack sequence.  The block that
+    // finishes last publishes this rank's valid range and its arrival flag (sequence number) to every peer.
+    uint32_t nPeers, rank;                   // nPeers == 0: plain local build
+    const chordb::ExchangePeers* peers;      // peer pointer table in device memory (indexed by a loop variable: not a kernel parameter)
+    chordb::ExchangeHeader* localHeader;
+    uint32_t parity;                         // which of the two history slots this build fills (ranges[parity])
 };
 
 __device__ __forceinline__ __half to_half_rtz(float v) { return __float2half_rz(v); }
@@ -85,8 +93,8 @@ __global__ void __launch_bounds__(256, (kMin && kMax) ? 6 : 8) k_hzb_build(HzbBu
         if (kMax) sMaxP[l] = mx;
         if (x < p.mip0W && y < p.mip0H) {
             const size_t o = p.mipOffset[0] + (size_t)y * p.mip0W + x;
-            if (doMin) p.minChain[o] = to_half_rtz(mn);
-            if (doMax) p.maxChain[o] = to_half_rtz(mx);
+            if (doMin) { const __half hv = to_half_rtz(mn); p.minChain[o] = hv; for (uint32_t q = 0; q < p.nPeers; q++) p.peers->min[q][o] = hv; }
+            if (doMax) { const __half hv = to_half_rtz(mx); p.maxChain[o] = hv; for (uint32_t q = 0; q < p.nPeers; q++) p.peers->max[q][o] = hv; }
         }
     };
     if (evenWidth && bx * 64 + 64 <= p.width && by * 64 + 64 <= p.height) {
@@ -174,14 +182,87 @@ __global__ void __launch_bounds__(256, (kMin && kMax) ? 6 : 8) k_hzb_build(HzbBu
             const uint32_t x = bx * nw + lx, y = by * nw + ly;
             if (x < mw && y < mh) {
                 const size_t o = p.mipOffset[mip] + (size_t)y * mw + x;
-                if (doMin) p.minChain[o] = to_half_rtz(mn);
-                if (doMax) p.maxChain[o] = (mip == 5) ? half_plus_ulp(to_half_rtz(mx)) : to_half_rtz(mx);
+                if (doMin) { const __half hv = to_half_rtz(mn); p.minChain[o] = hv; for (uint32_t q = 0; q < p.nPeers; q++) p.peers->min[q][o] = hv; }
+                if (doMax) {
+                    const __half hv = (mip == 5) ? half_plus_ulp(to_half_rtz(mx)) : to_half_rtz(mx);
+                    p.maxChain[o] = hv; for (uint32_t q = 0; q < p.nPeers; q++) p.peers->max[q][o] = hv;
+                }
             }
         }
         __syncthreads();
         float* t = srcMin; srcMin = dstMin; dstMin = t; t = srcMax; srcMax = dstMax; dstMax = t;
         w = nw;
     }
+    if (p.nPeers) {
+        // "last block done": every block makes its peer stores visible system-wide and counts itself; the block that brings
+        // the count to numBlocks knows that every store of this launch (all blocks, all peers) has been performed, publishes
+        // this rank's valid depth range and then - after another system-scope fence - the arrival flag of this frame.
+        __shared__ uint32_t sLast;
+        __threadfence_system();
+        __syncthreads();
+        if (tid == 0) sLast = (atomicAdd(p.counter, 1u) + 1u == p.numBlocks) ? 1u : 0u;
+        __syncthreads();
+        if (sLast) {
+            __threadfence_system();
+            uint32_t seq = 0;
+            if (tid == 0) {
+                *p.counter = 0u;                                             // re-armed for the next launch (stream-ordered)
+                seq = p.localHeader->localSeq + 1u;
+                p.localHeader->localSeq = seq;
+            }
+            __syncthreads();
+            if (tid <= p.nPeers) {
+                chordb::ExchangeHeader* dst = tid < p.nPeers ? p.peers->header[tid] : p.localHeader;
+                if (kRange) {
+                    const volatile uint32_t* vr = p.validRange;               // final: every block's atomics precede its count
+                    dst->ranges[p.parity][p.rank][0] = vr[0]; dst->ranges[p.parity][p.rank][1] = vr[1];
+                }
+            }
+            __threadfence_system();
+            __syncthreads();
+            if (tid == 0) {
+                // broadcast the sequence number to thread 0's peers: one thread writes all flags so that they follow the fence
+                const uint32_t s2 = p.localHeader->localSeq;
+                for (uint32_t q = 0; q < p.nPeers; q++) *((volatile uint32_t*)&p.peers->header[q]->arrived[p.rank]) = s2;
+                *((volatile uint32_t*)&p.localHeader->arrived[p.rank]) = s2;
+            }
+            (void)seq;
+        }
+    }
+}
+
+// Consumer side of the fused exchange: runs (one block) in front of the first reader of a gathered history chain.  Waits until
+// every peer's arrival flag has reached this rank's own sequence number (all ranks render the same frames, so the numbers
+// advance in lock step; a peer may be one frame ahead - it then writes the OTHER history slot), folds the ranks' valid
+// ranges into the chain's validRange words and rebuilds mips 6.. from the gathered mip 5.  The wait is bounded: if a peer
+// never arrives (it died), status[0] is set and the kernel leaves instead of hanging the GPU.
+__global__ void __launch_bounds__(256) k_hzb_exchange_wait_top(HzbBuildParams p, uint32_t world, uint32_t* __restrict__ status, uint32_t maxSpins)
+{
+    __shared__ float sMinP[4096], sMinQ[1024], sMaxP[4096], sMaxQ[1024];
+    __shared__ uint32_t sFail;
+    if (threadIdx.x == 0) sFail = 0u;
+    __syncthreads();
+    const uint32_t target = p.localHeader->localSeq;
+    if (threadIdx.x < world && threadIdx.x != p.rank) {
+        const volatile uint32_t* flag = &p.localHeader->arrived[threadIdx.x];
+        uint32_t spins = 0;
+        while ((int32_t)(*flag - target) < 0) {
+            if (++spins > maxSpins) { sFail = 1u; break; }
+            __nanosleep(200);
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (sFail) { if (threadIdx.x == 0) atomicExch(&status[0], 1u); return; }
+    if (threadIdx.x == 0 && p.validRange) {
+        uint32_t lo = ~0u, hi = 0u;
+        for (uint32_t r = 0; r < world; r++) {
+            const volatile uint32_t* rr = p.localHeader->ranges[p.parity][r];
+            lo = min(lo, rr[0]); hi = max(hi, rr[1]);
+        }
+        p.validRange[0] = lo; p.validRange[1] = hi;
+    }
+    hzb_top_levels(p, sMinP, sMinQ, sMaxP, sMaxQ);
 }
 
 __global__ void __launch_bounds__(256) k_hzb_top(HzbBuildParams p)
@@ -200,6 +281,7 @@ static HzbBuildParams make_params(chord_frame* fr, int bMin, int bMax, int bRang
     p.validRange = bRange ? dst->validRange : nullptr;
     p.counter = dst->counter;
     p.blockX0 = p.blockY0 = 0; p.numBlocks = 0;
+    p.nPeers = 0; p.rank = 0; p.parity = 0; p.localHeader = nullptr; p.peers = nullptr;
     return p;
 }
 
@@ -216,10 +298,15 @@ static void tile_blocks(const chord_hzb* h, const chord_rect& t, uint32_t frameW
 static bool tile_aligned(const chord_rect& t, uint32_t w, uint32_t h)
 { return (t.x0 % 64 == 0) && (t.y0 % 64 == 0) && (t.x1 % 64 == 0 || t.x1 == w) && (t.y1 % 64 == 0 || t.y1 == h); }
 
-int launch_build_hzb(chord_frame* fr, int bMin, int bMax, int bRange, chord_hzb* dst)
+int launch_build_hzb(chord_frame* fr, int bMin, int bMax, int bRange, chord_hzb* dst, const HzbExchange* ex)
 {
     chord_ctx* ctx = fr->ctx;
     HzbBuildParams p = make_params(fr, bMin, bMax, bRange, dst);
+    if (ex && ex->nPeers) {
+        CHORD_REQUIRE(bMin, "the exchanged history chain is the min chain");
+        CHORD_REQUIRE(bMax, "an exchanged build stores both chains (the peer table always carries max pointers)");
+        p.nPeers = ex->nPeers; p.rank = ex->rank; p.parity = ex->parity; p.localHeader = ex->localHeader; p.peers = ex->dPeers;
+    }
     dim3 grid((dst->mip0W + 31) / 32, (dst->mip0H + 31) / 32);            // hzb.cpp:74
     const bool fullFrame = fr->tile.x0 == 0 && fr->tile.y0 == 0 && fr->tile.x1 == fr->width && fr->tile.y1 == fr->height;
     if (!fullFrame) {
@@ -228,8 +315,10 @@ int launch_build_hzb(chord_frame* fr, int bMin, int bMax, int bRange, chord_hzb*
         CHORD_REQUIRE(tile_aligned(fr->tile, fr->width, fr->height), "tile rect must be cut on multiples of 64 px for a tiled HZB build");
         uint32_t bx0, by0, bx1, by1; tile_blocks(dst, fr->tile, fr->width, fr->height, bx0, by0, bx1, by1);
         p.blockX0 = bx0; p.blockY0 = by0; grid = dim3(bx1 - bx0, by1 - by0);
-        if (bMin) CHORD_CUDA(cudaMemsetAsync(dst->minChain, 0, sizeof(__half) * dst->totalTexels, ctx->stream));
-        if (bMax) CHORD_CUDA(cudaMemsetAsync(dst->maxChain, 0, sizeof(__half) * dst->totalTexels, ctx->stream));
+        // an exchanged chain is NOT cleared: every texel of mips 0..5 has exactly one owner who rewrites it each frame, and a
+        // peer that runs ahead may already have stored its part of this frame into it
+        if (bMin && !p.nPeers) CHORD_CUDA(cudaMemsetAsync(dst->minChain, 0, sizeof(__half) * dst->totalTexels, ctx->stream));
+        if (bMax && !p.nPeers) CHORD_CUDA(cudaMemsetAsync(dst->maxChain, 0, sizeof(__half) * dst->totalTexels, ctx->stream));
     }
     p.numBlocks = grid.x * grid.y;
     if (bRange) {
@@ -242,7 +331,20 @@ int launch_build_hzb(chord_frame* fr, int bMin, int bMax, int bRange, chord_hzb*
     else if (bMin)              k_hzb_build<true, false, false><<<grid, 256, 0, ctx->stream>>>(p);
     else                        k_hzb_build<false, true, false><<<grid, 256, 0, ctx->stream>>>(p);
     ctx->launches++;
-    if (dst->mipCount > 6) { k_hzb_top<<<1, 256, 0, ctx->stream>>>(p); ctx->launches++; }     // tiled builds: from the tile-local mip 5, like the phase-1 HZB wants
+    // mips 6..: from the (tile-)local mip 5 now, like the phase-1 HZB wants; an exchanged chain gets them from the GATHERED
+    // mip 5 later (launch_hzb_exchange_wait_top, in front of the first reader)
+    if (dst->mipCount > 6 && !p.nPeers) { k_hzb_top<<<1, 256, 0, ctx->stream>>>(p); ctx->launches++; }
+    CHORD_CUDA(cudaGetLastError());
+    return CHORD_OK;
+}
+
+int launch_hzb_exchange_wait_top(chord_frame* fr, chord_hzb* dst, const HzbExchange* ex, uint32_t world, uint32_t* status)
+{
+    HzbBuildParams p = make_params(fr, 1, 1, 1, dst);
+    p.rank = ex->rank; p.parity = ex->parity; p.localHeader = ex->localHeader;
+    // ~4 s at 200 ns per poll before the wait gives up (a peer that died must not hang this GPU)
+    k_hzb_exchange_wait_top<<<1, 256, 0, fr->ctx->stream>>>(p, world, status, 20u * 1000u * 1000u);
+    fr->ctx->launches++;
     CHORD_CUDA(cudaGetLastError());
     return CHORD_OK;
 }

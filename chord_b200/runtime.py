@@ -30,7 +30,11 @@ SYMBOLS = [
     'chord_cascade_views_create', 'chord_cascade_views_destroy', 'chord_cascade_setup', 'chord_cascade_views_readback',
     'chord_cascade_views_upload', 'chord_frame_begin_cascade', 'chord_hzb_culling_generic_cascade',
     'chord_selftest_vertex_records',
-    'chord_graph_begin_capture', 'chord_graph_end_capture', 'chord_graph_launch', 'chord_graph_kernel_nodes', 'chord_graph_destroy',
+    'chord_renderer_create', 'chord_renderer_destroy', 'chord_renderer_set_tile', 'chord_renderer_render', 'chord_renderer_clear_history',
+    'chord_renderer_frame', 'chord_renderer_post_cull', 'chord_renderer_history_hzb', 'chord_renderer_graph_replays', 'chord_renderer_pass_times',
+    'chord_renderer_exchange_export', 'chord_renderer_exchange_connect', 'chord_renderer_history_sync', 'chord_renderer_exchange_status',
+    'chord_nccl_unique_id', 'chord_nccl_comm_create', 'chord_nccl_comm_destroy', 'chord_hzb_allgather', 'chord_renderer_exchange_connect_nccl',
+    'chord_graph_begin_capture', 'chord_graph_end_capture', 'chord_graph_launch', 'chord_graph_kernel_nodes', 'chord_graph_destroy', 'chord_graph_update_frame_inputs',
 ]
 
 _lib = None
@@ -54,7 +58,11 @@ def lib():
         L.chord_ctx_get_switch_flags.restype = C.c_uint32
         L.chord_ctx_refcount.restype = C.c_uint32
         L.chord_cmdlist_capacity.restype = C.c_uint32
-        for n in ('chord_cmdlist_count_ptr', 'chord_cmdlist_cmds_ptr', 'chord_hzb_chain_ptr', 'chord_frame_vis64_ptr'):
+        L.chord_renderer_graph_replays.restype = C.c_uint64
+        for n in ('chord_renderer_destroy', 'chord_nccl_comm_destroy'):
+            getattr(L, n).restype = None
+        for n in ('chord_cmdlist_count_ptr', 'chord_cmdlist_cmds_ptr', 'chord_hzb_chain_ptr', 'chord_frame_vis64_ptr', 'chord_renderer_frame',
+                  'chord_renderer_post_cull', 'chord_renderer_history_hzb'):
             getattr(L, n).restype = C.c_void_p
         L.chord_graph_kernel_nodes.restype = C.c_uint32
         for n in ('chord_ctx_destroy', 'chord_cmdlist_destroy', 'chord_hzb_destroy', 'chord_frame_destroy', 'chord_graph_destroy',
@@ -218,6 +226,13 @@ class Graph:
     def launch(self):
         lib().chord_graph_launch(self.h)
 
+    def update_frame_inputs(self, frame, view, iview, objects):
+        """chord_graph_update_frame_inputs: the next replay renders this camera / these object transforms."""
+        view = np.ascontiguousarray(view, dtype=abi.PerframeCameraView).reshape(())
+        iview = np.ascontiguousarray(iview, dtype=abi.InstanceCullingViewInfo).reshape(())
+        objects = np.ascontiguousarray(objects, dtype=abi.GPUObjectGLTFPrimitive)
+        lib().chord_graph_update_frame_inputs(self.h, frame.h, _p(view), _p(iview), _p(objects), C.c_uint32(len(objects)))
+
     def close(self):
         if self.h:
             lib().chord_graph_destroy(self.h)
@@ -233,12 +248,18 @@ class Graph:
 class CmdList:
     """CountAndCmdBuffer (postprocessing.h:48)."""
 
-    def __init__(self, ctx, capacity):
+    def __init__(self, ctx, capacity, _borrowed=None):
         self.ctx, self.capacity = ctx, int(capacity)
         self.h = C.c_void_p()
-        lib().chord_cmdlist_create(ctx.h, C.c_uint32(capacity), C.byref(self.h))
+        self._borrowed = _borrowed is not None
+        if self._borrowed:
+            self.h = C.c_void_p(_borrowed)                # owned by a Renderer
+        else:
+            lib().chord_cmdlist_create(ctx.h, C.c_uint32(capacity), C.byref(self.h))
 
     def close(self):
+        if self._borrowed:
+            self.h = C.c_void_p()
         if self.h:
             lib().chord_cmdlist_destroy(self.h)
             self.h = C.c_void_p()
@@ -276,10 +297,14 @@ class CmdList:
 class Hzb:
     """HZBContext (render_helper.h:411-451)."""
 
-    def __init__(self, ctx, width, height):
+    def __init__(self, ctx, width, height, _borrowed=None):
         self.ctx, self.width, self.height = ctx, int(width), int(height)
         self.h = C.c_void_p()
-        lib().chord_hzb_create(ctx.h, C.c_uint32(width), C.c_uint32(height), C.byref(self.h))
+        self._borrowed = _borrowed is not None
+        if self._borrowed:
+            self.h = C.c_void_p(_borrowed)                # owned by a Renderer
+        else:
+            lib().chord_hzb_create(ctx.h, C.c_uint32(width), C.c_uint32(height), C.byref(self.h))
         a, b, c, d, e = (C.c_uint32() for _ in range(5))
         lib().chord_hzb_info(self.h, C.byref(a), C.byref(b), C.byref(c), C.byref(d), C.byref(e))
         self.mip0 = (a.value, b.value)
@@ -287,6 +312,8 @@ class Hzb:
         self.valid_area = (d.value, e.value)
 
     def close(self):
+        if self._borrowed:
+            self.h = C.c_void_p()
         if self.h:
             lib().chord_hzb_destroy(self.h)
             self.h = C.c_void_p()
@@ -348,13 +375,19 @@ class Hzb:
 class Frame:
     """GBufferTextures + per-view uniforms of one render dimension."""
 
-    def __init__(self, ctx, width, height):
+    def __init__(self, ctx, width, height, _borrowed=None):
         self.ctx, self.width, self.height = ctx, int(width), int(height)
         self.h = C.c_void_p()
-        lib().chord_frame_create(ctx.h, C.c_uint32(width), C.c_uint32(height), C.byref(self.h))
+        self._borrowed = _borrowed is not None
+        if self._borrowed:
+            self.h = C.c_void_p(_borrowed)                # owned by a Renderer
+        else:
+            lib().chord_frame_create(ctx.h, C.c_uint32(width), C.c_uint32(height), C.byref(self.h))
         self._keep = None
 
     def close(self):
+        if self._borrowed:
+            self.h = C.c_void_p()
         if self.h:
             lib().chord_frame_destroy(self.h)
             self.h = C.c_void_p()
@@ -496,3 +529,138 @@ class Frame:
     @property
     def vis64_ptr(self):
         return lib().chord_frame_vis64_ptr(self.h)
+
+
+RENDERER_RESOLVE, RENDERER_PACKED_GBUFFER, RENDERER_BVH, RENDERER_GRAPH, RENDERER_TIMERS = 1, 2, 4, 8, 16
+PASS_LABELS = ['GLTF Instance Culling', 'GLTF Visibility Stage0', 'BuildHZB Post Prepass Stage0', 'GLTF Visibility Stage1',
+               'BuildHZB', 'VisibilityTileMarker', 'lightingTile']           # renderer.cpp:322-363 timer labels
+
+
+class NcclComm:
+    """chord_nccl_comm: an NCCL communicator created inside libchord_b200.so (libnccl.so.2 resolved with dlopen)."""
+
+    def __init__(self, ctx, world, rank, unique_id):
+        self.ctx, self.world, self.rank = ctx, world, rank
+        self.h = C.c_void_p()
+        buf = (C.c_ubyte * 128).from_buffer_copy(bytes(unique_id))
+        lib().chord_nccl_comm_create(ctx.h, C.c_uint32(world), C.c_uint32(rank), buf, C.byref(self.h))
+
+    @staticmethod
+    def unique_id():
+        buf = (C.c_ubyte * 128)()
+        lib().chord_nccl_unique_id(buf)
+        return bytes(buf)
+
+    def close(self):
+        if self.h:
+            lib().chord_nccl_comm_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Renderer:
+    """chord_renderer: DeferredRenderer::render (renderer.cpp:311-363 + :489) as one native call per frame, optionally recorded
+    as CUDA graphs and replayed, optionally one rank of a tile-parallel frame (fused peer-store or NCCL exchange of the
+    history HZB)."""
+
+    def __init__(self, ctx, width, height, resolve=False, packed_gbuffer=False, bvh=False, graph=False, timers=False):
+        self.ctx, self.width, self.height = ctx, int(width), int(height)
+        flags = (RENDERER_RESOLVE if resolve else 0) | (RENDERER_PACKED_GBUFFER if packed_gbuffer else 0) | (RENDERER_BVH if bvh else 0) \
+            | (RENDERER_GRAPH if graph else 0) | (RENDERER_TIMERS if timers else 0)
+        self.h = C.c_void_p()
+        lib().chord_renderer_create(ctx.h, C.c_uint32(width), C.c_uint32(height), C.c_uint32(flags), C.byref(self.h))
+        self.frame = Frame(ctx, width, height, _borrowed=lib().chord_renderer_frame(self.h))
+        self.tile = (0, 0, self.width, self.height)
+        self.rank, self.world = 0, 1
+        self._keep = None
+        self._lod0 = 0
+
+    def close(self):
+        if self.h:
+            self.frame.close()
+            lib().chord_renderer_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_tile(self, tile):
+        if tile is None:
+            lib().chord_renderer_set_tile(self.h, None)
+            self.tile = (0, 0, self.width, self.height)
+        else:
+            lib().chord_renderer_set_tile(self.h, C.byref(abi.Rect(*tile)))
+            self.tile = tuple(tile)
+
+    def render(self, view, iview, objects, lod0_meshlet_count, meshlet_group_count):
+        view = np.ascontiguousarray(view, dtype=abi.PerframeCameraView).reshape(())
+        iview = np.ascontiguousarray(iview, dtype=abi.InstanceCullingViewInfo).reshape(())
+        objects = np.ascontiguousarray(objects, dtype=abi.GPUObjectGLTFPrimitive)
+        self._keep = (view, iview, objects)
+        self._lod0 = int(lod0_meshlet_count)
+        lib().chord_renderer_render(self.h, _p(view), _p(iview), _p(objects), C.c_uint32(len(objects)),
+                                    C.c_uint32(lod0_meshlet_count), C.c_uint32(meshlet_group_count))
+
+    def clear_history(self):
+        lib().chord_renderer_clear_history(self.h)
+
+    @property
+    def post_cull(self):
+        p = lib().chord_renderer_post_cull(self.h)
+        return CmdList(self.ctx, lib().chord_cmdlist_capacity(C.c_void_p(p)), _borrowed=p) if p else None
+
+    @property
+    def history_hzb(self):
+        p = lib().chord_renderer_history_hzb(self.h)
+        return Hzb(self.ctx, self.width, self.height, _borrowed=p) if p else None
+
+    @property
+    def graph_replays(self):
+        return int(lib().chord_renderer_graph_replays(self.h))
+
+    def pass_times(self):
+        """{reference timer label: GPU microseconds} of the last frame (needs timers=True; synchronises)."""
+        out = (C.c_float * 7)()
+        lib().chord_renderer_pass_times(self.h, out)
+        return dict(zip(PASS_LABELS, [float(x) for x in out]))
+
+    # ---- multi-GPU exchange
+    def exchange_export(self):
+        """-> (64-byte CUDA IPC handle, device pointer) of this rank's exchange block."""
+        h = (C.c_ubyte * 64)()
+        ptr = C.c_void_p()
+        lib().chord_renderer_exchange_export(self.h, h, C.byref(ptr))
+        return bytes(h), int(ptr.value)
+
+    def exchange_connect(self, rank, world, tiles, handles=None, local_ptrs=None):
+        arr = (abi.Rect * world)(*[abi.Rect(*t) for t in tiles])
+        hs = None
+        if handles is not None:
+            hs = (C.c_ubyte * (64 * world))()
+            for i, b in enumerate(handles):
+                hs[64 * i:64 * i + 64] = list(b)
+        lp = (C.c_void_p * world)(*[C.c_void_p(int(p)) for p in local_ptrs]) if local_ptrs is not None else None
+        lib().chord_renderer_exchange_connect(self.h, C.c_uint32(rank), C.c_uint32(world), arr, hs, lp)
+        self.rank, self.world, self.tile = rank, world, tuple(tiles[rank])
+
+    def exchange_connect_nccl(self, tiles, comm: NcclComm):
+        arr = (abi.Rect * comm.world)(*[abi.Rect(*t) for t in tiles])
+        lib().chord_renderer_exchange_connect_nccl(self.h, arr, comm.h)
+        self.rank, self.world, self.tile = comm.rank, comm.world, tuple(tiles[comm.rank])
+        self._comm = comm
+
+    def history_sync(self):
+        lib().chord_renderer_history_sync(self.h)
+
+    def exchange_timed_out(self):
+        v = C.c_uint32()
+        lib().chord_renderer_exchange_status(self.h, C.byref(v))
+        return bool(v.value)

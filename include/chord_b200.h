@@ -83,6 +83,16 @@ int  chord_graph_begin_capture(chord_ctx* ctx);
 int  chord_graph_end_capture(chord_ctx* ctx, chord_graph** out);
 int  chord_graph_launch(chord_graph* graph);                 /* stream-ordered, asynchronous */
 uint32_t chord_graph_kernel_nodes(const chord_graph* graph); /* kernels one replay launches */
+/* A recorded frame replayed with NEW per-frame uniforms (the reference re-records its command buffer every frame with the
+ * frame's view; here only the uniform snapshot changes): rewrites the pinned block(s) the recorded chord_frame_begin call(s)
+ * on `frame` upload, so that the next chord_graph_launch renders this camera / these object transforms.  What was baked into
+ * kernel parameters at capture time must not change: objectCount, frame size and tile, cameraFovy, switch flags, which lists /
+ * HZBs the calls used.  Host-side only (a memcpy into pinned memory); call it after the previous replay of this graph has
+ * started executing its upload node - in practice: alternate two graphs (last frame's HZB ping-pong needs two anyway) or
+ * keep at most one frame in flight. */
+int  chord_graph_update_frame_inputs(chord_graph* graph, chord_frame* frame, const chord_PerframeCameraView* view,
+                                     const chord_InstanceCullingViewInfo* instanceView,
+                                     const chord_GPUObjectGLTFPrimitive* objects, uint32_t objectCount);
 void chord_graph_destroy(chord_graph* graph);
 
 /* ---- scene: replaces gpu_scene.{h,cpp} pools + the asset GPU buffers
@@ -300,6 +310,68 @@ int chord_frame_set_gbuffer_packed(chord_frame* frame, int packed);
 int chord_readback_gbuffer_packed(chord_frame* frame, int which, void* host);
 void* chord_frame_vis64_ptr(chord_frame* frame);
 int   chord_frame_dims(const chord_frame* frame, uint32_t* w, uint32_t* h);
+
+/* ---- the whole frame as ONE call: DeferredRenderer::render between "Clear GBuffers" and "lightingTile"
+ * (source/renderer/renderer.cpp:311-363) + the history hand-off (:489, m_rendererHistory.hzbCtx):
+ *   uniforms + addClearGbufferPass -> instanceCulling -> gltfVisibilityRenderingStage0 against LAST frame's HZB -> buildHZB(min)
+ *   -> gltfVisibilityRenderingStage1 -> buildHZB(min, max, range), kept as history -> visibilityMark -> lighting.
+ * The renderer owns the frame, the pooled lists and HZBs (getBufferPool() / getTexturePool() stand-in).  Flags:
+ *   CHORD_RENDERER_RESOLVE         run visibilityMark + lighting (needs chord_atmosphere_luts_upload and vertex normals)
+ *   CHORD_RENDERER_PACKED_GBUFFER  lighting writes the reference's storage formats (28 B / px)
+ *   CHORD_RENDERER_BVH             instance culling through the cluster-group BVH traversal
+ *   CHORD_RENDERER_GRAPH           record the sequence once per history slot (the reference records its command buffer every
+ *                                  frame, command_list.h:23-38) and replay it with the frame's uniforms rewritten: one launch
+ *                                  per frame.  The first two frames (and the frame after any change of object count, totals,
+ *                                  tile, switch flags or cameraFovy) run eagerly.
+ *   CHORD_RENDERER_TIMERS          GPU timers at the reference's seven cut points (renderer.cpp:322-363; the timer lambda of
+ *                                  GLTFRenderContext, gltf_rendering.h:15-35), read with chord_renderer_pass_times */
+typedef struct chord_renderer chord_renderer;
+enum { CHORD_RENDERER_RESOLVE = 1u, CHORD_RENDERER_PACKED_GBUFFER = 2u, CHORD_RENDERER_BVH = 4u, CHORD_RENDERER_GRAPH = 8u, CHORD_RENDERER_TIMERS = 16u };
+int  chord_renderer_create(chord_ctx* ctx, uint32_t width, uint32_t height, uint32_t flags, chord_renderer** out);
+void chord_renderer_destroy(chord_renderer* renderer);
+/* NULL = the full frame; otherwise cull (through the instance view the caller passes), raster, HZB and resolve are restricted to the rect */
+int  chord_renderer_set_tile(chord_renderer* renderer, const chord_rect* tile);
+int  chord_renderer_render(chord_renderer* renderer, const chord_PerframeCameraView* view, const chord_InstanceCullingViewInfo* instanceView,
+                           const chord_GPUObjectGLTFPrimitive* objects, uint32_t objectCount, uint32_t lod0MeshletCount, uint32_t meshletGroupCount);
+int  chord_renderer_clear_history(chord_renderer* renderer);       /* renderer.cpp:95-105 (resize / camera cut) */
+chord_frame*   chord_renderer_frame(chord_renderer* renderer);
+chord_cmdlist* chord_renderer_post_cull(chord_renderer* renderer);   /* drawMeshletCmdBuffer of the last frame */
+chord_hzb*     chord_renderer_history_hzb(chord_renderer* renderer); /* m_rendererHistory.hzbCtx */
+uint64_t       chord_renderer_graph_replays(const chord_renderer* renderer);
+enum { CHORD_PASS_INSTANCE_CULLING = 0, CHORD_PASS_VISIBILITY_STAGE0, CHORD_PASS_BUILD_HZB_STAGE0, CHORD_PASS_VISIBILITY_STAGE1,
+       CHORD_PASS_BUILD_HZB, CHORD_PASS_VISIBILITY_TILE_MARKER, CHORD_PASS_LIGHTING_TILE, CHORD_PASS_COUNT };
+int  chord_renderer_pass_times(chord_renderer* renderer, float outMicroseconds[CHORD_PASS_COUNT]);
+
+/* ---- multi-GPU: one rank per GPU, one screen tile per rank (cut on multiples of 64 px), scene replicated.
+ * Phase 0 of the two-phase occlusion cull needs last frame's WHOLE min-HZB on every rank; the reference is single-GPU.
+ *
+ * Fused exchange (default): chord_renderer_exchange_export allocates the rank's exchange block (two history HZBs + flags) and
+ * returns its CUDA IPC handle (ranks in different processes) and / or its device pointer (ranks in one process); the host
+ * gathers the handles / pointers of all ranks by any means and hands them to chord_renderer_exchange_connect.  From then on
+ * the final buildHZB of every frame stores this rank's part of mips 0..5 (min + max) straight into every rank's chain over
+ * NVLink, publishes its valid range and an arrival flag; the next frame begins with a one-block kernel that waits for all
+ * flags (bounded: chord_renderer_exchange_status reports a peer that never arrived) and rebuilds mips 6..: no pack /
+ * all-gather / unpack, no host synchronisation, recordable (CHORD_RENDERER_GRAPH).  All ranks must render the same frames.
+ * chord_renderer_history_sync completes last frame's chain now (tests / read-backs of chord_renderer_history_hzb).
+ *
+ * NCCL exchange: chord_nccl_* wrap a communicator (libnccl.so.2 is resolved with dlopen at the first call, there is no
+ * link-time dependency); chord_hzb_allgather = pack -> ncclAllGather -> unpack -> rebuild of mips 6.. on the context stream,
+ * for callers that sequence the passes themselves; chord_renderer_exchange_connect_nccl makes the renderer use it. */
+#define CHORD_MAX_RANKS 16
+typedef struct { unsigned char bytes[64]; } chord_ipc_handle;
+int  chord_renderer_exchange_export(chord_renderer* renderer, chord_ipc_handle* outHandle /* may be NULL */, void** outLocalPtr /* may be NULL */);
+int  chord_renderer_exchange_connect(chord_renderer* renderer, uint32_t rank, uint32_t world, const chord_rect* tiles /* [world] */,
+                                     const chord_ipc_handle* handles /* [world] or NULL */, void* const* localPtrs /* [world] or NULL */);
+int  chord_renderer_history_sync(chord_renderer* renderer);
+int  chord_renderer_exchange_status(chord_renderer* renderer, uint32_t* outTimedOut);
+typedef struct chord_nccl_comm chord_nccl_comm;
+int  chord_nccl_unique_id(unsigned char outId[128]);                 /* rank 0; distribute the 128 bytes to every rank */
+int  chord_nccl_comm_create(chord_ctx* ctx, uint32_t world, uint32_t rank, const unsigned char id[128], chord_nccl_comm** out);
+void chord_nccl_comm_destroy(chord_nccl_comm* comm);
+/* staging: device memory of at least (world + 1) x the largest chord_hzb_tile_bytes (each rounded up to 256 bytes) */
+int  chord_hzb_allgather(chord_frame* frame, chord_hzb* hzb, const chord_rect* tiles /* [world] */, chord_nccl_comm* comm,
+                         int bMin, int bMax, void* staging, uint64_t stagingBytes);
+int  chord_renderer_exchange_connect_nccl(chord_renderer* renderer, const chord_rect* tiles /* [world] */, chord_nccl_comm* comm);
 
 /* ---- statistics written by the raster kernels (device counters, read back on demand) */
 typedef struct {

@@ -95,6 +95,7 @@ template <typename T> static inline T __ldg(const T* p) { return *p; }
 template <typename T> static inline T __ldcg(const T* p) { return *p; }
 static inline size_t __cvta_generic_to_shared(const void* p) { return (size_t)p; }
 static inline void __threadfence() {}
+static inline void __threadfence_system() {}
 static inline void __nanosleep(unsigned) { hostcc::yield(); }
 static inline int min(int a, int b) { return a < b ? a : b; }
 static inline int max(int a, int b) { return a > b ? a : b; }
@@ -180,6 +181,8 @@ static inline cudaError_t cudaFreeAsync(void* p, cudaStream_t) { free(p); return
 static inline cudaError_t cudaFreeHost(void* p) { free(p); return cudaSuccess; }
 static inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { memcpy(d, s, n); return cudaSuccess; }
 static inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t) { memcpy(d, s, n); return cudaSuccess; }
+template <typename T> static inline cudaError_t cudaMemcpyToSymbolAsync(T& symbol, const void* s, size_t n, size_t offset, cudaMemcpyKind, cudaStream_t)
+{ memcpy(reinterpret_cast<char*>(&symbol) + offset, s, n); return cudaSuccess; }
 static inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t) { memset(d, v, n); return cudaSuccess; }
 static inline cudaError_t cudaMemset2DAsync(void* d, size_t pitch, int v, size_t w, size_t h, cudaStream_t)
 { for (size_t y = 0; y < h; y++) memset((char*)d + y * pitch, v, w); return cudaSuccess; }
@@ -193,6 +196,21 @@ static inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { *
 static inline cudaError_t cudaEventDestroy(cudaEvent_t e) { free(e); return cudaSuccess; }
 static inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return cudaSuccess; }
 static inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
+enum { cudaEventRecordExternal = 1, cudaIpcMemLazyEnablePeerAccess = 1 };
+static inline cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = (cudaEvent_t)malloc(8); return cudaSuccess; }
+static inline cudaError_t cudaEventRecordWithFlags(cudaEvent_t, cudaStream_t, unsigned) { return cudaSuccess; }
+static inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent_t) { *ms = 0.0f; return cudaSuccess; }
+// multi-GPU plumbing of renderer.cu: every "device" of the stand-in is host memory of this process, so peer pointers are plain
+// pointers (the in-process path of chord_renderer_exchange_connect); CUDA IPC between processes is not modelled
+struct cudaIpcMemHandle_t { char reserved[64]; };
+struct cudaPointerAttributes { int device; };
+static const cudaError_t cudaErrorPeerAccessAlreadyEnabled = (cudaError_t)704;
+static inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t* h, void* p) { memset(h, 0, sizeof(*h)); memcpy(h, &p, sizeof(p)); return cudaSuccess; }
+static inline cudaError_t cudaIpcOpenMemHandle(void**, cudaIpcMemHandle_t, unsigned) { return cudaErrorNotSupported; }
+static inline cudaError_t cudaIpcCloseMemHandle(void*) { return cudaSuccess; }
+static inline cudaError_t cudaPointerGetAttributes(cudaPointerAttributes* a, const void*) { a->device = 0; return cudaSuccess; }
+static inline cudaError_t cudaDeviceEnablePeerAccess(int, unsigned) { return cudaSuccess; }
+static inline cudaError_t cudaMemset(void* d, int v, size_t n) { memset(d, v, n); return cudaSuccess; }
 // graphs: not modelled (chord_graph_begin_capture reports the error; the graph tests need a GPU)
 static inline cudaError_t cudaStreamBeginCapture(cudaStream_t, cudaStreamCaptureMode) { return cudaErrorNotSupported; }
 static inline cudaError_t cudaStreamEndCapture(cudaStream_t, cudaGraph_t* g) { *g = nullptr; return cudaErrorNotSupported; }

@@ -14,7 +14,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, 'chord_b200', 'csrc')
-SOURCES = ['ctx.cu', 'cull.cu', 'raster.cu', 'hzb.cu', 'resolve.cu', 'shadow.cu']
+SOURCES = ['ctx.cu', 'cull.cu', 'raster.cu', 'hzb.cu', 'resolve.cu', 'shadow.cu', 'renderer.cu']
 
 # helper name -> host body (the signature stays the product's)
 PTX_HELPERS = {
@@ -114,7 +114,7 @@ def build(outdir, opt='-O1', extra=()):
         if p.returncode != 0:
             raise RuntimeError(f'hostcc: {s} does not compile for the host:\n{out[-6000:]}')
     so = os.path.join(outdir, 'libchord_b200_hostcc_scratch.so')
-    subprocess.check_call([cxx, '-shared', '-o', so] + objs + list(extra))
+    subprocess.check_call([cxx, '-shared', '-o', so] + objs + list(extra) + ['-ldl'])
     return so
 
 

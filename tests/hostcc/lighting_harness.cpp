@@ -61,13 +61,14 @@ extern "C" int hostcc_lighting(const chord_scene_desc* desc, const chord_Perfram
         tileList.push_back(tx * 8); tileList.push_back((ty * 8) | (pbr ? 0x80000000u : 0u)); tileCount++;
     }
 
-    LightingConsts lc;
-    fill_lighting_consts(*view, lc);
+    fill_lighting_consts(*view, c_lightingView[0]);          // the constant-bank slot the launcher fills with a device-to-device copy
+    LightingTargets lc;
+    lc.slot = 0;
     lc.trLut = (const __half*)trLut; lc.irLut = (const __half*)irLut;
     for (int i = 0; i < CHORD_GBUF_COUNT; i++) { lc.planes[i] = packed ? nullptr : (float*)planes[i]; lc.packed[i] = packed ? planes[i] : nullptr; }
     const unsigned grid = (tileCount + 3) / 4;
-    if (packed) run_grid(grid, 64, [&] { k_lighting<true>(f, lc, recs.data(), tileList.data(), &tileCount); });
-    else        run_grid(grid, 64, [&] { k_lighting<false>(f, lc, recs.data(), tileList.data(), &tileCount); });
+    if (packed) run_grid(grid, 64, [&] { k_lighting<true>(f, lc, recs.data(), tileList.data(), &tileCount, &nPost, nPost); });
+    else        run_grid(grid, 64, [&] { k_lighting<false>(f, lc, recs.data(), tileList.data(), &tileCount, &nPost, nPost); });
     return 0;
 }
 

@@ -973,6 +973,135 @@ def test_native_cpp_renderer_camera_path(gpu_ctx, tmp_path, exe=None):
         prev = ref['hzb']
 
 
+def _is_host_executor():
+    return 'hostcc_scratch' in runtime.LIB_PATH
+
+
+def test_native_renderer_camera_path(gpu_ctx):
+    """chord_renderer (the frame sequence of renderer.cpp:311-363 + the history hand-off at :489 as ONE native call per frame):
+    every frame's post-cull list, packed surface and history HZB (min, max, valid range) equal the oracle's, which runs with
+    the oracle's own history; the per-pass GPU timers at the reference's seven cut points come back through the API."""
+    from cases import city_frames
+    w, h = 640, 360
+    scene, info, frames = city_frames(frames=4, w=w, h=h)
+    gpu_ctx.upload_scene(scene)
+    for bvh in (False, True):
+        r = runtime.Renderer(gpu_ctx, w, h, bvh=bvh, timers=True)
+        prev = None
+        for i, f in enumerate(frames):
+            r.render(f['view'], f['iview'], f['objects'], info['lod0MeshletCount'], info['meshletGroupCount'])
+            ref = oracle.run_frame(scene, f['view'], f['iview'], f['objects'], w, h, info['lod0MeshletCount'], prev)
+            _assert_lists_equal(r.post_cull.readback(), ref['post_cull'], f'native renderer frame {i}')
+            _assert_vis_equal(r.frame.vis64(), ref['vis64'], f'native renderer frame {i}')
+            hz = r.history_hzb
+            _assert_hzb_equal(hz, ref['hzb'], 'min'); _assert_hzb_equal(hz, ref['hzb'], 'max')
+            assert np.array_equal(hz.valid_range(), ref['hzb']['range'])
+            t = r.pass_times()
+            assert list(t) == runtime.PASS_LABELS and all(v >= 0.0 for v in t.values())
+            if i > 0:
+                assert 'stage1_visible' in ref             # the camera path exercises both phases
+            prev = ref['hzb']
+        r.close()
+
+
+def test_native_renderer_graph_replay(gpu_ctx):
+    """CHORD_RENDERER_GRAPH: from the third frame on the recorded sequence is REPLAYED with the frame's uniforms rewritten
+    (chord_graph_update_frame_inputs): lists, packed surface, history HZB and all six resolve planes of every frame must be
+    bit-identical to the eager renderer's, and lists / surface to the oracle's."""
+    if _is_host_executor():
+        pytest.skip('CUDA graphs are not modelled by the host executor')
+    from cases import city_frames
+    w, h = 640, 360
+    scene, info, frames = city_frames(frames=7, w=w, h=h)
+    gpu_ctx.upload_scene(scene)
+    tr, ir = synth.synthetic_luts()
+    gpu_ctx.upload_luts(tr, ir)
+    eager = runtime.Renderer(gpu_ctx, w, h, resolve=True)
+    graph = runtime.Renderer(gpu_ctx, w, h, resolve=True, graph=True, timers=True)
+    prev = None
+    for i, f in enumerate(frames):
+        a = (f['view'], f['iview'], f['objects'], info['lod0MeshletCount'], info['meshletGroupCount'])
+        eager.render(*a); graph.render(*a)
+        ref = oracle.run_frame(scene, f['view'], f['iview'], f['objects'], w, h, info['lod0MeshletCount'], prev)
+        _assert_lists_equal(graph.post_cull.readback(), ref['post_cull'], f'graph frame {i}')
+        _assert_vis_equal(graph.frame.vis64(), ref['vis64'], f'graph frame {i}')
+        _assert_hzb_equal(graph.history_hzb, ref['hzb'], 'min')
+        for k in range(6):
+            assert np.array_equal(graph.frame.gbuffer(k).view(np.uint32), eager.frame.gbuffer(k).view(np.uint32)), f'resolve plane {k} of frame {i}: replay differs from eager'
+        assert graph.frame.gbuffer(0).max() > 0.01
+        t = graph.pass_times()
+        assert sum(t.values()) > 0.0
+        prev = ref['hzb']
+    assert graph.graph_replays >= 3, graph.graph_replays
+    eager.close(); graph.close()
+
+
+def _tile_case(gpu_ctx, world, w, h, frames_n):
+    from cases import city_frames
+    from chord_b200 import multigpu
+    scene, info, frames = city_frames(n_buildings=12, frames=frames_n, w=w, h=h)
+    tiles = multigpu.all_tiles(world, w, h)
+    return scene, info, frames, tiles, multigpu
+
+
+def test_renderer_fused_exchange_in_process(gpu_ctx, world=2, use_graph=False):
+    """Tile-parallel frame with the FUSED exchange (k_hzb_build stores each rank's part of the history chain straight into every
+    rank's chain, arrival flags, wait + top-mip rebuild in front of the next frame's phase 0): `world` ranks as separate
+    contexts in one process (peer pointers are plain device pointers here; across processes they come from CUDA IPC).  Every
+    frame: each rank's tile equals the single full frame inside the tile (depth bits + decoded ids), nothing outside it, and -
+    after chord_renderer_history_sync - every rank holds the single-GPU min / max chains and valid range bit for bit."""
+    w, h = 640, 384
+    scene, info, frames, tiles, multigpu = _tile_case(gpu_ctx, world, w, h, 5)
+    if use_graph and _is_host_executor():
+        pytest.skip('CUDA graphs are not modelled by the host executor')
+    make = type(gpu_ctx)
+    ctxs = [make(gpu_ctx.device) for _ in range(world)]
+    for c in ctxs:
+        c.upload_scene(scene)
+    gpu_ctx.upload_scene(scene)
+    single = runtime.Renderer(gpu_ctx, w, h)
+    ranks = [runtime.Renderer(c, w, h, graph=use_graph) for c in ctxs]
+    ptrs = [r.exchange_export()[1] for r in ranks]
+    for i, r in enumerate(ranks):
+        r.exchange_connect(i, world, tiles, local_ptrs=ptrs)
+    lod0, groups = info['lod0MeshletCount'], info['meshletGroupCount']
+    for fi, f in enumerate(frames):
+        single.render(f['view'], f['iview'], f['objects'], lod0, groups)
+        for i, r in enumerate(ranks):                     # lock step: every rank renders frame fi before anyone starts fi + 1
+            r.render(f['view'], multigpu.tile_instance_view(f['view'], f['camera'], tiles[i]), f['objects'], lod0, groups)
+        vs = single.frame.vis64()
+        ds = single.frame.decoded(single.post_cull)
+        union = np.zeros_like(vs)
+        for i, r in enumerate(ranks):
+            x0, y0, x1, y1 = tiles[i]
+            vt = r.frame.vis64()
+            assert np.array_equal(vt[y0:y1, x0:x1] >> np.uint64(32), vs[y0:y1, x0:x1] >> np.uint64(32)), f'frame {fi} rank {i}: depth differs inside the tile'
+            assert np.array_equal(r.frame.decoded(r.post_cull)[y0:y1, x0:x1], ds[y0:y1, x0:x1]), f'frame {fi} rank {i}: decoded ids differ inside the tile'
+            outside = vt.copy(); outside[y0:y1, x0:x1] = 0
+            assert not outside.any(), f'frame {fi} rank {i}: texels outside the tile'
+            union[y0:y1, x0:x1] = vt[y0:y1, x0:x1]
+        assert (union != 0).sum() == (vs != 0).sum()
+        for i, r in enumerate(ranks):
+            r.history_sync()
+        hs = single.history_hzb
+        for i, r in enumerate(ranks):
+            assert not r.exchange_timed_out()
+            hr = r.history_hzb
+            for which in ('min', 'max'):
+                assert np.array_equal(hr.readback_chain(which), hs.readback_chain(which)), f'frame {fi} rank {i}: gathered {which} chain differs from the single-GPU chain'
+            assert np.array_equal(hr.valid_range(), hs.valid_range()), f'frame {fi} rank {i}: valid range'
+    if use_graph:
+        assert all(r.graph_replays >= 1 for r in ranks)
+    for r in ranks + [single]:
+        r.close()
+    for c in ctxs:
+        c.close()
+
+
+def test_renderer_fused_exchange_four_ranks_graph(gpu_ctx):
+    test_renderer_fused_exchange_in_process(gpu_ctx, world=4, use_graph=True)
+
+
 def test_extreme_frame_shapes(gpu_ctx, shapes=((64, 64), (4096, 64), (64, 4096), (4096, 128))):
     """Render dimensions at the limits renderer.h:52-53 allows: the 64 x 64 minimum (six HZB mips, the fewest hzb.cpp:119
     accepts) and the 4096 maximum in one axis with the other tiny (twelve mips, the non-square tail of the chain where one

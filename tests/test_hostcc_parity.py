@@ -96,6 +96,15 @@ def test_extreme_frame_shapes(host_ctx, cases):
     cases.test_extreme_frame_shapes(host_ctx, **({} if FULL else {'shapes': ((64, 64), (4096, 64))}))
 
 
+def test_native_renderer_camera_path(host_ctx, cases):
+    cases.test_native_renderer_camera_path(host_ctx)
+
+
+def test_renderer_fused_exchange_in_process(host_ctx, cases):
+    cases.test_renderer_fused_exchange_in_process(host_ctx, world=2)
+    cases.test_renderer_fused_exchange_in_process(host_ctx, world=4)
+
+
 def test_tall_frame_hzb_rows(host_ctx, cases):
     cases.test_tall_frame_hzb_rows(host_ctx)
 
