@@ -50,6 +50,10 @@ def parse():
     ap.add_argument('--no-frame', action='store_true', help='skip the secondary full-frame (S3 stand-in) measurement')
     ap.add_argument('--no-graph', action='store_true', help='time eager launches instead of the recorded step (CUDA graph replay)')
     ap.add_argument('--frame-only', action='store_true', help='profiling aid: run only the full-frame workload and print its dict')
+    ap.add_argument('--frame-eager', action='store_true', help='profiling aid: the frame workloads without CUDA graphs (every kernel its own launch)')
+    ap.add_argument('--raster-variant', type=int, default=-1, help='tuning aid: chord_ctx_set_raster_tuning variant (0, 11, 13)')
+    ap.add_argument('--raster-ctas', type=int, default=-1, help='tuning aid: CTAs per SM of the meshlet rasteriser')
+    ap.add_argument('--raster-warp-min', type=int, default=-1, help='tuning aid: list length below which the CTA-per-meshlet kernel is used')
     return ap.parse_args()
 
 
@@ -178,78 +182,121 @@ def cpu_baseline(dev_scene, view, iview, objects, budget_s=12.0):
                       f'OpenMP over meshlets; CPU restatement of chord (reference not runnable offline)'}
 
 
-CITY = dict(n_buildings=24, patches=16, lods=5, n_protos=6, err_scale=0.5, seed=3)     # 30 784 LOD-0 meshlets = 3.94 M triangles
+CITY = dict(n_buildings=24, patches=16, lods=5, n_protos=6, err_scale=0.5, seed=3)     # S3 stand-in: 30 784 LOD-0 meshlets = 3.94 M triangles
+CITY_S2 = dict(n_buildings=24, patches=4, lods=3, n_protos=6, err_scale=0.5, seed=2)    # S2 stand-in: 1 984 LOD-0 meshlets = 254 k triangles
 
 
-def frame_benchmark(ctx, stream, torch, steps=20, width=W4K, height=H4K):
-    """S3 stand-in (BASELINE configs[2]): procedural city, ~3.8 M LOD-0 triangles, full reference frame sequence
-    (instance cull -> stage 0 on last frame's HZB -> HZB -> stage 1 -> HZB -> tile mark -> PBR resolve) along a camera
-    path; per-pass CUDA-event times at the reference's timer cut points (renderer.cpp:322-363)."""
-    from chord_b200 import camera as cam, renderer, synth
-    scene, camera, objects, info = synth.city_scene(width=width, height=height, **CITY)
-    ctx.upload_scene(scene)
-    tr, ir = synth.synthetic_luts()
-    ctx.upload_luts(tr, ir)
-    r = renderer.DeferredRenderer(ctx, width, height, do_resolve=True, packed_gbuffer=True)     # reference storage formats, 28 B/px
-    labels = ['GLTF Instance Culling', 'GLTF Visibility Stage0', 'BuildHZB Post Prepass Stage0', 'GLTF Visibility Stage1',
-              'BuildHZB', 'VisibilityTileMarker', 'lightingTile']
-    acc = {k: 0.0 for k in labels}
-    frames = []
-    last_view, last_cam = None, None
-    total = steps + 3
-    for fi in range(total):
-        c = cam.Camera(camera.position + np.array([0.15 * fi, 0.01 * fi, -0.6 * fi]), camera.front, width=width, height=height)
+def city_camera_path(camera, info, n, width, height, step=(0.15, 0.01, -0.6)):
+    """Per-frame inputs of a camera path (built before any timed region): (camera, objects, view, full-frame instance view)."""
+    from chord_b200 import camera as cam, synth
+    frames, last_view, last_cam = [], None, None
+    for fi in range(n):
+        c = cam.Camera(camera.position + np.array(step) * fi, camera.front, width=width, height=height)
         objs = synth.refill_objects(info['transforms'], c, camera_last=last_cam)
         view = cam.fill_view(c, last_view=last_view, frame_counter=fi)
         frames.append((c, objs, view, cam.fill_instance_view(view)))
         last_view, last_cam = view, c
-    f = r.frame
+    return frames
+
+
+def pass_rooflines(pass_us, width, height, post_meshlets, stage_meshlets, avg_meshlet_bytes, peak_gbs):
+    """Per-pass roofline of one frame: algorithmic bytes (SURVEY 8d / DESIGN section 4 figures) / measured GPU time."""
+    px = width * height
+    p2 = lambda v: 1 << (int(v) - 1).bit_length()
+    chain = (4.0 / 3.0) * 2 * (p2(width) // 2) * (p2(height) // 2)                  # fp16 texels of one chain
+    bytes_ = {
+        'GLTF Instance Culling': 118 * post_meshlets,                                # 64 B meshlet + 10 B group + 12 B cmd + 32 B HZB texels per candidate
+        'GLTF Visibility Stage0': avg_meshlet_bytes * stage_meshlets[0] + 8 * px,    # meshlet stream + the packed surface written once
+        'BuildHZB Post Prepass Stage0': 8 * px + chain,
+        'GLTF Visibility Stage1': avg_meshlet_bytes * stage_meshlets[1],
+        'BuildHZB': 8 * px + 2 * chain,
+        'VisibilityTileMarker': 8 * px + 16 * (px // 64),
+        'lightingTile': (8 + 28) * px,                                               # + ~208 B per distinct triangle (not counted: lower bound)
+    }
+    out = []
+    for k, us in pass_us.items():
+        b = float(bytes_.get(k, 0))
+        gbs = b / (us * 1e-6) / 1e9 if us > 0 else 0.0
+        out.append({'pass': k, 'bytes': int(b), 'us': us, 'achieved_gbs': gbs, 'frac': gbs / peak_gbs})
+    return out
+
+
+def frame_benchmark(ctx, stream, torch, steps=20, width=W4K, height=H4K, city=None, use_graph=True, label='S3 stand-in (Bistro-sized)', extras=True):
+    """BASELINE configs[2] (and, with CITY_S2 at 1080p, configs[1]): procedural city, full reference frame sequence (instance cull
+    -> stage 0 on last frame's HZB -> HZB -> stage 1 -> HZB -> tile mark -> PBR resolve) along a camera path, through the
+    NATIVE renderer (chord_renderer_render: one C-ABI call per frame; the sequence is recorded as two CUDA graphs - one per
+    history slot - and replayed with the frame's uniforms rewritten).  Frame time = CUDA events around `steps` frames / steps
+    (frames in flight overlap host and GPU like in a running renderer); per-pass GPU times come from the renderer's own
+    timers at the reference's cut points (renderer.cpp:322-363), measured on a second, untimed pass over the same frames."""
+    from chord_b200 import runtime, synth
+    city = city or CITY
+    scene, camera, objects, info = synth.city_scene(width=width, height=height, **city)
+    ctx.upload_scene(scene)
+    tr, ir = synth.synthetic_luts()
+    ctx.upload_luts(tr, ir)
     lod0, groups = info['lod0MeshletCount'], info['meshletGroupCount']
-    t_frames = []
-    for fi, (c, objs, view, iview) in enumerate(frames):
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(9)]
-        ev[0].record(stream)
-        f.begin(view, iview, objs, lod0, groups)
-        rc = renderer.GLTFRenderContext(f, len(objs), lod0, groups, r.pool)
-        ev[1].record(stream)
-        r.pool.release(r.post_cull)
-        post = renderer.instanceCulling(rc); ev[2].record(stream)
-        need1, rejected = renderer.gltfVisibilityRenderingStage0(rc, r.history_hzb, post); ev[3].record(stream)
-        if need1:
-            tmp = renderer.buildHZB(rc, True, False, False); ev[4].record(stream)
-            renderer.gltfVisibilityRenderingStage1(rc, tmp, rejected); ev[5].record(stream)
-            r.pool.release(tmp)
-        else:
-            ev[4].record(stream); ev[5].record(stream)
-        r.pool.release(rejected)
-        hzb = renderer.buildHZB(rc, True, True, True); ev[6].record(stream)
-        renderer.visibilityMark(rc, post); ev[7].record(stream)
-        renderer.lighting(rc, post); ev[8].record(stream)
-        r.pool.release(r.history_hzb)
-        r.history_hzb, r.last_view, r.post_cull = hzb, view, post
-        torch.cuda.synchronize()
-        if fi >= 3:
-            for k, lab in enumerate(labels):
-                acc[lab] += ev[k + 1].elapsed_time(ev[k + 2])
-            t_frames.append(ev[0].elapsed_time(ev[8]))
-    n = len(t_frames)
-    ms = float(np.median(t_frames))
-    stats = f.raster_stats()
-    extras = {}
+    frames = city_camera_path(camera, info, steps + 4, width, height)
+    r = runtime.Renderer(ctx, width, height, resolve=True, packed_gbuffer=True, graph=use_graph, timers=True)
+
+    def run(fs):
+        for (c, objs, view, iview) in fs:
+            r.render(view, iview, objs, lod0, groups)
+    run(frames[:4])                          # 2 eager frames + the two graph captures
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record(stream)
+    run(frames[4:])
+    e1.record(stream)
+    torch.cuda.synchronize()
+    wall_ms = (time.perf_counter() - t0) * 1e3 / steps
+    ms = e0.elapsed_time(e1) / steps
+    # per-pass times: same frames again, one synchronising timer read per frame (untimed)
+    acc = {k: 0.0 for k in runtime.PASS_LABELS}
+    stage_meshlets = [0, 0]
+    r.frame.reset_stats()
+    for (c, objs, view, iview) in frames[4:]:
+        r.render(view, iview, objs, lod0, groups)
+        for k, v in r.pass_times().items():
+            acc[k] += v
+    n = len(frames) - 4
+    pass_us = {k: v / n for k, v in acc.items()}
+    stats = r.frame.raster_stats()
+    post_n = int(r.post_cull.count())
+    d = scene.datas[0]
+    vt = d['meshlets']['vertexTriangleCount']
+    V, T = float((vt & 0xFF).mean()), float(((vt >> 8) & 0xFF).mean())
+    avg_bytes = 12 + 64 + 4 * V + 4 * T + 12 * V
+    peak = _peak_gbs()
+    per_frame_meshlets = stats['meshletsRastered'] / n
+    out = {'workload': f'{label}: procedural city, {lod0} LOD-0 meshlet instances = {lod0 * 128} triangles ({scene.total_meshlets} unique meshlets over '
+                       f'{city["lods"]} LODs, {len(frames[0][1])} objects), {width}x{height}, LOD cut at 1 px error, two-phase HZB, HZB builds, tile classify + '
+                       f'PBR resolve (packed G-buffer), camera path',
+           'submission': ('chord_renderer_render, recorded as 2 CUDA graphs and replayed with rewritten uniforms' if use_graph else 'chord_renderer_render, eager launches'),
+           'frames_per_s': 1000.0 / ms, 'ms_per_frame': ms, 'ms_per_frame_wall': wall_ms, 'frames_timed': steps, 'graph_replays': r.graph_replays,
+           'pass_us': pass_us, 'pass_us_sum': sum(pass_us.values()),
+           'pass_roofline': pass_rooflines(pass_us, width, height, post_n, [per_frame_meshlets * 0.8, per_frame_meshlets * 0.2], avg_bytes, peak),
+           'post_cull_meshlets_last_frame': post_n, 'raster_stats_total': stats}
+    r.close()
+    if extras:
+        ex = {}
+        try:
+            ex['shadow'] = shadow_benchmark(ctx, stream, torch, (scene, info, frames[-1][2], frames[-1][1]))
+        except Exception as e:
+            ex['shadow'] = {'error': repr(e)}
+        try:
+            ex['masked'] = masked_benchmark(ctx, stream, torch)
+        except Exception as e:
+            ex['masked'] = {'error': repr(e)}
+        out['next_rows'] = ex
+    return out
+
+
+def _peak_gbs():
     try:
-        extras['shadow'] = shadow_benchmark(ctx, stream, torch, (scene, info, frames[-1][2], frames[-1][1]))
-    except Exception as e:
-        extras['shadow'] = {'error': repr(e)}
-    try:
-        extras['masked'] = masked_benchmark(ctx, stream, torch)
-    except Exception as e:
-        extras['masked'] = {'error': repr(e)}
-    return {'next_rows': extras, 'workload': f'S3 stand-in (Bistro-sized): procedural city, {lod0} LOD-0 meshlet instances = {lod0 * 128} triangles '
-                        f'({scene.total_meshlets} unique meshlets over 5 LODs, {len(frames[0][1])} objects), {width}x{height}, '
-                        f'LOD cut at 1 px error, two-phase HZB, HZB builds, tile classify + PBR resolve (packed G-buffer), camera path',
-            'frames_per_s': 1000.0 / ms, 'ms_per_frame': ms, 'frames_timed': n,
-            'pass_us': {k: 1000.0 * v / n for k, v in acc.items()},
-            'post_cull_meshlets_last_frame': int(post.count()), 'raster_stats_total': stats}
+        return float(json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json'))).get('hbm_gbs', 6650.0))
+    except Exception:
+        return 6650.0
 
 
 def shadow_benchmark(ctx, stream, torch, scene_pack, steps=8, dim=2048, cascades=4):
@@ -329,40 +376,131 @@ def masked_benchmark(ctx, stream, torch, n_meshlets=100000, steps=10):
             'fragments_alpha_killed_per_step': int(st['fragmentsAlphaKilled'] // steps)}
 
 
-def frame_benchmark_tiled(ctx, stream, torch, dist, rank, world, steps=20, width=W4K, height=H4K):
-    """BASELINE configs[3]: the same city frame split into `world` screen tiles, one per GPU: tile sub-frustum cull, scissored
-    raster, tile-local phase-1 HZB, ONE NCCL all-gather of the packed min-HZB tile parts per frame (history for the next
-    frame's phase 0), local rebuild of mips 6.., tile-local resolve.  Frame time = max over ranks (device events)."""
-    from chord_b200 import camera as cam, multigpu, renderer, synth
+def frame_benchmark_tiled(ctx, stream, torch, dist, rank, world, steps=20, width=W4K, height=H4K, use_graph=True):
+    """BASELINE configs[3]: the same city frame split into `world` screen tiles, one per GPU, through the native renderer: tile
+    sub-frustum cull, scissored raster, tile-local phase-1 HZB, and the FUSED exchange of the history HZB - the final buildHZB
+    stores every rank's part of mips 0..5 straight into all ranks' chains over NVLink (peer pointers from CUDA IPC), arrival
+    flags instead of a collective, top mips rebuilt in front of the next phase 0; the whole tiled frame is one CUDA-graph
+    launch per rank.  Measured beside it: the same frame with pack -> ncclAllGather -> unpack inside the library
+    (chord_renderer_exchange_connect_nccl).  Frame time = max over ranks of (CUDA events around `steps` frames / steps).
+    Parity (untimed): every rank also renders the FULL frame on its own GPU; its tile must equal the full frame inside the
+    tile (depth bits + decoded ids), nothing outside it, and the gathered min / max chains + valid range must equal the
+    single-GPU history bit for bit - all-reduced over the ranks into `parity`."""
+    from chord_b200 import multigpu, runtime, synth
     scene, camera, objects, info = synth.city_scene(width=width, height=height, **CITY)
     ctx.upload_scene(scene)
     tr, ir = synth.synthetic_luts()
     ctx.upload_luts(tr, ir)
-    tr_ = multigpu.TileRenderer(ctx, width, height, rank, world, dist)
-    tr_.r.do_resolve = True
-    tr_.r.frame.set_gbuffer_packed(True)
     lod0, groups = info['lod0MeshletCount'], info['meshletGroupCount']
-    last_cam, times = None, []
-    for fi in range(steps + 3):
-        c = cam.Camera(camera.position + np.array([0.15 * fi, 0.01 * fi, -0.6 * fi]), camera.front, width=width, height=height)
-        objs = synth.refill_objects(info['transforms'], c, camera_last=last_cam)
-        view = cam.fill_view(c, last_view=tr_.r.last_view, frame_counter=fi)
+    frames = city_camera_path(camera, info, steps + 4, width, height)
+    tiles = multigpu.all_tiles(world, width, height)
+    tile_iviews = [multigpu.tile_instance_view(view, c, tiles[rank]) for (c, objs, view, iview) in frames]      # hoisted out of the timed region
+    dev = f'cuda:{ctx.device}'
+
+    def timed(r):
+        def run(lo, hi):
+            for i in range(lo, hi):
+                c, objs, view, _ = frames[i]
+                r.render(view, tile_iviews[i], objs, lod0, groups)
+        run(0, 4)
+        torch.cuda.synchronize()
         dist.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
         e0.record(stream)
-        tr_.render(c, objs, lod0, groups, view=view)
+        run(4, len(frames))
         e1.record(stream)
         torch.cuda.synchronize()
-        if fi >= 3:
-            times.append(e0.elapsed_time(e1))
-        last_cam = c
-    # median over frames (NCCL sets up its channels lazily, the first collectives of a new size are outliers), max over ranks
-    t = torch.tensor([float(np.median(times)), float(np.mean(times)), float(np.max(times))], dtype=torch.float64, device=f'cuda:{ctx.device}')
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, ms_mean, ms_max = (float(x) for x in t.tolist())
-    return {'workload': f'S3 stand-in city ({lod0 * 128} LOD-0 triangles) at {width}x{height} split into {world} screen tiles (one per GPU), '
-                        f'NCCL all-gather of the min-HZB tile parts per frame', 'frames_per_s': 1000.0 / ms, 'ms_per_frame': ms, 'ms_per_frame_mean': ms_mean, 'ms_per_frame_max': ms_max,
-            'frames_timed': len(times), 'tile_rank0': list(tr_.tile), 'hzb_allgather_bytes': int(sum(tr_.r.history_hzb.tile_bytes(t_) for t_ in multigpu.all_tiles(world, width, height)))}
+        wall = (time.perf_counter() - t0) * 1e3 / steps
+        t = torch.tensor([e0.elapsed_time(e1) / steps, wall], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.barrier()
+        return float(t[0]), float(t[1])
+
+    out = {'workload': f'S3 stand-in city ({lod0 * 128} LOD-0 triangles) at {width}x{height} split into {world} screen tiles (one per GPU), full frame sequence incl. PBR resolve',
+           'tile_rank0': list(tiles[0])}
+    # ---- fused exchange
+    r = runtime.Renderer(ctx, width, height, resolve=True, packed_gbuffer=True, graph=use_graph)
+    multigpu.connect_fused(r, rank, world, dist, tiles)
+    ms, wall = timed(r)
+    timed_out = r.exchange_timed_out()
+    out.update({'frames_per_s': 1000.0 / ms, 'ms_per_frame': ms, 'ms_per_frame_wall': wall, 'frames_timed': steps,
+                'exchange': 'fused: k_hzb_build stores the tile parts into every rank\'s history chain over NVLink peer memory (CUDA IPC), arrival flags, no collective call',
+                'submission': 'one CUDA graph launch per rank and frame' if use_graph else 'eager launches', 'graph_replays': r.graph_replays,
+                'exchange_bytes_per_frame': int(2 * sum(r.history_hzb.tile_bytes(t_) for t_ in tiles) * (world - 1)),
+                'exchange_timed_out': bool(timed_out)})
+    # ---- parity, untimed: tile vs full frame on this GPU, gathered history vs single-GPU history
+    single = runtime.Renderer(ctx, width, height)
+    r.clear_history()
+    ok_img = ok_out = ok_hzb = True
+    for i in range(3):
+        c, objs, view, iview = frames[i]
+        r.render(view, tile_iviews[i], objs, lod0, groups)
+        single.render(view, iview, objs, lod0, groups)
+        dist.barrier()                                         # (host-side only: the ranks stay in lock step for the read-backs)
+        r.history_sync()
+        x0, y0, x1, y1 = tiles[rank]
+        vt, vs = r.frame.vis64(), single.frame.vis64()
+        dt, ds = r.frame.decoded(r.post_cull), single.frame.decoded(single.post_cull)
+        ok_img &= bool(np.array_equal(vt[y0:y1, x0:x1] >> np.uint64(32), vs[y0:y1, x0:x1] >> np.uint64(32)) and np.array_equal(dt[y0:y1, x0:x1], ds[y0:y1, x0:x1]))
+        outside = vt.copy(); outside[y0:y1, x0:x1] = 0
+        ok_out &= not bool(outside.any())
+        hr, hs = r.history_hzb, single.history_hzb
+        ok_hzb &= bool(np.array_equal(hr.readback_chain('min'), hs.readback_chain('min')) and np.array_equal(hr.readback_chain('max'), hs.readback_chain('max'))
+                       and np.array_equal(hr.valid_range(), hs.valid_range()))
+    flags = torch.tensor([int(ok_img), int(ok_out), int(ok_hzb)], dtype=torch.int32, device=dev)
+    dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+    ti, to, th = (bool(int(x)) for x in flags.tolist())
+    out['parity'] = {'result': 'pass' if (ti and to and th) else 'FAIL', 'tile_ok': ti, 'outside_clean': to, 'hzb_ok': th,
+                     'what': 'untimed, 3 frames, every rank: its tile == the full frame rendered on the same GPU inside the tile (depth bits + decoded object / meshlet / triangle), '
+                             'no texel outside the tile, gathered min / max history chains + valid range == the single-GPU history; all-reduced (min) over the ranks'}
+    single.close(); r.close()
+    # ---- the same frame with the NCCL all-gather inside the library, for comparison
+    try:
+        rn = runtime.Renderer(ctx, width, height, resolve=True, packed_gbuffer=True, graph=use_graph)
+        multigpu.connect_nccl(rn, rank, world, dist, tiles)
+        ms_n, wall_n = timed(rn)
+        out['nccl_exchange'] = {'ms_per_frame': ms_n, 'ms_per_frame_wall': wall_n, 'frames_per_s': 1000.0 / ms_n,
+                                'exchange': 'pack -> ncclAllGather (communicator created by chord_nccl_comm_create) -> unpack -> top rebuild, captured in the same graph'}
+        rn.close()
+    except Exception as e:
+        out['nccl_exchange'] = {'error': repr(e)}
+    return out
+
+
+def heavy_frame_benchmark(ctx, stream, torch, dist, rank, world, dev_scene, view, camera, objects, M, groups, steps=10):
+    """The S5 stream (100 M ~1 px^2 triangles) through the WHOLE visibility sequence instead of raster only: per frame the tile
+    sub-frustum instance cull of all 781 250 meshlets, two-phase HZB culling against last frame's (exchanged) chain, raster,
+    both HZB builds and, at N > 1, the fused exchange - one CUDA-graph launch per rank and frame.  (No resolve: the synthetic
+    stream carries no normals.)  Strong scaling: the same frame split over N screen tiles."""
+    from chord_b200 import camera as cam, multigpu, runtime
+    tiles = multigpu.all_tiles(world, W4K, H4K)
+    iview = multigpu.tile_instance_view(view, camera, tiles[rank]) if world > 1 else cam.fill_instance_view(view)
+    r = runtime.Renderer(ctx, W4K, H4K, graph=True)
+    if world > 1:
+        multigpu.connect_fused(r, rank, world, dist, tiles)
+
+    def run(n):
+        for _ in range(n):
+            r.render(view, iview, objects, M, groups)
+    run(4)
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    run(steps)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / steps], dtype=torch.float64, device=f'cuda:{ctx.device}')
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t[0])
+    n_post = int(r.post_cull.count())
+    r.close()
+    return {'workload': f'S5 stream through cull -> stage 0 (HZB phase 0) -> HZB -> stage 1 -> HZB (+ fused exchange at N > 1), {M} meshlets = {M * TRIS_PER_MESHLET} triangles, '
+                        f'3840x2160, {world} screen tile(s), static camera', 'ms_per_frame': ms, 'frames_per_s': 1000.0 / ms,
+            'mtri_per_s': M * TRIS_PER_MESHLET / (ms * 1e-3) / 1e6, 'post_cull_meshlets_rank0': n_post}
 
 
 def main():
@@ -402,8 +540,9 @@ def main():
     torch.cuda.set_device(local_rank)
     stream = torch.cuda.ExternalStream(ctx.stream, device=local_rank)
 
+    ctx.set_raster_tuning(args.raster_variant, args.raster_ctas, args.raster_warp_min)
     if args.frame_only:
-        print(json.dumps(frame_benchmark(ctx, stream, torch, steps=args.steps)), flush=True)
+        print(json.dumps(frame_benchmark(ctx, stream, torch, steps=args.steps, use_graph=not args.frame_eager)), flush=True)
         return
     M = args.meshlets
     from chord_b200 import synth_device
@@ -568,10 +707,16 @@ def main():
     clocks = sampler.stop()
     clocks['note'] = 'sampled every 100 ms from warm-up through the timed regions plus a 0.7 s untimed continuation of the same workload'
 
+    frame_heavy = None
+    if not args.no_frame:
+        try:
+            frame_heavy = heavy_frame_benchmark(ctx, stream, torch, dist, rank, world, scene, view, camera, objects, M, groups)
+        except Exception as e:
+            frame_heavy = {'error': repr(e)}
     frame_tiled = None
     if dist is not None and not args.no_frame:
         try:
-            frame_tiled = frame_benchmark_tiled(ctx, stream, torch, dist, rank, world)
+            frame_tiled = frame_benchmark_tiled(ctx, stream, torch, dist, rank, world, use_graph=not args.frame_eager)
         except Exception as e:
             frame_tiled = {'error': repr(e)}
     times = torch.tensor([total_ms, kern_ms, e2e_ms], dtype=torch.float64, device=f'cuda:{local_rank}')
@@ -593,9 +738,20 @@ def main():
         peak = float(peaks.get('hbm_gbs', 6650.0))
         alg_bytes = n_local * BYTES_PER_MESHLET + 8 * (tile[2] - tile[0]) * (tile[3] - tile[1])
         achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
-        traffic = None
+        # DRAM traffic of the dominant kernel comes from an ncu --set full capture (a profiler cannot run inside the bench): it
+        # is only quoted when the capture was made with THIS raster.cu (sha256 of the kernel source recorded with it) and is
+        # scaled by the share of the stream this rank rasterises; otherwise null.
+        traffic, traffic_note = None, 'no ncu capture of this kernel source on record (profiles/raster_ncu_summary.json)'
         try:
-            traffic = json.load(open(os.path.join(ROOT, 'profiles', 'raster_ncu_summary.json'))).get('dram_bytes_per_launch')
+            import hashlib
+            summ = json.load(open(os.path.join(ROOT, 'profiles', 'raster_ncu_summary.json')))
+            sha = hashlib.sha256(open(os.path.join(ROOT, 'chord_b200', 'csrc', 'raster.cu'), 'rb').read()).hexdigest()
+            if summ.get('raster_cu_sha256') == sha:
+                traffic = int(summ['dram_bytes_per_launch'] * (n_local / float(summ.get('meshlets_per_launch', N_MESHLETS))))
+                traffic_note = (f"ncu --set full capture of commit {summ.get('commit', '?')} (same raster.cu): dram__bytes_read.sum + dram__bytes_write.sum of one "
+                                f"k_raster_fast launch over {summ.get('meshlets_per_launch', N_MESHLETS)} meshlets, scaled by this rank's {n_local} meshlets")
+            else:
+                traffic_note = 'stale: profiles/raster_ncu_summary.json was captured with another raster.cu (sha256 differs)'
         except Exception:
             pass
         line = {
@@ -613,7 +769,7 @@ def main():
             'gpu_launches': int(launches),
             'clocks': clocks,
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                         'traffic': traffic, 'kernel': 'k_raster_fast (+ prepare / deferred / large, < 4 % of the step)', 'kernel_ms': kern_ms,
+                         'traffic': traffic, 'traffic_note': traffic_note, 'kernel': 'k_raster_fast (+ prepare / deferred / large, < 4 % of the step)', 'kernel_ms': kern_ms,
                          'peak_source': 'MEASURED_PEAKS.json hbm_gbs (of measured)' if peaks else '6650 GB/s (of fallback)',
                          'algorithmic_bytes_per_launch': int(alg_bytes),
                          'note': 'at 14.7 B/tri the HBM roofline is ~450 G tri/s; the binding limits are per-triangle setup '
@@ -622,13 +778,22 @@ def main():
         }
         if not args.no_cpu_baseline and n_gpus == 1:
             line['cpu_baseline'] = cpu_baseline(scene, view, iview, objects)
+        if frame_heavy is not None:
+            line['frame_heavy'] = frame_heavy
         if frame_tiled is not None:
             line['frame'] = frame_tiled
+            if isinstance(frame_tiled.get('parity'), dict):
+                line['parity'] = frame_tiled['parity']['result']
         if n_gpus == 1 and not args.no_frame:
             try:
-                line['frame'] = frame_benchmark(ctx, stream, torch)
+                line['frame'] = frame_benchmark(ctx, stream, torch, use_graph=not args.frame_eager)
             except Exception as e:      # the headline metric must not depend on the secondary workload
                 line['frame'] = {'error': repr(e)}
+            try:
+                line['frame_s2'] = frame_benchmark(ctx, stream, torch, width=1920, height=1080, city=CITY_S2, use_graph=not args.frame_eager,
+                                                   label='S2 stand-in (Sponza-sized, BASELINE configs[1])', extras=False)
+            except Exception as e:
+                line['frame_s2'] = {'error': repr(e)}
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()

@@ -167,6 +167,30 @@ def allgather_hzb(frame, hzb, rank, world, dist, which=('min',), staging=None):
     return staging
 
 
+def connect_fused(renderer, rank, world, dist, tiles=None):
+    """Fused exchange between processes: every rank exports its exchange block (CUDA IPC), the 64-byte handles travel through
+    torch.distributed once, chord_renderer_exchange_connect maps the peers.  After this the frames need no collective call."""
+    tiles = tiles or all_tiles(world, renderer.width, renderer.height)
+    handle, _ = renderer.exchange_export()
+    handles = [None] * world
+    dist.all_gather_object(handles, handle)
+    renderer.exchange_connect(rank, world, tiles, handles=handles)
+    dist.barrier()                       # nobody renders before every rank has mapped every peer
+    return tiles
+
+
+def connect_nccl(renderer, rank, world, dist, tiles=None):
+    """NCCL exchange: a communicator created inside libchord_b200.so (rank 0's unique id is broadcast once)."""
+    from .runtime import NcclComm
+    tiles = tiles or all_tiles(world, renderer.width, renderer.height)
+    box = [NcclComm.unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    comm = NcclComm(renderer.ctx, world, rank, box[0])
+    renderer.exchange_connect_nccl(tiles, comm)
+    dist.barrier()
+    return tiles
+
+
 class TileRenderer:
     """DeferredRenderer for one rank of a tile-parallel frame."""
 
