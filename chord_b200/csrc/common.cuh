@@ -24,6 +24,11 @@ struct DatasDev {
     const chord_GPUGLTFMeshletGroup* groups;
     const uint32_t*                  groupIndices;
     const chord_GPUBVHNode*          bvhNodes;
+    // built by chord_scene_upload for the rasteriser (raster.cu: build_meshlet_packs): per meshlet ONE contiguous block
+    // [triangle words | float3 positions in meshlet order], its offset in uint4 units, and the vertex base it was gathered with
+    const uint4*                     packBlocks;
+    const uint32_t*                  packOffset;
+    const uint32_t*                  packVertexBase;
 };
 
 struct SceneDev {
@@ -310,6 +315,8 @@ int launch_split_vis(chord_frame* f, uint32_t* vis32, float* depth32);
 int launch_decode(chord_frame* f, chord_cmdlist* post, uint32_t* triples);
 int launch_selftest_vertex_records(chord_ctx* ctx, uint32_t n, uint32_t seed, uint32_t width, uint32_t height, uint32_t clampZ, unsigned long long* dOut);
 int scan_reset(chord_ctx* ctx, uint32_t tilesNeeded);
+int build_meshlet_packs(chord_ctx* ctx, DatasDev* d, uint32_t datasId, uint32_t meshletCount, uint32_t vertexCount, uint32_t groupCount, uint32_t groupIndicesCount,
+                        const chord_GLTFPrimitiveBuffer* dPrims, uint32_t nPrims, void** outAllocs);
 size_t lighting_view_bytes();                                                     // resolve.cu: sizeof(LightingView)
 void fill_lighting_view(const chord_PerframeCameraView& view, void* dst);         // host-side derivation of the resolve uniforms
 // one frame's inputs, staged as ONE block [view | instance view | LightingView | objects ...] (chord_frame_begin)

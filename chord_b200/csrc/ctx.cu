@@ -176,7 +176,7 @@ uint32_t chord_ctx_get_switch_flags(const chord_ctx* ctx) { return ctx ? ctx->sw
 int chord_ctx_set_raster_tuning(chord_ctx* ctx, int variant, int ctasPerSm, int64_t warpMinMeshlets)
 {
     CHORD_REQUIRE(ctx, "ctx");
-    CHORD_REQUIRE(variant < 0 || variant == 0 || variant == 11 || variant == 13, "variant (0, 11 or 13)");
+    CHORD_REQUIRE(variant < 0 || variant == 0 || variant == 11 || variant == 13 || variant == 14, "variant (0, 11, 13 or 14)");
     CHORD_REQUIRE(ctasPerSm <= 32, "ctasPerSm");
     if (variant >= 0) ctx->rasterVariant = variant;
     if (ctasPerSm >= 0) ctx->rasterCtasPerSm = ctasPerSm;
@@ -209,8 +209,15 @@ int chord_scene_upload(chord_ctx* ctx, const chord_scene_desc* desc)
         if ((rc = upload(ctx, allocs, d.groupIndices, d.groupIndicesCount, &o.groupIndices))) break;
         if ((rc = upload(ctx, allocs, d.bvhNodes, d.bvhNodeCount, &o.bvhNodes))) break;
     }
-    if (rc == CHORD_OK) rc = upload(ctx, allocs, ctx->datasHost, desc->datasCount, &ctx->scene.datas);
     if (rc == CHORD_OK) rc = upload(ctx, allocs, desc->primitives, desc->primitiveCount, &ctx->scene.prims);
+    for (uint32_t i = 0; i < desc->datasCount && rc == CHORD_OK; i++) {
+        // the rasteriser's packed per-meshlet blocks (positions in meshlet order next to the triangle words)
+        const chord_primitive_datas_desc& d = desc->datas[i];
+        void* packAllocs[3] = { nullptr, nullptr, nullptr };
+        rc = build_meshlet_packs(ctx, &ctx->datasHost[i], i, d.meshletCount, d.vertexCount, d.groupCount, d.groupIndicesCount, ctx->scene.prims, desc->primitiveCount, packAllocs);
+        for (void* a : packAllocs) if (a) allocs.push_back(a);
+    }
+    if (rc == CHORD_OK) rc = upload(ctx, allocs, ctx->datasHost, desc->datasCount, &ctx->scene.datas);
     if (rc == CHORD_OK) rc = upload(ctx, allocs, desc->materials, desc->materialCount, &ctx->scene.mats);
     ctx->scene.nDatas = desc->datasCount; ctx->scene.nPrims = desc->primitiveCount; ctx->scene.nMats = desc->materialCount;
     ctx->primGroupCountHost = (uint32_t*)malloc(sizeof(uint32_t) * desc->primitiveCount);
