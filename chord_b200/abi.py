@@ -165,8 +165,11 @@ ADDRESS_REPEAT, ADDRESS_CLAMP_TO_EDGE, ADDRESS_MIRRORED_REPEAT = 0, 1, 2
 PASS_DEPTH, PASS_DEPTH_CLAMP = 1, 2
 
 
+TEXTURE_SRGB = 1
+
+
 class TextureDesc(C.Structure):
-    _fields_ = [('rgba8', C.c_void_p), ('width', C.c_uint32), ('height', C.c_uint32), ('mipCount', C.c_uint32)]
+    _fields_ = [('rgba8', C.c_void_p), ('width', C.c_uint32), ('height', C.c_uint32), ('mipCount', C.c_uint32), ('flags', C.c_uint32)]
 
 
 class SamplerDesc(C.Structure):
@@ -192,7 +195,8 @@ class TextureTable:
     white) or a list of (h, w, 4) uint8 mip levels (level k is max(1, w >> k) x max(1, h >> k)); ``samplers`` is a list
     of (addressU, addressV)."""
 
-    def __init__(self, textures, samplers=((ADDRESS_REPEAT, ADDRESS_REPEAT),)):
+    def __init__(self, textures, samplers=((ADDRESS_REPEAT, ADDRESS_REPEAT),), srgb=()):
+        """``srgb``: indices of the textures whose r, g, b are sRGB encoded (CHORD_TEXTURE_SRGB: base colour / emissive images)."""
         self._keep = []
         self.tex = (TextureDesc * max(len(textures), 1))()
         self.n_tex = len(textures)
@@ -205,6 +209,7 @@ class TextureTable:
             blob = np.concatenate([np.ascontiguousarray(lv).reshape(-1) for lv in t])
             self._keep.append(blob)
             self.tex[i].rgba8, self.tex[i].width, self.tex[i].height, self.tex[i].mipCount = blob.ctypes.data, w, h, len(t)
+            self.tex[i].flags = TEXTURE_SRGB if i in srgb else 0
         self.smp = (SamplerDesc * max(len(samplers), 1))()
         self.n_smp = len(samplers)
         for i, (u, v) in enumerate(samplers):

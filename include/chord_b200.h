@@ -125,12 +125,16 @@ int chord_scene_upload(chord_ctx* ctx, const chord_scene_desc* desc);
  * GLTFMaterialGPUData.baseColorId / baseColorSampler (gltf.h:118-153; mesh_raster.hlsl:107-112, :198-204) by an index
  * into the table uploaded here.  Texels are uncompressed RGBA8 unorm (asset_gltf_material.cpp:80-112 also knows BC
  * formats; decompress before upload), mip k is max(1, w >> k) x max(1, h >> k), mips tightly packed from 0 down.
- * Only the alpha channel is kept in HBM (one byte per texel): the raster path reads nothing else.
+ * The raster path reads a copy that keeps only the alpha channel (one byte per texel); the resolve (chord_lighting: base
+ * colour, normal map, occlusion / roughness / metallic through SampleGrad, material.hlsli:30-154) reads the RGBA8 chains.
  * An id that is out of range, CHORD_UNVALID_ID or whose desc has rgba8 == NULL is the builtin white texture
  * (alpha 1; asset_gltf.cpp:295-326), which makes the alpha test a per-meshlet constant.
  * The sampler is specified in DESIGN.md section 3 (trilinear, LOD from forward-differenced perspective-correct uv). */
 enum { CHORD_ADDRESS_REPEAT = 0, CHORD_ADDRESS_CLAMP_TO_EDGE = 1, CHORD_ADDRESS_MIRRORED_REPEAT = 2 };
-typedef struct { const uint8_t* rgba8; uint32_t width, height, mipCount; } chord_texture_desc;
+/* flags: CHORD_TEXTURE_SRGB = the texel's r, g, b are sRGB-encoded and decoded to linear BEFORE filtering, as a *_SRGB image
+ * format does (base colour / emissive images: asset_gltf_material.cpp:130-155, :510-511); alpha is always linear. */
+enum { CHORD_TEXTURE_SRGB = 1u };
+typedef struct { const uint8_t* rgba8; uint32_t width, height, mipCount, flags; } chord_texture_desc;
 typedef struct { uint32_t addressU, addressV; } chord_sampler_desc;
 int chord_textures_upload(chord_ctx* ctx, const chord_texture_desc* textures, uint32_t textureCount,
                           const chord_sampler_desc* samplers, uint32_t samplerCount);

@@ -574,6 +574,76 @@ float oracle_sample_alpha(const chord_texture_desc* tex, const chord_sampler_des
     return a;
 }
 
+/* ---- K11 material textures: SampleGrad (material.hlsli:66-79, :103-107, :126-130) with the SAME pinned sampler, on all four
+ * channels and with the explicit gradients the resolve computes analytically (base.hlsli:457-498).  A texture flagged
+ * CHORD_TEXTURE_SRGB decodes r, g, b texel-wise to linear before filtering (what a *_SRGB image format does): the decode is a
+ * 256-entry table built once with the IEC 61966-2-1 formula in double precision (the library builds the same table with the
+ * same host libm, so both sides hold identical floats). */
+static float g_srgb_lut[256]; static int g_srgb_lut_ready = 0;
+static const float* srgb_lut(void)
+{
+    if (!g_srgb_lut_ready) {
+        for (int i = 0; i < 256; i++) {
+            const double c = (double)i / 255.0;
+            g_srgb_lut[i] = (float)(c <= 0.04045 ? c / 12.92 : pow((c + 0.055) / 1.055, 2.4));
+        }
+        __atomic_store_n(&g_srgb_lut_ready, 1, __ATOMIC_RELEASE);
+    }
+    return g_srgb_lut;
+}
+
+static void rgba_bilinear(const uint8_t* rgba8, int w, int h, uint32_t modeU, uint32_t modeV, float u, float v, const float* lut, float out[4])
+{
+    const float x = fmaf(u, (float)w, -0.5f), y = fmaf(v, (float)h, -0.5f);
+    const float fx0 = fminf(fmaxf(floorf(x), -16777216.0f), 16777216.0f), fy0 = fminf(fmaxf(floorf(y), -16777216.0f), 16777216.0f);
+    float fx = x - fx0, fy = y - fy0;
+    if (!(fx >= 0.0f && fx <= 1.0f)) fx = 0.0f;
+    if (!(fy >= 0.0f && fy <= 1.0f)) fy = 0.0f;
+    const int x0 = wrap_texel((int)fx0, w, modeU), x1 = wrap_texel((int)fx0 + 1, w, modeU);
+    const int y0 = wrap_texel((int)fy0, h, modeV), y1 = wrap_texel((int)fy0 + 1, h, modeV);
+    const uint8_t* t00 = rgba8 + ((size_t)y0 * w + x0) * 4; const uint8_t* t10 = rgba8 + ((size_t)y0 * w + x1) * 4;
+    const uint8_t* t01 = rgba8 + ((size_t)y1 * w + x0) * 4; const uint8_t* t11 = rgba8 + ((size_t)y1 * w + x1) * 4;
+    for (int c = 0; c < 4; c++) {
+        const int dec = lut != NULL && c < 3;
+        const float a00 = dec ? lut[t00[c]] : (float)t00[c] / 255.0f, a10 = dec ? lut[t10[c]] : (float)t10[c] / 255.0f;
+        const float a01 = dec ? lut[t01[c]] : (float)t01[c] / 255.0f, a11 = dec ? lut[t11[c]] : (float)t11[c] / 255.0f;
+        const float top = fmaf(fx, a10 - a00, a00), bot = fmaf(fx, a11 - a01, a01);
+        out[c] = fmaf(fy, bot - top, top);
+    }
+}
+
+/* returns 0 (and builtin white) when the id does not name an uploaded texture */
+int oracle_sample_rgba(const chord_texture_desc* tex, const chord_sampler_desc* smp, float u, float v,
+                       float dudx, float dvdx, float dudy, float dvdy, float out[4])
+{
+    out[0] = out[1] = out[2] = out[3] = 1.0f;
+    if (!tex || !tex->rgba8 || tex->width == 0 || tex->height == 0 || tex->mipCount == 0) return 0;     /* builtin white */
+    const uint32_t modeU = smp ? smp->addressU : CHORD_ADDRESS_REPEAT, modeV = smp ? smp->addressV : CHORD_ADDRESS_REPEAT;
+    const float* lut = (tex->flags & CHORD_TEXTURE_SRGB) ? srgb_lut() : NULL;
+    const float W0 = (float)tex->width, H0 = (float)tex->height;
+    const float ax = dudx * W0, bx = dvdx * H0, ay = dudy * W0, by = dvdy * H0;
+    const float rx2 = fmaf(bx, bx, ax * ax), ry2 = fmaf(by, by, ay * ay);
+    const float r2 = fmaxf(rx2, ry2);
+    uint32_t level = 0; float frac = 0.0f;
+    if (r2 > 1.0f) {
+        const float rho = sqrtf(r2);
+        const uint32_t bits = f2u(rho);
+        const uint32_t e = (bits >> 23) & 0xFFu;
+        if (e - 127u >= tex->mipCount - 1u) { level = tex->mipCount - 1u; frac = 0.0f; }
+        else { level = e - 127u; frac = u2f((bits & 0x007FFFFFu) | 0x3F800000u) - 1.0f; }
+    }
+    int w, h;
+    const uint8_t* t0 = mip_texels(tex, level, &w, &h);
+    rgba_bilinear(t0, w, h, modeU, modeV, u, v, lut, out);
+    if (frac > 0.0f) {
+        float o1[4];
+        const uint8_t* t1 = mip_texels(tex, level + 1u, &w, &h);
+        rgba_bilinear(t1, w, h, modeU, modeV, u, v, lut, o1);
+        for (int c = 0; c < 4; c++) out[c] = fmaf(frac, o1[c] - out[c], out[c]);
+    }
+    return 1;
+}
+
 /* per-triangle attributes of the masked bucket: 1/w and uv0 per (possibly clipped) vertex + the material's test */
 typedef struct {
     const chord_texture_desc* tex; const chord_sampler_desc* smp;
@@ -1091,6 +1161,11 @@ static v3 sun_and_sky_irradiance(const chord_AtmosphereParameters* at, const uin
 
 static inline double storage_to_double(chord_uint2 u) { uint64_t b = (uint64_t)u.x | ((uint64_t)u.y << 32); double d; memcpy(&d, &b, 8); return d; }
 
+static inline const chord_texture_desc* tex_lookup(const oracle_frame* f, uint32_t id)
+{ return (f->textures && id < f->textureCount && f->textures[id].rgba8) ? &f->textures[id] : NULL; }
+static inline const chord_sampler_desc* smp_lookup(const oracle_frame* f, uint32_t id)
+{ return (f->samplers && id < f->samplerCount) ? &f->samplers[id] : NULL; }
+
 void oracle_lighting(const oracle_frame* f, const uint64_t* vis64, const chord_draw_cmd* postCull, uint32_t postCullCount,
                      const uint16_t* trLut, const uint16_t* irLut, float* const planes[6])
 {
@@ -1122,7 +1197,11 @@ void oracle_lighting(const oracle_frame* f, const uint64_t* vis64, const chord_d
             const chord_GPUGLTFMeshlet* m = &o.datas->meshlets[cmd.meshletId];
             const uint32_t V = m->vertexTriangleCount & 0xFFu;
             const uint32_t idx = o.datas->meshletData[m->dataOffset + V + tri];
-            v3 posRS[3], nrm[3]; f4 hs[3]; v3 hsNJ[3], hsLast[3]; float uv[3][2];
+            v3 posRS[3], nrm[3], tanRS[3], bitRS[3]; f4 hs[3]; v3 hsNJ[3], hsLast[3]; float uv[3][2];
+            const chord_GLTFMaterialGPUData* matT = o.material;
+            /* a texture id "exists" when it names an uploaded texture; the normal map additionally needs the tangent stream */
+            const chord_texture_desc* texBase = tex_lookup(f, matT->baseColorId), *texNrm = tex_lookup(f, matT->normalTexture), *texMR = tex_lookup(f, matT->metallicRoughnessTexture);
+            const int bExistNormalTexture = texNrm != NULL && o.datas->tangents != NULL && o.datas->uv0 != NULL;
             for (int i = 0; i < 3; i++) {
                 uint32_t vi = o.prim->vertexOffset + o.datas->meshletData[m->dataOffset + ((idx >> (i * 8)) & 0xFFu)];
                 const float* p = &o.datas->positions[(size_t)vi * 3];
@@ -1137,8 +1216,17 @@ void oracle_lighting(const oracle_frame* f, const uint64_t* vis64, const chord_d
                 const float* M = o.object->basicData.translatedWorldToLocal.m;
                 v3 nn = v3_(n[0] * M[0] + n[1] * M[1] + n[2] * M[2], n[0] * M[4] + n[1] * M[5] + n[2] * M[6], n[0] * M[8] + n[1] * M[9] + n[2] * M[10]);
                 nrm[i] = v3norm(nn);
+                tanRS[i] = bitRS[i] = v3_(0, 0, 0);
+                if (bExistNormalTexture) {                                   /* nanite_shared.hlsli:160-176 */
+                    const float* tg = &o.datas->tangents[(size_t)vi * 4];
+                    f4 tw = mat_mul_vec(l2w, tg[0], tg[1], tg[2], 0.0f);
+                    v3 t = v3_(tw.x, tw.y, tw.z);
+                    t = v3norm(v3sub(t, v3s(nrm[i], v3dot(t, nrm[i]))));     /* Gram-Schmidt */
+                    tanRS[i] = t;
+                    const v3 n_ = nrm[i];
+                    bitRS[i] = v3s(v3_(n_.y * t.z - n_.z * t.y, n_.z * t.x - n_.x * t.z, n_.x * t.y - n_.y * t.x), tg[3]);
+                }
             }
-            (void)uv;
             /* calculateTriangleBarycentrics (base.hlsli:457-498) */
             const float su = ((float)px + 0.5f) * tsx, sv = ((float)py + 0.5f) * tsy;
             const float pcx = 2.0f * (su - 0.5f), pcy = 2.0f * (0.5f - sv);
@@ -1153,19 +1241,50 @@ void oracle_lighting(const oracle_frame* f, const uint64_t* vis64, const chord_d
             const float Hs = C0 * rw0 + C1 * rw1 + C2 * rw2;
             const float rH = 1.0f / Hs;
             const float b0 = G0 * rH, b1 = G1 * rH, b2 = G2 * rH;
+            /* analytic screen-space derivatives of the barycentrics (base.hlsli:478-496) and of uv (material.hlsli:52-54) */
+            const float Gdx0 = cdx0 * rw0, Gdx1 = cdx1 * rw1, Gdx2 = cdx2 * rw2, Gdy0 = cdy0 * rw0, Gdy1 = cdy1 * rw1, Gdy2 = cdy2 * rw2;
+            const float Hdx = cdx0 * rw0 + cdx1 * rw1 + cdx2 * rw2, Hdy = cdy0 * rw0 + cdy1 * rw1 + cdy2 * rw2;
+            const float rH2 = rH * rH, sxs = 2.0f * tsx, sys = -2.0f * tsy;
+            const float ddx0 = (Gdx0 * Hs - G0 * Hdx) * rH2 * sxs, ddx1 = (Gdx1 * Hs - G1 * Hdx) * rH2 * sxs, ddx2 = (Gdx2 * Hs - G2 * Hdx) * rH2 * sxs;
+            const float ddy0 = (Gdy0 * Hs - G0 * Hdy) * rH2 * sys, ddy1 = (Gdy1 * Hs - G1 * Hdy) * rH2 * sys, ddy2 = (Gdy2 * Hs - G2 * Hdy) * rH2 * sys;
+            const float mu = uv[0][0] * b0 + uv[1][0] * b1 + uv[2][0] * b2, mv = uv[0][1] * b0 + uv[1][1] * b1 + uv[2][1] * b2;
+            const float mudx = uv[0][0] * ddx0 + uv[1][0] * ddx1 + uv[2][0] * ddx2, mvdx = uv[0][1] * ddx0 + uv[1][1] * ddx1 + uv[2][1] * ddx2;
+            const float mudy = uv[0][0] * ddy0 + uv[1][0] * ddy1 + uv[2][0] * ddy2, mvdy = uv[0][1] * ddy0 + uv[1][1] * ddy1 + uv[2][1] * ddy2;
             /* motion vector */
             v3 mp = v3add(v3add(v3s(hsNJ[0], b0), v3s(hsNJ[1], b1)), v3s(hsNJ[2], b2));
             v3 ml = v3add(v3add(v3s(hsLast[0], b0), v3s(hsLast[1], b1)), v3s(hsLast[2], b2));
             const float mvx = (ml.x / ml.z - mp.x / mp.z) * 0.5f, mvy = (ml.y / ml.z - mp.y / mp.z) * -0.5f;
             v3 posR = v3add(v3add(v3s(posRS[0], b0), v3s(posRS[1], b1)), v3s(posRS[2], b2));
-            /* material (untextured: builtin white base colour, transparent emissive) */
+            /* material (material.hlsli:66-153).  A base colour id that names no uploaded texture is the builtin white the reference
+             * binds (asset_gltf.cpp:295-326); the emissive texture is sampled by the reference but its value is never added to the
+             * colour on this path (material.hlsli:81 stores it, lighting.hlsl never reads it), so it is not sampled here */
             const chord_GLTFMaterialGPUData* mat = o.material;
-            v3 base = mat3_mul(ap1, v3_(1.0f * mat->baseColorFactor.x, 1.0f * mat->baseColorFactor.y, 1.0f * mat->baseColorFactor.z));
+            float bc[4];
+            oracle_sample_rgba(texBase, smp_lookup(f, mat->baseColorSampler), mu, mv, mudx, mvdx, mudy, mvdy, bc);
+            v3 base = mat3_mul(ap1, v3_(bc[0] * mat->baseColorFactor.x, bc[1] * mat->baseColorFactor.y, bc[2] * mat->baseColorFactor.z));
             v3 vnrm = v3add(v3add(v3s(nrm[0], b0), v3s(nrm[1], b1)), v3s(nrm[2], b2));
             v3 pnrm = vnrm;
-            const float rough = mat->roughnessFactor;
-            const float metal = mat->metallicFactor >= 1.0f ? 0.0f : mat->metallicFactor;      /* getFallbackMetallic, gltf.h:53-58 */
-            const float ao = 1.0f;
+            if (bExistNormalTexture) {
+                const v3 tRS = v3add(v3add(v3s(tanRS[0], b0), v3s(tanRS[1], b1)), v3s(tanRS[2], b2));
+                const v3 bRS = v3add(v3add(v3s(bitRS[0], b0), v3s(bitRS[1], b1)), v3s(bitRS[2], b2));
+                float nt[4];
+                oracle_sample_rgba(texNrm, smp_lookup(f, mat->normalSampler), mu, mv, mudx, mvdx, mudy, mvdy, nt);
+                float nx = nt[0] * 2.0f - 1.0f, ny = nt[1] * 2.0f - 1.0f;
+                const float nz = sqrtf(1.0f - (nx * nx + ny * ny));
+                nx *= mat->normalFactorScale; ny *= mat->normalFactorScale;
+                const v3 q = v3norm(v3_(nx, ny, nz));
+                /* mul(normalize(xyz), TBN): row vector times the matrix whose rows are T, B, N */
+                pnrm = v3_(q.x * tRS.x + q.y * bRS.x + q.z * vnrm.x, q.x * tRS.y + q.y * bRS.y + q.z * vnrm.y, q.x * tRS.z + q.y * bRS.z + q.z * vnrm.z);
+            }
+            float rough = mat->roughnessFactor;
+            float metal = mat->metallicFactor >= 1.0f ? 0.0f : mat->metallicFactor;      /* getFallbackMetallic, gltf.h:53-58 */
+            float ao = 1.0f;
+            if (texMR != NULL && o.datas->uv0 != NULL) {
+                float mr[4];
+                oracle_sample_rgba(texMR, smp_lookup(f, mat->metallicRoughnessSampler), mu, mv, mudx, mvdx, mudy, mvdy, mr);
+                rough = mr[1]; metal = mr[2];
+                ao = mat->bExistOcclusion ? mat->occlusionTextureStrength * mr[0] : 1.0f;
+            }
             /* gltfMetallicRoughnessPBR_Lighting (lighting.hlsl:203-268) */
             const v3 f0 = v3_(0.04f, 0.04f, 0.04f);
             v3 diffuseColor = v3s(v3mul(base, v3_(1.0f - f0.x, 1.0f - f0.y, 1.0f - f0.z)), 1.0f - metal);
