@@ -50,7 +50,8 @@ struct ObjectDerived {
 };
 
 // material texture table of the masked raster bucket (chord_textures_upload): alpha channel only, A8 mip chain
-struct TextureDev { const uint8_t* alpha; uint32_t width, height, mipCount, pad; };     // alpha == nullptr: builtin white
+// alpha: A8 chain for the masked raster bucket; rgba: RGBA8 chain for the resolve; both nullptr: builtin white
+struct TextureDev { const uint8_t* alpha; const uint8_t* rgba; uint32_t width, height, mipCount, flags; };
 struct SamplerDev { uint32_t addressU, addressV; };
 
 struct FrameDev {
@@ -221,7 +222,8 @@ struct chord_ctx {
     bool capturing; void** captureAllocs; uint32_t nCaptureAllocs;
     chord_graph_frame_inputs* captureFrames; uint32_t nCaptureFrames;     // chord_frame_begin calls recorded by the capture in flight
     // material textures (masked bucket)
-    chordb::TextureDev* dTextures; chordb::SamplerDev* dSamplers; uint8_t* dTexels; uint32_t nTextures, nSamplers;
+    chordb::TextureDev* dTextures; chordb::SamplerDev* dSamplers; uint8_t* dTexels; uint8_t* dTexelsRgba; uint32_t nTextures, nSamplers;
+    float* dSrgbLut;                    // 256 floats, sRGB byte -> linear (CHORD_TEXTURE_SRGB texel decode in the resolve)
 };
 
 struct chord_cascade_views {

@@ -106,7 +106,7 @@ static void ctx_teardown(chord_ctx* ctx)
     if (ctx->scanBlock) cudaFree(ctx->scanBlock);
     if (ctx->lutTransmittance) cudaFree(ctx->lutTransmittance);
     if (ctx->lutIrradiance) cudaFree(ctx->lutIrradiance);
-    cudaFree(ctx->dTextures); cudaFree(ctx->dSamplers); cudaFree(ctx->dTexels);
+    cudaFree(ctx->dTextures); cudaFree(ctx->dSamplers); cudaFree(ctx->dTexels); cudaFree(ctx->dTexelsRgba); cudaFree(ctx->dSrgbLut);
     if (ctx->uploadStream) { cudaStreamSynchronize(ctx->uploadStream); cudaStreamDestroy(ctx->uploadStream); }
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     free(ctx);
@@ -138,11 +138,17 @@ int chord_ctx_create(int device, chord_ctx** out)
     c->device = device;
     c->refs = 1;                                                   // the owner's reference, dropped by chord_ctx_destroy
     c->switchFlags = 0b111;
-    { static int nextSlot = 0; c->lightingSlot = (uint32_t)(__atomic_fetch_add(&nextSlot, 1, __ATOMIC_RELAXED) & 7); }
+    { static int nextSlot = 0; c->lightingSlot = (uint32_t)(__atomic_fetch_add(&nextSlot, 1, __ATOMIC_RELAXED) & 3); }
     c->rasterVariant = 11; c->rasterCtasPerSm = 0; c->rasterWarpMin = 16384u;
     c->smCount = prop.multiProcessorCount;
     const int rc = [&]() -> int {
         CHORD_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        // sRGB byte -> linear float (IEC 61966-2-1), the texel decode a *_SRGB image format performs; double precision on the
+        // host, rounded once (the oracle builds the identical table)
+        float lut[256];
+        for (int i = 0; i < 256; i++) { const double v = (double)i / 255.0; lut[i] = (float)(v <= 0.04045 ? v / 12.92 : pow((v + 0.055) / 1.055, 2.4)); }
+        CHORD_CUDA(cudaMalloc(&c->dSrgbLut, sizeof(lut)));
+        CHORD_CUDA(cudaMemcpy(c->dSrgbLut, lut, sizeof(lut), cudaMemcpyHostToDevice));
         return CHORD_OK;
     }();
     if (rc != CHORD_OK) { chord_ctx_destroy(c); return rc; }      // nothing half-built survives a failed create
@@ -896,33 +902,38 @@ int chord_textures_upload(chord_ctx* ctx, const chord_texture_desc* textures, ui
     CHORD_REQUIRE(samplerCount == 0 || samplers, "samplers");
     CHORD_CUDA(cudaSetDevice(ctx->device));
     CHORD_CUDA(cudaStreamSynchronize(ctx->stream));
-    cudaFree(ctx->dTextures); cudaFree(ctx->dSamplers); cudaFree(ctx->dTexels);
-    ctx->dTextures = nullptr; ctx->dSamplers = nullptr; ctx->dTexels = nullptr; ctx->nTextures = ctx->nSamplers = 0;
+    cudaFree(ctx->dTextures); cudaFree(ctx->dSamplers); cudaFree(ctx->dTexels); cudaFree(ctx->dTexelsRgba);
+    ctx->dTextures = nullptr; ctx->dSamplers = nullptr; ctx->dTexels = nullptr; ctx->dTexelsRgba = nullptr; ctx->nTextures = ctx->nSamplers = 0;
     if (textureCount == 0) return CHORD_OK;
-    // keep the alpha channel only (the raster path reads nothing else): one A8 mip chain per texture, 16-byte aligned
+    // two copies per texture, each one mip chain, 16-byte aligned: the alpha channel alone (all the raster path reads: one byte
+    // per texel) and the RGBA8 texels (resolve: base colour / normal map / occlusion-roughness-metallic)
     std::vector<TextureDev> table(textureCount);
     std::vector<size_t> offset(textureCount, 0);
     size_t total = 0;
     for (uint32_t i = 0; i < textureCount; i++) {
         const chord_texture_desc& t = textures[i];
-        table[i] = TextureDev{nullptr, t.width, t.height, t.mipCount, 0u};
+        table[i] = TextureDev{nullptr, nullptr, t.width, t.height, t.mipCount, t.flags};
         if (!t.rgba8) continue;
         CHORD_REQUIRE(t.width >= 1 && t.height >= 1 && t.width <= 16384 && t.height <= 16384 && t.mipCount >= 1 && t.mipCount <= 15, "texture dimensions / mip count");
+        CHORD_REQUIRE((t.flags & ~(uint32_t)CHORD_TEXTURE_SRGB) == 0u, "texture flags");
         size_t texels = 0; uint32_t w = t.width, h = t.height;
         for (uint32_t l = 0; l < t.mipCount; l++) { texels += (size_t)w * h; w = w > 1 ? w >> 1 : 1; h = h > 1 ? h >> 1 : 1; }
         offset[i] = total; total += (texels + 15) & ~(size_t)15;
     }
-    std::vector<uint8_t> alpha(total + 16, 0);
+    std::vector<uint8_t> alpha(total + 16, 0), rgba(4 * total + 64, 0);
     for (uint32_t i = 0; i < textureCount; i++) {
         const chord_texture_desc& t = textures[i];
         if (!t.rgba8) continue;
         size_t texels = 0; uint32_t w = t.width, h = t.height;
         for (uint32_t l = 0; l < t.mipCount; l++) { texels += (size_t)w * h; w = w > 1 ? w >> 1 : 1; h = h > 1 ? h >> 1 : 1; }
         for (size_t k = 0; k < texels; k++) alpha[offset[i] + k] = t.rgba8[4 * k + 3];
+        memcpy(rgba.data() + 4 * offset[i], t.rgba8, 4 * texels);
     }
     CHORD_CUDA(cudaMalloc(&ctx->dTexels, alpha.size()));
     CHORD_CUDA(cudaMemcpy(ctx->dTexels, alpha.data(), alpha.size(), cudaMemcpyHostToDevice));
-    for (uint32_t i = 0; i < textureCount; i++) if (textures[i].rgba8) table[i].alpha = ctx->dTexels + offset[i];
+    CHORD_CUDA(cudaMalloc(&ctx->dTexelsRgba, rgba.size()));
+    CHORD_CUDA(cudaMemcpy(ctx->dTexelsRgba, rgba.data(), rgba.size(), cudaMemcpyHostToDevice));
+    for (uint32_t i = 0; i < textureCount; i++) if (textures[i].rgba8) { table[i].alpha = ctx->dTexels + offset[i]; table[i].rgba = ctx->dTexelsRgba + 4 * offset[i]; }
     CHORD_CUDA(cudaMalloc(&ctx->dTextures, sizeof(TextureDev) * textureCount));
     CHORD_CUDA(cudaMemcpy(ctx->dTextures, table.data(), sizeof(TextureDev) * textureCount, cudaMemcpyHostToDevice));
     if (samplerCount) {

@@ -690,3 +690,40 @@ def masked_scene(width=512, height=384, seed=11, n_random=24):
                                     camera, int(rng.integers(0, 2)), int(rng.integers(0, len(mats)))))
     objects = np.array(objs)
     return scene, camera, objects
+
+
+def textured_scene(width=512, height=384, seed=12, n_random=30):
+    """a11 test scene (material.hlsli:30-154 with textures): the patch instances of ``masked_scene`` drawn OPAQUE with textured
+    PBR materials - sRGB base colour maps (all mip levels, three address-mode pairs), a tangent-space normal map with a normal
+    scale, an occlusion / roughness / metallic map with and without occlusion - next to untextured ones."""
+    scene, camera, objects = masked_scene(width, height, seed, n_random=n_random)
+    rng = np.random.default_rng(seed + 100)
+    texs = alpha_test_textures(seed)                      # [None (builtin white), leaf 64x64, link 128x32, checker 16x16], random RGB
+    yy, xx = np.mgrid[0:64, 0:64]
+    nx = 0.55 * np.sin(xx * (2 * math.pi / 16.0)) * np.cos(yy * (2 * math.pi / 32.0))
+    ny = 0.55 * np.cos(xx * (2 * math.pi / 64.0)) * np.sin(yy * (2 * math.pi / 8.0))
+    nmap = np.zeros((64, 64, 4), dtype=np.uint8)
+    nmap[..., 0] = np.rint((nx * 0.5 + 0.5) * 255.0); nmap[..., 1] = np.rint((ny * 0.5 + 0.5) * 255.0); nmap[..., 2] = 255; nmap[..., 3] = 255
+    yy, xx = np.mgrid[0:32, 0:32]
+    mr = np.zeros((32, 32, 4), dtype=np.uint8)
+    mr[..., 0] = 120 + (xx * 4) % 130                       # occlusion
+    mr[..., 1] = rng.integers(30, 250, (32, 32))            # roughness
+    mr[..., 2] = ((xx // 4 + yy // 4) % 2) * 255            # metallic checker
+    mr[..., 3] = 255
+    texs = texs + [abi.box_mip_chain(nmap), abi.box_mip_chain(mr)]          # ids 4, 5
+    scene.textures = abi.TextureTable(texs, samplers=((abi.ADDRESS_REPEAT, abi.ADDRESS_REPEAT),
+                                                      (abi.ADDRESS_CLAMP_TO_EDGE, abi.ADDRESS_MIRRORED_REPEAT),
+                                                      (abi.ADDRESS_MIRRORED_REPEAT, abi.ADDRESS_CLAMP_TO_EDGE)), srgb=(1, 2, 3))
+    mats = scene.materials
+    for i in range(len(mats)):
+        m = mats[i]
+        m['alphaMode'], m['bTwoSided'] = 0, i % 2
+        m['baseColorFactor'] = (0.9, 0.8 + 0.02 * i, 0.7, 1.0)
+        v = i % 5
+        m['baseColorId'], m['baseColorSampler'] = (0 if v == 4 else 1 + i % 3), i % 3
+        m['normalTexture'], m['normalSampler'] = (4 if v in (1, 2) else abi.UNVALID_ID), (i + 1) % 3
+        m['normalFactorScale'] = 0.7 if v == 1 else 1.3
+        m['metallicRoughnessTexture'], m['metallicRoughnessSampler'] = (5 if v in (2, 3) else abi.UNVALID_ID), (i + 2) % 3
+        m['bExistOcclusion'], m['occlusionTextureStrength'] = (1 if v == 2 else 0), 0.8
+        m['roughnessFactor'], m['metallicFactor'] = 0.3 + 0.05 * i, 0.1 * (i % 4)
+    return scene, camera, objects

@@ -132,3 +132,11 @@ def case_tall_frame(w=64, h=4096):
     view = cam.fill_view(camera)
     return dict(name='tall_frame', scene=scene, view=view, iview=cam.fill_instance_view(view), objects=objects, w=w, h=h,
                 lod0=2, groups=1, cmds=cmds)
+
+
+def case_textured(w=512, h=384, seed=12):
+    """SURVEY 8 row a11 widened: textured PBR materials in the resolve (chord_b200/synth.py::textured_scene)."""
+    scene, camera, objects = synth.textured_scene(w, h, seed)
+    view = cam.fill_view(camera)
+    return dict(name='textured', scene=scene, view=view, iview=cam.fill_instance_view(view), objects=objects, w=w, h=h,
+                lod0=len(objects), groups=len(objects), camera=camera)

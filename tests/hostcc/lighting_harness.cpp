@@ -5,6 +5,7 @@
 // host run does and does not prove.
 #include "common.cuh"
 
+#include <cmath>
 #include <vector>
 
 namespace chordb { void set_error(const char*, ...) {} }
@@ -63,12 +64,14 @@ extern "C" int hostcc_lighting(const chord_scene_desc* desc, const chord_Perfram
 
     fill_lighting_consts(*view, c_lightingView[0]);          // the constant-bank slot the launcher fills with a device-to-device copy
     LightingTargets lc;
-    lc.slot = 0;
+    static float srgb[256];
+    for (int i = 0; i < 256; i++) { const double v = (double)i / 255.0; srgb[i] = (float)(v <= 0.04045 ? v / 12.92 : pow((v + 0.055) / 1.055, 2.4)); }
+    lc.srgbLut = srgb;
     lc.trLut = (const __half*)trLut; lc.irLut = (const __half*)irLut;
     for (int i = 0; i < CHORD_GBUF_COUNT; i++) { lc.planes[i] = packed ? nullptr : (float*)planes[i]; lc.packed[i] = packed ? planes[i] : nullptr; }
     const unsigned grid = (tileCount + 3) / 4;
-    if (packed) run_grid(grid, 64, [&] { k_lighting<true>(f, lc, recs.data(), tileList.data(), &tileCount, &nPost, nPost); });
-    else        run_grid(grid, 64, [&] { k_lighting<false>(f, lc, recs.data(), tileList.data(), &tileCount, &nPost, nPost); });
+    if (packed) run_grid(grid, 64, [&] { k_lighting<true, 0>(f, lc, recs.data(), tileList.data(), &tileCount, &nPost, nPost); });
+    else        run_grid(grid, 64, [&] { k_lighting<false, 0>(f, lc, recs.data(), tileList.data(), &tileCount, &nPost, nPost); });
     return 0;
 }
 

@@ -30,7 +30,8 @@ def hostlib(tmp_path_factory):
     d = tmp_path_factory.mktemp('hostcc')
     src = open(os.path.join(ROOT, 'chord_b200', 'csrc', 'resolve.cu')).read()
     src, n = re.subn(r'^int launch_\w+\([^)]*\)\n\{.*?^\}\n', '', src, flags=re.S | re.M)
-    assert n == 2 and '<<<' not in src, 'expected to cut exactly the two launchers out of resolve.cu'
+    src, n2 = re.subn(r'^template <bool kPacked, int kSlot>\nstatic void lighting_launch\([^)]*\)\n\{.*?^\}\n', '', src, flags=re.S | re.M)
+    assert n == 2 and n2 == 1 and '<<<' not in src, 'expected to cut exactly the launchers out of resolve.cu'
     src = src.replace('#include "common.cuh"', '')
     open(d / 'resolve_device.inc', 'w').write(src)
     so = str(d / 'libhostcc_resolve.so')
@@ -63,11 +64,10 @@ def _host_lighting(lib, scene, f, w, h, vis64, post, tr, ir, packed):
     return planes
 
 
-# sha256 over the six fp32 planes + the six packed planes of the host run, per frame, as produced by the kernel text of
-# commit 42ed6d7 (the one timed at 406 us on the B200): the rewrites since then (triangle-cache hoist, constant-bank uniforms,
-# div_uniform, vector loads) are claimed to be bit-identical transformations, and on the host they are.  A deliberate change
-# of the kernel's arithmetic has to re-baseline these (and say so).
-HOST_RUN_SHA256 = ['3d6a0eaf2dd282141e37642a854b520f7dab08a3447d179fba3bcc460f098847', '3e23ee9208eb3cf979de8e08f5684c8d71da631a87523792b7d9e178ea11a3ba']
+# sha256 over the six fp32 planes + the six packed planes of the host run, per frame.  Round 2 re-baselined them: k_lighting now
+# restates the oracle operation for operation (every fp32 plane equals the oracle's), so these digests are the ORACLE's bits plus
+# their quantisation into the reference's storage formats.  A deliberate change of the contract has to re-baseline them (and say so).
+HOST_RUN_SHA256 = ['61b4e51d50551a3b2f463b95b700d010f103f2cca225de02853c4172a007c572', '472bf8312b0457f28d50ec41cf1aa39cc1a0514c21969388f7d549149b91f431']
 
 
 def test_lighting_kernel_source_matches_oracle(hostlib):
@@ -84,20 +84,11 @@ def test_lighting_kernel_source_matches_oracle(hostlib):
         g = oracle.lighting(ref['frame'], ref['vis64'], ref['post_cull'], tr, ir)
         got = _host_lighting(hostlib, scene, f, w, h, ref['vis64'], ref['post_cull'], tr, ir, packed=False)
         names = ['color', 'baseColor', 'vertexNormal', 'pixelNormal', 'motion', 'aoRoughMetal']
+        # round 2: the kernel is the oracle's arithmetic operation for operation -> every plane EQUAL (round 1: fused / fast
+        # normalisations, colour within 1.5e-7 relative and single pixels up to 3.5e-5 at GGX peaks)
         for i, name in enumerate(names):
-            err = np.abs(got[i] - g[i])
-            tol = 1e-5 + 1e-5 * np.abs(g[i])
-            assert (err <= tol).all(), f'{name}: max err {err.max()} at {np.unravel_index(err.argmax(), err.shape)}'
-            assert np.array_equal(got[i].any(axis=-1), g[i].any(axis=-1)), f'{name}: coverage differs'
+            assert np.array_equal(got[i], g[i], equal_nan=True), f'{name}: max |difference| {np.nanmax(np.abs(got[i] - g[i]))}'
         assert g[0].max() > 0.05
-        # ao / roughness / metallic are copies: exact.  Base colour differs by the fused sRGB -> AP1 matrix rows only.
-        assert np.array_equal(got[5], g[5])
-        assert np.abs(got[1] - g[1]).max() <= 1.2e-7
-        print('max abs err per plane:', [float(np.abs(got[i] - g[i]).max()) for i in range(6)])
-        # colour: the ill-conditioned chain is IEEE on both sides; what differs is fused vs separate rounding in the
-        # well-conditioned BRDF part (1e-7 relative)
-        rel = np.abs(got[0] - g[0]) / np.maximum(np.abs(g[0]), 1e-3)
-        assert rel.max() < 5e-6, rel.max()
         prev = ref['hzb']
 
         # packed storage formats: same checks as test_lighting_packed_formats
