@@ -40,7 +40,23 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+BUILDER_SRC = os.path.join(CSRC, 'nanite_builder.cpp')
+BUILDER_OUT = os.path.join(HERE, 'libchord_builder.so')
+
+
+def build_builder(force=False):
+    """chord_b200/libchord_builder.so: the meshlet-DAG builder's C++ core (host only, g++ -O2 -fopenmp; an asset-import tool, not
+    part of the per-frame library)."""
+    deps = [BUILDER_SRC, os.path.join(HERE, '..', 'include', 'chord_abi_types.h')]
+    if not force and os.path.exists(BUILDER_OUT) and all(os.path.getmtime(d) <= os.path.getmtime(BUILDER_OUT) for d in deps):
+        return BUILDER_OUT
+    cxx = '/usr/bin/g++' if os.path.exists('/usr/bin/g++') else 'g++'
+    subprocess.check_call([cxx, '-O2', '-std=c++17', '-fPIC', '-shared', '-fopenmp', '-Wall', '-Wno-misleading-indentation', '-o', BUILDER_OUT, BUILDER_SRC])
+    return BUILDER_OUT
+
+
 def build(force=False, verbose=False, extra=()):
+    build_builder(force)
     if not force and not needs_build():
         return OUT
     objs = []

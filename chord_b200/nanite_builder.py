@@ -376,6 +376,93 @@ def build(positions, triangles, normals=None, uv0=None, max_lods=MAX_LODS):
                 lods=int(recs['lod'].max()) + 1)
 
 
+_native = None
+
+
+def _native_lib():
+    """chord_b200/libchord_builder.so (chord_b200/csrc/nanite_builder.cpp, built by chord_b200/build.py)."""
+    global _native
+    if _native is None:
+        import ctypes as C
+        import os
+        from . import build as _build
+        L = C.CDLL(_build.build_builder())
+        for n in ('chord_builder_meshlet_count', 'chord_builder_data_count', 'chord_builder_lod_count'):
+            getattr(L, n).restype = C.c_uint32
+        L.chord_builder_free.restype = None
+        _native = L
+    return _native
+
+
+def build_native(positions, triangles, normals=None, uv0=None, max_lods=MAX_LODS):
+    """Same result layout as ``build`` with the hot loops (meshlet clustering, grouping, quadric simplification, cones, packing)
+    in C++ (chord_b200/csrc/nanite_builder.cpp): millions of triangles in minutes.  Cluster groups and the BVH are formed here
+    from the per-meshlet (error, centre, parent error, parent centre) the native core returns."""
+    import ctypes as C
+    L = _native_lib()
+    pos = np.ascontiguousarray(positions, dtype=np.float32)
+    idx = np.ascontiguousarray(triangles, dtype=np.uint32).reshape(-1, 3)
+    h = C.c_void_p()
+    rc = L.chord_builder_build(C.c_void_p(pos.ctypes.data), C.c_uint32(len(pos)), C.c_void_p(idx.ctypes.data), C.c_uint32(len(idx)), C.c_uint32(max_lods), C.byref(h))
+    if rc != 0:
+        raise ValueError('chord_builder_build: bad input (index out of range / empty mesh)')
+    try:
+        nm, nd, nl = L.chord_builder_meshlet_count(h), L.chord_builder_data_count(h), L.chord_builder_lod_count(h)
+        recs = np.zeros(nm, dtype=abi.GPUGLTFMeshlet)
+        data = np.zeros(nd, dtype=np.uint32)
+        err, perr = np.zeros(nm, dtype=np.float32), np.zeros(nm, dtype=np.float32)
+        cen, pcen = np.zeros((nm, 3), dtype=np.float32), np.zeros((nm, 3), dtype=np.float32)
+        lm, lt = np.zeros(nl, dtype=np.uint32), np.zeros(nl, dtype=np.uint32)
+        p = lambda a: C.c_void_p(a.ctypes.data)
+        L.chord_builder_copy(h, p(recs), p(data), p(err), p(cen), p(perr), p(pcen), p(lm), p(lt))
+    finally:
+        L.chord_builder_free(h)
+    if normals is None:
+        nacc = np.zeros_like(pos, dtype=np.float64)
+        t64 = idx.astype(np.int64)
+        fn = np.cross(pos[t64[:, 1]] - pos[t64[:, 0]], pos[t64[:, 2]] - pos[t64[:, 0]])
+        for k in range(3):
+            np.add.at(nacc, t64[:, k], fn)
+        normals = (nacc / np.maximum(np.linalg.norm(nacc, axis=1, keepdims=True), 1e-30)).astype(np.float32)
+    if uv0 is None:
+        uv0 = np.zeros((len(pos), 2), dtype=np.float32)
+    # ---- cluster groups: meshlets sharing own + parent spheres, <= 4 each (nanite_builder.cpp:330-395), vectorised: sort by key
+    key = np.concatenate([err.view(np.uint32)[:, None], cen.view(np.uint32), perr.view(np.uint32)[:, None], pcen.view(np.uint32)], axis=1)
+    order = np.lexsort(key.T[::-1])
+    sk = key[order]
+    new = np.ones(nm, dtype=bool)
+    new[1:] = (sk[1:] != sk[:-1]).any(axis=1)
+    run_id = np.cumsum(new) - 1
+    pos_in_run = np.arange(nm) - np.maximum.accumulate(np.where(new, np.arange(nm), 0))
+    gid_sorted = run_id * 0
+    # split runs into chunks of 4
+    chunk = pos_in_run // abi.CLUSTER_GROUP_MERGE_MAX
+    gkey = np.stack([run_id, chunk], axis=1)
+    gnew = np.ones(nm, dtype=bool)
+    gnew[1:] = (gkey[1:] != gkey[:-1]).any(axis=1)
+    gid_sorted = np.cumsum(gnew) - 1
+    ng = int(gid_sorted[-1]) + 1 if nm else 0
+    first = np.nonzero(gnew)[0]
+    groups = np.zeros(ng, dtype=abi.GPUGLTFMeshletGroup)
+    rep = order[first]
+    groups['clusterPosCenter'], groups['error'] = cen[rep], err[rep]
+    groups['parentPosCenter'], groups['parentError'] = pcen[rep], perr[rep]
+    groups['meshletOffset'] = first
+    groups['meshletCount'] = np.diff(np.append(first, nm))
+    gidx = order.astype(np.uint32)
+    groups, gidx, nodes = build_bvh(groups, gidx)
+    prim = np.zeros(1, dtype=abi.GLTFPrimitiveBuffer)
+    prim['posMin'], prim['posMax'], prim['posAverage'] = pos.min(axis=0), pos.max(axis=0), pos.mean(axis=0)
+    prim['vertexCount'], prim['meshletGroupCount'] = len(pos), len(groups)
+    tang = np.tile(np.array([1, 0, 0, 1], dtype=np.float32), (len(pos), 1))
+    datas = dict(meshlets=recs, positions=pos, normals=normals, uv0=uv0, tangents=tang, meshletData=data,
+                 groups=groups, groupIndices=gidx, bvhNodes=nodes)
+    lod0 = int((recs['lod'] == 0).sum())
+    stats = [(i, int(lm[i]), int(lt[i])) for i in range(nl)]
+    return dict(datas=datas, primitive=prim, lod0MeshletCount=lod0, meshletGroupCount=len(groups), lod_stats=stats,
+                lods=int(recs['lod'].max()) + 1 if nm else 0)
+
+
 def host_scene(asset, materials=None):
     return abi.HostScene([asset['datas']], asset['primitive'], np.array(materials if materials is not None else [default_material()]))
 

@@ -1089,7 +1089,10 @@ static inline v3 v3sub(v3 a, v3 b) { return v3_(a.x - b.x, a.y - b.y, a.z - b.z)
 static inline v3 v3mul(v3 a, v3 b) { return v3_(a.x * b.x, a.y * b.y, a.z * b.z); }
 static inline v3 v3s(v3 a, float s) { return v3_(a.x * s, a.y * s, a.z * s); }
 static inline float v3dot(v3 a, v3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
-static inline v3 v3norm(v3 a) { float l = sqrtf(v3dot(a, a)); return v3_(a.x / l, a.y / l, a.z / l); }
+/* HLSL normalize() in K11: v * rcp(sqrt(dot(v, v))) - IEEE square root, IEEE reciprocal, three products.
+ * (DXC lowers normalize to GLSL.std.450 Normalize, which drivers implement as v * inversesqrt(dot(v, v)); the reciprocal form is
+ * the faithful one and costs one division instead of three.) */
+static inline v3 v3norm(v3 a) { const float r = 1.0f / sqrtf(v3dot(a, a)); return v3_(a.x * r, a.y * r, a.z * r); }
 static inline float clampf(float v, float lo, float hi) { return fminf(fmaxf(v, lo), hi); }
 
 static void srgb_to_ap1_matrix(float m[9])

@@ -70,8 +70,8 @@ extern "C" int hostcc_lighting(const chord_scene_desc* desc, const chord_Perfram
     lc.trLut = (const __half*)trLut; lc.irLut = (const __half*)irLut;
     for (int i = 0; i < CHORD_GBUF_COUNT; i++) { lc.planes[i] = packed ? nullptr : (float*)planes[i]; lc.packed[i] = packed ? planes[i] : nullptr; }
     const unsigned grid = (tileCount + 3) / 4;
-    if (packed) run_grid(grid, 64, [&] { k_lighting<true, 0>(f, lc, recs.data(), tileList.data(), &tileCount, &nPost, nPost); });
-    else        run_grid(grid, 64, [&] { k_lighting<false, 0>(f, lc, recs.data(), tileList.data(), &tileCount, &nPost, nPost); });
+    if (packed) run_grid(grid, 64, [&] { k_lighting<true, 0, false>(f, lc, recs.data(), tileList.data(), &tileCount, &nPost, nPost); });
+    else        run_grid(grid, 64, [&] { k_lighting<false, 0, false>(f, lc, recs.data(), tileList.data(), &tileCount, &nPost, nPost); });
     return 0;
 }
 

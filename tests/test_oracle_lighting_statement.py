@@ -34,8 +34,10 @@ def _dot3(a, b):
 
 
 def _normalize(a):
+    """normalize(v) = v * rcp(sqrt(dot(v, v))): IEEE sqrt, IEEE reciprocal, three products."""
     with np.errstate(invalid='ignore', divide='ignore'):
-        return (a / np.sqrt(_dot3(a, a))[..., None]).astype(F)
+        r = (F(1.0) / np.sqrt(_dot3(a, a)).astype(F)).astype(F)
+        return (a * r[..., None]).astype(F)
 
 
 def _mul33(M, v):
