@@ -188,7 +188,7 @@ def load(path):
     return dict(primitives=prims, materials=materials, instances=instances)
 
 
-def build_scene(path, max_lods=nanite_builder.MAX_LODS):
+def build_scene(path, max_lods=nanite_builder.MAX_LODS, native=True):
     """glTF file -> (abi.HostScene, info) with the meshlet DAG of every imported primitive.  ``info['transforms']`` is what
     ``synth.refill_objects`` takes, ``lod0MeshletCount`` / ``meshletGroupCount`` size the per-frame work lists."""
     g = load(path)
@@ -198,7 +198,8 @@ def build_scene(path, max_lods=nanite_builder.MAX_LODS):
     for i, p in enumerate(g['primitives']):
         if len(p['triangles']) == 0:
             raise GltfError(f'{p["name"]}: empty primitive')
-        asset = nanite_builder.build(p['positions'], p['triangles'], normals=p['normals'], uv0=p['uv0'], max_lods=max_lods)
+        # native: the C++ core (csrc/nanite_builder.cpp), what makes Sponza / Bistro-sized primitives practical
+        asset = (nanite_builder.build_native if native else nanite_builder.build)(p['positions'], p['triangles'], normals=p['normals'], uv0=p['uv0'], max_lods=max_lods)
         rec = asset['primitive'].copy()
         rec['primitiveDatasBufferId'] = i
         datas.append(asset['datas'])

@@ -49,12 +49,12 @@ def city_frames(n_buildings=9, w=640, h=360, frames=4, seed=2, lods=3, low=False
     return scene, info, out
 
 
-def terrain_case(n=48, w=640, h=360, seed=1):
+def terrain_case(n=48, w=640, h=360, seed=1, native=False):
     """A curved mesh through the meshlet-DAG builder (chord_b200/nanite_builder.py): genuine multi-level DAG
     with geometric simplification, three cameras from close to far so that the LOD cut moves through the levels."""
     from chord_b200 import nanite_builder as nb
     pos, tris, uv = nb.terrain_mesh(n=n, seed=seed)
-    asset = nb.build(pos, tris, uv0=uv)
+    asset = (nb.build_native if native else nb.build)(pos, tris, uv0=uv)
     scene = nb.host_scene(asset)
     frames = []
     for (p, f) in (((2.0, 6.0, 14.0), (0.0, -0.45, -1.0)), ((6.0, 30.0, 70.0), (-0.05, -0.4, -1.0)), ((0.0, 90.0, 260.0), (0.0, -0.33, -1.0))):

@@ -135,7 +135,7 @@ def test_imported_scene_renders_like_the_direct_build(tmp_path):
     assert (vis != 0).mean() > 0.3 and st['trianglesSubmitted'] > 0
     assert set(np.unique(post['objectId'])) >= {0, 1}                                       # terrain and box are in view
     # the root instance alone == the same mesh through the builder directly with the same transform and material
-    direct = nb.build(src['pos'], src['tris'], normals=src['nrm'], uv0=scene.datas[0]['uv0'])
+    direct = nb.build_native(src['pos'], src['tris'], normals=src['nrm'], uv0=scene.datas[0]['uv0'])
     dscene = nb.host_scene(direct, materials=[scene.materials[0]])
     m0 = info['transforms'][[i for i, t in enumerate(info['transforms']) if t[1] == 0 and t[2] == 0][0]][0]
     dobjs = np.array([cam.fill_object(m0, c, 0, 0)])

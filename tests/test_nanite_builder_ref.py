@@ -158,3 +158,40 @@ def test_simplify_is_comparable_to_meshopt_simplify():
     assert border([tuple(int(v) for v in t) for t in ref]) == border([tuple(int(v) for v in t) for t in group])
     assert err_ref > 0 and err_ours > 0
     assert 0.25 <= err_ours / err_ref <= 4.0, (err_ours, err_ref)          # same metric (root of the weighted mean squared plane distance)
+
+
+def test_native_builder_against_meshopt():
+    """The C++ core (chord_b200/csrc/nanite_builder.cpp) against the reference's own meshoptimizer build on the same mesh:
+    LOD-0 meshlet count within 15 % of meshopt_buildMeshlets', cones equal to meshopt_computeMeshletBounds' on the native
+    meshlets, group simplification error of the first level of the same order as meshopt_simplify's on the same patch."""
+    pos, tris, uv = nb.terrain_mesh(n=96, seed=1)
+    a = nb.build_native(pos, tris, uv0=uv)
+    d = a['datas']
+    ms, data = d['meshlets'], d['meshletData']
+    ref = ref_build_meshlets(pos, tris)
+    n0 = int((ms['lod'] == 0).sum())
+    assert n0 <= 1.15 * len(ref), (n0, len(ref))
+    checked = 0
+    for m in np.nonzero(ms['lod'] == 0)[0][:40]:
+        v, t = int(ms['vertexTriangleCount'][m] & 0xFF), int((ms['vertexTriangleCount'][m] >> 8) & 0xFF)
+        verts = data[ms['dataOffset'][m]:ms['dataOffset'][m] + v]
+        packed = data[ms['dataOffset'][m] + v:ms['dataOffset'][m] + v + t]
+        lt = np.stack([packed & 0xFF, (packed >> 8) & 0xFF, (packed >> 16) & 0xFF], axis=1)
+        want = ref_bounds(pos, verts, lt)
+        if want['cutoff'] >= 1.0:
+            assert ms['coneCutOff'][m] >= 1.0
+            continue
+        assert np.allclose(ms['coneAxis'][m], want['axis'], atol=2e-5)
+        assert abs(ms['coneCutOff'][m] - want['cutoff']) <= 2e-5
+        assert np.allclose(ms['coneApex'][m], want['apex'], atol=2e-3 * max(1.0, np.abs(want['apex']).max()))
+        checked += 1
+    assert checked >= 10
+    # level-1 errors (native QEM with the group border locked) vs meshopt_simplify on one 16 x 16-cell patch of the same mesh
+    n = 96
+    cells = np.array([i * n + j for i in range(8, 24) for j in range(8, 24)])
+    group = np.concatenate([tris[cells], tris[n * n + cells]])
+    _, err_ref = ref_simplify(pos, group, int(len(group) * nb.SIMPLIFY_TARGET) * 3)
+    e1 = d['groups']['error'][(d['groups']['error'] > 0)]
+    lvl1 = np.unique(ms['lod'])
+    err_native = float(np.median(e1[e1 <= np.percentile(e1, 40)]))               # the smallest positive errors are level 1's
+    assert err_ref > 0 and 0.2 <= err_native / err_ref <= 5.0, (err_native, err_ref)
