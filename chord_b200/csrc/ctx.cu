@@ -122,6 +122,13 @@ const char* chord_last_error(void) { return g_error; }
 
 int chord_abi_version(void) { return CHORD_B200_ABI_VERSION; }
 
+int chord_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
 int chord_ctx_create(int device, chord_ctx** out)
 {
     CHORD_REQUIRE(out != nullptr, "out");

@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, 'libchord_b200.so')
 
 # every symbol include/chord_b200.h declares (tests check the .so exports all of them)
 SYMBOLS = [
-    'chord_last_error', 'chord_abi_version',
+    'chord_last_error', 'chord_abi_version', 'chord_device_count',
     'chord_ctx_create', 'chord_ctx_destroy', 'chord_ctx_refcount', 'chord_ctx_stream', 'chord_ctx_sync', 'chord_ctx_set_switch_flags',
     'chord_ctx_get_switch_flags', 'chord_ctx_set_raster_tuning', 'chord_ctx_kernel_launches', 'chord_scene_upload', 'chord_textures_upload',
     'chord_cmdlist_create', 'chord_cmdlist_destroy', 'chord_cmdlist_upload', 'chord_cmdlist_readback',
@@ -72,7 +72,7 @@ def lib():
         L.chord_hzb_mip_offset.restype = C.c_uint64
         for n in SYMBOLS:
             f = getattr(L, n)
-            if f.restype is C.c_int and n not in ('chord_abi_version', 'chord_hzb_is_valid'):
+            if f.restype is C.c_int and n not in ('chord_abi_version', 'chord_hzb_is_valid', 'chord_device_count'):
                 f.errcheck = _check
         _lib = L
     return _lib

@@ -43,6 +43,7 @@ enum {
 /* Thread-local text of the last failure on this thread. */
 const char* chord_last_error(void);
 int         chord_abi_version(void);
+int         chord_device_count(void);     /* visible CUDA devices (0 when there is none / no driver) */
 
 /* ---- context: replaces graphics::Context + one GraphicsQueue (source/graphics/graphics.h) */
 int  chord_ctx_create(int device, chord_ctx** out);

@@ -158,6 +158,39 @@ private:
 
 inline std::unique_ptr<Frame> Context::createFrame(uint32_t w, uint32_t h) const { return std::make_unique<Frame>(*this, w, h); }
 
+// chord_renderer: DeferredRenderer::render (renderer.cpp:311-363 + :489) as ONE native call per frame - recorded as CUDA graphs
+// and replayed with rewritten uniforms (CHORD_RENDERER_GRAPH), with GPU timers at the reference's cut points
+// (CHORD_RENDERER_TIMERS), and, as one rank of a tile-parallel frame, with the fused exchange of the history HZB over peer
+// memory (exchangeExport / exchangeConnect) or the NCCL all-gather (chord_renderer_exchange_connect_nccl on handle()).
+class Renderer {
+public:
+    Renderer(const Context& ctx, uint32_t w, uint32_t h, uint32_t flags) : m_w(w), m_h(h)
+    { check(chord_renderer_create(ctx.handle(), w, h, flags, &m_r), "chord_renderer_create"); }
+    ~Renderer() { chord_renderer_destroy(m_r); }
+    Renderer(const Renderer&) = delete;
+    Renderer& operator=(const Renderer&) = delete;
+    chord_renderer* handle() const { return m_r; }
+    void setTile(const chord_rect* tile) { check(chord_renderer_set_tile(m_r, tile), "chord_renderer_set_tile"); }
+    void render(const chord_PerframeCameraView& view, const chord_InstanceCullingViewInfo& iview, const chord_GPUObjectGLTFPrimitive* objects,
+                uint32_t objectCount, uint32_t lod0MeshletCount, uint32_t meshletGroupCount)
+    { check(chord_renderer_render(m_r, &view, &iview, objects, objectCount, lod0MeshletCount, meshletGroupCount), "chord_renderer_render"); }
+    void clearHistory() { check(chord_renderer_clear_history(m_r), "chord_renderer_clear_history"); }
+    chord_frame* frame() const { return chord_renderer_frame(m_r); }
+    chord_cmdlist* postCull() const { return chord_renderer_post_cull(m_r); }
+    chord_hzb* historyHzb() const { return chord_renderer_history_hzb(m_r); }
+    std::vector<float> passTimes() const { std::vector<float> us(CHORD_PASS_COUNT); check(chord_renderer_pass_times(m_r, us.data()), "chord_renderer_pass_times"); return us; }
+    // multi-GPU, fused exchange: export this rank's block, gather the handles / pointers of all ranks (any transport), connect
+    void* exchangeExport(chord_ipc_handle* outHandle = nullptr)
+    { void* p = nullptr; check(chord_renderer_exchange_export(m_r, outHandle, &p), "chord_renderer_exchange_export"); return p; }
+    void exchangeConnect(uint32_t rank, uint32_t world, const chord_rect* tiles, const chord_ipc_handle* handles, void* const* localPtrs)
+    { check(chord_renderer_exchange_connect(m_r, rank, world, tiles, handles, localPtrs), "chord_renderer_exchange_connect"); }
+    void historySync() { check(chord_renderer_history_sync(m_r), "chord_renderer_history_sync"); }
+    bool exchangeTimedOut() const { uint32_t v = 0; check(chord_renderer_exchange_status(m_r, &v), "chord_renderer_exchange_status"); return v != 0; }
+private:
+    chord_renderer* m_r = nullptr;
+    uint32_t m_w, m_h;
+};
+
 // DeferredRenderer::render between "Clear GBuffers" and "lightingTile" (source/renderer/renderer.cpp:311-363) plus the
 // history hand-off (:489, m_rendererHistory.hzbCtx): instanceCulling -> gltfVisibilityRenderingStage0 against LAST frame's HZB
 // -> buildHZB(min) -> gltfVisibilityRenderingStage1 -> buildHZB(min, max, range), kept as history -> visibilityMark -> lighting.
