@@ -338,6 +338,23 @@ int launch_build_hzb(chord_frame* fr, int bMin, int bMax, int bRange, chord_hzb*
     return CHORD_OK;
 }
 
+// NCCL path: the ranks' {minBits, maxBits} pairs (all-gathered) folded into the chain's valid range
+__global__ void k_hzb_range_reduce(const uint32_t* __restrict__ pairs, uint32_t world, uint32_t* __restrict__ validRange)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    uint32_t lo = ~0u, hi = 0u;
+    for (uint32_t r = 0; r < world; r++) { lo = min(lo, pairs[2 * r]); hi = max(hi, pairs[2 * r + 1]); }
+    validRange[0] = lo; validRange[1] = hi;
+}
+
+int launch_hzb_range_reduce(chord_ctx* ctx, const uint32_t* pairs, uint32_t world, uint32_t* validRange)
+{
+    k_hzb_range_reduce<<<1, 32, 0, ctx->stream>>>(pairs, world, validRange);
+    ctx->launches++;
+    CHORD_CUDA(cudaGetLastError());
+    return CHORD_OK;
+}
+
 int launch_hzb_exchange_wait_top(chord_frame* fr, chord_hzb* dst, const HzbExchange* ex, uint32_t world, uint32_t* status)
 {
     HzbBuildParams p = make_params(fr, 1, 1, 1, dst);

@@ -195,7 +195,11 @@ static int nccl_allgather_history(chord_renderer* r, chord_hzb* h)
         CHORD_NCCL(api, api->allGather(r->sendBuf, r->recvBuf, (size_t)r->slotBytes, /* ncclUint8 */ 1, r->nccl->comm, r->ctx->stream));
         if ((rc = chord_hzb_unpack_tiles(h, which, r->tiles, r->world, r->recvBuf, r->slotBytes))) return rc;
     }
-    // the tiles' valid ranges are not reduced on this path: only the min / max chains are whole-frame afterwards
+    // the tiles' valid depth ranges: one more (8-byte) all-gather, folded on the device
+    CHORD_CUDA(cudaMemcpyAsync(r->sendBuf, h->validRange, 8, cudaMemcpyDeviceToDevice, r->ctx->stream));
+    CHORD_NCCL(api, api->allGather(r->sendBuf, r->recvBuf, 8, /* ncclUint8 */ 1, r->nccl->comm, r->ctx->stream));
+    const int rc = launch_hzb_range_reduce(r->ctx, reinterpret_cast<const uint32_t*>(r->recvBuf), r->world, h->validRange);
+    if (rc) return rc;
     return chord_hzb_finish_top(r->frame, 1, 1, h);
 }
 

@@ -143,8 +143,11 @@ class _DevPtr:
         self.__cuda_array_interface__ = {'shape': (nbytes,), 'typestr': '|u1', 'data': (int(ptr), False), 'version': 2}
 
 
-def allgather_hzb(frame, hzb, rank, world, dist, which=('min',), staging=None):
-    """Exchange the tiles' parts of mips 0..5 of ``hzb`` between all ranks and rebuild mips 6.. everywhere.
+def allgather_hzb(frame, hzb, rank, world, dist, which=('min', 'max'), staging=None):
+    """Exchange the tiles' parts of mips 0..5 of ``hzb`` between all ranks and rebuild mips 6.. everywhere (for callers that
+    sequence the passes themselves through torch.distributed; the renderer-level paths are ``connect_fused`` / ``connect_nccl``).
+    The tiles' valid depth ranges are NOT reduced here: a chain gathered this way must not be used as ``validRangeSource`` of
+    chord_cascade_setup (the fused exchange of chord_renderer does reduce them).
 
     ``dist`` is torch.distributed (NCCL); the collective is enqueued on the library's stream via an ExternalStream so
     that pack -> all-gather -> unpack -> finish_top is stream-ordered without host synchronisation."""
@@ -192,20 +195,20 @@ def connect_nccl(renderer, rank, world, dist, tiles=None):
 
 
 class TileRenderer:
-    """DeferredRenderer for one rank of a tile-parallel frame."""
+    """One rank of a tile-parallel frame: the native renderer (chord_renderer, one C-ABI call per frame) with its history HZB
+    exchanged by the fused peer-store path (``exchange='fused'``, default) or by the NCCL all-gather inside the library
+    (``exchange='nccl'``).  Both leave min chain, max chain and valid range of the history identical to a single-GPU frame on
+    every rank (round 1 gathered the min chain only and left max / valid range rank-local: ADVICE r1)."""
 
-    def __init__(self, ctx, width, height, rank, world, dist):
-        from .renderer import DeferredRenderer
-        self.r = DeferredRenderer(ctx, width, height)
+    def __init__(self, ctx, width, height, rank, world, dist, exchange='fused', resolve=False, packed_gbuffer=False, graph=False):
+        from .runtime import Renderer
+        self.r = Renderer(ctx, width, height, resolve=resolve, packed_gbuffer=packed_gbuffer, graph=graph)
         self.rank, self.world, self.dist = rank, world, dist
         self.tile = tile_for_rank(rank, world, width, height)
-        self._staging = None
+        if world > 1:
+            (connect_fused if exchange == 'fused' else connect_nccl)(self.r, rank, world, dist)
 
-    def render(self, camera, objects, lod0, groups, view=None):
-        if view is None:
-            view = cam.fill_view(camera, last_view=self.r.last_view, frame_counter=self.r.frame_counter)
+    def render(self, camera, objects, lod0, groups, view):
         iview = tile_instance_view(view, camera, self.tile) if self.world > 1 else cam.fill_instance_view(view)
-        post = self.r.render(camera, objects, lod0, groups, tile=self.tile if self.world > 1 else None, view=view, iview=iview)
-        if self.world > 1:
-            self._staging = allgather_hzb(self.r.frame, self.r.history_hzb, self.rank, self.world, self.dist, ('min',), self._staging)
-        return post
+        self.r.render(view, iview, objects, lod0, groups)
+        return self.r.post_cull

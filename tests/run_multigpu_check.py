@@ -28,18 +28,23 @@ def main():
     scene, info, frames = city_frames(n_buildings=16, w=w, h=h, frames=4)
     ctx = runtime.Context(local)
     ctx.upload_scene(scene)
-    tiled = multigpu.TileRenderer(ctx, w, h, rank, world, dist)
+    exchange = sys.argv[1] if len(sys.argv) > 1 else 'fused'
+    tiled = multigpu.TileRenderer(ctx, w, h, rank, world, dist, exchange=exchange)
     single = renderer.DeferredRenderer(ctx, w, h)
     ok = True
     for fi, f in enumerate(frames):
         post_t = tiled.render(f['camera'], f['objects'], info['lod0MeshletCount'], info['meshletGroupCount'], view=f['view'])
         post_s = single.render(f['camera'], f['objects'], info['lod0MeshletCount'], info['meshletGroupCount'], view=f['view'], iview=f['iview'])
+        dist.barrier()
+        tiled.r.history_sync()
         x0, y0, x1, y1 = tiled.tile
         vt, vs = tiled.r.frame.vis64(), single.frame.vis64()
         dt, ds = tiled.r.frame.decoded(post_t), single.frame.decoded(post_s)
         same = np.array_equal(vt[y0:y1, x0:x1] >> np.uint64(32), vs[y0:y1, x0:x1] >> np.uint64(32)) and np.array_equal(dt[y0:y1, x0:x1], ds[y0:y1, x0:x1])
         outside = vt.copy(); outside[y0:y1, x0:x1] = 0
-        hz = np.array_equal(tiled.r.history_hzb.readback_chain('min'), single.history_hzb.readback_chain('min'))
+        ht, hs = tiled.r.history_hzb, single.history_hzb
+        hz = (np.array_equal(ht.readback_chain('min'), hs.readback_chain('min')) and np.array_equal(ht.readback_chain('max'), hs.readback_chain('max'))
+              and np.array_equal(ht.valid_range(), hs.valid_range()))
         print(f'[rank {rank}] frame {fi}: tile {tiled.tile} list {post_t.count()}/{post_s.count()} image_ok={same} outside_clean={not outside.any()} hzb_ok={hz}', flush=True)
         ok &= same and (not outside.any()) and hz
     res = torch.tensor([1 if ok else 0], device=f'cuda:{local}')
