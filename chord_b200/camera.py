@@ -141,6 +141,11 @@ def fill_view(camera, jitter=(0.0, 0.0), last_view=None, frame_counter=0, sun_di
     at['sunSpectralRadianceToLumiance'] = (98242.79, 69954.4, 66475.0)
     at['ground_albedo'] = (0.1, 0.1, 0.1)
     at['mu_s_min'] = -0.2
+    # read by the sky branch only (lighting.hlsl:75-166; Bruneton earth constants in km^-1, manager_atmosphere.cpp:518-544)
+    at['rayleigh_scattering'] = (0.005802, 0.013558, 0.0331)
+    at['mie_scattering'] = (0.003996, 0.003996, 0.003996)
+    at['mie_phase_function_g'] = 0.8
+    at['bCombineScattering'] = 1
     if last_view is None:
         last_view = v
         v['bCameraCut'] = 1

@@ -218,6 +218,7 @@ struct chord_ctx {
     uint32_t* scanTicket;
     // atmosphere LUTs
     __half* lutTransmittance; __half* lutIrradiance;
+    __half* lutScattering; __half* lutSingleMie;      // 256 x 128 x 32 RGBA16F volumes of the sky branch (null: no sky branch)
     // graph capture (chord_graph_begin_capture .. end_capture): pinned snapshots made while capturing
     bool capturing; void** captureAllocs; uint32_t nCaptureAllocs;
     chord_graph_frame_inputs* captureFrames; uint32_t nCaptureFrames;     // chord_frame_begin calls recorded by the capture in flight

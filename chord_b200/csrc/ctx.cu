@@ -106,6 +106,7 @@ static void ctx_teardown(chord_ctx* ctx)
     if (ctx->scanBlock) cudaFree(ctx->scanBlock);
     if (ctx->lutTransmittance) cudaFree(ctx->lutTransmittance);
     if (ctx->lutIrradiance) cudaFree(ctx->lutIrradiance);
+    cudaFree(ctx->lutScattering); cudaFree(ctx->lutSingleMie);
     cudaFree(ctx->dTextures); cudaFree(ctx->dSamplers); cudaFree(ctx->dTexels); cudaFree(ctx->dTexelsRgba); cudaFree(ctx->dSrgbLut);
     if (ctx->uploadStream) { cudaStreamSynchronize(ctx->uploadStream); cudaStreamDestroy(ctx->uploadStream); }
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -727,6 +728,27 @@ int chord_atmosphere_luts_upload(chord_ctx* ctx, const chord_atmosphere_luts* lu
     if (!ctx->lutIrradiance) CHORD_CUDA(cudaMalloc(&ctx->lutIrradiance, 64 * 16 * 4 * sizeof(__half)));
     CHORD_CUDA(cudaMemcpyAsync(ctx->lutTransmittance, luts->transmittance, 256 * 64 * 4 * sizeof(__half), cudaMemcpyHostToDevice, ctx->stream));
     CHORD_CUDA(cudaMemcpyAsync(ctx->lutIrradiance, luts->irradiance, 64 * 16 * 4 * sizeof(__half), cudaMemcpyHostToDevice, ctx->stream));
+    CHORD_CUDA(cudaStreamSynchronize(ctx->stream));
+    return CHORD_OK;
+}
+
+int chord_atmosphere_scattering_upload(chord_ctx* ctx, const uint16_t* scattering, const uint16_t* singleMie)
+{
+    CHORD_REQUIRE(ctx, "null");
+    CHORD_REQUIRE(!ctx->capturing, "LUT uploads are invalid while capturing");
+    CHORD_CUDA(cudaSetDevice(ctx->device));
+    constexpr size_t kBytes = (size_t)256 * 128 * 32 * 4 * sizeof(__half);
+    CHORD_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (!scattering) {                                   // removes the sky branch from chord_lighting
+        cudaFree(ctx->lutScattering); cudaFree(ctx->lutSingleMie); ctx->lutScattering = nullptr; ctx->lutSingleMie = nullptr;
+        return CHORD_OK;
+    }
+    if (!ctx->lutScattering) CHORD_CUDA(cudaMalloc(&ctx->lutScattering, kBytes));
+    CHORD_CUDA(cudaMemcpyAsync(ctx->lutScattering, scattering, kBytes, cudaMemcpyHostToDevice, ctx->stream));
+    if (singleMie) {
+        if (!ctx->lutSingleMie) CHORD_CUDA(cudaMalloc(&ctx->lutSingleMie, kBytes));
+        CHORD_CUDA(cudaMemcpyAsync(ctx->lutSingleMie, singleMie, kBytes, cudaMemcpyHostToDevice, ctx->stream));
+    } else { cudaFree(ctx->lutSingleMie); ctx->lutSingleMie = nullptr; }
     CHORD_CUDA(cudaStreamSynchronize(ctx->stream));
     return CHORD_OK;
 }

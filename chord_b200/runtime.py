@@ -23,7 +23,7 @@ SYMBOLS = [
     'chord_frame_create', 'chord_frame_destroy', 'chord_frame_begin', 'chord_instance_culling', 'chord_instance_culling_bvh',
     'chord_readback_bvh_candidates', 'chord_hzb_culling',
     'chord_render_mesh', 'chord_render_mesh_depth', 'chord_hzb_culling_generic', 'chord_visibility_stage0', 'chord_visibility_stage1', 'chord_build_hzb',
-    'chord_visibility_mark', 'chord_atmosphere_luts_upload', 'chord_lighting',
+    'chord_visibility_mark', 'chord_atmosphere_luts_upload', 'chord_atmosphere_scattering_upload', 'chord_lighting',
     'chord_readback_vis64', 'chord_readback_visibility32', 'chord_readback_depth32', 'chord_readback_decoded',
     'chord_readback_tile_marker', 'chord_readback_gbuffer_f32', 'chord_frame_set_gbuffer_packed', 'chord_readback_gbuffer_packed', 'chord_frame_vis64_ptr', 'chord_frame_dims',
     'chord_frame_raster_stats', 'chord_frame_reset_stats', 'chord_frame_set_queue_limits',
@@ -153,6 +153,17 @@ class Context:
         assert t.shape == (64, 256, 4) and i.shape == (16, 64, 4)
         luts = abi.AtmosphereLuts(t.ctypes.data, i.ctypes.data)
         lib().chord_atmosphere_luts_upload(self.h, C.byref(luts))
+
+    def upload_scattering(self, scattering, single_mie=None):
+        """Scattering volumes of the sky branch, (32, 128, 256, 4) float16 each; ``scattering=None`` removes the branch."""
+        if scattering is None:
+            lib().chord_atmosphere_scattering_upload(self.h, None, None)
+            return
+        s = np.ascontiguousarray(scattering, dtype=np.float16)
+        assert s.shape == (32, 128, 256, 4)
+        m = np.ascontiguousarray(single_mie, dtype=np.float16) if single_mie is not None else None
+        assert m is None or m.shape == s.shape
+        lib().chord_atmosphere_scattering_upload(self.h, C.c_void_p(s.ctypes.data), C.c_void_p(m.ctypes.data) if m is not None else None)
 
 
 class CascadeViews:

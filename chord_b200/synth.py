@@ -579,6 +579,20 @@ def synthetic_luts(seed=7):
     return np.ascontiguousarray(tr), np.ascontiguousarray(ir)
 
 
+def synthetic_scattering_luts(seed=8):
+    """Seeded stand-ins for the Bruneton scattering (combined: rgb = Rayleigh + multiple scattering, a = single Mie red) and
+    single-Mie 4-D LUTs packed as 256 x 128 x 32 RGBA16F volumes (atmosphere.hlsli:43-49): smooth, positive, with structure in
+    every texture dimension so that a wrong coordinate shows."""
+    rng = np.random.default_rng(seed)
+    x = np.linspace(0, 1, 256)[None, None, :, None]
+    y = np.linspace(0, 1, 128)[None, :, None, None]
+    z = np.linspace(0, 1, 32)[:, None, None, None]
+    base = 0.02 + 0.3 * (0.5 + 0.5 * np.sin(6.0 * x + 2.0 * y)) * (0.3 + 0.7 * y) * (1.0 - 0.6 * z) + 0.01 * rng.random((32, 128, 256, 1))
+    sc = np.concatenate([base * np.array([0.35, 0.6, 1.0]), 0.05 + 0.2 * (1.0 - y) * (0.5 + 0.5 * np.cos(9.0 * x)) * np.ones((32, 1, 1, 1))], axis=-1)
+    mie = np.concatenate([(0.03 + 0.15 * (1.0 - y) * (0.5 + 0.5 * np.cos(5.0 * x + z))) * np.array([1.0, 0.95, 0.9]) * np.ones((32, 1, 1, 1)), np.ones((32, 128, 256, 1))], axis=-1)
+    return np.ascontiguousarray(sc.astype(np.float16)), np.ascontiguousarray(mie.astype(np.float16))
+
+
 # ----------------------------------------------------------------------------------------------- masked bucket (N2)
 def alpha_test_textures(seed=7):
     """Procedural RGBA8 alpha-test textures with full box-filtered mip chains: [None (builtin white), 64x64 leaf blobs,

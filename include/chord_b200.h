@@ -281,6 +281,14 @@ typedef struct {
     const uint16_t* irradiance;      /* RGBA16F, 64 x 16, host pointer */
 } chord_atmosphere_luts;
 int chord_atmosphere_luts_upload(chord_ctx* ctx, const chord_atmosphere_luts* luts);
+/* The sky branch of the same pass (LIGHTING_TYPE == None: lighting.hlsl:75-166 skyColorEvaluate, the {None, PBR} loop of
+ * lighting.cpp:193-246): once the scattering volumes are uploaded, chord_lighting also writes the sky colour into every texel
+ * of the tile rect that holds no geometry (colour plane only).  scattering / singleMie: RGBA16F, 256 x 128 x 32 (x = nu * 32 +
+ * mu_s, y = mu, z = r; atmosphere.hlsli:43-49), host pointers.  singleMie is read only when atmosphere.bCombineScattering == 0
+ * (lighting.hlsl:84) and may be NULL otherwise; NULL with bCombineScattering == 0 - a state the reference leaves undefined
+ * (its push constant stays bindless id 0, lighting.cpp:230-233) - makes the scattering volume stand in.  scattering == NULL
+ * removes the branch again (unshaded texels keep the addClearGbufferPass value). */
+int chord_atmosphere_scattering_upload(chord_ctx* ctx, const uint16_t* scattering, const uint16_t* singleMie);
 int chord_lighting(chord_frame* frame, chord_cmdlist* postInstanceCull);
 
 /* ---- read-backs (synchronise the stream) */

@@ -248,6 +248,21 @@ def lighting(frame, vis64, post_cull, transmittance, irradiance):
     return out
 
 
+def sky(frame, vis64, transmittance, irradiance, scattering, single_mie=None, color=None):
+    """The sky branch of the lighting pass (LIGHTING_TYPE == None, lighting.hlsl:75-166) on the CPU: writes the colour plane's
+    texels that hold no geometry.  ``scattering`` (32, 128, 256, 4) float16; ``single_mie`` same shape or None (combined)."""
+    tr = np.ascontiguousarray(transmittance, dtype=np.float16)
+    ir = np.ascontiguousarray(irradiance, dtype=np.float16)
+    sc = np.ascontiguousarray(scattering, dtype=np.float16)
+    assert sc.shape == (32, 128, 256, 4)
+    mie = np.ascontiguousarray(single_mie, dtype=np.float16) if single_mie is not None else None
+    if color is None:
+        color = np.zeros((frame.height, frame.width, 4), dtype=np.float32)
+    lib().oracle_sky(C.byref(frame.c), C.c_void_p(vis64.ctypes.data), C.c_void_p(tr.ctypes.data), C.c_void_p(ir.ctypes.data),
+                     C.c_void_p(sc.ctypes.data), C.c_void_p(mie.ctypes.data) if mie is not None else None, C.c_void_p(color.ctypes.data))
+    return color
+
+
 def sample_alpha(table, tex_id, smp_id, u, v, dudx, dvdx, dudy, dvdy):
     """The specified sampler of the masked bucket on one sample."""
     fn = lib().oracle_sample_alpha

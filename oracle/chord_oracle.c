@@ -1164,6 +1164,160 @@ static v3 sun_and_sky_irradiance(const chord_AtmosphereParameters* at, const uin
 
 static inline double storage_to_double(chord_uint2 u) { uint64_t b = (uint64_t)u.x | ((uint64_t)u.y << 32); double d; memcpy(&d, &b, 8); return d; }
 
+
+/* ------------------------------------------------------------------ K11, LIGHTING_TYPE == None: the sky branch
+ * lighting.hlsl:75-166 (skyColorEvaluate) + atmosphere.hlsli:948-997 (GetSkyRadiance), :916-946 (GetCombinedScattering),
+ * :405-462 (GetScatteringTextureUvwzFromRMuMuSNu), :904-914, :116-121, :99-106; base.hlsli:601-615 (phase functions).
+ * Pins: Texture3D SampleLevel(linear clamp, 0) = fp32 trilinear on the RGBA16F texels (x, then y, then z,
+ * each a + (b - a) * t); pow(x, 1.5) in the Cornette-Shanks phase = x * sqrt(x) (IEEE), the transcendental is implementation
+ * defined on a GPU; everything else plain fp32 in the HLSL's order; normalize = v * rcp(sqrt(dot)). */
+#define SC_R 32
+#define SC_MU 128
+#define SC_MU_S 32
+#define SC_NU 8
+typedef struct { float x, y, z, w; } v4;
+static v4 sample_lut3d(const uint16_t* lut, float u, float v, float w)
+{
+    const int W = SC_NU * SC_MU_S, H = SC_MU, D = SC_R;
+    const float x = u * (float)W - 0.5f, y = v * (float)H - 0.5f, z = w * (float)D - 0.5f;
+    const float fx0 = floorf(x), fy0 = floorf(y), fz0 = floorf(z);
+    const float fx = x - fx0, fy = y - fy0, fz = z - fz0;
+    int x0 = (int)fx0, y0 = (int)fy0, z0 = (int)fz0, x1 = x0 + 1, y1 = y0 + 1, z1 = z0 + 1;
+#define CL(a, n) do { if (a < 0) a = 0; if (a > n - 1) a = n - 1; } while (0)
+    CL(x0, W); CL(x1, W); CL(y0, H); CL(y1, H); CL(z0, D); CL(z1, D);
+#undef CL
+    float o[4];
+    for (int c = 0; c < 4; c++) {
+        float zz[2];
+        for (int k = 0; k < 2; k++) {
+            const int zi = k ? z1 : z0;
+            const uint16_t* s = lut + ((size_t)zi * H * W) * 4;
+            const float a = oracle_f16_to_f32(s[((size_t)y0 * W + x0) * 4 + c]), b = oracle_f16_to_f32(s[((size_t)y0 * W + x1) * 4 + c]);
+            const float d = oracle_f16_to_f32(s[((size_t)y1 * W + x0) * 4 + c]), e = oracle_f16_to_f32(s[((size_t)y1 * W + x1) * 4 + c]);
+            const float top = a + (b - a) * fx, bot = d + (e - d) * fx;
+            zz[k] = top + (bot - top) * fy;
+        }
+        o[c] = zz[0] + (zz[1] - zz[0]) * fz;
+    }
+    v4 r = { o[0], o[1], o[2], o[3] };
+    return r;
+}
+
+static inline float safe_sqrt(float a) { return sqrtf(fmaxf(a, 0.0f)); }
+static inline float dist_to_top(const chord_AtmosphereParameters* at, float r, float mu)
+{ const float disc = r * r * (mu * mu - 1.0f) + at->top_radius * at->top_radius; return fmaxf(-r * mu + safe_sqrt(disc), 0.0f); }
+
+static v3 sky_radiance(const chord_AtmosphereParameters* at, const uint16_t* scLut, const uint16_t* mieLut, const float ap1[9],
+                       v3 camera, v3 ray, v3 sunDir)
+{
+    float r = sqrtf(v3dot(camera, camera));
+    float rmu = v3dot(camera, ray);
+    const float dtop = -rmu - sqrtf(rmu * rmu - r * r + at->top_radius * at->top_radius);
+    if (dtop > 0.0f) { camera = v3add(camera, v3s(ray, dtop)); r = at->top_radius; rmu += dtop; }
+    else if (r > at->top_radius) return v3_(0, 0, 0);
+    const float mu = rmu / r;
+    const float mu_s = v3dot(camera, sunDir) / r;
+    const float nu = v3dot(ray, sunDir);
+    const int hitsGround = mu < 0.0f && r * r * (mu * mu - 1.0f) + at->bottom_radius * at->bottom_radius >= 0.0f;
+    /* GetScatteringTextureUvwzFromRMuMuSNu */
+    const float H = sqrtf(at->top_radius * at->top_radius - at->bottom_radius * at->bottom_radius);
+    const float rho = safe_sqrt(r * r - at->bottom_radius * at->bottom_radius);
+    const float u_r = tex_coord_from_unit(rho / H, SC_R);
+    const float r_mu = r * mu;
+    const float disc = r_mu * r_mu - r * r + at->bottom_radius * at->bottom_radius;
+    float u_mu;
+    if (hitsGround) {
+        const float d = -r_mu - safe_sqrt(disc), d_min = r - at->bottom_radius, d_max = rho;
+        u_mu = 0.5f - 0.5f * tex_coord_from_unit(d_max == d_min ? 0.0f : (d - d_min) / (d_max - d_min), SC_MU / 2);
+    } else {
+        const float d = -r_mu + safe_sqrt(disc + H * H), d_min = at->top_radius - r, d_max = rho + H;
+        u_mu = 0.5f + 0.5f * tex_coord_from_unit((d - d_min) / (d_max - d_min), SC_MU / 2);
+    }
+    const float d = dist_to_top(at, at->bottom_radius, mu_s);
+    const float d_min = at->top_radius - at->bottom_radius, d_max = H;
+    const float a = (d - d_min) / (d_max - d_min);
+    const float Dd = dist_to_top(at, at->bottom_radius, at->mu_s_min);
+    const float A = (Dd - d_min) / (d_max - d_min);
+    const float u_mu_s = tex_coord_from_unit(fmaxf(1.0f - a / A, 0.0f) / (1.0f + a), SC_MU_S);
+    const float u_nu = (nu + 1.0f) / 2.0f;
+    /* GetCombinedScattering */
+    const float tcx = u_nu * (float)(SC_NU - 1);
+    const float tex_x = floorf(tcx), lerp = tcx - tex_x;
+    const float ua = (tex_x + u_mu_s) / (float)SC_NU, ub = (tex_x + 1.0f + u_mu_s) / (float)SC_NU;
+    const v4 s0 = sample_lut3d(scLut, ua, u_mu, u_r), s1 = sample_lut3d(scLut, ub, u_mu, u_r);
+    const float w0 = 1.0f - lerp;
+    v3 scattering = v3_(s0.x * w0 + s1.x * lerp, s0.y * w0 + s1.y * lerp, s0.z * w0 + s1.z * lerp), mie;
+    if (at->bCombineScattering != 0) {
+        const float ca = s0.w * w0 + s1.w * lerp;
+        if (scattering.x <= 0.0f) mie = v3_(0, 0, 0);
+        else {
+            const float k = at->rayleigh_scattering.x / at->mie_scattering.x;
+            mie = v3_(scattering.x * ca / scattering.x * k * (at->mie_scattering.x / at->rayleigh_scattering.x),
+                      scattering.y * ca / scattering.x * k * (at->mie_scattering.y / at->rayleigh_scattering.y),
+                      scattering.z * ca / scattering.x * k * (at->mie_scattering.z / at->rayleigh_scattering.z));
+        }
+    } else {
+        const v4 m0 = sample_lut3d(mieLut, ua, u_mu, u_r), m1 = sample_lut3d(mieLut, ub, u_mu, u_r);
+        mie = v3_(m0.x * w0 + m1.x * lerp, m0.y * w0 + m1.y * lerp, m0.z * w0 + m1.z * lerp);
+    }
+    const float kPI = 3.14159265358979323846f;
+    const float rayleigh = (3.0f / (16.0f * kPI)) * (1.0f + nu * nu);
+    const float g = at->mie_phase_function_g, g2 = g * g;
+    const float kk = 3.0f / (8.0f * kPI) * (1.0f - g2) / (2.0f + g2);
+    const float base = 1.0f + g2 - 2.0f * g * nu;
+    const float miePhase = kk * (1.0f + nu * nu) / (base * sqrtf(base));             /* pow(base, 1.5) pinned as base * sqrt(base) */
+    const v3 skyL = at->luminanceMode != 0 ? v3_(at->skySpectralRadianceToLumiance.x, at->skySpectralRadianceToLumiance.y, at->skySpectralRadianceToLumiance.z) : v3_(1, 1, 1);
+    const v3 sc = v3add(v3s(scattering, rayleigh), v3s(mie, miePhase));
+    return mat3_mul(ap1, v3mul(sc, skyL));
+}
+
+/* lighting.hlsl:75-166 for every pixel of the tile without geometry; writes the colour plane only (exportGbuffer with
+ * LIGHTING_TYPE == None stores sceneColor alone, lighting.hlsl:62-73) */
+void oracle_sky(const oracle_frame* f, const uint64_t* vis64, const uint16_t* trLut, const uint16_t* irLut, const uint16_t* scLut,
+                const uint16_t* mieLut, float* colorPlane)
+{
+    float ap1[9]; srgb_to_ap1_matrix(ap1);
+    const chord_PerframeCameraView* view = f->view;
+    const chord_AtmosphereParameters* at = &view->basicData.atmosphere;
+    if (!mieLut) mieLut = scLut;      /* bCombineScattering == 0 without a single-Mie volume: undefined in the reference (bindless id 0); pinned */
+    const float tsx = 1.0f / (float)f->width, tsy = 1.0f / (float)f->height;
+    const v3 sunDir = v3_(-view->basicData.sunInfo.direction.x, -view->basicData.sunInfo.direction.y, -view->basicData.sunInfo.direction.z);
+    const v3 camEarth = v3_((float)storage_to_double(view->cameraToEarthCenter_km.x), (float)storage_to_double(view->cameraToEarthCenter_km.y), (float)storage_to_double(view->cameraToEarthCenter_km.z));
+    const v3 camKm = v3_((float)storage_to_double(view->cameraPositionWS_km.x), (float)storage_to_double(view->cameraPositionWS_km.y), (float)storage_to_double(view->cameraPositionWS_km.z));
+    const v3 earthC = v3_(at->earthCenterKm.x, at->earthCenterKm.y, at->earthCenterKm.z);
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic, 4)
+#endif
+    for (uint32_t py = f->tile.y0; py < f->tile.y1; py++)
+        for (uint32_t px = f->tile.x0; px < f->tile.x1; px++) {
+            const size_t pi = (size_t)py * f->width + px;
+            if ((uint32_t)(vis64[pi] & 0xFFFFFFFFu) != 0u) continue;
+            const float su = ((float)px + 0.5f) * tsx, sv = ((float)py + 0.5f) * tsy;
+            const f4 vp = mat_mul_vec(&view->clipToTranslatedWorld, 2.0f * (su - 0.5f), 2.0f * (0.5f - sv), 1.192092896e-07f, 1.0f);
+            const v3 dir = v3norm(v3_(vp.x / vp.w, vp.y / vp.w, vp.z / vp.w));
+            float groundAlpha = 0.0f; v3 ground = v3_(0, 0, 0);
+            const float pov = v3dot(camEarth, dir), pop = v3dot(camEarth, camEarth);
+            const float rsq = pop - pov * pov;
+            const float d2i = -pov - sqrtf(at->bottom_radius * at->bottom_radius - rsq);
+            if (d2i > 0.0f) {
+                const v3 ip = v3add(camKm, v3s(dir, d2i));
+                const v3 rel = v3sub(ip, earthC);
+                const v3 normal = v3norm(rel);
+                v3 skyIrr;
+                const v3 sunIrr = sun_and_sky_irradiance(at, trLut, irLut, ap1, rel, normal, sunDir, &skyIrr);
+                const v3 alb = v3s(v3_(at->ground_albedo.x, at->ground_albedo.y, at->ground_albedo.z), 1.0f / 3.14159265358979323846f);
+                ground = v3mul(alb, v3add(v3s(sunIrr, 1.0f), v3s(skyIrr, 1.0f)));
+                groundAlpha = 1.0f;
+            }
+            v3 rad = sky_radiance(at, scLut, mieLut, ap1, camEarth, dir, sunDir);
+            rad = v3_(rad.x + (ground.x - rad.x) * groundAlpha, rad.y + (ground.y - rad.y) * groundAlpha, rad.z + (ground.z - rad.z) * groundAlpha);
+            const float k = at->luminanceMode == 0 ? 1.0f : 1e-5f;
+            v3 color = v3_(10.0f * rad.x * k, 10.0f * rad.y * k, 10.0f * rad.z * k);
+            if (isnan(color.x) || isnan(color.y) || isnan(color.z)) color = v3_(0, 0, 0);
+            float* o0 = colorPlane + pi * 4; o0[0] = color.x; o0[1] = color.y; o0[2] = color.z; o0[3] = 0.0f;
+        }
+}
+
 static inline const chord_texture_desc* tex_lookup(const oracle_frame* f, uint32_t id)
 { return (f->textures && id < f->textureCount && f->textures[id].rgba8) ? &f->textures[id] : NULL; }
 static inline const chord_sampler_desc* smp_lookup(const oracle_frame* f, uint32_t id)
@@ -1322,8 +1476,8 @@ void oracle_lighting(const oracle_frame* f, const uint64_t* vis64, const chord_d
                 diff = v3s(dc, NdotL); spec = v3s(sc, NdotL);
             }
             diff = v3mul(diff, radiance); spec = v3mul(spec, radiance);
-            const float expo = 10.0f * (at->luminanceMode == 0 ? 1.0f : 1e-5f);
-            diff = v3s(diff, expo); spec = v3s(spec, expo);
+            const float expoK = at->luminanceMode == 0 ? 1.0f : 1e-5f;           /* finalRadianceExposureModify: 10.0 * radiance * k, left to right */
+            diff = v3s(v3s(diff, 10.0f), expoK); spec = v3s(v3s(spec, 10.0f), expoK);
             v3 color = v3add(diff, spec);
             if (isnan(color.x) || isnan(color.y) || isnan(color.z)) color = v3_(0, 0, 0);
             float* o0 = planes[0] + pi * 4; o0[0] = color.x; o0[1] = color.y; o0[2] = color.z; o0[3] = 0.0f;

@@ -81,6 +81,10 @@ void oracle_visibility_mark(const oracle_frame* f, const uint64_t* vis64,
 
 /* K11: lighting.hlsl:270-381, PBR branch, untextured materials.  planes[6] = CHORD_GBUF_* order, 4 floats per pixel,
  * pre-quantisation fp32 values; untouched pixels are 0.  LUTs are RGBA16F bit patterns (256x64 and 64x16). */
+/* sky branch of the lighting pass (lighting.hlsl:75-166) for the texels without geometry: scattering = RGBA16F 256 x 128 x 32
+ * (atmosphere.hlsli:43-49), singleMie = same shape or NULL when atmosphere.bCombineScattering != 0 */
+void oracle_sky(const oracle_frame* f, const uint64_t* vis64, const uint16_t* trLut, const uint16_t* irLut, const uint16_t* scattering,
+                const uint16_t* singleMie, float* colorPlane);
 void oracle_lighting(const oracle_frame* f, const uint64_t* vis64, const chord_draw_cmd* postCull, uint32_t postCullCount,
                      const uint16_t* transmittanceLut, const uint16_t* irradianceLut, float* const planes[6]);
 

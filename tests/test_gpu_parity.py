@@ -328,6 +328,91 @@ def test_lighting_textured_materials(gpu_ctx):
     gpu_ctx.upload_textures(None)
 
 
+def _sky_frame_on_s1(ctx, view, tr, ir, sc, mie, packed=False, w=256, h=256):
+    scene, camera, objects = synth.single_meshlet_scene(w, h)
+    iview = cam.fill_instance_view(view)
+    ctx.upload_scene(scene)
+    fr = runtime.Frame(ctx, w, h)
+    if packed:
+        fr.set_gbuffer_packed(True)
+    fr.begin(view, iview, objects, 1, 1)
+    post = runtime.CmdList(ctx, 4)
+    fr.instance_culling(post)
+    fr.render_mesh(post)
+    fr.visibility_mark(post)
+    fr.lighting(post)
+    ofr = oracle.Frame(scene, view, iview, objects, w, h)
+    opost = ofr.instance_culling(4)
+    ovis, _ = ofr.render_mesh(opost)
+    _assert_vis_equal(fr.vis64(), ovis, 'vis64')
+    g = oracle.lighting(ofr, ovis, opost, tr, ir)
+    pbr = g[0].copy()
+    if sc is not None:
+        oracle.sky(ofr, ovis, tr, ir, sc, mie, color=g[0])
+    return fr, g, pbr, ovis
+
+
+def test_sky_branch(gpu_ctx):
+    """Row a11, LIGHTING_TYPE == None (lighting.hlsl:75-166; the {None, PBR} loop of lighting.cpp:193-246): with the scattering
+    volumes uploaded, chord_lighting writes skyColorEvaluate into every texel without geometry - GetSkyRadiance through the
+    4-D scattering table packed in a 3-D volume, the ground branch (GetSunAndSkyIrradiance on the intersection with the
+    planet) below the horizon - and nothing but the colour plane there.  Every plane equal to the oracle's, for the combined
+    table (single Mie extrapolated from its alpha) and for a separate single-Mie volume; packed colour RGBA16F equal too."""
+    from cases import city_frames
+    tr, ir = synth.synthetic_luts()
+    sc, mie = synth.synthetic_scattering_luts()
+    gpu_ctx.upload_luts(tr, ir)
+    scene, camera, objects = synth.single_meshlet_scene()
+    try:
+        for combine, m in ((1, None), (0, mie), (0, None)):
+            view = cam.fill_view(camera)
+            view['basicData']['atmosphere']['bCombineScattering'] = combine
+            gpu_ctx.upload_scattering(sc, m)
+            fr, g, pbr, ovis = _sky_frame_on_s1(gpu_ctx, view, tr, ir, sc, m)
+            _assert_gbuffer_equal(fr, g)
+            empty = (ovis & 0xFFFFFFFF) == 0
+            # the case must exercise both halves: rays above the horizon (scattering only) and rays that hit the planet
+            assert empty.sum() > 10000 and (g[0][empty][:, :3].sum(axis=-1) > 0).all()
+            assert np.array_equal(g[0][~empty], pbr[~empty])                   # the sky branch leaves shaded texels alone
+            if combine == 1:
+                black = view.copy()
+                black['basicData']['atmosphere']['ground_albedo'] = 0.0
+                iv = cam.fill_instance_view(black)
+                o2 = oracle.Frame(scene, black, iv, objects, 256, 256)
+                no_ground = oracle.sky(o2, ovis, tr, ir, sc, m)
+                hits = (no_ground != g[0]).any(axis=-1) & empty
+                assert hits.sum() > 5000 and (empty & ~hits).sum() > 5000, (hits.sum(), empty.sum())
+            for k in range(1, 6):
+                assert not g[k][empty].any()
+        # luminance mode (skySpectralRadianceToLumiance, the 1e-5 exposure factor) and the packed colour format
+        view = cam.fill_view(camera)
+        view['basicData']['atmosphere']['luminanceMode'] = 1
+        gpu_ctx.upload_scattering(sc, None)
+        fr, g, _, _ = _sky_frame_on_s1(gpu_ctx, view, tr, ir, sc, None)
+        _assert_gbuffer_equal(fr, g)
+        fr, g, _, _ = _sky_frame_on_s1(gpu_ctx, cam.fill_view(camera), tr, ir, sc, None, packed=True)
+        assert np.array_equal(g[0].astype(np.float16).view(np.uint16), fr.gbuffer_packed(0).view(np.uint16))
+        # a frame with real geometry through the renderer: sky between the buildings
+        w, h = 640, 360
+        scene2, info, frames = city_frames(frames=2, w=w, h=h)
+        gpu_ctx.upload_scene(scene2)
+        r = renderer.DeferredRenderer(gpu_ctx, w, h, do_resolve=True)
+        prev = None
+        for f in frames:
+            r.render(f['camera'], f['objects'], info['lod0MeshletCount'], info['meshletGroupCount'], view=f['view'], iview=f['iview'])
+            ref = oracle.run_frame(scene2, f['view'], f['iview'], f['objects'], w, h, info['lod0MeshletCount'], prev)
+            g = oracle.lighting(ref['frame'], ref['vis64'], ref['post_cull'], tr, ir)
+            oracle.sky(ref['frame'], ref['vis64'], tr, ir, sc, None, color=g[0])
+            _assert_gbuffer_equal(r.frame, g)
+            prev = ref['hzb']
+        # the branch goes away with its volumes: unshaded texels read as cleared again
+        gpu_ctx.upload_scattering(None)
+        fr, g, _, _ = _sky_frame_on_s1(gpu_ctx, cam.fill_view(camera), tr, ir, None, None)
+        _assert_gbuffer_equal(fr, g)
+    finally:
+        gpu_ctx.upload_scattering(None)
+
+
 def test_bvh_traversal(gpu_ctx):
     """N4: persistent-warp BVH traversal -> same post-cull list as the flat kernel and as the oracle; same candidate set."""
     from cases import case_stream, city_frames

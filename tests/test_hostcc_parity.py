@@ -130,6 +130,10 @@ def test_lighting_textured_materials(host_ctx, cases):
     cases.test_lighting_textured_materials(host_ctx)
 
 
+def test_sky_branch(host_ctx, cases):
+    cases.test_sky_branch(host_ctx)
+
+
 def test_lighting_packed_formats(host_ctx, cases):
     cases.test_lighting_packed_formats(host_ctx)
 

@@ -31,7 +31,8 @@ def hostlib(tmp_path_factory):
     src = open(os.path.join(ROOT, 'chord_b200', 'csrc', 'resolve.cu')).read()
     src, n = re.subn(r'^int launch_\w+\([^)]*\)\n\{.*?^\}\n', '', src, flags=re.S | re.M)
     src, n2 = re.subn(r'^template <bool kPacked, int kSlot>\nstatic void lighting_launch\([^)]*\)\n\{.*?^\}\n', '', src, flags=re.S | re.M)
-    assert n == 2 and n2 == 1 and '<<<' not in src, 'expected to cut exactly the launchers out of resolve.cu'
+    src, n3 = re.subn(r'^template <bool kPacked, int kSlot>\nstatic void sky_launch\([^)]*\)\n\{.*?^\}\n', '', src, flags=re.S | re.M)
+    assert n == 2 and n2 == 1 and n3 == 1 and '<<<' not in src, 'expected to cut exactly the launchers out of resolve.cu'
     src = src.replace('#include "common.cuh"', '')
     open(d / 'resolve_device.inc', 'w').write(src)
     so = str(d / 'libhostcc_resolve.so')

@@ -213,6 +213,184 @@ def lighting_statement(scene, view, objects, vis64, post, tr_lut, ir_lut):
     return planes
 
 
+# ---------------------------------------------------------------------------------------------- the sky branch
+def _sample3d_level0(lut, u, v, w):
+    """Texture3D.SampleLevel(linear clamp, 0) on a (D, H, W, 4) RGBA16F volume: weighted sum of the eight texels."""
+    D, H, W = lut.shape[:3]
+    t = lut.astype(F)
+    out = np.zeros((len(u), 4), dtype=np.float64)
+    x, y, z = (u * F(W) - F(0.5)).astype(F), (v * F(H) - F(0.5)).astype(F), (w * F(D) - F(0.5)).astype(F)
+    x0, y0, z0 = np.floor(x), np.floor(y), np.floor(z)
+    fx, fy, fz = (x - x0).astype(np.float64), (y - y0).astype(np.float64), (z - z0).astype(np.float64)
+    x0, y0, z0 = x0.astype(np.int64), y0.astype(np.int64), z0.astype(np.int64)
+    for dz in (0, 1):
+        for dy in (0, 1):
+            for dx in (0, 1):
+                wgt = (fx if dx else 1 - fx) * (fy if dy else 1 - fy) * (fz if dz else 1 - fz)
+                out += t[np.clip(z0 + dz, 0, D - 1), np.clip(y0 + dy, 0, H - 1), np.clip(x0 + dx, 0, W - 1)].astype(np.float64) * wgt[:, None]
+    return out.astype(F)
+
+
+def _sun_and_sky_irradiance(at, ap1, point, normal, sun_dir, tr_lut, ir_lut):
+    """GetSunAndSkyIrradiance (atmosphere.hlsli:1063-1088) -> (sun, sky), both through sRGB_2_AP1."""
+    bottom, top = F(at['bottom_radius']), F(at['top_radius'])
+    lum = at['luminanceMode'] != 0
+    sky_l = np.asarray(at['skySpectralRadianceToLumiance'], dtype=F) if lum else np.ones(3, dtype=F)
+    sun_l = np.asarray(at['sunSpectralRadianceToLumiance'], dtype=F) if lum else np.ones(3, dtype=F)
+    r = np.sqrt(_dot3(point, point)).astype(F)
+    sun_b = np.broadcast_to(sun_dir, point.shape)
+    mu_s = (_dot3(point, sun_b) / r).astype(F)
+    irr = _sample_level0(ir_lut, _coord_from_unit((mu_s * F(0.5) + F(0.5)).astype(F), 64), _coord_from_unit(((r - bottom) / (top - bottom)).astype(F), 16))
+    sky = ((irr * (F(1.0) + (_dot3(normal, point) / r).astype(F))[:, None]).astype(F) * F(0.5)).astype(F)
+    sky = _mul33(ap1, (sky * sky_l).astype(F))
+    sin_h = (bottom / r).astype(F)
+    cos_h = (-np.sqrt(np.maximum(F(1.0) - (sin_h * sin_h).astype(F), F(0.0)))).astype(F)
+    big_h = np.sqrt((top * top) - (bottom * bottom)).astype(F)
+    rho = np.sqrt(np.maximum(((r * r).astype(F) - bottom * bottom).astype(F), F(0.0))).astype(F)
+    disc = (((r * r).astype(F) * ((mu_s * mu_s).astype(F) - F(1.0)).astype(F)).astype(F) + top * top).astype(F)
+    d = np.maximum(((-r * mu_s).astype(F) + np.sqrt(np.maximum(disc, F(0.0))).astype(F)).astype(F), F(0.0))
+    x_mu = ((d - (top - r)).astype(F) / ((rho + big_h) - (top - r)).astype(F)).astype(F)
+    transmittance = _sample_level0(tr_lut, _coord_from_unit(x_mu, 256), _coord_from_unit((rho / big_h).astype(F), 64))
+    sar = F(at['sun_angular_radius'])
+    e0, e1 = (-sin_h * sar).astype(F), (sin_h * sar).astype(F)
+    t = np.clip((((mu_s - cos_h).astype(F) - e0).astype(F) / (e1 - e0).astype(F)).astype(F), 0, 1).astype(F)
+    smooth = ((t * t).astype(F) * (F(3.0) - (F(2.0) * t).astype(F)).astype(F)).astype(F)
+    n_dot_sun = np.maximum(_dot3(normal, sun_b), F(0.0))
+    sun_radiance = ((np.asarray(at['solar_irradiance'], dtype=F) * (transmittance * smooth[:, None]).astype(F)).astype(F) * n_dot_sun[:, None]).astype(F)
+    return _mul33(ap1, (sun_l * sun_radiance).astype(F)), sky
+
+
+def sky_statement(view, vis64, tr_lut, ir_lut, sc_lut, mie_lut=None):
+    """skyColorEvaluate (lighting.hlsl:75-166) for every texel without geometry: GetSkyRadiance (atmosphere.hlsli:948-997),
+    GetCombinedScattering (:916-946), GetScatteringTextureUvwzFromRMuMuSNu (:405-462), the ground branch through
+    GetSunAndSkyIrradiance, rayleighPhase / cornetteShanksMiePhase (base.hlsli:601-615), finalRadianceExposureModify."""
+    view = np.asarray(view).reshape(())
+    H, W = vis64.shape
+    color = np.zeros((H, W, 4), dtype=F)
+    ys, xs = np.nonzero((vis64 & np.uint64(0xFFFFFFFF)) == 0)
+    at = view['basicData']['atmosphere']
+    ap1 = _srgb_to_ap1()
+    texel = np.array([F(1.0) / F(W), F(1.0) / F(H)], dtype=F)
+    uv = ((np.stack([xs, ys], axis=-1).astype(F) + F(0.5)) * texel).astype(F)
+    ndc = np.stack([F(2.0) * (uv[:, 0] - F(0.5)), F(2.0) * (F(0.5) - uv[:, 1]), np.full(len(xs), 1.192092896e-07, dtype=F), np.ones(len(xs), dtype=F)], axis=-1).astype(F)
+    vp = mul_mv(mat(view['clipToTranslatedWorld']), ndc)
+    ray = _normalize((vp[:, :3] / vp[:, 3:4]).astype(F))
+    sun_dir = (-np.asarray(view['basicData']['sunInfo']['direction'], dtype=F)).astype(F)
+    cam_earth = np.array([_d(view['cameraToEarthCenter_km'][k]) for k in range(3)]).astype(F)
+    cam_km = np.array([_d(view['cameraPositionWS_km'][k]) for k in range(3)]).astype(F)
+    bottom, top = F(at['bottom_radius']), F(at['top_radius'])
+    camera = np.broadcast_to(cam_earth, ray.shape).astype(F)
+    # ---- ground
+    pov, pop = _dot3(camera, ray), _dot3(camera, camera)
+    with np.errstate(invalid='ignore'):
+        d2i = ((-pov).astype(F) - np.sqrt(((bottom * bottom) - (pop - (pov * pov).astype(F)).astype(F)).astype(F)).astype(F)).astype(F)
+    hit = d2i > 0
+    ground = np.zeros_like(ray)
+    if hit.any():
+        ip = (cam_km + (ray[hit] * d2i[hit, None]).astype(F)).astype(F)
+        rel = (ip - np.asarray(at['earthCenterKm'], dtype=F)).astype(F)
+        sun_i, sky_i = _sun_and_sky_irradiance(at, ap1, rel, _normalize(rel), sun_dir, tr_lut, ir_lut)
+        ground[hit] = ((np.asarray(at['ground_albedo'], dtype=F) * (F(1.0) / F(np.pi))).astype(F) * (sun_i + sky_i).astype(F)).astype(F)
+    # ---- GetSkyRadiance (the camera of these tests is inside the atmosphere: the move-to-the-top branch is asserted away)
+    r = np.sqrt(pop).astype(F)
+    rmu = pov
+    with np.errstate(invalid='ignore'):
+        dtop = ((-rmu).astype(F) - np.sqrt((((rmu * rmu).astype(F) - (r * r).astype(F)).astype(F) + top * top).astype(F))).astype(F)
+    assert not (dtop > 0).any() and (r <= top).all()
+    mu = (rmu / r).astype(F)
+    sun_b = np.broadcast_to(sun_dir, ray.shape)
+    mu_s = (_dot3(camera, sun_b) / r).astype(F)
+    nu = _dot3(ray, sun_b)
+    hits_ground = (mu < 0) & ((((r * r).astype(F) * ((mu * mu).astype(F) - F(1.0)).astype(F)).astype(F) + bottom * bottom).astype(F) >= 0)
+    big_h = np.sqrt((top * top) - (bottom * bottom)).astype(F)
+    rho = np.sqrt(np.maximum(((r * r).astype(F) - bottom * bottom).astype(F), F(0.0))).astype(F)
+    u_r = _coord_from_unit((rho / big_h).astype(F), 32)
+    r_mu = (r * mu).astype(F)
+    disc = (((r_mu * r_mu).astype(F) - (r * r).astype(F)).astype(F) + bottom * bottom).astype(F)
+    with np.errstate(invalid='ignore', divide='ignore'):
+        dg = ((-r_mu).astype(F) - np.sqrt(np.maximum(disc, F(0.0))).astype(F)).astype(F)
+        dg_min, dg_max = (r - bottom).astype(F), rho
+        xg = np.where(dg_max == dg_min, F(0.0), ((dg - dg_min).astype(F) / (dg_max - dg_min).astype(F)).astype(F)).astype(F)
+        u_mu_g = (F(0.5) - (F(0.5) * _coord_from_unit(xg, 64)).astype(F)).astype(F)
+        dt = ((-r_mu).astype(F) + np.sqrt(np.maximum((disc + (big_h * big_h).astype(F)).astype(F), F(0.0))).astype(F)).astype(F)
+        dt_min, dt_max = (top - r).astype(F), (rho + big_h).astype(F)
+        u_mu_t = (F(0.5) + (F(0.5) * _coord_from_unit(((dt - dt_min).astype(F) / (dt_max - dt_min).astype(F)).astype(F), 64)).astype(F)).astype(F)
+    u_mu = np.where(hits_ground, u_mu_g, u_mu_t).astype(F)
+
+    def dist_top(mu_):          # DistanceToTopAtmosphereBoundary(atmosphere, bottom_radius, mu)
+        dsc = (((bottom * bottom) * ((mu_ * mu_).astype(F) - F(1.0)).astype(F)).astype(F) + top * top).astype(F)
+        return np.maximum(((-bottom * mu_).astype(F) + np.sqrt(np.maximum(dsc, F(0.0))).astype(F)).astype(F), F(0.0)).astype(F)
+    d_min, d_max = F(top - bottom), big_h
+    a = ((dist_top(mu_s) - d_min).astype(F) / F(d_max - d_min)).astype(F)
+    big_a = F((dist_top(np.array([at['mu_s_min']], dtype=F))[0] - d_min) / F(d_max - d_min))
+    u_mu_s = _coord_from_unit((np.maximum((F(1.0) - (a / big_a).astype(F)).astype(F), F(0.0)) / (F(1.0) + a).astype(F)).astype(F), 32)
+    u_nu = ((nu + F(1.0)).astype(F) / F(2.0)).astype(F)
+    tcx = (u_nu * F(7.0)).astype(F)
+    tex_x = np.floor(tcx).astype(F)
+    lerp = (tcx - tex_x).astype(F)
+    ua, ub = ((tex_x + u_mu_s).astype(F) / F(8.0)).astype(F), (((tex_x + F(1.0)).astype(F) + u_mu_s).astype(F) / F(8.0)).astype(F)
+    s0, s1 = _sample3d_level0(sc_lut, ua, u_mu, u_r), _sample3d_level0(sc_lut, ub, u_mu, u_r)
+    w0 = (F(1.0) - lerp).astype(F)[:, None]
+    comb = ((s0 * w0).astype(F) + (s1 * lerp[:, None]).astype(F)).astype(F)
+    scattering = comb[:, :3]
+    if at['bCombineScattering'] != 0:
+        ray_s, mie_s = np.asarray(at['rayleigh_scattering'], dtype=F), np.asarray(at['mie_scattering'], dtype=F)
+        with np.errstate(invalid='ignore', divide='ignore'):
+            ext = ((((scattering * comb[:, 3:4]).astype(F) / comb[:, 0:1]).astype(F) * F(ray_s[0] / mie_s[0])).astype(F) * (mie_s / ray_s).astype(F)).astype(F)
+        mie = np.where(comb[:, 0:1] <= 0, F(0.0), ext).astype(F)
+    else:
+        ml = mie_lut if mie_lut is not None else sc_lut
+        m0, m1 = _sample3d_level0(ml, ua, u_mu, u_r), _sample3d_level0(ml, ub, u_mu, u_r)
+        mie = ((m0[:, :3] * w0).astype(F) + (m1[:, :3] * lerp[:, None]).astype(F)).astype(F)
+    one_nu2 = (F(1.0) + (nu * nu).astype(F)).astype(F)
+    rayleigh_phase = (F(F(3.0) / (F(16.0) * F(np.pi))) * one_nu2).astype(F)
+    g = F(at['mie_phase_function_g'])
+    g2 = F(g * g)
+    kk = F(F(F(3.0) / F(F(8.0) * F(np.pi))) * F(F(1.0) - g2)) / F(F(2.0) + g2)
+    base = ((F(1.0) + g2) - (F(F(2.0) * g) * nu).astype(F)).astype(F)
+    mie_phase = ((F(kk) * one_nu2).astype(F) / (base * np.sqrt(base).astype(F)).astype(F)).astype(F)          # pow(base, 1.5) pinned as base * sqrt(base)
+    lum = at['luminanceMode'] != 0
+    sky_l = np.asarray(at['skySpectralRadianceToLumiance'], dtype=F) if lum else np.ones(3, dtype=F)
+    rad = _mul33(ap1, (((scattering * rayleigh_phase[:, None]).astype(F) + (mie * mie_phase[:, None]).astype(F)).astype(F) * sky_l).astype(F))
+    alpha = hit.astype(F)[:, None]
+    rad = (rad + ((ground - rad).astype(F) * alpha).astype(F)).astype(F)                              # lerp(radiance, groundRadiance, groundAlpha)
+    k = F(1.0) if not lum else F(1e-5)
+    out = ((F(10.0) * rad).astype(F) * k).astype(F)
+    out[np.isnan(out).any(axis=1)] = 0
+    color[ys, xs, :3] = out
+    return color
+
+
+def test_sky_matches_the_hlsl_statement():
+    """The oracle's sky branch against the numpy statement, on the single-meshlet frame (half of the empty texels look above the
+    horizon, half hit the planet) and between the buildings of the city, combined and separate single-Mie volumes, radiance and
+    luminance mode."""
+    from chord_b200 import camera as cam
+    tr, ir = synth.synthetic_luts()
+    sc, mie = synth.synthetic_scattering_luts()
+    scene, camera, objects = synth.single_meshlet_scene()
+    for combine, m, lum in ((1, None, 0), (0, mie, 0), (1, None, 1)):
+        view = cam.fill_view(camera)
+        view['basicData']['atmosphere']['bCombineScattering'] = combine
+        view['basicData']['atmosphere']['luminanceMode'] = lum
+        iview = cam.fill_instance_view(view)
+        fr = oracle.Frame(scene, view, iview, objects, 256, 256)
+        vis, _ = fr.render_mesh(fr.instance_culling(4))
+        got = oracle.sky(fr, vis, tr, ir, sc, m)
+        want = sky_statement(view, vis, tr, ir, sc, m)
+        err = np.abs(got - want)
+        assert (err <= 1e-5 + 1e-5 * np.abs(want)).all(), (combine, lum, err.max(), np.unravel_index(err.argmax(), err.shape))
+        assert np.array_equal(got.any(axis=-1), want.any(axis=-1)) and (want[..., :3].sum(axis=-1) > 0).sum() > 10000
+    scene, info, frames = city_frames(frames=1)
+    f = frames[0]
+    ref = oracle.run_frame(scene, f['view'], f['iview'], f['objects'], 640, 360, info['lod0MeshletCount'], None)
+    got = oracle.sky(ref['frame'], ref['vis64'], tr, ir, sc)
+    want = sky_statement(f['view'], ref['vis64'], tr, ir, sc)
+    err = np.abs(got - want)
+    assert (err <= 1e-5 + 1e-5 * np.abs(want)).all(), err.max()
+    assert (want[..., :3].sum(axis=-1) > 0).sum() > 5000
+
+
 def test_resolve_matches_the_hlsl_statement():
     scene, info, frames = city_frames(frames=2)
     tr, ir = synth.synthetic_luts()
