@@ -234,32 +234,43 @@ def frame_benchmark(ctx, stream, torch, steps=20, width=W4K, height=H4K, city=No
     ctx.upload_scene(scene)
     tr, ir = synth.synthetic_luts()
     ctx.upload_luts(tr, ir)
+    ctx.upload_scattering(synth.synthetic_scattering_luts()[0])      # the sky branch of the lighting pass (lighting.cpp:193-246 runs it every frame)
     lod0, groups = info['lod0MeshletCount'], info['meshletGroupCount']
-    frames = city_camera_path(camera, info, steps + 4, width, height)
-    r = runtime.Renderer(ctx, width, height, resolve=True, packed_gbuffer=True, graph=use_graph, timers=True)
+    WARM = 6                                 # eager frames + the graph captures of both history slots
+    frames = city_camera_path(camera, info, steps + WARM, width, height)
 
-    def run(fs):
-        for (c, objs, view, iview) in fs:
-            r.render(view, iview, objs, lod0, groups)
-    run(frames[:4])                          # 2 eager frames + the two graph captures
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t0 = time.perf_counter()
-    e0.record(stream)
-    run(frames[4:])
-    e1.record(stream)
-    torch.cuda.synchronize()
-    wall_ms = (time.perf_counter() - t0) * 1e3 / steps
-    ms = e0.elapsed_time(e1) / steps
+    def timed(r):
+        def run(fs):
+            for (c, objs, view, iview) in fs:
+                r.render(view, iview, objs, lod0, groups)
+        run(frames[:WARM])
+        _ = r.frame                          # (asynchronous resolve: orders the context stream after the last resolve)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record(stream)
+        run(frames[WARM:])
+        _ = r.frame
+        e1.record(stream)
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / steps, (time.perf_counter() - t0) * 1e3 / steps
+    # headline frame time: two frames in flight, the resolve of frame N on its own stream under the visibility passes of N + 1
+    ra = runtime.Renderer(ctx, width, height, resolve=True, packed_gbuffer=True, graph=use_graph, async_resolve=True)
+    ms, wall_ms = timed(ra)
+    replays_async = ra.graph_replays
+    ra.close()
+    # the same frames one pass after the other on one stream (the reference's single graphics queue), with the per-pass timers
+    r = runtime.Renderer(ctx, width, height, resolve=True, packed_gbuffer=True, graph=use_graph, timers=True)
+    ms_serial, _ = timed(r)
     # per-pass times: same frames again, one synchronising timer read per frame (untimed)
     acc = {k: 0.0 for k in runtime.PASS_LABELS}
     stage_meshlets = [0, 0]
     r.frame.reset_stats()
-    for (c, objs, view, iview) in frames[4:]:
+    for (c, objs, view, iview) in frames[WARM:]:
         r.render(view, iview, objs, lod0, groups)
         for k, v in r.pass_times().items():
             acc[k] += v
-    n = len(frames) - 4
+    n = len(frames) - WARM
     pass_us = {k: v / n for k, v in acc.items()}
     stats = r.frame.raster_stats()
     post_n = int(r.post_cull.count())
@@ -271,9 +282,13 @@ def frame_benchmark(ctx, stream, torch, steps=20, width=W4K, height=H4K, city=No
     per_frame_meshlets = stats['meshletsRastered'] / n
     out = {'workload': f'{label}: procedural city, {lod0} LOD-0 meshlet instances = {lod0 * 128} triangles ({scene.total_meshlets} unique meshlets over '
                        f'{city["lods"]} LODs, {len(frames[0][1])} objects), {width}x{height}, LOD cut at 1 px error, two-phase HZB, HZB builds, tile classify + '
-                       f'PBR resolve (packed G-buffer), camera path',
-           'submission': ('chord_renderer_render, recorded as 2 CUDA graphs and replayed with rewritten uniforms' if use_graph else 'chord_renderer_render, eager launches'),
-           'frames_per_s': 1000.0 / ms, 'ms_per_frame': ms, 'ms_per_frame_wall': wall_ms, 'frames_timed': steps, 'graph_replays': r.graph_replays,
+                       f'PBR + sky resolve (packed G-buffer), camera path',
+           'submission': (('chord_renderer_render, recorded as CUDA graphs (visibility passes + resolve per history slot) and replayed with rewritten uniforms'
+                           if use_graph else 'chord_renderer_render, eager launches')
+                          + '; CHORD_RENDERER_ASYNC_RESOLVE: the resolve of frame N runs on a second stream under the visibility passes of frame N + 1'),
+           'frames_per_s': 1000.0 / ms, 'ms_per_frame': ms, 'ms_per_frame_wall': wall_ms, 'frames_timed': steps, 'graph_replays': replays_async,
+           'ms_per_frame_serial': ms_serial, 'frames_per_s_serial': 1000.0 / ms_serial,
+           'serial_note': 'same frames, every pass after the other on one stream (timers renderer); pass_us below are measured on this run',
            'pass_us': pass_us, 'pass_us_sum': sum(pass_us.values()),
            'pass_roofline': pass_rooflines(pass_us, width, height, post_n, [per_frame_meshlets * 0.8, per_frame_meshlets * 0.2], avg_bytes, peak),
            'post_cull_meshlets_last_frame': post_n, 'raster_stats_total': stats}
@@ -391,8 +406,10 @@ def frame_benchmark_tiled(ctx, stream, torch, dist, rank, world, steps=20, width
     ctx.upload_scene(scene)
     tr, ir = synth.synthetic_luts()
     ctx.upload_luts(tr, ir)
+    ctx.upload_scattering(synth.synthetic_scattering_luts()[0])      # the sky branch of the lighting pass (lighting.cpp:193-246 runs it every frame)
     lod0, groups = info['lod0MeshletCount'], info['meshletGroupCount']
-    frames = city_camera_path(camera, info, steps + 4, width, height)
+    WARM = 6
+    frames = city_camera_path(camera, info, steps + WARM, width, height)
     tiles = multigpu.all_tiles(world, width, height)
     tile_iviews = [multigpu.tile_instance_view(view, c, tiles[rank]) for (c, objs, view, iview) in frames]      # hoisted out of the timed region
     dev = f'cuda:{ctx.device}'
@@ -402,13 +419,15 @@ def frame_benchmark_tiled(ctx, stream, torch, dist, rank, world, steps=20, width
             for i in range(lo, hi):
                 c, objs, view, _ = frames[i]
                 r.render(view, tile_iviews[i], objs, lod0, groups)
-        run(0, 4)
+        run(0, WARM)
+        _ = r.frame
         torch.cuda.synchronize()
         dist.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
         e0.record(stream)
-        run(4, len(frames))
+        run(WARM, len(frames))
+        _ = r.frame                                            # asynchronous resolve: the last resolve is inside the timed region
         e1.record(stream)
         torch.cuda.synchronize()
         wall = (time.perf_counter() - t0) * 1e3 / steps
@@ -420,13 +439,21 @@ def frame_benchmark_tiled(ctx, stream, torch, dist, rank, world, steps=20, width
     out = {'workload': f'S3 stand-in city ({lod0 * 128} LOD-0 triangles) at {width}x{height} split into {world} screen tiles (one per GPU), full frame sequence incl. PBR resolve',
            'tile_rank0': list(tiles[0])}
     # ---- fused exchange
-    r = runtime.Renderer(ctx, width, height, resolve=True, packed_gbuffer=True, graph=use_graph)
+    r = runtime.Renderer(ctx, width, height, resolve=True, packed_gbuffer=True, graph=use_graph, async_resolve=True)
     multigpu.connect_fused(r, rank, world, dist, tiles)
     ms, wall = timed(r)
+    try:                                                       # the same without the overlap, for the record
+        rs = runtime.Renderer(ctx, width, height, resolve=True, packed_gbuffer=True, graph=use_graph)
+        multigpu.connect_fused(rs, rank, world, dist, tiles)
+        out['ms_per_frame_serial'] = timed(rs)[0]
+        rs.close()
+    except Exception as e:
+        out['ms_per_frame_serial'] = repr(e)
     timed_out = r.exchange_timed_out()
     out.update({'frames_per_s': 1000.0 / ms, 'ms_per_frame': ms, 'ms_per_frame_wall': wall, 'frames_timed': steps,
                 'exchange': 'fused: k_hzb_build stores the tile parts into every rank\'s history chain over NVLink peer memory (CUDA IPC), arrival flags, no collective call',
-                'submission': 'one CUDA graph launch per rank and frame' if use_graph else 'eager launches', 'graph_replays': r.graph_replays,
+                'submission': ('two CUDA graph launches per rank and frame (visibility passes; resolve on a second stream, overlapping the next frame)' if use_graph else 'eager launches'),
+                'graph_replays': r.graph_replays,
                 'exchange_bytes_per_frame': int(2 * sum(r.history_hzb.tile_bytes(t_) for t_ in tiles) * (world - 1)),
                 'exchange_timed_out': bool(timed_out)})
     # ---- parity, untimed: tile vs full frame on this GPU, gathered history vs single-GPU history

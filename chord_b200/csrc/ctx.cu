@@ -150,7 +150,10 @@ int chord_ctx_create(int device, chord_ctx** out)
     c->rasterVariant = 11; c->rasterCtasPerSm = 0; c->rasterWarpMin = 16384u;
     c->smCount = prop.multiProcessorCount;
     const int rc = [&]() -> int {
-        CHORD_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        // greatest priority: a renderer's asynchronous resolve stream (least priority) yields to the passes enqueued here
+        int leastPrio = 0, greatestPrio = 0;
+        CHORD_CUDA(cudaDeviceGetStreamPriorityRange(&leastPrio, &greatestPrio));
+        CHORD_CUDA(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, greatestPrio));
         // sRGB byte -> linear float (IEC 61966-2-1), the texel decode a *_SRGB image format performs; double precision on the
         // host, rounded once (the oracle builds the identical table)
         float lut[256];

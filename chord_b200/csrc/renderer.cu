@@ -76,7 +76,12 @@ using namespace chordb;
 struct chord_renderer {
     chord_ctx* ctx;
     uint32_t width, height, flags;
-    chord_frame* frame;
+    chord_frame* frame;                                             // the frame of the most recent chord_renderer_render
+    chord_frame* frames[2];                                         // async resolve: one frame per history slot; otherwise frames[0] only
+    // CHORD_RENDERER_ASYNC_RESOLVE: visibilityMark + lighting of frame N run on `resolveStream` while the context stream
+    // already runs the visibility passes of frame N + 1 (they touch disjoint state: the two frames, post[p])
+    bool async; cudaStream_t resolveStream; cudaEvent_t geomDone[2], resolveDone[2]; bool resolvePending[2];
+    chord_graph* graphResolve[2];
     chord_cmdlist* post[2]; chord_cmdlist* visible; chord_cmdlist* rejected; chord_cmdlist* visible1;
     uint32_t listCapacity;
     chord_hzb* tmpHzb; chord_hzb* hist[2];
@@ -114,6 +119,7 @@ static void drop_graphs(chord_renderer* r)
 {
     for (int p = 0; p < 2; p++) {
         if (r->graph[p]) { chord_graph_destroy(r->graph[p]); r->graph[p] = nullptr; }
+        if (r->graphResolve[p]) { chord_graph_destroy(r->graphResolve[p]); r->graphResolve[p] = nullptr; }
         r->graphLaunched[p] = false;
     }
     r->eagerWithHistory = 0;
@@ -139,9 +145,10 @@ static int record_event(chord_renderer* r, int i)
 
 static int nccl_allgather_history(chord_renderer* r, chord_hzb* h);
 
-// the frame sequence itself (eager, or while the context is capturing)
-static int record_frame(chord_renderer* r, uint32_t p, const chord_PerframeCameraView* view, const chord_InstanceCullingViewInfo* iview,
-                        const chord_GPUObjectGLTFPrimitive* objects, uint32_t objectCount, uint32_t lod0, uint32_t groups)
+// the frame sequence itself (eager, or while the context is capturing), in two parts: the visibility passes up to the history
+// HZB, and the resolve (visibilityMark + lighting)
+static int record_geometry(chord_renderer* r, uint32_t p, const chord_PerframeCameraView* view, const chord_InstanceCullingViewInfo* iview,
+                           const chord_GPUObjectGLTFPrimitive* objects, uint32_t objectCount, uint32_t lod0, uint32_t groups)
 {
     chord_frame* f = r->frame;
     int rc = chord_frame_begin(f, view, iview, objects, objectCount, lod0, groups, r->tiled ? &r->tile : nullptr);      // uniforms + addClearGbufferPass
@@ -174,7 +181,13 @@ static int record_frame(chord_renderer* r, uint32_t p, const chord_PerframeCamer
         if ((rc = chord_build_hzb(f, 1, 1, 1, hzb))) return rc;
         if (r->mode == 2 && (rc = nccl_allgather_history(r, hzb))) return rc;
     }
-    if ((rc = record_event(r, 5))) return rc;
+    return record_event(r, 5);
+}
+
+static int record_resolve(chord_renderer* r, uint32_t p)
+{
+    chord_frame* f = r->frame;
+    int rc;
     if (r->flags & CHORD_RENDERER_RESOLVE) {
         if ((rc = chord_visibility_mark(f, r->post[p]))) return rc;
         if ((rc = record_event(r, 6))) return rc;
@@ -183,6 +196,25 @@ static int record_frame(chord_renderer* r, uint32_t p, const chord_PerframeCamer
     if ((rc = record_event(r, 7))) return rc;
     r->timersRecorded = (r->flags & CHORD_RENDERER_TIMERS) != 0u;
     return CHORD_OK;
+}
+
+static int record_frame(chord_renderer* r, uint32_t p, const chord_PerframeCameraView* view, const chord_InstanceCullingViewInfo* iview,
+                        const chord_GPUObjectGLTFPrimitive* objects, uint32_t objectCount, uint32_t lod0, uint32_t groups)
+{
+    const int rc = record_geometry(r, p, view, iview, objects, objectCount, lod0, groups);
+    return rc ? rc : record_resolve(r, p);
+}
+
+// Runs `fn` with the context's stream pointing at the resolve stream: every launcher of the library enqueues on ctx->stream, so
+// this is how a pass is moved to the second stream (host code is single-threaded per context).
+template <typename Fn>
+static int on_resolve_stream(chord_renderer* r, Fn fn)
+{
+    cudaStream_t main = r->ctx->stream;
+    r->ctx->stream = r->resolveStream;
+    const int rc = fn();
+    r->ctx->stream = main;
+    return rc;
 }
 
 static int nccl_allgather_history(chord_renderer* r, chord_hzb* h)
@@ -216,8 +248,24 @@ int chord_renderer_create(chord_ctx* ctx, uint32_t width, uint32_t height, uint3
     r->tile = chord_rect{0, 0, width, height};
     const int rc = [&]() -> int {
         int e;
-        if ((e = chord_frame_create(ctx, width, height, &r->frame))) return e;
-        if ((e = chord_frame_set_gbuffer_packed(r->frame, (flags & CHORD_RENDERER_PACKED_GBUFFER) ? 1 : 0))) return e;
+        // timers serialise the passes they measure: the asynchronous resolve is for renderers without them
+        r->async = (flags & CHORD_RENDERER_ASYNC_RESOLVE) && (flags & CHORD_RENDERER_RESOLVE) && !(flags & CHORD_RENDERER_TIMERS);
+        for (int k = 0; k < (r->async ? 2 : 1); k++) {
+            if ((e = chord_frame_create(ctx, width, height, &r->frames[k]))) return e;
+            if ((e = chord_frame_set_gbuffer_packed(r->frames[k], (flags & CHORD_RENDERER_PACKED_GBUFFER) ? 1 : 0))) return e;
+        }
+        r->frame = r->frames[0];
+        if (r->async) {
+            // the resolve yields to the context stream (created with the greatest priority, chord_ctx_create): CTAs of the
+            // latency-bound visibility passes are scheduled ahead of the resolve's whenever both are pending
+            int least = 0, greatest = 0;
+            CHORD_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+            CHORD_CUDA(cudaStreamCreateWithPriority(&r->resolveStream, cudaStreamNonBlocking, least));
+            for (int k = 0; k < 2; k++) {
+                CHORD_CUDA(cudaEventCreateWithFlags(&r->geomDone[k], cudaEventDisableTiming));
+                CHORD_CUDA(cudaEventCreateWithFlags(&r->resolveDone[k], cudaEventDisableTiming));
+            }
+        }
         if ((e = chord_hzb_create(ctx, width, height, &r->tmpHzb))) return e;
         if ((e = chord_hzb_create(ctx, width, height, &r->hist[0]))) return e;
         if ((e = chord_hzb_create(ctx, width, height, &r->hist[1]))) return e;
@@ -248,9 +296,12 @@ void chord_renderer_destroy(chord_renderer* r)
     if (!r) return;
     cudaSetDevice(r->ctx->device);
     cudaStreamSynchronize(r->ctx->stream);
+    if (r->resolveStream) cudaStreamSynchronize(r->resolveStream);
     drop_graphs(r);
     exchange_teardown(r);
-    chord_frame_destroy(r->frame);
+    chord_frame_destroy(r->frames[0]); chord_frame_destroy(r->frames[1]);
+    if (r->resolveStream) cudaStreamDestroy(r->resolveStream);
+    for (int k = 0; k < 2; k++) { if (r->geomDone[k]) cudaEventDestroy(r->geomDone[k]); if (r->resolveDone[k]) cudaEventDestroy(r->resolveDone[k]); }
     chord_cmdlist** all[5] = { &r->post[0], &r->post[1], &r->visible, &r->rejected, &r->visible1 };
     for (auto l : all) chord_cmdlist_destroy(*l);
     chord_hzb_destroy(r->tmpHzb); chord_hzb_destroy(r->hist[0]); chord_hzb_destroy(r->hist[1]);
@@ -302,6 +353,11 @@ int chord_renderer_render(chord_renderer* r, const chord_PerframeCameraView* vie
     const bool same = r->sig.valid && memcmp(&s, &r->sig, sizeof(s)) == 0;
     if (!same) { drop_graphs(r); memset(&r->sig, 0, sizeof(r->sig)); r->sig = s; }
     const bool wantGraph = (r->flags & CHORD_RENDERER_GRAPH) != 0u && r->historyValid;
+    if (r->async) {
+        // this slot's frame was last read by the resolve of two frames ago, which may still be running on the resolve stream
+        r->frame = r->frames[p];
+        if (r->resolvePending[p]) CHORD_CUDA(cudaStreamWaitEvent(ctx->stream, r->resolveDone[p], 0));
+    }
     if (wantGraph && r->graph[p]) {
         // replay: rewrite the pinned uniform snapshot once the previous replay of THIS graph (two frames ago) is done with it
         if (r->graphLaunched[p]) CHORD_CUDA(cudaEventSynchronize(r->graphDone[p]));
@@ -309,21 +365,55 @@ int chord_renderer_render(chord_renderer* r, const chord_PerframeCameraView* vie
         if ((rc = chord_graph_launch(r->graph[p]))) return rc;
         CHORD_CUDA(cudaEventRecord(r->graphDone[p], ctx->stream));
         r->graphLaunched[p] = true; r->graphReplays++;
-    } else if (wantGraph && r->eagerWithHistory >= 1u) {
-        // every lazily sized buffer has seen a frame with history: record this slot's graph, then run it
+        if (r->async) {
+            CHORD_CUDA(cudaEventRecord(r->geomDone[p], ctx->stream));
+            CHORD_CUDA(cudaStreamWaitEvent(r->resolveStream, r->geomDone[p], 0));
+            if ((rc = on_resolve_stream(r, [&]() { return chord_graph_launch(r->graphResolve[p]); }))) return rc;
+        }
+    } else if (wantGraph && r->eagerWithHistory >= (r->async ? 2u : 1u)) {
+        // every lazily sized buffer (of this slot's frame, when there are two) has seen a frame with history: record this slot's
+        // graph(s), then run them
         if ((rc = chord_graph_begin_capture(ctx))) return rc;
-        rc = record_frame(r, p, view, iview, objects, objectCount, lod0MeshletCount, meshletGroupCount);
+        rc = r->async ? record_geometry(r, p, view, iview, objects, objectCount, lod0MeshletCount, meshletGroupCount)
+                      : record_frame(r, p, view, iview, objects, objectCount, lod0MeshletCount, meshletGroupCount);
         chord_graph* g = nullptr;
         const int rc2 = chord_graph_end_capture(ctx, &g);
         if (rc) { if (g) chord_graph_destroy(g); return rc; }
         if (rc2) return rc2;
         r->graph[p] = g; r->graphCaptures++;
+        if (r->async) {
+            chord_graph* gr = nullptr;
+            rc = on_resolve_stream(r, [&]() -> int {
+                int e = chord_graph_begin_capture(ctx);
+                if (e) return e;
+                e = record_resolve(r, p);
+                const int e2 = chord_graph_end_capture(ctx, &gr);
+                return e ? e : e2;
+            });
+            if (rc) { if (gr) chord_graph_destroy(gr); return rc; }
+            r->graphResolve[p] = gr;
+        }
         if ((rc = chord_graph_launch(g))) return rc;
         CHORD_CUDA(cudaEventRecord(r->graphDone[p], ctx->stream));
         r->graphLaunched[p] = true;
+        if (r->async) {
+            CHORD_CUDA(cudaEventRecord(r->geomDone[p], ctx->stream));
+            CHORD_CUDA(cudaStreamWaitEvent(r->resolveStream, r->geomDone[p], 0));
+            if ((rc = on_resolve_stream(r, [&]() { return chord_graph_launch(r->graphResolve[p]); }))) return rc;
+        }
+    } else if (r->async) {
+        if ((rc = record_geometry(r, p, view, iview, objects, objectCount, lod0MeshletCount, meshletGroupCount))) return rc;
+        CHORD_CUDA(cudaEventRecord(r->geomDone[p], ctx->stream));
+        CHORD_CUDA(cudaStreamWaitEvent(r->resolveStream, r->geomDone[p], 0));
+        if ((rc = on_resolve_stream(r, [&]() { return record_resolve(r, p); }))) return rc;
+        if (r->historyValid) r->eagerWithHistory++;
     } else {
         if ((rc = record_frame(r, p, view, iview, objects, objectCount, lod0MeshletCount, meshletGroupCount))) return rc;
         if (r->historyValid) r->eagerWithHistory++;
+    }
+    if (r->async) {
+        CHORD_CUDA(cudaEventRecord(r->resolveDone[p], r->resolveStream));
+        r->resolvePending[p] = true;
     }
     r->hist[p]->valid = 1;
     r->historyValid = true;                                                     // m_rendererHistory.hzbCtx = hzbCtx (renderer.cpp:489)
@@ -331,7 +421,17 @@ int chord_renderer_render(chord_renderer* r, const chord_PerframeCameraView* vie
     return CHORD_OK;
 }
 
-chord_frame* chord_renderer_frame(chord_renderer* r) { return r ? r->frame : nullptr; }
+chord_frame* chord_renderer_frame(chord_renderer* r)
+{
+    if (!r) return nullptr;
+    // asynchronous resolve: whatever the caller enqueues on the context stream next (read-backs, its own passes) is ordered
+    // after the resolve of the frame it asks for
+    if (r->async && r->frameIndex) {
+        const uint32_t p = (r->frameIndex - 1u) & 1u;
+        if (r->resolvePending[p]) { cudaSetDevice(r->ctx->device); cudaStreamWaitEvent(r->ctx->stream, r->resolveDone[p], 0); }
+    }
+    return r->frame;
+}
 chord_cmdlist* chord_renderer_post_cull(chord_renderer* r) { return (r && r->frameIndex) ? r->post[(r->frameIndex - 1u) & 1u] : nullptr; }
 chord_hzb* chord_renderer_history_hzb(chord_renderer* r) { return (r && r->historyValid) ? r->hist[(r->frameIndex - 1u) & 1u] : nullptr; }
 uint64_t chord_renderer_graph_replays(const chord_renderer* r) { return r ? r->graphReplays : 0; }

@@ -542,7 +542,7 @@ class Frame:
         return lib().chord_frame_vis64_ptr(self.h)
 
 
-RENDERER_RESOLVE, RENDERER_PACKED_GBUFFER, RENDERER_BVH, RENDERER_GRAPH, RENDERER_TIMERS = 1, 2, 4, 8, 16
+RENDERER_RESOLVE, RENDERER_PACKED_GBUFFER, RENDERER_BVH, RENDERER_GRAPH, RENDERER_TIMERS, RENDERER_ASYNC_RESOLVE = 1, 2, 4, 8, 16, 32
 PASS_LABELS = ['GLTF Instance Culling', 'GLTF Visibility Stage0', 'BuildHZB Post Prepass Stage0', 'GLTF Visibility Stage1',
                'BuildHZB', 'VisibilityTileMarker', 'lightingTile']           # renderer.cpp:322-363 timer labels
 
@@ -579,21 +579,31 @@ class Renderer:
     as CUDA graphs and replayed, optionally one rank of a tile-parallel frame (fused peer-store or NCCL exchange of the
     history HZB)."""
 
-    def __init__(self, ctx, width, height, resolve=False, packed_gbuffer=False, bvh=False, graph=False, timers=False):
+    def __init__(self, ctx, width, height, resolve=False, packed_gbuffer=False, bvh=False, graph=False, timers=False, async_resolve=False):
         self.ctx, self.width, self.height = ctx, int(width), int(height)
         flags = (RENDERER_RESOLVE if resolve else 0) | (RENDERER_PACKED_GBUFFER if packed_gbuffer else 0) | (RENDERER_BVH if bvh else 0) \
-            | (RENDERER_GRAPH if graph else 0) | (RENDERER_TIMERS if timers else 0)
+            | (RENDERER_GRAPH if graph else 0) | (RENDERER_TIMERS if timers else 0) | (RENDERER_ASYNC_RESOLVE if async_resolve else 0)
         self.h = C.c_void_p()
         lib().chord_renderer_create(ctx.h, C.c_uint32(width), C.c_uint32(height), C.c_uint32(flags), C.byref(self.h))
-        self.frame = Frame(ctx, width, height, _borrowed=lib().chord_renderer_frame(self.h))
+        self._frames = {}
         self.tile = (0, 0, self.width, self.height)
         self.rank, self.world = 0, 1
         self._keep = None
         self._lod0 = 0
 
+    @property
+    def frame(self):
+        """The frame of the most recent render() (with async_resolve: one of two; the context stream is ordered after its resolve)."""
+        p = lib().chord_renderer_frame(self.h)
+        if p not in self._frames:
+            self._frames[p] = Frame(self.ctx, self.width, self.height, _borrowed=p)
+        return self._frames[p]
+
     def close(self):
         if self.h:
-            self.frame.close()
+            for f in self._frames.values():
+                f.close()
+            self._frames = {}
             lib().chord_renderer_destroy(self.h)
             self.h = C.c_void_p()
 

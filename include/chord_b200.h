@@ -337,9 +337,16 @@ int   chord_frame_dims(const chord_frame* frame, uint32_t* w, uint32_t* h);
  *                                  per frame.  The first two frames (and the frame after any change of object count, totals,
  *                                  tile, switch flags or cameraFovy) run eagerly.
  *   CHORD_RENDERER_TIMERS          GPU timers at the reference's seven cut points (renderer.cpp:322-363; the timer lambda of
- *                                  GLTFRenderContext, gltf_rendering.h:15-35), read with chord_renderer_pass_times */
+ *                                  GLTFRenderContext, gltf_rendering.h:15-35), read with chord_renderer_pass_times
+ *   CHORD_RENDERER_ASYNC_RESOLVE   visibilityMark + lighting of frame N run on a second, lower-priority stream while the context
+ *                                  stream already runs the visibility passes of frame N + 1 (two frames in flight, one per history
+ *                                  slot; the reference submits everything to one graphics queue).  The latency-bound cull / raster
+ *                                  / HZB kernels leave most issue slots of a B200 idle, the ALU-bound resolve fills them.  Results
+ *                                  are identical; chord_renderer_frame orders the context stream after the resolve of the frame it
+ *                                  returns.  Needs CHORD_RENDERER_RESOLVE; ignored with CHORD_RENDERER_TIMERS (timers serialise). */
 typedef struct chord_renderer chord_renderer;
-enum { CHORD_RENDERER_RESOLVE = 1u, CHORD_RENDERER_PACKED_GBUFFER = 2u, CHORD_RENDERER_BVH = 4u, CHORD_RENDERER_GRAPH = 8u, CHORD_RENDERER_TIMERS = 16u };
+enum { CHORD_RENDERER_RESOLVE = 1u, CHORD_RENDERER_PACKED_GBUFFER = 2u, CHORD_RENDERER_BVH = 4u, CHORD_RENDERER_GRAPH = 8u, CHORD_RENDERER_TIMERS = 16u,
+       CHORD_RENDERER_ASYNC_RESOLVE = 32u };
 int  chord_renderer_create(chord_ctx* ctx, uint32_t width, uint32_t height, uint32_t flags, chord_renderer** out);
 void chord_renderer_destroy(chord_renderer* renderer);
 /* NULL = the full frame; otherwise cull (through the instance view the caller passes), raster, HZB and resolve are restricted to the rect */

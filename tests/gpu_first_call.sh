@@ -46,4 +46,5 @@ timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_li
     python bench.py --frame-only --steps 2 > /dev/null 2>&1
 timeout 400 ncu --set full --clock-control none --import-source on -k 'regex:k_raster_deferred|k_raster_large|k_hzb_build|k_tile_marker|k_group_cull' -s 15 -c 5 -f -o gpurun_out/frame_misc \
     python bench.py --frame-only --steps 2 > /dev/null 2>&1
+timeout 120 python tests/pcie_probe.py > gpurun_out/pcie.json 2>&1; cat gpurun_out/pcie.json
 ls -la gpurun_out

@@ -1164,6 +1164,53 @@ def test_native_renderer_graph_replay(gpu_ctx):
     eager.close(); graph.close()
 
 
+@pytest.mark.parametrize('use_graph', [False, True])
+def test_native_renderer_async_resolve(gpu_ctx, use_graph):
+    """CHORD_RENDERER_ASYNC_RESOLVE: visibilityMark + lighting of frame N on a second stream while the context stream runs the
+    visibility passes of frame N + 1 (two frames in flight).  Same results as the serial renderer: per frame when every frame
+    is read back, and for the last frame + its history after a run of frames enqueued without touching any result."""
+    if use_graph and _is_host_executor():
+        pytest.skip('CUDA graphs are not modelled by the host executor')
+    from cases import city_frames
+    w, h = 640, 360
+    scene, info, frames = city_frames(frames=9, w=w, h=h)
+    gpu_ctx.upload_scene(scene)
+    tr, ir = synth.synthetic_luts()
+    sc, _ = synth.synthetic_scattering_luts()
+    gpu_ctx.upload_luts(tr, ir)
+    gpu_ctx.upload_scattering(sc)
+    try:
+        serial = runtime.Renderer(gpu_ctx, w, h, resolve=True)
+        a_sync = runtime.Renderer(gpu_ctx, w, h, resolve=True, graph=use_graph, async_resolve=True)
+        last = None
+        for i, f in enumerate(frames):
+            a = (f['view'], f['iview'], f['objects'], info['lod0MeshletCount'], info['meshletGroupCount'])
+            serial.render(*a); a_sync.render(*a)
+            _assert_lists_equal(a_sync.post_cull.readback(), serial.post_cull.readback(), f'async frame {i}')
+            _assert_vis_equal(a_sync.frame.vis64(), serial.frame.vis64(), f'async frame {i}')
+            last = [serial.frame.gbuffer(k) for k in range(6)]
+            for k in range(6):
+                assert np.array_equal(a_sync.frame.gbuffer(k).view(np.uint32), last[k].view(np.uint32)), f'resolve plane {k} of frame {i}'
+            assert np.array_equal(a_sync.frame.tile_marker(), serial.frame.tile_marker())
+        assert last[0].max() > 0.01
+        if use_graph:
+            assert a_sync.graph_replays >= 2, a_sync.graph_replays
+        a_sync.close()
+        # the same frames enqueued back to back: nothing is read until the end, so resolves and visibility passes overlap
+        a_sync = runtime.Renderer(gpu_ctx, w, h, resolve=True, graph=use_graph, async_resolve=True)
+        for f in frames:
+            a_sync.render(f['view'], f['iview'], f['objects'], info['lod0MeshletCount'], info['meshletGroupCount'])
+        _assert_lists_equal(a_sync.post_cull.readback(), serial.post_cull.readback(), 'async run, last frame')
+        _assert_vis_equal(a_sync.frame.vis64(), serial.frame.vis64(), 'async run, last frame')
+        for k in range(6):
+            assert np.array_equal(a_sync.frame.gbuffer(k).view(np.uint32), last[k].view(np.uint32)), f'async run: resolve plane {k} of the last frame'
+        for which in ('min', 'max'):
+            assert np.array_equal(a_sync.history_hzb.readback_chain(which), serial.history_hzb.readback_chain(which)), f'async run: history {which} chain'
+        a_sync.close(); serial.close()
+    finally:
+        gpu_ctx.upload_scattering(None)
+
+
 def _tile_case(gpu_ctx, world, w, h, frames_n):
     from cases import city_frames
     from chord_b200 import multigpu

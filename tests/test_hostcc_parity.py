@@ -100,6 +100,10 @@ def test_native_renderer_camera_path(host_ctx, cases):
     cases.test_native_renderer_camera_path(host_ctx)
 
 
+def test_native_renderer_async_resolve(host_ctx, cases):
+    cases.test_native_renderer_async_resolve(host_ctx, False)
+
+
 def test_renderer_fused_exchange_in_process(host_ctx, cases):
     cases.test_renderer_fused_exchange_in_process(host_ctx, world=2)
     cases.test_renderer_fused_exchange_in_process(host_ctx, world=4)
