@@ -181,7 +181,11 @@ static int record_geometry(chord_renderer* r, uint32_t p, const chord_PerframeCa
         if ((rc = chord_build_hzb(f, 1, 1, 1, hzb))) return rc;
         if (r->mode == 2 && (rc = nccl_allgather_history(r, hzb))) return rc;
     }
-    return record_event(r, 5);
+    if ((rc = record_event(r, 5))) return rc;
+    // asynchronous resolve: the tile classification (memory-latency bound, 8 B / pixel) stays on the context stream with the
+    // other visibility passes; the second stream gets the ALU-bound part only
+    if (r->async && (rc = chord_visibility_mark(f, r->post[p]))) return rc;
+    return CHORD_OK;
 }
 
 static int record_resolve(chord_renderer* r, uint32_t p)
@@ -189,7 +193,7 @@ static int record_resolve(chord_renderer* r, uint32_t p)
     chord_frame* f = r->frame;
     int rc;
     if (r->flags & CHORD_RENDERER_RESOLVE) {
-        if ((rc = chord_visibility_mark(f, r->post[p]))) return rc;
+        if (!r->async && (rc = chord_visibility_mark(f, r->post[p]))) return rc;
         if ((rc = record_event(r, 6))) return rc;
         if ((rc = chord_lighting(f, r->post[p]))) return rc;
     } else if ((rc = record_event(r, 6))) return rc;

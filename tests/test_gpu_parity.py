@@ -254,6 +254,9 @@ def test_tile_scissor(gpu_ctx):
         acc |= part
         ot, _ = oracle.Frame(scene, view, iview, objects, w, h, tile=tile).render_mesh(cmds)
         _assert_vis_equal(part, ot, f'tile {tile}')
+        # tile classification of a tiled frame: 8x8 tiles outside the rect are marked 'no geometry' without being read
+        fr.visibility_mark(lst)
+        assert np.array_equal(fr.tile_marker(), oracle.Frame(scene, view, iview, objects, w, h, tile=tile).visibility_mark(ot, cmds)), f'marker of tile {tile}'
     _assert_vis_equal(acc, full, 'union of tiles')
 
 
