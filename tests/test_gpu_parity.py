@@ -387,6 +387,21 @@ def test_sky_branch(gpu_ctx):
                 assert hits.sum() > 5000 and (empty & ~hits).sum() > 5000, (hits.sum(), empty.sum())
             for k in range(1, 6):
                 assert not g[k][empty].any()
+        # viewer in space (GetSkyRadiance moves it to the top of the atmosphere along the ray; rays that miss the atmosphere
+        # return black) and viewer just under the top boundary
+        from chord_b200 import abi
+        for dist_km in (6500.0, 6419.0):
+            view = cam.fill_view(camera)
+            cam_km = np.array([0.0, dist_km - 6360.0, 0.0])
+            view['cameraPositionWS_km'] = abi.double3_to_storage(cam_km)
+            view['cameraToEarthCenter_km'] = abi.double3_to_storage(cam_km - np.array([0.0, -6360.0, 0.0]))
+            gpu_ctx.upload_scattering(sc, None)
+            fr, g, _, ovis = _sky_frame_on_s1(gpu_ctx, view, tr, ir, sc, None)
+            _assert_gbuffer_equal(fr, g)
+            empty = (ovis & 0xFFFFFFFF) == 0
+            if dist_km > 6420.0:
+                black = empty & ~g[0][..., :3].any(axis=-1)
+                assert black.sum() > 500 and (empty & ~black).sum() > 500, (black.sum(), empty.sum())
         # luminance mode (skySpectralRadianceToLumiance, the 1e-5 exposure factor) and the packed colour format
         view = cam.fill_view(camera)
         view['basicData']['atmosphere']['luminanceMode'] = 1
