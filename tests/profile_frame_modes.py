@@ -26,6 +26,18 @@ def main():
     lod0, groups = info['lod0MeshletCount'], info['meshletGroupCount']
     steps, warm = 20, 6
     frames = bench.city_camera_path(camera, info, steps + warm, w, h)
+    if '--ncu-tile' in sys.argv:
+        # for `ncu --metrics gpu__time_duration.sum`: the tile's frames with eager launches, so that every kernel is a row
+        tile = multigpu.all_tiles(8, w, h)[0]
+        r = runtime.Renderer(ctx, w, h, resolve=True, packed_gbuffer=True, graph=False)
+        r.set_tile(tile)
+        for i in range(8):
+            c, objs, view, iview = frames[i]
+            r.render(view, multigpu.tile_instance_view(view, c, tile), objs, lod0, groups)
+        _ = r.frame
+        torch.cuda.synchronize()
+        r.close()
+        return
     out = {}
     for label, tile in (('full', None), ('tile_1_of_8', multigpu.all_tiles(8, w, h)[0])):
         ivs = [multigpu.tile_instance_view(view, c, tile) if tile else iview for (c, objs, view, iview) in frames]
