@@ -81,6 +81,7 @@ struct chord_renderer {
     // CHORD_RENDERER_ASYNC_RESOLVE: visibilityMark + lighting of frame N run on `resolveStream` while the context stream
     // already runs the visibility passes of frame N + 1 (they touch disjoint state: the two frames, post[p])
     bool async; cudaStream_t resolveStream; cudaEvent_t geomDone[2], resolveDone[2]; bool resolvePending[2];
+    cudaStream_t auxStream; cudaEvent_t auxFork, auxJoin;            // fused exchange: the consumer-side wait runs beside the instance culling
     chord_graph* graphResolve[2];
     chord_cmdlist* post[2]; chord_cmdlist* visible; chord_cmdlist* rejected; chord_cmdlist* visible1;
     uint32_t listCapacity;
@@ -151,10 +152,27 @@ static int record_geometry(chord_renderer* r, uint32_t p, const chord_PerframeCa
                            const chord_GPUObjectGLTFPrimitive* objects, uint32_t objectCount, uint32_t lod0, uint32_t groups)
 {
     chord_frame* f = r->frame;
-    int rc = chord_frame_begin(f, view, iview, objects, objectCount, lod0, groups, r->tiled ? &r->tile : nullptr);      // uniforms + addClearGbufferPass
-    if (rc) return rc;
+    chord_ctx* ctx = r->ctx;
+    int rc;
     chord_hzb* last = r->historyValid ? r->hist[p ^ 1u] : nullptr;
-    if (last && r->mode == 1) {
+    const bool forkWait = last && r->mode == 1 && r->auxStream && !(r->flags & CHORD_RENDERER_TIMERS);
+    if (forkWait) {
+        // fused exchange, consumer side, on a stream of its own: the wait for the peers' arrival flags (the slowest rank of last
+        // frame) and the rebuild of mips 6.. run beside this frame's uniform upload, clear and instance culling, none of which
+        // reads the history; the first reader (phase-0 cull below) joins
+        CHORD_CUDA(cudaEventRecord(r->auxFork, ctx->stream));
+        CHORD_CUDA(cudaStreamWaitEvent(r->auxStream, r->auxFork, 0));
+        const HzbExchange ex = make_exchange(r, p ^ 1u);
+        cudaStream_t main = ctx->stream;
+        ctx->stream = r->auxStream;
+        rc = launch_hzb_exchange_wait_top(f, last, &ex, r->world, r->dStatus);
+        ctx->stream = main;
+        if (rc) return rc;
+        CHORD_CUDA(cudaEventRecord(r->auxJoin, r->auxStream));
+    }
+    rc = chord_frame_begin(f, view, iview, objects, objectCount, lod0, groups, r->tiled ? &r->tile : nullptr);      // uniforms + addClearGbufferPass
+    if (rc) return rc;
+    if (last && r->mode == 1 && !forkWait) {
         // fused exchange, consumer side: all peers' parts of last frame's chain have landed; rebuild mips 6.. from them
         const HzbExchange ex = make_exchange(r, p ^ 1u);
         if ((rc = launch_hzb_exchange_wait_top(f, last, &ex, r->world, r->dStatus))) return rc;
@@ -162,6 +180,7 @@ static int record_geometry(chord_renderer* r, uint32_t p, const chord_PerframeCa
     if ((rc = record_event(r, 0))) return rc;
     rc = (r->flags & CHORD_RENDERER_BVH) ? chord_instance_culling_bvh(f, r->post[p]) : chord_instance_culling(f, r->post[p]);
     if (rc) return rc;
+    if (forkWait) CHORD_CUDA(cudaStreamWaitEvent(ctx->stream, r->auxJoin, 0));
     if ((rc = record_event(r, 1))) return rc;
     int need1 = 0;
     if ((rc = chord_visibility_stage0(f, last, r->post[p], r->visible, r->rejected, &need1))) return rc;     // mesh_raster.cpp:269-312
@@ -305,6 +324,7 @@ void chord_renderer_destroy(chord_renderer* r)
     exchange_teardown(r);
     chord_frame_destroy(r->frames[0]); chord_frame_destroy(r->frames[1]);
     if (r->resolveStream) cudaStreamDestroy(r->resolveStream);
+    if (r->auxStream) { cudaStreamSynchronize(r->auxStream); cudaStreamDestroy(r->auxStream); cudaEventDestroy(r->auxFork); cudaEventDestroy(r->auxJoin); }
     for (int k = 0; k < 2; k++) { if (r->geomDone[k]) cudaEventDestroy(r->geomDone[k]); if (r->resolveDone[k]) cudaEventDestroy(r->resolveDone[k]); }
     chord_cmdlist** all[5] = { &r->post[0], &r->post[1], &r->visible, &r->rejected, &r->visible1 };
     for (auto l : all) chord_cmdlist_destroy(*l);
@@ -567,6 +587,13 @@ int chord_renderer_exchange_connect(chord_renderer* r, uint32_t rank, uint32_t w
     CHORD_CUDA(cudaMalloc(&r->dPeers, sizeof(host)));
     CHORD_CUDA(cudaMemcpy(r->dPeers, host, sizeof(host), cudaMemcpyHostToDevice));
     CHORD_CUDA(cudaMemset(r->dStatus, 0, 16));
+    if (!r->auxStream) {
+        int least = 0, greatest = 0;
+        CHORD_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+        CHORD_CUDA(cudaStreamCreateWithPriority(&r->auxStream, cudaStreamNonBlocking, greatest));
+        CHORD_CUDA(cudaEventCreateWithFlags(&r->auxFork, cudaEventDisableTiming));
+        CHORD_CUDA(cudaEventCreateWithFlags(&r->auxJoin, cudaEventDisableTiming));
+    }
     r->mode = 1;
     r->historyValid = false; r->hist[0]->valid = r->hist[1]->valid = 0; r->frameIndex = 0;
     return CHORD_OK;

@@ -53,6 +53,12 @@ public:
     // material textures of the masked bucket (bindless Texture2D / SamplerState ids -> table indices)
     void uploadTextures(const chord_texture_desc* tex, uint32_t nTex, const chord_sampler_desc* smp, uint32_t nSmp)
     { check(chord_textures_upload(m_ctx, tex, nTex, smp, nSmp), "chord_textures_upload"); }
+    // AtmosphereLut of the lighting pass: transmittance 256 x 64 + irradiance 64 x 16 (PBR turn), scattering / optional single-Mie
+    // volumes 256 x 128 x 32 (sky turn; leave them out and texels without geometry keep the cleared value), all RGBA16F
+    void uploadAtmosphereLuts(const uint16_t* transmittance, const uint16_t* irradiance)
+    { const chord_atmosphere_luts l = { transmittance, irradiance }; check(chord_atmosphere_luts_upload(m_ctx, &l), "chord_atmosphere_luts_upload"); }
+    void uploadScattering(const uint16_t* scattering, const uint16_t* singleMie = nullptr)
+    { check(chord_atmosphere_scattering_upload(m_ctx, scattering, singleMie), "chord_atmosphere_scattering_upload"); }
     void setSwitchFlags(uint32_t f) { check(chord_ctx_set_switch_flags(m_ctx, f), "chord_ctx_set_switch_flags"); }
     void sync() { check(chord_ctx_sync(m_ctx), "chord_ctx_sync"); }
     void* stream() const { return chord_ctx_stream(m_ctx); }
