@@ -314,7 +314,8 @@ int launch_build_hzb(chord_frame* f, int bMin, int bMax, int bRange, chord_hzb* 
 int launch_hzb_range_reduce(chord_ctx* ctx, const uint32_t* pairs, uint32_t world, uint32_t* validRange);
 int launch_hzb_exchange_wait_top(chord_frame* f, chord_hzb* dst, const HzbExchange* exchange, uint32_t world, uint32_t* status);
 int launch_visibility_mark(chord_frame* f, chord_cmdlist* post);
-int launch_lighting(chord_frame* f, chord_cmdlist* post);
+enum { CHORD_LIGHTING_PREPARE = 1u, CHORD_LIGHTING_SHADE = 2u };
+int launch_lighting(chord_frame* f, chord_cmdlist* post, uint32_t parts = CHORD_LIGHTING_PREPARE | CHORD_LIGHTING_SHADE);
 int launch_split_vis(chord_frame* f, uint32_t* vis32, float* depth32);
 int launch_decode(chord_frame* f, chord_cmdlist* post, uint32_t* triples);
 int launch_selftest_vertex_records(chord_ctx* ctx, uint32_t n, uint32_t seed, uint32_t width, uint32_t height, uint32_t clampZ, unsigned long long* dOut);

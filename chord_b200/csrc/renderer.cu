@@ -203,7 +203,10 @@ static int record_geometry(chord_renderer* r, uint32_t p, const chord_PerframeCa
     if ((rc = record_event(r, 5))) return rc;
     // asynchronous resolve: the tile classification (memory-latency bound, 8 B / pixel) stays on the context stream with the
     // other visibility passes; the second stream gets the ALU-bound part only
-    if (r->async && (rc = chord_visibility_mark(f, r->post[p]))) return rc;
+    if (r->async) {
+        if ((rc = chord_visibility_mark(f, r->post[p]))) return rc;
+        if ((rc = launch_lighting(f, r->post[p], CHORD_LIGHTING_PREPARE))) return rc;      // tile list + resolve records: same stream
+    }
     return CHORD_OK;
 }
 
@@ -214,7 +217,10 @@ static int record_resolve(chord_renderer* r, uint32_t p)
     if (r->flags & CHORD_RENDERER_RESOLVE) {
         if (!r->async && (rc = chord_visibility_mark(f, r->post[p]))) return rc;
         if ((rc = record_event(r, 6))) return rc;
-        if ((rc = chord_lighting(f, r->post[p]))) return rc;
+        if (r->async) {
+            CHORD_REQUIRE(f->ctx->lutTransmittance && f->ctx->lutIrradiance, "atmosphere LUTs not uploaded");
+            if ((rc = launch_lighting(f, r->post[p], CHORD_LIGHTING_SHADE))) return rc;
+        } else if ((rc = chord_lighting(f, r->post[p]))) return rc;
     } else if ((rc = record_event(r, 6))) return rc;
     if ((rc = record_event(r, 7))) return rc;
     r->timersRecorded = (r->flags & CHORD_RENDERER_TIMERS) != 0u;
