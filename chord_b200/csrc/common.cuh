@@ -320,6 +320,7 @@ int launch_split_vis(chord_frame* f, uint32_t* vis32, float* depth32);
 int launch_decode(chord_frame* f, chord_cmdlist* post, uint32_t* triples);
 int launch_selftest_vertex_records(chord_ctx* ctx, uint32_t n, uint32_t seed, uint32_t width, uint32_t height, uint32_t clampZ, unsigned long long* dOut);
 int scan_reset(chord_ctx* ctx, uint32_t tilesNeeded);
+int launch_fill_u32(chord_ctx* ctx, void* dst, uint32_t v0, uint32_t v1, size_t words);    // ctx.cu: small fills as kernels (cheaper graph nodes than memsets)
 int build_meshlet_packs(chord_ctx* ctx, DatasDev* d, uint32_t datasId, uint32_t meshletCount, uint32_t vertexCount, uint32_t groupCount, uint32_t groupIndicesCount,
                         const chord_GLTFPrimitiveBuffer* dPrims, uint32_t nPrims, void** outAllocs);
 size_t lighting_view_bytes();                                                     // resolve.cu: sizeof(LightingView)

@@ -634,7 +634,7 @@ static int launch_instance_culling_impl(chord_frame* fr, chord_cmdlist* out, boo
         }
         CHORD_CUDA(cudaMemsetAsync(fr->bvhEntries, 0xFF, sizeof(unsigned long long) * (size_t)cap, ctx->stream));
         CHORD_CUDA(cudaMemsetAsync(fr->bvhBits, 0, sizeof(uint32_t) * (size_t)words, ctx->stream));
-        CHORD_CUDA(cudaMemsetAsync(fr->bvhCtrl, 0, 32, ctx->stream));
+        { const int rcFill = launch_fill_u32(ctx, fr->bvhCtrl, 0u, 0u, 8); if (rcFill) return rcFill; }
         k_bvh_seed<<<(fr->objectCount + 127) / 128, 128, 0, ctx->stream>>>(f, fr->objGroupCount, (unsigned long long*)fr->bvhEntries, cap, fr->bvhCtrl);
         k_bvh_traverse<<<(uint32_t)ctx->smCount * 2u, 128, 0, ctx->stream>>>(f, fr->objGroupBase, (unsigned long long*)fr->bvhEntries, cap, fr->bvhCtrl, fr->bvhBits, fr->bvhWords);
         ctx->launches += 2;

@@ -334,8 +334,8 @@ int launch_build_hzb(chord_frame* fr, int bMin, int bMax, int bRange, chord_hzb*
     }
     p.numBlocks = grid.x * grid.y;
     if (bRange) {
-        static const uint32_t kInit[2] = { ~0u, 0u };                       // hzb.cpp:105-106 (static: a captured graph re-reads it)
-        CHORD_CUDA(cudaMemcpyAsync(dst->validRange, kInit, 8, cudaMemcpyHostToDevice, ctx->stream));
+        const int rcFill = launch_fill_u32(ctx, dst->validRange, ~0u, 0u, 2);   // hzb.cpp:105-106: {min bits, max bits} seed
+        if (rcFill) return rcFill;
     }
     // hzb.cpp:44-47: at least one of min / max, a valid range only with both
     if (bMin && bMax && bRange) k_hzb_build<true, true, true><<<grid, 256, 0, ctx->stream>>>(p);
