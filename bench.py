@@ -456,6 +456,32 @@ def frame_benchmark_tiled(ctx, stream, torch, dist, rank, world, steps=20, width
                 'graph_replays': r.graph_replays,
                 'exchange_bytes_per_frame': int(2 * sum(r.history_hzb.tile_bytes(t_) for t_ in tiles) * (world - 1)),
                 'exchange_timed_out': bool(timed_out)})
+    # ---- where a rank's frame goes: per-pass GPU times of this rank (timers renderer, serial) and the residual of its frame
+    # time - the wait for the slowest rank's arrival flags, graph launch gaps, uniform upload - max / min over the ranks
+    try:
+        rt = runtime.Renderer(ctx, width, height, resolve=True, packed_gbuffer=True, graph=use_graph, timers=True)
+        multigpu.connect_fused(rt, rank, world, dist, tiles)
+        ms_t, _ = timed(rt)
+        acc = {k: 0.0 for k in runtime.PASS_LABELS}
+        for i in range(WARM, len(frames)):
+            c, objs, view, _ = frames[i]
+            rt.render(view, tile_iviews[i], objs, lod0, groups)
+            for k, v in rt.pass_times().items():
+                acc[k] += v
+        n = len(frames) - WARM
+        mine = [acc[k] / n for k in runtime.PASS_LABELS]
+        busy = sum(mine)
+        t = torch.tensor(mine + [busy, ms_t * 1000.0 - busy], dtype=torch.float64, device=dev)
+        tmax, tmin = t.clone(), t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX); dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
+        labels = list(runtime.PASS_LABELS) + ['gpu_busy_sum', 'residual (frame - busy: exchange wait, launch gaps, upload)']
+        out['rank_pass_us'] = {'ms_per_frame_timers': ms_t, 'max_over_ranks': {k: float(v) for k, v in zip(labels, tmax.tolist())},
+                               'min_over_ranks': {k: float(v) for k, v in zip(labels, tmin.tolist())},
+                               'note': 'timers renderer (serial passes, fused exchange); BuildHZB includes the peer stores of the exchange; the per-frame timer '
+                                       'read-back of this untimed pass keeps the ranks in lock step, the frame time is from the timed pass before it'}
+        rt.close()
+    except Exception as e:
+        out['rank_pass_us'] = {'error': repr(e)}
     # ---- parity, untimed: tile vs full frame on this GPU, gathered history vs single-GPU history
     single = runtime.Renderer(ctx, width, height)
     r.clear_history()

@@ -105,8 +105,8 @@ __global__ void __launch_bounds__(256, (kMin && kMax) ? 6 : 8) k_hzb_build(HzbBu
         if (kMax) sMaxP[l] = mx;
         if (x < p.mip0W && y < p.mip0H) {
             const size_t o = p.mipOffset[0] + (size_t)y * p.mip0W + x;
-            if (doMin) { const __half hv = to_half_rtz(mn); p.minChain[o] = hv; for (uint32_t q = 0; q < p.nPeers; q++) p.peers->min[q][o] = hv; }
-            if (doMax) { const __half hv = to_half_rtz(mx); p.maxChain[o] = hv; for (uint32_t q = 0; q < p.nPeers; q++) p.peers->max[q][o] = hv; }
+            if (doMin) p.minChain[o] = to_half_rtz(mn);
+            if (doMax) p.maxChain[o] = to_half_rtz(mx);
         }
     };
     if (evenWidth && bx * 64 + 64 <= p.width && by * 64 + 64 <= p.height) {
@@ -194,10 +194,10 @@ __global__ void __launch_bounds__(256, (kMin && kMax) ? 6 : 8) k_hzb_build(HzbBu
             const uint32_t x = bx * nw + lx, y = by * nw + ly;
             if (x < mw && y < mh) {
                 const size_t o = p.mipOffset[mip] + (size_t)y * mw + x;
-                if (doMin) { const __half hv = to_half_rtz(mn); p.minChain[o] = hv; for (uint32_t q = 0; q < p.nPeers; q++) p.peers->min[q][o] = hv; }
+                if (doMin) p.minChain[o] = to_half_rtz(mn);
                 if (doMax) {
                     const __half hv = (mip == 5) ? half_plus_ulp(to_half_rtz(mx)) : to_half_rtz(mx);
-                    p.maxChain[o] = hv; for (uint32_t q = 0; q < p.nPeers; q++) p.peers->max[q][o] = hv;
+                    p.maxChain[o] = hv;
                 }
             }
         }
@@ -205,7 +205,44 @@ __global__ void __launch_bounds__(256, (kMin && kMax) ? 6 : 8) k_hzb_build(HzbBu
         float* t = srcMin; srcMin = dstMin; dstMin = t; t = srcMax; srcMax = dstMax; dstMax = t;
         w = nw;
     }
-    if (p.nPeers) {
+}
+
+// ---- fused exchange, producer side (multi-GPU) ----------------------------------------------------------------
+// This rank's part of mips 0..5 of both chains - built into its own history chain by k_hzb_build just before - is pushed into
+// the same positions of EVERY peer's chain over NVLink (peer pointers: CUDA IPC / peer access): one warp per (chain, mip, row)
+// of the tile region, 16-byte loads from the local chain (L2 hits) and 16-byte stores per peer, i.e. rows of up to 960
+// contiguous bytes per peer.  (Round 2 first did these stores out of k_hzb_build's own epilogue, one 2-byte store per texel
+// and peer - 64 contiguous bytes per warp instruction and a system-scope fence per 64 x 64 block: ~280 GB/s, 40 us for one
+// peer at 2 GPUs, ~70 us at 8; profiles/r02_o_*.)  The block that finishes last publishes this rank's valid depth range and -
+// after a system-scope fence - its arrival flag to every peer; k_hzb_exchange_wait_top is the consumer.
+struct TileRegion { uint32_t bx0, by0, bx1, by1; };
+__global__ void __launch_bounds__(256) k_hzb_exchange_put(HzbBuildParams p, TileRegion r, uint32_t rowsPerChain, int kRange)
+{
+    const uint32_t tid = threadIdx.x, lane = tid & 31u;
+    const uint32_t warpsPerGrid = gridDim.x * (blockDim.x >> 5);
+    for (uint32_t w = blockIdx.x * (blockDim.x >> 5) + (tid >> 5); w < 2u * rowsPerChain; w += warpsPerGrid) {
+        const uint32_t which = w / rowsPerChain;                       // 0 = min chain, 1 = max chain
+        uint32_t k = w % rowsPerChain, mip = 0;
+        while (k >= (((r.by1 - r.by0) * 32u) >> mip)) { k -= ((r.by1 - r.by0) * 32u) >> mip; mip++; }
+        const uint32_t rw = ((r.bx1 - r.bx0) * 32u) >> mip;            // texels of this row inside the region
+        const uint32_t x0 = (r.bx0 * 32u) >> mip, y = ((r.by0 * 32u) >> mip) + k;
+        const size_t o = p.mipOffset[mip] + (size_t)y * mip_dim(p.mip0W, mip) + x0;
+        const __half* src = (which ? p.maxChain : p.minChain) + o;
+        if (((o | (size_t)rw) & 7u) == 0u) {
+            // (every chain starts on a 256-byte boundary: o % 8 == 0 makes source and destinations 16-byte aligned)
+            const uint4* src16 = reinterpret_cast<const uint4*>(src);
+            for (uint32_t i = lane; i < rw / 8u; i += 32u) {
+                const uint4 v = src16[i];
+                for (uint32_t q = 0; q < p.nPeers; q++) reinterpret_cast<uint4*>((which ? p.peers->max[q] : p.peers->min[q]) + o)[i] = v;
+            }
+        } else {
+            for (uint32_t i = lane; i < rw; i += 32u) {
+                const __half v = src[i];
+                for (uint32_t q = 0; q < p.nPeers; q++) (which ? p.peers->max[q] : p.peers->min[q])[o + i] = v;
+            }
+        }
+    }
+    {
         // "last block done": every block makes its peer stores visible system-wide and counts itself; the block that brings
         // the count to numBlocks knows that every store of this launch (all blocks, all peers) has been performed, publishes
         // this rank's valid depth range and then - after another system-scope fence - the arrival flag of this frame.
@@ -321,12 +358,15 @@ int launch_build_hzb(chord_frame* fr, int bMin, int bMax, int bRange, chord_hzb*
     }
     dim3 grid((dst->mip0W + 31) / 32, (dst->mip0H + 31) / 32);            // hzb.cpp:74
     const bool fullFrame = fr->tile.x0 == 0 && fr->tile.y0 == 0 && fr->tile.x1 == fr->width && fr->tile.y1 == fr->height;
+    TileRegion region = { 0u, 0u, grid.x, grid.y };
+    CHORD_REQUIRE(!(p.nPeers && fullFrame), "an exchanged build renders one screen tile of several");
     if (!fullFrame) {
         // screen-tile partition: build only the blocks this tile owns; everything else reads as 0 (= far,
         // never occludes) until the tiles of the other GPUs are gathered in and chord_hzb_finish_top rebuilds mips 6..
         CHORD_REQUIRE(tile_aligned(fr->tile, fr->width, fr->height), "tile rect must be cut on multiples of 64 px for a tiled HZB build");
         uint32_t bx0, by0, bx1, by1; tile_blocks(dst, fr->tile, fr->width, fr->height, bx0, by0, bx1, by1);
         p.blockX0 = bx0; p.blockY0 = by0; grid = dim3(bx1 - bx0, by1 - by0);
+        region = TileRegion{ bx0, by0, bx1, by1 };
         // an exchanged chain is NOT cleared: every texel of mips 0..5 has exactly one owner who rewrites it each frame, and a
         // peer that runs ahead may already have stored its part of this frame into it
         if (bMin && !p.nPeers) CHORD_CUDA(cudaMemsetAsync(dst->minChain, 0, sizeof(__half) * dst->totalTexels, ctx->stream));
@@ -346,6 +386,15 @@ int launch_build_hzb(chord_frame* fr, int bMin, int bMax, int bRange, chord_hzb*
     // mips 6..: from the (tile-)local mip 5 now, like the phase-1 HZB wants; an exchanged chain gets them from the GATHERED
     // mip 5 later (launch_hzb_exchange_wait_top, in front of the first reader)
     if (dst->mipCount > 6 && !p.nPeers) { k_hzb_top<<<1, 256, 0, ctx->stream>>>(p); ctx->launches++; }
+    if (p.nPeers) {
+        // producer side of the fused exchange: push the tile's rows of mips 0..5 (both chains) to every peer, then the flags
+        uint32_t rows = 0;
+        for (uint32_t m = 0; m < 6 && m < dst->mipCount; m++) rows += ((region.by1 - region.by0) * 32u) >> m;
+        uint32_t pgrid = (2u * rows + 7u) / 8u; if (pgrid > (uint32_t)ctx->smCount * 8u) pgrid = (uint32_t)ctx->smCount * 8u; if (pgrid == 0u) pgrid = 1u;
+        p.numBlocks = pgrid;
+        k_hzb_exchange_put<<<pgrid, 256, 0, ctx->stream>>>(p, region, rows, bRange ? 1 : 0);
+        ctx->launches++;
+    }
     CHORD_CUDA(cudaGetLastError());
     return CHORD_OK;
 }
@@ -381,8 +430,6 @@ int launch_hzb_exchange_wait_top(chord_frame* fr, chord_hzb* dst, const HzbExcha
 }  // namespace chordb
 
 namespace chordb {
-
-struct TileRegion { uint32_t bx0, by0, bx1, by1; };
 
 __device__ __forceinline__ uint64_t tile_region_texels(const TileRegion& r, uint32_t mip)
 { return (uint64_t)(((r.bx1 - r.bx0) * 32u) >> mip) * (((r.by1 - r.by0) * 32u) >> mip); }
