@@ -393,10 +393,10 @@ def masked_benchmark(ctx, stream, torch, n_meshlets=100000, steps=10):
 
 def frame_benchmark_tiled(ctx, stream, torch, dist, rank, world, steps=20, width=W4K, height=H4K, use_graph=True):
     """BASELINE configs[3]: the same city frame split into `world` screen tiles, one per GPU, through the native renderer: tile
-    sub-frustum cull, scissored raster, tile-local phase-1 HZB, and the FUSED exchange of the history HZB - the final buildHZB
-    stores every rank's part of mips 0..5 straight into all ranks' chains over NVLink (peer pointers from CUDA IPC), arrival
-    flags instead of a collective, top mips rebuilt in front of the next phase 0; the whole tiled frame is one CUDA-graph
-    launch per rank.  Measured beside it: the same frame with pack -> ncclAllGather -> unpack inside the library
+    sub-frustum cull, scissored raster, tile-local phase-1 HZB, and the FUSED exchange of the history HZB - behind the final
+    buildHZB a put kernel stores every rank's part of mips 0..5 straight into all ranks' chains over NVLink (peer pointers from
+    CUDA IPC), arrival flags instead of a collective, top mips rebuilt in front of the next phase 0; the tiled frame is two
+    CUDA-graph launches per rank (visibility passes; resolve on a second stream).  Measured beside it: the same frame with pack -> ncclAllGather -> unpack inside the library
     (chord_renderer_exchange_connect_nccl).  Frame time = max over ranks of (CUDA events around `steps` frames / steps).
     Parity (untimed): every rank also renders the FULL frame on its own GPU; its tile must equal the full frame inside the
     tile (depth bits + decoded ids), nothing outside it, and the gathered min / max chains + valid range must equal the
@@ -451,7 +451,7 @@ def frame_benchmark_tiled(ctx, stream, torch, dist, rank, world, steps=20, width
         out['ms_per_frame_serial'] = repr(e)
     timed_out = r.exchange_timed_out()
     out.update({'frames_per_s': 1000.0 / ms, 'ms_per_frame': ms, 'ms_per_frame_wall': wall, 'frames_timed': steps,
-                'exchange': 'fused: k_hzb_build stores the tile parts into every rank\'s history chain over NVLink peer memory (CUDA IPC), arrival flags, no collective call',
+                'exchange': 'fused: k_hzb_exchange_put pushes the tile parts into every rank\'s history chain over NVLink peer memory (CUDA IPC) behind the HZB build, arrival flags, no collective call',
                 'submission': ('two CUDA graph launches per rank and frame (visibility passes; resolve on a second stream, overlapping the next frame)' if use_graph else 'eager launches'),
                 'graph_replays': r.graph_replays,
                 'exchange_bytes_per_frame': int(2 * sum(r.history_hzb.tile_bytes(t_) for t_ in tiles) * (world - 1)),

@@ -73,7 +73,7 @@ struct FrameDev {
 // ------------------------------------------------------------------------------------------------ multi-GPU exchange
 // One block of this layout per rank (one cudaMalloc, exported with CUDA IPC or reached through peer access): the header, then
 // the two history HZBs (min + max chains each).  Peers write into it: their part of mips 0..5, their valid range, their
-// arrival flag (hzb.cu: k_hzb_build epilogue / k_hzb_exchange_wait_top).
+// arrival flag (hzb.cu: k_hzb_exchange_put / k_hzb_exchange_wait_top).
 #define CHORD_MAX_EXCHANGE_RANKS 16
 struct ExchangeHeader {
     uint32_t arrived[CHORD_MAX_EXCHANGE_RANKS];          // [rank] = last frame sequence number whose stores into THIS block are complete

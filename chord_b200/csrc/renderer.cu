@@ -6,10 +6,11 @@
 //                              visibilityMark -> lighting.  With CHORD_RENDERER_GRAPH the sequence is recorded once per history
 //                              slot (two CUDA graphs: the history ping-pongs between two HZBs) and replayed with the frame's
 //                              uniforms rewritten in the graphs' pinned snapshot: one launch per frame instead of ~30.
-//   exchange, fused (default)  every rank owns one screen tile.  The final buildHZB of a frame stores the tile's part of
-//                              mips 0..5 straight into EVERY rank's history chain (peer pointers over NVLink: CUDA IPC between
-//                              processes, peer access inside one), its last block publishes an arrival flag; the next frame
-//                              starts with a one-block kernel that waits for all flags and rebuilds mips 6.. locally.
+//   exchange, fused (default)  every rank owns one screen tile.  Behind the final buildHZB of a frame a put kernel pushes the
+//                              tile's rows of mips 0..5 straight into EVERY rank's history chain (peer pointers over NVLink: CUDA
+//                              IPC between processes, peer access inside one), its last block publishes an arrival flag; the next
+//                              frame has a one-block kernel (on a stream of its own, beside the instance culling) that waits for
+//                              all flags and rebuilds mips 6.. locally.
 //                              No pack / all-gather / unpack, no host involvement, graph-capturable.
 //   exchange, NCCL             pack -> ncclAllGather -> unpack -> top rebuild on the context stream (NCCL resolved at run time
 //                              with dlopen; the literal "NCCL all-gather of the HZB mip chain" of the north star, and the
