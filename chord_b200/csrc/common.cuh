@@ -310,7 +310,8 @@ int launch_render_mesh(chord_frame* f, chord_cmdlist* list);
 int launch_cascade_setup(chord_frame* mainFrame, const chord_cascade_setup_desc* desc, const chord_hzb* validRangeSource, chord_InstanceCullingViewInfo* dViews);
 int launch_hzb_culling_generic(chord_frame* f, const chord_hzb* hzb, const chord_InstanceCullingViewInfo* hzbView, float extentScale,
                                int useLastFrame, chord_cmdlist* in, chord_cmdlist* outVis, const chord_InstanceCullingViewInfo* dHzbView = nullptr);
-int launch_build_hzb(chord_frame* f, int bMin, int bMax, int bRange, chord_hzb* dst, const HzbExchange* exchange = nullptr);
+int launch_build_hzb(chord_frame* f, int bMin, int bMax, int bRange, chord_hzb* dst, const HzbExchange* exchange = nullptr, bool deferPut = false);
+int launch_hzb_exchange_put(chord_frame* f, int bRange, chord_hzb* dst, const HzbExchange* exchange, uint32_t seq);   // seq 0: the kernel advances the sequence number itself
 int launch_hzb_range_reduce(chord_ctx* ctx, const uint32_t* pairs, uint32_t world, uint32_t* validRange);
 int launch_hzb_exchange_wait_top(chord_frame* f, chord_hzb* dst, const HzbExchange* exchange, uint32_t world, uint32_t* status);
 int launch_visibility_mark(chord_frame* f, chord_cmdlist* post);

@@ -216,7 +216,7 @@ __global__ void __launch_bounds__(256, (kMin && kMax) ? 6 : 8) k_hzb_build(HzbBu
 // peer at 2 GPUs, ~70 us at 8; profiles/r02_o_*.)  The block that finishes last publishes this rank's valid depth range and -
 // after a system-scope fence - its arrival flag to every peer; k_hzb_exchange_wait_top is the consumer.
 struct TileRegion { uint32_t bx0, by0, bx1, by1; };
-__global__ void __launch_bounds__(256) k_hzb_exchange_put(HzbBuildParams p, TileRegion r, uint32_t rowsPerChain, int kRange)
+__global__ void __launch_bounds__(256) k_hzb_exchange_put(HzbBuildParams p, TileRegion r, uint32_t rowsPerChain, int kRange, uint32_t seqParam)
 {
     const uint32_t tid = threadIdx.x, lane = tid & 31u;
     const uint32_t warpsPerGrid = gridDim.x * (blockDim.x >> 5);
@@ -256,22 +256,28 @@ __global__ void __launch_bounds__(256) k_hzb_exchange_put(HzbBuildParams p, Tile
             uint32_t seq = 0;
             if (tid == 0) {
                 *p.counter = 0u;                                             // re-armed for the next launch (stream-ordered)
-                seq = p.localHeader->localSeq + 1u;
-                p.localHeader->localSeq = seq;
+                // seqParam == 0: this kernel advances the rank's sequence number itself (it runs in stream order behind the
+                // build); otherwise k_hzb_exchange_advance did that in stream order and the host hands the number in - the
+                // deferred put of the asynchronous renderer may run after later passes have read the counter
+                if (seqParam == 0u) { seq = p.localHeader->localSeq + 1u; p.localHeader->localSeq = seq; }
             }
             __syncthreads();
             if (tid <= p.nPeers) {
                 chordb::ExchangeHeader* dst = tid < p.nPeers ? p.peers->header[tid] : p.localHeader;
                 if (kRange) {
-                    const volatile uint32_t* vr = p.validRange;               // final: every block's atomics precede its count
-                    dst->ranges[p.parity][p.rank][0] = vr[0]; dst->ranges[p.parity][p.rank][1] = vr[1];
+                    // stream-ordered put: the chain's valid-range words are final (the build precedes this launch).  Deferred
+                    // put: k_hzb_exchange_advance saved them in this rank's own header entry - by now the next frame's
+                    // k_hzb_exchange_wait_top may have folded all ranks' ranges into the chain's words
+                    const volatile uint32_t* vr = seqParam ? p.localHeader->ranges[p.parity][p.rank] : p.validRange;
+                    const uint32_t lo = vr[0], hi = vr[1];
+                    dst->ranges[p.parity][p.rank][0] = lo; dst->ranges[p.parity][p.rank][1] = hi;
                 }
             }
             __threadfence_system();
             __syncthreads();
             if (tid == 0) {
                 // broadcast the sequence number to thread 0's peers: one thread writes all flags so that they follow the fence
-                const uint32_t s2 = p.localHeader->localSeq;
+                const uint32_t s2 = seqParam ? seqParam : p.localHeader->localSeq;
                 for (uint32_t q = 0; q < p.nPeers; q++) *((volatile uint32_t*)&p.peers->header[q]->arrived[p.rank]) = s2;
                 *((volatile uint32_t*)&p.localHeader->arrived[p.rank]) = s2;
             }
@@ -347,7 +353,45 @@ static void tile_blocks(const chord_hzb* h, const chord_rect& t, uint32_t frameW
 static bool tile_aligned(const chord_rect& t, uint32_t w, uint32_t h)
 { return (t.x0 % 64 == 0) && (t.y0 % 64 == 0) && (t.x1 % 64 == 0 || t.x1 == w) && (t.y1 % 64 == 0 || t.y1 == h); }
 
-int launch_build_hzb(chord_frame* fr, int bMin, int bMax, int bRange, chord_hzb* dst, const HzbExchange* ex)
+// the rank's own sequence number, advanced in stream order behind a build whose put is deferred to another stream
+// (and this rank's own valid-range entry of the slot: the next frame's k_hzb_exchange_wait_top folds it in whether or not the
+// put - which carries it to the peers - has run yet)
+__global__ void k_hzb_exchange_advance(chordb::ExchangeHeader* __restrict__ header, const uint32_t* __restrict__ validRange, uint32_t parity, uint32_t rank)
+{
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        header->localSeq = header->localSeq + 1u;
+        if (validRange) { header->ranges[parity][rank][0] = validRange[0]; header->ranges[parity][rank][1] = validRange[1]; }
+    }
+}
+
+static uint32_t exchange_put_rows(const chord_hzb* dst, const TileRegion& region)
+{
+    uint32_t rows = 0;
+    for (uint32_t m = 0; m < 6 && m < dst->mipCount; m++) rows += ((region.by1 - region.by0) * 32u) >> m;
+    return rows;
+}
+
+// producer side of the fused exchange on its own (the asynchronous renderer runs it on a stream beside the next passes): the
+// tile's rows of mips 0..5 of `dst` (complete in this rank's own chain) go to every peer, then the valid range and the flags
+int launch_hzb_exchange_put(chord_frame* fr, int bRange, chord_hzb* dst, const HzbExchange* ex, uint32_t seq)
+{
+    chord_ctx* ctx = fr->ctx;
+    CHORD_REQUIRE(ex && ex->nPeers, "no exchange");
+    HzbBuildParams p = make_params(fr, 1, 1, bRange, dst);
+    p.nPeers = ex->nPeers; p.rank = ex->rank; p.parity = ex->parity; p.localHeader = ex->localHeader; p.peers = ex->dPeers;
+    CHORD_REQUIRE(tile_aligned(fr->tile, fr->width, fr->height), "tile rect must be cut on multiples of 64 px for a tiled HZB build");
+    TileRegion region;
+    tile_blocks(dst, fr->tile, fr->width, fr->height, region.bx0, region.by0, region.bx1, region.by1);
+    const uint32_t rows = exchange_put_rows(dst, region);
+    uint32_t pgrid = (2u * rows + 7u) / 8u; if (pgrid > (uint32_t)ctx->smCount * 8u) pgrid = (uint32_t)ctx->smCount * 8u; if (pgrid == 0u) pgrid = 1u;
+    p.numBlocks = pgrid;
+    k_hzb_exchange_put<<<pgrid, 256, 0, ctx->stream>>>(p, region, rows, bRange ? 1 : 0, seq);
+    ctx->launches++;
+    CHORD_CUDA(cudaGetLastError());
+    return CHORD_OK;
+}
+
+int launch_build_hzb(chord_frame* fr, int bMin, int bMax, int bRange, chord_hzb* dst, const HzbExchange* ex, bool deferPut)
 {
     chord_ctx* ctx = fr->ctx;
     HzbBuildParams p = make_params(fr, bMin, bMax, bRange, dst);
@@ -386,16 +430,16 @@ int launch_build_hzb(chord_frame* fr, int bMin, int bMax, int bRange, chord_hzb*
     // mips 6..: from the (tile-)local mip 5 now, like the phase-1 HZB wants; an exchanged chain gets them from the GATHERED
     // mip 5 later (launch_hzb_exchange_wait_top, in front of the first reader)
     if (dst->mipCount > 6 && !p.nPeers) { k_hzb_top<<<1, 256, 0, ctx->stream>>>(p); ctx->launches++; }
-    if (p.nPeers) {
-        // producer side of the fused exchange: push the tile's rows of mips 0..5 (both chains) to every peer, then the flags
-        uint32_t rows = 0;
-        for (uint32_t m = 0; m < 6 && m < dst->mipCount; m++) rows += ((region.by1 - region.by0) * 32u) >> m;
-        uint32_t pgrid = (2u * rows + 7u) / 8u; if (pgrid > (uint32_t)ctx->smCount * 8u) pgrid = (uint32_t)ctx->smCount * 8u; if (pgrid == 0u) pgrid = 1u;
-        p.numBlocks = pgrid;
-        k_hzb_exchange_put<<<pgrid, 256, 0, ctx->stream>>>(p, region, rows, bRange ? 1 : 0);
-        ctx->launches++;
-    }
     CHORD_CUDA(cudaGetLastError());
+    // producer side of the fused exchange: right behind the build, unless the caller launches it itself (on another stream)
+    if (p.nPeers && !deferPut) return launch_hzb_exchange_put(fr, bRange, dst, ex, 0u);
+    if (p.nPeers) {
+        // deferred put: the sequence number still advances here, in stream order (k_hzb_exchange_wait_top of the next frame
+        // reads it as its target); the caller launches the put with the same number
+        k_hzb_exchange_advance<<<1, 32, 0, ctx->stream>>>(p.localHeader, bRange ? dst->validRange : nullptr, p.parity, p.rank);
+        ctx->launches++;
+        CHORD_CUDA(cudaGetLastError());
+    }
     return CHORD_OK;
 }
 

@@ -83,6 +83,7 @@ struct chord_renderer {
     // already runs the visibility passes of frame N + 1 (they touch disjoint state: the two frames, post[p])
     bool async; cudaStream_t resolveStream; cudaEvent_t geomDone[2], resolveDone[2]; bool resolvePending[2];
     cudaStream_t auxStream; cudaEvent_t auxFork, auxJoin;            // fused exchange: the consumer-side wait runs beside the instance culling
+    cudaEvent_t putDone[2]; bool putPending[2]; uint32_t putSeq;    // putSeq mirrors the device-side sequence number (one build per frame)                     // ... and with the asynchronous resolve the producer-side put runs there too
     chord_graph* graphResolve[2];
     chord_cmdlist* post[2]; chord_cmdlist* visible; chord_cmdlist* rejected; chord_cmdlist* visible1;
     uint32_t listCapacity;
@@ -149,6 +150,11 @@ static int nccl_allgather_history(chord_renderer* r, chord_hzb* h);
 
 // the frame sequence itself (eager, or while the context is capturing), in two parts: the visibility passes up to the history
 // HZB, and the resolve (visibilityMark + lighting)
+// Asynchronous renderer + fused exchange: the put of a frame's history (k_hzb_exchange_put) is not part of the visibility
+// passes' stream order; it runs on the auxiliary stream as soon as they are done (after_geometry), so that the next frame's
+// uniform upload, clear and instance culling do not wait for 20 MB of NVLink stores nobody on THIS GPU needs.
+static bool defer_put(const chord_renderer* r) { return r->async && r->mode == 1 && r->auxStream != nullptr; }
+
 static int record_geometry(chord_renderer* r, uint32_t p, const chord_PerframeCameraView* view, const chord_InstanceCullingViewInfo* iview,
                            const chord_GPUObjectGLTFPrimitive* objects, uint32_t objectCount, uint32_t lod0, uint32_t groups)
 {
@@ -195,7 +201,7 @@ static int record_geometry(chord_renderer* r, uint32_t p, const chord_PerframeCa
     chord_hzb* hzb = r->hist[p];
     if (r->mode == 1) {
         const HzbExchange ex = make_exchange(r, p);
-        if ((rc = launch_build_hzb(f, 1, 1, 1, hzb, &ex))) return rc;
+        if ((rc = launch_build_hzb(f, 1, 1, 1, hzb, &ex, defer_put(r)))) return rc;
         hzb->valid = 1;
     } else {
         if ((rc = chord_build_hzb(f, 1, 1, 1, hzb))) return rc;
@@ -233,6 +239,26 @@ static int record_frame(chord_renderer* r, uint32_t p, const chord_PerframeCamer
 {
     const int rc = record_geometry(r, p, view, iview, objects, objectCount, lod0, groups);
     return rc ? rc : record_resolve(r, p);
+}
+
+// asynchronous renderer: what follows the visibility passes of slot p once they are enqueued on the context stream
+static int after_geometry(chord_renderer* r, uint32_t p)
+{
+    chord_ctx* ctx = r->ctx;
+    CHORD_CUDA(cudaEventRecord(r->geomDone[p], ctx->stream));
+    if (defer_put(r)) {
+        CHORD_CUDA(cudaStreamWaitEvent(r->auxStream, r->geomDone[p], 0));
+        const HzbExchange ex = make_exchange(r, p);
+        cudaStream_t main = ctx->stream;
+        ctx->stream = r->auxStream;
+        const int rc = launch_hzb_exchange_put(r->frame, 1, r->hist[p], &ex, ++r->putSeq);
+        ctx->stream = main;
+        if (rc) return rc;
+        CHORD_CUDA(cudaEventRecord(r->putDone[p], r->auxStream));
+        r->putPending[p] = true;
+    }
+    CHORD_CUDA(cudaStreamWaitEvent(r->resolveStream, r->geomDone[p], 0));
+    return CHORD_OK;
 }
 
 // Runs `fn` with the context's stream pointing at the resolve stream: every launcher of the library enqueues on ctx->stream, so
@@ -331,7 +357,7 @@ void chord_renderer_destroy(chord_renderer* r)
     exchange_teardown(r);
     chord_frame_destroy(r->frames[0]); chord_frame_destroy(r->frames[1]);
     if (r->resolveStream) cudaStreamDestroy(r->resolveStream);
-    if (r->auxStream) { cudaStreamSynchronize(r->auxStream); cudaStreamDestroy(r->auxStream); cudaEventDestroy(r->auxFork); cudaEventDestroy(r->auxJoin); }
+    if (r->auxStream) { cudaStreamSynchronize(r->auxStream); cudaStreamDestroy(r->auxStream); cudaEventDestroy(r->auxFork); cudaEventDestroy(r->auxJoin); cudaEventDestroy(r->putDone[0]); cudaEventDestroy(r->putDone[1]); }
     for (int k = 0; k < 2; k++) { if (r->geomDone[k]) cudaEventDestroy(r->geomDone[k]); if (r->resolveDone[k]) cudaEventDestroy(r->resolveDone[k]); }
     chord_cmdlist** all[5] = { &r->post[0], &r->post[1], &r->visible, &r->rejected, &r->visible1 };
     for (auto l : all) chord_cmdlist_destroy(*l);
@@ -388,6 +414,8 @@ int chord_renderer_render(chord_renderer* r, const chord_PerframeCameraView* vie
         // this slot's frame was last read by the resolve of two frames ago, which may still be running on the resolve stream
         r->frame = r->frames[p];
         if (r->resolvePending[p]) CHORD_CUDA(cudaStreamWaitEvent(ctx->stream, r->resolveDone[p], 0));
+        // ... and its history chain by the put of two frames ago (auxiliary stream)
+        if (r->putPending[p]) CHORD_CUDA(cudaStreamWaitEvent(ctx->stream, r->putDone[p], 0));
     }
     if (wantGraph && r->graph[p]) {
         // replay: rewrite the pinned uniform snapshot once the previous replay of THIS graph (two frames ago) is done with it
@@ -397,8 +425,7 @@ int chord_renderer_render(chord_renderer* r, const chord_PerframeCameraView* vie
         CHORD_CUDA(cudaEventRecord(r->graphDone[p], ctx->stream));
         r->graphLaunched[p] = true; r->graphReplays++;
         if (r->async) {
-            CHORD_CUDA(cudaEventRecord(r->geomDone[p], ctx->stream));
-            CHORD_CUDA(cudaStreamWaitEvent(r->resolveStream, r->geomDone[p], 0));
+            if ((rc = after_geometry(r, p))) return rc;
             if ((rc = on_resolve_stream(r, [&]() { return chord_graph_launch(r->graphResolve[p]); }))) return rc;
         }
     } else if (wantGraph && r->eagerWithHistory >= (r->async ? 2u : 1u)) {
@@ -428,14 +455,12 @@ int chord_renderer_render(chord_renderer* r, const chord_PerframeCameraView* vie
         CHORD_CUDA(cudaEventRecord(r->graphDone[p], ctx->stream));
         r->graphLaunched[p] = true;
         if (r->async) {
-            CHORD_CUDA(cudaEventRecord(r->geomDone[p], ctx->stream));
-            CHORD_CUDA(cudaStreamWaitEvent(r->resolveStream, r->geomDone[p], 0));
+            if ((rc = after_geometry(r, p))) return rc;
             if ((rc = on_resolve_stream(r, [&]() { return chord_graph_launch(r->graphResolve[p]); }))) return rc;
         }
     } else if (r->async) {
         if ((rc = record_geometry(r, p, view, iview, objects, objectCount, lod0MeshletCount, meshletGroupCount))) return rc;
-        CHORD_CUDA(cudaEventRecord(r->geomDone[p], ctx->stream));
-        CHORD_CUDA(cudaStreamWaitEvent(r->resolveStream, r->geomDone[p], 0));
+        if ((rc = after_geometry(r, p))) return rc;
         if ((rc = on_resolve_stream(r, [&]() { return record_resolve(r, p); }))) return rc;
         if (r->historyValid) r->eagerWithHistory++;
     } else {
@@ -474,6 +499,7 @@ int chord_renderer_history_sync(chord_renderer* r)
     CHORD_REQUIRE(r, "null");
     if (r->mode != 1 || !r->historyValid) return CHORD_OK;
     const uint32_t p = (r->frameIndex - 1u) & 1u;
+    if (r->putPending[p]) CHORD_CUDA(cudaStreamWaitEvent(r->ctx->stream, r->putDone[p], 0));      // this rank's own put advances its sequence number
     const HzbExchange ex = make_exchange(r, p);
     return launch_hzb_exchange_wait_top(r->frame, r->hist[p], &ex, r->world, r->dStatus);
 }
@@ -600,7 +626,12 @@ int chord_renderer_exchange_connect(chord_renderer* r, uint32_t rank, uint32_t w
         CHORD_CUDA(cudaStreamCreateWithPriority(&r->auxStream, cudaStreamNonBlocking, greatest));
         CHORD_CUDA(cudaEventCreateWithFlags(&r->auxFork, cudaEventDisableTiming));
         CHORD_CUDA(cudaEventCreateWithFlags(&r->auxJoin, cudaEventDisableTiming));
+        CHORD_CUDA(cudaEventCreateWithFlags(&r->putDone[0], cudaEventDisableTiming));
+        CHORD_CUDA(cudaEventCreateWithFlags(&r->putDone[1], cudaEventDisableTiming));
     }
+    r->putPending[0] = r->putPending[1] = false;
+    // the host mirror of this rank's sequence number starts where the device-side word stands
+    CHORD_CUDA(cudaMemcpy(&r->putSeq, &reinterpret_cast<ExchangeHeader*>(r->block)->localSeq, sizeof(uint32_t), cudaMemcpyDeviceToHost));
     r->mode = 1;
     r->historyValid = false; r->hist[0]->valid = r->hist[1]->valid = 0; r->frameIndex = 0;
     return CHORD_OK;

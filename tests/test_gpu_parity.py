@@ -1241,23 +1241,26 @@ def _tile_case(gpu_ctx, world, w, h, frames_n):
     return scene, info, frames, tiles, multigpu
 
 
-def test_renderer_fused_exchange_in_process(gpu_ctx, world=2, use_graph=False):
+def test_renderer_fused_exchange_in_process(gpu_ctx, world=2, use_graph=False, async_resolve=False, n_frames=5):
     """Tile-parallel frame with the FUSED exchange (k_hzb_build stores each rank's part of the history chain straight into every
     rank's chain, arrival flags, wait + top-mip rebuild in front of the next frame's phase 0): `world` ranks as separate
     contexts in one process (peer pointers are plain device pointers here; across processes they come from CUDA IPC).  Every
     frame: each rank's tile equals the single full frame inside the tile (depth bits + decoded ids), nothing outside it, and -
     after chord_renderer_history_sync - every rank holds the single-GPU min / max chains and valid range bit for bit."""
     w, h = 640, 384
-    scene, info, frames, tiles, multigpu = _tile_case(gpu_ctx, world, w, h, 5)
+    scene, info, frames, tiles, multigpu = _tile_case(gpu_ctx, world, w, h, n_frames)
     if use_graph and _is_host_executor():
         pytest.skip('CUDA graphs are not modelled by the host executor')
     make = type(gpu_ctx)
     ctxs = [make(gpu_ctx.device) for _ in range(world)]
     for c in ctxs:
         c.upload_scene(scene)
+        if async_resolve:
+            c.upload_luts(*synth.synthetic_luts())
     gpu_ctx.upload_scene(scene)
     single = runtime.Renderer(gpu_ctx, w, h)
-    ranks = [runtime.Renderer(c, w, h, graph=use_graph) for c in ctxs]
+    # async_resolve: the resolve of frame N on a second stream, and the put of its history on a third one, beside frame N + 1
+    ranks = [runtime.Renderer(c, w, h, graph=use_graph, resolve=async_resolve, async_resolve=async_resolve) for c in ctxs]
     ptrs = [r.exchange_export()[1] for r in ranks]
     for i, r in enumerate(ranks):
         r.exchange_connect(i, world, tiles, local_ptrs=ptrs)
@@ -1297,6 +1300,14 @@ def test_renderer_fused_exchange_in_process(gpu_ctx, world=2, use_graph=False):
 
 def test_renderer_fused_exchange_four_ranks_graph(gpu_ctx):
     test_renderer_fused_exchange_in_process(gpu_ctx, world=4, use_graph=True)
+
+
+@pytest.mark.parametrize('world,use_graph', [(2, False), (4, True)])
+def test_renderer_fused_exchange_async(gpu_ctx, world, use_graph):
+    """The same with CHORD_RENDERER_ASYNC_RESOLVE: the producer-side put (k_hzb_exchange_put) leaves the visibility passes'
+    stream order - it runs on the auxiliary stream with a host-passed sequence number while the rank's own sequence number and
+    valid-range entry advance in stream order (k_hzb_exchange_advance); replayed graphs from the fourth frame on."""
+    test_renderer_fused_exchange_in_process(gpu_ctx, world=world, use_graph=use_graph, async_resolve=True, n_frames=8 if use_graph else 4)
 
 
 @pytest.mark.parametrize('world,mode', [(2, 'eager'), (4, 'graph')])

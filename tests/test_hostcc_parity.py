@@ -110,6 +110,10 @@ def test_renderer_fused_exchange_in_process(host_ctx, cases):
         cases.test_renderer_fused_exchange_in_process(host_ctx, world=4)
 
 
+def test_renderer_fused_exchange_async(host_ctx, cases):
+    cases.test_renderer_fused_exchange_async(host_ctx, 2, False)
+
+
 def test_tall_frame_hzb_rows(host_ctx, cases):
     cases.test_tall_frame_hzb_rows(host_ctx)
 
