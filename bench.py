@@ -795,6 +795,7 @@ def main():
         # is only quoted when the capture was made with THIS raster.cu (sha256 of the kernel source recorded with it) and is
         # scaled by the share of the stream this rank rasterises; otherwise null.
         traffic, traffic_note = None, 'no ncu capture of this kernel source on record (profiles/raster_ncu_summary.json)'
+        ncu_extra = None
         try:
             import hashlib
             summ = json.load(open(os.path.join(ROOT, 'profiles', 'raster_ncu_summary.json')))
@@ -803,6 +804,11 @@ def main():
                 traffic = int(summ['dram_bytes_per_launch'] * (n_local / float(summ.get('meshlets_per_launch', N_MESHLETS))))
                 traffic_note = (f"ncu --set full capture of commit {summ.get('commit', '?')} (same raster.cu): dram__bytes_read.sum + dram__bytes_write.sum of one "
                                 f"k_raster_fast launch over {summ.get('meshlets_per_launch', N_MESHLETS)} meshlets, scaled by this rank's {n_local} meshlets")
+                # (ii) DRAM rate under ncu, (iii) L2 atomic unit vs its peak, and which limit binds - from the same capture
+                ncu_extra = {'dram_gbs_under_ncu': summ['dram_bytes_per_launch'] / (summ['duration_ms_under_ncu'] * 1e-3) / 1e9,
+                             'l2_red_sectors_per_launch': summ.get('l2_red_sectors'), 'l2_red_pct_of_peak_sustained': summ.get('l2_red_pct_of_peak_sustained'),
+                             'issue_slots_busy_pct': summ.get('issue_slots_busy_pct'), 'warp_instructions_per_triangle': summ.get('warp_instructions_per_triangle'),
+                             'binding_limit': summ.get('binding_limit')}
             else:
                 traffic_note = 'stale: profiles/raster_ncu_summary.json was captured with another raster.cu (sha256 differs)'
         except Exception:
@@ -824,7 +830,7 @@ def main():
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                          'traffic': traffic, 'traffic_note': traffic_note, 'kernel': 'k_raster_fast (+ prepare / deferred / large, < 4 % of the step)', 'kernel_ms': kern_ms,
                          'peak_source': 'MEASURED_PEAKS.json hbm_gbs (of measured)' if peaks else '6650 GB/s (of fallback)',
-                         'algorithmic_bytes_per_launch': int(alg_bytes),
+                         'algorithmic_bytes_per_launch': int(alg_bytes), 'ncu': ncu_extra,
                          'note': 'at 14.7 B/tri the HBM roofline is ~450 G tri/s; the binding limits are per-triangle setup '
                                  'issue rate and L2 atomics (see profiles/)'},
             'raster_stats': stats,

@@ -36,7 +36,12 @@ def main():
               'duration_ms_under_ncu': m('gpu__time_duration.sum'), 'dram_bytes_read': int(rd), 'dram_bytes_write': int(wr), 'dram_bytes_per_launch': int(rd + wr),
               'traffic_over_algorithmic': (rd + wr) / s['algorithmic_bytes_per_launch'], 'warp_instructions': int(inst),
               'warp_instructions_per_triangle': inst / (s['meshlets_per_launch'] * 128.0),
-              'avg_active_threads_per_instruction': m('smsp__thread_inst_executed_per_inst_executed.ratio')})
+              'avg_active_threads_per_instruction': m('smsp__thread_inst_executed_per_inst_executed.ratio'),
+              # the L2 atomic unit (every covered sample is one 64-bit RED.MAX)
+              'l2_red_sectors': int(m('lts__t_sectors_srcunit_tex_op_red.sum')),
+              'l2_red_pct_of_peak_sustained': m('lts__t_sectors_srcunit_tex_op_red.sum.pct_of_peak_sustained_elapsed'),
+              'l2_atomic_input_cycles_pct_of_peak': m('lts__d_atomic_input_cycles_active.avg.pct_of_peak_sustained_elapsed'),
+              'issue_slots_busy_pct': m('sm__inst_issued.avg.pct_of_peak_sustained_active') if 'sm__inst_issued.avg.pct_of_peak_sustained_active' in h else s.get('issue_slots_busy_pct')})
     json.dump(s, open(path, 'w'), indent=1)
     subprocess.run(f'ncu -i {rep} --page details > {os.path.join(ROOT, "profiles", details)}', shell=True)
     print({k: s[k] for k in ('commit', 'dram_bytes_per_launch', 'traffic_over_algorithmic', 'warp_instructions_per_triangle')})
