@@ -202,7 +202,6 @@ struct chord_ctx {
     int device;
     cudaStream_t stream;
     cudaStream_t uploadStream;          // created by the first chord_cmdlist_upload_async
-    cudaStream_t clearStream;           // the visibility surface's clear runs here, beside the first passes of a frame (frame_join_clear)
     uint32_t switchFlags;
     uint32_t lightingSlot;              // this context's slot of the resolve kernel's constant-bank uniforms (resolve.cu)
     int rasterVariant, rasterCtasPerSm; uint32_t rasterWarpMin;    // chord_ctx_set_raster_tuning (defaults 11, 0 = built-in, 16384)
@@ -277,7 +276,6 @@ struct chord_frame {
     chord_PerframeCameraView* dView; chord_InstanceCullingViewInfo* dIView; void* dLightingView; size_t lightingViewOffset, objectsOffset;
     chord_GPUObjectGLTFPrimitive* dObjects; uint32_t objectCapacity, objectCount;
     chord_rect clearedTile; bool clearedValid;     // region that may hold non-zero texels (tile-only clears)
-    cudaEvent_t clearFork, clearDone; bool clearPending;      // the clear of chord_frame_begin, in flight on ctx->clearStream
     chordb::ObjectDerived* dDerived;
     uint32_t lod0MeshletCount, meshletGroupCount;
     float tanHalfFovy;
@@ -322,7 +320,6 @@ int launch_lighting(chord_frame* f, chord_cmdlist* post, uint32_t parts = CHORD_
 int launch_split_vis(chord_frame* f, uint32_t* vis32, float* depth32);
 int launch_decode(chord_frame* f, chord_cmdlist* post, uint32_t* triples);
 int launch_selftest_vertex_records(chord_ctx* ctx, uint32_t n, uint32_t seed, uint32_t width, uint32_t height, uint32_t clampZ, unsigned long long* dOut);
-int frame_join_clear(chord_frame* f);      // ctx.cu: orders the context stream behind the frame's pending clear; every reader / writer of vis64 calls it first
 int scan_reset(chord_ctx* ctx, uint32_t tilesNeeded);
 int launch_fill_u32(chord_ctx* ctx, void* dst, uint32_t v0, uint32_t v1, size_t words);    // ctx.cu: small fills as kernels (cheaper graph nodes than memsets)
 int build_meshlet_packs(chord_ctx* ctx, DatasDev* d, uint32_t datasId, uint32_t meshletCount, uint32_t vertexCount, uint32_t groupCount, uint32_t groupIndicesCount,

@@ -56,15 +56,6 @@ int launch_fill_u32(chord_ctx* ctx, void* dst, uint32_t v0, uint32_t v1, size_t 
 
 // Scratch of the ordered compactions: ONE allocation [ticket word | status[0 .. tiles]] so that one fill per cull
 // kernel resets both (two stream operations per cull call, four cull calls per frame, were ~2 us each on the timeline).
-int frame_join_clear(chord_frame* f)
-{
-    if (f->clearPending) {
-        CHORD_CUDA(cudaStreamWaitEvent(f->ctx->stream, f->clearDone, 0));
-        f->clearPending = false;
-    }
-    return CHORD_OK;
-}
-
 int scan_reset(chord_ctx* ctx, uint32_t tilesNeeded)
 {
     if (tilesNeeded > ctx->scanTiles || !ctx->scanBlock) {
@@ -136,7 +127,6 @@ static void ctx_teardown(chord_ctx* ctx)
     cudaFree(ctx->lutScattering); cudaFree(ctx->lutSingleMie);
     cudaFree(ctx->dTextures); cudaFree(ctx->dSamplers); cudaFree(ctx->dTexels); cudaFree(ctx->dTexelsRgba); cudaFree(ctx->dSrgbLut);
     if (ctx->uploadStream) { cudaStreamSynchronize(ctx->uploadStream); cudaStreamDestroy(ctx->uploadStream); }
-    if (ctx->clearStream) { cudaStreamSynchronize(ctx->clearStream); cudaStreamDestroy(ctx->clearStream); }
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     free(ctx);
 }
@@ -510,8 +500,6 @@ void chord_frame_destroy(chord_frame* f)
 {
     if (!f) return;
     cudaStreamSynchronize(f->ctx->stream);
-    if (f->ctx->clearStream) cudaStreamSynchronize(f->ctx->clearStream);
-    if (f->clearFork) { cudaEventDestroy(f->clearFork); cudaEventDestroy(f->clearDone); }
     cudaFree(f->vis64); cudaFree(f->dInputs); cudaFree(f->dDerived);
     for (int k = 0; k < 4; k++) { if (f->hInputs[k]) cudaFreeHost(f->hInputs[k]); if (f->inputsCopied[k]) cudaEventDestroy(f->inputsCopied[k]); }
     cudaFree(f->objGroupCount); cudaFree(f->objGroupBase); cudaFree(f->totalGroups);
@@ -610,34 +598,17 @@ int chord_frame_begin(chord_frame* f, const chord_PerframeCameraView* view, cons
     // addClearGbufferPass (render_textures.cpp:74-102): visibility = 0, depth = 0.0 -> packed texel 0.  Only texels inside
     // the region that can be non-zero are rewritten: a rank that renders the same screen tile every frame clears just
     // that tile (1/N of the surface); everything outside stays 0.
-    // The clear (66 MB at 4K, ~22 us) runs on a stream of its own, forked here behind everything already enqueued: the passes
-    // that follow without touching the surface - uniform prepare, instance culling, the phase-0 HZB cull, the raster's work-record
-    // prepass - overlap it; whoever reads or writes vis64 first joins (frame_join_clear).
     {
-        if (!ctx->clearStream) {
-            int least = 0, greatest = 0;
-            CHORD_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
-            CHORD_CUDA(cudaStreamCreateWithPriority(&ctx->clearStream, cudaStreamNonBlocking, greatest));
-        }
-        if (!f->clearFork) {
-            CHORD_CUDA(cudaEventCreateWithFlags(&f->clearFork, cudaEventDisableTiming));
-            CHORD_CUDA(cudaEventCreateWithFlags(&f->clearDone, cudaEventDisableTiming));
-        }
-        CHORD_CUDA(cudaEventRecord(f->clearFork, ctx->stream));
-        CHORD_CUDA(cudaStreamWaitEvent(ctx->clearStream, f->clearFork, 0));
-        cudaStream_t cs = ctx->clearStream;
         const chord_rect& t = f->tile;
         const bool same = f->clearedValid && f->clearedTile.x0 == t.x0 && f->clearedTile.y0 == t.y0 && f->clearedTile.x1 == t.x1 && f->clearedTile.y1 == t.y1;
         if (same && t.x1 - t.x0 < f->width) {
             CHORD_CUDA(cudaMemset2DAsync(f->vis64 + (size_t)t.y0 * f->width + t.x0, sizeof(unsigned long long) * (size_t)f->width, 0,
-                                         sizeof(unsigned long long) * (size_t)(t.x1 - t.x0), t.y1 - t.y0, cs));
+                                         sizeof(unsigned long long) * (size_t)(t.x1 - t.x0), t.y1 - t.y0, ctx->stream));
         } else if (same) {
-            CHORD_CUDA(cudaMemsetAsync(f->vis64 + (size_t)t.y0 * f->width, 0, sizeof(unsigned long long) * (size_t)f->width * (t.y1 - t.y0), cs));
+            CHORD_CUDA(cudaMemsetAsync(f->vis64 + (size_t)t.y0 * f->width, 0, sizeof(unsigned long long) * (size_t)f->width * (t.y1 - t.y0), ctx->stream));
         } else {
-            CHORD_CUDA(cudaMemsetAsync(f->vis64, 0, sizeof(unsigned long long) * (size_t)f->width * f->height, cs));
+            CHORD_CUDA(cudaMemsetAsync(f->vis64, 0, sizeof(unsigned long long) * (size_t)f->width * f->height, ctx->stream));
         }
-        CHORD_CUDA(cudaEventRecord(f->clearDone, cs));
-        f->clearPending = true;
         f->clearedTile = t; f->clearedValid = true;
     }
     f->begun = true;
@@ -893,9 +864,6 @@ int chord_graph_end_capture(chord_ctx* ctx, chord_graph** out)
 {
     CHORD_REQUIRE(ctx && out && ctx->capturing, "null / not capturing");
     *out = nullptr;
-    // a recorded sequence that never touched a frame's surface still has that frame's clear forked off: join it, or the capture
-    // ends with unjoined work
-    for (uint32_t i = 0; i < ctx->nCaptureFrames; i++) if (ctx->captureFrames[i].frame) frame_join_clear(ctx->captureFrames[i].frame);
     ctx->capturing = false;
     cudaGraph_t graph = nullptr;
     const cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
@@ -1045,7 +1013,6 @@ int chord_lighting(chord_frame* f, chord_cmdlist* post)
 int chord_readback_vis64(chord_frame* f, uint64_t* host)
 {
     CHORD_REQUIRE(f && host, "null");
-    { const int rcj = frame_join_clear(f); if (rcj) return rcj; }
     CHORD_CUDA(cudaMemcpyAsync(host, f->vis64, sizeof(uint64_t) * (size_t)f->width * f->height, cudaMemcpyDeviceToHost, f->ctx->stream));
     CHORD_CUDA(cudaStreamSynchronize(f->ctx->stream));
     return CHORD_OK;
@@ -1215,7 +1182,7 @@ int chord_readback_gbuffer_packed(chord_frame* f, int which, void* host)
     return CHORD_OK;
 }
 
-void* chord_frame_vis64_ptr(chord_frame* f) { if (!f) return nullptr; frame_join_clear(f); return f->vis64; }      // (stream-ordered on the context stream)
+void* chord_frame_vis64_ptr(chord_frame* f) { return f ? f->vis64 : nullptr; }
 int chord_frame_dims(const chord_frame* f, uint32_t* w, uint32_t* h) { CHORD_REQUIRE(f, "null"); if (w) *w = f->width; if (h) *h = f->height; return CHORD_OK; }
 
 int chord_frame_raster_stats(chord_frame* f, chord_raster_stats* out)

@@ -394,7 +394,6 @@ int launch_hzb_exchange_put(chord_frame* fr, int bRange, chord_hzb* dst, const H
 int launch_build_hzb(chord_frame* fr, int bMin, int bMax, int bRange, chord_hzb* dst, const HzbExchange* ex, bool deferPut)
 {
     chord_ctx* ctx = fr->ctx;
-    { const int rcj = frame_join_clear(fr); if (rcj) return rcj; }
     HzbBuildParams p = make_params(fr, bMin, bMax, bRange, dst);
     if (ex && ex->nPeers) {
         CHORD_REQUIRE(bMin, "the exchanged history chain is the min chain");
