@@ -402,7 +402,6 @@ int launch_build_hzb(chord_frame* fr, int bMin, int bMax, int bRange, chord_hzb*
     }
     dim3 grid((dst->mip0W + 31) / 32, (dst->mip0H + 31) / 32);            // hzb.cpp:74
     const bool fullFrame = fr->tile.x0 == 0 && fr->tile.y0 == 0 && fr->tile.x1 == fr->width && fr->tile.y1 == fr->height;
-    TileRegion region = { 0u, 0u, grid.x, grid.y };
     CHORD_REQUIRE(!(p.nPeers && fullFrame), "an exchanged build renders one screen tile of several");
     if (!fullFrame) {
         // screen-tile partition: build only the blocks this tile owns; everything else reads as 0 (= far,
@@ -410,7 +409,6 @@ int launch_build_hzb(chord_frame* fr, int bMin, int bMax, int bRange, chord_hzb*
         CHORD_REQUIRE(tile_aligned(fr->tile, fr->width, fr->height), "tile rect must be cut on multiples of 64 px for a tiled HZB build");
         uint32_t bx0, by0, bx1, by1; tile_blocks(dst, fr->tile, fr->width, fr->height, bx0, by0, bx1, by1);
         p.blockX0 = bx0; p.blockY0 = by0; grid = dim3(bx1 - bx0, by1 - by0);
-        region = TileRegion{ bx0, by0, bx1, by1 };
         // an exchanged chain is NOT cleared: every texel of mips 0..5 has exactly one owner who rewrites it each frame, and a
         // peer that runs ahead may already have stored its part of this frame into it
         if (bMin && !p.nPeers) CHORD_CUDA(cudaMemsetAsync(dst->minChain, 0, sizeof(__half) * dst->totalTexels, ctx->stream));
