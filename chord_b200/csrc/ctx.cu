@@ -24,7 +24,7 @@ FrameDev make_frame_dev(const chord_frame* f)
 {
     FrameDev d;
     d.scene = f->ctx->scene;
-    d.view = f->dView; d.iview = f->dIView; d.objects = f->dObjects; d.derived = f->dDerived;
+    d.view = f->dView; d.iview = f->dIView; d.objects = f->dObjects; d.derived = f->dDerived; d.resolved = f->dResolved;
     d.objectCount = f->objectCount;
     d.width = f->width; d.height = f->height; d.tile = f->tile;
     d.switchFlags = f->ctx->switchFlags;
@@ -474,6 +474,7 @@ int chord_frame_create(chord_ctx* ctx, uint32_t width, uint32_t height, chord_fr
     const int rc = [&]() -> int {
         CHORD_CUDA(cudaMalloc(&f->vis64, sizeof(unsigned long long) * (size_t)width * height));
         CHORD_CUDA(cudaMalloc(&f->totalGroups, 16));
+        CHORD_CUDA(cudaMemsetAsync(f->totalGroups, 0, 16, ctx->stream));      // word 0: total groups; word 2: block counter of k_object_cull_scan
         CHORD_CUDA(cudaMalloc(&f->bvhCtrl, 32));
         CHORD_CUDA(cudaMemsetAsync(f->bvhCtrl, 0, 32, ctx->stream));
         f->largeTriCapacity = kLargeTriCapacity; f->largeItemCapacity = kLargeItemCapacity;
@@ -500,7 +501,7 @@ void chord_frame_destroy(chord_frame* f)
 {
     if (!f) return;
     cudaStreamSynchronize(f->ctx->stream);
-    cudaFree(f->vis64); cudaFree(f->dInputs); cudaFree(f->dDerived);
+    cudaFree(f->vis64); cudaFree(f->dInputs); cudaFree(f->dDerived); cudaFree(f->dResolved);
     for (int k = 0; k < 4; k++) { if (f->hInputs[k]) cudaFreeHost(f->hInputs[k]); if (f->inputsCopied[k]) cudaEventDestroy(f->inputsCopied[k]); }
     cudaFree(f->objGroupCount); cudaFree(f->objGroupBase); cudaFree(f->totalGroups);
     cudaFree(f->bvhEntries); cudaFree(f->bvhBits); cudaFree(f->bvhCtrl);
@@ -548,9 +549,9 @@ int chord_frame_begin(chord_frame* f, const chord_PerframeCameraView* view, cons
     if (objectCount > f->objectCapacity) {
         CHORD_NO_RESIZE_IN_CAPTURE(ctx, "the frame's object buffers");
         CHORD_CUDA(cudaStreamSynchronize(ctx->stream));
-        cudaFree(f->dInputs); cudaFree(f->dDerived); cudaFree(f->objGroupCount); cudaFree(f->objGroupBase);
+        cudaFree(f->dInputs); cudaFree(f->dDerived); cudaFree(f->dResolved); cudaFree(f->objGroupCount); cudaFree(f->objGroupBase);
         for (int k = 0; k < 4; k++) { if (f->hInputs[k]) cudaFreeHost(f->hInputs[k]); f->hInputs[k] = nullptr; }
-        f->dInputs = nullptr; f->dDerived = nullptr; f->objGroupCount = nullptr; f->objGroupBase = nullptr; f->objectCapacity = 0;
+        f->dInputs = nullptr; f->dDerived = nullptr; f->dResolved = nullptr; f->objGroupCount = nullptr; f->objGroupBase = nullptr; f->objectCapacity = 0;
         uint32_t cap = objectCount + objectCount / 4 + 16;
         f->lightingViewOffset = kViewBytes + kIViewBytes; f->objectsOffset = kViewBytes + kIViewBytes + kLvBytes;
         f->inputsBytes = f->objectsOffset + sizeof(chord_GPUObjectGLTFPrimitive) * (size_t)cap;
@@ -564,6 +565,7 @@ int chord_frame_begin(chord_frame* f, const chord_PerframeCameraView* view, cons
         f->dLightingView = f->dInputs + f->lightingViewOffset;
         f->dObjects = (chord_GPUObjectGLTFPrimitive*)(f->dInputs + f->objectsOffset);
         CHORD_CUDA(cudaMalloc(&f->dDerived, sizeof(ObjectDerived) * (size_t)cap));
+        CHORD_CUDA(cudaMalloc(&f->dResolved, sizeof(ObjectResolved) * (size_t)cap));
         CHORD_CUDA(cudaMalloc(&f->objGroupCount, sizeof(uint32_t) * (size_t)(cap + 1)));
         CHORD_CUDA(cudaMalloc(&f->objGroupBase, sizeof(uint32_t) * (size_t)(cap + 1)));
         f->objectCapacity = cap;

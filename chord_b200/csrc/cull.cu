@@ -1,8 +1,9 @@
 // cull.cu — cluster culling for the visibility-buffer path (sm_100a).
 //
-//   k_object_prepare     per-object derived matrices (what every HLSL thread recomputes with mul())
-//   k_object_cull        K1  instance_culling.hlsl:47-131   object OBB vs frustum -> group count
-//   k_object_scan        exclusive scan of the group counts (canonical object order replaces the InterlockedAdd)
+//   k_object_prepare     per-object derived matrices (what every HLSL thread recomputes with mul()) + the object -> primitive ->
+//                        datas chain resolved once per object (ObjectResolved)
+//   k_object_cull_scan   K1  instance_culling.hlsl:47-131   object OBB vs frustum -> group count, and - last block done - the
+//                        exclusive scan of the counts (canonical object order replaces the InterlockedAdd)
 //   k_group_cull         K2  instance_culling.hlsl:133-208  LOD-DAG cut + cone/frustum per meshlet, ordered compaction
 //   k_hzb_cull<phase>    K3  hzb_mainview_culling.hlsl:35-213 two-phase HZB occlusion, ordered compaction x2
 //
@@ -130,7 +131,7 @@ __device__ bool is_meshlet_visible(uint32_t switchFlags, const chord_float4* __r
 }
 
 // ------------------------------------------------------------------------------------------------ per-object prepare
-__global__ void __launch_bounds__(96) k_object_prepare(FrameDev f, ObjectDerived* __restrict__ out)
+__global__ void __launch_bounds__(96) k_object_prepare(FrameDev f, ObjectDerived* __restrict__ out, ObjectResolved* __restrict__ res)
 {
     // one object per block, 96 threads = 6 matrices x 16 elements
     const uint32_t o = blockIdx.x;
@@ -146,57 +147,76 @@ __global__ void __launch_bounds__(96) k_object_prepare(FrameDev f, ObjectDerived
     default: A = f.view->translatedWorldToClip.m;           B = obj.basicData.localToTranslatedWorld.m;          dst = out[o].localToClipHzb1.m; break;
     }
     dst[c * 4 + r] = dot4f(A[r], A[4 + r], A[8 + r], A[12 + r], B[c * 4], B[c * 4 + 1], B[c * 4 + 2], B[c * 4 + 3]);
+    if (threadIdx.x == 95u) {
+        // object -> primitive -> datas, followed once per object instead of once per cull thread
+        const chord_GLTFPrimitiveBuffer& prim = f.scene.prims[obj.GLTFPrimitiveDetail];
+        const DatasDev& datas = f.scene.datas[prim.primitiveDatasBufferId];
+        ObjectResolved rr;
+        rr.meshlets = datas.meshlets;
+        rr.groups = datas.groups + prim.meshletGroupOffset;
+        rr.groupIndices = datas.groupIndices + prim.meshletGroupIndicesOffset;
+        rr.meshletOffset = prim.meshletOffset;
+        rr.twoSided = f.scene.mats[obj.GLTFMaterialData].bTwoSided;
+        rr.groupCount = prim.meshletGroupCount;
+        rr.pad = 0u;
+        res[o] = rr;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ K1
-__global__ void __launch_bounds__(128) k_object_cull(FrameDev f, uint32_t* __restrict__ groupCount)
+// instanceCullingCS (instance_culling.hlsl:47-131): per-object frustum test -> number of cluster groups the object contributes,
+// and - in the same launch - the exclusive scan of those counts (the reference's InterlockedAdd slot allocation made ordered):
+// the block that finishes last scans all counts ("last block done"; one block when there are <= 128 objects).
+__global__ void __launch_bounds__(128) k_object_cull_scan(FrameDev f, uint32_t* __restrict__ groupCount, uint32_t* __restrict__ groupBase,
+                                                           uint32_t* __restrict__ total, uint32_t* __restrict__ blocksDone)
 {
     const uint32_t o = blockIdx.x * blockDim.x + threadIdx.x;
-    if (o >= f.objectCount) return;
-    const chord_GPUObjectGLTFPrimitive& obj = f.objects[o];
-    const chord_GLTFPrimitiveBuffer& prim = f.scene.prims[obj.GLTFPrimitiveDetail];
-    bool visible = true;
-    if (has_flag(f.switchFlags, CHORD_FLAG_FRUSTUM_CULL_BIT)) {
-        f3 c, e;
-        c.x = __fmul_rn(__fadd_rn(prim.posMin.x, prim.posMax.x), 0.5f); c.y = __fmul_rn(__fadd_rn(prim.posMin.y, prim.posMax.y), 0.5f); c.z = __fmul_rn(__fadd_rn(prim.posMin.z, prim.posMax.z), 0.5f);
-        e.x = __fsub_rn(prim.posMax.x, c.x); e.y = __fsub_rn(prim.posMax.y, c.y); e.z = __fsub_rn(prim.posMax.z, c.z);
-        const float* l2c = f.derived[o].localToClip.m;
-        if (l2c[15] == 1.0f) visible = !ortho_frustum_culling(c, e, l2c);
-        else                 visible = !frustum_culling(f.iview->frustumPlanesRS, c, e, obj.basicData.localToTranslatedWorld.m);
+    if (o < f.objectCount) {
+        const chord_GPUObjectGLTFPrimitive& obj = f.objects[o];
+        const chord_GLTFPrimitiveBuffer& prim = f.scene.prims[obj.GLTFPrimitiveDetail];
+        bool visible = true;
+        if (has_flag(f.switchFlags, CHORD_FLAG_FRUSTUM_CULL_BIT)) {
+            f3 c, e;
+            c.x = __fmul_rn(__fadd_rn(prim.posMin.x, prim.posMax.x), 0.5f); c.y = __fmul_rn(__fadd_rn(prim.posMin.y, prim.posMax.y), 0.5f); c.z = __fmul_rn(__fadd_rn(prim.posMin.z, prim.posMax.z), 0.5f);
+            e.x = __fsub_rn(prim.posMax.x, c.x); e.y = __fsub_rn(prim.posMax.y, c.y); e.z = __fsub_rn(prim.posMax.z, c.z);
+            const float* l2c = f.derived[o].localToClip.m;
+            if (l2c[15] == 1.0f) visible = !ortho_frustum_culling(c, e, l2c);
+            else                 visible = !frustum_culling(f.iview->frustumPlanesRS, c, e, obj.basicData.localToTranslatedWorld.m);
+        }
+        groupCount[o] = visible ? prim.meshletGroupCount : 0u;
     }
-    groupCount[o] = visible ? prim.meshletGroupCount : 0u;
-}
-
-// single block exclusive scan (object counts are small: hundreds to a few hundred thousand)
-__global__ void __launch_bounds__(1024) k_object_scan(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, uint32_t n, uint32_t* __restrict__ total)
-{
-    __shared__ uint32_t warpSums[32];
+    // ---- last block done
+    __shared__ uint32_t sLast;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) sLast = (atomicAdd(blocksDone, 1u) + 1u == gridDim.x) ? 1u : 0u;
+    __syncthreads();
+    if (!sLast) return;
+    if (threadIdx.x == 0) *blocksDone = 0u;                                  // re-armed for the next launch (stream-ordered)
+    __threadfence();
+    // single block exclusive scan of the counts written by all blocks (read past L1: other SMs wrote them)
+    __shared__ uint32_t warpSums[4];
     __shared__ uint32_t carry;
     if (threadIdx.x == 0) carry = 0;
     __syncthreads();
-    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    for (uint32_t base = 0; base < n; base += 1024) {
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, n = f.objectCount;
+    for (uint32_t base = 0; base < n; base += 128) {
         const uint32_t i = base + threadIdx.x;
-        uint32_t v = (i < n) ? in[i] : 0u;
+        const uint32_t v = (i < n) ? __ldcg(groupCount + i) : 0u;
         uint32_t s = v;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, s, o); if (lane >= (uint32_t)o) s += t; }
+        for (int k = 1; k < 32; k <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, s, k); if (lane >= (uint32_t)k) s += t; }
         if (lane == 31) warpSums[warp] = s;
         __syncthreads();
-        if (warp == 0) {
-            uint32_t w = warpSums[lane];
+        uint32_t warpBase = 0, blockTotal = 0;
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, w, o); if (lane >= (uint32_t)o) w += t; }
-            warpSums[lane] = w;
-        }
+        for (int w = 0; w < 4; w++) { const uint32_t t = warpSums[w]; if (w < (int)warp) warpBase += t; blockTotal += t; }
+        if (i < n) groupBase[i] = carry + warpBase + s - v;
         __syncthreads();
-        const uint32_t warpBase = warp ? warpSums[warp - 1] : 0u;
-        if (i < n) out[i] = carry + warpBase + s - v;
-        __syncthreads();
-        if (threadIdx.x == 1023) carry += warpBase + s;
+        if (threadIdx.x == 0) carry += blockTotal;
         __syncthreads();
     }
-    if (threadIdx.x == 0) { *total = carry; out[n] = carry; }
+    if (threadIdx.x == 0) { *total = carry; groupBase[n] = carry; }
 }
 
 // ------------------------------------------------------------------------------------------------ K2
@@ -232,16 +252,14 @@ __global__ void __launch_bounds__(kCullBlock) k_group_cull(FrameDev f, const uin
             objectId = lo;
             const uint32_t groupId = t - objGroupBase[lo];
             const chord_GPUObjectGLTFPrimitive& obj = f.objects[objectId];
-            const chord_GLTFPrimitiveBuffer& prim = f.scene.prims[obj.GLTFPrimitiveDetail];
-            const chord_GLTFMaterialGPUData& mat = f.scene.mats[obj.GLTFMaterialData];
-            const DatasDev& datas = f.scene.datas[prim.primitiveDatasBufferId];
-            const chord_GPUGLTFMeshletGroup g = datas.groups[prim.meshletGroupOffset + groupId];
+            const ObjectResolved res = f.resolved[objectId];                     // object -> primitive -> datas, resolved by k_object_prepare
+            const chord_GPUGLTFMeshletGroup g = res.groups[groupId];
             const ObjectDerived& der = f.derived[objectId];
             if (is_meshlet_group_visible(f.view->renderDimension.y, f.tanHalfFovy, obj.basicData.scaleExtractFromMatrix.w, der.localToView.m, g)) {
                 for (uint32_t i = 0; i < g.meshletCount && i < CHORD_CLUSTER_GROUP_MERGE_MAX; i++) {
-                    const uint32_t meshletIndex = prim.meshletOffset + datas.groupIndices[i + g.meshletOffset + prim.meshletGroupIndicesOffset];
-                    const chord_GPUGLTFMeshlet m = datas.meshlets[meshletIndex];
-                    if (is_meshlet_visible(f.switchFlags, f.iview->frustumPlanesRS, obj, der.localToClip.m, m, mat.bTwoSided))
+                    const uint32_t meshletIndex = res.meshletOffset + res.groupIndices[i + g.meshletOffset];
+                    const chord_GPUGLTFMeshlet m = res.meshlets[meshletIndex];
+                    if (is_meshlet_visible(f.switchFlags, f.iview->frustumPlanesRS, obj, der.localToClip.m, m, res.twoSided))
                         visId[visCount++] = meshletIndex;
                 }
             }
@@ -304,10 +322,7 @@ __global__ void __launch_bounds__(kCullBlock) k_hzb_cull(FrameDev f, HzbDev hzb,
         if (active) {
             cmd = inCmds[t];
             if (has_flag(f.switchFlags, CHORD_FLAG_HZB_CULL_BIT)) {
-                const chord_GPUObjectGLTFPrimitive& obj = f.objects[cmd.objectId];
-                const chord_GLTFPrimitiveBuffer& prim = f.scene.prims[obj.GLTFPrimitiveDetail];
-                const DatasDev& datas = f.scene.datas[prim.primitiveDatasBufferId];
-                const chord_GPUGLTFMeshlet m = datas.meshlets[cmd.meshletId];
+                const chord_GPUGLTFMeshlet m = f.resolved[cmd.objectId].meshlets[cmd.meshletId];      // (object -> primitive -> datas resolved by k_object_prepare)
                 f3 c, e; meshlet_center_extent(m, false, c, e);
                 const float* mvp = kFirstStage ? f.derived[cmd.objectId].localToClipHzb0.m : f.derived[cmd.objectId].localToClipHzb1.m;
                 float mn0 = 10.0f, mn1 = 10.0f, mn2 = 10.0f, mx0 = -10.0f, mx1 = -10.0f, mx2 = -10.0f;
@@ -433,11 +448,9 @@ __global__ void __launch_bounds__(kCullBlock) k_hzb_cull_generic(FrameDev f, Hzb
         if (active) {
             cmd = inCmds[t];
             if (has_flag(f.switchFlags, CHORD_FLAG_HZB_CULL_BIT)) {
-                const chord_GPUObjectGLTFPrimitive& obj = f.objects[cmd.objectId];
-                const chord_GLTFPrimitiveBuffer& prim = f.scene.prims[obj.GLTFPrimitiveDetail];
-                const DatasDev& datas = f.scene.datas[prim.primitiveDatasBufferId];
-                const chord_GPUGLTFMeshlet m = datas.meshlets[cmd.meshletId];
+                const chord_GPUGLTFMeshlet m = f.resolved[cmd.objectId].meshlets[cmd.meshletId];      // (object -> primitive -> datas resolved by k_object_prepare)
                 f3 c, e; meshlet_center_extent(m, false, c, e);
+                const chord_GPUObjectGLTFPrimitive& obj = f.objects[cmd.objectId];
                 float l2w[16], mvp[16];
                 const float* src = prm.useLastFrame ? obj.basicData.localToTranslatedWorldLastFrame.m : obj.basicData.localToTranslatedWorld.m;
 #pragma unroll
@@ -600,7 +613,7 @@ int launch_object_prepare(chord_frame* fr)
 {
     chord_ctx* ctx = fr->ctx;
     FrameDev f = make_frame_dev(fr);
-    k_object_prepare<<<fr->objectCount, 96, 0, ctx->stream>>>(f, fr->dDerived);
+    k_object_prepare<<<fr->objectCount, 96, 0, ctx->stream>>>(f, fr->dDerived, fr->dResolved);
     ctx->launches++;
     CHORD_CUDA(cudaGetLastError());
     return CHORD_OK;
@@ -617,8 +630,7 @@ static int launch_instance_culling_impl(chord_frame* fr, chord_cmdlist* out, boo
     const uint32_t tiles = (fr->meshletGroupCount + kCullBlock - 1) / kCullBlock + 1;
     int rc = scan_reset(ctx, tiles);
     if (rc) return rc;
-    k_object_cull<<<(fr->objectCount + 127) / 128, 128, 0, ctx->stream>>>(f, fr->objGroupCount);
-    k_object_scan<<<1, 1024, 0, ctx->stream>>>(fr->objGroupCount, fr->objGroupBase, fr->objectCount, fr->totalGroups);
+    k_object_cull_scan<<<(fr->objectCount + 127) / 128, 128, 0, ctx->stream>>>(f, fr->objGroupCount, fr->objGroupBase, fr->totalGroups, fr->totalGroups + 2);
     const uint32_t* bits = nullptr;
     if (useBvh) {
         for (uint32_t i = 0; i < ctx->scene.nDatas; i++) CHORD_REQUIRE(ctx->datasHost[i].bvhNodes != nullptr, "scene was uploaded without BVH nodes");
@@ -643,7 +655,7 @@ static int launch_instance_culling_impl(chord_frame* fr, chord_cmdlist* out, boo
     uint32_t grid = tiles < (uint32_t)ctx->smCount * 8u ? tiles : (uint32_t)ctx->smCount * 8u;
     k_group_cull<<<grid, kCullBlock, 0, ctx->stream>>>(f, fr->objGroupBase, fr->totalGroups, ctx->scanStatus, ctx->scanTicket,
                                                        out->cmds, out->count, out->capacity, bits, fr->bvhCtrl);
-    ctx->launches += 3;
+    ctx->launches += 2;
     CHORD_CUDA(cudaGetLastError());
     return CHORD_OK;
 }
