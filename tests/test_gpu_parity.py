@@ -1150,6 +1150,26 @@ def test_native_renderer_camera_path(gpu_ctx):
         r.close()
 
 
+def test_many_objects_instance_culling(gpu_ctx):
+    """K1 with more objects than one block of k_object_cull_scan holds (> 128): the group counts of several blocks are scanned
+    by the block that finishes last; post-cull lists (flat and BVH) and the surface equal the oracle's over two frames."""
+    from cases import city_frames
+    w, h = 320, 192
+    scene, info, frames = city_frames(n_buildings=170, frames=2, w=w, h=h, lods=2)
+    assert len(frames[0]['objects']) > 128
+    gpu_ctx.upload_scene(scene)
+    for bvh in (False, True):
+        r = runtime.Renderer(gpu_ctx, w, h, bvh=bvh)
+        prev = None
+        for i, f in enumerate(frames):
+            r.render(f['view'], f['iview'], f['objects'], info['lod0MeshletCount'], info['meshletGroupCount'])
+            ref = oracle.run_frame(scene, f['view'], f['iview'], f['objects'], w, h, info['lod0MeshletCount'], prev)
+            _assert_lists_equal(r.post_cull.readback(), ref['post_cull'], f'{len(f["objects"])} objects, frame {i}, bvh {bvh}')
+            _assert_vis_equal(r.frame.vis64(), ref['vis64'], f'frame {i}')
+            prev = ref['hzb']
+        r.close()
+
+
 def test_native_renderer_graph_replay(gpu_ctx):
     """CHORD_RENDERER_GRAPH: from the third frame on the recorded sequence is REPLAYED with the frame's uniforms rewritten
     (chord_graph_update_frame_inputs): lists, packed surface, history HZB and all six resolve planes of every frame must be

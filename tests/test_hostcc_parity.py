@@ -100,6 +100,10 @@ def test_native_renderer_camera_path(host_ctx, cases):
     cases.test_native_renderer_camera_path(host_ctx)
 
 
+def test_many_objects_instance_culling(host_ctx, cases):
+    cases.test_many_objects_instance_culling(host_ctx)
+
+
 def test_native_renderer_async_resolve(host_ctx, cases):
     cases.test_native_renderer_async_resolve(host_ctx, False)
 
