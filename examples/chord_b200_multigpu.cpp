@@ -1,7 +1,7 @@
 // chord_b200_multigpu.cpp — native multi-rank host: one thread per rank (the ABI's "one host thread per GPU"), every rank one
-// screen tile of the frame through chord_b200::Renderer, history HZB exchanged by the FUSED path (each rank's final buildHZB
-// stores its tile part straight into every rank's chain; in one process the peers are plain device pointers, between processes
-// the same call takes CUDA IPC handles).  Ranks map onto the visible GPUs round-robin, so the same binary runs 2 / 4 / 8 ranks
+// screen tile of the frame through chord_b200::Renderer, history HZB exchanged by the FUSED path (behind each rank's final
+// buildHZB a put kernel stores its tile part straight into every rank's chain; in one process the peers are plain device
+// pointers, between processes the same call takes CUDA IPC handles).  Ranks map onto the visible GPUs round-robin, so the same binary runs 2 / 4 / 8 ranks
 // on an 8-GPU box and on a single GPU.
 //
 //   g++ -std=c++17 -pthread -Iinclude examples/chord_b200_multigpu.cpp -Lchord_b200 -l:libchord_b200.so -Wl,-rpath,$PWD/chord_b200 -o multigpu
