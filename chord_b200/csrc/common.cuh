@@ -327,7 +327,7 @@ int launch_hzb_culling_generic(chord_frame* f, const chord_hzb* hzb, const chord
 int launch_build_hzb(chord_frame* f, int bMin, int bMax, int bRange, chord_hzb* dst, const HzbExchange* exchange = nullptr, bool deferPut = false);
 int launch_hzb_exchange_put(chord_frame* f, int bRange, chord_hzb* dst, const HzbExchange* exchange, uint32_t seq);   // seq 0: the kernel advances the sequence number itself
 int launch_hzb_range_reduce(chord_ctx* ctx, const uint32_t* pairs, uint32_t world, uint32_t* validRange);
-int launch_hzb_exchange_wait_top(chord_frame* f, chord_hzb* dst, const HzbExchange* exchange, uint32_t world, uint32_t* status);
+int launch_hzb_exchange_wait_top(chord_frame* f, chord_hzb* dst, const HzbExchange* exchange, uint32_t world, uint32_t* status, uint32_t maxPolls);
 int launch_visibility_mark(chord_frame* f, chord_cmdlist* post);
 enum { CHORD_LIGHTING_PREPARE = 1u, CHORD_LIGHTING_SHADE = 2u };
 int launch_lighting(chord_frame* f, chord_cmdlist* post, uint32_t parts = CHORD_LIGHTING_PREPARE | CHORD_LIGHTING_SHADE);

@@ -458,12 +458,13 @@ int launch_hzb_range_reduce(chord_ctx* ctx, const uint32_t* pairs, uint32_t worl
     return CHORD_OK;
 }
 
-int launch_hzb_exchange_wait_top(chord_frame* fr, chord_hzb* dst, const HzbExchange* ex, uint32_t world, uint32_t* status)
+int launch_hzb_exchange_wait_top(chord_frame* fr, chord_hzb* dst, const HzbExchange* ex, uint32_t world, uint32_t* status, uint32_t maxPolls)
 {
     HzbBuildParams p = make_params(fr, 1, 1, 1, dst);
     p.rank = ex->rank; p.parity = ex->parity; p.localHeader = ex->localHeader;
-    // ~4 s at 200 ns per poll before the wait gives up (a peer that died must not hang this GPU)
-    k_hzb_exchange_wait_top<<<1, 256, 0, fr->ctx->stream>>>(p, world, status, 20u * 1000u * 1000u);
+    // 200 ns per poll; the default 20 M polls = ~4 s before the wait gives up (a peer that died must not hang this GPU;
+    // chord_renderer_set_exchange_timeout)
+    k_hzb_exchange_wait_top<<<1, 256, 0, fr->ctx->stream>>>(p, world, status, maxPolls ? maxPolls : 20u * 1000u * 1000u);
     fr->ctx->launches++;
     CHORD_CUDA(cudaGetLastError());
     return CHORD_OK;

@@ -101,7 +101,7 @@ struct chord_renderer {
     unsigned char* block; size_t blockBytes, chainBytes, headerBytes;
     ExchangePeers* dPeers;                                          // [2]: one table per history slot
     void* opened[CHORD_MAX_EXCHANGE_RANKS]; bool openedIpc[CHORD_MAX_EXCHANGE_RANKS];
-    uint32_t* dStatus;
+    uint32_t* dStatus; uint32_t exchangeMaxPolls;                  // 0 = default (~4 s)
     chord_nccl_comm* nccl; unsigned char* sendBuf; unsigned char* recvBuf; uint64_t slotBytes;
 };
 
@@ -172,7 +172,7 @@ static int record_geometry(chord_renderer* r, uint32_t p, const chord_PerframeCa
         const HzbExchange ex = make_exchange(r, p ^ 1u);
         cudaStream_t main = ctx->stream;
         ctx->stream = r->auxStream;
-        rc = launch_hzb_exchange_wait_top(f, last, &ex, r->world, r->dStatus);
+        rc = launch_hzb_exchange_wait_top(f, last, &ex, r->world, r->dStatus, r->exchangeMaxPolls);
         ctx->stream = main;
         if (rc) return rc;
         CHORD_CUDA(cudaEventRecord(r->auxJoin, r->auxStream));
@@ -182,7 +182,7 @@ static int record_geometry(chord_renderer* r, uint32_t p, const chord_PerframeCa
     if (last && r->mode == 1 && !forkWait) {
         // fused exchange, consumer side: all peers' parts of last frame's chain have landed; rebuild mips 6.. from them
         const HzbExchange ex = make_exchange(r, p ^ 1u);
-        if ((rc = launch_hzb_exchange_wait_top(f, last, &ex, r->world, r->dStatus))) return rc;
+        if ((rc = launch_hzb_exchange_wait_top(f, last, &ex, r->world, r->dStatus, r->exchangeMaxPolls))) return rc;
     }
     if ((rc = record_event(r, 0))) return rc;
     rc = (r->flags & CHORD_RENDERER_BVH) ? chord_instance_culling_bvh(f, r->post[p]) : chord_instance_culling(f, r->post[p]);
@@ -501,7 +501,16 @@ int chord_renderer_history_sync(chord_renderer* r)
     const uint32_t p = (r->frameIndex - 1u) & 1u;
     if (r->putPending[p]) CHORD_CUDA(cudaStreamWaitEvent(r->ctx->stream, r->putDone[p], 0));      // this rank's own put advances its sequence number
     const HzbExchange ex = make_exchange(r, p);
-    return launch_hzb_exchange_wait_top(r->frame, r->hist[p], &ex, r->world, r->dStatus);
+    return launch_hzb_exchange_wait_top(r->frame, r->hist[p], &ex, r->world, r->dStatus, r->exchangeMaxPolls);
+}
+
+int chord_renderer_set_exchange_timeout(chord_renderer* r, uint32_t maxPolls)
+{
+    // the bound is a kernel parameter of the consumer-side wait: recorded frames are dropped so that they pick the new value up
+    CHORD_REQUIRE(r, "null");
+    r->exchangeMaxPolls = maxPolls;
+    drop_graphs(r);
+    return CHORD_OK;
 }
 
 int chord_renderer_exchange_status(chord_renderer* r, uint32_t* outTimedOut)

@@ -32,7 +32,7 @@ SYMBOLS = [
     'chord_selftest_vertex_records',
     'chord_renderer_create', 'chord_renderer_destroy', 'chord_renderer_set_tile', 'chord_renderer_render', 'chord_renderer_clear_history',
     'chord_renderer_frame', 'chord_renderer_post_cull', 'chord_renderer_history_hzb', 'chord_renderer_graph_replays', 'chord_renderer_pass_times',
-    'chord_renderer_exchange_export', 'chord_renderer_exchange_connect', 'chord_renderer_history_sync', 'chord_renderer_exchange_status',
+    'chord_renderer_exchange_export', 'chord_renderer_exchange_connect', 'chord_renderer_history_sync', 'chord_renderer_exchange_status', 'chord_renderer_set_exchange_timeout',
     'chord_nccl_unique_id', 'chord_nccl_comm_create', 'chord_nccl_comm_destroy', 'chord_hzb_allgather', 'chord_renderer_exchange_connect_nccl',
     'chord_graph_begin_capture', 'chord_graph_end_capture', 'chord_graph_launch', 'chord_graph_kernel_nodes', 'chord_graph_destroy', 'chord_graph_update_frame_inputs',
 ]
@@ -680,6 +680,10 @@ class Renderer:
 
     def history_sync(self):
         lib().chord_renderer_history_sync(self.h)
+
+    def set_exchange_timeout(self, max_polls):
+        """Bound of the wait for the peers' arrival flags: max_polls x 200 ns (0 = default, ~4 s)."""
+        lib().chord_renderer_set_exchange_timeout(self.h, C.c_uint32(int(max_polls)))
 
     def exchange_timed_out(self):
         v = C.c_uint32()

@@ -384,6 +384,10 @@ int  chord_renderer_exchange_connect(chord_renderer* renderer, uint32_t rank, ui
                                      const chord_ipc_handle* handles /* [world] or NULL */, void* const* localPtrs /* [world] or NULL */);
 int  chord_renderer_history_sync(chord_renderer* renderer);
 int  chord_renderer_exchange_status(chord_renderer* renderer, uint32_t* outTimedOut);
+/* Failure detection of the fused exchange: how long a rank waits for its peers' arrival flags before it gives up, raises the
+ * status word above and renders on with the history it has (a peer that died must not hang the others).  maxPolls x 200 ns;
+ * 0 = the default, 20 000 000 polls = ~4 s. */
+int  chord_renderer_set_exchange_timeout(chord_renderer* renderer, uint32_t maxPolls);
 typedef struct chord_nccl_comm chord_nccl_comm;
 int  chord_nccl_unique_id(unsigned char outId[128]);                 /* rank 0; distribute the 128 bytes to every rank */
 int  chord_nccl_comm_create(chord_ctx* ctx, uint32_t world, uint32_t rank, const unsigned char id[128], chord_nccl_comm** out);

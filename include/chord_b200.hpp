@@ -191,6 +191,7 @@ public:
     void exchangeConnect(uint32_t rank, uint32_t world, const chord_rect* tiles, const chord_ipc_handle* handles, void* const* localPtrs)
     { check(chord_renderer_exchange_connect(m_r, rank, world, tiles, handles, localPtrs), "chord_renderer_exchange_connect"); }
     void historySync() { check(chord_renderer_history_sync(m_r), "chord_renderer_history_sync"); }
+    void setExchangeTimeout(uint32_t maxPolls) { check(chord_renderer_set_exchange_timeout(m_r, maxPolls), "chord_renderer_set_exchange_timeout"); }
     bool exchangeTimedOut() const { uint32_t v = 0; check(chord_renderer_exchange_status(m_r, &v), "chord_renderer_exchange_status"); return v != 0; }
 private:
     chord_renderer* m_r = nullptr;

@@ -1318,6 +1318,45 @@ def test_renderer_fused_exchange_in_process(gpu_ctx, world=2, use_graph=False, a
         c.close()
 
 
+def test_exchange_wait_gives_up_on_a_dead_peer(gpu_ctx):
+    """Failure detection of the fused exchange: a rank whose peer stops rendering must not hang - the consumer-side wait is
+    bounded (chord_renderer_set_exchange_timeout), raises the status word (chord_renderer_exchange_status) and the rank renders
+    on with the history it has.  Two ranks in one process; rank 1 "dies" after the first frame."""
+    w, h = 640, 384
+    scene, info, frames, tiles, multigpu = _tile_case(gpu_ctx, 2, w, h, 4)
+    make = type(gpu_ctx)
+    ctxs = [make(gpu_ctx.device) for _ in range(2)]
+    for c in ctxs:
+        c.upload_scene(scene)
+    ranks = [runtime.Renderer(c, w, h) for c in ctxs]
+    ptrs = [r.exchange_export()[1] for r in ranks]
+    for i, r in enumerate(ranks):
+        r.exchange_connect(i, 2, tiles, local_ptrs=ptrs)
+        r.set_exchange_timeout(20000)                   # 20 000 polls x 200 ns = 4 ms instead of the default 4 s
+    lod0, groups = info['lod0MeshletCount'], info['meshletGroupCount']
+
+    def render(i, fi):
+        f = frames[fi]
+        ranks[i].render(f['view'], multigpu.tile_instance_view(f['view'], f['camera'], tiles[i]), f['objects'], lod0, groups)
+    render(0, 0); render(1, 0)
+    render(0, 1)                                        # waits for rank 1's frame 0: it is there
+    ctxs[0].sync()
+    assert not ranks[0].exchange_timed_out()
+    render(0, 2)                                        # waits for rank 1's frame 1, which never comes
+    ctxs[0].sync()                                      # ... and returns
+    assert ranks[0].exchange_timed_out()
+    # the rank is still alive: its own tile of the next frame is rendered (occlusion culling against what history it has is
+    # conservative or not, the rasteriser resolves visibility either way)
+    render(0, 3)
+    x0, y0, x1, y1 = tiles[0]
+    vt = ranks[0].frame.vis64()
+    assert vt[y0:y1, x0:x1].any()
+    for r in ranks:
+        r.close()
+    for c in ctxs:
+        c.close()
+
+
 def test_renderer_fused_exchange_four_ranks_graph(gpu_ctx):
     test_renderer_fused_exchange_in_process(gpu_ctx, world=4, use_graph=True)
 

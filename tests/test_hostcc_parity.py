@@ -114,6 +114,10 @@ def test_renderer_fused_exchange_in_process(host_ctx, cases):
         cases.test_renderer_fused_exchange_in_process(host_ctx, world=4)
 
 
+def test_exchange_wait_gives_up_on_a_dead_peer(host_ctx, cases):
+    cases.test_exchange_wait_gives_up_on_a_dead_peer(host_ctx)
+
+
 def test_renderer_fused_exchange_async(host_ctx, cases):
     cases.test_renderer_fused_exchange_async(host_ctx, 2, False)
 
