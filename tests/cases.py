@@ -10,6 +10,17 @@ def digest(a):
     return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
 
 
+def gbuffer_digest(frame, vis64, post_cull):
+    """sha256 over the six fp32 G-buffer planes of the ORACLE's resolve (PBR branch + sky branch over the colour plane) with the
+    seeded LUTs of chord_b200/synth.py - the golden fixtures' K11 entry."""
+    import oracle
+    tr, ir = synth.synthetic_luts()
+    sc, _ = synth.synthetic_scattering_luts()
+    g = oracle.lighting(frame, vis64, post_cull, tr, ir)
+    oracle.sky(frame, vis64, tr, ir, sc, None, color=g[0])
+    return hashlib.sha256(b''.join(np.ascontiguousarray(p).tobytes() for p in g)).hexdigest()
+
+
 def case_s1():
     scene, camera, objects = synth.single_meshlet_scene()
     view = cam.fill_view(camera)

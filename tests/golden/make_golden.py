@@ -16,7 +16,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 sys.path.insert(0, os.path.dirname(HERE))
 
 import oracle  # noqa: E402
-from cases import case_masked, case_ragged, case_s1, case_stream, city_frames, digest  # noqa: E402
+from cases import case_masked, case_ragged, case_s1, case_stream, city_frames, digest, gbuffer_digest  # noqa: E402
 
 
 def entry_static(c, flags=0b111, prebuilt=False):
@@ -25,7 +25,10 @@ def entry_static(c, flags=0b111, prebuilt=False):
     cmds = c['cmds'] if prebuilt else post
     vis, stats = fr.render_mesh(cmds)
     hz = fr.build_hzb(vis, True, True, True)
-    return dict(post=digest(post), post_count=len(post), vis64=digest(vis), covered=int((vis != 0).sum()),
+    extra = {}
+    if c.get('name') == 's1' and flags == 0b111:
+        extra['gbuffer'] = gbuffer_digest(fr, vis, post)              # K11: PBR + sky, six fp32 planes
+    return dict(extra, post=digest(post), post_count=len(post), vis64=digest(vis), covered=int((vis != 0).sum()),
                 hzb_min=digest(hz['min']), hzb_max=digest(hz['max']), valid_range=[int(x) for x in hz['range']],
                 marker=digest(fr.visibility_mark(vis, post)) if not prebuilt else None,
                 culled=stats['trianglesCulled'], clipped=stats['trianglesClipped'], submitted=stats['trianglesSubmitted'],
@@ -48,6 +51,8 @@ def main():
             e = dict(post=digest(ref['post_cull']), post_count=len(ref['post_cull']), vis64=digest(ref['vis64']),
                      covered=int((ref['vis64'] != 0).sum()), hzb_min=digest(ref['hzb']['min']), hzb_max=digest(ref['hzb']['max']),
                      valid_range=[int(x) for x in ref['hzb']['range']])
+            if not low and fi < 2:
+                e['gbuffer'] = gbuffer_digest(ref['frame'], ref['vis64'], ref['post_cull'])
             if 'stage0_visible' in ref:
                 e.update(stage0_visible=len(ref['stage0_visible']), stage0_rejected=len(ref['stage0_rejected']),
                          stage1_visible=len(ref['stage1_visible']))
